@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""bench.py -- guides/s of the off-target enumeration hot path (BASELINE.json metric) on N B200s of one node.
+
+A step = one pass of the hot path (search both strand indexes + locate + coordinates + CFD + specificity) over one
+batch of synthetic guides per GPU.  One process per GPU (torchrun), index replicated, guides sharded, no data-path
+collective ("scaling": "weak": the per-GPU batch is fixed).  Timing: CUDA events inside the library for the
+device-resident number (`value`), wall clock bracketed by barrier + synchronize for the end-to-end number through the
+C ABI with host buffers (`e2e`), max over ranks.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl gsx|reference] [--genome-mb MB] [--guides-per-step G]
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "guidescan-cli_b200"))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+METRIC = "guides/sec at k=3 mismatches"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json hbm_gbs, streaming copy)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def random_gather_peak():
+    p = os.path.join(ROOT, "profiles", "random_gather_peak.json")
+    if os.path.exists(p):
+        return json.load(open(p))
+    return None
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, gpu_index=0):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.samples = []
+        self.stop_flag = False
+        self.proc = None
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag:
+                    break
+                self.samples.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(float(s[0])); mx = max(mx, float(s[1]))
+                for n, v in zip(names, s[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def dist_setup(n_gpus):
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_mod
+        torch.cuda.set_device(local)
+        dist_mod.init_process_group(backend="nccl" if torch.cuda.is_available() else "gloo")
+        dist = dist_mod
+    return rank, world, local, dist
+
+
+def barrier_sync(dist, local):
+    import torch
+    if torch.cuda.is_available():
+        torch.cuda.synchronize(local)
+    if dist is not None:
+        dist.barrier()
+
+
+def reduce_max(dist, local, x):
+    if dist is None:
+        return x
+    import torch
+    t = torch.tensor([x], dtype=torch.float64, device=("cuda:%d" % local) if torch.cuda.is_available() else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def reduce_sum(dist, local, x):
+    if dist is None:
+        return x
+    import torch
+    t = torch.tensor([x], dtype=torch.float64, device=("cuda:%d" % local) if torch.cuda.is_available() else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+def shard_guides(n_total, rank, world):
+    """Contiguous shard of the guide list for `rank` (the multi-GPU partition; no collective on the data path)."""
+    return n_total * rank // world, n_total * (rank + 1) // world
+
+
+def make_workload(args, world):
+    import synth
+    G = int(args.genome_mb * 1e6)
+    t0 = time.time()
+    g = synth.make_genome(G, args.seed)
+    n_total = args.guides_per_step * world * (args.steps + args.warmup)
+    pos, kmers = synth.sample_guides(g, n_total, args.seed)
+    n_plant = min(n_total, args.plant_guides)
+    synth.plant(g, kmers[:n_plant], args.seed)
+    chroms = synth.chromosome_table(G, args.n_chr)
+    log("workload: genome %.1f Mb, %d guides total (%d with planted copies) in %.1f s" % (G / 1e6, n_total, n_plant, time.time() - t0))
+    return g, chroms, pos, kmers
+
+
+def build_index(gsx, g, chroms, local, args, workdir):
+    t0 = time.time()
+    try:
+        ix = gsx.Index.build_from_text(g, chroms, sa_shift=args.sa_shift, devices=[local])
+        how = "gpu-built"
+    except gsx.GsxError as e:
+        if "not implemented" not in str(e):
+            raise
+        import oracle as O
+        import synth
+        fa = os.path.join(workdir, "bench.fa")
+        if int(os.environ.get("RANK", 0)) == 0 or not os.path.exists(fa):
+            synth.write_fasta(fa, g, chroms)
+            O.ref_index(fa, os.path.join(workdir, "bench"), cwd=workdir)
+        ix = gsx.Index.open(os.path.join(workdir, "bench"), devices=[local])
+        how = "reference-built (guidescan index), converted"
+    log("index: %s in %.1f s, %.2f GB on device" % (how, time.time() - t0, ix.device_bytes / 1e9))
+    return ix, how
+
+
+def run_gsx(args):
+    import gsx
+    rank, world, local, dist = dist_setup(args.gpus)
+    workdir = args.workdir
+    os.makedirs(workdir, exist_ok=True)
+    g, chroms, pos, kmers = make_workload(args, world)
+    ix, how = build_index(gsx, g, chroms, local, args, workdir)
+    params = gsx.make_params(mismatches=args.mismatches)
+    per = args.guides_per_step
+    # host buffers of every step's guides for this rank (pinned memory is allocated inside the library for results)
+    steps = []
+    for s in range(args.steps + args.warmup):
+        lo = (s * world + rank) * per
+        seqs = [kmers[i, :20].tobytes() for i in range(lo, lo + per)]
+        arr = (gsx.Guide * per)()
+        for i, sq in enumerate(seqs):
+            arr[i] = gsx.Guide(sq, b"NGG")
+        steps.append((arr, seqs))
+    h2d_bytes = per * 80
+    for s in range(args.warmup):
+        ix.enumerate_raw(steps[s][0], per, params).close()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    barrier_sync(dist, local)
+    t0 = time.perf_counter()
+    dev_ms = search_ms = 0.0
+    ctr_tot = {}
+    d2h_bytes = 0
+    for s in range(args.warmup, args.warmup + args.steps):
+        r = ix.enumerate_raw(steps[s][0], per, params)
+        c = r.counters()
+        dev_ms += c["ms_total_device"]; search_ms += c["ms_search"]
+        for k, v in c.items():
+            ctr_tot[k] = ctr_tot.get(k, 0) + v
+        d2h_bytes = r.n_guides * (1 + 4 + 4 + 4 + 1 + 4 * (args.mismatches + 1)) + r.n_hits * (8 + 4 + 4 + 4 + 6 + 4 + 4) + c["matches"] * 32
+        spec_sum = float(r.guide_arrays()["specificity"].sum())       # the step's result is read on the host
+        r.close()
+    barrier_sync(dist, local)
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.finish() if sampler else None
+    e2e_s = reduce_max(dist, local, e2e_s)
+    dev_ms = reduce_max(dist, local, dev_ms)
+    search_ms_max = reduce_max(dist, local, search_ms)
+    lookups = reduce_sum(dist, local, ctr_tot["lookups"])
+    nodes = reduce_sum(dist, local, ctr_tot["nodes"])
+    hits = reduce_sum(dist, local, ctr_tot["hits"])
+    total_guides = per * world * args.steps
+    if rank == 0:
+        peak, peak_src = peaks()
+        alg_bytes_per_launch = ctr_tot["lookups"] * 32.0 / args.steps
+        launch_ms = search_ms / args.steps
+        achieved = alg_bytes_per_launch / (launch_ms * 1e-3) / 1e9
+        rg = random_gather_peak()
+        line = {
+            "metric": METRIC, "value": total_guides / (dev_ms * 1e-3), "unit": "guides/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": {"workload": "%.0f Mb uniform-random synthetic genome (seed %d, %d chr, planted 1-4 mismatch copies), "
+                                   "%d NGG 20-mer guides per GPU per step, mismatches=%d, both strand indexes, locate + CFD + specificity"
+                                   % (args.genome_mb, args.seed, args.n_chr, per, args.mismatches),
+                       "genome_mb": args.genome_mb, "guides_per_gpu_per_step": per, "mismatches": args.mismatches,
+                       "index": how, "sa_sample_rows": 1 << args.sa_shift, "parallelism": "guides sharded x%d, index replicated" % world,
+                       "l2": "index (%.2f GB) is far larger than L2; every step uses new guides" % (ix.device_bytes / 1e9)},
+            "e2e": {"value": total_guides / e2e_s, "unit": "guides/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": int(d2h_bytes),
+                    "ms_per_step": e2e_s * 1e3 / args.steps},
+            "gpu_launches": int(args.steps * 9),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "kernel": "search_kernel", "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes_per_launch, "lookups_per_guide": lookups / total_guides,
+                         "nodes_per_guide": nodes / total_guides, "launch_ms": launch_ms,
+                         "random_sector_peak_gbs": rg["gb_per_s"] if rg else None,
+                         "frac_of_random_sector_peak": (achieved / rg["gb_per_s"]) if rg else None},
+            "counters": {"hits_per_guide": hits / total_guides, "spills": ctr_tot["spills"], "lf_steps": ctr_tot["lf_steps"],
+                         "ms_search": ctr_tot["ms_search"] / args.steps, "ms_arrange": ctr_tot["ms_arrange"] / args.steps,
+                         "ms_locate": ctr_tot["ms_locate"] / args.steps, "ms_score": ctr_tot["ms_score"] / args.steps,
+                         "ms_d2h": ctr_tot["ms_d2h"] / args.steps},
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args, g, chroms, kmers, workdir)
+        print(json.dumps(line), flush=True)
+    ix.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(args, g, chroms, kmers, workdir, steps=1, sample=None):
+    """The reference's own CPU implementation (oracle/_ref/guidescan, unmodified) on a bounded sample of the workload."""
+    import oracle as O
+    import synth
+    cores = os.cpu_count() or 1
+    fa = os.path.join(workdir, "bench.fa")
+    prefix = os.path.join(workdir, "bench")
+    if not O.have_ref():
+        return {"value": None, "unit": "guides/s", "cores": cores, "kind": "reference", "sample": "oracle/_ref/guidescan missing"}
+    if not os.path.exists(prefix + ".forward"):
+        t0 = time.time()
+        synth.write_fasta(fa, g, chroms)
+        O.ref_index(fa, prefix, cwd=workdir)
+        log("cpu_baseline: reference index built in %.1f s" % (time.time() - t0))
+    n = sample or args.cpu_sample
+    gcsv = os.path.join(workdir, "cpu_sample.csv")
+    with open(gcsv, "w") as f:
+        f.write("id,sequence,pam,chromosome,position,sense\n")
+        for i in range(n):
+            f.write("g%d,%s,NGG,chr1,1,+\n" % (i, kmers[i, :20].tobytes().decode()))
+    best = None
+    for _ in range(steps):
+        t0 = time.time()
+        O.ref_enumerate(prefix, gcsv, os.path.join(workdir, "cpu.out"), mismatches=args.mismatches, threads=cores)
+        dt = time.time() - t0
+        best = dt if best is None else min(best, dt)
+    return {"value": n / best, "unit": "guides/s", "cores": cores, "kind": "reference",
+            "sample": "first %d guides of the workload, guidescan enumerate -n %d, wall clock incl. index load (%.1f s)" % (n, cores, best)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    import synth
+    os.makedirs(args.workdir, exist_ok=True)
+    g, chroms, pos, kmers = make_workload(args, 1)
+    cb = cpu_baseline(args, g, chroms, kmers, args.workdir, steps=max(1, args.steps), sample=args.cpu_sample)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "guides/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": "%.0f Mb uniform-random synthetic genome (seed %d), NGG 20-mer guides, mismatches=%d" % (args.genome_mb, args.seed, args.mismatches)},
+            "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "guides/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="gsx", choices=["gsx", "reference"])
+    ap.add_argument("--genome-mb", type=float, default=float(os.environ.get("GSX_BENCH_GENOME_MB", 120)))
+    ap.add_argument("--n-chr", type=int, default=8)
+    ap.add_argument("--guides-per-step", type=int, default=int(os.environ.get("GSX_BENCH_GUIDES", 20000)))
+    ap.add_argument("--plant-guides", type=int, default=2000)
+    ap.add_argument("--mismatches", type=int, default=3)
+    ap.add_argument("--seed", type=int, default=2)
+    ap.add_argument("--sa-shift", type=int, default=6)
+    ap.add_argument("--cpu-sample", type=int, default=2000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workdir", default=os.environ.get("GSX_BENCH_DIR", "/tmp/gsx_bench"))
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gsx(args)
+
+
+if __name__ == "__main__":
+    main()

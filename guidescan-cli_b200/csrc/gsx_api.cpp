@@ -1,0 +1,544 @@
+// gsx_api.cpp -- C ABI (include/gsx.h): index upload, batched enumerate on 1..N devices, result arenas.
+// Host orchestration only; all arithmetic of the path runs in the kernels of gsx_kernels.cu.  No CPU fallback.
+#include "../../include/gsx.h"
+#include "gsx_host.h"
+#include "gsx_core.h"
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <thread>
+#include <vector>
+
+using namespace gsx;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+struct CudaError : std::runtime_error { using std::runtime_error::runtime_error; };
+#define CK(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) throw CudaError(std::string(#call) + ": " + cudaGetErrorString(e__)); } while (0)
+
+extern "C" const char* gsx_last_error(void) { return g_err.c_str(); }
+extern "C" const char* gsx_version(void) { return "2.0.0"; }
+extern "C" void gsx_free(void* p) { free(p); }
+extern "C" int gsx_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
+
+extern "C" void gsx_params_default(gsx_params* p) {
+    memset(p, 0, sizeof *p);
+    p->mismatches = 3; p->max_bulge_size = 1; p->threshold = -1; p->max_off_targets = -1;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// index
+// ---------------------------------------------------------------------------------------------------------
+template <class T> static void* upload(const std::vector<T>& v, uint64_t& bytes) {
+    void* d = nullptr; size_t n = std::max<size_t>(v.size(), 1) * sizeof(T);
+    CK(cudaMalloc(&d, n));
+    if (!v.empty()) CK(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    bytes += n;
+    return d;
+}
+
+static void upload_index(gsx_index* ix, const int* devices, int n_devices) {
+    ix->chroms.clear();
+    uint64_t start = 0;
+    for (size_t i = 0; i < ix->host.chr_lens.size(); i++) { ix->chroms.push_back({start, ix->host.chr_lens[i]}); start += ix->host.chr_lens[i]; }
+    std::vector<int> devs;
+    if (!devices || n_devices <= 0) devs.push_back(0); else devs.assign(devices, devices + n_devices);
+    for (int dv : devs) {
+        DeviceIndex di; di.device = dv;
+        CK(cudaSetDevice(dv));
+        cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, dv));
+        di.sm_count = prop.multiProcessorCount;
+        CK(upload_cfd_tables());
+        for (int s = 0; s < 2; s++) {
+            const HostStrand& h = ix->host.st[s];
+            DeviceStrand& d = di.st[s];
+            d.blocks = upload(h.blocks, di.bytes); d.sa = upload(h.sa_samples, di.bytes);
+            d.exc_rows = upload(h.exc_rows, di.bytes); d.exc_lf = upload(h.exc_lf, di.bytes); d.n_rows = upload(h.n_rows, di.bytes);
+            d.d.blocks = (const OccBlock*)d.blocks; d.d.sa_samples = (const uint32_t*)d.sa;
+            d.d.exc_rows = (const uint32_t*)d.exc_rows; d.d.exc_lf = (const uint32_t*)d.exc_lf; d.d.n_rows = (const uint32_t*)d.n_rows;
+            d.d.n = (uint32_t)h.n; d.d.n_exc = (uint32_t)h.exc_rows.size(); d.d.n_nrows = (uint32_t)h.n_rows.size();
+            d.d.sa_shift = h.sa_shift;
+            for (int c = 0; c < 5; c++) d.d.C[c] = h.C[c];
+            d.d.exc_lo = h.exc_rows.empty() ? 0xFFFFFFFFu : h.exc_rows.front();
+            d.d.exc_hi = h.exc_rows.empty() ? 0u : h.exc_rows.back();
+        }
+        di.chroms = (Chrom*)upload(ix->chroms, di.bytes);
+        ix->dev.push_back(di);
+    }
+}
+
+static void free_device_index(DeviceIndex& di) {
+    cudaSetDevice(di.device);
+    for (int s = 0; s < 2; s++) { cudaFree(di.st[s].blocks); cudaFree(di.st[s].sa); cudaFree(di.st[s].exc_rows); cudaFree(di.st[s].exc_lf); cudaFree(di.st[s].n_rows); }
+    cudaFree(di.chroms);
+}
+
+static bool file_exists(const std::string& p) { FILE* f = fopen(p.c_str(), "rb"); if (!f) return false; fclose(f); return true; }
+
+static int check_devices(const int* devices, int n_devices) {
+    int have = gsx_device_count();
+    if (have <= 0) return fail(GSX_ERR_NO_DEVICE, "no CUDA device available (this library has no CPU path)");
+    for (int i = 0; devices && i < n_devices; i++)
+        if (devices[i] < 0 || devices[i] >= have) return fail(GSX_ERR_ARG, "device ordinal out of range");
+    return GSX_OK;
+}
+
+extern "C" int gsx_index_open(const char* prefix, const int* devices, int n_devices, gsx_index** out) {
+    if (!prefix || !out) return fail(GSX_ERR_ARG, "null argument");
+    *out = nullptr;
+    gsx_index* ix = new gsx_index();
+    std::string p(prefix), err;
+    bool ok;
+    if (file_exists(p + ".forward") || !file_exists(p + ".gsx")) {
+        ok = load_genome_structure(p + ".gs", ix->host, err);
+        if (ok && !file_exists(p + ".forward")) { ok = false; err = "No forward index file " + p + ".forward located."; }
+        if (ok && !file_exists(p + ".reverse")) { ok = false; err = "No forward index file " + p + ".reverse located."; }   // sic: src/guidescan.cxx:205
+        if (ok) {
+            std::string e0, e1; bool ok0 = false, ok1 = false;
+            std::thread t0([&] { ok0 = load_sdsl_strand(p + ".forward", ix->host.st[0], e0); });
+            std::thread t1([&] { ok1 = load_sdsl_strand(p + ".reverse", ix->host.st[1], e1); });
+            t0.join(); t1.join();
+            ok = ok0 && ok1; if (!ok) err = ok0 ? e1 : e0;
+        }
+    } else ok = load_gsx(p, ix->host, err);
+    if (!ok) { delete ix; return fail(GSX_ERR_IO, err); }
+    if (int rc = check_devices(devices, n_devices)) { delete ix; return rc; }
+    try { upload_index(ix, devices, n_devices); }
+    catch (const CudaError& e) { for (auto& d : ix->dev) free_device_index(d); delete ix; return fail(GSX_ERR_CUDA, e.what()); }
+    *out = ix;
+    return GSX_OK;
+}
+
+static int build_from_text(gsx_index* ix, std::vector<uint8_t>& seq, uint32_t sa_shift, const char* save_prefix,
+                           const int* devices, int n_devices, gsx_index** out) {
+    std::string err;
+    if (seq.size() + 1 > 0xFFFFFFFFull) { delete ix; return fail(GSX_ERR_ARG, "genome longer than 2^32 - 2 bases"); }
+    if (sa_shift > 12) { delete ix; return fail(GSX_ERR_ARG, "sa_shift must be <= 12"); }
+    int dev0 = (devices && n_devices > 0) ? devices[0] : 0;
+    if (!build_strand_gpu(dev0, seq.data(), seq.size(), sa_shift, ix->host.st[0], err)) { delete ix; return fail(GSX_ERR_CUDA, err); }
+    {   // reverse complement of the whole concatenated genome, in place (seq_io.cxx:65-72)
+        size_t n = seq.size();
+        for (size_t i = 0; i < n / 2; i++) { uint8_t a = seq[i], b = seq[n - 1 - i]; seq[i] = (uint8_t)complement_char((char)b); seq[n - 1 - i] = (uint8_t)complement_char((char)a); }
+        if (n & 1) seq[n / 2] = (uint8_t)complement_char((char)seq[n / 2]);
+    }
+    if (!build_strand_gpu(dev0, seq.data(), seq.size(), sa_shift, ix->host.st[1], err)) { delete ix; return fail(GSX_ERR_CUDA, err); }
+    if (save_prefix && !save_gsx(save_prefix, ix->host, err)) { delete ix; return fail(GSX_ERR_IO, err); }
+    try { upload_index(ix, devices, n_devices); }
+    catch (const CudaError& e) { for (auto& d : ix->dev) free_device_index(d); delete ix; return fail(GSX_ERR_CUDA, e.what()); }
+    *out = ix;
+    return GSX_OK;
+}
+
+extern "C" int gsx_index_build(const char* fasta_path, const char* save_prefix, const int* devices, int n_devices, gsx_index** out) {
+    if (!fasta_path || !out) return fail(GSX_ERR_ARG, "null argument");
+    *out = nullptr;
+    if (int rc = check_devices(devices, n_devices)) return rc;
+    gsx_index* ix = new gsx_index();
+    std::string err; std::vector<uint8_t> seq;
+    if (!read_fasta(fasta_path, seq, ix->host, err)) { delete ix; return fail(GSX_ERR_IO, err); }
+    return build_from_text(ix, seq, 6, save_prefix, devices, n_devices, out);
+}
+
+extern "C" int gsx_index_build_text(const uint8_t* text, uint64_t length, const char* const* chr_names, const uint64_t* chr_lengths,
+                                    uint32_t n_chr, uint32_t sa_shift, const char* save_prefix, const int* devices, int n_devices,
+                                    gsx_index** out) {
+    if (!text || !out || !chr_names || !chr_lengths) return fail(GSX_ERR_ARG, "null argument");
+    *out = nullptr;
+    if (int rc = check_devices(devices, n_devices)) return rc;
+    gsx_index* ix = new gsx_index();
+    uint64_t tot = 0;
+    for (uint32_t i = 0; i < n_chr; i++) { ix->host.chr_names.push_back(chr_names[i]); ix->host.chr_lens.push_back(chr_lengths[i]); tot += chr_lengths[i]; }
+    ix->host.genome_length = tot;
+    std::vector<uint8_t> seq(text, text + length);
+    return build_from_text(ix, seq, sa_shift, save_prefix, devices, n_devices, out);
+}
+
+extern "C" int gsx_index_close(gsx_index* ix) {
+    if (!ix) return GSX_OK;
+    for (auto& d : ix->dev) free_device_index(d);
+    delete ix;
+    return GSX_OK;
+}
+extern "C" uint64_t gsx_index_genome_length(const gsx_index* ix) { return ix->host.genome_length; }
+extern "C" uint32_t gsx_index_n_chromosomes(const gsx_index* ix) { return (uint32_t)ix->host.chr_names.size(); }
+extern "C" const char* gsx_index_chromosome_name(const gsx_index* ix, uint32_t i) { return ix->host.chr_names[i].c_str(); }
+extern "C" uint64_t gsx_index_chromosome_length(const gsx_index* ix, uint32_t i) { return ix->host.chr_lens[i]; }
+extern "C" uint64_t gsx_index_device_bytes(const gsx_index* ix) { return ix->dev.empty() ? 0 : ix->dev[0].bytes; }
+extern "C" int gsx_index_n_devices(const gsx_index* ix) { return (int)ix->dev.size(); }
+
+static uint8_t sym_of(char c) { return c == 'A' ? SYM_A : c == 'C' ? SYM_C : c == 'G' ? SYM_G : c == 'T' ? SYM_T : c == 'N' ? SYM_N : SYM_X; }
+
+extern "C" int gsx_index_rank(const gsx_index* ix, int strand, const uint64_t* rows, const char* syms, size_t n, uint64_t* out) {
+    if (!ix || ix->dev.empty() || strand < 0 || strand > 1) return fail(GSX_ERR_ARG, "bad argument");
+    try {
+        const DeviceIndex& di = ix->dev[0];
+        CK(cudaSetDevice(di.device));
+        std::vector<uint32_t> r(n), o(n); std::vector<uint8_t> s(n);
+        for (size_t i = 0; i < n; i++) { if (rows[i] > di.st[strand].d.n) return fail(GSX_ERR_ARG, "row out of range"); r[i] = (uint32_t)rows[i]; s[i] = sym_of(syms[i]); }
+        uint32_t *dr, *dout; uint8_t* ds;
+        CK(cudaMalloc(&dr, n * 4 + 4)); CK(cudaMalloc(&dout, n * 4 + 4)); CK(cudaMalloc(&ds, n + 4));
+        CK(cudaMemcpy(dr, r.data(), n * 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(ds, s.data(), n, cudaMemcpyHostToDevice));
+        CK(launch_rank_query(di.st[strand].d, dr, ds, (uint32_t)n, dout, 0));
+        CK(cudaMemcpy(o.data(), dout, n * 4, cudaMemcpyDeviceToHost));
+        cudaFree(dr); cudaFree(dout); cudaFree(ds);
+        for (size_t i = 0; i < n; i++) out[i] = o[i];
+    } catch (const CudaError& e) { return fail(GSX_ERR_CUDA, e.what()); }
+    return GSX_OK;
+}
+
+extern "C" int gsx_index_locate(const gsx_index* ix, int strand, const uint64_t* rows, size_t n, uint64_t* out) {
+    if (!ix || ix->dev.empty() || strand < 0 || strand > 1) return fail(GSX_ERR_ARG, "bad argument");
+    try {
+        const DeviceIndex& di = ix->dev[0];
+        CK(cudaSetDevice(di.device));
+        std::vector<uint32_t> r(n), o(n);
+        for (size_t i = 0; i < n; i++) { if (rows[i] >= di.st[strand].d.n) return fail(GSX_ERR_ARG, "row out of range"); r[i] = (uint32_t)rows[i]; }
+        uint32_t *dr, *dout;
+        CK(cudaMalloc(&dr, n * 4 + 4)); CK(cudaMalloc(&dout, n * 4 + 4));
+        CK(cudaMemcpy(dr, r.data(), n * 4, cudaMemcpyHostToDevice));
+        CK(launch_locate_query(di.st[strand].d, dr, (uint32_t)n, dout, 0));
+        CK(cudaMemcpy(o.data(), dout, n * 4, cudaMemcpyDeviceToHost));
+        cudaFree(dr); cudaFree(dout);
+        for (size_t i = 0; i < n; i++) out[i] = o[i];
+    } catch (const CudaError& e) { return fail(GSX_ERR_CUDA, e.what()); }
+    return GSX_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// enumerate
+// ---------------------------------------------------------------------------------------------------------
+struct DevBufs {
+    std::vector<void*> ptrs;
+    template <class T> T* alloc(size_t n, bool zero = false) {
+        void* p = nullptr; size_t b = std::max<size_t>(n, 1) * sizeof(T);
+        CK(cudaMalloc(&p, b)); ptrs.push_back(p);
+        if (zero) CK(cudaMemset(p, 0, b));
+        return (T*)p;
+    }
+    void free_one(void* p) { auto it = std::find(ptrs.begin(), ptrs.end(), p); if (it != ptrs.end()) { cudaFree(p); ptrs.erase(it); } }
+    ~DevBufs() { for (void* p : ptrs) cudaFree(p); }
+};
+
+int gsx_prepare_guides(const gsx_guide* guides, size_t n, const gsx_params* p, gsx::Prepared& out) {
+    if (p->max_bulge_size != 1) return fail(GSX_ERR_ARG, "max_bulge_size must be 1 (the reference hard-wires it: process.hpp:82-87)");
+    if (p->mismatches >= (uint32_t)kMaxDist) return fail(GSX_ERR_ARG, "mismatches must be <= 7");
+    if (p->rna_bulges > 7 || p->dna_bulges > 7) return fail(GSX_ERR_ARG, "bulge counts must be <= 7");
+    if (p->threshold >= kMaxDist) return fail(GSX_ERR_ARG, "threshold must be <= 7");
+    if (p->n_alt_pams + 1 > (uint32_t)kMaxPams) return fail(GSX_ERR_ARG, "too many alternative PAMs (max 7)");
+    memset(out.pamsets, 0, sizeof out.pamsets);
+    std::map<std::string, int> set_of;
+    out.recs.resize(n);
+    size_t max_total = 0;
+    const bool bulges = p->rna_bulges || p->dna_bulges;
+    for (size_t i = 0; i < n; i++) {
+        const char* seq = guides[i].seq ? guides[i].seq : "";
+        const char* pam = guides[i].pam ? guides[i].pam : "";
+        size_t sl = strlen(seq), pl = strlen(pam);
+        if (sl == 0 || sl > (size_t)kMaxQ) return fail(GSX_ERR_ARG, "guide sequence length must be 1..32");
+        if (pl > (size_t)kMaxPamLen) return fail(GSX_ERR_ARG, "PAM longer than 8");
+        GuideRec& r = out.recs[i];
+        memset(&r, 0, sizeof r);
+        r.qlen = (uint8_t)sl; r.seqlen = (uint8_t)sl;
+        memcpy(r.seq, seq, sl);
+        for (size_t l = 0; l < sl; l++)       // consumption order: process.hpp:63, index.hpp:214
+            r.q[l] = p->start ? sym_of(seq[sl - 1 - l]) : sym_of(complement_char(seq[l]));
+        auto it = set_of.find(pam);
+        if (it == set_of.end()) {
+            if (set_of.size() >= (size_t)kMaxPamSets) return fail(GSX_ERR_ARG, "more than 16 distinct PAM column values in one call");
+            int id = (int)set_of.size();
+            PamSet& ps = out.pamsets[id];
+            std::vector<std::string> pams;                                   // process.hpp:51-56
+            if (pl == 0) pams.push_back("");
+            else { for (uint32_t a = 0; a < p->n_alt_pams; a++) pams.push_back(p->alt_pams[a] ? p->alt_pams[a] : ""); pams.push_back(pam); }
+            ps.n_pams = (uint8_t)pams.size(); ps.kpam_len = (uint8_t)pl;
+            for (size_t k = 0; k < pams.size(); k++) {
+                const std::string& s = pams[k];
+                if (s.size() > (size_t)kMaxPamLen) return fail(GSX_ERR_ARG, "alternative PAM longer than 8");
+                if (s.empty() && pams.size() > 1) return fail(GSX_ERR_ARG, "empty alternative PAM");
+                ps.plen[k] = (uint8_t)s.size();
+                for (size_t j = 0; j < s.size(); j++)
+                    ps.sym[k][j] = p->start ? sym_of(s[s.size() - 1 - j]) : sym_of(complement_char(s[j]));
+            }
+            out.max_pams = std::max<uint32_t>(out.max_pams, ps.n_pams);
+            it = set_of.emplace(pam, id).first;
+        }
+        r.pamset = (uint8_t)it->second;
+        size_t mp = 0; const PamSet& ps = out.pamsets[r.pamset];
+        for (int k = 0; k < ps.n_pams; k++) mp = std::max<size_t>(mp, ps.plen[k]);
+        max_total = std::max(max_total, sl + mp);
+    }
+    out.wide = bulges || max_total > 27;
+    if (max_total + p->dna_bulges > 32) return fail(GSX_ERR_ARG, "guide + PAM + DNA bulges longer than 32 characters");
+    return GSX_OK;
+}
+
+struct DeviceJob {
+    const gsx_index* ix = nullptr; int slot = 0;
+    const Prepared* prep = nullptr; const gsx_params* p = nullptr;
+    size_t g0 = 0, g1 = 0;
+    HostArrays out; gsx_counters ctr{};
+    int status = GSX_OK; std::string err;
+};
+
+static int env_int(const char* name, int dflt) { const char* v = getenv(name); return v && *v ? atoi(v) : dflt; }
+
+static void run_device_job(DeviceJob* job) {
+    try {
+        const DeviceIndex& di = job->ix->dev[job->slot];
+        const Prepared& prep = *job->prep; const gsx_params& p = *job->p;
+        const uint32_t n = (uint32_t)(job->g1 - job->g0);
+        const uint32_t n_dist = p.mismatches + 1;
+        CK(cudaSetDevice(di.device));
+        cudaStream_t s; CK(cudaStreamCreate(&s));
+        cudaEvent_t ev[8]; for (auto& e : ev) CK(cudaEventCreate(&e));
+        DevBufs B;
+        HostArrays& H = job->out; H.n_guides = n;
+        H.dropped = H.alloc<uint8_t>(n); H.n_hits_of = H.alloc<uint32_t>(n); H.hoff = H.alloc<uint32_t>(n + 1);
+        H.specificity = H.alloc<float>(n); H.perfect = H.alloc<uint8_t>(n); H.cbd = H.alloc<uint32_t>((size_t)n * n_dist);
+        if (n == 0) { H.hoff[0] = 0; cudaStreamDestroy(s); return; }
+
+        auto t_h2d0 = std::chrono::steady_clock::now();
+        GuideRec* d_guides = B.alloc<GuideRec>(n);
+        PamSet* d_pamsets = B.alloc<PamSet>(kMaxPamSets);
+        CK(cudaMemcpyAsync(d_guides, prep.recs.data() + job->g0, (size_t)n * sizeof(GuideRec), cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(d_pamsets, prep.pamsets, sizeof(prep.pamsets), cudaMemcpyHostToDevice, s));
+        CK(cudaStreamSynchronize(s));
+        job->ctr.ms_h2d = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_h2d0).count();
+
+        uint32_t* d_nmatch = B.alloc<uint32_t>(n + 1, true);
+        uint8_t* d_dropped = B.alloc<uint8_t>(n, true);
+        uint32_t* d_ctrs = B.alloc<uint32_t>(8, true);            // [0] task counter [1] match count [2] error flag
+        unsigned long long* d_stats = B.alloc<unsigned long long>(8, true);
+        const int variant_n = env_int("GSX_SEARCH_VARIANT", 1), variant_w = env_int("GSX_SEARCH_VARIANT_WIDE", 0);
+
+        SearchArgs a{};
+        a.st[0] = di.st[0].d; a.st[1] = di.st[1].d; a.guides = d_guides; a.pamsets = d_pamsets;
+        a.task_counter = d_ctrs + 0; a.match_count = d_ctrs + 1; a.error_flag = d_ctrs + 2; a.stats = d_stats;
+        a.guide_nmatch = d_nmatch; a.max_iters = 1u << 28; a.max_pams = prep.max_pams;
+        a.p.n_tasks = 2 * n;
+
+        CK(cudaEventRecord(ev[0], s));
+        // ---- threshold prefilter (process.hpp:66-76): mismatch-only counting search, guide dropped if > 1 site -----
+        if (p.threshold > 0) {
+            unsigned long long* d_gcount = B.alloc<unsigned long long>(n, true);
+            uint32_t spill_cap = 4096;
+            for (;;) {
+                int warps = search_grid_warps(false, variant_n, di.sm_count);
+                uint32_t* d_spill = B.alloc<uint32_t>((size_t)warps * spill_cap * 6);
+                CK(cudaMemsetAsync(d_ctrs, 0, 8 * sizeof(uint32_t), s));
+                CK(cudaMemsetAsync(d_gcount, 0, (size_t)n * 8, s));
+                SearchArgs c = a; c.p.M = (uint32_t)p.threshold; c.p.R = c.p.D = 0; c.p.counting = 1; c.p.match_cap = 0; c.p.spill_cap = spill_cap;
+                c.guide_count = d_gcount; c.spill = d_spill; c.skip = nullptr; c.matches = nullptr;
+                CK(launch_search(c, false, variant_n, di.sm_count, s, nullptr));
+                uint32_t h[3]; CK(cudaMemcpyAsync(h, d_ctrs, sizeof h, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s));
+                B.free_one(d_spill);
+                if (h[2] & GSX_KERR_WATCHDOG) throw std::runtime_error("search kernel watchdog tripped");
+                if (h[2] & GSX_KERR_SPILL_OVERFLOW) { spill_cap *= 4; continue; }
+                break;
+            }
+            CK(launch_threshold(d_gcount, d_dropped, n, s));
+            B.free_one(d_gcount);
+            unsigned long long zero[8] = {0}; CK(cudaMemcpyAsync(d_stats, zero, sizeof zero, cudaMemcpyHostToDevice, s));
+        }
+        // ---- main search ---------------------------------------------------------------------------------------------
+        const bool wide = prep.wide;
+        const int variant = wide ? variant_w : variant_n;
+        uint64_t match_cap = std::max<uint64_t>((uint64_t)n * (wide ? 2048 : 48), 1u << 18);
+        match_cap = std::min<uint64_t>(match_cap, 1u << 27);
+        uint32_t spill_cap = wide ? 8192 : 2048;
+        if (env_int("GSX_MATCH_CAP", 0) > 0) match_cap = (uint64_t)env_int("GSX_MATCH_CAP", 0);      // tests: force the retry path
+        if (env_int("GSX_SPILL_CAP", 0) > 0) spill_cap = (uint32_t)env_int("GSX_SPILL_CAP", 0);
+        MatchRec* d_matches = nullptr; uint32_t* d_spill = nullptr; uint32_t n_matches = 0;
+        for (int attempt = 0;; attempt++) {
+            if (attempt > 12) throw std::runtime_error("search arenas keep overflowing");
+            int warps = search_grid_warps(wide, variant, di.sm_count);
+            if (warps <= 0) throw std::runtime_error("unknown search kernel variant");
+            d_matches = B.alloc<MatchRec>(match_cap);
+            d_spill = B.alloc<uint32_t>((size_t)warps * spill_cap * (wide ? 8 : 6));
+            CK(cudaMemsetAsync(d_ctrs, 0, 8 * sizeof(uint32_t), s));
+            CK(cudaMemsetAsync(d_nmatch, 0, (size_t)(n + 1) * 4, s));
+            CK(cudaMemsetAsync(d_stats, 0, 8 * sizeof(unsigned long long), s));
+            SearchArgs m = a; m.p.M = p.mismatches; m.p.R = p.rna_bulges; m.p.D = p.dna_bulges; m.p.counting = 0;
+            m.p.match_cap = (uint32_t)match_cap; m.p.spill_cap = spill_cap; m.spill = d_spill; m.matches = d_matches;
+            m.skip = p.threshold > 0 ? d_dropped : nullptr;
+            CK(launch_search(m, wide, variant, di.sm_count, s, nullptr));
+            uint32_t h[3]; CK(cudaMemcpyAsync(h, d_ctrs, sizeof h, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s));
+            B.free_one(d_spill);
+            if (h[2] & GSX_KERR_WATCHDOG) throw std::runtime_error("search kernel watchdog tripped");
+            if (h[2] & (GSX_KERR_MATCH_OVERFLOW | GSX_KERR_SPILL_OVERFLOW)) {
+                B.free_one(d_matches);
+                if (h[2] & GSX_KERR_MATCH_OVERFLOW) match_cap = std::max<uint64_t>(match_cap * 2, (uint64_t)h[1] + (h[1] >> 2));
+                if (h[2] & GSX_KERR_SPILL_OVERFLOW) spill_cap *= 4;
+                if (match_cap > (1ull << 31)) throw std::runtime_error("more than 2^31 matches in one batch; lower the batch size");
+                continue;
+            }
+            n_matches = h[1];
+            break;
+        }
+        CK(cudaEventRecord(ev[1], s));
+        // ---- arrange --------------------------------------------------------------------------------------------------
+        uint32_t* d_moff = B.alloc<uint32_t>(n + 1);
+        uint32_t* d_cursor = B.alloc<uint32_t>(n, true);
+        uint32_t* d_by_guide = B.alloc<uint32_t>(n_matches);
+        uint32_t* d_sorted = B.alloc<uint32_t>(n_matches);
+        uint32_t* d_sorted_off = B.alloc<uint32_t>(n_matches);
+        uint32_t* d_nhits = B.alloc<uint32_t>(n + 1, true);
+        uint32_t* d_hoff = B.alloc<uint32_t>(n + 1);
+        uint32_t* d_cbd = B.alloc<uint32_t>((size_t)n * n_dist, true);
+        CK(launch_scan(d_nmatch, d_moff, n, s));
+        CK(launch_scatter(d_matches, n_matches, d_moff, d_cursor, d_by_guide, s));
+        CK(launch_order(d_matches, d_moff, d_by_guide, n, n_dist, d_sorted, d_sorted_off, d_nhits, d_cbd, s));
+        {   // total hits can exceed 2^32 only for absurd inputs; the scan is 32-bit, so check with a 64-bit host sum
+            CK(cudaMemcpyAsync(H.n_hits_of, d_nhits, (size_t)n * 4, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s));
+            uint64_t tot = 0; for (uint32_t i = 0; i < n; i++) tot += H.n_hits_of[i];
+            if (tot >= (1ull << 32)) throw std::runtime_error("more than 2^32 hits in one batch; lower the batch size");
+            H.n_hits = (size_t)tot;
+        }
+        CK(launch_scan(d_nhits, d_hoff, n, s));
+        const uint32_t nh = (uint32_t)H.n_hits;
+        uint32_t* d_hit_match = B.alloc<uint32_t>(nh); uint32_t* d_hit_row = B.alloc<uint32_t>(nh); uint32_t* d_hit_guide = B.alloc<uint32_t>(nh);
+        CK(launch_expand(d_matches, d_moff, d_sorted, d_sorted_off, d_hoff, n, n_matches, d_hit_match, d_hit_row, d_hit_guide, s));
+        CK(cudaEventRecord(ev[2], s));
+        // ---- locate + coordinates + CFD ------------------------------------------------------------------------------
+        LocateArgs L{};
+        L.st[0] = di.st[0].d; L.st[1] = di.st[1].d; L.matches = d_matches; L.guides = d_guides; L.pamsets = d_pamsets; L.chroms = di.chroms;
+        L.hit_match = d_hit_match; L.hit_row = d_hit_row; L.n_hits = nh; L.n_chr = (uint32_t)job->ix->chroms.size(); L.wide = wide;
+        L.genome_length = job->ix->host.genome_length;
+        L.abs_pos = B.alloc<int64_t>(nh); L.chr = B.alloc<int32_t>(nh); L.pos1 = B.alloc<uint32_t>(nh); L.strand = B.alloc<uint8_t>(nh);
+        L.distance = B.alloc<uint8_t>(nh); L.dna = B.alloc<uint8_t>(nh); L.rna = B.alloc<uint8_t>(nh); L.index_id = B.alloc<uint8_t>(nh);
+        L.cfd = B.alloc<float>(nh); L.flags = B.alloc<uint8_t>(nh); L.stats = d_stats;
+        CK(launch_locate_score(L, s));
+        CK(cudaEventRecord(ev[3], s));
+        // ---- specificity ------------------------------------------------------------------------------------------------
+        SpecArgs S{};
+        S.guide_hoff = d_hoff; S.count_by_distance = d_cbd; S.chr = L.chr; S.cfd = L.cfd; S.flags = L.flags;
+        S.counted = B.alloc<uint8_t>(nh, true); S.specificity = B.alloc<float>(n); S.perfect = B.alloc<uint8_t>(n);
+        S.n_guides = n; S.n_dist = n_dist; S.sam_rule = p.sam_scoring ? 1 : 0; S.max_off_targets = p.max_off_targets;
+        CK(launch_specificity(S, s));
+        CK(cudaEventRecord(ev[4], s));
+        // ---- results to host ---------------------------------------------------------------------------------------------
+        H.abs_pos = H.alloc<int64_t>(nh); H.sa_row = H.alloc<uint32_t>(nh); H.chr = H.alloc<int32_t>(nh); H.pos1 = H.alloc<uint32_t>(nh);
+        H.strand = H.alloc<uint8_t>(nh); H.distance = H.alloc<uint8_t>(nh); H.rna = H.alloc<uint8_t>(nh); H.dna = H.alloc<uint8_t>(nh);
+        H.index_id = H.alloc<uint8_t>(nh); H.cfd = H.alloc<float>(nh); H.counted = H.alloc<uint8_t>(nh); H.hit_match = H.alloc<uint32_t>(nh);
+        H.matches = H.alloc<MatchRec>(n_matches); H.n_matches = n_matches;
+        auto d2h = [&](void* dst, const void* src, size_t bytes) { if (bytes) CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s)); };
+        d2h(H.dropped, d_dropped, n); d2h(H.hoff, d_hoff, (size_t)(n + 1) * 4); d2h(H.specificity, S.specificity, (size_t)n * 4);
+        d2h(H.perfect, S.perfect, n); d2h(H.cbd, d_cbd, (size_t)n * n_dist * 4);
+        d2h(H.abs_pos, L.abs_pos, (size_t)nh * 8); d2h(H.sa_row, d_hit_row, (size_t)nh * 4); d2h(H.chr, L.chr, (size_t)nh * 4);
+        d2h(H.pos1, L.pos1, (size_t)nh * 4); d2h(H.strand, L.strand, nh); d2h(H.distance, L.distance, nh); d2h(H.rna, L.rna, nh);
+        d2h(H.dna, L.dna, nh); d2h(H.index_id, L.index_id, nh); d2h(H.cfd, L.cfd, (size_t)nh * 4); d2h(H.counted, S.counted, nh);
+        d2h(H.hit_match, d_hit_match, (size_t)nh * 4); d2h(H.matches, d_matches, (size_t)n_matches * sizeof(MatchRec));
+        unsigned long long st[8]; d2h(st, d_stats, sizeof st);
+        CK(cudaEventRecord(ev[5], s));
+        CK(cudaStreamSynchronize(s));
+        float ms;
+        CK(cudaEventElapsedTime(&ms, ev[0], ev[1])); job->ctr.ms_search = ms;
+        CK(cudaEventElapsedTime(&ms, ev[1], ev[2])); job->ctr.ms_arrange = ms;
+        CK(cudaEventElapsedTime(&ms, ev[2], ev[3])); job->ctr.ms_locate = ms;
+        CK(cudaEventElapsedTime(&ms, ev[3], ev[4])); job->ctr.ms_score = ms;
+        CK(cudaEventElapsedTime(&ms, ev[0], ev[4])); job->ctr.ms_total_device = ms;
+        CK(cudaEventElapsedTime(&ms, ev[4], ev[5])); job->ctr.ms_d2h = ms;
+        job->ctr.nodes = st[0]; job->ctr.lookups = st[1]; job->ctr.spills = st[2]; job->ctr.lf_steps = st[3];
+        job->ctr.matches = n_matches; job->ctr.hits = nh;
+        for (auto& e : ev) cudaEventDestroy(e);
+        cudaStreamDestroy(s);
+    } catch (const CudaError& e) { job->status = GSX_ERR_CUDA; job->err = e.what(); }
+    catch (const std::bad_alloc&) { job->status = GSX_ERR_NOMEM; job->err = "out of host memory"; }
+    catch (const std::exception& e) { job->status = GSX_ERR_INTERNAL; job->err = e.what(); }
+}
+
+void gsx_build_view(gsx_result* r) {
+    gsx_result_view& v = r->view;
+    size_t ng = 0, nh = 0;
+    for (auto& p : r->parts) { ng += p.n_guides; nh += p.n_hits; }
+    v.n_guides = ng; v.n_hits = nh; v.n_dist = r->n_dist;
+    r->first_hit.resize(ng);
+    size_t g = 0, h = 0;
+    for (auto& p : r->parts) { for (size_t i = 0; i < p.n_guides; i++) r->first_hit[g + i] = h + p.hoff[i]; g += p.n_guides; h += p.n_hits; }
+    v.first_hit = r->first_hit.data();
+    if (r->parts.size() == 1) {
+        HostArrays& p = r->parts[0];
+        v.dropped = p.dropped; v.n_hits_of = p.n_hits_of; v.specificity = p.specificity; v.perfect_match = p.perfect; v.count_by_distance = p.cbd;
+        v.abs_pos = p.abs_pos; v.sa_row = p.sa_row; v.chr = p.chr; v.pos1 = p.pos1; v.strand = p.strand; v.distance = p.distance;
+        v.rna_bulges = p.rna; v.dna_bulges = p.dna; v.index_id = p.index_id; v.cfd = p.cfd; v.counted = p.counted;
+        return;
+    }
+    auto cat = [&](auto& dst, auto member, bool per_hit, size_t mult) {
+        dst.clear();
+        for (auto& p : r->parts) { size_t n = (per_hit ? p.n_hits : p.n_guides) * mult; auto* src = p.*member; dst.insert(dst.end(), src, src + n); }
+    };
+    cat(r->dropped, &HostArrays::dropped, false, 1); cat(r->n_hits_of, &HostArrays::n_hits_of, false, 1);
+    cat(r->specificity, &HostArrays::specificity, false, 1); cat(r->perfect, &HostArrays::perfect, false, 1);
+    cat(r->cbd, &HostArrays::cbd, false, r->n_dist);
+    cat(r->abs_pos, &HostArrays::abs_pos, true, 1); cat(r->sa_row, &HostArrays::sa_row, true, 1); cat(r->chr, &HostArrays::chr, true, 1);
+    cat(r->pos1, &HostArrays::pos1, true, 1); cat(r->strand, &HostArrays::strand, true, 1); cat(r->distance, &HostArrays::distance, true, 1);
+    cat(r->rna, &HostArrays::rna, true, 1); cat(r->dna, &HostArrays::dna, true, 1); cat(r->index_id, &HostArrays::index_id, true, 1);
+    cat(r->cfd, &HostArrays::cfd, true, 1); cat(r->counted, &HostArrays::counted, true, 1);
+    v.dropped = r->dropped.data(); v.n_hits_of = r->n_hits_of.data(); v.specificity = r->specificity.data(); v.perfect_match = r->perfect.data();
+    v.count_by_distance = r->cbd.data(); v.abs_pos = r->abs_pos.data(); v.sa_row = r->sa_row.data(); v.chr = r->chr.data(); v.pos1 = r->pos1.data();
+    v.strand = r->strand.data(); v.distance = r->distance.data(); v.rna_bulges = r->rna.data(); v.dna_bulges = r->dna.data();
+    v.index_id = r->index_id.data(); v.cfd = r->cfd.data(); v.counted = r->counted.data();
+}
+
+extern "C" int gsx_enumerate(const gsx_index* ix, const gsx_guide* guides, size_t n_guides, const gsx_params* p, gsx_result** out) {
+    if (!ix || !p || !out || (!guides && n_guides)) return fail(GSX_ERR_ARG, "null argument");
+    *out = nullptr;
+    if (ix->dev.empty()) return fail(GSX_ERR_NO_DEVICE, "index is not resident on any device");
+    if (n_guides >= (1ull << 30)) return fail(GSX_ERR_ARG, "too many guides in one call");
+    Prepared prep;
+    if (int rc = gsx_prepare_guides(guides, n_guides, p, prep)) return rc;
+    const size_t nd = ix->dev.size();
+    // guides are independent: contiguous shards per device, no data-path collective
+    std::vector<DeviceJob> jobs(nd);
+    for (size_t d = 0; d < nd; d++) {
+        jobs[d].ix = ix; jobs[d].slot = (int)d; jobs[d].prep = &prep; jobs[d].p = p;
+        jobs[d].g0 = n_guides * d / nd; jobs[d].g1 = n_guides * (d + 1) / nd;
+    }
+    if (nd == 1) run_device_job(&jobs[0]);
+    else { std::vector<std::thread> th; for (auto& j : jobs) th.emplace_back(run_device_job, &j); for (auto& t : th) t.join(); }
+    for (auto& j : jobs) if (j.status != GSX_OK) { for (auto& k : jobs) k.out.release(); return fail(j.status, j.err); }
+    gsx_result* r = new gsx_result();
+    r->n_dist = p->mismatches + 1; r->wide = prep.wide; r->guides = std::move(prep.recs);
+    size_t g = 0, h = 0;
+    for (auto& j : jobs) {
+        r->part_g0.push_back(g); r->part_h0.push_back(h); g += j.out.n_guides; h += j.out.n_hits;
+        r->parts.push_back(std::move(j.out));
+        gsx_counters& c = r->counters;
+        c.nodes += j.ctr.nodes; c.lookups += j.ctr.lookups; c.matches += j.ctr.matches; c.hits += j.ctr.hits; c.lf_steps += j.ctr.lf_steps; c.spills += j.ctr.spills;
+        c.ms_search = std::max(c.ms_search, j.ctr.ms_search); c.ms_arrange = std::max(c.ms_arrange, j.ctr.ms_arrange);
+        c.ms_locate = std::max(c.ms_locate, j.ctr.ms_locate); c.ms_score = std::max(c.ms_score, j.ctr.ms_score);
+        c.ms_total_device = std::max(c.ms_total_device, j.ctr.ms_total_device); c.ms_h2d = std::max(c.ms_h2d, j.ctr.ms_h2d); c.ms_d2h = std::max(c.ms_d2h, j.ctr.ms_d2h);
+    }
+    gsx_build_view(r);
+    *out = r;
+    return GSX_OK;
+}
+
+extern "C" int gsx_result_view_get(const gsx_result* r, gsx_result_view* view) { if (!r || !view) return fail(GSX_ERR_ARG, "null argument"); *view = r->view; return GSX_OK; }
+extern "C" int gsx_result_counters(const gsx_result* r, gsx_counters* out) { if (!r || !out) return fail(GSX_ERR_ARG, "null argument"); *out = r->counters; return GSX_OK; }
+
+extern "C" int gsx_result_match_sequence(const gsx_result* r, size_t hit, char* buf, size_t buf_len) {
+    if (!r || !buf || buf_len < 48) return fail(GSX_ERR_ARG, "buffer must hold 48 bytes");
+    if (hit >= r->view.n_hits) return fail(GSX_ERR_ARG, "hit index out of range");
+    size_t pi = std::upper_bound(r->part_h0.begin(), r->part_h0.end(), hit) - r->part_h0.begin() - 1;
+    const HostArrays& p = r->parts[pi];
+    const MatchRec& m = p.matches[p.hit_match[hit - r->part_h0[pi]]];
+    const GuideRec& g = r->guides[r->part_g0[pi] + (m.task >> 1)];
+    uint32_t len = decode_match(m, g, r->wide, buf);
+    for (uint32_t i = 0; i < len; i++) buf[i] = complement_char(buf[i]);
+    buf[len] = 0;
+    return GSX_OK;
+}
+
+extern "C" void gsx_result_free(gsx_result* r) {
+    if (!r) return;
+    for (auto& p : r->parts) p.release();
+    delete r;
+}

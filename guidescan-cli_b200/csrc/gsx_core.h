@@ -1,0 +1,370 @@
+// gsx_core.h -- per-node arithmetic of the search, shared verbatim by the CUDA kernels and by the host-side
+// unit tests of this arithmetic (tests/host_core_check.cpp).  Nothing here is a CPU fallback of the product: the
+// product only ever calls these from device code.
+//
+// Semantics follow the reference's three recursions in include/genomics/index.hpp (125-170 PAM / wildcard
+// stage, 182-248 mismatch-only, 250-375 bulge-aware); the traversal ORDER differs (children are explored in
+// parallel), the set of emitted (string, sp, ep, mismatches, dna, rna) tuples does not.
+#ifndef GSX_CORE_H
+#define GSX_CORE_H
+#include "gsx_types.h"
+#include "gsx_kernels.h"
+
+namespace gsx {
+
+GSX_HD uint32_t popc64(uint64_t v) {
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__popcll(v);
+#else
+    return (uint32_t)__builtin_popcountll(v);
+#endif
+}
+
+GSX_HD uint32_t lower_bound_u32(const uint32_t* a, uint32_t n, uint32_t v) {   // first index with a[idx] >= v
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (a[mid] < v) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// number of exception rows in [start, i)
+GSX_HD uint32_t exc_in(const DevStrand& st, uint32_t start, uint32_t i) {
+    if (i <= st.exc_lo || start > st.exc_hi) return 0;
+    if (st.n_exc == 1) return 1;        // exc_lo == exc_hi lies in [start, i)
+    return lower_bound_u32(st.exc_rows, st.n_exc, i) - lower_bound_u32(st.exc_rows, st.n_exc, start);
+}
+
+// occurrences of 'N' in BWT[0, i)
+GSX_HD uint32_t rank_n(const DevStrand& st, uint32_t i) { return lower_bound_u32(st.n_rows, st.n_nrows, i); }
+
+// occ(c, i) for c = A,C,G,T from the block that holds row i  (= csa.rank_bwt(i, c), sdsl csa_wt.hpp:270-273)
+GSX_HD void block_occ(const DevStrand& st, const uint32_t cnt[4], uint64_t bhi, uint64_t blo, uint32_t i, uint32_t o[4]) {
+    uint32_t r = i & 63u;
+    uint64_t mask = r ? (~0ull >> (64 - r)) : 0ull;
+    uint64_t hi = bhi & mask, lo = blo & mask;
+    uint32_t t = popc64(hi & lo);
+    uint32_t g = popc64(hi) - t;
+    uint32_t c = popc64(lo) - t;
+    uint32_t a = r - t - g - c;                   // rows below r with code 0, exceptions included ...
+    if (st.n_exc) a -= exc_in(st, i - r, i);      // ... and removed here
+    o[0] = cnt[0] + a; o[1] = cnt[1] + c; o[2] = cnt[2] + g; o[3] = cnt[3] + t;
+}
+
+// BWT symbol code of a non-exception row
+GSX_HD uint32_t block_sym(uint64_t bhi, uint64_t blo, uint32_t row) {
+    uint32_t r = row & 63u;
+    return (uint32_t)(((bhi >> r) & 1ull) << 1 | ((blo >> r) & 1ull));
+}
+
+// ---- string sort keys --------------------------------------------------------------------------------
+// The reference orders the matches of one guide/strand/mismatch bucket by std::string comparison of the consumed
+// characters (structures.hpp:43); in ASCII '.' < 'A' < 'C' < 'G' < 'N' < 'T' < 'a' < 'c' < 'g' < 't'.
+//   narrow key (no bulges, qlen + plen <= 27): base-5 number, one digit per character. Protospacer position:
+//     0 = the guide's own (upper-case) character, 1..4 = lower-case a,c,g,t. PAM position: A,C,G,N,T = 0..4.
+//   wide key (bulges): 4 bits per character, '.'=1 A=2 C=3 G=4 N=5 T=6 a=7 c=8 g=9 t=10, left aligned in 128 bits.
+GSX_HD uint32_t wide_upper_digit(uint32_t s) { return s < 3 ? 2 + s : (s == 3 ? 6u : 5u); }   // s: 0..3 ACGT, 4 N
+
+template <bool WIDE>
+GSX_HD void key_append(Node& n, uint32_t digit) {
+    if (WIDE) {
+        n.key_hi = (n.key_hi << 4) | (n.key_lo >> 60);
+        n.key_lo = (n.key_lo << 4) | digit;
+    } else {
+        n.key_lo = n.key_lo * 5ull + digit;
+    }
+}
+
+GSX_HD void key_left_align(uint64_t& hi, uint64_t& lo, uint32_t len) {   // wide key: shift left by 4*(32-len) bits
+    uint32_t sh = 4u * (32u - len);
+    if (sh == 0) return;
+    if (sh >= 64) { hi = sh == 64 ? lo : (lo << (sh - 64)); lo = 0; }
+    else { hi = (hi << sh) | (lo >> (64 - sh)); lo <<= sh; }
+}
+
+struct ExpandCtx {
+    const DevStrand* st;
+    const GuideRec* g;
+    const PamSet* ps;
+    uint32_t M, R, D;
+};
+
+// candidate children of one node
+enum : int {
+    CAND_SYM0 = 0,        // 0..3: consume genome symbol A,C,G,T (exact / mismatch / PAM character)
+    CAND_LITN = 4,        // consume a literal genome 'N' (query character or PAM pattern character is N)
+    CAND_FORK = 5,        // same node for the next alternative PAM
+    CAND_DNA0 = 6,        // 6..9: DNA bulge consuming A,C,G,T            (bulge kernels only)
+    CAND_RNA = 10,        // RNA bulge                                    (bulge kernels only)
+    CAND_SELF = 11,       // emit the node itself (bulge kernels, guide without PAM)
+    CAND_END = 12
+};
+
+GSX_HD uint32_t meta_lvl(uint32_t m) { return m & META_LVL_MASK; }
+GSX_HD uint32_t meta_mm(uint32_t m) { return (m >> META_MM_SHIFT) & 7u; }
+GSX_HD uint32_t meta_pam(uint32_t m) { return (m >> META_PAM_SHIFT) & 7u; }
+GSX_HD uint32_t meta_dna(uint32_t m) { return (m >> META_DNA_SHIFT) & 7u; }
+GSX_HD uint32_t meta_rna(uint32_t m) { return (m >> META_RNA_SHIFT) & 7u; }
+GSX_HD uint32_t meta_state(uint32_t m) { return (m >> META_STATE_SHIFT) & 3u; }
+GSX_HD uint32_t meta_curr(uint32_t m) { return (m >> META_CURR_SHIFT) & 1u; }
+GSX_HD uint32_t meta_make(uint32_t lvl, uint32_t mm, uint32_t pam, uint32_t dna, uint32_t rna, uint32_t state, uint32_t curr) {
+    return lvl | (mm << META_MM_SHIFT) | (pam << META_PAM_SHIFT) | (dna << META_DNA_SHIFT) | (rna << META_RNA_SHIFT) |
+           (state << META_STATE_SHIFT) | (curr << META_CURR_SHIFT);
+}
+
+// Evaluates candidate `cand` of node `nd`.  os / oe = occ(A,C,G,T) at nd.sp and at nd.ep + 1.
+// Returns false if the candidate does not exist; otherwise fills `ch` and sets `emit` when the child is a
+// finished alignment (it is then reported as a match and never expanded).
+template <bool WIDE>
+GSX_HD bool make_child(int cand, const Node& nd, const ExpandCtx& cx, const uint32_t os[4], const uint32_t oe[4],
+                       Node& ch, bool& emit) {
+    const uint32_t meta = nd.meta;
+    const uint32_t lvl = meta_lvl(meta), mm = meta_mm(meta), pam = meta_pam(meta);
+    const uint32_t dna = meta_dna(meta), rna = meta_rna(meta), state = meta_state(meta), curr = meta_curr(meta);
+    const uint32_t qlen = cx.g->qlen;
+    const bool in_proto = lvl < qlen;
+    emit = false;
+    ch = nd;
+
+    if (cand < 4 || cand == CAND_LITN) {
+        uint32_t s = (uint32_t)cand;                 // 0..3, or 4 for N
+        uint32_t nmm = mm, digit;
+        if (in_proto) {
+            uint32_t c = cx.g->q[lvl];
+            bool exact = c == s;
+            if (cand == CAND_LITN) { if (!exact) return false; }
+            else if (!exact) { if (mm >= cx.M) return false; nmm = mm + 1; }        // index.hpp:226, 331
+            digit = WIDE ? (exact ? wide_upper_digit(s) : 7u + s) : (exact ? 0u : 1u + s);
+        } else {
+            uint32_t j = lvl - qlen;
+            if (j >= cx.ps->plen[pam]) return false;
+            uint32_t pc = cx.ps->sym[pam][j];
+            if (cand == CAND_LITN) { if (pc != SYM_N) return false; }
+            else if (!(pc == s || pc == SYM_N)) return false;                       // index.hpp:151-168 with mismatches = 0
+            digit = WIDE ? wide_upper_digit(s) : (s < 3 ? s : (s == 3 ? 4u : 3u));
+        }
+        uint32_t o_s, o_e;
+        if (cand == CAND_LITN) {
+            if (cx.st->n_nrows == 0) return false;
+            o_s = rank_n(*cx.st, nd.sp); o_e = rank_n(*cx.st, nd.ep + 1);
+        } else { o_s = os[s]; o_e = oe[s]; }
+        uint32_t within = o_e - o_s;
+        if (within == 0) return false;
+        ch.sp = cx.st->C[s] + o_s;
+        ch.ep = ch.sp + within - 1;
+        key_append<WIDE>(ch, digit);
+        uint32_t nl = lvl + 1;
+        uint32_t npam = nl <= qlen ? 0u : pam;
+        ch.meta = meta_make(nl, nmm, npam, dna, rna, in_proto ? 0u : state, curr);   // state -> none, curr kept (index.hpp:319-320)
+        emit = (nl == qlen + cx.ps->plen[npam]) && !(WIDE && nl == qlen);
+        return true;
+    }
+    if (cand == CAND_FORK) {
+        if (lvl != qlen || pam + 1 >= cx.ps->n_pams) return false;                  // for (pam : pams) index.hpp:210-212
+        ch.meta = meta_make(lvl, mm, pam + 1, dna, rna, state, curr);
+        return true;
+    }
+    if (!WIDE) return false;
+    if (cand >= CAND_DNA0 && cand < CAND_DNA0 + 4) {                                // index.hpp:265-296
+        if (lvl > qlen) return false;
+        uint32_t d_state = state, d_curr = curr, d_dna = dna;
+        if (cx.D > dna) { if (state != 1u || d_curr == 1u) { d_state = 1; d_curr = 0; d_dna = dna + 1; } }
+        if (!(d_state == 1u && d_curr < 1u && lvl != 0)) return false;              // position != query.length() - 1
+        d_curr += 1;
+        uint32_t s = (uint32_t)(cand - CAND_DNA0);
+        uint32_t within = oe[s] - os[s];
+        if (within == 0) return false;
+        ch.sp = cx.st->C[s] + os[s];
+        ch.ep = ch.sp + within - 1;
+        key_append<WIDE>(ch, 7u + s);
+        ch.meta = meta_make(lvl, mm, pam, d_dna, rna, d_state, d_curr);
+        return true;
+    }
+    if (cand == CAND_RNA) {                                                         // index.hpp:352-368
+        if (!in_proto) return false;
+        uint32_t r_state = state, r_curr = curr, r_rna = rna;
+        if (cx.R > rna) { if (state != 2u || r_curr == 1u) { r_state = 2; r_curr = 0; r_rna = rna + 1; } }
+        if (!(r_state == 2u && r_curr < 1u && lvl != 0)) return false;
+        r_curr += 1;
+        key_append<WIDE>(ch, 1u);
+        ch.meta = meta_make(lvl + 1, mm, 0, dna, r_rna, r_state, r_curr);
+        return true;
+    }
+    if (cand == CAND_SELF) {
+        if (lvl != qlen || cx.ps->plen[pam] != 0) return false;                     // empty PAM: emit at position < 0
+        emit = true;
+        return true;
+    }
+    return false;
+}
+
+GSX_HD uint32_t string_len(uint32_t meta) { return meta_lvl(meta) + meta_dna(meta); }
+
+GSX_HD void fill_match(MatchRec& m, const Node& ch, bool wide) {
+    uint32_t len = string_len(ch.meta);
+    uint64_t hi = ch.key_hi, lo = ch.key_lo;
+    if (wide) key_left_align(hi, lo, len); else hi = 0;
+    m.key_hi = hi; m.key_lo = lo; m.task = ch.task; m.sp = ch.sp; m.width = ch.ep - ch.sp + 1;
+    m.info = meta_mm(ch.meta) | (meta_dna(ch.meta) << 8) | (meta_rna(ch.meta) << 16) | (len << 24);
+}
+
+// ---- decoding a match back into the reference's match.sequence ---------------------------------------------
+GSX_HD char sym_char(uint32_t s) { return s == 0 ? 'A' : s == 1 ? 'C' : s == 2 ? 'G' : s == 3 ? 'T' : s == 4 ? 'N' : '?'; }
+GSX_HD char complement_char(char c) {                                               // sequences.cxx:14-28
+    switch (c) {
+    case 'A': return 'T'; case 'T': return 'A'; case 'C': return 'G'; case 'G': return 'C';
+    case 'a': return 't'; case 't': return 'a'; case 'c': return 'g'; case 'g': return 'c';
+    default: return c;
+    }
+}
+
+// out receives match.sequence (the consumed characters, pre-complement); returns its length (<= 32)
+GSX_HD uint32_t decode_match(const MatchRec& m, const GuideRec& g, bool wide, char* out) {
+    uint32_t len = m.info >> 24;
+    if (wide) {
+        uint64_t hi = m.key_hi, lo = m.key_lo;
+        for (uint32_t i = 0; i < len; i++) {
+            uint32_t d = (uint32_t)(hi >> 60);
+            hi = (hi << 4) | (lo >> 60); lo <<= 4;
+            out[i] = d == 1 ? '.' : d == 2 ? 'A' : d == 3 ? 'C' : d == 4 ? 'G' : d == 5 ? 'N' : d == 6 ? 'T'
+                   : d == 7 ? 'a' : d == 8 ? 'c' : d == 9 ? 'g' : d == 10 ? 't' : '?';
+        }
+    } else {
+        uint64_t k = m.key_lo;
+        for (uint32_t ii = 0; ii < len; ii++) {
+            uint32_t i = len - 1 - ii;
+            uint32_t d = (uint32_t)(k % 5ull); k /= 5ull;
+            if (i < g.qlen) out[i] = d == 0 ? sym_char(g.q[i]) : (d == 1 ? 'a' : d == 2 ? 'c' : d == 3 ? 'g' : 't');
+            else out[i] = d == 0 ? 'A' : d == 1 ? 'C' : d == 2 ? 'G' : d == 3 ? 'N' : 'T';
+        }
+    }
+    return len;
+}
+
+GSX_HD int cfd_base(char c) { return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : -1; }
+GSX_HD char upper_char(char c) { return (c >= 'a' && c <= 'z') ? (char)(c - 32) : c; }
+
+// calculate_cfd (printer.hpp:98-113) on match_sequence = complement(match.sequence).
+// mmtab[4][4][20] / pamtab[4][4]: flat double tables (missing key => 0.0).
+GSX_HD float cfd_score(const char* sgrna, uint32_t sglen, const char* match_seq, uint32_t mlen,
+                       const double* mmtab, const double* pamtab) {
+    uint32_t plen = mlen < 20 ? 0 : (mlen - 20 < 3 ? mlen - 20 : 3);
+    if (sglen != 20 || plen != 3) return 1.0f;
+    float cfd = 1.0f;
+    for (int i = 0; i < 20; i++) {
+        char a = sgrna[i], b = match_seq[i];
+        if (a != b) {
+            int r = a == 'U' ? 3 : cfd_base(a);
+            int d = cfd_base(upper_char(complement_char(b)));
+            double v = (r >= 0 && d >= 0) ? mmtab[(r * 4 + d) * 20 + i] : 0.0;
+            cfd = (float)((double)cfd * v);
+        }
+    }
+    int p1 = cfd_base(match_seq[21]), p2 = cfd_base(match_seq[22]);
+    double pv = (p1 >= 0 && p2 >= 0) ? pamtab[p1 * 4 + p2] : 0.0;
+    cfd = (float)((double)cfd * pv);
+    return cfd;
+}
+
+// resolve_absolute (structures.cxx:7-52). chroms: cumulative starts + lengths, zero-length chromosomes can never
+// hold a position.  Returns chromosome index or -1 (sentinel).
+GSX_HD int resolve_abs(const Chrom* chroms, uint32_t n_chr, int64_t abs, uint32_t seq_len, uint32_t pam_len,
+                       uint32_t* pos1, uint8_t* strand) {
+    *strand = '+';
+    if (abs < 0) { abs = -abs; *strand = '-'; }
+    // last chromosome with start <= abs and length > 0 containing abs
+    uint32_t lo = 0, hi = n_chr;
+    while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (chroms[mid].start + chroms[mid].length <= (uint64_t)abs) lo = mid + 1; else hi = mid; }
+    if (lo >= n_chr) return -1;
+    int64_t off = abs - (int64_t)chroms[lo].start;
+    int64_t start, end;
+    if (*strand == '+') { end = off + 1; start = end - (int64_t)seq_len - (int64_t)pam_len + 1; }
+    else { start = off + 1; end = start + (int64_t)seq_len + (int64_t)pam_len - 1; }
+    if (start < 0 || end > (int64_t)chroms[lo].length) return -1;
+    *pos1 = (uint32_t)start;
+    return (int)lo;
+}
+
+// csa[row]: LF walk to the next sampled row, then sample + steps (mod n) -- sdsl csa_wt.hpp:333-346,
+// suffix_array_helper.hpp:337-349.  `ld` loads one OccBlock (LDG.E.256 on the device).
+template <class LoadBlk>
+GSX_HD uint32_t locate_row_t(const DevStrand& st, uint32_t row, uint32_t* steps, LoadBlk ld) {
+    uint32_t off = 0;
+    const uint32_t smask = (1u << st.sa_shift) - 1u;
+    while (row & smask) {
+        bool is_exc = false;
+        if (st.n_exc && row >= st.exc_lo && row <= st.exc_hi) {
+            uint32_t j = lower_bound_u32(st.exc_rows, st.n_exc, row);
+            if (j < st.n_exc && st.exc_rows[j] == row) { row = st.exc_lf[j]; is_exc = true; }
+        }
+        if (!is_exc) {
+            uint32_t c[4], o[4]; uint64_t hi, lo;
+            ld(st.blocks + (row >> 6), c, hi, lo);
+            block_occ(st, c, hi, lo, row, o);
+            uint32_t s = block_sym(hi, lo, row);
+            row = st.C[s] + o[s];
+        }
+        off++;
+    }
+    *steps += off;
+    uint64_t v = (uint64_t)st.sa_samples[row >> st.sa_shift] + off;
+    return (uint32_t)(v >= st.n ? v - st.n : v);
+}
+
+// one located hit: absolute coordinate (process.hpp:104,111), chromosome (structures.cxx:7-52), CFD (printer.hpp:98-113)
+GSX_HD void score_hit(const LocateArgs& a, uint32_t h, const MatchRec& m, uint32_t sa, const double* mmtab, const double* pamtab) {
+    const uint32_t strand = m.task & 1u;
+    const GuideRec& g = a.guides[m.task >> 1];
+    const PamSet& ps = a.pamsets[g.pamset];
+    int64_t abs = strand == 0 ? -(int64_t)sa : (int64_t)a.genome_length - ((int64_t)sa + 1);
+    uint32_t pos1 = 0; uint8_t sc = '+';
+    int chr = resolve_abs(a.chroms, a.n_chr, abs, g.seqlen, ps.kpam_len, &pos1, &sc);
+    char ms[kMaxQ + kMaxPamLen + 8];
+    uint32_t len = decode_match(m, g, a.wide != 0, ms);
+    for (uint32_t i = 0; i < len; i++) ms[i] = complement_char(ms[i]);            // match_sequence, printer.hpp:264
+    float cfd = cfd_score(g.seq, g.seqlen, ms, len, mmtab, pamtab);
+    uint32_t mm = m.info & 0xffu;
+    bool perfect = mm == 0 && len >= 23 && ms[21] == 'G' && ms[22] == 'G';        // printer.hpp:276
+    a.abs_pos[h] = abs; a.chr[h] = chr; a.pos1[h] = pos1; a.strand[h] = sc;
+    a.distance[h] = (uint8_t)mm; a.dna[h] = (uint8_t)((m.info >> 8) & 0xffu); a.rna[h] = (uint8_t)((m.info >> 16) & 0xffu);
+    a.index_id[h] = (uint8_t)strand; a.cfd[h] = cfd; a.flags[h] = perfect ? 1 : 0;
+}
+
+// per-guide float32 reduction in the reference's output order (printer.hpp:244-300 CSV rule / 115-170 SAM rule)
+GSX_HD void guide_specificity(const SpecArgs& a, uint32_t g) {
+    const uint32_t b = a.guide_hoff[g], n = a.guide_hoff[g + 1] - b;
+    float cfd_sum = 0.0f; bool perfect = false;
+    uint32_t i = 0;
+    for (uint32_t d = 0; d < a.n_dist; d++) {
+        const uint32_t cnt = a.count_by_distance[(size_t)g * a.n_dist + d];
+        int64_t n_off = 0;
+        for (uint32_t j = 0; j < cnt; j++) {
+            const uint32_t h = b + i + j;
+            if (a.sam_rule) { if (a.max_off_targets != -1 && n_off >= a.max_off_targets) break; }       // printer.hpp:129
+            else { if (a.max_off_targets != -1 && (int64_t)j >= a.max_off_targets) break; }              // printer.hpp:259
+            if (a.flags[h] & 1) perfect = true;
+            if (a.chr[h] < 0) continue;
+            cfd_sum += a.cfd[h];
+            a.counted[h] = 1;
+            n_off++;
+        }
+        i += cnt;
+    }
+    float spec = 0.0f;
+    if (n == 0 && !a.sam_rule) spec = 1.0f;                                       // NA row, printer.hpp:190-199
+    else { if (!perfect) cfd_sum += 1.0f; if (cfd_sum > 0.0f) spec = 1.0f / cfd_sum; }
+    a.specificity[g] = spec; a.perfect[g] = perfect ? 1 : 0;
+}
+
+// ordering of the matches of one guide: bucket (mismatches) ascending, forward index before reverse index, string order
+GSX_HD int match_cmp(const MatchRec& x, const MatchRec& y) {
+    uint32_t bx = ((x.info & 0xffu) << 1) | (x.task & 1u), by = ((y.info & 0xffu) << 1) | (y.task & 1u);
+    if (bx != by) return bx < by ? -1 : 1;
+    if (x.key_hi != y.key_hi) return x.key_hi < y.key_hi ? -1 : 1;
+    if (x.key_lo != y.key_lo) return x.key_lo < y.key_lo ? -1 : 1;
+    return 0;
+}
+
+}  // namespace gsx
+#endif

@@ -1,0 +1,120 @@
+// gsx_host.h -- host-side structures behind the C ABI (include/gsx.h).
+#ifndef GSX_HOST_H
+#define GSX_HOST_H
+#include "gsx_types.h"
+#include "gsx_kernels.h"
+#include <string>
+#include <vector>
+#include <cstdint>
+
+namespace gsx {
+
+struct HostStrand {
+    uint64_t n = 0;                       // rows = text length + 1
+    std::vector<OccBlock> blocks;         // n/64 + 1
+    std::vector<uint32_t> sa_samples;
+    uint32_t sa_shift = 6;
+    std::vector<uint32_t> exc_rows, exc_lf, n_rows;
+    uint32_t C[5] = {0, 0, 0, 0, 0};
+};
+
+struct HostIndex {
+    HostStrand st[2];
+    std::vector<std::string> chr_names;
+    std::vector<uint64_t> chr_lens;
+    uint64_t genome_length = 0;
+};
+
+// Builds blocks / exception tables / C from a BWT given as bytes (0 = sentinel).  `next` yields row i's symbol.
+struct StrandBuilder {
+    HostStrand* out;
+    uint64_t n, row = 0;
+    uint64_t run[256];
+    std::vector<uint8_t> exc_sym;
+    std::vector<uint64_t> exc_rank;
+    OccBlock cur;
+    explicit StrandBuilder(HostStrand* o, uint64_t n_rows);
+    void push(uint8_t sym);
+    void finish();
+};
+
+bool load_sdsl_strand(const std::string& path, HostStrand& out, std::string& err);
+bool load_genome_structure(const std::string& path, HostIndex& ix, std::string& err);    // seq_io.cxx:124-144
+bool read_fasta(const std::string& path, std::vector<uint8_t>& seq, HostIndex& ix, std::string& err);   // seq_io.cxx:57-63,74-110
+bool save_gsx(const std::string& prefix, const HostIndex& ix, std::string& err);
+bool load_gsx(const std::string& prefix, HostIndex& ix, std::string& err);
+
+struct DeviceStrand {
+    DevStrand d{};
+    void* blocks = nullptr; void* sa = nullptr; void* exc_rows = nullptr; void* exc_lf = nullptr; void* n_rows = nullptr;
+};
+struct DeviceIndex {
+    int device = 0;
+    int sm_count = 148;
+    DeviceStrand st[2];
+    Chrom* chroms = nullptr;
+    uint64_t bytes = 0;
+};
+
+// GPU suffix sorting (gsx_build.cu): text (bytes, no sentinel) -> HostStrand with samples every 2^sa_shift rows
+bool build_strand_gpu(int device, const uint8_t* text, uint64_t len, uint32_t sa_shift, HostStrand& out, std::string& err);
+
+}  // namespace gsx
+
+struct gsx_index {
+    gsx::HostIndex host;
+    std::vector<gsx::DeviceIndex> dev;
+    std::vector<gsx::Chrom> chroms;
+};
+
+#include "../../include/gsx.h"
+#include <new>
+namespace gsx {
+struct HostArrays {             // one device batch worth of results (pinned host memory)
+    size_t n_guides = 0, n_hits = 0;
+    uint8_t* dropped = nullptr; uint32_t* n_hits_of = nullptr; uint32_t* hoff = nullptr; float* specificity = nullptr; uint8_t* perfect = nullptr;
+    uint32_t* cbd = nullptr;
+    int64_t* abs_pos = nullptr; uint32_t* sa_row = nullptr; int32_t* chr = nullptr; uint32_t* pos1 = nullptr; uint8_t* strand = nullptr;
+    uint8_t* distance = nullptr; uint8_t* rna = nullptr; uint8_t* dna = nullptr; uint8_t* index_id = nullptr; float* cfd = nullptr;
+    uint8_t* counted = nullptr; uint32_t* hit_match = nullptr;
+    MatchRec* matches = nullptr; size_t n_matches = 0;
+    std::vector<void*> owned;
+    template <class T> T* alloc(size_t n) {
+        void* p = nullptr;
+        if (cudaHostAlloc(&p, (n ? n : 1) * sizeof(T), cudaHostAllocDefault) != cudaSuccess) throw std::bad_alloc();
+        owned.push_back(p); return (T*)p;
+    }
+    void release() { for (void* p : owned) cudaFreeHost(p); owned.clear(); }
+};
+
+}  // namespace gsx
+
+namespace gsx {
+struct Prepared {
+    std::vector<GuideRec> recs;
+    PamSet pamsets[kMaxPamSets];
+    uint32_t max_pams = 1;
+    bool wide = false;
+};
+}  // namespace gsx
+
+struct gsx_result {
+    using HostArrays = gsx::HostArrays; using GuideRec = gsx::GuideRec;
+    std::vector<HostArrays> parts;          // in guide order
+    std::vector<size_t> part_g0, part_h0;
+    // merged view (only materialised when there is more than one part)
+    std::vector<uint8_t> dropped, perfect, strand, distance, rna, dna, index_id, counted;
+    std::vector<uint64_t> first_hit; std::vector<uint32_t> n_hits_of, cbd, sa_row, pos1; std::vector<float> specificity, cfd;
+    std::vector<int64_t> abs_pos; std::vector<int32_t> chr;
+    std::vector<GuideRec> guides;
+    gsx_result_view view{};
+    gsx_counters counters{};
+    uint32_t n_dist = 0; bool wide = false;
+};
+
+
+// internal entry points shared with the host-side unit-test harness (tests/host_core_check.cpp)
+int gsx_prepare_guides(const gsx_guide* guides, size_t n, const gsx_params* p, gsx::Prepared& out);
+void gsx_build_view(gsx_result* r);
+
+#endif

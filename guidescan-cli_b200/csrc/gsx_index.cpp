@@ -1,0 +1,223 @@
+// gsx_index.cpp -- host side of the GPU index: reading the reference's index files and laying them out for HBM.
+//
+// Input format = what the reference's `guidescan index` stores with sdsl::store_to_file
+// (reference src/guidescan.cxx:167-175): csa_wt<wt_huff<>,64,8192>::serialize (sdsl csa_wt.hpp:372-382) =
+// wt_pc::serialize (wt_pc.hpp:656-671) + SA samples + ISA samples + byte_alphabet.  Field layout verified
+// against real files: SURVEY.md App. B.
+#include "gsx_host.h"
+#include <algorithm>
+#include <cctype>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+
+namespace gsx {
+
+static inline int sym_code(uint8_t c) { return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : -1; }
+
+StrandBuilder::StrandBuilder(HostStrand* o, uint64_t n_rows) : out(o), n(n_rows) {
+    memset(run, 0, sizeof run);
+    memset(&cur, 0, sizeof cur);
+    out->n = n;
+    out->blocks.clear(); out->blocks.reserve(n / 64 + 1);
+    out->exc_rows.clear(); out->exc_lf.clear(); out->n_rows.clear();
+}
+
+void StrandBuilder::push(uint8_t sym) {
+    uint32_t r = (uint32_t)(row & 63);
+    if (r == 0) {
+        memset(&cur, 0, sizeof cur);
+        cur.cnt[0] = (uint32_t)run['A']; cur.cnt[1] = (uint32_t)run['C']; cur.cnt[2] = (uint32_t)run['G']; cur.cnt[3] = (uint32_t)run['T'];
+    }
+    int code = sym_code(sym);
+    if (code < 0) {
+        out->exc_rows.push_back((uint32_t)row);
+        exc_sym.push_back(sym); exc_rank.push_back(run[sym]);
+        if (sym == 'N') out->n_rows.push_back((uint32_t)row);
+        code = 0;
+    }
+    cur.hi |= (uint64_t)(code >> 1) << r;
+    cur.lo |= (uint64_t)(code & 1) << r;
+    run[sym]++;
+    row++;
+    if ((row & 63) == 0) out->blocks.push_back(cur);
+}
+
+void StrandBuilder::finish() {
+    if (row & 63) out->blocks.push_back(cur);
+    else {      // n is a multiple of 64: one more checkpoint-only block for lookups at i == n
+        memset(&cur, 0, sizeof cur);
+        cur.cnt[0] = (uint32_t)run['A']; cur.cnt[1] = (uint32_t)run['C']; cur.cnt[2] = (uint32_t)run['G']; cur.cnt[3] = (uint32_t)run['T'];
+        out->blocks.push_back(cur);
+    }
+    uint64_t Cb[257]; uint64_t acc = 0;
+    for (int c = 0; c < 256; c++) { Cb[c] = acc; acc += run[c]; }
+    out->C[0] = (uint32_t)Cb['A']; out->C[1] = (uint32_t)Cb['C']; out->C[2] = (uint32_t)Cb['G']; out->C[3] = (uint32_t)Cb['T'];
+    out->C[4] = (uint32_t)Cb['N'];
+    out->exc_lf.resize(out->exc_rows.size());
+    for (size_t i = 0; i < out->exc_rows.size(); i++) out->exc_lf[i] = (uint32_t)(Cb[exc_sym[i]] + exc_rank[i]);
+}
+
+// ---- sdsl file reader ------------------------------------------------------------------------------------
+namespace {
+struct Reader {
+    FILE* f = nullptr; std::string err;
+    bool u64(uint64_t& v) { return fread(&v, 8, 1, f) == 1; }
+    bool u8(uint8_t& v) { return fread(&v, 1, 1, f) == 1; }
+    // int_vector<w>: u64 size in bits, [u8 width if w == 0], ceil(bits/64) words  (sdsl int_vector.hpp:593-609,1563-1595)
+    bool int_vector(int w, uint64_t& bits, uint8_t& width, std::vector<uint64_t>* data) {
+        if (!u64(bits)) return false;
+        width = (uint8_t)w;
+        if (w == 0 && !u8(width)) return false;
+        uint64_t words = (bits + 63) / 64;
+        if (data) { data->resize(words); return words == 0 || fread(data->data(), 8, words, f) == words; }
+        return fseeko(f, (off_t)(words * 8), SEEK_CUR) == 0;
+    }
+    // select_support_mcl (select_support_mcl.hpp:425-493): skipped, the hot path never selects
+    bool skip_select() {
+        uint64_t arg_cnt; if (!u64(arg_cnt)) return false;
+        if (!arg_cnt) return true;
+        uint64_t bits; uint8_t w;
+        if (!int_vector(0, bits, w, nullptr)) return false;     // superblock
+        if (!int_vector(1, bits, w, nullptr)) return false;     // mini_or_long
+        uint64_t sb = (arg_cnt + 4095) >> 12;
+        for (uint64_t i = 0; i < sb; i++) if (!int_vector(0, bits, w, nullptr)) return false;
+        return true;
+    }
+};
+struct WtNode { uint64_t bv_pos, bv_pos_rank; uint16_t parent, child[2]; };
+}  // namespace
+
+bool load_sdsl_strand(const std::string& path, HostStrand& out, std::string& err) {
+    Reader r; r.f = fopen(path.c_str(), "rb");
+    if (!r.f) { err = "cannot open " + path; return false; }
+    auto fail = [&](const char* what) { err = std::string("malformed index file ") + path + " (" + what + ")"; fclose(r.f); return false; };
+    uint64_t size, sigma, bits; uint8_t w;
+    if (!r.u64(size) || !r.u64(sigma)) return fail("header");
+    if (size == 0 || size > 0xFFFFFFFFull) return fail("size out of range for 32-bit rows");
+    std::vector<uint64_t> bv;
+    if (!r.int_vector(1, bits, w, &bv)) return fail("wavelet tree bit vector");
+    if (!r.int_vector(64, bits, w, nullptr)) return fail("rank support");
+    if (!r.skip_select() || !r.skip_select()) return fail("select support");
+    uint64_t n_nodes; if (!r.u64(n_nodes) || n_nodes == 0 || n_nodes > 1024) return fail("tree size");
+    std::vector<WtNode> nodes(n_nodes);
+    for (auto& nd : nodes) {                                   // wt_helper.hpp:109-126
+        if (fread(&nd.bv_pos, 8, 1, r.f) != 1 || fread(&nd.bv_pos_rank, 8, 1, r.f) != 1 || fread(&nd.parent, 2, 1, r.f) != 1 ||
+            fread(nd.child, 2, 2, r.f) != 2) return fail("tree nodes");
+    }
+    if (fseeko(r.f, 256 * 2 + 256 * 8, SEEK_CUR) != 0) return fail("c_to_leaf/path");
+    std::vector<uint64_t> sa_words; uint64_t sa_bits; uint8_t sa_w;
+    if (!r.int_vector(0, sa_bits, sa_w, &sa_words)) return fail("sa samples");
+    fclose(r.f);
+    if (sa_w == 0 || sa_w > 32) { err = "SA sample width unsupported in " + path; return false; }
+
+    // BWT recovery: walk the tree for every row with one read cursor per inner node (children receive their
+    // elements in order, so no rank is needed).
+    std::vector<uint64_t> cursor(n_nodes);
+    for (size_t v = 0; v < n_nodes; v++) cursor[v] = nodes[v].bv_pos;
+    StrandBuilder b(&out, size);
+    const uint64_t* bvp = bv.data();
+    for (uint64_t i = 0; i < size; i++) {
+        uint32_t v = 0;
+        while (nodes[v].child[0] != 0xFFFF) {
+            uint64_t p = cursor[v]++;
+            uint32_t bit = (uint32_t)((bvp[p >> 6] >> (p & 63)) & 1);
+            v = nodes[v].child[bit];
+        }
+        b.push((uint8_t)nodes[v].bv_pos_rank);
+    }
+    b.finish();
+    // SA samples: entry k = SA[64 k], bit-packed little-endian (csa_sampling_strategy.hpp:85-111)
+    uint64_t n_samples = sa_bits / sa_w;
+    if (n_samples < (size + 63) / 64) { err = "too few SA samples in " + path; return false; }
+    out.sa_shift = 6;
+    out.sa_samples.resize(n_samples);
+    const uint64_t mask = sa_w == 64 ? ~0ull : ((1ull << sa_w) - 1);
+    for (uint64_t k = 0; k < n_samples; k++) {
+        uint64_t bitpos = k * sa_w, wd = bitpos >> 6, sh = bitpos & 63;
+        uint64_t v = sa_words[wd] >> sh;
+        if (sh + sa_w > 64) v |= sa_words[wd + 1] << (64 - sh);
+        out.sa_samples[k] = (uint32_t)(v & mask);
+    }
+    return true;
+}
+
+bool load_genome_structure(const std::string& path, HostIndex& ix, std::string& err) {
+    std::ifstream fs(path);
+    if (!fs) { err = "No genome structure file " + path + " located."; return false; }
+    ix.chr_names.clear(); ix.chr_lens.clear(); ix.genome_length = 0;
+    while (fs) {
+        std::string name, len;
+        std::getline(fs, name); std::getline(fs, len);
+        if (name.empty() || len.empty()) break;
+        ix.chr_names.push_back(name); ix.chr_lens.push_back((uint64_t)std::stoll(len));
+        ix.genome_length += ix.chr_lens.back();
+    }
+    return true;
+}
+
+bool read_fasta(const std::string& path, std::vector<uint8_t>& seq, HostIndex& ix, std::string& err) {
+    std::ifstream is(path);
+    if (!is) { err = "ERROR: FASTA file \"" + path + "\" does not exist."; return false; }
+    ix.chr_names.clear(); ix.chr_lens.clear(); seq.clear();
+    std::string line;
+    while (std::getline(is, line)) {
+        if (!line.empty() && line[0] == '>') {
+            std::string name = line.substr(1);
+            size_t b = 0; while (b < name.size() && isspace((unsigned char)name[b])) b++;
+            size_t e = name.size(); while (e > b && isspace((unsigned char)name[e - 1])) e--;
+            name = name.substr(b, e - b);
+            size_t sp = name.find(' ');
+            if (sp != std::string::npos) name = name.substr(0, sp);
+            ix.chr_names.push_back(name); ix.chr_lens.push_back(0);
+            continue;
+        }
+        if (!ix.chr_lens.empty()) ix.chr_lens.back() += line.size();        // raw line length, as the reference counts it
+        size_t b = 0; while (b < line.size() && isspace((unsigned char)line[b])) b++;
+        size_t e = line.size(); while (e > b && isspace((unsigned char)line[e - 1])) e--;
+        for (size_t i = b; i < e; i++) seq.push_back((uint8_t)toupper((unsigned char)line[i]));
+    }
+    ix.genome_length = 0;
+    for (auto l : ix.chr_lens) ix.genome_length += l;
+    return true;
+}
+
+// ---- native cache format (<prefix>.gsx): a flat dump of the HBM layout ----------------------------------------
+namespace {
+const char kMagic[8] = {'G', 'S', 'X', 'I', 'D', 'X', '0', '1'};
+template <class T> bool wr(FILE* f, const std::vector<T>& v) { uint64_t n = v.size(); return fwrite(&n, 8, 1, f) == 1 && (n == 0 || fwrite(v.data(), sizeof(T), n, f) == n); }
+template <class T> bool rd(FILE* f, std::vector<T>& v) { uint64_t n; if (fread(&n, 8, 1, f) != 1) return false; v.resize(n); return n == 0 || fread(v.data(), sizeof(T), n, f) == n; }
+}  // namespace
+
+bool save_gsx(const std::string& prefix, const HostIndex& ix, std::string& err) {
+    FILE* f = fopen((prefix + ".gsx").c_str(), "wb");
+    if (!f) { err = "cannot write " + prefix + ".gsx"; return false; }
+    bool ok = fwrite(kMagic, 8, 1, f) == 1;
+    for (int s = 0; s < 2 && ok; s++) {
+        const HostStrand& h = ix.st[s];
+        ok = fwrite(&h.n, 8, 1, f) == 1 && fwrite(&h.sa_shift, 4, 1, f) == 1 && fwrite(h.C, 4, 5, f) == 5 && wr(f, h.blocks) &&
+             wr(f, h.sa_samples) && wr(f, h.exc_rows) && wr(f, h.exc_lf) && wr(f, h.n_rows);
+    }
+    fclose(f);
+    if (!ok) { err = "short write to " + prefix + ".gsx"; return false; }
+    std::ofstream gs(prefix + ".gs");                                     // seq_io.cxx:112-122
+    for (size_t i = 0; i < ix.chr_names.size(); i++) gs << ix.chr_names[i] << "\n" << ix.chr_lens[i] << "\n";
+    return true;
+}
+
+bool load_gsx(const std::string& prefix, HostIndex& ix, std::string& err) {
+    FILE* f = fopen((prefix + ".gsx").c_str(), "rb");
+    if (!f) { err = "cannot open " + prefix + ".gsx"; return false; }
+    char magic[8]; bool ok = fread(magic, 8, 1, f) == 1 && memcmp(magic, kMagic, 8) == 0;
+    for (int s = 0; s < 2 && ok; s++) {
+        HostStrand& h = ix.st[s];
+        ok = fread(&h.n, 8, 1, f) == 1 && fread(&h.sa_shift, 4, 1, f) == 1 && fread(h.C, 4, 5, f) == 5 && rd(f, h.blocks) &&
+             rd(f, h.sa_samples) && rd(f, h.exc_rows) && rd(f, h.exc_lf) && rd(f, h.n_rows);
+    }
+    fclose(f);
+    if (!ok) { err = "malformed " + prefix + ".gsx"; return false; }
+    return load_genome_structure(prefix + ".gs", ix, err);
+}
+
+}  // namespace gsx

@@ -1,0 +1,462 @@
+// gsx_kernels.cu -- sm_100a kernels of the off-target enumeration path.
+//
+//   search_kernel   backtracking backward search (reference include/genomics/index.hpp:125-398), all guides, both
+//                   strand indexes.  Persistent grid; every WARP is an independent worker with its own search stack
+//                   (a ring buffer in shared memory, spilling to global memory), one search-tree node per lane per
+//                   iteration, children compacted onto the stack with ballot/popc.  Each occurrence lookup is one
+//                   32-byte LDG.E.256 of an OccBlock; a node needs the blocks of rows sp and ep+1 (one load if both
+//                   fall into the same block).  HBM-random-access bound: no tensor cores, no TMA (32 B gathers).
+//   arrange_*       group the emitted SA intervals per guide, order them as the reference's std::set does,
+//                   drop duplicates, expand to SA rows (reference include/genomics/process.hpp:100-115).
+//   locate_score    LF walk to an SA sample per hit (sdsl csa_wt.hpp:333-346), absolute coordinate, chromosome
+//                   resolution (src/genomics/structures.cxx:7-52), CFD (include/genomics/printer.hpp:98-113).
+//   specificity     per-guide float32 reduction in reference order (printer.hpp:244-300 / 115-170).
+#include "gsx_kernels.h"
+#include "gsx_core.h"
+#include "cfd_tables.h"
+#include <cuda_runtime.h>
+
+namespace gsx {
+
+__constant__ double c_cfd_mm[4 * 4 * 20];
+__constant__ double c_cfd_pam[4 * 4];
+
+cudaError_t upload_cfd_tables() {
+    cudaError_t e = cudaMemcpyToSymbol(c_cfd_mm, GSX_CFD_MM, sizeof(c_cfd_mm));
+    if (e != cudaSuccess) return e;
+    return cudaMemcpyToSymbol(c_cfd_pam, GSX_CFD_PAM, sizeof(c_cfd_pam));
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// search
+// ---------------------------------------------------------------------------------------------------------
+struct Blk { uint32_t c0, c1, c2, c3; uint64_t hi, lo; };
+
+__device__ __forceinline__ Blk ld_block(const OccBlock* p) {
+    Blk b; uint32_t h0, h1, l0, l1;
+    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(b.c0), "=r"(b.c1), "=r"(b.c2), "=r"(b.c3), "=r"(h0), "=r"(h1), "=r"(l0), "=r"(l1)
+                 : "l"(p));
+    b.hi = ((uint64_t)h1 << 32) | h0; b.lo = ((uint64_t)l1 << 32) | l0;
+    return b;
+}
+
+template <bool WIDE, int CAP>
+struct WarpRing {
+    uint32_t* sp; uint32_t* ep; uint32_t* meta; uint32_t* task; uint64_t* klo; uint64_t* khi;
+    __device__ __forceinline__ void store(uint32_t slot, const Node& n) {
+        slot &= (CAP - 1);
+        sp[slot] = n.sp; ep[slot] = n.ep; meta[slot] = n.meta; task[slot] = n.task; klo[slot] = n.key_lo;
+        if (WIDE) khi[slot] = n.key_hi;
+    }
+    __device__ __forceinline__ void load(uint32_t slot, Node& n) const {
+        slot &= (CAP - 1);
+        n.sp = sp[slot]; n.ep = ep[slot]; n.meta = meta[slot]; n.task = task[slot]; n.key_lo = klo[slot];
+        n.key_hi = WIDE ? khi[slot] : 0ull;
+    }
+};
+
+template <bool WIDE> __host__ __device__ constexpr int node_words() { return WIDE ? 8 : 6; }
+
+// global spill area of one warp: SoA, `cap` nodes
+template <bool WIDE>
+struct SpillView {
+    uint32_t* base; uint32_t cap;
+    __device__ __forceinline__ void store(uint32_t i, const Node& n) {
+        base[i] = n.sp; base[cap + i] = n.ep; base[2 * cap + i] = n.meta; base[3 * cap + i] = n.task;
+        reinterpret_cast<uint64_t*>(base + 4 * (size_t)cap)[i] = n.key_lo;
+        if (WIDE) reinterpret_cast<uint64_t*>(base + 6 * (size_t)cap)[i] = n.key_hi;
+    }
+    __device__ __forceinline__ void load(uint32_t i, Node& n) const {
+        n.sp = base[i]; n.ep = base[cap + i]; n.meta = base[2 * cap + i]; n.task = base[3 * cap + i];
+        n.key_lo = reinterpret_cast<const uint64_t*>(base + 4 * (size_t)cap)[i];
+        n.key_hi = WIDE ? reinterpret_cast<const uint64_t*>(base + 6 * (size_t)cap)[i] : 0ull;
+    }
+};
+
+template <bool WIDE, int WARPS, int CAP, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) search_kernel(SearchArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ PamSet s_pams[kMaxPamSets];
+    __shared__ DevStrand s_st[2];       // indexed per lane by strand: kept out of the (statically indexed) param bank
+    for (int i = threadIdx.x; i < (int)(sizeof(PamSet) * kMaxPamSets / 4); i += blockDim.x)
+        reinterpret_cast<uint32_t*>(s_pams)[i] = reinterpret_cast<const uint32_t*>(a.pamsets)[i];
+    if (threadIdx.x == 0) { s_st[0] = a.st[0]; s_st[1] = a.st[1]; }
+    __syncthreads();
+
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint32_t FULL = 0xffffffffu;
+    constexpr int WORDS = node_words<WIDE>();
+
+    WarpRing<WIDE, CAP> ring;
+    {
+        unsigned char* base = smem_raw + (size_t)warp * CAP * WORDS * 4;
+        ring.klo = reinterpret_cast<uint64_t*>(base); base += CAP * 8;
+        ring.khi = reinterpret_cast<uint64_t*>(base); if (WIDE) base += CAP * 8;
+        ring.sp = reinterpret_cast<uint32_t*>(base); base += CAP * 4;
+        ring.ep = reinterpret_cast<uint32_t*>(base); base += CAP * 4;
+        ring.meta = reinterpret_cast<uint32_t*>(base); base += CAP * 4;
+        ring.task = reinterpret_cast<uint32_t*>(base);
+    }
+    const uint32_t gwarp = blockIdx.x * WARPS + warp;
+    SpillView<WIDE> spill;
+    spill.cap = a.p.spill_cap;
+    spill.base = a.spill + (size_t)gwarp * a.p.spill_cap * WORDS;
+
+    uint32_t head = 0, count = 0, spill_count = 0;      // warp-uniform
+    bool tasks_remain = true;                           // warp-uniform
+    bool has = false;
+    Node nd; nd.sp = nd.ep = nd.meta = nd.task = 0; nd.key_lo = nd.key_hi = 0;
+    unsigned long long n_nodes = 0, n_lookups = 0, n_spilled = 0;
+    const bool any_n = (a.st[0].n_nrows | a.st[1].n_nrows) != 0;
+    uint32_t iters = 0;
+
+    for (;;) {
+        if (++iters > a.max_iters) { if (lane == 0) atomicOr(a.error_flag, GSX_KERR_WATCHDOG); break; }
+        // ---- 1. give idle lanes a node ------------------------------------------------------------------
+        uint32_t need_mask = __ballot_sync(FULL, !has);
+        uint32_t n_need = __popc(need_mask);
+        if (n_need) {
+            if (count < n_need && spill_count > 0) {                 // bring back the most recently spilled chunk
+                uint32_t take = spill_count < 64u ? spill_count : 64u;
+                for (uint32_t j = lane; j < take; j += 32) {
+                    Node t; spill.load(spill_count - take + j, t);
+                    ring.store(head + count + j, t);
+                }
+                __syncwarp();
+                count += take; spill_count -= take;
+            }
+            if (count < n_need && tasks_remain) {                    // start one more (guide, strand) task
+                uint32_t t = 0;
+                if (lane == 0) t = atomicAdd(a.task_counter, 1u);
+                t = __shfl_sync(FULL, t, 0);
+                if (t >= a.p.n_tasks) tasks_remain = false;
+                else if (!(a.skip && a.skip[t >> 1])) {
+                    if (lane == 0) {
+                        Node r; r.sp = 0; r.ep = s_st[t & 1u].n - 1; r.meta = 0; r.task = t; r.key_lo = r.key_hi = 0;
+                        ring.store(head + count, r);
+                    }
+                    __syncwarp();
+                    count += 1;
+                }
+            }
+            uint32_t take = count < n_need ? count : n_need;
+            uint32_t rank = __popc(need_mask & lt_mask);
+            if (!has && rank < take) { ring.load(head + count - 1 - rank, nd); has = true; }
+            __syncwarp();
+            count -= take;
+        }
+        uint32_t act = __ballot_sync(FULL, has);
+        if (act == 0) {
+            if (count == 0 && spill_count == 0 && !tasks_remain) break;
+            continue;
+        }
+        // ---- 2. occurrence lookups -----------------------------------------------------------------------
+        uint32_t os[4] = {0, 0, 0, 0}, oe[4] = {0, 0, 0, 0};
+        const uint32_t strand = nd.task & 1u;
+        const DevStrand& st = s_st[strand];
+        if (has) {
+            const OccBlock* blocks = st.blocks;
+            uint32_t bs = nd.sp >> 6, be = (nd.ep + 1u) >> 6;
+            Blk B0 = ld_block(blocks + bs);
+            Blk B1 = B0;
+            if (be != bs) B1 = ld_block(blocks + be);
+            n_nodes++; n_lookups += (be != bs) ? 2 : 1;
+            uint32_t c0[4] = {B0.c0, B0.c1, B0.c2, B0.c3};
+            block_occ(st, c0, B0.hi, B0.lo, nd.sp, os);
+            uint32_t c1[4] = {B1.c0, B1.c1, B1.c2, B1.c3};
+            block_occ(st, c1, B1.hi, B1.lo, nd.ep + 1u, oe);
+        }
+        // ---- 3. children ---------------------------------------------------------------------------------
+        ExpandCtx cx;
+        const GuideRec* g = a.guides + (nd.task >> 1);
+        cx.st = &st; cx.g = g; cx.ps = &s_pams[has ? g->pamset : 0]; cx.M = a.p.M; cx.R = a.p.R; cx.D = a.p.D;
+        Node keep; bool has_keep = false;
+        keep = nd;
+#pragma unroll
+        for (int cand = 0; cand < CAND_END; cand++) {
+            if (!WIDE && cand > CAND_FORK) break;
+            if (cand == CAND_LITN && !any_n) continue;
+            if (cand == CAND_FORK && a.max_pams <= 1) continue;
+            Node ch; bool emit = false;
+            bool valid = has && make_child<WIDE>(cand, nd, cx, os, oe, ch, emit);
+            // finished alignments -> match arena (or per-guide width counter in the threshold pass)
+            uint32_t emask = __ballot_sync(FULL, valid && emit);
+            if (emask) {
+                if (a.p.counting) {
+                    if (valid && emit) atomicAdd(a.guide_count + (ch.task >> 1), (unsigned long long)(ch.ep - ch.sp + 1));
+                } else {
+                    uint32_t base = 0;
+                    int leader = __ffs(emask) - 1;
+                    if ((int)lane == leader) base = atomicAdd(a.match_count, (uint32_t)__popc(emask));
+                    base = __shfl_sync(FULL, base, leader);
+                    if (valid && emit) {
+                        uint32_t slot = base + __popc(emask & lt_mask);
+                        if (slot < a.p.match_cap) {
+                            MatchRec m; fill_match(m, ch, WIDE);
+                            a.matches[slot] = m;
+                            atomicAdd(a.guide_nmatch + (ch.task >> 1), 1u);
+                        } else atomicOr(a.error_flag, GSX_KERR_MATCH_OVERFLOW);
+                    }
+                }
+            }
+            bool push = valid && !emit;
+            if (push && !has_keep) { keep = ch; has_keep = true; push = false; }     // continue depth-first in registers
+            uint32_t pmask = __ballot_sync(FULL, push);
+            if (pmask) {
+                uint32_t np = __popc(pmask);
+                if (count + np > (uint32_t)CAP) {                                     // spill the 64 oldest nodes
+                    if (spill_count + 64u > spill.cap) {
+                        if (lane == 0) atomicOr(a.error_flag, GSX_KERR_SPILL_OVERFLOW);
+                    } else {
+                        for (uint32_t j = lane; j < 64u; j += 32) { Node t; ring.load(head + j, t); spill.store(spill_count + j, t); }
+                        spill_count += 64u; n_spilled += (lane == 0) ? 64 : 0;
+                    }
+                    __syncwarp();
+                    head = (head + 64u) & (CAP - 1); count -= 64u;
+                }
+                if (push) ring.store(head + count + __popc(pmask & lt_mask), ch);
+                __syncwarp();
+                count += np;
+            }
+        }
+        has = has_keep;
+        nd = keep;
+    }
+    // ---- statistics ----------------------------------------------------------------------------------------
+    for (int o = 16; o; o >>= 1) {
+        n_nodes += __shfl_xor_sync(FULL, n_nodes, o);
+        n_lookups += __shfl_xor_sync(FULL, n_lookups, o);
+        n_spilled += __shfl_xor_sync(FULL, n_spilled, o);
+    }
+    if (lane == 0) {
+        atomicAdd(a.stats + 0, n_nodes); atomicAdd(a.stats + 1, n_lookups); atomicAdd(a.stats + 2, n_spilled);
+    }
+}
+
+template <bool WIDE, int WARPS, int CAP, int MINB>
+static cudaError_t launch_search_t(const SearchArgs& a, int sm_count, cudaStream_t s) {
+    size_t smem = (size_t)WARPS * CAP * node_words<WIDE>() * 4;
+    int blocks = sm_count * MINB;
+    auto k = search_kernel<WIDE, WARPS, CAP, MINB>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k<<<blocks, WARPS * 32, smem, s>>>(a);
+    return cudaGetLastError();
+}
+
+// variant -> (warps per CTA, ring capacity, CTAs per SM); the CTA count per SM is enforced through __launch_bounds__
+#define GSX_SEARCH_VARIANTS(X) \
+    X(false, 0, 8, 256, 3) /* 768 thr/SM, 144 KB smem */ \
+    X(false, 1, 8, 256, 4) /* 1024 thr/SM (<= 64 regs) */ \
+    X(false, 2, 8, 128, 6) /* 1536 thr/SM (<= 40 regs) */ \
+    X(false, 3, 8, 512, 2) /* 512 thr/SM, deep rings */ \
+    X(false, 4, 4, 256, 8) /* 1024 thr/SM in 4-warp CTAs */ \
+    X(true, 0, 8, 256, 2)  /* 512 thr/SM, 128 KB smem */ \
+    X(true, 1, 8, 128, 4)  /* 1024 thr/SM */
+
+cudaError_t launch_search(const SearchArgs& a, bool wide, int variant, int sm_count, cudaStream_t s, int* warps_total) {
+#define X(W, V, WARPS, CAP, MINB) \
+    if (wide == W && variant == V) { if (warps_total) *warps_total = sm_count * MINB * WARPS; return launch_search_t<W, WARPS, CAP, MINB>(a, sm_count, s); }
+    GSX_SEARCH_VARIANTS(X)
+#undef X
+    return cudaErrorInvalidValue;
+}
+
+int search_grid_warps(bool wide, int variant, int sm_count) {
+#define X(W, V, WARPS, CAP, MINB) if (wide == W && variant == V) return sm_count * MINB * WARPS;
+    GSX_SEARCH_VARIANTS(X)
+#undef X
+    return -1;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// arrange: group by guide, order, de-duplicate, expand
+// ---------------------------------------------------------------------------------------------------------
+// exclusive scan of in[0..n) into out[0..n], out[n] = total; one block
+__global__ void scan_u32_kernel(const uint32_t* in, uint32_t* out, uint32_t n) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (uint32_t base = 0; base < n; base += blockDim.x) {
+        uint32_t i = base + threadIdx.x;
+        uint32_t v = i < n ? in[i] : 0, x = v;
+        for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= (uint32_t)o) x += y; }
+        if (lane == 31) s_warp[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = lane < nw ? s_warp[lane] : 0, z = w;
+            for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, z, o); if (lane >= (uint32_t)o) z += y; }
+            s_warp[lane] = z - w;
+        }
+        __syncthreads();
+        uint32_t carry = s_carry;
+        if (i < n) out[i] = carry + s_warp[warp] + x - v;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) s_carry = carry + s_warp[warp] + x;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[n] = s_carry;
+}
+
+__global__ void scatter_matches_kernel(const MatchRec* matches, uint32_t n_matches, const uint32_t* guide_moff,
+                                       uint32_t* cursor, uint32_t* by_guide) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_matches; i += gridDim.x * blockDim.x) {
+        uint32_t g = matches[i].task >> 1;
+        by_guide[guide_moff[g] + atomicAdd(cursor + g, 1u)] = i;
+    }
+}
+
+// one warp per guide: rank sort of its matches (typically ~10), duplicates (same bucket and string) die
+__global__ void order_matches_kernel(const MatchRec* matches, const uint32_t* guide_moff, const uint32_t* by_guide,
+                                     uint32_t n_guides, uint32_t n_dist, uint32_t* sorted, uint32_t* sorted_off,
+                                     uint32_t* guide_nhits, uint32_t* count_by_distance) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t g = wid; g < n_guides; g += nw) {
+        const uint32_t b = guide_moff[g], s = guide_moff[g + 1] - b;
+        for (uint32_t i = lane; i < s; i += 32) {
+            const uint32_t mi = by_guide[b + i];
+            const MatchRec x = matches[mi];
+            uint32_t rank = 0; bool dup = false;
+            for (uint32_t j = 0; j < s; j++) {
+                const uint32_t mj = by_guide[b + j];
+                if (mj == mi) continue;
+                int c = match_cmp(matches[mj], x);
+                if (c < 0) rank++;
+                else if (c == 0) { if (mj < mi) { rank++; dup = true; } }
+            }
+            sorted[b + rank] = dup ? (mi | 0x80000000u) : mi;
+        }
+        __syncwarp();
+        // hit offsets in sorted order
+        uint32_t running = 0;
+        for (uint32_t base = 0; base < s; base += 32) {
+            uint32_t i = base + lane;
+            uint32_t w = 0, d = 0;
+            if (i < s) { uint32_t e = sorted[b + i]; if (!(e & 0x80000000u)) { w = matches[e].width; d = matches[e].info & 0xffu; } }
+            uint32_t x = w;
+            for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= (uint32_t)o) x += y; }
+            if (i < s) sorted_off[b + i] = running + x - w;
+            if (w && d < n_dist) atomicAdd(count_by_distance + (size_t)g * n_dist + d, w);
+            running += __shfl_sync(0xffffffffu, x, 31);
+        }
+        if (lane == 0) guide_nhits[g] = running;
+        __syncwarp();
+    }
+}
+
+// one warp per sorted match: write its rows
+__global__ void expand_hits_kernel(const MatchRec* matches, const uint32_t* guide_moff, const uint32_t* sorted,
+                                   const uint32_t* sorted_off, const uint32_t* guide_hoff, uint32_t n_guides,
+                                   uint32_t n_sorted, uint32_t* hit_match, uint32_t* hit_row, uint32_t* hit_guide) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t i = wid; i < n_sorted; i += nw) {
+        uint32_t e = sorted[i];
+        if (e & 0x80000000u) continue;
+        const uint32_t g = matches[e].task >> 1;
+        const uint32_t base = guide_hoff[g] + sorted_off[i];
+        const uint32_t sp = matches[e].sp, w = matches[e].width;
+        for (uint32_t r = lane; r < w; r += 32) { hit_match[base + r] = e; hit_row[base + r] = sp + r; hit_guide[base + r] = g; }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// locate + coordinates + CFD, one thread per hit
+// ---------------------------------------------------------------------------------------------------------
+struct DevBlockLoader {
+    __device__ __forceinline__ void operator()(const OccBlock* p, uint32_t c[4], uint64_t& hi, uint64_t& lo) const {
+        Blk B = ld_block(p); c[0] = B.c0; c[1] = B.c1; c[2] = B.c2; c[3] = B.c3; hi = B.hi; lo = B.lo;
+    }
+};
+__device__ __forceinline__ uint32_t locate_row(const DevStrand& st, uint32_t row, uint32_t* steps) {
+    return locate_row_t(st, row, steps, DevBlockLoader());
+}
+
+__global__ void locate_score_kernel(LocateArgs a) {
+    __shared__ DevStrand s_st[2];
+    if (threadIdx.x == 0) { s_st[0] = a.st[0]; s_st[1] = a.st[1]; }
+    __syncthreads();
+    uint32_t steps = 0;
+    for (uint32_t h = blockIdx.x * blockDim.x + threadIdx.x; h < a.n_hits; h += gridDim.x * blockDim.x) {
+        const MatchRec m = a.matches[a.hit_match[h]];
+        uint32_t sa = locate_row(s_st[m.task & 1u], a.hit_row[h], &steps);
+        score_hit(a, h, m, sa, c_cfd_mm, c_cfd_pam);
+    }
+    for (int o = 16; o; o >>= 1) steps += __shfl_xor_sync(0xffffffffu, steps, o);
+    if ((threadIdx.x & 31) == 0 && steps) atomicAdd(a.stats + 3, (unsigned long long)steps);
+}
+
+// one thread per guide: float32 running sum in the reference's output order
+__global__ void specificity_kernel(SpecArgs a) {
+    for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < a.n_guides; g += gridDim.x * blockDim.x) guide_specificity(a, g);
+}
+
+__global__ void threshold_kernel(const unsigned long long* guide_count, uint8_t* dropped, uint32_t n_guides) {
+    for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < n_guides; g += gridDim.x * blockDim.x)
+        dropped[g] = guide_count[g] > 1ull ? 1 : 0;                               // process.hpp:68,70
+}
+
+// primitive queries for parity tests
+__global__ void rank_query_kernel(DevStrand st, const uint32_t* rows, const uint8_t* syms, uint32_t n, uint32_t* out) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        uint32_t row = rows[i], s = syms[i], r = 0;
+        if (s < 4) {
+            Blk B = ld_block(st.blocks + (row >> 6));
+            uint32_t c[4] = {B.c0, B.c1, B.c2, B.c3}, o[4];
+            block_occ(st, c, B.hi, B.lo, row, o);
+            r = o[s];
+        } else if (s == SYM_N) r = rank_n(st, row);
+        out[i] = r;
+    }
+}
+__global__ void locate_query_kernel(DevStrand st, const uint32_t* rows, uint32_t n, uint32_t* out) {
+    uint32_t steps = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = locate_row(st, rows[i], &steps);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host-side launchers
+// ---------------------------------------------------------------------------------------------------------
+static inline int grid_for(uint32_t n, int threads, int cap) { long b = ((long)n + threads - 1) / threads; if (b < 1) b = 1; if (b > cap) b = cap; return (int)b; }
+
+cudaError_t launch_scan(const uint32_t* in, uint32_t* out, uint32_t n, cudaStream_t s) {
+    scan_u32_kernel<<<1, 1024, 0, s>>>(in, out, n); return cudaGetLastError();
+}
+cudaError_t launch_scatter(const MatchRec* m, uint32_t n, const uint32_t* moff, uint32_t* cursor, uint32_t* by_guide, cudaStream_t s) {
+    if (!n) return cudaSuccess;
+    scatter_matches_kernel<<<grid_for(n, 256, 148 * 8), 256, 0, s>>>(m, n, moff, cursor, by_guide); return cudaGetLastError();
+}
+cudaError_t launch_order(const MatchRec* m, const uint32_t* moff, const uint32_t* by_guide, uint32_t n_guides, uint32_t n_dist,
+                         uint32_t* sorted, uint32_t* sorted_off, uint32_t* nhits, uint32_t* cbd, cudaStream_t s) {
+    order_matches_kernel<<<grid_for(n_guides * 32u, 256, 148 * 8), 256, 0, s>>>(m, moff, by_guide, n_guides, n_dist, sorted, sorted_off, nhits, cbd);
+    return cudaGetLastError();
+}
+cudaError_t launch_expand(const MatchRec* m, const uint32_t* moff, const uint32_t* sorted, const uint32_t* sorted_off, const uint32_t* hoff,
+                          uint32_t n_guides, uint32_t n_sorted, uint32_t* hit_match, uint32_t* hit_row, uint32_t* hit_guide, cudaStream_t s) {
+    if (!n_sorted) return cudaSuccess;
+    expand_hits_kernel<<<grid_for(n_sorted * 32u, 256, 148 * 8), 256, 0, s>>>(m, moff, sorted, sorted_off, hoff, n_guides, n_sorted, hit_match, hit_row, hit_guide);
+    return cudaGetLastError();
+}
+cudaError_t launch_locate_score(const LocateArgs& a, cudaStream_t s) {
+    if (!a.n_hits) return cudaSuccess;
+    locate_score_kernel<<<grid_for(a.n_hits, 128, 148 * 16), 128, 0, s>>>(a); return cudaGetLastError();
+}
+cudaError_t launch_specificity(const SpecArgs& a, cudaStream_t s) {
+    specificity_kernel<<<grid_for(a.n_guides, 128, 148 * 8), 128, 0, s>>>(a); return cudaGetLastError();
+}
+cudaError_t launch_threshold(const unsigned long long* gc, uint8_t* dropped, uint32_t n, cudaStream_t s) {
+    threshold_kernel<<<grid_for(n, 256, 148 * 4), 256, 0, s>>>(gc, dropped, n); return cudaGetLastError();
+}
+cudaError_t launch_rank_query(const DevStrand& st, const uint32_t* rows, const uint8_t* syms, uint32_t n, uint32_t* out, cudaStream_t s) {
+    rank_query_kernel<<<grid_for(n, 256, 148 * 8), 256, 0, s>>>(st, rows, syms, n, out); return cudaGetLastError();
+}
+cudaError_t launch_locate_query(const DevStrand& st, const uint32_t* rows, uint32_t n, uint32_t* out, cudaStream_t s) {
+    locate_query_kernel<<<grid_for(n, 128, 148 * 16), 128, 0, s>>>(st, rows, n, out); return cudaGetLastError();
+}
+
+}  // namespace gsx

@@ -1,0 +1,73 @@
+// gsx_kernels.h -- launch interface between the C-ABI host code and the CUDA kernels.
+#ifndef GSX_KERNELS_H
+#define GSX_KERNELS_H
+#include "gsx_types.h"
+#include <cuda_runtime.h>
+
+namespace gsx {
+
+enum : uint32_t {
+    GSX_KERR_MATCH_OVERFLOW = 1,   // match arena too small: host retries with a larger one
+    GSX_KERR_SPILL_OVERFLOW = 2,   // a warp's global spill stack is full: host retries with a larger one
+    GSX_KERR_WATCHDOG = 4          // iteration cap hit (never expected)
+};
+
+struct SearchArgs {
+    DevStrand st[2];
+    const GuideRec* guides;
+    const PamSet* pamsets;             // kMaxPamSets entries
+    SearchParams p;
+    const uint8_t* skip;               // per guide: 1 = do not search (dropped by the threshold pass); may be null
+    MatchRec* matches;
+    uint32_t* match_count;
+    uint32_t* guide_nmatch;            // per guide
+    unsigned long long* guide_count;   // per guide, counting pass only
+    uint32_t* task_counter;
+    uint32_t* spill;                   // warps_total * spill_cap * node_words u32
+    unsigned long long* stats;         // [0] nodes [1] lookups [2] spilled nodes [3] LF steps
+    uint32_t* error_flag;
+    uint32_t max_iters;
+    uint32_t max_pams;
+};
+
+struct LocateArgs {
+    DevStrand st[2];
+    const MatchRec* matches;
+    const GuideRec* guides;
+    const PamSet* pamsets;
+    const Chrom* chroms;
+    const uint32_t* hit_match;
+    const uint32_t* hit_row;
+    uint32_t n_hits, n_chr, wide;
+    uint64_t genome_length;
+    int64_t* abs_pos; int32_t* chr; uint32_t* pos1; uint8_t* strand; uint8_t* distance; uint8_t* dna; uint8_t* rna;
+    uint8_t* index_id; float* cfd; uint8_t* flags;
+    unsigned long long* stats;
+};
+
+struct SpecArgs {
+    const uint32_t* guide_hoff;        // n_guides + 1
+    const uint32_t* count_by_distance;
+    const int32_t* chr; const float* cfd; const uint8_t* flags;
+    uint8_t* counted; float* specificity; uint8_t* perfect;
+    uint32_t n_guides, n_dist, sam_rule;
+    int64_t max_off_targets;
+};
+
+cudaError_t upload_cfd_tables();
+int search_grid_warps(bool wide, int variant, int sm_count);
+cudaError_t launch_search(const SearchArgs& a, bool wide, int variant, int sm_count, cudaStream_t s, int* warps_total);
+cudaError_t launch_scan(const uint32_t* in, uint32_t* out, uint32_t n, cudaStream_t s);
+cudaError_t launch_scatter(const MatchRec* m, uint32_t n, const uint32_t* moff, uint32_t* cursor, uint32_t* by_guide, cudaStream_t s);
+cudaError_t launch_order(const MatchRec* m, const uint32_t* moff, const uint32_t* by_guide, uint32_t n_guides, uint32_t n_dist,
+                         uint32_t* sorted, uint32_t* sorted_off, uint32_t* nhits, uint32_t* cbd, cudaStream_t s);
+cudaError_t launch_expand(const MatchRec* m, const uint32_t* moff, const uint32_t* sorted, const uint32_t* sorted_off, const uint32_t* hoff,
+                          uint32_t n_guides, uint32_t n_sorted, uint32_t* hit_match, uint32_t* hit_row, uint32_t* hit_guide, cudaStream_t s);
+cudaError_t launch_locate_score(const LocateArgs& a, cudaStream_t s);
+cudaError_t launch_specificity(const SpecArgs& a, cudaStream_t s);
+cudaError_t launch_threshold(const unsigned long long* gc, uint8_t* dropped, uint32_t n, cudaStream_t s);
+cudaError_t launch_rank_query(const DevStrand& st, const uint32_t* rows, const uint8_t* syms, uint32_t n, uint32_t* out, cudaStream_t s);
+cudaError_t launch_locate_query(const DevStrand& st, const uint32_t* rows, uint32_t n, uint32_t* out, cudaStream_t s);
+
+}  // namespace gsx
+#endif

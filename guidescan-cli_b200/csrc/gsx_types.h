@@ -1,0 +1,105 @@
+// gsx_types.h -- data layout shared by host code and CUDA kernels.
+//
+// GPU index layout (per strand index; replaces sdsl::csa_wt<wt_huff<>,64,8192>, reference src/guidescan.cxx:24-27):
+//   * OccBlock[n/64 + 1]: one 32-byte sector per 64 BWT rows = 4 x u32 occurrence checkpoints (A,C,G,T before the
+//     block) + the 64 rows' 2-bit symbols as two bit planes.  One occurrence lookup = ONE aligned 32 B load
+//     (LDG.E.256), against 4-6 dependent cache lines in wt_pc::rank (sdsl wt_pc.hpp:360-384).
+//   * rows whose BWT symbol is not A/C/G/T ('$' sentinel row, genome N / IUPAC) are stored as code 0 in the planes
+//     and listed in a sorted exception table; occ(A) is corrected from it, so rank stays exact.
+//   * SA samples: SA[row] for every row that is a multiple of 2^sa_shift (reference density: 64 rows).
+#ifndef GSX_TYPES_H
+#define GSX_TYPES_H
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define GSX_HD __host__ __device__ __forceinline__
+#else
+#define GSX_HD inline
+#endif
+
+namespace gsx {
+
+constexpr int kMaxQ = 32;          // protospacer length limit
+constexpr int kMaxPamLen = 8;
+constexpr int kMaxPams = 8;        // alt PAMs + the guide's own
+constexpr int kMaxPamSets = 16;    // distinct (pam column value) groups per call
+constexpr int kMaxDist = 8;        // mismatches <= 7
+
+// symbol codes: 0..3 = A,C,G,T ; 4 = N ; 5 = anything else (never matches)
+enum : uint8_t { SYM_A = 0, SYM_C = 1, SYM_G = 2, SYM_T = 3, SYM_N = 4, SYM_X = 5 };
+
+struct alignas(32) OccBlock {
+    uint32_t cnt[4];   // occurrences of A,C,G,T in BWT[0, 64*b)
+    uint64_t hi;       // bit j = high bit of the 2-bit code of row 64*b + j
+    uint64_t lo;       // bit j = low bit
+};
+
+struct DevStrand {
+    const OccBlock* blocks;
+    const uint32_t* sa_samples;    // SA[k << sa_shift]
+    const uint32_t* exc_rows;      // sorted rows whose BWT symbol is not ACGT
+    const uint32_t* exc_lf;        // LF target of each exception row
+    const uint32_t* n_rows;        // sorted rows whose BWT symbol is 'N'
+    uint32_t n;                    // number of rows = genome length + 1
+    uint32_t n_exc;
+    uint32_t n_nrows;
+    uint32_t sa_shift;
+    uint32_t C[5];                 // C[A],C[C],C[G],C[T],C[N]: rows whose suffix starts with a smaller symbol
+    uint32_t exc_lo, exc_hi;       // first / last exception row (fast reject)
+};
+
+struct GuideRec {                  // 80 bytes
+    uint8_t q[kMaxQ];              // symbol code consumed at level l (consumption order)
+    char    seq[kMaxQ];            // k.sequence as given (for CFD)
+    uint8_t qlen;
+    uint8_t pamset;
+    uint8_t seqlen;
+    uint8_t pad[13];
+};
+
+struct PamSet {
+    uint8_t n_pams;
+    uint8_t plen[kMaxPams];
+    uint8_t sym[kMaxPams][kMaxPamLen];   // consumption order; SYM_N = wildcard
+    uint8_t kpam_len;                    // length of the guide's own pam column (coordinates use it: structures.cxx:36,41)
+    uint8_t pad[6];
+};
+
+struct SearchParams {
+    uint32_t M, R, D;              // max mismatches / RNA bulges / DNA bulges (max_bulge_size is 1)
+    uint32_t counting;             // 1 = threshold prefilter pass: only add interval widths per guide
+    uint32_t n_tasks;              // 2 * n_guides  (task = guide * 2 + strand)
+    uint32_t match_cap;
+    uint32_t spill_cap;            // nodes per warp in the global spill stack
+};
+
+// one emitted SA interval (= reference `match`, structures.hpp:33-43)
+struct alignas(8) MatchRec {
+    uint64_t key_hi;               // string sort key (wide form: 4 bits per character, left aligned; narrow: 0)
+    uint64_t key_lo;               // narrow form: base-5 path number
+    uint32_t task;                 // guide * 2 + strand
+    uint32_t sp;
+    uint32_t width;                // ep - sp + 1
+    uint32_t info;                 // mm | dna << 8 | rna << 16 | len << 24
+};
+
+struct Chrom { uint64_t start; uint64_t length; };
+
+// node meta word
+constexpr uint32_t META_LVL_MASK = 63u;           // bits 0..5   guide positions + PAM characters consumed
+constexpr uint32_t META_MM_SHIFT = 6;             // bits 6..8
+constexpr uint32_t META_PAM_SHIFT = 9;            // bits 9..11
+constexpr uint32_t META_DNA_SHIFT = 12;           // bits 12..14
+constexpr uint32_t META_RNA_SHIFT = 15;           // bits 15..17
+constexpr uint32_t META_STATE_SHIFT = 18;         // bits 18..19  0 none 1 dna 2 rna
+constexpr uint32_t META_CURR_SHIFT = 20;          // bit 20
+
+struct Node {
+    uint32_t sp, ep;
+    uint64_t key_lo, key_hi;
+    uint32_t meta;
+    uint32_t task;
+};
+
+}  // namespace gsx
+#endif

@@ -57,3 +57,40 @@ def canonical_blocks(text: str, fmt: str):
         key = line.split("\t" if fmt == "sam" else ",", 1)[0]
         blocks.setdefault(key, []).append(line)
     return header, blocks
+
+
+@pytest.fixture(scope="session")
+def golden_index(golden_dir, tmp_path_factory):
+    """{case: index prefix} built by the unmodified reference `guidescan index` (oracle/_ref)."""
+    import oracle as O
+    if not O.have_ref():
+        pytest.skip("oracle/_ref/guidescan not built (needs /root/reference in the build container)")
+    out = {}
+    for case, (fa, _) in golden_dir.items():
+        d = tmp_path_factory.mktemp("idx_" + case)
+        prefix = os.path.join(d, case)
+        O.ref_index(fa, prefix, cwd=str(d))
+        out[case] = prefix
+    return out
+
+
+def variant_cli_args(kw):
+    """golden variant options -> argument list shared by tests/host_core_check and bin/guidescan-style tools"""
+    a = ["-m", str(kw.get("mismatches", 3))]
+    if kw.get("rna_bulges"):
+        a += ["--rna", str(kw["rna_bulges"])]
+    if kw.get("dna_bulges"):
+        a += ["--dna", str(kw["dna_bulges"])]
+    if kw.get("threshold") is not None:
+        a += ["-t", str(kw["threshold"])]
+    if kw.get("start"):
+        a += ["--start"]
+    if kw.get("max_off_targets") is not None:
+        a += ["--max", str(kw["max_off_targets"])]
+    if kw.get("fmt") == "sam":
+        a += ["--sam"]
+    if kw.get("mode") == "succinct":
+        a += ["--succinct"]
+    for p in kw.get("alt_pams", ()):
+        a += ["-a", p]
+    return a

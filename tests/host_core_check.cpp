@@ -1,0 +1,165 @@
+// tests/host_core_check.cpp -- UNIT-TEST HARNESS (not part of the product, never shipped in libgsx.so).
+//
+// Runs the per-node arithmetic that the CUDA kernels are built from (guidescan-cli_b200/csrc/gsx_core.h: occurrence
+// lookup in the 32-byte block layout, child generation, string keys, LF-walk locate, coordinates, CFD, specificity)
+// as a plain sequential depth-first search on the host, over an index laid out by the product's own loader, and
+// writes CSV / SAM through the product's own formatter.  tests/test_host_core.py diffs that text against the
+// reference's golden output.  This pins every piece of device arithmetic on a machine without a GPU; what remains
+// GPU-only (warp stacks, ballots, atomics, arenas) is covered by the -m gpu parity tests.
+//
+// usage: host_core_check <index prefix> <guides.csv> <out> [-m N] [--rna N] [--dna N] [-t N] [--start] [--max N]
+//                        [--sam] [--succinct] [-a PAM]...
+#include "../include/gsx.h"
+#include "../guidescan-cli_b200/csrc/gsx_host.h"
+#include "../guidescan-cli_b200/csrc/gsx_core.h"
+#include "../guidescan-cli_b200/csrc/cfd_tables.h"
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <string>
+#include <vector>
+
+using namespace gsx;
+
+struct HostBlockLoader {
+    void operator()(const OccBlock* p, uint32_t c[4], uint64_t& hi, uint64_t& lo) const { for (int i = 0; i < 4; i++) c[i] = p->cnt[i]; hi = p->hi; lo = p->lo; }
+};
+
+static DevStrand view_of(const HostStrand& h) {
+    DevStrand d{};
+    d.blocks = h.blocks.data(); d.sa_samples = h.sa_samples.data(); d.exc_rows = h.exc_rows.data(); d.exc_lf = h.exc_lf.data();
+    d.n_rows = h.n_rows.data(); d.n = (uint32_t)h.n; d.n_exc = (uint32_t)h.exc_rows.size(); d.n_nrows = (uint32_t)h.n_rows.size();
+    d.sa_shift = h.sa_shift; for (int c = 0; c < 5; c++) d.C[c] = h.C[c];
+    d.exc_lo = h.exc_rows.empty() ? 0xFFFFFFFFu : h.exc_rows.front(); d.exc_hi = h.exc_rows.empty() ? 0 : h.exc_rows.back();
+    return d;
+}
+
+template <bool WIDE>
+static void dfs(const DevStrand st[2], const Prepared& prep, uint32_t task, uint32_t M, uint32_t R, uint32_t D, bool counting,
+                uint64_t* count, std::vector<MatchRec>& out, uint64_t* nodes) {
+    const DevStrand& s = st[task & 1];
+    const GuideRec& g = prep.recs[task >> 1];
+    ExpandCtx cx{&s, &g, &prep.pamsets[g.pamset], M, R, D};
+    std::vector<Node> stack;
+    Node root{}; root.sp = 0; root.ep = s.n - 1; root.task = task;
+    stack.push_back(root);
+    while (!stack.empty()) {
+        Node nd = stack.back(); stack.pop_back();
+        (*nodes)++;
+        uint32_t os[4], oe[4];
+        const OccBlock& b0 = s.blocks[nd.sp >> 6]; const OccBlock& b1 = s.blocks[(nd.ep + 1) >> 6];
+        block_occ(s, b0.cnt, b0.hi, b0.lo, nd.sp, os);
+        block_occ(s, b1.cnt, b1.hi, b1.lo, nd.ep + 1, oe);
+        for (int cand = 0; cand < CAND_END; cand++) {
+            if (!WIDE && cand > CAND_FORK) break;
+            Node ch; bool emit;
+            if (!make_child<WIDE>(cand, nd, cx, os, oe, ch, emit)) continue;
+            if (emit) {
+                if (counting) *count += ch.ep - ch.sp + 1;
+                else { MatchRec m; fill_match(m, ch, WIDE); out.push_back(m); }
+            } else stack.push_back(ch);
+        }
+    }
+}
+
+int main(int argc, char** argv) {
+    if (argc < 4) { fprintf(stderr, "usage: host_core_check <prefix> <guides.csv> <out> [options]\n"); return 2; }
+    std::string prefix = argv[1], guides_csv = argv[2], out_path = argv[3];
+    gsx_params p; gsx_params_default(&p);
+    bool sam = false, complete = true; std::vector<const char*> alts;
+    for (int i = 4; i < argc; i++) {
+        std::string a = argv[i];
+        if (a == "-m") p.mismatches = atoi(argv[++i]); else if (a == "--rna") p.rna_bulges = atoi(argv[++i]);
+        else if (a == "--dna") p.dna_bulges = atoi(argv[++i]); else if (a == "-t") p.threshold = atoi(argv[++i]);
+        else if (a == "--start") p.start = 1; else if (a == "--max") p.max_off_targets = atoll(argv[++i]);
+        else if (a == "--sam") sam = true; else if (a == "--succinct") complete = false; else if (a == "-a") alts.push_back(argv[++i]);
+        else { fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
+    }
+    p.alt_pams = alts.data(); p.n_alt_pams = (uint32_t)alts.size(); p.sam_scoring = sam;
+
+    gsx_index ix; std::string err;
+    if (!load_genome_structure(prefix + ".gs", ix.host, err) || !load_sdsl_strand(prefix + ".forward", ix.host.st[0], err) ||
+        !load_sdsl_strand(prefix + ".reverse", ix.host.st[1], err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
+    uint64_t start = 0;
+    for (auto l : ix.host.chr_lens) { ix.chroms.push_back({start, l}); start += l; }
+    DevStrand st[2] = {view_of(ix.host.st[0]), view_of(ix.host.st[1])};
+
+    // guides file: id,sequence,pam,chromosome,position,sense (fixed column order is enough for the harness)
+    std::vector<std::string> ids, seqs, pams; std::vector<int> pos;
+    { std::ifstream f(guides_csv); std::string line; std::getline(f, line);
+      while (std::getline(f, line)) { if (line.empty()) continue; std::vector<std::string> fl; size_t b = 0;
+        for (;;) { size_t e = line.find(',', b); fl.push_back(line.substr(b, e == std::string::npos ? e : e - b)); if (e == std::string::npos) break; b = e + 1; }
+        ids.push_back(fl[0]); seqs.push_back(fl[1]); pams.push_back(fl[2]); pos.push_back(fl[5] == "+"); } }
+    const size_t n = ids.size();
+    std::vector<gsx_guide> gg(n); std::vector<gsx_guide_row> rows(n);
+    for (size_t i = 0; i < n; i++) { gg[i] = {seqs[i].c_str(), pams[i].c_str()}; rows[i] = {ids[i].c_str(), seqs[i].c_str(), pams[i].c_str(), pos[i]}; }
+    Prepared prep;
+    if (gsx_prepare_guides(gg.data(), n, &p, prep)) { fprintf(stderr, "%s\n", gsx_last_error()); return 1; }
+    const uint32_t n_dist = p.mismatches + 1;
+
+    // ---- search + order + expand (what search_kernel / order_matches_kernel / expand_hits_kernel do) ----------------
+    std::vector<uint8_t> dropped(n, 0);
+    std::vector<MatchRec> sorted; std::vector<uint32_t> hit_match, hit_row, hoff(n + 1, 0), nhits(n, 0), cbd(n * n_dist, 0);
+    uint64_t nodes = 0;
+    for (size_t g = 0; g < n; g++) {
+        hoff[g] = (uint32_t)hit_row.size();
+        if (p.threshold > 0) {
+            uint64_t count = 0; std::vector<MatchRec> dummy;
+            dfs<false>(st, prep, (uint32_t)(2 * g), p.threshold, 0, 0, true, &count, dummy, &nodes);
+            dfs<false>(st, prep, (uint32_t)(2 * g + 1), p.threshold, 0, 0, true, &count, dummy, &nodes);
+            if (count > 1) { dropped[g] = 1; continue; }
+        }
+        std::vector<MatchRec> ms;
+        for (uint32_t s = 0; s < 2; s++) {
+            if (prep.wide) dfs<true>(st, prep, (uint32_t)(2 * g + s), p.mismatches, p.rna_bulges, p.dna_bulges, false, nullptr, ms, &nodes);
+            else dfs<false>(st, prep, (uint32_t)(2 * g + s), p.mismatches, p.rna_bulges, p.dna_bulges, false, nullptr, ms, &nodes);
+        }
+        std::stable_sort(ms.begin(), ms.end(), [](const MatchRec& a, const MatchRec& b) { return match_cmp(a, b) < 0; });
+        for (size_t i = 0; i < ms.size(); i++) {
+            if (i && match_cmp(ms[i - 1], ms[i]) == 0) continue;
+            uint32_t mi = (uint32_t)sorted.size(); sorted.push_back(ms[i]);
+            for (uint32_t r = 0; r < ms[i].width; r++) { hit_match.push_back(mi); hit_row.push_back(ms[i].sp + r); }
+            cbd[g * n_dist + (ms[i].info & 0xff)] += ms[i].width; nhits[g] += ms[i].width;
+        }
+    }
+    hoff[n] = (uint32_t)hit_row.size();
+    const uint32_t nh = hoff[n];
+
+    // ---- locate + score + specificity through the same HD functions the kernels call -------------------------------
+    gsx_result res; HostArrays H; H.n_guides = n; H.n_hits = nh;
+    std::vector<int64_t> abs_pos(nh + 1); std::vector<int32_t> chr(nh + 1); std::vector<uint32_t> pos1(nh + 1);
+    std::vector<uint8_t> strand(nh + 1), distance(nh + 1), dna(nh + 1), rna(nh + 1), index_id(nh + 1), flags(nh + 1), counted(nh + 1, 0), perfect(n + 1);
+    std::vector<float> cfd(nh + 1), spec(n + 1);
+    LocateArgs L{}; L.st[0] = st[0]; L.st[1] = st[1]; L.matches = sorted.data(); L.guides = prep.recs.data(); L.pamsets = prep.pamsets;
+    L.chroms = ix.chroms.data(); L.hit_match = hit_match.data(); L.hit_row = hit_row.data(); L.n_hits = nh; L.n_chr = (uint32_t)ix.chroms.size();
+    L.wide = prep.wide; L.genome_length = ix.host.genome_length; L.abs_pos = abs_pos.data(); L.chr = chr.data(); L.pos1 = pos1.data();
+    L.strand = strand.data(); L.distance = distance.data(); L.dna = dna.data(); L.rna = rna.data(); L.index_id = index_id.data();
+    L.cfd = cfd.data(); L.flags = flags.data();
+    uint32_t steps = 0;
+    for (uint32_t h = 0; h < nh; h++) {
+        const MatchRec& m = sorted[hit_match[h]];
+        uint32_t sa = locate_row_t(st[m.task & 1], hit_row[h], &steps, HostBlockLoader());
+        score_hit(L, h, m, sa, &GSX_CFD_MM[0][0][0], &GSX_CFD_PAM[0][0]);
+    }
+    SpecArgs S{}; S.guide_hoff = hoff.data(); S.count_by_distance = cbd.data(); S.chr = chr.data(); S.cfd = cfd.data(); S.flags = flags.data();
+    S.counted = counted.data(); S.specificity = spec.data(); S.perfect = perfect.data(); S.n_guides = (uint32_t)n; S.n_dist = n_dist;
+    S.sam_rule = sam; S.max_off_targets = p.max_off_targets;
+    for (uint32_t g = 0; g < n; g++) guide_specificity(S, g);
+
+    H.dropped = dropped.data(); H.n_hits_of = nhits.data(); H.hoff = hoff.data(); H.specificity = spec.data(); H.perfect = perfect.data(); H.cbd = cbd.data();
+    H.abs_pos = abs_pos.data(); H.sa_row = hit_row.data(); H.chr = chr.data(); H.pos1 = pos1.data(); H.strand = strand.data(); H.distance = distance.data();
+    H.rna = rna.data(); H.dna = dna.data(); H.index_id = index_id.data(); H.cfd = cfd.data(); H.counted = counted.data(); H.hit_match = hit_match.data();
+    H.matches = sorted.data(); H.n_matches = sorted.size();
+    res.parts.push_back(H); res.part_g0.push_back(0); res.part_h0.push_back(0); res.n_dist = n_dist; res.wide = prep.wide; res.guides = prep.recs;
+    gsx_build_view(&res);
+
+    FILE* out = fopen(out_path.c_str(), "wb");
+    char* buf; size_t len;
+    gsx_format_header(&ix, sam, complete, &buf, &len); fwrite(buf, 1, len, out); gsx_free(buf);
+    if (gsx_format_rows(&ix, &res, rows.data(), 0, n, &p, sam, complete, &buf, &len)) { fprintf(stderr, "format failed\n"); return 1; }
+    fwrite(buf, 1, len, out); gsx_free(buf); fclose(out);
+    fprintf(stderr, "host_core_check: %zu guides, %llu nodes, %u hits, %u LF steps\n", n, (unsigned long long)nodes, nh, steps);
+    return 0;
+}

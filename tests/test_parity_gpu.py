@@ -1,0 +1,119 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path, called through the C ABI (libgsx.so), against the
+reference's golden output and against the CPU oracle on seeded inputs.  Bit-exact text, including float32
+specificity as printed (std::to_string, 6 decimals)."""
+import os
+import random
+
+import pytest
+
+from conftest import golden_cases, golden_manifest, golden_output
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900)]
+
+
+@pytest.fixture(scope="module")
+def gsx():
+    import gsx as g
+    if g.device_count() < 1:
+        pytest.fail("no CUDA device: the product has no CPU path")
+    return g
+
+
+@pytest.fixture(scope="module")
+def gpu_index(gsx, golden_index):
+    cache = {}
+
+    def get(case):
+        if case not in cache:
+            cache[case] = gsx.Index.open(golden_index[case], devices=[0])
+        return cache[case]
+    yield get
+    for ix in cache.values():
+        ix.close()
+
+
+def _params(gsx, kw):
+    return gsx.make_params(mismatches=kw.get("mismatches", 3), rna_bulges=kw.get("rna_bulges", 0), dna_bulges=kw.get("dna_bulges", 0),
+                           threshold=kw.get("threshold", -1) if kw.get("threshold") is not None else -1, start=kw.get("start", False),
+                           max_off_targets=kw.get("max_off_targets", -1) if kw.get("max_off_targets") is not None else -1,
+                           alt_pams=tuple(kw.get("alt_pams", ())))
+
+
+def test_rank_and_locate_match_oracle(gsx, gpu_index, golden_dir):
+    import oracle as O
+    oix = O.Index(golden_dir["g150kN"][0])
+    ix = gpu_index("g150kN")
+    rnd = random.Random(7)
+    n = oix.n
+    for strand in (0, 1):
+        rows = [rnd.randrange(0, n + 1) for _ in range(4000)] + [0, n, 63, 64, 65, n - 1]
+        syms = "".join(rnd.choice("ACGTN") for _ in rows)
+        got = ix.rank(strand, rows, syms)
+        want = [oix.rank_bwt(strand, r, c) for r, c in zip(rows, syms)]
+        assert got.tolist() == want
+        rows = [rnd.randrange(0, n) for _ in range(3000)] + [0, n - 1]
+        assert ix.locate(strand, rows).tolist() == [oix.sa(strand, r) for r in rows]
+
+
+@pytest.mark.parametrize("case,variant", golden_cases())
+def test_gpu_matches_reference_golden(gsx, gpu_index, golden_dir, tmp_path, case, variant):
+    kw = golden_manifest()["cases"][case]["variants"][variant]["opts"]
+    out = os.path.join(tmp_path, "g.out")
+    gpu_index(case).enumerate_file(golden_dir[case][1], out, _params(gsx, kw), fmt=kw.get("fmt", "csv"), mode=kw.get("mode", "complete"))
+    assert open(out, "rb").read() == golden_output(case, variant)
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
+def test_every_search_kernel_variant(gsx, gpu_index, golden_dir, tmp_path, variant, monkeypatch):
+    monkeypatch.setenv("GSX_SEARCH_VARIANT", str(variant))
+    out = os.path.join(tmp_path, "g.out")
+    gpu_index("g200k").enumerate_file(golden_dir["g200k"][1], out, gsx.make_params(mismatches=4, max_off_targets=2))
+    assert open(out, "rb").read() == golden_output("g200k", "m4_max2_csv")
+
+
+def test_tiny_arenas_force_retry_and_spill(gsx, gpu_index, golden_dir, tmp_path, monkeypatch):
+    monkeypatch.setenv("GSX_MATCH_CAP", "64")
+    monkeypatch.setenv("GSX_SPILL_CAP", "64")
+    monkeypatch.setenv("GSX_SEARCH_VARIANT_WIDE", "1")
+    out = os.path.join(tmp_path, "g.out")
+    gpu_index("g200k").enumerate_file(golden_dir["g200k"][1], out, gsx.make_params(mismatches=1, rna_bulges=1, dna_bulges=1))
+    assert open(out, "rb").read() == golden_output("g200k", "m1_r1_d1_csv")
+
+
+@pytest.mark.parametrize("G,n_guides,m", [(2_000_000, 300, 3), (3_000_000, 100, 4)])
+def test_seeded_genome_vs_oracle(gsx, tmp_path, G, n_guides, m):
+    import oracle as O
+    import synth
+    d = str(tmp_path)
+    synth.make_dataset(d, G, 6, n_guides, seed=G % 1000 + m, name="s")
+    fa, gcsv = os.path.join(d, "s.fa"), os.path.join(d, "s.guides.csv")
+    if not O.have_ref():
+        pytest.skip("needs oracle/_ref/guidescan to build the index files")
+    O.ref_index(fa, os.path.join(d, "s"), cwd=d)
+    ix = gsx.Index.open(os.path.join(d, "s"), devices=[0])
+    oix = O.Index(fa)
+    for fmt in ("csv", "sam"):
+        out = os.path.join(d, "g." + fmt)
+        _, ctr = ix.enumerate_file(gcsv, out, gsx.make_params(mismatches=m), fmt=fmt)
+        octr = oix.enumerate_file(O.make_opts(mismatches=m, fmt=fmt), gcsv, os.path.join(d, "o." + fmt), nthreads=8)
+        assert open(out, "rb").read() == open(os.path.join(d, "o." + fmt), "rb").read()
+        assert ctr["hits"] == octr.hits
+    ix.close()
+
+
+def test_result_arrays_and_api_errors(gsx, gpu_index, golden_dir):
+    ix = gpu_index("g200k")
+    guides = [("ACGTACGTACGTACGTACGT", "NGG"), ("A" * 20, "NGG")]
+    r = ix.enumerate(guides, gsx.make_params(mismatches=2))
+    ga, ha = r.guide_arrays(), r.hit_arrays()
+    assert len(ga["specificity"]) == 2 and int(ga["n_hits"].sum()) == r.n_hits == len(ha["abs_pos"])
+    assert r.counters()["nodes"] > 0
+    r.close()
+    r = ix.enumerate([], gsx.make_params())
+    assert r.n_guides == 0 and r.n_hits == 0
+    with pytest.raises(gsx.GsxError):
+        ix.enumerate([("", "NGG")], gsx.make_params())
+    with pytest.raises(gsx.GsxError):
+        ix.enumerate([("ACGT" * 5, "NGG")], gsx.make_params(mismatches=9))
+    with pytest.raises(gsx.GsxError):
+        gsx.Index.open("/nonexistent/prefix")
