@@ -156,11 +156,12 @@ def build_index(gsx, g, chroms, local, args, workdir):
             raise
         import oracle as O
         import synth
-        fa = os.path.join(workdir, "bench.fa")
-        if int(os.environ.get("RANK", 0)) == 0 or not os.path.exists(fa):
+        tag = "bench_%dmb_s%d" % (int(args.genome_mb), args.seed)
+        fa = os.path.join(workdir, tag + ".fa")
+        if not os.path.exists(os.path.join(workdir, tag + ".reverse")):
             synth.write_fasta(fa, g, chroms)
-            O.ref_index(fa, os.path.join(workdir, "bench"), cwd=workdir)
-        ix = gsx.Index.open(os.path.join(workdir, "bench"), devices=[local])
+            O.ref_index(fa, os.path.join(workdir, tag), cwd=workdir)
+        ix = gsx.Index.open(os.path.join(workdir, tag), devices=[local])
         how = "reference-built (guidescan index), converted"
     log("index: %s in %.1f s, %.2f GB on device" % (how, time.time() - t0, ix.device_bytes / 1e9))
     return ix, how
@@ -258,11 +259,12 @@ def cpu_baseline(args, g, chroms, kmers, workdir, steps=1, sample=None):
     import oracle as O
     import synth
     cores = os.cpu_count() or 1
-    fa = os.path.join(workdir, "bench.fa")
-    prefix = os.path.join(workdir, "bench")
+    tag = "bench_%dmb_s%d" % (int(args.genome_mb), args.seed)
+    fa = os.path.join(workdir, tag + ".fa")
+    prefix = os.path.join(workdir, tag)
     if not O.have_ref():
         return {"value": None, "unit": "guides/s", "cores": cores, "kind": "reference", "sample": "oracle/_ref/guidescan missing"}
-    if not os.path.exists(prefix + ".forward"):
+    if not os.path.exists(prefix + ".reverse"):
         t0 = time.time()
         synth.write_fasta(fa, g, chroms)
         O.ref_index(fa, prefix, cwd=workdir)
