@@ -186,6 +186,19 @@ def run_gsx(args):
             arr[i] = gsx.Guide(sq, b"NGG")
         steps.append((arr, seqs))
     h2d_bytes = per * 80
+    if args.sweep_variants and rank == 0:
+        # kernel-variant sweep on the first step's guides (diagnostic lines on stderr; not the bench value)
+        for v in [int(x) for x in args.sweep_variants.split(",")]:
+            os.environ["GSX_SEARCH_VARIANT"] = str(v)
+            best = None
+            for rep in range(3):
+                r = ix.enumerate_raw(steps[0][0], per, params); c = r.counters(); r.close()
+                best = c if best is None or c["ms_search"] < best["ms_search"] else best
+            log(json.dumps({"variant": v, "ms_search": best["ms_search"], "guides_per_s_search": per / best["ms_search"] * 1e3,
+                            "glookups_per_s": best["lookups"] / best["ms_search"] / 1e6, "spills": best["spills"], "nodes": best["nodes"]}))
+        os.environ.pop("GSX_SEARCH_VARIANT", None)
+        if args.variant is not None:
+            os.environ["GSX_SEARCH_VARIANT"] = str(args.variant)
     for s in range(args.warmup):
         ix.enumerate_raw(steps[s][0], per, params).close()
     sampler = ClockSampler(local) if rank == 0 else None
@@ -315,8 +328,12 @@ def main():
     ap.add_argument("--sa-shift", type=int, default=6)
     ap.add_argument("--cpu-sample", type=int, default=2000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sweep-variants", default="")
+    ap.add_argument("--variant", type=int, default=None)
     ap.add_argument("--workdir", default=os.environ.get("GSX_BENCH_DIR", "/tmp/gsx_bench"))
     args = ap.parse_args()
+    if args.variant is not None:
+        os.environ["GSX_SEARCH_VARIANT"] = str(args.variant)
     if args.impl == "reference":
         run_reference(args)
     else:

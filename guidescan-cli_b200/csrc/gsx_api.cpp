@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <thread>
@@ -162,7 +163,8 @@ extern "C" int gsx_index_build_text(const uint8_t* text, uint64_t length, const 
 
 extern "C" int gsx_index_close(gsx_index* ix) {
     if (!ix) return GSX_OK;
-    for (auto& d : ix->dev) free_device_index(d);
+    for (auto& d : ix->dev) { free_device_index(d); pool_trim(d.device); }
+    pool_trim(-1);
     delete ix;
     return GSX_OK;
 }
@@ -214,16 +216,60 @@ extern "C" int gsx_index_locate(const gsx_index* ix, int strand, const uint64_t*
 // ---------------------------------------------------------------------------------------------------------
 // enumerate
 // ---------------------------------------------------------------------------------------------------------
+// ---- allocation pools -----------------------------------------------------------------------------------------
+namespace {
+struct Pool {
+    std::mutex mu;
+    std::multimap<size_t, void*> free_;
+};
+Pool& pool_of(int device) { static Pool pools[65]; return pools[device + 1]; }
+size_t bucket(size_t bytes) { size_t b = 512; while (b < bytes) b <<= 1; return b; }
+}  // namespace
+
+void* gsx::pool_get(int device, size_t bytes) {
+    size_t b = bucket(bytes);
+    Pool& P = pool_of(device);
+    {
+        std::lock_guard<std::mutex> g(P.mu);
+        auto it = P.free_.find(b);
+        if (it != P.free_.end()) { void* p = it->second; P.free_.erase(it); return p; }
+    }
+    void* p = nullptr;
+    cudaError_t e = device < 0 ? cudaHostAlloc(&p, b, cudaHostAllocDefault) : cudaMalloc(&p, b);
+    if (e != cudaSuccess) {                       // give cached blocks back to the driver and retry once
+        cudaGetLastError(); pool_trim(device);
+        e = device < 0 ? cudaHostAlloc(&p, b, cudaHostAllocDefault) : cudaMalloc(&p, b);
+        if (e != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    }
+    return p;
+}
+void gsx::pool_put(int device, void* p, size_t bytes) {
+    if (!p) return;
+    Pool& P = pool_of(device);
+    std::lock_guard<std::mutex> g(P.mu);
+    P.free_.emplace(bucket(bytes), p);
+}
+void gsx::pool_trim(int device) {
+    Pool& P = pool_of(device);
+    std::lock_guard<std::mutex> g(P.mu);
+    for (auto& kv : P.free_) { if (device < 0) cudaFreeHost(kv.second); else cudaFree(kv.second); }
+    P.free_.clear();
+}
+
 struct DevBufs {
-    std::vector<void*> ptrs;
-    template <class T> T* alloc(size_t n, bool zero = false) {
-        void* p = nullptr; size_t b = std::max<size_t>(n, 1) * sizeof(T);
-        CK(cudaMalloc(&p, b)); ptrs.push_back(p);
-        if (zero) CK(cudaMemset(p, 0, b));
+    int device;
+    std::vector<std::pair<void*, size_t>> ptrs;
+    explicit DevBufs(int dev) : device(dev) {}
+    template <class T> T* alloc(size_t n, bool zero = false, cudaStream_t s = 0) {
+        size_t b = std::max<size_t>(n, 1) * sizeof(T);
+        void* p = pool_get(device, b);
+        if (!p) throw CudaError("out of device memory");
+        ptrs.emplace_back(p, b);
+        if (zero) CK(cudaMemsetAsync(p, 0, b, s));
         return (T*)p;
     }
-    void free_one(void* p) { auto it = std::find(ptrs.begin(), ptrs.end(), p); if (it != ptrs.end()) { cudaFree(p); ptrs.erase(it); } }
-    ~DevBufs() { for (void* p : ptrs) cudaFree(p); }
+    void free_one(void* p) { for (auto it = ptrs.begin(); it != ptrs.end(); ++it) if (it->first == p) { pool_put(device, p, it->second); ptrs.erase(it); return; } }
+    ~DevBufs() { for (auto& q : ptrs) pool_put(device, q.first, q.second); }
 };
 
 int gsx_prepare_guides(const gsx_guide* guides, size_t n, const gsx_params* p, gsx::Prepared& out) {
@@ -298,7 +344,7 @@ static void run_device_job(DeviceJob* job) {
         CK(cudaSetDevice(di.device));
         cudaStream_t s; CK(cudaStreamCreate(&s));
         cudaEvent_t ev[8]; for (auto& e : ev) CK(cudaEventCreate(&e));
-        DevBufs B;
+        DevBufs B(di.device);
         HostArrays& H = job->out; H.n_guides = n;
         H.dropped = H.alloc<uint8_t>(n); H.n_hits_of = H.alloc<uint32_t>(n); H.hoff = H.alloc<uint32_t>(n + 1);
         H.specificity = H.alloc<float>(n); H.perfect = H.alloc<uint8_t>(n); H.cbd = H.alloc<uint32_t>((size_t)n * n_dist);
@@ -312,10 +358,10 @@ static void run_device_job(DeviceJob* job) {
         CK(cudaStreamSynchronize(s));
         job->ctr.ms_h2d = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_h2d0).count();
 
-        uint32_t* d_nmatch = B.alloc<uint32_t>(n + 1, true);
-        uint8_t* d_dropped = B.alloc<uint8_t>(n, true);
-        uint32_t* d_ctrs = B.alloc<uint32_t>(8, true);            // [0] task counter [1] match count [2] error flag
-        unsigned long long* d_stats = B.alloc<unsigned long long>(8, true);
+        uint32_t* d_nmatch = B.alloc<uint32_t>(n + 1, true, s);
+        uint8_t* d_dropped = B.alloc<uint8_t>(n, true, s);
+        uint32_t* d_ctrs = B.alloc<uint32_t>(8, true, s);            // [0] task counter [1] match count [2] error flag
+        unsigned long long* d_stats = B.alloc<unsigned long long>(8, true, s);
         const int variant_n = env_int("GSX_SEARCH_VARIANT", 1), variant_w = env_int("GSX_SEARCH_VARIANT_WIDE", 0);
 
         SearchArgs a{};
@@ -327,7 +373,7 @@ static void run_device_job(DeviceJob* job) {
         CK(cudaEventRecord(ev[0], s));
         // ---- threshold prefilter (process.hpp:66-76): mismatch-only counting search, guide dropped if > 1 site -----
         if (p.threshold > 0) {
-            unsigned long long* d_gcount = B.alloc<unsigned long long>(n, true);
+            unsigned long long* d_gcount = B.alloc<unsigned long long>(n, true, s);
             uint32_t spill_cap = 4096;
             for (;;) {
                 int warps = search_grid_warps(false, variant_n, di.sm_count);
@@ -344,7 +390,6 @@ static void run_device_job(DeviceJob* job) {
                 break;
             }
             CK(launch_threshold(d_gcount, d_dropped, n, s));
-            B.free_one(d_gcount);
             unsigned long long zero[8] = {0}; CK(cudaMemcpyAsync(d_stats, zero, sizeof zero, cudaMemcpyHostToDevice, s));
         }
         // ---- main search ---------------------------------------------------------------------------------------------
@@ -385,13 +430,13 @@ static void run_device_job(DeviceJob* job) {
         CK(cudaEventRecord(ev[1], s));
         // ---- arrange --------------------------------------------------------------------------------------------------
         uint32_t* d_moff = B.alloc<uint32_t>(n + 1);
-        uint32_t* d_cursor = B.alloc<uint32_t>(n, true);
+        uint32_t* d_cursor = B.alloc<uint32_t>(n, true, s);
         uint32_t* d_by_guide = B.alloc<uint32_t>(n_matches);
         uint32_t* d_sorted = B.alloc<uint32_t>(n_matches);
         uint32_t* d_sorted_off = B.alloc<uint32_t>(n_matches);
-        uint32_t* d_nhits = B.alloc<uint32_t>(n + 1, true);
+        uint32_t* d_nhits = B.alloc<uint32_t>(n + 1, true, s);
         uint32_t* d_hoff = B.alloc<uint32_t>(n + 1);
-        uint32_t* d_cbd = B.alloc<uint32_t>((size_t)n * n_dist, true);
+        uint32_t* d_cbd = B.alloc<uint32_t>((size_t)n * n_dist, true, s);
         CK(launch_scan(d_nmatch, d_moff, n, s));
         CK(launch_scatter(d_matches, n_matches, d_moff, d_cursor, d_by_guide, s));
         CK(launch_order(d_matches, d_moff, d_by_guide, n, n_dist, d_sorted, d_sorted_off, d_nhits, d_cbd, s));
@@ -419,7 +464,7 @@ static void run_device_job(DeviceJob* job) {
         // ---- specificity ------------------------------------------------------------------------------------------------
         SpecArgs S{};
         S.guide_hoff = d_hoff; S.count_by_distance = d_cbd; S.chr = L.chr; S.cfd = L.cfd; S.flags = L.flags;
-        S.counted = B.alloc<uint8_t>(nh, true); S.specificity = B.alloc<float>(n); S.perfect = B.alloc<uint8_t>(n);
+        S.counted = B.alloc<uint8_t>(nh, true, s); S.specificity = B.alloc<float>(n); S.perfect = B.alloc<uint8_t>(n);
         S.n_guides = n; S.n_dist = n_dist; S.sam_rule = p.sam_scoring ? 1 : 0; S.max_off_targets = p.max_off_targets;
         CK(launch_specificity(S, s));
         CK(cudaEventRecord(ev[4], s));

@@ -70,6 +70,12 @@ struct gsx_index {
 #include "../../include/gsx.h"
 #include <new>
 namespace gsx {
+// size-bucketed recycling of device (device >= 0) and pinned host (device == -1) allocations: cudaMalloc /
+// cudaHostAlloc cost milliseconds each, far more than the kernels of a small batch
+void* pool_get(int device, size_t bytes);
+void pool_put(int device, void* p, size_t bytes);
+void pool_trim(int device);
+
 struct HostArrays {             // one device batch worth of results (pinned host memory)
     size_t n_guides = 0, n_hits = 0;
     uint8_t* dropped = nullptr; uint32_t* n_hits_of = nullptr; uint32_t* hoff = nullptr; float* specificity = nullptr; uint8_t* perfect = nullptr;
@@ -78,13 +84,14 @@ struct HostArrays {             // one device batch worth of results (pinned hos
     uint8_t* distance = nullptr; uint8_t* rna = nullptr; uint8_t* dna = nullptr; uint8_t* index_id = nullptr; float* cfd = nullptr;
     uint8_t* counted = nullptr; uint32_t* hit_match = nullptr;
     MatchRec* matches = nullptr; size_t n_matches = 0;
-    std::vector<void*> owned;
+    std::vector<std::pair<void*, size_t>> owned;
     template <class T> T* alloc(size_t n) {
-        void* p = nullptr;
-        if (cudaHostAlloc(&p, (n ? n : 1) * sizeof(T), cudaHostAllocDefault) != cudaSuccess) throw std::bad_alloc();
-        owned.push_back(p); return (T*)p;
+        size_t bytes = (n ? n : 1) * sizeof(T);
+        void* p = pool_get(-1, bytes);               // pinned host memory, recycled between calls
+        if (!p) throw std::bad_alloc();
+        owned.emplace_back(p, bytes); return (T*)p;
     }
-    void release() { for (void* p : owned) cudaFreeHost(p); owned.clear(); }
+    void release() { for (auto& q : owned) pool_put(-1, q.first, q.second); owned.clear(); }
 };
 
 }  // namespace gsx

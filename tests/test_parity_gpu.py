@@ -117,3 +117,64 @@ def test_result_arrays_and_api_errors(gsx, gpu_index, golden_dir):
         ix.enumerate([("ACGT" * 5, "NGG")], gsx.make_params(mismatches=9))
     with pytest.raises(gsx.GsxError):
         gsx.Index.open("/nonexistent/prefix")
+
+
+@pytest.mark.parametrize("case", ["g200k", "g150kN"])
+def test_gpu_built_index_equals_reference_index(gsx, gpu_index, golden_dir, tmp_path, case):
+    """gsx_index_build (GPU suffix sorting) must give the same rows, ranks and located positions as the index the
+    reference's `guidescan index` wrote -- and the same enumerate output."""
+    built = gsx.Index.build(golden_dir[case][0], save_prefix=os.path.join(tmp_path, case), devices=[0])
+    ref = gpu_index(case)
+    assert built.chromosomes() == ref.chromosomes() and built.genome_length == ref.genome_length
+    rnd = random.Random(11)
+    n = built.genome_length + 1
+    for strand in (0, 1):
+        rows = [rnd.randrange(0, n + 1) for _ in range(5000)] + [0, n]
+        syms = "".join(rnd.choice("ACGTN") for _ in rows)
+        assert built.rank(strand, rows, syms).tolist() == ref.rank(strand, rows, syms).tolist()
+        rows = [rnd.randrange(0, n) for _ in range(5000)] + [0, n - 1]
+        assert built.locate(strand, rows).tolist() == ref.locate(strand, rows).tolist()
+    for variant in ("m3_csv", "m1_r1_d1_csv", "m3_altNAG_sam"):
+        kw = golden_manifest()["cases"][case]["variants"][variant]["opts"]
+        out = os.path.join(tmp_path, "b.out")
+        built.enumerate_file(golden_dir[case][1], out, _params(gsx, kw), fmt=kw.get("fmt", "csv"), mode=kw.get("mode", "complete"))
+        assert open(out, "rb").read() == golden_output(case, variant)
+    built.close()
+    # the saved native index (<prefix>.gsx + .gs) reloads to the same thing
+    again = gsx.Index.open(os.path.join(tmp_path, case), devices=[0])
+    out = os.path.join(tmp_path, "c.out")
+    again.enumerate_file(golden_dir[case][1], out, gsx.make_params(mismatches=3))
+    assert open(out, "rb").read() == golden_output(case, "m3_csv")
+    again.close()
+
+
+def test_gpu_built_index_with_repeats_and_dense_samples(gsx, tmp_path):
+    """prefix doubling needs several rounds on repetitive text; sa_shift 0 keeps the full suffix array"""
+    import numpy as np
+    import oracle as O
+    rng = np.random.default_rng(5)
+    unit = np.frombuffer(b"ACGTTGCAAGGCTTAACCGGATATCGCGTAGCTAGCTAGGATCC", dtype=np.uint8)
+    g = np.concatenate([np.tile(unit, 300), np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, 50_000)],
+                        np.full(700, ord("A"), dtype=np.uint8), np.tile(unit, 200), np.full(300, ord("N"), dtype=np.uint8),
+                        np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, 20_000)]])
+    import synth
+    chroms = [("c1", 40_000), ("c2", len(g) - 40_000)]
+    fa = os.path.join(tmp_path, "rep.fa")
+    synth.write_fasta(fa, g, chroms)
+    oix = O.Index(fa)
+    for shift in (0, 3, 6):
+        ix = gsx.Index.build_from_text(g, chroms, sa_shift=shift, devices=[0])
+        n = len(g) + 1
+        rnd = random.Random(shift)
+        for strand in (0, 1):
+            rows = [rnd.randrange(0, n) for _ in range(3000)]
+            assert ix.locate(strand, rows).tolist() == [O.lib().gso_sa_direct(oix.h, strand, r) for r in rows]
+            rows = [rnd.randrange(0, n + 1) for _ in range(3000)]
+            syms = "".join(rnd.choice("ACGTN") for _ in rows)
+            assert ix.rank(strand, rows, syms).tolist() == [oix.rank_bwt(strand, r, c) for r, c in zip(rows, syms)]
+        guides = [(bytes(unit[:20]).decode(), "NGG"), ("A" * 20, "NGG"), (bytes(g[45_000:45_020]).decode(), "NGG")]
+        r = ix.enumerate(guides, gsx.make_params(mismatches=2))
+        rows_txt = r.format([("g%d" % i, s, p, True) for i, (s, p) in enumerate(guides)], gsx.make_params(mismatches=2))
+        want = "".join(oix.process_kmer(O.make_opts(mismatches=2), "g%d" % i, s, p) for i, (s, p) in enumerate(guides))
+        assert rows_txt.decode() == want
+        r.close(); ix.close()
