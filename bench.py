@@ -246,7 +246,7 @@ def run_gsx(args):
                        "l2": "index (%.2f GB) is far larger than L2; every step uses new guides" % (ix.device_bytes / 1e9)},
             "e2e": {"value": total_guides / e2e_s, "unit": "guides/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": int(d2h_bytes),
                     "ms_per_step": e2e_s * 1e3 / args.steps},
-            "gpu_launches": int(args.steps * 9),
+            "gpu_launches": int(ctr_tot["launches"]),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                          "kernel": "search_kernel", "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes_per_launch, "lookups_per_guide": lookups / total_guides,
@@ -260,42 +260,87 @@ def run_gsx(args):
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(args, g, chroms, kmers, workdir)
+            cb = cpu_baseline(args, g, chroms, kmers, workdir, ix=ix)
+            line["parity_on_cpu_sample"] = parity_on_sample(ix, gsx, cb, args)
+            cb.pop("out"); cb.pop("csv")
+            line["cpu_baseline"] = cb
         print(json.dumps(line), flush=True)
     ix.close()
     if dist is not None:
         dist.destroy_process_group()
 
 
-def cpu_baseline(args, g, chroms, kmers, workdir, steps=1, sample=None):
-    """The reference's own CPU implementation (oracle/_ref/guidescan, unmodified) on a bounded sample of the workload."""
-    import oracle as O
-    import synth
-    cores = os.cpu_count() or 1
-    tag = "bench_%dmb_s%d" % (int(args.genome_mb), args.seed)
-    fa = os.path.join(workdir, tag + ".fa")
-    prefix = os.path.join(workdir, tag)
-    if not O.have_ref():
-        return {"value": None, "unit": "guides/s", "cores": cores, "kind": "reference", "sample": "oracle/_ref/guidescan missing"}
-    if not os.path.exists(prefix + ".reverse"):
-        t0 = time.time()
-        synth.write_fasta(fa, g, chroms)
-        O.ref_index(fa, prefix, cwd=workdir)
-        log("cpu_baseline: reference index built in %.1f s" % (time.time() - t0))
-    n = sample or args.cpu_sample
-    gcsv = os.path.join(workdir, "cpu_sample.csv")
-    with open(gcsv, "w") as f:
+def write_sample_csv(path, kmers, n):
+    with open(path, "w") as f:
         f.write("id,sequence,pam,chromosome,position,sense\n")
         for i in range(n):
             f.write("g%d,%s,NGG,chr1,1,+\n" % (i, kmers[i, :20].tobytes().decode()))
+
+
+def cpu_baseline(args, g, chroms, kmers, workdir, steps=1, sample=None, ix=None):
+    """The reference's CPU implementation of the path on a bounded sample of the workload, all host cores.
+    kind "reference": the unmodified reference binary (oracle/_ref/guidescan index + enumerate) -- used when its own
+    single-threaded index build fits the time budget (genomes up to --ref-max-mb).
+    kind "port": the CPU oracle (oracle/gs_oracle.c, pinned byte-for-byte to the reference) over the FM-index the GPU
+    builder exported -- the reference's `guidescan index` needs about an hour for a 3.1 Gb genome."""
+    import oracle as O
+    import synth
+    cores = os.cpu_count() or 1
+    n = sample or args.cpu_sample
+    gcsv = os.path.join(workdir, "cpu_sample.csv")
+    write_sample_csv(gcsv, kmers, n)
+    out = os.path.join(workdir, "cpu.out")
+    if args.genome_mb <= args.ref_max_mb and O.have_ref():
+        tag = "bench_%dmb_s%d" % (int(args.genome_mb), args.seed)
+        fa, prefix = os.path.join(workdir, tag + ".fa"), os.path.join(workdir, tag)
+        if not os.path.exists(prefix + ".reverse"):
+            t0 = time.time()
+            synth.write_fasta(fa, g, chroms)
+            O.ref_index(fa, prefix, cwd=workdir)
+            log("cpu_baseline: reference index built in %.1f s" % (time.time() - t0))
+        best = None
+        for _ in range(steps):
+            t0 = time.time()
+            O.ref_enumerate(prefix, gcsv, out, mismatches=args.mismatches, threads=cores)
+            dt = time.time() - t0
+            best = dt if best is None else min(best, dt)
+        return {"value": n / best, "unit": "guides/s", "cores": cores, "kind": "reference", "out": out, "csv": gcsv,
+                "sample": "first %d guides of the workload, unmodified `guidescan enumerate -n %d`, wall clock incl. index load (%.1f s)" % (n, cores, best)}
+    # port: oracle over the exported FM-index
+    t0 = time.time()
+    own = ix is None
+    if own:
+        import gsx
+        ix = gsx.Index.build_from_text(g, chroms, sa_shift=6, devices=[int(os.environ.get("LOCAL_RANK", 0))])
+    b0, b1 = ix.export_bwt(0), ix.export_bwt(1)
+    (s0, sh0), (s1, sh1) = ix.export_sa_samples(0), ix.export_sa_samples(1)
+    if sh0 != 6:
+        raise RuntimeError("cpu_baseline port needs SA samples every 64 rows")
+    oix = O.Index.from_bwt(b0, s0, b1, s1, chroms)
+    del b0, b1
+    log("cpu_baseline: oracle index imported in %.1f s" % (time.time() - t0))
     best = None
     for _ in range(steps):
         t0 = time.time()
-        O.ref_enumerate(prefix, gcsv, os.path.join(workdir, "cpu.out"), mismatches=args.mismatches, threads=cores)
+        oix.enumerate_file(O.make_opts(mismatches=args.mismatches), gcsv, out, nthreads=cores)
         dt = time.time() - t0
         best = dt if best is None else min(best, dt)
-    return {"value": n / best, "unit": "guides/s", "cores": cores, "kind": "reference",
-            "sample": "first %d guides of the workload, guidescan enumerate -n %d, wall clock incl. index load (%.1f s)" % (n, cores, best)}
+    oix.close()
+    if own:
+        ix.close()
+    return {"value": n / best, "unit": "guides/s", "cores": cores, "kind": "port", "out": out, "csv": gcsv,
+            "sample": "first %d guides of the workload, oracle/gs_oracle.c (CPU port pinned to the reference) on %d threads over the "
+                      "exported FM-index, wall clock of enumerate (%.1f s)" % (n, cores, best)}
+
+
+def parity_on_sample(ix, gsx, cb, args):
+    """the CPU arm's CSV for the sample must equal the GPU arm's, byte for byte"""
+    out = cb["out"] + ".gpu"
+    ix.enumerate_file(cb["csv"], out, gsx.make_params(mismatches=args.mismatches))
+    a, b = open(out, "rb").read(), open(cb["out"], "rb").read()
+    if cb["kind"] == "reference":      # the reference interleaves per-guide blocks by thread timing: compare sorted lines
+        a, b = b"\n".join(sorted(a.split(b"\n"))), b"\n".join(sorted(b.split(b"\n")))
+    return a == b
 
 
 def run_reference(args):
@@ -306,6 +351,7 @@ def run_reference(args):
     os.makedirs(args.workdir, exist_ok=True)
     g, chroms, pos, kmers = make_workload(args, 1)
     cb = cpu_baseline(args, g, chroms, kmers, args.workdir, steps=max(1, args.steps), sample=args.cpu_sample)
+    cb.pop("out"); cb.pop("csv")
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "guides/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {"workload": "%.0f Mb uniform-random synthetic genome (seed %d), NGG 20-mer guides, mismatches=%d" % (args.genome_mb, args.seed, args.mismatches)},
@@ -319,14 +365,15 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="gsx", choices=["gsx", "reference"])
-    ap.add_argument("--genome-mb", type=float, default=float(os.environ.get("GSX_BENCH_GENOME_MB", 120)))
-    ap.add_argument("--n-chr", type=int, default=8)
-    ap.add_argument("--guides-per-step", type=int, default=int(os.environ.get("GSX_BENCH_GUIDES", 20000)))
+    ap.add_argument("--genome-mb", type=float, default=float(os.environ.get("GSX_BENCH_GENOME_MB", 3100)))
+    ap.add_argument("--n-chr", type=int, default=24)
+    ap.add_argument("--guides-per-step", type=int, default=int(os.environ.get("GSX_BENCH_GUIDES", 50000)))
+    ap.add_argument("--ref-max-mb", type=float, default=200.0)
     ap.add_argument("--plant-guides", type=int, default=2000)
     ap.add_argument("--mismatches", type=int, default=3)
-    ap.add_argument("--seed", type=int, default=2)
+    ap.add_argument("--seed", type=int, default=3)
     ap.add_argument("--sa-shift", type=int, default=6)
-    ap.add_argument("--cpu-sample", type=int, default=2000)
+    ap.add_argument("--cpu-sample", type=int, default=1000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sweep-variants", default="")
     ap.add_argument("--variant", type=int, default=None)

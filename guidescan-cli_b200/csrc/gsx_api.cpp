@@ -213,6 +213,27 @@ extern "C" int gsx_index_locate(const gsx_index* ix, int strand, const uint64_t*
     return GSX_OK;
 }
 
+extern "C" int gsx_index_export_bwt(const gsx_index* ix, int strand, uint8_t* out) {
+    if (!ix || !out || strand < 0 || strand > 1) return fail(GSX_ERR_ARG, "bad argument");
+    const HostStrand& h = ix->host.st[strand];
+    static const uint8_t SYM[4] = {'A', 'C', 'G', 'T'};
+    for (uint64_t row = 0; row < h.n; row++) {
+        const OccBlock& b = h.blocks[row >> 6];
+        out[row] = SYM[block_sym(b.hi, b.lo, (uint32_t)row)];
+    }
+    for (size_t i = 0; i < h.exc_rows.size(); i++) out[h.exc_rows[i]] = h.exc_sym[i];
+    return GSX_OK;
+}
+
+extern "C" int gsx_index_export_sa_samples(const gsx_index* ix, int strand, uint32_t* out, uint64_t* n_samples, uint32_t* sa_shift) {
+    if (!ix || strand < 0 || strand > 1) return fail(GSX_ERR_ARG, "bad argument");
+    const HostStrand& h = ix->host.st[strand];
+    if (n_samples) *n_samples = h.sa_samples.size();
+    if (sa_shift) *sa_shift = h.sa_shift;
+    if (out) memcpy(out, h.sa_samples.data(), h.sa_samples.size() * 4);
+    return GSX_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // enumerate
 // ---------------------------------------------------------------------------------------------------------
@@ -362,7 +383,7 @@ static void run_device_job(DeviceJob* job) {
         uint8_t* d_dropped = B.alloc<uint8_t>(n, true, s);
         uint32_t* d_ctrs = B.alloc<uint32_t>(8, true, s);            // [0] task counter [1] match count [2] error flag
         unsigned long long* d_stats = B.alloc<unsigned long long>(8, true, s);
-        const int variant_n = env_int("GSX_SEARCH_VARIANT", 1), variant_w = env_int("GSX_SEARCH_VARIANT_WIDE", 0);
+        const int variant_n = env_int("GSX_SEARCH_VARIANT", 0), variant_w = env_int("GSX_SEARCH_VARIANT_WIDE", 0);
 
         SearchArgs a{};
         a.st[0] = di.st[0].d; a.st[1] = di.st[1].d; a.guides = d_guides; a.pamsets = d_pamsets;
@@ -371,6 +392,7 @@ static void run_device_job(DeviceJob* job) {
         a.p.n_tasks = 2 * n;
 
         CK(cudaEventRecord(ev[0], s));
+        uint64_t n_launches = 0;
         // ---- threshold prefilter (process.hpp:66-76): mismatch-only counting search, guide dropped if > 1 site -----
         if (p.threshold > 0) {
             unsigned long long* d_gcount = B.alloc<unsigned long long>(n, true, s);
@@ -382,14 +404,14 @@ static void run_device_job(DeviceJob* job) {
                 CK(cudaMemsetAsync(d_gcount, 0, (size_t)n * 8, s));
                 SearchArgs c = a; c.p.M = (uint32_t)p.threshold; c.p.R = c.p.D = 0; c.p.counting = 1; c.p.match_cap = 0; c.p.spill_cap = spill_cap;
                 c.guide_count = d_gcount; c.spill = d_spill; c.skip = nullptr; c.matches = nullptr;
-                CK(launch_search(c, false, variant_n, di.sm_count, s, nullptr));
+                CK(launch_search(c, false, variant_n, di.sm_count, s, nullptr)); n_launches++;
                 uint32_t h[3]; CK(cudaMemcpyAsync(h, d_ctrs, sizeof h, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s));
                 B.free_one(d_spill);
                 if (h[2] & GSX_KERR_WATCHDOG) throw std::runtime_error("search kernel watchdog tripped");
                 if (h[2] & GSX_KERR_SPILL_OVERFLOW) { spill_cap *= 4; continue; }
                 break;
             }
-            CK(launch_threshold(d_gcount, d_dropped, n, s));
+            CK(launch_threshold(d_gcount, d_dropped, n, s)); n_launches++;
             unsigned long long zero[8] = {0}; CK(cudaMemcpyAsync(d_stats, zero, sizeof zero, cudaMemcpyHostToDevice, s));
         }
         // ---- main search ---------------------------------------------------------------------------------------------
@@ -413,7 +435,7 @@ static void run_device_job(DeviceJob* job) {
             SearchArgs m = a; m.p.M = p.mismatches; m.p.R = p.rna_bulges; m.p.D = p.dna_bulges; m.p.counting = 0;
             m.p.match_cap = (uint32_t)match_cap; m.p.spill_cap = spill_cap; m.spill = d_spill; m.matches = d_matches;
             m.skip = p.threshold > 0 ? d_dropped : nullptr;
-            CK(launch_search(m, wide, variant, di.sm_count, s, nullptr));
+            CK(launch_search(m, wide, variant, di.sm_count, s, nullptr)); n_launches++;
             uint32_t h[3]; CK(cudaMemcpyAsync(h, d_ctrs, sizeof h, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s));
             B.free_one(d_spill);
             if (h[2] & GSX_KERR_WATCHDOG) throw std::runtime_error("search kernel watchdog tripped");
@@ -437,7 +459,7 @@ static void run_device_job(DeviceJob* job) {
         uint32_t* d_nhits = B.alloc<uint32_t>(n + 1, true, s);
         uint32_t* d_hoff = B.alloc<uint32_t>(n + 1);
         uint32_t* d_cbd = B.alloc<uint32_t>((size_t)n * n_dist, true, s);
-        CK(launch_scan(d_nmatch, d_moff, n, s));
+        CK(launch_scan(d_nmatch, d_moff, n, s)); n_launches += 2 + (n_matches ? 1 : 0);
         CK(launch_scatter(d_matches, n_matches, d_moff, d_cursor, d_by_guide, s));
         CK(launch_order(d_matches, d_moff, d_by_guide, n, n_dist, d_sorted, d_sorted_off, d_nhits, d_cbd, s));
         {   // total hits can exceed 2^32 only for absurd inputs; the scan is 32-bit, so check with a 64-bit host sum
@@ -449,6 +471,7 @@ static void run_device_job(DeviceJob* job) {
         CK(launch_scan(d_nhits, d_hoff, n, s));
         const uint32_t nh = (uint32_t)H.n_hits;
         uint32_t* d_hit_match = B.alloc<uint32_t>(nh); uint32_t* d_hit_row = B.alloc<uint32_t>(nh); uint32_t* d_hit_guide = B.alloc<uint32_t>(nh);
+        n_launches += (n_matches ? 1 : 0) + (H.n_hits ? 1 : 0) + 2;      // scan, expand, locate_score, specificity
         CK(launch_expand(d_matches, d_moff, d_sorted, d_sorted_off, d_hoff, n, n_matches, d_hit_match, d_hit_row, d_hit_guide, s));
         CK(cudaEventRecord(ev[2], s));
         // ---- locate + coordinates + CFD ------------------------------------------------------------------------------
@@ -491,7 +514,7 @@ static void run_device_job(DeviceJob* job) {
         CK(cudaEventElapsedTime(&ms, ev[0], ev[4])); job->ctr.ms_total_device = ms;
         CK(cudaEventElapsedTime(&ms, ev[4], ev[5])); job->ctr.ms_d2h = ms;
         job->ctr.nodes = st[0]; job->ctr.lookups = st[1]; job->ctr.spills = st[2]; job->ctr.lf_steps = st[3];
-        job->ctr.matches = n_matches; job->ctr.hits = nh;
+        job->ctr.matches = n_matches; job->ctr.hits = nh; job->ctr.launches = n_launches;
         for (auto& e : ev) cudaEventDestroy(e);
         cudaStreamDestroy(s);
     } catch (const CudaError& e) { job->status = GSX_ERR_CUDA; job->err = e.what(); }
@@ -556,7 +579,7 @@ extern "C" int gsx_enumerate(const gsx_index* ix, const gsx_guide* guides, size_
         r->part_g0.push_back(g); r->part_h0.push_back(h); g += j.out.n_guides; h += j.out.n_hits;
         r->parts.push_back(std::move(j.out));
         gsx_counters& c = r->counters;
-        c.nodes += j.ctr.nodes; c.lookups += j.ctr.lookups; c.matches += j.ctr.matches; c.hits += j.ctr.hits; c.lf_steps += j.ctr.lf_steps; c.spills += j.ctr.spills;
+        c.nodes += j.ctr.nodes; c.lookups += j.ctr.lookups; c.matches += j.ctr.matches; c.hits += j.ctr.hits; c.lf_steps += j.ctr.lf_steps; c.spills += j.ctr.spills; c.launches += j.ctr.launches;
         c.ms_search = std::max(c.ms_search, j.ctr.ms_search); c.ms_arrange = std::max(c.ms_arrange, j.ctr.ms_arrange);
         c.ms_locate = std::max(c.ms_locate, j.ctr.ms_locate); c.ms_score = std::max(c.ms_score, j.ctr.ms_score);
         c.ms_total_device = std::max(c.ms_total_device, j.ctr.ms_total_device); c.ms_h2d = std::max(c.ms_h2d, j.ctr.ms_h2d); c.ms_d2h = std::max(c.ms_d2h, j.ctr.ms_d2h);

@@ -212,11 +212,11 @@ bool build_strand_gpu(int device, const uint8_t* text, uint64_t len, uint32_t sa
         uint64_t Cb[257]; uint64_t acc = 0; hist[0] = 1;
         for (int c = 0; c < 256; c++) { Cb[c] = acc; acc += hist[c]; }
         out.C[0] = (uint32_t)Cb['A']; out.C[1] = (uint32_t)Cb['C']; out.C[2] = (uint32_t)Cb['G']; out.C[3] = (uint32_t)Cb['T']; out.C[4] = (uint32_t)Cb['N'];
-        out.exc_rows.resize(n_exc); out.exc_lf.resize(n_exc); out.n_rows.clear();
+        out.exc_rows.resize(n_exc); out.exc_lf.resize(n_exc); out.exc_sym.resize(n_exc); out.n_rows.clear();
         uint64_t seen[256]; memset(seen, 0, sizeof seen);
         for (uint64_t i = 0; i < n_exc; i++) {
             uint32_t row = er[order[i]]; uint8_t sym = es[order[i]];
-            out.exc_rows[i] = row; out.exc_lf[i] = (uint32_t)(Cb[sym] + seen[sym]++);       // LF = C[c] + rank_c(row)
+            out.exc_rows[i] = row; out.exc_sym[i] = sym; out.exc_lf[i] = (uint32_t)(Cb[sym] + seen[sym]++);       // LF = C[c] + rank_c(row)
             if (sym == 'N') out.n_rows.push_back(row);
         }
         return true;

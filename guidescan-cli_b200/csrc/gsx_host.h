@@ -15,6 +15,7 @@ struct HostStrand {
     std::vector<uint32_t> sa_samples;
     uint32_t sa_shift = 6;
     std::vector<uint32_t> exc_rows, exc_lf, n_rows;
+    std::vector<uint8_t> exc_sym;         // BWT byte of each exception row (0 = sentinel)
     uint32_t C[5] = {0, 0, 0, 0, 0};
 };
 
@@ -30,7 +31,6 @@ struct StrandBuilder {
     HostStrand* out;
     uint64_t n, row = 0;
     uint64_t run[256];
-    std::vector<uint8_t> exc_sym;
     std::vector<uint64_t> exc_rank;
     OccBlock cur;
     explicit StrandBuilder(HostStrand* o, uint64_t n_rows);

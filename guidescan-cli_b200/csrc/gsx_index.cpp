@@ -21,7 +21,7 @@ StrandBuilder::StrandBuilder(HostStrand* o, uint64_t n_rows) : out(o), n(n_rows)
     memset(&cur, 0, sizeof cur);
     out->n = n;
     out->blocks.clear(); out->blocks.reserve(n / 64 + 1);
-    out->exc_rows.clear(); out->exc_lf.clear(); out->n_rows.clear();
+    out->exc_rows.clear(); out->exc_lf.clear(); out->n_rows.clear(); out->exc_sym.clear();
 }
 
 void StrandBuilder::push(uint8_t sym) {
@@ -33,7 +33,7 @@ void StrandBuilder::push(uint8_t sym) {
     int code = sym_code(sym);
     if (code < 0) {
         out->exc_rows.push_back((uint32_t)row);
-        exc_sym.push_back(sym); exc_rank.push_back(run[sym]);
+        out->exc_sym.push_back(sym); exc_rank.push_back(run[sym]);
         if (sym == 'N') out->n_rows.push_back((uint32_t)row);
         code = 0;
     }
@@ -56,7 +56,7 @@ void StrandBuilder::finish() {
     out->C[0] = (uint32_t)Cb['A']; out->C[1] = (uint32_t)Cb['C']; out->C[2] = (uint32_t)Cb['G']; out->C[3] = (uint32_t)Cb['T'];
     out->C[4] = (uint32_t)Cb['N'];
     out->exc_lf.resize(out->exc_rows.size());
-    for (size_t i = 0; i < out->exc_rows.size(); i++) out->exc_lf[i] = (uint32_t)(Cb[exc_sym[i]] + exc_rank[i]);
+    for (size_t i = 0; i < out->exc_rows.size(); i++) out->exc_lf[i] = (uint32_t)(Cb[out->exc_sym[i]] + exc_rank[i]);
 }
 
 // ---- sdsl file reader ------------------------------------------------------------------------------------
@@ -185,7 +185,7 @@ bool read_fasta(const std::string& path, std::vector<uint8_t>& seq, HostIndex& i
 
 // ---- native cache format (<prefix>.gsx): a flat dump of the HBM layout ----------------------------------------
 namespace {
-const char kMagic[8] = {'G', 'S', 'X', 'I', 'D', 'X', '0', '1'};
+const char kMagic[8] = {'G', 'S', 'X', 'I', 'D', 'X', '0', '2'};
 template <class T> bool wr(FILE* f, const std::vector<T>& v) { uint64_t n = v.size(); return fwrite(&n, 8, 1, f) == 1 && (n == 0 || fwrite(v.data(), sizeof(T), n, f) == n); }
 template <class T> bool rd(FILE* f, std::vector<T>& v) { uint64_t n; if (fread(&n, 8, 1, f) != 1) return false; v.resize(n); return n == 0 || fread(v.data(), sizeof(T), n, f) == n; }
 }  // namespace
@@ -197,7 +197,7 @@ bool save_gsx(const std::string& prefix, const HostIndex& ix, std::string& err) 
     for (int s = 0; s < 2 && ok; s++) {
         const HostStrand& h = ix.st[s];
         ok = fwrite(&h.n, 8, 1, f) == 1 && fwrite(&h.sa_shift, 4, 1, f) == 1 && fwrite(h.C, 4, 5, f) == 5 && wr(f, h.blocks) &&
-             wr(f, h.sa_samples) && wr(f, h.exc_rows) && wr(f, h.exc_lf) && wr(f, h.n_rows);
+             wr(f, h.sa_samples) && wr(f, h.exc_rows) && wr(f, h.exc_lf) && wr(f, h.n_rows) && wr(f, h.exc_sym);
     }
     fclose(f);
     if (!ok) { err = "short write to " + prefix + ".gsx"; return false; }
@@ -213,7 +213,7 @@ bool load_gsx(const std::string& prefix, HostIndex& ix, std::string& err) {
     for (int s = 0; s < 2 && ok; s++) {
         HostStrand& h = ix.st[s];
         ok = fread(&h.n, 8, 1, f) == 1 && fread(&h.sa_shift, 4, 1, f) == 1 && fread(h.C, 4, 5, f) == 5 && rd(f, h.blocks) &&
-             rd(f, h.sa_samples) && rd(f, h.exc_rows) && rd(f, h.exc_lf) && rd(f, h.n_rows);
+             rd(f, h.sa_samples) && rd(f, h.exc_rows) && rd(f, h.exc_lf) && rd(f, h.n_rows) && rd(f, h.exc_sym);
     }
     fclose(f);
     if (!ok) { err = "malformed " + prefix + ".gsx"; return false; }

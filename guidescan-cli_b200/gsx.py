@@ -45,7 +45,7 @@ class Counters(C.Structure):
     _fields_ = [("nodes", C.c_uint64), ("lookups", C.c_uint64), ("matches", C.c_uint64), ("hits", C.c_uint64),
                 ("lf_steps", C.c_uint64), ("spills", C.c_uint64), ("ms_search", C.c_double), ("ms_arrange", C.c_double),
                 ("ms_locate", C.c_double), ("ms_score", C.c_double), ("ms_total_device", C.c_double),
-                ("ms_h2d", C.c_double), ("ms_d2h", C.c_double)]
+                ("ms_h2d", C.c_double), ("ms_d2h", C.c_double), ("launches", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -58,7 +58,7 @@ class GuideRow(C.Structure):
 EXPORTS = ["gsx_params_default", "gsx_index_open", "gsx_index_build", "gsx_index_build_text", "gsx_index_close",
            "gsx_index_genome_length",
            "gsx_index_n_chromosomes", "gsx_index_chromosome_name", "gsx_index_chromosome_length", "gsx_index_device_bytes",
-           "gsx_index_n_devices", "gsx_index_rank", "gsx_index_locate", "gsx_enumerate", "gsx_result_view_get",
+           "gsx_index_n_devices", "gsx_index_rank", "gsx_index_locate", "gsx_index_export_bwt", "gsx_index_export_sa_samples", "gsx_enumerate", "gsx_result_view_get",
            "gsx_result_counters", "gsx_result_match_sequence", "gsx_result_free", "gsx_format_rows", "gsx_format_header",
            "gsx_enumerate_file", "gsx_free", "gsx_last_error", "gsx_version", "gsx_device_count"]
 
@@ -81,6 +81,8 @@ _L.gsx_index_device_bytes.restype = C.c_uint64
 _L.gsx_index_device_bytes.argtypes = [C.c_void_p]
 _L.gsx_index_rank.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_char_p, C.c_size_t, C.c_void_p]
 _L.gsx_index_locate.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]
+_L.gsx_index_export_bwt.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+_L.gsx_index_export_sa_samples.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
 _L.gsx_enumerate.argtypes = [C.c_void_p, C.POINTER(Guide), C.c_size_t, C.POINTER(Params), C.POINTER(C.c_void_p)]
 _L.gsx_result_view_get.argtypes = [C.c_void_p, C.POINTER(ResultView)]
 _L.gsx_result_counters.argtypes = [C.c_void_p, C.POINTER(Counters)]
@@ -257,6 +259,18 @@ class Index:
         out = np.zeros(len(rows), dtype=np.uint64)
         _ck(_L.gsx_index_locate(self.h, strand, rows.ctypes.data, len(rows), out.ctypes.data), "gsx_index_locate")
         return out
+
+    def export_bwt(self, strand: int) -> np.ndarray:
+        out = np.empty(self.genome_length + 1, dtype=np.uint8)
+        _ck(_L.gsx_index_export_bwt(self.h, strand, out.ctypes.data), "gsx_index_export_bwt")
+        return out
+
+    def export_sa_samples(self, strand: int):
+        n, sh = C.c_uint64(), C.c_uint32()
+        _ck(_L.gsx_index_export_sa_samples(self.h, strand, None, C.byref(n), C.byref(sh)), "gsx_index_export_sa_samples")
+        out = np.empty(n.value, dtype=np.uint32)
+        _ck(_L.gsx_index_export_sa_samples(self.h, strand, out.ctypes.data, C.byref(n), C.byref(sh)), "gsx_index_export_sa_samples")
+        return out, sh.value
 
     def enumerate(self, guides, params) -> Result:
         """guides: sequence of (seq, pam) strings.  Mirrors genome_index::inexact_search + resolve + scoring for all guides."""

@@ -98,6 +98,7 @@ typedef struct {
     uint64_t spills;           /* search-stack nodes spilled from shared memory to global memory */
     double   ms_search, ms_arrange, ms_locate, ms_score, ms_total_device;   /* CUDA-event times, max over devices */
     double   ms_h2d, ms_d2h;
+    uint64_t launches;         /* kernels launched by this library for the call (all devices) */
 } gsx_counters;
 
 /* ---- index ------------------------------------------------------------------------------------------- */
@@ -126,6 +127,11 @@ int         gsx_index_n_devices(const gsx_index*);
  * (sdsl csa_wt.hpp:270-273) and SA[row] = csa[row] (csa_wt.hpp:333-346), batched. strand 0 = forward index. */
 int gsx_index_rank(const gsx_index*, int strand, const uint64_t* rows, const char* syms, size_t n, uint64_t* out);
 int gsx_index_locate(const gsx_index*, int strand, const uint64_t* rows, size_t n, uint64_t* out);
+/* Host copies of what the index was built from, for cross-checking other implementations against the same index:
+ * the BWT of text+'\0' as bytes (0 in the sentinel row; `out` holds genome_length + 1 bytes) and the SA samples
+ * (SA[k << *sa_shift], ((n - 1) >> sa_shift) + 1 values). */
+int gsx_index_export_bwt(const gsx_index*, int strand, uint8_t* out);
+int gsx_index_export_sa_samples(const gsx_index*, int strand, uint32_t* out, uint64_t* n_samples, uint32_t* sa_shift);
 
 /* ---- enumerate --------------------------------------------------------------------------------------- */
 /* All guides, both strand indexes: search + locate + coordinates + CFD + specificity; results in host memory.

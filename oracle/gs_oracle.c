@@ -25,7 +25,8 @@
 typedef struct {
     uint64_t  n;            /* csa.size() = text length + 1 */
     uint8_t*  bwt;          /* n bytes, 0 in the row whose suffix starts at text position 0 */
-    uint32_t* sa;           /* full suffix array (self-check and sampling source) */
+    uint32_t* sa;           /* full suffix array (self-check and sampling source); NULL for an imported index */
+    uint32_t* sa_samples;   /* SA[64 k] */
     uint64_t  C[257];       /* C[c] = number of symbols smaller than c in text+'\0'  (csa.C[char2comp[c]]) */
     int       present[256];
     int       slot[256];
@@ -92,16 +93,10 @@ static uint32_t* build_sa(const uint8_t* t, uint64_t n) {
     return sa;
 }
 
-static int fm_build(fm_t* f, const uint8_t* text, uint64_t len) {
-    memset(f, 0, sizeof *f);
-    f->n = len + 1;
-    uint8_t* t = (uint8_t*)malloc(f->n);
-    memcpy(t, text, len); t[len] = 0;                 /* sdsl appends the 0 sentinel: construct.hpp:121-165 */
-    f->sa = build_sa(t, f->n);
-    if (!f->sa) { free(t); return -1; }
-    f->bwt = (uint8_t*)malloc(f->n);
+/* occurrence checkpoints + C from a finished BWT (f->bwt, f->n set) */
+static void fm_finish(fm_t* f) {
     uint64_t cnt[256]; memset(cnt, 0, sizeof cnt);
-    for (uint64_t i = 0; i < f->n; i++) { f->bwt[i] = f->sa[i] ? t[f->sa[i] - 1] : 0; cnt[t[i]]++; }
+    for (uint64_t i = 0; i < f->n; i++) cnt[f->bwt[i]]++;      /* the BWT is a permutation of text+sentinel */
     uint64_t acc = 0;
     for (int c = 0; c < 256; c++) { f->C[c] = acc; acc += cnt[c]; f->present[c] = cnt[c] > 0; }
     f->C[256] = acc;
@@ -114,11 +109,26 @@ static int fm_build(fm_t* f, const uint8_t* text, uint64_t len) {
         run[f->slot[f->bwt[i]]]++;
     }
     if ((f->n & 63) == 0) memcpy(f->ckpt + (f->n / 64) * f->nslot, run, sizeof(uint64_t) * f->nslot);
+}
+
+static int fm_build(fm_t* f, const uint8_t* text, uint64_t len) {
+    memset(f, 0, sizeof *f);
+    f->n = len + 1;
+    uint8_t* t = (uint8_t*)malloc(f->n);
+    memcpy(t, text, len); t[len] = 0;                 /* sdsl appends the 0 sentinel: construct.hpp:121-165 */
+    f->sa = build_sa(t, f->n);
+    if (!f->sa) { free(t); return -1; }
+    f->bwt = (uint8_t*)malloc(f->n);
+    for (uint64_t i = 0; i < f->n; i++) f->bwt[i] = f->sa[i] ? t[f->sa[i] - 1] : 0;
+    uint64_t ns = (f->n - 1) / 64 + 1;
+    f->sa_samples = (uint32_t*)malloc(ns * sizeof(uint32_t));
+    for (uint64_t k = 0; k < ns; k++) f->sa_samples[k] = f->sa[k * 64];
+    fm_finish(f);
     free(t);
     return 0;
 }
 
-static void fm_free(fm_t* f) { free(f->bwt); free(f->sa); free(f->ckpt); }
+static void fm_free(fm_t* f) { free(f->bwt); free(f->sa); free(f->sa_samples); free(f->ckpt); }
 
 /* csa.rank_bwt(i, c): occurrences of c in BWT[0, i); 0 for a symbol the text does not contain.
  * reference sdsl/include/sdsl/csa_wt.hpp:270-273 -> wt_pc.hpp:360-384 */
@@ -141,7 +151,7 @@ static uint64_t sa_walk(const fm_t* f, uint64_t i, gso_counters* ctr) {
         off++;
         if (ctr) ctr->lf_steps++;
     }
-    uint64_t r = (uint64_t)f->sa[i] + off;       /* sample[i/64] == SA[i] */
+    uint64_t r = (uint64_t)f->sa_samples[i >> 6] + off;
     return r < f->n ? r : r - f->n;
 }
 
@@ -739,6 +749,24 @@ gso_index* gso_index_from_fasta(const char* path) {
     return ix;
 }
 
+/* An index over an existing BWT (bytes, 0 = sentinel row) and SA samples every 64 rows, e.g. exported by the GPU index
+ * builder -- lets the CPU port run on genomes whose suffix array the simple sorter above could not build in time. */
+gso_index* gso_index_from_bwt(const uint8_t* bwt_fwd, const uint32_t* sa64_fwd, const uint8_t* bwt_rev, const uint32_t* sa64_rev,
+                              uint64_t n, int n_chr, const char* const* names, const uint64_t* lens) {
+    gso_index* ix = (gso_index*)calloc(1, sizeof *ix);
+    ix->G = n - 1; ix->n_chr = n_chr; ix->names = (char**)calloc(n_chr + 1, sizeof(char*)); ix->lens = (uint64_t*)calloc(n_chr + 1, sizeof(uint64_t));
+    for (int i = 0; i < n_chr; i++) { ix->names[i] = strdup(names[i]); ix->lens[i] = lens[i]; }
+    const uint8_t* b[2] = {bwt_fwd, bwt_rev}; const uint32_t* sm[2] = {sa64_fwd, sa64_rev};
+    uint64_t ns = (n - 1) / 64 + 1;
+    for (int s = 0; s < 2; s++) {
+        fm_t* f = &ix->fm[s]; memset(f, 0, sizeof *f);
+        f->n = n; f->bwt = (uint8_t*)malloc(n); memcpy(f->bwt, b[s], n);
+        f->sa_samples = (uint32_t*)malloc(ns * sizeof(uint32_t)); memcpy(f->sa_samples, sm[s], ns * sizeof(uint32_t));
+        fm_finish(f);
+    }
+    return ix;
+}
+
 void gso_index_free(gso_index* ix) {
     if (!ix) return;
     fm_free(&ix->fm[0]); fm_free(&ix->fm[1]);
@@ -751,7 +779,7 @@ const char* gso_index_chr_name(const gso_index* ix, int i) { return ix->names[i]
 uint64_t gso_index_chr_len(const gso_index* ix, int i) { return ix->lens[i]; }
 uint64_t gso_rank_bwt(const gso_index* ix, int s, uint64_t i, int c) { return rank_bwt(&ix->fm[s], i, c, NULL); }
 uint64_t gso_sa(const gso_index* ix, int s, uint64_t row) { return sa_walk(&ix->fm[s], row, NULL); }
-uint64_t gso_sa_direct(const gso_index* ix, int s, uint64_t row) { return ix->fm[s].sa[row]; }
+uint64_t gso_sa_direct(const gso_index* ix, int s, uint64_t row) { return ix->fm[s].sa ? ix->fm[s].sa[row] : sa_walk(&ix->fm[s], row, NULL); }
 uint8_t gso_bwt(const gso_index* ix, int s, uint64_t row) { return ix->fm[s].bwt[row]; }
 uint64_t gso_C(const gso_index* ix, int s, int c) { return ix->fm[s].C[c & 255]; }
 void gso_free(void* p) { free(p); }

@@ -54,6 +54,8 @@ typedef struct {
 gso_index* gso_index_from_text(const uint8_t* fwd, uint64_t G, int n_chr,
                                const char* const* names, const uint64_t* lens);
 gso_index* gso_index_from_fasta(const char* fasta_path);
+gso_index* gso_index_from_bwt(const uint8_t* bwt_fwd, const uint32_t* sa64_fwd, const uint8_t* bwt_rev, const uint32_t* sa64_rev,
+                              uint64_t n, int n_chr, const char* const* names, const uint64_t* lens);
 void       gso_index_free(gso_index*);
 uint64_t   gso_index_n(const gso_index*);                       /* csa.size() = G + 1 */
 int        gso_index_n_chr(const gso_index*);

@@ -44,6 +44,8 @@ def lib():
         L.gso_index_from_fasta.argtypes = [C.c_char_p]
         L.gso_index_from_text.restype = C.c_void_p
         L.gso_index_from_text.argtypes = [C.c_char_p, C.c_uint64, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_uint64)]
+        L.gso_index_from_bwt.restype = C.c_void_p
+        L.gso_index_from_bwt.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_uint64)]
         L.gso_index_free.argtypes = [C.c_void_p]
         L.gso_index_n.restype = C.c_uint64
         L.gso_index_n.argtypes = [C.c_void_p]
@@ -84,10 +86,19 @@ def make_opts(mismatches=3, rna_bulges=0, dna_bulges=0, threshold=-1, start=Fals
 
 
 class Index:
-    def __init__(self, fasta: str):
-        self.h = lib().gso_index_from_fasta(fasta.encode())
+    def __init__(self, fasta: str | None, handle=None):
+        self.h = handle if handle is not None else lib().gso_index_from_fasta(fasta.encode())
         if not self.h:
-            raise RuntimeError("oracle: cannot index " + fasta)
+            raise RuntimeError("oracle: cannot index %s" % fasta)
+
+    @classmethod
+    def from_bwt(cls, bwt_fwd, sa64_fwd, bwt_rev, sa64_rev, chroms):
+        """bwt_*: uint8 numpy arrays (0 in the sentinel row), sa64_*: uint32 SA samples every 64 rows"""
+        names = (C.c_char_p * len(chroms))(*[c[0].encode() for c in chroms])
+        lens = (C.c_uint64 * len(chroms))(*[int(c[1]) for c in chroms])
+        h = lib().gso_index_from_bwt(bwt_fwd.ctypes.data, sa64_fwd.ctypes.data, bwt_rev.ctypes.data, sa64_rev.ctypes.data,
+                                     len(bwt_fwd), len(chroms), names, lens)
+        return cls(None, handle=h)
 
     def close(self):
         if self.h:
