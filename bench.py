@@ -188,17 +188,19 @@ def run_gsx(args):
     h2d_bytes = per * 80
     if args.sweep_variants and rank == 0:
         # kernel-variant sweep on the first step's guides (diagnostic lines on stderr; not the bench value)
-        for v in [int(x) for x in args.sweep_variants.split(",")]:
-            os.environ["GSX_SEARCH_VARIANT"] = str(v)
+        # items: "f<k>" = specialised kernel variant k, "g<k>" = general kernel variant k
+        for item in args.sweep_variants.split(","):
+            env = {"GSX_FORCE_GENERAL": "1", "GSX_SEARCH_VARIANT": item[1:]} if item[0] == "g" else {"GSX_FORCE_GENERAL": "0", "GSX_FAST_VARIANT": item[1:]}
+            os.environ.update(env)
             best = None
             for rep in range(3):
                 r = ix.enumerate_raw(steps[0][0], per, params); c = r.counters(); r.close()
                 best = c if best is None or c["ms_search"] < best["ms_search"] else best
-            log(json.dumps({"variant": v, "ms_search": best["ms_search"], "guides_per_s_search": per / best["ms_search"] * 1e3,
+            log(json.dumps({"variant": item, "ms_search": best["ms_search"], "guides_per_s_search": per / best["ms_search"] * 1e3,
                             "glookups_per_s": best["lookups"] / best["ms_search"] / 1e6, "spills": best["spills"], "nodes": best["nodes"]}))
-        os.environ.pop("GSX_SEARCH_VARIANT", None)
-        if args.variant is not None:
-            os.environ["GSX_SEARCH_VARIANT"] = str(args.variant)
+        for k in ("GSX_FORCE_GENERAL", "GSX_SEARCH_VARIANT", "GSX_FAST_VARIANT"):
+            os.environ.pop(k, None)
+        apply_variant(args)
     for s in range(args.warmup):
         ix.enumerate_raw(steps[s][0], per, params).close()
     sampler = ClockSampler(local) if rank == 0 else None
@@ -248,7 +250,7 @@ def run_gsx(args):
                     "ms_per_step": e2e_s * 1e3 / args.steps},
             "gpu_launches": int(ctr_tot["launches"]),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                         "kernel": "search_kernel", "peak_source": peak_src,
+                         "kernel": "search_fast_kernel" if not os.environ.get("GSX_FORCE_GENERAL", "0") == "1" else "search_kernel", "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes_per_launch, "lookups_per_guide": lookups / total_guides,
                          "nodes_per_guide": nodes / total_guides, "launch_ms": launch_ms,
                          "random_sector_peak_gbs": rg["gb_per_s"] if rg else None,
@@ -359,6 +361,14 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def apply_variant(args):
+    if args.variant:
+        if args.variant[0] == "g":
+            os.environ.update({"GSX_FORCE_GENERAL": "1", "GSX_SEARCH_VARIANT": args.variant[1:]})
+        else:
+            os.environ.update({"GSX_FORCE_GENERAL": "0", "GSX_FAST_VARIANT": args.variant[1:]})
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -373,14 +383,13 @@ def main():
     ap.add_argument("--mismatches", type=int, default=3)
     ap.add_argument("--seed", type=int, default=3)
     ap.add_argument("--sa-shift", type=int, default=6)
-    ap.add_argument("--cpu-sample", type=int, default=1000)
+    ap.add_argument("--cpu-sample", type=int, default=8000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sweep-variants", default="")
-    ap.add_argument("--variant", type=int, default=None)
+    ap.add_argument("--variant", default=None, help="f<k> specialised kernel variant k, g<k> general kernel variant k")
     ap.add_argument("--workdir", default=os.environ.get("GSX_BENCH_DIR", "/tmp/gsx_bench"))
     args = ap.parse_args()
-    if args.variant is not None:
-        os.environ["GSX_SEARCH_VARIANT"] = str(args.variant)
+    apply_variant(args)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -343,6 +343,21 @@ int gsx_prepare_guides(const gsx_guide* guides, size_t n, const gsx_params* p, g
     }
     out.wide = bulges || max_total > 27;
     if (max_total + p->dna_bulges > 32) return fail(GSX_ERR_ARG, "guide + PAM + DNA bulges longer than 32 characters");
+    // fast path: no bulges, one PAM pattern for every guide, ACGT-only guides of at most 29 nt
+    out.fast_ok = !out.wide && set_of.size() == 1 && out.pamsets[0].n_pams == 1 && n > 0;
+    if (out.fast_ok) {
+        out.gq.resize(n);
+        for (size_t i = 0; i < n && out.fast_ok; i++) {
+            const GuideRec& r = out.recs[i];
+            if (r.qlen > 29) { out.fast_ok = false; break; }
+            uint64_t v = (uint64_t)r.qlen << 58;
+            for (uint32_t l = 0; l < r.qlen; l++) { if (r.q[l] > 3) { out.fast_ok = false; break; } v |= (uint64_t)r.q[l] << (2 * l); }
+            out.gq[i] = v;
+        }
+        const PamSet& ps = out.pamsets[0];
+        out.plen = ps.plen[0]; out.pampack = 0;
+        for (uint32_t j = 0; j < ps.plen[0]; j++) out.pampack |= (uint32_t)ps.sym[0][j] << (3 * j);
+    }
     return GSX_OK;
 }
 
@@ -390,6 +405,15 @@ static void run_device_job(DeviceJob* job) {
         a.task_counter = d_ctrs + 0; a.match_count = d_ctrs + 1; a.error_flag = d_ctrs + 2; a.stats = d_stats;
         a.guide_nmatch = d_nmatch; a.max_iters = 1u << 28; a.max_pams = prep.max_pams;
         a.p.n_tasks = 2 * n;
+        // fast path (search_fast_kernel) when the batch and the index allow it; GSX_FORCE_GENERAL=1 keeps the general kernel
+        const bool use_fast = prep.fast_ok && !env_int("GSX_FORCE_GENERAL", 0) && n < (1u << 23) &&
+                              di.st[0].d.n_exc == 1 && di.st[1].d.n_exc == 1 && di.st[0].d.n_nrows == 0 && di.st[1].d.n_nrows == 0;
+        const int variant_f = env_int("GSX_FAST_VARIANT", 0);
+        if (use_fast) {
+            uint64_t* d_gq = B.alloc<uint64_t>(n);
+            CK(cudaMemcpyAsync(d_gq, prep.gq.data() + job->g0, (size_t)n * 8, cudaMemcpyHostToDevice, s));
+            a.gq = d_gq; a.pampack = prep.pampack; a.plen = prep.plen;
+        }
 
         CK(cudaEventRecord(ev[0], s));
         uint64_t n_launches = 0;
@@ -398,13 +422,15 @@ static void run_device_job(DeviceJob* job) {
             unsigned long long* d_gcount = B.alloc<unsigned long long>(n, true, s);
             uint32_t spill_cap = 4096;
             for (;;) {
-                int warps = search_grid_warps(false, variant_n, di.sm_count);
+                int warps = use_fast ? search_fast_grid_warps(variant_f, di.sm_count) : search_grid_warps(false, variant_n, di.sm_count);
+                if (warps <= 0) throw std::runtime_error("unknown search kernel variant");
                 uint32_t* d_spill = B.alloc<uint32_t>((size_t)warps * spill_cap * 6);
                 CK(cudaMemsetAsync(d_ctrs, 0, 8 * sizeof(uint32_t), s));
                 CK(cudaMemsetAsync(d_gcount, 0, (size_t)n * 8, s));
                 SearchArgs c = a; c.p.M = (uint32_t)p.threshold; c.p.R = c.p.D = 0; c.p.counting = 1; c.p.match_cap = 0; c.p.spill_cap = spill_cap;
                 c.guide_count = d_gcount; c.spill = d_spill; c.skip = nullptr; c.matches = nullptr;
-                CK(launch_search(c, false, variant_n, di.sm_count, s, nullptr)); n_launches++;
+                if (use_fast) CK(launch_search_fast(c, variant_f, di.sm_count, s)); else CK(launch_search(c, false, variant_n, di.sm_count, s, nullptr));
+                n_launches++;
                 uint32_t h[3]; CK(cudaMemcpyAsync(h, d_ctrs, sizeof h, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s));
                 B.free_one(d_spill);
                 if (h[2] & GSX_KERR_WATCHDOG) throw std::runtime_error("search kernel watchdog tripped");
@@ -425,7 +451,7 @@ static void run_device_job(DeviceJob* job) {
         MatchRec* d_matches = nullptr; uint32_t* d_spill = nullptr; uint32_t n_matches = 0;
         for (int attempt = 0;; attempt++) {
             if (attempt > 12) throw std::runtime_error("search arenas keep overflowing");
-            int warps = search_grid_warps(wide, variant, di.sm_count);
+            int warps = use_fast ? search_fast_grid_warps(variant_f, di.sm_count) : search_grid_warps(wide, variant, di.sm_count);
             if (warps <= 0) throw std::runtime_error("unknown search kernel variant");
             d_matches = B.alloc<MatchRec>(match_cap);
             d_spill = B.alloc<uint32_t>((size_t)warps * spill_cap * (wide ? 8 : 6));
@@ -435,7 +461,8 @@ static void run_device_job(DeviceJob* job) {
             SearchArgs m = a; m.p.M = p.mismatches; m.p.R = p.rna_bulges; m.p.D = p.dna_bulges; m.p.counting = 0;
             m.p.match_cap = (uint32_t)match_cap; m.p.spill_cap = spill_cap; m.spill = d_spill; m.matches = d_matches;
             m.skip = p.threshold > 0 ? d_dropped : nullptr;
-            CK(launch_search(m, wide, variant, di.sm_count, s, nullptr)); n_launches++;
+            if (use_fast) CK(launch_search_fast(m, variant_f, di.sm_count, s)); else CK(launch_search(m, wide, variant, di.sm_count, s, nullptr));
+            n_launches++;
             uint32_t h[3]; CK(cudaMemcpyAsync(h, d_ctrs, sizeof h, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s));
             B.free_one(d_spill);
             if (h[2] & GSX_KERR_WATCHDOG) throw std::runtime_error("search kernel watchdog tripped");

@@ -102,6 +102,10 @@ struct Prepared {
     PamSet pamsets[kMaxPamSets];
     uint32_t max_pams = 1;
     bool wide = false;
+    // fast-path description (search_fast_kernel): valid when fast_ok
+    bool fast_ok = false;
+    std::vector<uint64_t> gq;      // per guide: 2-bit symbols in consumption order | qlen << 58
+    uint32_t pampack = 0, plen = 0;
 };
 }  // namespace gsx
 

@@ -272,6 +272,230 @@ int search_grid_warps(bool wide, int variant, int sm_count) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// search, fast path: the same search specialised for what the headline workload is -- no bulges, one PAM pattern shared
+// by all guides, ACGT-only guides, an index whose only non-ACGT BWT row is the sentinel.  Same tree, same matches, same
+// keys as search_kernel; fewer instructions per node:
+//   * node = 5 words (sp, ep, 64-bit key, task | mismatches << 24 | level << 27); the guide's packed symbols stay in a
+//     register of the lane while it follows one path and are re-read only when the lane pops another guide's node
+//   * strand-dependent constants (block base, C[], sentinel row) are selected from the parameter bank, no shared copy
+//   * all four children are evaluated branch-free; siblings are compacted with two ballots (push count bit 0 / bit 1)
+// ---------------------------------------------------------------------------------------------------------
+template <int WARPS, int CAP, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) search_fast_kernel(SearchArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint32_t FULL = 0xffffffffu;
+    uint64_t* r_key = reinterpret_cast<uint64_t*>(smem_raw + (size_t)warp * CAP * 20);
+    uint32_t* r_sp = reinterpret_cast<uint32_t*>(r_key + CAP);
+    uint32_t* r_ep = r_sp + CAP;
+    uint32_t* r_tlm = r_ep + CAP;
+    const uint32_t gwarp = blockIdx.x * WARPS + warp;
+    const uint32_t scap = a.p.spill_cap;
+    uint32_t* s_base = a.spill + (size_t)gwarp * scap * 6;          // sp | ep | tlm | key (u64)
+    uint64_t* s_key = reinterpret_cast<uint64_t*>(s_base + 4 * (size_t)scap);
+
+    uint32_t head = 0, count = 0, spill_count = 0;
+    bool tasks_remain = true, has = false;
+    uint32_t sp = 0, ep = 0, tlm = 0; uint64_t key = 0, q = 0;
+    unsigned long long n_nodes = 0, n_lookups = 0, n_spilled = 0;     // accumulated by lane 0 only
+    const uint32_t M = a.p.M, plen = a.plen;
+    uint32_t iters = 0;
+
+    for (;;) {
+        if (++iters > a.max_iters) { if (lane == 0) atomicOr(a.error_flag, GSX_KERR_WATCHDOG); break; }
+        uint32_t need_mask = __ballot_sync(FULL, !has);
+        if (need_mask) {
+            uint32_t n_need = __popc(need_mask);
+            if (count < n_need && spill_count > 0) {
+                uint32_t take = spill_count < 64u ? spill_count : 64u;
+                for (uint32_t j = lane; j < take; j += 32) {
+                    uint32_t i = spill_count - take + j, slot = (head + count + j) & (CAP - 1);
+                    r_sp[slot] = s_base[i]; r_ep[slot] = s_base[scap + i]; r_tlm[slot] = s_base[2 * scap + i]; r_key[slot] = s_key[i];
+                }
+                __syncwarp();
+                count += take; spill_count -= take;
+            }
+            if (count < n_need && tasks_remain) {
+                uint32_t t = 0;
+                if (lane == 0) t = atomicAdd(a.task_counter, 1u);
+                t = __shfl_sync(FULL, t, 0);
+                if (t >= a.p.n_tasks) tasks_remain = false;
+                else if (!(a.skip && a.skip[t >> 1])) {
+                    if (lane == 0) {
+                        uint32_t slot = (head + count) & (CAP - 1);
+                        r_sp[slot] = 0; r_ep[slot] = ((t & 1u) ? a.st[1].n : a.st[0].n) - 1u; r_tlm[slot] = t; r_key[slot] = 0;
+                    }
+                    __syncwarp();
+                    count += 1;
+                }
+            }
+            uint32_t take = count < n_need ? count : n_need;
+            uint32_t rank = __popc(need_mask & lt_mask);
+            if (!has && rank < take) {
+                uint32_t slot = (head + count - 1 - rank) & (CAP - 1);
+                sp = r_sp[slot]; ep = r_ep[slot]; tlm = r_tlm[slot]; key = r_key[slot];
+                q = __ldg(a.gq + ((tlm & 0xFFFFFFu) >> 1));
+                has = true;
+            }
+            __syncwarp();
+            count -= take;
+        }
+        const uint32_t act = __ballot_sync(FULL, has);
+        if (act == 0) {
+            if (count == 0 && spill_count == 0 && !tasks_remain) break;
+            continue;
+        }
+        // ---- occurrence lookups -----------------------------------------------------------------------------
+        const bool s1 = (tlm & 1u) != 0;
+        uint32_t os0 = 0, os1 = 0, os2 = 0, os3 = 0, oe0 = 0, oe1 = 0, oe2 = 0, oe3 = 0;
+        bool two = false;
+        if (has) {
+            const OccBlock* blocks = s1 ? a.st[1].blocks : a.st[0].blocks;
+            const uint32_t dollar = s1 ? a.st[1].exc_lo : a.st[0].exc_lo;
+            const uint32_t e1 = ep + 1u, bs = sp >> 6, be = e1 >> 6;
+            two = be != bs;
+            Blk B0 = ld_block(blocks + bs);
+            Blk B1 = B0;
+            if (two) B1 = ld_block(blocks + be);
+            {
+                uint32_t r = sp & 63u; uint64_t mask = r ? (~0ull >> (64 - r)) : 0ull;
+                uint64_t hi = B0.hi & mask, lo = B0.lo & mask;
+                uint32_t t = __popcll(hi & lo), g = __popcll(hi) - t, c = __popcll(lo) - t;
+                uint32_t aa = r - t - g - c - ((dollar >= sp - r && dollar < sp) ? 1u : 0u);
+                os0 = B0.c0 + aa; os1 = B0.c1 + c; os2 = B0.c2 + g; os3 = B0.c3 + t;
+            }
+            {
+                uint32_t r = e1 & 63u; uint64_t mask = r ? (~0ull >> (64 - r)) : 0ull;
+                uint64_t hi = B1.hi & mask, lo = B1.lo & mask;
+                uint32_t t = __popcll(hi & lo), g = __popcll(hi) - t, c = __popcll(lo) - t;
+                uint32_t aa = r - t - g - c - ((dollar >= e1 - r && dollar < e1) ? 1u : 0u);
+                oe0 = B1.c0 + aa; oe1 = B1.c1 + c; oe2 = B1.c2 + g; oe3 = B1.c3 + t;
+            }
+        }
+        if (lane == 0) { n_nodes += __popc(act); }
+        {
+            uint32_t two_mask = __ballot_sync(FULL, has && two);
+            if (lane == 0) n_lookups += __popc(act) + __popc(two_mask);
+        }
+        // ---- children (branch-free) ---------------------------------------------------------------------------
+        const uint32_t lvl = tlm >> 27, mm = (tlm >> 24) & 7u, qlen = (uint32_t)(q >> 58);
+        const bool in_proto = lvl < qlen;
+        const uint32_t c = in_proto ? ((uint32_t)(q >> (2u * lvl)) & 3u) : ((a.pampack >> (3u * (lvl - qlen))) & 7u);
+        const bool allow = in_proto ? (mm < M) : (c == 4u);
+        const bool final_lvl = (lvl + 1u == qlen + plen);
+        const uint32_t w0 = oe0 - os0, w1 = oe1 - os1, w2 = oe2 - os2, w3 = oe3 - os3;
+        const bool v0 = has && w0 && (c == 0u || allow), v1 = has && w1 && (c == 1u || allow);
+        const bool v2 = has && w2 && (c == 2u || allow), v3 = has && w3 && (c == 3u || allow);
+        const uint32_t C0 = s1 ? a.st[1].C[0] : a.st[0].C[0], C1 = s1 ? a.st[1].C[1] : a.st[0].C[1];
+        const uint32_t C2 = s1 ? a.st[1].C[2] : a.st[0].C[2], C3 = s1 ? a.st[1].C[3] : a.st[0].C[3];
+        const uint64_t key5 = key * 5ull;
+        const uint32_t tlm1 = tlm + (1u << 27);
+        const uint32_t mis = in_proto ? (1u << 24) : 0u;                 // a protospacer child other than c costs one mismatch
+        // child s: sp' = Cs + os_s, ep' = sp' + w_s - 1, key' = key5 + digit_s, tlm' = tlm1 + (s != c ? mis : 0)
+#define GSX_CH_SP(s) (C##s + os##s)
+#define GSX_CH_DIGIT(s) (in_proto ? (c == (s) ? 0u : 1u + (s)) : ((s) < 3 ? (uint32_t)(s) : 4u))
+#define GSX_CH_TLM(s) (tlm1 + (c == (s) ? 0u : mis))
+        // ---- finished alignments (rare) ---------------------------------------------------------------------------
+        if (__any_sync(FULL, final_lvl && (v0 || v1 || v2 || v3))) {
+#define GSX_EMIT(s)                                                                                                   \
+            {                                                                                                         \
+                const bool e = final_lvl && v##s;                                                                      \
+                const uint32_t emask = __ballot_sync(FULL, e);                                                         \
+                if (emask) {                                                                                          \
+                    if (a.p.counting) {                                                                               \
+                        if (e) atomicAdd(a.guide_count + ((tlm & 0xFFFFFFu) >> 1), (unsigned long long)w##s);          \
+                    } else {                                                                                          \
+                        uint32_t base = 0; const int leader = __ffs(emask) - 1;                                       \
+                        if ((int)lane == leader) base = atomicAdd(a.match_count, (uint32_t)__popc(emask));            \
+                        base = __shfl_sync(FULL, base, leader);                                                       \
+                        if (e) {                                                                                      \
+                            const uint32_t slot = base + __popc(emask & lt_mask);                                     \
+                            if (slot < a.p.match_cap) {                                                               \
+                                MatchRec m; m.key_hi = 0; m.key_lo = key5 + GSX_CH_DIGIT(s); m.task = tlm & 0xFFFFFFu;  \
+                                m.sp = GSX_CH_SP(s); m.width = w##s;                                                   \
+                                m.info = ((GSX_CH_TLM(s) >> 24) & 7u) | ((lvl + 1u) << 24);                            \
+                                a.matches[slot] = m;                                                                  \
+                                atomicAdd(a.guide_nmatch + ((tlm & 0xFFFFFFu) >> 1), 1u);                              \
+                            } else atomicOr(a.error_flag, GSX_KERR_MATCH_OVERFLOW);                                   \
+                        }                                                                                             \
+                    }                                                                                                 \
+                }                                                                                                     \
+            }
+            GSX_EMIT(0) GSX_EMIT(1) GSX_EMIT(2) GSX_EMIT(3)
+#undef GSX_EMIT
+        }
+        // ---- keep one child in registers, push the siblings ---------------------------------------------------------
+        const uint32_t nvalid = final_lvl ? 0u : ((uint32_t)v0 + (uint32_t)v1 + (uint32_t)v2 + (uint32_t)v3);
+        const uint32_t pushes = nvalid ? nvalid - 1u : 0u;
+        const uint32_t b0 = __ballot_sync(FULL, pushes & 1u), b1 = __ballot_sync(FULL, pushes & 2u);
+        const uint32_t total = __popc(b0) + 2u * __popc(b1);
+        if (total) {
+            if (count + total > (uint32_t)CAP) {                          // spill the 64 oldest nodes
+                if (spill_count + 64u > scap) { if (lane == 0) atomicOr(a.error_flag, GSX_KERR_SPILL_OVERFLOW); }
+                else {
+                    for (uint32_t j = lane; j < 64u; j += 32) {
+                        uint32_t slot = (head + j) & (CAP - 1), i = spill_count + j;
+                        s_base[i] = r_sp[slot]; s_base[scap + i] = r_ep[slot]; s_base[2 * scap + i] = r_tlm[slot]; s_key[i] = r_key[slot];
+                    }
+                    spill_count += 64u; if (lane == 0) n_spilled += 64;
+                }
+                __syncwarp();
+                head = (head + 64u) & (CAP - 1); count -= 64u;
+            }
+        }
+        uint32_t slot = head + count + __popc(b0 & lt_mask) + 2u * __popc(b1 & lt_mask);
+        bool kept = false;
+        uint32_t nsp = sp, nep = ep, ntlm = tlm; uint64_t nkey = key;
+#define GSX_CHILD(s)                                                                                                  \
+        if (v##s && !final_lvl) {                                                                                     \
+            const uint32_t csp = GSX_CH_SP(s), cep = csp + w##s - 1u, ctlm = GSX_CH_TLM(s);                             \
+            const uint64_t ckey = key5 + GSX_CH_DIGIT(s);                                                              \
+            if (!kept) { kept = true; nsp = csp; nep = cep; ntlm = ctlm; nkey = ckey; }                                 \
+            else { const uint32_t w = slot & (CAP - 1); r_sp[w] = csp; r_ep[w] = cep; r_tlm[w] = ctlm; r_key[w] = ckey; slot++; } \
+        }
+        GSX_CHILD(0) GSX_CHILD(1) GSX_CHILD(2) GSX_CHILD(3)
+#undef GSX_CHILD
+#undef GSX_CH_SP
+#undef GSX_CH_DIGIT
+#undef GSX_CH_TLM
+        if (total) { __syncwarp(); count += total; }
+        has = kept; sp = nsp; ep = nep; tlm = ntlm; key = nkey;
+    }
+    if (lane == 0) { atomicAdd(a.stats + 0, n_nodes); atomicAdd(a.stats + 1, n_lookups); atomicAdd(a.stats + 2, n_spilled); }
+}
+
+template <int WARPS, int CAP, int MINB>
+static cudaError_t launch_fast_t(const SearchArgs& a, int sm_count, cudaStream_t s) {
+    size_t smem = (size_t)WARPS * CAP * 20;
+    auto k = search_fast_kernel<WARPS, CAP, MINB>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k<<<sm_count * MINB, WARPS * 32, smem, s>>>(a);
+    return cudaGetLastError();
+}
+
+#define GSX_FAST_VARIANTS(X) \
+    X(0, 8, 256, 4) /* 1024 thr/SM, 160 KB smem */ \
+    X(1, 8, 256, 3) /* 768 thr/SM */ \
+    X(2, 8, 128, 6) /* 1536 thr/SM */ \
+    X(3, 8, 128, 8) /* 2048 thr/SM (<= 32 regs) */ \
+    X(4, 8, 256, 5) /* 1280 thr/SM, 200 KB smem */
+
+cudaError_t launch_search_fast(const SearchArgs& a, int variant, int sm_count, cudaStream_t s) {
+#define X(V, WARPS, CAP, MINB) if (variant == V) return launch_fast_t<WARPS, CAP, MINB>(a, sm_count, s);
+    GSX_FAST_VARIANTS(X)
+#undef X
+    return cudaErrorInvalidValue;
+}
+int search_fast_grid_warps(int variant, int sm_count) {
+#define X(V, WARPS, CAP, MINB) if (variant == V) return sm_count * MINB * WARPS;
+    GSX_FAST_VARIANTS(X)
+#undef X
+    return -1;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // arrange: group by guide, order, de-duplicate, expand
 // ---------------------------------------------------------------------------------------------------------
 // exclusive scan of in[0..n) into out[0..n], out[n] = total; one block

@@ -28,6 +28,10 @@ struct SearchArgs {
     uint32_t* error_flag;
     uint32_t max_iters;
     uint32_t max_pams;
+    // fast path only (search_fast_kernel): one PAM for all guides, ACGT-only guides, sentinel-only exception tables
+    const uint64_t* gq;                // per guide: 2-bit symbol codes in consumption order | qlen << 58
+    uint32_t pampack;                  // 3 bits per PAM character in consumption order (4 = N wildcard, 5 = never matches)
+    uint32_t plen;
 };
 
 struct LocateArgs {
@@ -57,6 +61,8 @@ struct SpecArgs {
 cudaError_t upload_cfd_tables();
 int search_grid_warps(bool wide, int variant, int sm_count);
 cudaError_t launch_search(const SearchArgs& a, bool wide, int variant, int sm_count, cudaStream_t s, int* warps_total);
+int search_fast_grid_warps(int variant, int sm_count);
+cudaError_t launch_search_fast(const SearchArgs& a, int variant, int sm_count, cudaStream_t s);
 cudaError_t launch_scan(const uint32_t* in, uint32_t* out, uint32_t n, cudaStream_t s);
 cudaError_t launch_scatter(const MatchRec* m, uint32_t n, const uint32_t* moff, uint32_t* cursor, uint32_t* by_guide, cudaStream_t s);
 cudaError_t launch_order(const MatchRec* m, const uint32_t* moff, const uint32_t* by_guide, uint32_t n_guides, uint32_t n_dist,

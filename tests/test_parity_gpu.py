@@ -178,3 +178,52 @@ def test_gpu_built_index_with_repeats_and_dense_samples(gsx, tmp_path):
         want = "".join(oix.process_kmer(O.make_opts(mismatches=2), "g%d" % i, s, p) for i, (s, p) in enumerate(guides))
         assert rows_txt.decode() == want
         r.close(); ix.close()
+
+
+@pytest.fixture(scope="module")
+def seeded_case(gsx, tmp_path_factory):
+    """1.5 Mb uniform genome, 400 NGG guides: eligible for the specialised search kernel (one PAM, ACGT guides, no N)"""
+    import oracle as O
+    import synth
+    d = str(tmp_path_factory.mktemp("fast"))
+    synth.make_dataset(d, 1_500_000, 5, 400, seed=21, name="f")
+    fa, gcsv = os.path.join(d, "f.fa"), os.path.join(d, "f.guides.csv")
+    ix = gsx.Index.build(fa, devices=[0])
+    oix = O.Index(fa)
+    yield d, gcsv, ix, oix
+    ix.close()
+
+
+@pytest.mark.parametrize("kw", [dict(mismatches=3), dict(mismatches=4, max_off_targets=3), dict(mismatches=2, threshold=1),
+                                dict(mismatches=0), dict(mismatches=3, fmt="sam")])
+def test_fast_and_general_kernels_agree_with_oracle(gsx, seeded_case, monkeypatch, kw):
+    import oracle as O
+    d, gcsv, ix, oix = seeded_case
+    fmt = kw.get("fmt", "csv")
+    okw = {k: v for k, v in kw.items()}
+    want = os.path.join(d, "o.out")
+    oix.enumerate_file(O.make_opts(**okw), gcsv, want, nthreads=8)
+    want = open(want, "rb").read()
+    p = gsx.make_params(mismatches=kw["mismatches"], threshold=kw.get("threshold", -1), max_off_targets=kw.get("max_off_targets", -1))
+    nodes = {}
+    for force_general in ("0", "1"):
+        monkeypatch.setenv("GSX_FORCE_GENERAL", force_general)
+        out = os.path.join(d, "g%s.out" % force_general)
+        _, ctr = ix.enumerate_file(gcsv, out, p, fmt=fmt)
+        assert open(out, "rb").read() == want
+        nodes[force_general] = (ctr["nodes"], ctr["lookups"], ctr["matches"], ctr["hits"])
+    assert nodes["0"] == nodes["1"]          # same tree, same lookups, whichever kernel walks it
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
+def test_every_fast_kernel_variant(gsx, seeded_case, monkeypatch, variant):
+    import oracle as O
+    d, gcsv, ix, oix = seeded_case
+    monkeypatch.setenv("GSX_FAST_VARIANT", str(variant))
+    monkeypatch.setenv("GSX_SPILL_CAP", "64" if variant % 2 else "2048")
+    monkeypatch.setenv("GSX_MATCH_CAP", "100" if variant == 2 else "0")
+    want = os.path.join(d, "o4.out")
+    oix.enumerate_file(O.make_opts(mismatches=4), gcsv, want, nthreads=8)
+    out = os.path.join(d, "v.out")
+    ix.enumerate_file(gcsv, out, gsx.make_params(mismatches=4))
+    assert open(out, "rb").read() == open(want, "rb").read()

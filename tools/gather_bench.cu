@@ -58,6 +58,44 @@ __global__ void chain_kernel(const E32* __restrict__ a, uint64_t n_elems, uint32
     if (acc == 0x12345678u) out[0] = acc;
 }
 
+// one 64-byte (PAIR = 2) or 128-byte (PAIR = 4) element per lane group, fetched by ONE warp-level load instruction:
+// lane j of a group loads sector j of the group's element, so the request carries 2 (4) sectors of one 128 B line
+template <int PAIR>
+__global__ void grouped_kernel(const E32* __restrict__ a, uint64_t n_elems, uint32_t iters, uint32_t* out) {
+    uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, acc = 0;
+    uint32_t grp = tid / PAIR, sub = tid % PAIR;
+    uint32_t ctr = grp * 2654435761u;
+    for (uint32_t it = 0; it < iters; it++) {
+        uint32_t r[4][8];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            ctr += 0x9e3779b9u;
+            uint64_t idx = (((uint64_t)mix(ctr) * (n_elems / PAIR)) >> 32) * PAIR + sub;
+            ld32(a + idx, r[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) acc ^= r[u][0] ^ r[u][7];
+    }
+    if (acc == 0x12345678u) out[0] = acc;
+}
+
+__device__ __forceinline__ void ld32_hint256(const E32* p, uint32_t (&r)[8]) {
+    asm volatile("ld.global.nc.L2::256B.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "l"(p));
+}
+__global__ void hint_kernel(const E32* __restrict__ a, uint64_t n_elems, uint32_t iters, uint32_t* out) {
+    uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, acc = 0;
+    uint32_t ctr = tid * 2654435761u;
+    for (uint32_t it = 0; it < iters; it++) {
+        uint32_t r[4][8];
+#pragma unroll
+        for (int u = 0; u < 4; u++) { ctr += 0x9e3779b9u; uint64_t idx = ((uint64_t)mix(ctr) * n_elems) >> 32; ld32_hint256(a + idx, r[u]); }
+#pragma unroll
+        for (int u = 0; u < 4; u++) acc ^= r[u][0] ^ r[u][7];
+    }
+    if (acc == 0x12345678u) out[0] = acc;
+}
+
 __global__ void fill_kernel(uint32_t* p, uint64_t n) {
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) p[i] = mix((uint32_t)i);
 }
@@ -91,6 +129,17 @@ int main(int argc, char** argv) {
                 float ms = time_ms([&] { indep_kernel<64, 4><<<blocks, 256>>>(a, n_elems, iters, out); });
                 double loads = (double)blocks * 256 * iters * 4;
                 printf("{\"mode\":\"indep\",\"bytes\":64,\"array_gb\":%.2f,\"threads_per_sm\":%d,\"unroll\":4,\"ms\":%.3f,\"gelems_per_s\":%.2f,\"gb_per_s\":%.1f}\n", gb, tps, ms, loads / ms / 1e6, loads * 64 / ms / 1e6);
+            }
+            if (tps == 1024) {
+                float ms = time_ms([&] { grouped_kernel<2><<<blocks, 256>>>(a, n_elems, iters, out); });
+                double elems = (double)blocks * 256 * iters * 4 / 2;
+                printf("{\"mode\":\"grouped\",\"bytes\":64,\"array_gb\":%.2f,\"threads_per_sm\":%d,\"ms\":%.3f,\"gelems_per_s\":%.2f,\"gb_per_s\":%.1f}\n", gb, tps, ms, elems / ms / 1e6, elems * 64 / ms / 1e6);
+                ms = time_ms([&] { grouped_kernel<4><<<blocks, 256>>>(a, n_elems, iters, out); });
+                elems = (double)blocks * 256 * iters * 4 / 4;
+                printf("{\"mode\":\"grouped\",\"bytes\":128,\"array_gb\":%.2f,\"threads_per_sm\":%d,\"ms\":%.3f,\"gelems_per_s\":%.2f,\"gb_per_s\":%.1f}\n", gb, tps, ms, elems / ms / 1e6, elems * 128 / ms / 1e6);
+                ms = time_ms([&] { hint_kernel<<<blocks, 256>>>(a, n_elems, iters, out); });
+                double loads = (double)blocks * 256 * iters * 4;
+                printf("{\"mode\":\"indep_L2_256B_hint\",\"bytes\":32,\"array_gb\":%.2f,\"threads_per_sm\":%d,\"ms\":%.3f,\"gsectors_per_s\":%.2f,\"gb_per_s\":%.1f}\n", gb, tps, ms, loads / ms / 1e6, loads * 32 / ms / 1e6);
             }
             auto chain = [&](int chains, auto kern) {
                 float ms = time_ms([&] { kern<<<blocks, 256>>>(a, n_elems, iters, out); });
