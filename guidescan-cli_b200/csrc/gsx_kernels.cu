@@ -431,17 +431,15 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) search_fast_kernel(SearchArg
         const uint32_t b0 = __ballot_sync(FULL, pushes & 1u), b1 = __ballot_sync(FULL, pushes & 2u);
         const uint32_t total = __popc(b0) + 2u * __popc(b1);
         if (total) {
-            if (count + total > (uint32_t)CAP) {                          // spill the 64 oldest nodes
-                if (spill_count + 64u > scap) { if (lane == 0) atomicOr(a.error_flag, GSX_KERR_SPILL_OVERFLOW); }
+            while (count + total > (uint32_t)CAP) {                       // spill the 32 oldest nodes (total can reach 96)
+                if (spill_count + 32u > scap) { if (lane == 0) atomicOr(a.error_flag, GSX_KERR_SPILL_OVERFLOW); }
                 else {
-                    for (uint32_t j = lane; j < 64u; j += 32) {
-                        uint32_t slot = (head + j) & (CAP - 1), i = spill_count + j;
-                        s_base[i] = r_sp[slot]; s_base[scap + i] = r_ep[slot]; s_base[2 * scap + i] = r_tlm[slot]; s_key[i] = r_key[slot];
-                    }
-                    spill_count += 64u; if (lane == 0) n_spilled += 64;
+                    const uint32_t slot = (head + lane) & (CAP - 1), i = spill_count + lane;
+                    s_base[i] = r_sp[slot]; s_base[scap + i] = r_ep[slot]; s_base[2 * scap + i] = r_tlm[slot]; s_key[i] = r_key[slot];
+                    spill_count += 32u; if (lane == 0) n_spilled += 32;
                 }
                 __syncwarp();
-                head = (head + 64u) & (CAP - 1); count -= 64u;
+                head = (head + 32u) & (CAP - 1); count -= 32u;
             }
         }
         uint32_t slot = head + count + __popc(b0 & lt_mask) + 2u * __popc(b1 & lt_mask);

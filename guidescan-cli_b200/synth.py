@@ -49,10 +49,11 @@ def sample_guides(g: np.ndarray, n_guides: int, seed: int, margin: int = 1000):
     return pos, kmers
 
 
-def plant(g: np.ndarray, kmers: np.ndarray, seed: int, dists=(1, 2, 3, 4), margin: int = 1000) -> None:
+def plant(g: np.ndarray, kmers: np.ndarray, seed: int, dists=(1, 2, 3, 4), margin: int = 1000):
     """For each guide and each d: a copy with exactly d substitutions in the protospacer, in place."""
     rng = np.random.default_rng(seed + 2000003)
     G = len(g)
+    placed = []
     for i in range(len(kmers)):
         for d in dists:
             c = kmers[i].copy()
@@ -61,10 +62,13 @@ def plant(g: np.ndarray, kmers: np.ndarray, seed: int, dists=(1, 2, 3, 4), margi
                 alt = [b for b in b"ACGT" if b != c[w]]
                 c[w] = alt[rng.integers(0, 3)]
             c[20] = _ACGT[rng.integers(0, 4)]
-            if rng.random() < 0.5:
+            rc = bool(rng.random() < 0.5)
+            if rc:
                 c = revcomp_bytes(c)
             at = int(rng.integers(margin, G - margin - 23))
             g[at:at + 23] = c
+            placed.append((i, d, at, rc))
+    return placed
 
 
 def chromosome_table(G: int, n_chr: int):

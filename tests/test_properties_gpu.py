@@ -1,0 +1,122 @@
+"""GPU tests at BASELINE.json's full sizes through size-independent properties (the oracle cannot run these sizes in
+seconds): every reported hit is re-verified against the genome text, every intact on-target site and planted copy is
+found, hits are ordered by distance, and the float32 specificity is recomputed from the per-hit CFDs."""
+import numpy as np
+import pytest
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(1500)]
+
+COMP = np.zeros(256, dtype=np.uint8)
+for a, b in zip(b"ACGTN", b"TGCAN"):
+    COMP[a] = b
+
+
+def _run_case(G, n_chr, n_guides, seed, n_plant, brute_guides):
+    import gsx
+    import synth
+    g = synth.make_genome(G, seed)
+    pos, kmers = synth.sample_guides(g, n_guides, seed)
+    placed = synth.plant(g, kmers[:n_plant], seed)
+    chroms = synth.chromosome_table(G, n_chr)
+    ix = gsx.Index.build_from_text(g, chroms, devices=[0])
+    arr = (gsx.Guide * n_guides)()
+    keep = [kmers[i, :20].tobytes() for i in range(n_guides)]
+    for i, sq in enumerate(keep):
+        arr[i] = gsx.Guide(sq, b"NGG")
+    r = ix.enumerate_raw(arr, n_guides, gsx.make_params(mismatches=3))
+    ga, ha = r.guide_arrays(), r.hit_arrays()
+    nh = r.n_hits
+    assert nh == int(ga["n_hits"].sum()) and nh > n_guides // 2
+    hit_guide = np.repeat(np.arange(n_guides), ga["n_hits"])
+    first = ga["first_hit"].astype(np.int64)
+    assert np.array_equal(first, np.concatenate([[0], np.cumsum(ga["n_hits"].astype(np.int64))[:-1]]))
+
+    # 1. every hit is a true site: text at the reported absolute position, in guide orientation, within `distance`
+    #    substitutions of the protospacer and followed by xGG
+    ab = ha["abs_pos"]
+    minus = ab < 0
+    start = np.where(minus, -ab, ab - 22)                       # '+': abs is the 0-based END, '-': abs is the 0-based start
+    inside = (start >= 0) & (start + 23 <= G)
+    idx = start[inside][:, None] + np.arange(23)[None, :]
+    txt = g[idx]
+    mi = minus[inside]
+    txt[mi] = COMP[txt[mi][:, ::-1]]
+    gk = kmers[hit_guide[inside]]
+    mism = (txt[:, :20] != gk[:, :20]).sum(axis=1)
+    assert np.array_equal(mism, ha["distance"][inside].astype(np.int64))
+    assert np.all(txt[:, 21] == ord("G")) and np.all(txt[:, 22] == ord("G"))
+    assert np.all(ha["distance"] <= 3)
+    # strand / index bookkeeping (process.hpp:104,111): forward index <=> '-' strand
+    assert np.array_equal(ha["index_id"] == 0, minus | (ab == 0))
+
+    # 2. ordering: distance ascending inside a guide, forward-index hits before reverse-index hits inside a distance
+    same = hit_guide[1:] == hit_guide[:-1]
+    assert np.all(ha["distance"][1:][same] >= ha["distance"][:-1][same])
+    same_d = same & (ha["distance"][1:] == ha["distance"][:-1])
+    assert np.all(ha["index_id"][1:][same_d] >= ha["index_id"][:-1][same_d])
+
+    # 3. recall on what was put there: intact on-target sites and intact planted copies
+    keyset = set(zip(hit_guide.tolist(), ab.tolist()))
+    intact = np.all(g[pos[:, None] + np.arange(23)[None, :]] == kmers, axis=1)
+    assert intact.sum() > 0.9 * n_guides
+    for i in np.nonzero(intact)[0][:20000]:
+        assert (int(i), int(pos[i]) + 22) in keyset
+    n_checked = 0
+    for (i, d, at, rc) in placed:
+        site = g[at:at + 23]
+        s = COMP[site[::-1]] if rc else site
+        dd = int((s[:20] != kmers[i, :20]).sum())
+        if dd <= 3 and s[21] == ord("G") and s[22] == ord("G"):
+            assert (i, -at if rc else at + 22) in keyset
+            n_checked += 1
+    assert n_checked > n_plant
+
+    # 4. specificity = 1 / (float32 running sum of the counted CFDs, +1 without a perfect match), printer.hpp:244-300
+    cfd, counted = ha["cfd"], ha["counted"]
+    spec = ga["specificity"]
+    for gidx in np.random.default_rng(0).choice(n_guides, 3000, replace=False):
+        b, n = int(first[gidx]), int(ga["n_hits"][gidx])
+        ssum = np.float32(0.0)
+        for h in range(b, b + n):
+            if counted[h]:
+                ssum = np.float32(ssum + cfd[h])
+        if n == 0:
+            assert spec[gidx] == np.float32(1.0)
+            continue
+        if not ga["perfect_match"][gidx]:
+            ssum = np.float32(ssum + np.float32(1.0))
+        assert spec[gidx] == (np.float32(1.0) / ssum if ssum > 0 else np.float32(0.0))
+
+    # 5. brute-force recall for a few guides: scan both strands for <= 3 mismatches + NGG
+    for gidx in range(brute_guides):
+        want = set()
+        for strand, text in ((+1, g), (-1, None)):
+            q = kmers[gidx, :20] if strand > 0 else COMP[kmers[gidx, :20][::-1]]
+            # '+' site at p: text[p:p+20] ~ q, text[p+21:p+23] == GG ; '-' site at p: text[p:p+3] == CCN, text[p+3:p+23] ~ revcomp(q)
+            off = 0 if strand > 0 else 3
+            mm = np.zeros(G - 23, dtype=np.uint8)
+            for j in range(20):
+                mm += g[off + j:off + j + G - 23] != q[j]
+            if strand > 0:
+                ok = (mm <= 3) & (g[21:21 + G - 23] == ord("G")) & (g[22:22 + G - 23] == ord("G"))
+                want |= {int(p) + 22 for p in np.nonzero(ok)[0]}
+            else:
+                ok = (mm <= 3) & (g[0:G - 23] == ord("C")) & (g[1:1 + G - 23] == ord("C"))
+                want |= {-int(p) for p in np.nonzero(ok)[0]}
+        b, n = int(first[gidx]), int(ga["n_hits"][gidx])
+        assert set(ab[b:b + n].tolist()) == want
+    ctr = r.counters()
+    r.close(); ix.close()
+    return ctr
+
+
+def test_config1_size_120mb_100k_guides():
+    """BASELINE.json configs[1]: 120 Mb synthetic genome, 100k guides, mismatches=3"""
+    ctr = _run_case(120_000_000, 8, 100_000, seed=2, n_plant=1500, brute_guides=2)
+    assert ctr["nodes"] > 100_000 * 60_000
+
+
+def test_config2_size_3100mb():
+    """BASELINE.json configs[2] genome size (3.1 Gb); 200k guides keep the host-side verification short"""
+    ctr = _run_case(3_100_000_000, 24, 200_000, seed=3, n_plant=1000, brute_guides=0)
+    assert ctr["nodes"] > 200_000 * 100_000
