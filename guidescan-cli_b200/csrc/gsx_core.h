@@ -300,7 +300,7 @@ GSX_HD uint32_t locate_row_t(const DevStrand& st, uint32_t row, uint32_t* steps,
         }
         if (!is_exc) {
             uint32_t c[4], o[4]; uint64_t hi, lo;
-            ld(st.blocks + (row >> 6), c, hi, lo);
+            ld(block_ptr(st, row >> 6), c, hi, lo);
             block_occ(st, c, hi, lo, row, o);
             uint32_t s = block_sym(hi, lo, row);
             row = st.C[s] + o[s];
@@ -355,6 +355,47 @@ GSX_HD void guide_specificity(const SpecArgs& a, uint32_t g) {
     if (n == 0 && !a.sam_rule) spec = 1.0f;                                       // NA row, printer.hpp:190-199
     else { if (!perfect) cfd_sum += 1.0f; if (cfd_sum > 0.0f) spec = 1.0f / cfd_sum; }
     a.specificity[g] = spec; a.perfect[g] = perfect ? 1 : 0;
+}
+
+// ---- look-ahead pruning (blk_shift = 7 indexes, specialised search kernel) --------------------------------------
+// hi[j], lo[j]: bit planes of t_j for the 64 rows of one block, t_0 being the BWT symbol itself.  A backward search
+// sitting on row r at level lvl will consume t_0(r), t_1(r), ... against the query characters of levels lvl, lvl+1, ...
+// Returns a 4-bit mask: bit s is set iff some row of [sp, ep] (all in this block) with t_0 = s can consume its next
+// J = min(7, total - lvl) characters with at most `budget` further protospacer mismatches and every fixed PAM
+// character matched.  A child whose bit is clear can never reach the final level, so it is not expanded: the set of
+// emitted matches is unchanged.  Planes hold arbitrary symbols where the true one is not A/C/G/T or lies before the
+// text start; that can only set bits spuriously (no pruning), never clear one that should be set, because such a
+// path cannot be continued by an A/C/G/T query character in the first place.
+GSX_HD uint32_t viable_children(const uint64_t hi[7], const uint64_t lo[7], uint32_t sp, uint32_t ep, uint32_t lvl,
+                                uint32_t qlen, uint32_t total, uint64_t q, uint32_t pampack, uint32_t budget) {
+    const uint32_t r0 = sp & 63u, r1 = ep & 63u;
+    uint64_t rows = (r1 == 63u ? ~0ull : ((1ull << (r1 + 1u)) - 1ull)) & ~((1ull << r0) - 1ull);
+    uint64_t c0 = 0, c1 = 0, c2 = 0, dead = 0;          // bit-sliced per-row mismatch counter (0..7)
+    const uint32_t left = total - lvl;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (uint32_t j = 0; j < 7; j++) {
+        if (j < left) {
+            const uint32_t L = lvl + j;
+            uint32_t sym; bool proto = L < qlen, wild = false, kill = false;
+            if (proto) sym = (uint32_t)(q >> (2u * L)) & 3u;
+            else { uint32_t pc = (pampack >> (3u * (L - qlen))) & 7u; sym = pc & 3u; wild = pc == 4u; kill = pc > 4u; }
+            const uint64_t eq = ~(hi[j] ^ ((sym & 2u) ? ~0ull : 0ull)) & ~(lo[j] ^ ((sym & 1u) ? ~0ull : 0ull));
+            if (proto) {
+                const uint64_t mis = ~eq;
+                const uint64_t k0 = c0 & mis; c0 ^= mis;
+                const uint64_t k1 = c1 & k0; c1 ^= k0;
+                c2 ^= k1;
+            } else if (kill) dead = ~0ull;
+            else if (!wild) dead |= ~eq;
+        }
+    }
+    const uint64_t B0 = (budget & 1u) ? ~0ull : 0ull, B1 = (budget & 2u) ? ~0ull : 0ull, B2 = (budget & 4u) ? ~0ull : 0ull;
+    const uint64_t gt = (c2 & ~B2) | (~(c2 ^ B2) & ((c1 & ~B1) | (~(c1 ^ B1) & (c0 & ~B0))));
+    const uint64_t alive = rows & ~dead & ~gt;
+    const uint64_t h0 = hi[0], l0 = lo[0];
+    return ((alive & ~h0 & ~l0) ? 1u : 0u) | ((alive & ~h0 & l0) ? 2u : 0u) | ((alive & h0 & ~l0) ? 4u : 0u) | ((alive & h0 & l0) ? 8u : 0u);
 }
 
 // ordering of the matches of one guide: bucket (mismatches) ascending, forward index before reverse index, string order

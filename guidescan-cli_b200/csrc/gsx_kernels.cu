@@ -157,11 +157,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) search_kernel(SearchArgs a) 
         const uint32_t strand = nd.task & 1u;
         const DevStrand& st = s_st[strand];
         if (has) {
-            const OccBlock* blocks = st.blocks;
             uint32_t bs = nd.sp >> 6, be = (nd.ep + 1u) >> 6;
-            Blk B0 = ld_block(blocks + bs);
+            Blk B0 = ld_block(block_ptr(st, bs));
             Blk B1 = B0;
-            if (be != bs) B1 = ld_block(blocks + be);
+            if (be != bs) B1 = ld_block(block_ptr(st, be));
             n_nodes++; n_lookups += (be != bs) ? 2 : 1;
             uint32_t c0[4] = {B0.c0, B0.c1, B0.c2, B0.c3};
             block_occ(st, c0, B0.hi, B0.lo, nd.sp, os);
@@ -628,7 +627,7 @@ __global__ void rank_query_kernel(DevStrand st, const uint32_t* rows, const uint
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         uint32_t row = rows[i], s = syms[i], r = 0;
         if (s < 4) {
-            Blk B = ld_block(st.blocks + (row >> 6));
+            Blk B = ld_block(block_ptr(st, row >> 6));
             uint32_t c[4] = {B.c0, B.c1, B.c2, B.c3}, o[4];
             block_occ(st, c, B.hi, B.lo, row, o);
             r = o[s];
