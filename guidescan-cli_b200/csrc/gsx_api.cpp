@@ -24,6 +24,8 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
 struct CudaError : std::runtime_error { using std::runtime_error::runtime_error; };
 #define CK(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) throw CudaError(std::string(#call) + ": " + cudaGetErrorString(e__)); } while (0)
 
+static int env_int(const char* name, int dflt) { const char* v = getenv(name); return v && *v ? atoi(v) : dflt; }
+
 extern "C" const char* gsx_last_error(void) { return g_err.c_str(); }
 extern "C" const char* gsx_version(void) { return "2.0.0"; }
 extern "C" void gsx_free(void* p) { free(p); }
@@ -69,6 +71,17 @@ static void upload_index(gsx_index* ix, const int* devices, int n_devices) {
             for (int c = 0; c < 5; c++) d.d.C[c] = h.C[c];
             d.d.exc_lo = h.exc_rows.empty() ? 0xFFFFFFFFu : h.exc_rows.front();
             d.d.exc_hi = h.exc_rows.empty() ? 0u : h.exc_rows.back();
+            d.d.blk_shift = 5;
+            if (env_int("GSX_LOOKAHEAD", 1)) {
+                // one 128-byte line per 64 rows: OccBlock + look-ahead planes t1..t6, derived on the device by LF walks
+                const uint32_t nb = (uint32_t)h.blocks.size();
+                void* lines = nullptr;
+                CK(cudaMalloc(&lines, (size_t)nb * 128));
+                CK(launch_build_lookahead(d.d, (unsigned char*)lines, nb, 0));
+                CK(cudaDeviceSynchronize());
+                cudaFree(d.blocks); di.bytes -= std::max<size_t>(h.blocks.size(), 1) * sizeof(OccBlock);
+                d.blocks = lines; d.d.blocks = (const OccBlock*)lines; d.d.blk_shift = 7; di.bytes += (uint64_t)nb * 128;
+            }
         }
         di.chroms = (Chrom*)upload(ix->chroms, di.bytes);
         ix->dev.push_back(di);
@@ -369,7 +382,6 @@ struct DeviceJob {
     int status = GSX_OK; std::string err;
 };
 
-static int env_int(const char* name, int dflt) { const char* v = getenv(name); return v && *v ? atoi(v) : dflt; }
 
 static void run_device_job(DeviceJob* job) {
     try {

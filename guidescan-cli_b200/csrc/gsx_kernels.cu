@@ -271,6 +271,53 @@ int search_grid_warps(bool wide, int variant, int sm_count) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// look-ahead planes: t_j(r) = BWT[LF^j(r)], j = 1..6, stored behind each OccBlock in its own 128-byte line
+// ---------------------------------------------------------------------------------------------------------
+__global__ void build_lookahead_kernel(DevStrand st, unsigned char* __restrict__ lines, uint32_t n_blocks) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5, n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t hb = warp; hb < 2ull * n_blocks; hb += n_warps) {          // one warp per half block (32 rows)
+        const uint32_t b = (uint32_t)(hb >> 1), half = (uint32_t)(hb & 1);
+        unsigned char* line = lines + (size_t)b * 128;
+        if (half == 0 && lane < 8) reinterpret_cast<uint32_t*>(line)[lane] = reinterpret_cast<const uint32_t*>(block_ptr(st, b))[lane];
+        const uint64_t row64 = (uint64_t)b * 64 + half * 32 + lane;
+        const bool valid = row64 < st.n;
+        uint32_t cur = valid ? (uint32_t)row64 : 0u;
+        uint32_t steps = 0;
+        for (int j = 1; j <= 6; j++) {
+            uint32_t sym = 0;
+            if (valid) {
+                bool exc = false;
+                if (st.n_exc && cur >= st.exc_lo && cur <= st.exc_hi) {
+                    uint32_t k = lower_bound_u32(st.exc_rows, st.n_exc, cur);
+                    if (k < st.n_exc && st.exc_rows[k] == cur) { cur = st.exc_lf[k]; exc = true; }
+                }
+                if (!exc) {
+                    Blk B = ld_block(block_ptr(st, cur >> 6));
+                    uint32_t c[4] = {B.c0, B.c1, B.c2, B.c3}, o[4];
+                    block_occ(st, c, B.hi, B.lo, cur, o);
+                    uint32_t s0 = block_sym(B.hi, B.lo, cur);
+                    cur = st.C[s0] + o[s0];
+                }
+                const OccBlock* nb = block_ptr(st, cur >> 6);
+                sym = block_sym(nb->hi, nb->lo, cur);                   // exception rows read as code 0
+            }
+            const uint32_t mh = __ballot_sync(0xffffffffu, valid && (sym & 2u)), ml = __ballot_sync(0xffffffffu, valid && (sym & 1u));
+            if (lane == 0) {
+                uint32_t* p = reinterpret_cast<uint32_t*>(line + 32 + 16 * (j - 1));
+                p[half] = mh; p[2 + half] = ml;                          // hi plane = words 0,1 ; lo plane = words 2,3
+            }
+        }
+        (void)steps;
+    }
+}
+
+cudaError_t launch_build_lookahead(const DevStrand& src, unsigned char* lines, uint32_t n_blocks, cudaStream_t s) {
+    build_lookahead_kernel<<<148 * 16, 256, 0, s>>>(src, lines, n_blocks);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // search, fast path: the same search specialised for what the headline workload is -- no bulges, one PAM pattern shared
 // by all guides, ACGT-only guides, an index whose only non-ACGT BWT row is the sentinel.  Same tree, same matches, same
 // keys as search_kernel; fewer instructions per node:
@@ -279,7 +326,7 @@ int search_grid_warps(bool wide, int variant, int sm_count) {
 //   * strand-dependent constants (block base, C[], sentinel row) are selected from the parameter bank, no shared copy
 //   * all four children are evaluated branch-free; siblings are compacted with two ballots (push count bit 0 / bit 1)
 // ---------------------------------------------------------------------------------------------------------
-template <int WARPS, int CAP, int MINB>
+template <int WARPS, int CAP, int MINB, bool LOOK>
 __global__ void __launch_bounds__(WARPS * 32, MINB) search_fast_kernel(SearchArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -349,14 +396,32 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) search_fast_kernel(SearchArg
         const bool s1 = (tlm & 1u) != 0;
         uint32_t os0 = 0, os1 = 0, os2 = 0, os3 = 0, oe0 = 0, oe1 = 0, oe2 = 0, oe3 = 0;
         bool two = false;
+        uint64_t phi[7] = {0, 0, 0, 0, 0, 0, 0}, plo[7] = {0, 0, 0, 0, 0, 0, 0};      // look-ahead planes (LOOK only)
+        bool narrow = false;
+        const uint32_t lvl = tlm >> 27, mm = (tlm >> 24) & 7u, qlen = (uint32_t)(q >> 58);
         if (has) {
-            const OccBlock* blocks = s1 ? a.st[1].blocks : a.st[0].blocks;
+            const char* blocks = reinterpret_cast<const char*>(s1 ? a.st[1].blocks : a.st[0].blocks);
+            constexpr uint32_t SH = LOOK ? 7u : 5u;
             const uint32_t dollar = s1 ? a.st[1].exc_lo : a.st[0].exc_lo;
             const uint32_t e1 = ep + 1u, bs = sp >> 6, be = e1 >> 6;
             two = be != bs;
-            Blk B0 = ld_block(blocks + bs);
+            const char* line = blocks + ((size_t)bs << SH);
+            Blk B0 = ld_block(reinterpret_cast<const OccBlock*>(line));
             Blk B1 = B0;
-            if (two) B1 = ld_block(blocks + be);
+            if (two) B1 = ld_block(reinterpret_cast<const OccBlock*>(blocks + ((size_t)be << SH)));
+            else if (LOOK) {
+                // all rows of the interval sit in this block: fetch as much of the rest of its 128-byte line as the
+                // remaining levels can use (same line as B0, so no further DRAM traffic)
+                narrow = true;
+                const uint32_t left = qlen + plen - lvl;
+                if (left > 1) { Blk P = ld_block(reinterpret_cast<const OccBlock*>(line + 32));
+                                phi[1] = ((uint64_t)P.c1 << 32) | P.c0; plo[1] = ((uint64_t)P.c3 << 32) | P.c2; phi[2] = P.hi; plo[2] = P.lo; }
+                if (left > 3) { Blk P = ld_block(reinterpret_cast<const OccBlock*>(line + 64));
+                                phi[3] = ((uint64_t)P.c1 << 32) | P.c0; plo[3] = ((uint64_t)P.c3 << 32) | P.c2; phi[4] = P.hi; plo[4] = P.lo; }
+                if (left > 5) { Blk P = ld_block(reinterpret_cast<const OccBlock*>(line + 96));
+                                phi[5] = ((uint64_t)P.c1 << 32) | P.c0; plo[5] = ((uint64_t)P.c3 << 32) | P.c2; phi[6] = P.hi; plo[6] = P.lo; }
+                phi[0] = B0.hi; plo[0] = B0.lo;
+            }
             {
                 uint32_t r = sp & 63u; uint64_t mask = r ? (~0ull >> (64 - r)) : 0ull;
                 uint64_t hi = B0.hi & mask, lo = B0.lo & mask;
@@ -378,14 +443,17 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) search_fast_kernel(SearchArg
             if (lane == 0) n_lookups += __popc(act) + __popc(two_mask);
         }
         // ---- children (branch-free) ---------------------------------------------------------------------------
-        const uint32_t lvl = tlm >> 27, mm = (tlm >> 24) & 7u, qlen = (uint32_t)(q >> 58);
         const bool in_proto = lvl < qlen;
         const uint32_t c = in_proto ? ((uint32_t)(q >> (2u * lvl)) & 3u) : ((a.pampack >> (3u * (lvl - qlen))) & 7u);
         const bool allow = in_proto ? (mm < M) : (c == 4u);
         const bool final_lvl = (lvl + 1u == qlen + plen);
         const uint32_t w0 = oe0 - os0, w1 = oe1 - os1, w2 = oe2 - os2, w3 = oe3 - os3;
-        const bool v0 = has && w0 && (c == 0u || allow), v1 = has && w1 && (c == 1u || allow);
-        const bool v2 = has && w2 && (c == 2u || allow), v3 = has && w3 && (c == 3u || allow);
+        bool v0 = has && w0 && (c == 0u || allow), v1 = has && w1 && (c == 1u || allow);
+        bool v2 = has && w2 && (c == 2u || allow), v3 = has && w3 && (c == 3u || allow);
+        if (LOOK && narrow) {        // drop children that cannot survive the next (up to) seven characters
+            const uint32_t vm = viable_children(phi, plo, sp, ep, lvl, qlen, qlen + plen, q, a.pampack, M - mm);
+            v0 = v0 && (vm & 1u); v1 = v1 && (vm & 2u); v2 = v2 && (vm & 4u); v3 = v3 && (vm & 8u);
+        }
         const uint32_t C0 = s1 ? a.st[1].C[0] : a.st[0].C[0], C1 = s1 ? a.st[1].C[1] : a.st[0].C[1];
         const uint32_t C2 = s1 ? a.st[1].C[2] : a.st[0].C[2], C3 = s1 ? a.st[1].C[3] : a.st[0].C[3];
         const uint64_t key5 = key * 5ull;
@@ -462,10 +530,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) search_fast_kernel(SearchArg
     if (lane == 0) { atomicAdd(a.stats + 0, n_nodes); atomicAdd(a.stats + 1, n_lookups); atomicAdd(a.stats + 2, n_spilled); }
 }
 
-template <int WARPS, int CAP, int MINB>
+template <int WARPS, int CAP, int MINB, bool LOOK>
 static cudaError_t launch_fast_t(const SearchArgs& a, int sm_count, cudaStream_t s) {
     size_t smem = (size_t)WARPS * CAP * 20;
-    auto k = search_fast_kernel<WARPS, CAP, MINB>;
+    auto k = search_fast_kernel<WARPS, CAP, MINB, LOOK>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     k<<<sm_count * MINB, WARPS * 32, smem, s>>>(a);
@@ -480,7 +548,8 @@ static cudaError_t launch_fast_t(const SearchArgs& a, int sm_count, cudaStream_t
     X(4, 8, 256, 5) /* 1280 thr/SM, 200 KB smem */
 
 cudaError_t launch_search_fast(const SearchArgs& a, int variant, int sm_count, cudaStream_t s) {
-#define X(V, WARPS, CAP, MINB) if (variant == V) return launch_fast_t<WARPS, CAP, MINB>(a, sm_count, s);
+    const bool look = a.st[0].blk_shift == 7 && a.st[1].blk_shift == 7;
+#define X(V, WARPS, CAP, MINB) if (variant == V) return look ? launch_fast_t<WARPS, CAP, MINB, true>(a, sm_count, s) : launch_fast_t<WARPS, CAP, MINB, false>(a, sm_count, s);
     GSX_FAST_VARIANTS(X)
 #undef X
     return cudaErrorInvalidValue;

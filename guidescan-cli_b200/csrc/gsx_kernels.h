@@ -59,6 +59,8 @@ struct SpecArgs {
 };
 
 cudaError_t upload_cfd_tables();
+// packed 32-byte blocks (src, blk_shift 5) -> 128-byte lines with look-ahead planes t1..t6 (dst must hold n_blocks * 128 bytes)
+cudaError_t launch_build_lookahead(const DevStrand& src, unsigned char* lines, uint32_t n_blocks, cudaStream_t s);
 int search_grid_warps(bool wide, int variant, int sm_count);
 cudaError_t launch_search(const SearchArgs& a, bool wide, int variant, int sm_count, cudaStream_t s, int* warps_total);
 int search_fast_grid_warps(int variant, int sm_count);

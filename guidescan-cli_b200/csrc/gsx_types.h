@@ -14,6 +14,7 @@
 #ifndef GSX_TYPES_H
 #define GSX_TYPES_H
 #include <stdint.h>
+#include <stddef.h>
 
 #if defined(__CUDACC__)
 #define GSX_HD __host__ __device__ __forceinline__

@@ -37,6 +37,36 @@ static DevStrand view_of(const HostStrand& h) {
     return d;
 }
 
+// look-ahead planes t1..t6 per 64-row block (what build_lookahead_kernel writes behind each OccBlock), built on the host
+static std::vector<uint64_t> g_look[2];     // 12 words per block: hi1, lo1, ..., hi6, lo6
+static bool g_prune = false;
+
+static void build_look(const DevStrand& st, std::vector<uint64_t>& look) {
+    const uint32_t nb = st.n / 64 + 1;
+    look.assign((size_t)nb * 12, 0);
+    for (uint32_t row = 0; row < st.n; row++) {
+        uint32_t cur = row;
+        for (int j = 1; j <= 6; j++) {
+            // cur = LF(cur)
+            bool exc = false;
+            if (st.n_exc && cur >= st.exc_lo && cur <= st.exc_hi) {
+                uint32_t k = lower_bound_u32(st.exc_rows, st.n_exc, cur);
+                if (k < st.n_exc && st.exc_rows[k] == cur) { cur = st.exc_lf[k]; exc = true; }
+            }
+            if (!exc) {
+                const OccBlock& b = st.blocks[cur >> 6]; uint32_t o[4];
+                block_occ(st, b.cnt, b.hi, b.lo, cur, o);
+                uint32_t sy = block_sym(b.hi, b.lo, cur);
+                cur = st.C[sy] + o[sy];
+            }
+            const OccBlock& c = st.blocks[cur >> 6];
+            uint32_t sy = block_sym(c.hi, c.lo, cur);       // exception rows read as code 0, as on the device
+            look[(size_t)(row >> 6) * 12 + 2 * (j - 1)] |= (uint64_t)(sy >> 1) << (row & 63);
+            look[(size_t)(row >> 6) * 12 + 2 * (j - 1) + 1] |= (uint64_t)(sy & 1) << (row & 63);
+        }
+    }
+}
+
 template <bool WIDE>
 static void dfs(const DevStrand st[2], const Prepared& prep, uint32_t task, uint32_t M, uint32_t R, uint32_t D, bool counting,
                 uint64_t* count, std::vector<MatchRec>& out, uint64_t* nodes) {
@@ -53,8 +83,16 @@ static void dfs(const DevStrand st[2], const Prepared& prep, uint32_t task, uint
         const OccBlock& b0 = s.blocks[nd.sp >> 6]; const OccBlock& b1 = s.blocks[(nd.ep + 1) >> 6];
         block_occ(s, b0.cnt, b0.hi, b0.lo, nd.sp, os);
         block_occ(s, b1.cnt, b1.hi, b1.lo, nd.ep + 1, oe);
+        uint32_t vmask = 15;
+        if (g_prune && !WIDE && (nd.sp >> 6) == ((nd.ep + 1) >> 6)) {       // the pruning step of search_fast_kernel
+            const std::vector<uint64_t>& lk = g_look[task & 1];
+            uint64_t hi[7], lo[7]; hi[0] = b0.hi; lo[0] = b0.lo;
+            for (int j = 1; j <= 6; j++) { hi[j] = lk[(size_t)(nd.sp >> 6) * 12 + 2 * (j - 1)]; lo[j] = lk[(size_t)(nd.sp >> 6) * 12 + 2 * (j - 1) + 1]; }
+            vmask = viable_children(hi, lo, nd.sp, nd.ep, meta_lvl(nd.meta), g.qlen, g.qlen + prep.plen, prep.gq[task >> 1], prep.pampack, M - meta_mm(nd.meta));
+        }
         for (int cand = 0; cand < CAND_END; cand++) {
             if (!WIDE && cand > CAND_FORK) break;
+            if (cand < 4 && !((vmask >> cand) & 1)) continue;
             Node ch; bool emit;
             if (!make_child<WIDE>(cand, nd, cx, os, oe, ch, emit)) continue;
             if (emit) {
@@ -75,6 +113,7 @@ int main(int argc, char** argv) {
         if (a == "-m") p.mismatches = atoi(argv[++i]); else if (a == "--rna") p.rna_bulges = atoi(argv[++i]);
         else if (a == "--dna") p.dna_bulges = atoi(argv[++i]); else if (a == "-t") p.threshold = atoi(argv[++i]);
         else if (a == "--start") p.start = 1; else if (a == "--max") p.max_off_targets = atoll(argv[++i]);
+        else if (a == "--lookahead") g_prune = true;
         else if (a == "--sam") sam = true; else if (a == "--succinct") complete = false; else if (a == "-a") alts.push_back(argv[++i]);
         else { fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
     }
@@ -99,6 +138,10 @@ int main(int argc, char** argv) {
     Prepared prep;
     if (gsx_prepare_guides(gg.data(), n, &p, prep)) { fprintf(stderr, "%s\n", gsx_last_error()); return 1; }
     const uint32_t n_dist = p.mismatches + 1;
+    if (g_prune) {
+        if (!prep.fast_ok) { fprintf(stderr, "--lookahead needs a fast-path batch (one PAM, ACGT guides, no bulges)\n"); return 2; }
+        build_look(st[0], g_look[0]); build_look(st[1], g_look[1]);
+    }
 
     // ---- search + order + expand (what search_kernel / order_matches_kernel / expand_hits_kernel do) ----------------
     std::vector<uint8_t> dropped(n, 0);

@@ -33,3 +33,26 @@ def test_device_arithmetic_on_host_matches_golden(harness, golden_dir, golden_in
     subprocess.check_call([harness, golden_index[case], golden_dir[case][1], out] + variant_cli_args(kw),
                           stderr=subprocess.DEVNULL)
     assert open(out, "rb").read() == golden_output(case, variant)
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("m", [2, 3, 4])
+def test_lookahead_pruning_keeps_output_and_cuts_nodes(harness, tmp_path, m):
+    """viable_children (gsx_core.h), the pruning step of the specialised search kernel, on host-built look-ahead planes:
+    identical text, fewer expanded nodes."""
+    import oracle as O
+    import synth
+    if not O.have_ref():
+        pytest.skip("needs oracle/_ref/guidescan for the index files")
+    d = str(tmp_path)
+    synth.make_dataset(d, 400_000, 3, 60, seed=31, name="la")
+    fa, gcsv = os.path.join(d, "la.fa"), os.path.join(d, "la.guides.csv")
+    O.ref_index(fa, os.path.join(d, "la"), cwd=d)
+    O.Index(fa).enumerate_file(O.make_opts(mismatches=m), gcsv, os.path.join(d, "o.out"), nthreads=4)
+    nodes = {}
+    for tag, extra in (("plain", []), ("look", ["--lookahead"])):
+        out = os.path.join(d, tag + ".out")
+        r = subprocess.run([harness, os.path.join(d, "la"), gcsv, out, "-m", str(m)] + extra, capture_output=True, text=True, check=True)
+        assert open(out, "rb").read() == open(os.path.join(d, "o.out"), "rb").read()
+        nodes[tag] = int(r.stderr.split(" guides, ")[1].split(" nodes")[0])
+    assert nodes["look"] < 0.8 * nodes["plain"], nodes

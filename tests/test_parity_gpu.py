@@ -180,17 +180,24 @@ def test_gpu_built_index_with_repeats_and_dense_samples(gsx, tmp_path):
         r.close(); ix.close()
 
 
-@pytest.fixture(scope="module")
-def seeded_case(gsx, tmp_path_factory):
-    """1.5 Mb uniform genome, 400 NGG guides: eligible for the specialised search kernel (one PAM, ACGT guides, no N)"""
+@pytest.fixture(scope="module", params=["lookahead", "packed"])
+def seeded_case(gsx, tmp_path_factory, request):
+    """1.5 Mb uniform genome, 400 NGG guides: eligible for the specialised search kernel (one PAM, ACGT guides, no N);
+    once with 128-byte lines + look-ahead planes (default), once with packed 32-byte blocks"""
     import oracle as O
     import synth
     d = str(tmp_path_factory.mktemp("fast"))
     synth.make_dataset(d, 1_500_000, 5, 400, seed=21, name="f")
     fa, gcsv = os.path.join(d, "f.fa"), os.path.join(d, "f.guides.csv")
+    old = os.environ.get("GSX_LOOKAHEAD")
+    os.environ["GSX_LOOKAHEAD"] = "1" if request.param == "lookahead" else "0"
     ix = gsx.Index.build(fa, devices=[0])
+    if old is None:
+        os.environ.pop("GSX_LOOKAHEAD")
+    else:
+        os.environ["GSX_LOOKAHEAD"] = old
     oix = O.Index(fa)
-    yield d, gcsv, ix, oix
+    yield d, gcsv, ix, oix, request.param
     ix.close()
 
 
@@ -198,7 +205,7 @@ def seeded_case(gsx, tmp_path_factory):
                                 dict(mismatches=0), dict(mismatches=3, fmt="sam")])
 def test_fast_and_general_kernels_agree_with_oracle(gsx, seeded_case, monkeypatch, kw):
     import oracle as O
-    d, gcsv, ix, oix = seeded_case
+    d, gcsv, ix, oix, layout = seeded_case
     fmt = kw.get("fmt", "csv")
     okw = {k: v for k, v in kw.items()}
     want = os.path.join(d, "o.out")
@@ -212,13 +219,19 @@ def test_fast_and_general_kernels_agree_with_oracle(gsx, seeded_case, monkeypatc
         _, ctr = ix.enumerate_file(gcsv, out, p, fmt=fmt)
         assert open(out, "rb").read() == want
         nodes[force_general] = (ctr["nodes"], ctr["lookups"], ctr["matches"], ctr["hits"])
-    assert nodes["0"] == nodes["1"]          # same tree, same lookups, whichever kernel walks it
+    assert nodes["0"][2:] == nodes["1"][2:]  # same matches and hits whichever kernel walks the tree
+    if layout == "packed" or kw["mismatches"] == 0:
+        assert nodes["0"][0] <= nodes["1"][0]
+    else:
+        assert nodes["0"][0] < nodes["1"][0]     # look-ahead pruning expands fewer nodes
+    if layout == "packed":
+        assert nodes["0"] == nodes["1"]          # without it: same tree, same lookups
 
 
 @pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
 def test_every_fast_kernel_variant(gsx, seeded_case, monkeypatch, variant):
     import oracle as O
-    d, gcsv, ix, oix = seeded_case
+    d, gcsv, ix, oix, layout = seeded_case
     monkeypatch.setenv("GSX_FAST_VARIANT", str(variant))
     monkeypatch.setenv("GSX_SPILL_CAP", "64" if variant % 2 else "2048")
     monkeypatch.setenv("GSX_MATCH_CAP", "100" if variant == 2 else "0")
