@@ -190,7 +190,12 @@ def run_gsx(args):
         # kernel-variant sweep on the first step's guides (diagnostic lines on stderr; not the bench value)
         # items: "f<k>" = specialised kernel variant k, "g<k>" = general kernel variant k
         for item in args.sweep_variants.split(","):
-            env = {"GSX_FORCE_GENERAL": "1", "GSX_SEARCH_VARIANT": item[1:]} if item[0] == "g" else {"GSX_FORCE_GENERAL": "0", "GSX_FAST_VARIANT": item[1:]}
+            name, _, pin = item.partition("@")          # "f1@64": specialised kernel variant 1 with a 64 MB L2 residency budget
+            env = {"GSX_FORCE_GENERAL": "1", "GSX_SEARCH_VARIANT": name[1:]} if name[0] == "g" else {"GSX_FORCE_GENERAL": "0", "GSX_FAST_VARIANT": name[1:]}
+            if pin:
+                env["GSX_L2_PIN_MB"] = pin
+            else:
+                os.environ.pop("GSX_L2_PIN_MB", None)
             os.environ.update(env)
             best = None
             for rep in range(3):
@@ -198,7 +203,7 @@ def run_gsx(args):
                 best = c if best is None or c["ms_search"] < best["ms_search"] else best
             log(json.dumps({"variant": item, "ms_search": best["ms_search"], "guides_per_s_search": per / best["ms_search"] * 1e3,
                             "glookups_per_s": best["lookups"] / best["ms_search"] / 1e6, "spills": best["spills"], "nodes": best["nodes"]}))
-        for k in ("GSX_FORCE_GENERAL", "GSX_SEARCH_VARIANT", "GSX_FAST_VARIANT"):
+        for k in ("GSX_FORCE_GENERAL", "GSX_SEARCH_VARIANT", "GSX_FAST_VARIANT", "GSX_L2_PIN_MB"):
             os.environ.pop(k, None)
         apply_variant(args)
     for s in range(args.warmup):

@@ -71,16 +71,15 @@ static void upload_index(gsx_index* ix, const int* devices, int n_devices) {
             for (int c = 0; c < 5; c++) d.d.C[c] = h.C[c];
             d.d.exc_lo = h.exc_rows.empty() ? 0xFFFFFFFFu : h.exc_rows.front();
             d.d.exc_hi = h.exc_rows.empty() ? 0u : h.exc_rows.back();
-            d.d.blk_shift = 5;
+            d.d.blk_shift = 5; d.d.lines = nullptr;
             if (env_int("GSX_LOOKAHEAD", 1)) {
-                // one 128-byte line per 64 rows: OccBlock + look-ahead planes t1..t6, derived on the device by LF walks
+                // second copy for narrow intervals: one 128-byte line per 64 rows = OccBlock + look-ahead planes t1..t6,
+                // derived on the device by LF walks over the packed blocks
                 const uint32_t nb = (uint32_t)h.blocks.size();
-                void* lines = nullptr;
-                CK(cudaMalloc(&lines, (size_t)nb * 128));
-                CK(launch_build_lookahead(d.d, (unsigned char*)lines, nb, 0));
+                CK(cudaMalloc(&d.lines, (size_t)nb * 128));
+                CK(launch_build_lookahead(d.d, (unsigned char*)d.lines, nb, 0));
                 CK(cudaDeviceSynchronize());
-                cudaFree(d.blocks); di.bytes -= std::max<size_t>(h.blocks.size(), 1) * sizeof(OccBlock);
-                d.blocks = lines; d.d.blocks = (const OccBlock*)lines; d.d.blk_shift = 7; di.bytes += (uint64_t)nb * 128;
+                d.d.lines = (const unsigned char*)d.lines; di.bytes += (uint64_t)nb * 128;
             }
         }
         di.chroms = (Chrom*)upload(ix->chroms, di.bytes);
@@ -90,7 +89,7 @@ static void upload_index(gsx_index* ix, const int* devices, int n_devices) {
 
 static void free_device_index(DeviceIndex& di) {
     cudaSetDevice(di.device);
-    for (int s = 0; s < 2; s++) { cudaFree(di.st[s].blocks); cudaFree(di.st[s].sa); cudaFree(di.st[s].exc_rows); cudaFree(di.st[s].exc_lf); cudaFree(di.st[s].n_rows); }
+    for (int s = 0; s < 2; s++) { cudaFree(di.st[s].blocks); cudaFree(di.st[s].lines); cudaFree(di.st[s].sa); cudaFree(di.st[s].exc_rows); cudaFree(di.st[s].exc_lf); cudaFree(di.st[s].n_rows); }
     cudaFree(di.chroms);
 }
 
@@ -420,11 +419,16 @@ static void run_device_job(DeviceJob* job) {
         // fast path (search_fast_kernel) when the batch and the index allow it; GSX_FORCE_GENERAL=1 keeps the general kernel
         const bool use_fast = prep.fast_ok && !env_int("GSX_FORCE_GENERAL", 0) && n < (1u << 23) &&
                               di.st[0].d.n_exc == 1 && di.st[1].d.n_exc == 1 && di.st[0].d.n_nrows == 0 && di.st[1].d.n_nrows == 0;
-        const int variant_f = env_int("GSX_FAST_VARIANT", 0);
+        const int variant_f = env_int("GSX_FAST_VARIANT", di.st[0].d.lines ? 1 : 0);
         if (use_fast) {
             uint64_t* d_gq = B.alloc<uint64_t>(n);
             CK(cudaMemcpyAsync(d_gq, prep.gq.data() + job->g0, (size_t)n * 8, cudaMemcpyHostToDevice, s));
             a.gq = d_gq; a.pampack = prep.pampack; a.plen = prep.plen;
+            // L2 residency hint: intervals wide enough that all such blocks of both strands fit the L2 budget
+            // (a level-d interval end costs one 128-byte line; lines touched down to level D ~ 2.7 * 4^D per strand)
+            const double l2_bytes = (double)env_int("GSX_L2_PIN_MB", 64) * 1e6;
+            const double w = l2_bytes > 0 ? (double)di.st[0].d.n * 2.0 * 2.7 * 128.0 / l2_bytes : 4.0e9;
+            a.pin_width = w >= 4.0e9 ? 0xFFFFFFFFu : (uint32_t)std::max(256.0, w);
         }
 
         CK(cudaEventRecord(ev[0], s));

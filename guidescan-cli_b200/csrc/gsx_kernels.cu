@@ -41,6 +41,15 @@ __device__ __forceinline__ Blk ld_block(const OccBlock* p) {
     return b;
 }
 
+__device__ __forceinline__ Blk ld_block_hint(const void* p, uint64_t policy) {
+    Blk b; uint32_t h0, h1, l0, l1;
+    asm volatile("ld.global.nc.L2::cache_hint.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+                 : "=r"(b.c0), "=r"(b.c1), "=r"(b.c2), "=r"(b.c3), "=r"(h0), "=r"(h1), "=r"(l0), "=r"(l1)
+                 : "l"(p), "l"(policy));
+    b.hi = ((uint64_t)h1 << 32) | h0; b.lo = ((uint64_t)l1 << 32) | l0;
+    return b;
+}
+
 template <bool WIDE, int CAP>
 struct WarpRing {
     uint32_t* sp; uint32_t* ep; uint32_t* meta; uint32_t* task; uint64_t* klo; uint64_t* khi;
@@ -347,6 +356,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) search_fast_kernel(SearchArg
     unsigned long long n_nodes = 0, n_lookups = 0, n_spilled = 0;     // accumulated by lane 0 only
     const uint32_t M = a.p.M, plen = a.plen;
     uint32_t iters = 0;
+    uint64_t pol_keep, pol_stream;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
 
     for (;;) {
         if (++iters > a.max_iters) { if (lane == 0) atomicOr(a.error_flag, GSX_KERR_WATCHDOG); break; }
@@ -400,27 +412,32 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) search_fast_kernel(SearchArg
         bool narrow = false;
         const uint32_t lvl = tlm >> 27, mm = (tlm >> 24) & 7u, qlen = (uint32_t)(q >> 58);
         if (has) {
-            const char* blocks = reinterpret_cast<const char*>(s1 ? a.st[1].blocks : a.st[0].blocks);
-            constexpr uint32_t SH = LOOK ? 7u : 5u;
+            const OccBlock* blocks = s1 ? a.st[1].blocks : a.st[0].blocks;
             const uint32_t dollar = s1 ? a.st[1].exc_lo : a.st[0].exc_lo;
             const uint32_t e1 = ep + 1u, bs = sp >> 6, be = e1 >> 6;
             two = be != bs;
-            const char* line = blocks + ((size_t)bs << SH);
-            Blk B0 = ld_block(reinterpret_cast<const OccBlock*>(line));
-            Blk B1 = B0;
-            if (two) B1 = ld_block(reinterpret_cast<const OccBlock*>(blocks + ((size_t)be << SH)));
-            else if (LOOK) {
-                // all rows of the interval sit in this block: fetch as much of the rest of its 128-byte line as the
-                // remaining levels can use (same line as B0, so no further DRAM traffic)
+            Blk B0, B1;
+            if (LOOK && !two) {
+                // all rows of the interval sit in one block: read its own 128-byte line (OccBlock + as many look-ahead
+                // planes as the remaining levels can use -- same line, so no further DRAM traffic); streaming in L2
                 narrow = true;
+                const unsigned char* line = (s1 ? a.st[1].lines : a.st[0].lines) + ((size_t)bs << 7);
+                B0 = ld_block_hint(line, pol_stream);
                 const uint32_t left = qlen + plen - lvl;
-                if (left > 1) { Blk P = ld_block(reinterpret_cast<const OccBlock*>(line + 32));
+                if (left > 1) { Blk P = ld_block_hint(line + 32, pol_stream);
                                 phi[1] = ((uint64_t)P.c1 << 32) | P.c0; plo[1] = ((uint64_t)P.c3 << 32) | P.c2; phi[2] = P.hi; plo[2] = P.lo; }
-                if (left > 3) { Blk P = ld_block(reinterpret_cast<const OccBlock*>(line + 64));
+                if (left > 3) { Blk P = ld_block_hint(line + 64, pol_stream);
                                 phi[3] = ((uint64_t)P.c1 << 32) | P.c0; plo[3] = ((uint64_t)P.c3 << 32) | P.c2; phi[4] = P.hi; plo[4] = P.lo; }
-                if (left > 5) { Blk P = ld_block(reinterpret_cast<const OccBlock*>(line + 96));
+                if (left > 5) { Blk P = ld_block_hint(line + 96, pol_stream);
                                 phi[5] = ((uint64_t)P.c1 << 32) | P.c0; plo[5] = ((uint64_t)P.c3 << 32) | P.c2; phi[6] = P.hi; plo[6] = P.lo; }
                 phi[0] = B0.hi; plo[0] = B0.lo;
+                B1 = B0;
+            } else {
+                // packed blocks: 256 rows per line; the top of the tree is shared by all guides -> keep it in L2
+                const uint64_t pol = (ep - sp >= a.pin_width) ? pol_keep : pol_stream;
+                B0 = ld_block_hint(blocks + bs, pol);
+                B1 = B0;
+                if (two) B1 = ld_block_hint(blocks + be, pol);
             }
             {
                 uint32_t r = sp & 63u; uint64_t mask = r ? (~0ull >> (64 - r)) : 0ull;
@@ -548,7 +565,7 @@ static cudaError_t launch_fast_t(const SearchArgs& a, int sm_count, cudaStream_t
     X(4, 8, 256, 5) /* 1280 thr/SM, 200 KB smem */
 
 cudaError_t launch_search_fast(const SearchArgs& a, int variant, int sm_count, cudaStream_t s) {
-    const bool look = a.st[0].blk_shift == 7 && a.st[1].blk_shift == 7;
+    const bool look = a.st[0].lines != nullptr && a.st[1].lines != nullptr;
 #define X(V, WARPS, CAP, MINB) if (variant == V) return look ? launch_fast_t<WARPS, CAP, MINB, true>(a, sm_count, s) : launch_fast_t<WARPS, CAP, MINB, false>(a, sm_count, s);
     GSX_FAST_VARIANTS(X)
 #undef X

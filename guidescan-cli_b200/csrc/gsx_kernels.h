@@ -32,6 +32,7 @@ struct SearchArgs {
     const uint64_t* gq;                // per guide: 2-bit symbol codes in consumption order | qlen << 58
     uint32_t pampack;                  // 3 bits per PAM character in consumption order (4 = N wildcard, 5 = never matches)
     uint32_t plen;
+    uint32_t pin_width;                // packed-block loads of intervals at least this wide ask L2 to keep the line (evict_last)
 };
 
 struct LocateArgs {
@@ -59,7 +60,7 @@ struct SpecArgs {
 };
 
 cudaError_t upload_cfd_tables();
-// packed 32-byte blocks (src, blk_shift 5) -> 128-byte lines with look-ahead planes t1..t6 (dst must hold n_blocks * 128 bytes)
+// packed 32-byte blocks (src) -> 128-byte lines with look-ahead planes t1..t6 (dst must hold n_blocks * 128 bytes)
 cudaError_t launch_build_lookahead(const DevStrand& src, unsigned char* lines, uint32_t n_blocks, cudaStream_t s);
 int search_grid_warps(bool wide, int variant, int sm_count);
 cudaError_t launch_search(const SearchArgs& a, bool wide, int variant, int sm_count, cudaStream_t s, int* warps_total);

@@ -7,10 +7,13 @@
 //   * rows whose BWT symbol is not A/C/G/T ('$' sentinel row, genome N / IUPAC) are stored as code 0 in the planes
 //     and listed in a sorted exception table; occ(A) is corrected from it, so rank stays exact.
 //   * SA samples: SA[row] for every row that is a multiple of 2^sa_shift (reference density: 64 rows).
-//   * optional look-ahead planes (blk_shift = 7): a B200 L1 miss always pulls the whole 128-byte line from L2/DRAM
-//     (profiles/r01e_gather_width_ncu.csv), so each 64-row block owns a full line: bytes 0..31 the OccBlock, bytes
-//     32..127 the 2-bit symbols t1..t6 of the same rows, t_j(r) = BWT[LF^j(r)] = text[SA[r] - 1 - j] -- the next six
-//     characters a backward search from row r would consume.  The search prunes children that cannot survive them.
+//   * optional look-ahead lines: a B200 L1 miss always pulls the whole 128-byte line from L2/DRAM
+//     (profiles/r01e_gather_width_ncu.csv).  Wide SA intervals (top of the search tree) use the packed blocks, where
+//     one line covers 256 rows and both interval ends usually share it; for narrow intervals (all rows inside one
+//     64-row block, the deep random-access part of the tree) a second array gives each block its own line:
+//     bytes 0..31 the OccBlock, bytes 32..127 the 2-bit symbols t1..t6 of the same rows,
+//     t_j(r) = BWT[LF^j(r)] = text[SA[r] - 1 - j] -- the next six characters a backward search from row r would
+//     consume.  The search prunes children that cannot survive them, at no extra DRAM traffic.
 #ifndef GSX_TYPES_H
 #define GSX_TYPES_H
 #include <stdint.h>
@@ -51,8 +54,9 @@ struct DevStrand {
     uint32_t sa_shift;
     uint32_t C[5];                 // C[A],C[C],C[G],C[T],C[N]: rows whose suffix starts with a smaller symbol
     uint32_t exc_lo, exc_hi;       // first / last exception row (fast reject)
-    uint32_t blk_shift;            // log2 of the byte stride between OccBlocks: 5 = packed, 7 = one 128-byte line per 64 rows
-                                   // (OccBlock + six look-ahead symbol planes, see build_lookahead_kernel)
+    uint32_t blk_shift;            // log2 of the byte stride between OccBlocks in `blocks` (5 = packed)
+    const unsigned char* lines;    // optional second copy, one 128-byte line per 64 rows: OccBlock + six look-ahead symbol
+                                   // planes (see build_lookahead_kernel); nullptr if absent
 };
 
 GSX_HD const OccBlock* block_ptr(const DevStrand& st, uint32_t b) {
