@@ -71,7 +71,22 @@ static void upload_index(gsx_index* ix, const int* devices, int n_devices) {
             for (int c = 0; c < 5; c++) d.d.C[c] = h.C[c];
             d.d.exc_lo = h.exc_rows.empty() ? 0xFFFFFFFFu : h.exc_rows.front();
             d.d.exc_hi = h.exc_rows.empty() ? 0u : h.exc_rows.back();
-            d.d.blk_shift = 5; d.d.lines = nullptr;
+            d.d.blk_shift = 5; d.d.lines = nullptr; d.d.ftab = nullptr; d.d.ftab_L = 0;
+            {
+                // k-mer jump table: depth L such that a level-L interval still holds a handful of rows
+                int L = env_int("GSX_FTAB", -1);
+                if (L < 0) { L = 0; uint64_t v = h.n; while (v >= 4) { v >>= 2; L++; } L -= 1; if (L > 14) L = 14; if (L < 6) L = 0; }
+                if (L > 16) L = 16;
+                if (L >= 4) {
+                    void* tmp = nullptr;
+                    CK(cudaMalloc(&d.ftab, (size_t)8 << (2 * L)));
+                    CK(cudaMalloc(&tmp, (size_t)8 << (2 * L)));
+                    CK(launch_build_ftab(d.d, (uint32_t)L, d.ftab, tmp, 0));
+                    CK(cudaDeviceSynchronize());
+                    cudaFree(tmp);
+                    d.d.ftab = d.ftab; d.d.ftab_L = (uint32_t)L; di.bytes += (uint64_t)8 << (2 * L);
+                }
+            }
             if (env_int("GSX_LOOKAHEAD", 1)) {
                 // second copy for narrow intervals: one 128-byte line per 64 rows = OccBlock + look-ahead planes t1..t6,
                 // derived on the device by LF walks over the packed blocks
@@ -89,7 +104,7 @@ static void upload_index(gsx_index* ix, const int* devices, int n_devices) {
 
 static void free_device_index(DeviceIndex& di) {
     cudaSetDevice(di.device);
-    for (int s = 0; s < 2; s++) { cudaFree(di.st[s].blocks); cudaFree(di.st[s].lines); cudaFree(di.st[s].sa); cudaFree(di.st[s].exc_rows); cudaFree(di.st[s].exc_lf); cudaFree(di.st[s].n_rows); }
+    for (int s = 0; s < 2; s++) { cudaFree(di.st[s].blocks); cudaFree(di.st[s].lines); cudaFree(di.st[s].ftab); cudaFree(di.st[s].sa); cudaFree(di.st[s].exc_rows); cudaFree(di.st[s].exc_lf); cudaFree(di.st[s].n_rows); }
     cudaFree(di.chroms);
 }
 
@@ -429,6 +444,7 @@ static void run_device_job(DeviceJob* job) {
             const double l2_bytes = (double)env_int("GSX_L2_PIN_MB", 64) * 1e6;
             const double w = l2_bytes > 0 ? (double)di.st[0].d.n * 2.0 * 2.7 * 128.0 / l2_bytes : 4.0e9;
             a.pin_width = w >= 4.0e9 ? 0xFFFFFFFFu : (uint32_t)std::max(256.0, w);
+            a.combos = nullptr; a.n_combos = 0;
         }
 
         CK(cudaEventRecord(ev[0], s));
@@ -444,6 +460,12 @@ static void run_device_job(DeviceJob* job) {
                 CK(cudaMemsetAsync(d_ctrs, 0, 8 * sizeof(uint32_t), s));
                 CK(cudaMemsetAsync(d_gcount, 0, (size_t)n * 8, s));
                 SearchArgs c = a; c.p.M = (uint32_t)p.threshold; c.p.R = c.p.D = 0; c.p.counting = 1; c.p.match_cap = 0; c.p.spill_cap = spill_cap;
+                if (use_fast && di.st[0].d.ftab_L) {
+                    std::vector<uint64_t> cb = ftab_combos(di.st[0].d.ftab_L - 2, c.p.M);
+                    uint64_t* d_cb = B.alloc<uint64_t>(cb.size());
+                    CK(cudaMemcpyAsync(d_cb, cb.data(), cb.size() * 8, cudaMemcpyHostToDevice, s)); CK(cudaStreamSynchronize(s));
+                    c.combos = d_cb; c.n_combos = (uint32_t)cb.size();
+                }
                 c.guide_count = d_gcount; c.spill = d_spill; c.skip = nullptr; c.matches = nullptr;
                 if (use_fast) CK(launch_search_fast(c, variant_f, di.sm_count, s)); else CK(launch_search(c, false, variant_n, di.sm_count, s, nullptr));
                 n_launches++;
@@ -465,6 +487,12 @@ static void run_device_job(DeviceJob* job) {
         if (env_int("GSX_MATCH_CAP", 0) > 0) match_cap = (uint64_t)env_int("GSX_MATCH_CAP", 0);      // tests: force the retry path
         if (env_int("GSX_SPILL_CAP", 0) > 0) spill_cap = (uint32_t)env_int("GSX_SPILL_CAP", 0);
         MatchRec* d_matches = nullptr; uint32_t* d_spill = nullptr; uint32_t n_matches = 0;
+        if (use_fast && di.st[0].d.ftab_L) {
+            std::vector<uint64_t> cb = ftab_combos(di.st[0].d.ftab_L - 2, p.mismatches);
+            uint64_t* d_cb = B.alloc<uint64_t>(cb.size());
+            CK(cudaMemcpyAsync(d_cb, cb.data(), cb.size() * 8, cudaMemcpyHostToDevice, s)); CK(cudaStreamSynchronize(s));
+            a.combos = d_cb; a.n_combos = (uint32_t)cb.size();
+        }
         for (int attempt = 0;; attempt++) {
             if (attempt > 12) throw std::runtime_error("search arenas keep overflowing");
             int warps = use_fast ? search_fast_grid_warps(variant_f, di.sm_count) : search_grid_warps(wide, variant, di.sm_count);

@@ -398,6 +398,37 @@ GSX_HD uint32_t viable_children(const uint64_t hi[7], const uint64_t lo[7], uint
     return ((alive & ~h0 & ~l0) ? 1u : 0u) | ((alive & ~h0 & l0) ? 2u : 0u) | ((alive & h0 & ~l0) ? 4u : 0u) | ((alive & h0 & l0) ? 8u : 0u);
 }
 
+// ---- k-mer jump table (specialised search kernel) -----------------------------------------------------------------
+// ftab[s][e] = SA interval of the L-character pattern whose consumed characters c_0 .. c_{L-1} give the index
+// e = sum c_i * 4^(L-1-i)  (the LAST consumed character is the least significant digit, so the 16 patterns that differ
+// only in their last two characters share one 128-byte line).  Instead of walking the top L levels of the tree, the
+// kernel enumerates every pattern within the mismatch budget of the guide's first L characters -- one "combo" per
+// choice of substituted positions among the first L-2 characters, times the 16 endings -- and starts the tree search
+// from the surviving level-L intervals.  Same nodes at level L, same keys, as the level-by-level search.
+struct FtabEntry { uint32_t sp, width; };
+
+// combo word: bits 0..2 = number of substitutions j, then j fields of 6 bits: position (4 bits, < L-2) | sub << 4
+// (sub = 1..3: the substituted symbol is (c_p + sub) & 3)
+GSX_HD void ftab_apply(uint64_t combo, uint64_t q, uint32_t L, uint32_t gidx, const uint64_t* pow5,
+                       uint32_t& idx, uint64_t& key, uint32_t& j) {
+    j = (uint32_t)(combo & 7u); idx = gidx; key = 0;
+    for (uint32_t t = 0; t < j; t++) {
+        const uint32_t f = (uint32_t)(combo >> (3u + 6u * t)) & 63u, p = f & 15u, sub = f >> 4;
+        const uint32_t c = (uint32_t)(q >> (2u * p)) & 3u, s2 = (c + sub) & 3u;
+        idx += (uint32_t)((int32_t)(s2 - c) << (2u * (L - 1u - p)));
+        key += (uint64_t)(1u + s2) * pow5[L - 1u - p];
+    }
+}
+// ending e (0..15) of a combo: symbols of positions L-2 and L-1; returns the extra mismatches and adds their key digits
+GSX_HD uint32_t ftab_ending(uint32_t e, uint64_t q, uint32_t L, uint64_t& key) {
+    const uint32_t sa = e >> 2, sb = e & 3u;
+    const uint32_t ca = (uint32_t)(q >> (2u * (L - 2u))) & 3u, cb = (uint32_t)(q >> (2u * (L - 1u))) & 3u;
+    uint32_t extra = 0;
+    if (sa != ca) { extra++; key += (uint64_t)(1u + sa) * 5ull; }
+    if (sb != cb) { extra++; key += (uint64_t)(1u + sb); }
+    return extra;
+}
+
 // ordering of the matches of one guide: bucket (mismatches) ascending, forward index before reverse index, string order
 GSX_HD int match_cmp(const MatchRec& x, const MatchRec& y) {
     uint32_t bx = ((x.info & 0xffu) << 1) | (x.task & 1u), by = ((y.info & 0xffu) << 1) | (y.task & 1u);

@@ -46,7 +46,7 @@ bool load_gsx(const std::string& prefix, HostIndex& ix, std::string& err);
 
 struct DeviceStrand {
     DevStrand d{};
-    void* blocks = nullptr; void* lines = nullptr; void* sa = nullptr; void* exc_rows = nullptr; void* exc_lf = nullptr; void* n_rows = nullptr;
+    void* blocks = nullptr; void* lines = nullptr; void* ftab = nullptr; void* sa = nullptr; void* exc_rows = nullptr; void* exc_lf = nullptr; void* n_rows = nullptr;
 };
 struct DeviceIndex {
     int device = 0;
@@ -107,6 +107,11 @@ struct Prepared {
     std::vector<uint64_t> gq;      // per guide: 2-bit symbols in consumption order | qlen << 58
     uint32_t pampack = 0, plen = 0;
 };
+
+// every way to substitute at most M of the first n_pos characters (k-mer jump table enumeration, gsx_core.h)
+std::vector<uint64_t> ftab_combos(uint32_t n_pos, uint32_t M);
+// table index of the guide's first L characters (2-bit codes c_i at bits 2i of q): sum c_i * 4^(L-1-i)
+inline uint32_t ftab_exact_index(uint64_t q, uint32_t L) { uint32_t e = 0; for (uint32_t i = 0; i < L; i++) e = (e << 2) | (uint32_t)((q >> (2 * i)) & 3); return e; }
 }  // namespace gsx
 
 struct gsx_result {

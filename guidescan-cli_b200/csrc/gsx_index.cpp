@@ -183,6 +183,26 @@ bool read_fasta(const std::string& path, std::vector<uint8_t>& seq, HostIndex& i
     return true;
 }
 
+std::vector<uint64_t> ftab_combos(uint32_t n_pos, uint32_t M) {
+    std::vector<uint64_t> out;
+    if (n_pos > 16) n_pos = 16;
+    std::vector<uint32_t> pos;
+    // subsets of positions in increasing order, each with 3^j substitution choices
+    struct Rec { static void go(uint32_t start, uint32_t n_pos, uint32_t M, std::vector<uint32_t>& pos, std::vector<uint64_t>& out) {
+        const uint32_t j = (uint32_t)pos.size();
+        uint32_t n_sub = 1; for (uint32_t t = 0; t < j; t++) n_sub *= 3;
+        for (uint32_t code = 0; code < n_sub; code++) {
+            uint64_t w = j; uint32_t c = code;
+            for (uint32_t t = 0; t < j; t++) { uint32_t sub = 1 + c % 3; c /= 3; w |= (uint64_t)(pos[t] | (sub << 4)) << (3 + 6 * t); }
+            out.push_back(w);
+        }
+        if (j == M) return;
+        for (uint32_t p = start; p < n_pos; p++) { pos.push_back(p); go(p + 1, n_pos, M, pos, out); pos.pop_back(); }
+    } };
+    Rec::go(0, n_pos, M, pos, out);
+    return out;
+}
+
 // ---- native cache format (<prefix>.gsx): a flat dump of the HBM layout ----------------------------------------
 namespace {
 const char kMagic[8] = {'G', 'S', 'X', 'I', 'D', 'X', '0', '2'};

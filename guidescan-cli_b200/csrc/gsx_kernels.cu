@@ -21,8 +21,13 @@ namespace gsx {
 __constant__ double c_cfd_mm[4 * 4 * 20];
 __constant__ double c_cfd_pam[4 * 4];
 
+__constant__ uint64_t c_pow5[32];
+
 cudaError_t upload_cfd_tables() {
     cudaError_t e = cudaMemcpyToSymbol(c_cfd_mm, GSX_CFD_MM, sizeof(c_cfd_mm));
+    if (e != cudaSuccess) return e;
+    uint64_t p5[32]; p5[0] = 1; for (int i = 1; i < 32; i++) p5[i] = p5[i - 1] * 5ull;      // 5^27 < 2^63
+    e = cudaMemcpyToSymbol(c_pow5, p5, sizeof(p5));
     if (e != cudaSuccess) return e;
     return cudaMemcpyToSymbol(c_cfd_pam, GSX_CFD_PAM, sizeof(c_cfd_pam));
 }
@@ -280,6 +285,45 @@ int search_grid_warps(bool wide, int variant, int sm_count) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// k-mer jump table: one backward-search expansion per entry and level (children of entry e are entries 4e .. 4e+3)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void ftab_expand_kernel(DevStrand st, const FtabEntry* __restrict__ cur, FtabEntry* __restrict__ nxt, uint32_t n_cur) {
+    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n_cur; e += gridDim.x * blockDim.x) {
+        const FtabEntry t = cur[e];
+        uint32_t os[4] = {0, 0, 0, 0}, oe[4] = {0, 0, 0, 0};
+        if (t.width) {
+            const uint32_t e1 = t.sp + t.width;
+            Blk B0 = ld_block(block_ptr(st, t.sp >> 6));
+            uint32_t c0[4] = {B0.c0, B0.c1, B0.c2, B0.c3};
+            block_occ(st, c0, B0.hi, B0.lo, t.sp, os);
+            Blk B1 = ld_block(block_ptr(st, e1 >> 6));
+            uint32_t c1[4] = {B1.c0, B1.c1, B1.c2, B1.c3};
+            block_occ(st, c1, B1.hi, B1.lo, e1, oe);
+        }
+        FtabEntry o[4];
+        for (int s = 0; s < 4; s++) { o[s].sp = st.C[s] + os[s]; o[s].width = oe[s] - os[s]; }
+        reinterpret_cast<uint4*>(nxt)[2 * (size_t)e] = make_uint4(o[0].sp, o[0].width, o[1].sp, o[1].width);
+        reinterpret_cast<uint4*>(nxt)[2 * (size_t)e + 1] = make_uint4(o[2].sp, o[2].width, o[3].sp, o[3].width);
+    }
+}
+__global__ void ftab_root_kernel(FtabEntry* t, uint32_t n) { if (threadIdx.x == 0 && blockIdx.x == 0) { t[0].sp = 0; t[0].width = n; } }
+
+cudaError_t launch_build_ftab(const DevStrand& st, uint32_t L, void* tab, void* tmp, cudaStream_t s) {
+    // ping-pong so that level L lands in `tab`
+    FtabEntry* a = (FtabEntry*)((L & 1) ? tmp : tab);
+    FtabEntry* b = (FtabEntry*)((L & 1) ? tab : tmp);
+    ftab_root_kernel<<<1, 32, 0, s>>>(a, st.n);
+    uint32_t n_cur = 1;
+    for (uint32_t d = 0; d < L; d++) {
+        long blocks = ((long)n_cur + 255) / 256; if (blocks > 148 * 16) blocks = 148 * 16;
+        ftab_expand_kernel<<<(int)blocks, 256, 0, s>>>(st, a, b, n_cur);
+        FtabEntry* t = a; a = b; b = t;
+        n_cur *= 4;
+    }
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // look-ahead planes: t_j(r) = BWT[LF^j(r)], j = 1..6, stored behind each OccBlock in its own 128-byte line
 // ---------------------------------------------------------------------------------------------------------
 __global__ void build_lookahead_kernel(DevStrand st, unsigned char* __restrict__ lines, uint32_t n_blocks) {
@@ -353,6 +397,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) search_fast_kernel(SearchArg
     uint32_t head = 0, count = 0, spill_count = 0;
     bool tasks_remain = true, has = false;
     uint32_t sp = 0, ep = 0, tlm = 0; uint64_t key = 0, q = 0;
+    // k-mer jump table phase of the warp's current task (all warp-uniform)
+    uint32_t cur_task = 0xFFFFFFFFu, cursor = 0, task_gidx = 0; uint64_t task_q = 0;
     unsigned long long n_nodes = 0, n_lookups = 0, n_spilled = 0;     // accumulated by lane 0 only
     const uint32_t M = a.p.M, plen = a.plen;
     uint32_t iters = 0;
@@ -374,19 +420,79 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) search_fast_kernel(SearchArg
                 __syncwarp();
                 count += take; spill_count -= take;
             }
-            if (count < n_need && tasks_remain) {
+            if (count < n_need && cur_task == 0xFFFFFFFFu && tasks_remain) {
                 uint32_t t = 0;
                 if (lane == 0) t = atomicAdd(a.task_counter, 1u);
                 t = __shfl_sync(FULL, t, 0);
                 if (t >= a.p.n_tasks) tasks_remain = false;
                 else if (!(a.skip && a.skip[t >> 1])) {
-                    if (lane == 0) {
-                        uint32_t slot = (head + count) & (CAP - 1);
-                        r_sp[slot] = 0; r_ep[slot] = ((t & 1u) ? a.st[1].n : a.st[0].n) - 1u; r_tlm[slot] = t; r_key[slot] = 0;
+                    const uint64_t tq = __ldg(a.gq + (t >> 1));
+                    const uint32_t L = (t & 1u) ? a.st[1].ftab_L : a.st[0].ftab_L;
+                    if (L && (uint32_t)(tq >> 58) >= L && a.n_combos) {
+                        // start the task from the k-mer jump table: exact index of its first L characters
+                        cur_task = t; cursor = 0; task_q = tq;
+                        uint32_t e = 0;
+                        for (uint32_t i = 0; i < L; i++) e = (e << 2) | ((uint32_t)(tq >> (2u * i)) & 3u);
+                        task_gidx = e;
+                    } else {
+                        if (lane == 0) {
+                            uint32_t slot = (head + count) & (CAP - 1);
+                            r_sp[slot] = 0; r_ep[slot] = ((t & 1u) ? a.st[1].n : a.st[0].n) - 1u; r_tlm[slot] = t; r_key[slot] = 0;
+                        }
+                        __syncwarp();
+                        count += 1;
                     }
-                    __syncwarp();
-                    count += 1;
                 }
+            }
+            if (count < n_need && cur_task != 0xFFFFFFFFu) {
+                // one table step: lane = one substitution combo over the first L-2 characters = one 128-byte line of
+                // 16 endings; every ending within the remaining budget whose interval is non-empty becomes a level-L node
+                const bool s1t = (cur_task & 1u) != 0;
+                const uint32_t L = s1t ? a.st[1].ftab_L : a.st[0].ftab_L;
+                const FtabEntry* tab = reinterpret_cast<const FtabEntry*>(s1t ? a.st[1].ftab : a.st[0].ftab);
+                const uint32_t ci = cursor + lane;
+                const bool hasc = ci < a.n_combos;
+                uint32_t idx = 0, j = 0; uint64_t kbase = 0;
+                if (hasc) ftab_apply(__ldg(a.combos + ci), task_q, L, task_gidx, c_pow5, idx, kbase, j);
+                const uint32_t budget = M - j;                       // combos hold at most M substitutions
+                const uint32_t e0 = (((uint32_t)(task_q >> (2u * (L - 2u))) & 3u) << 2) | ((uint32_t)(task_q >> (2u * (L - 1u))) & 3u);
+                {
+                    const uint32_t lines_mask = __ballot_sync(FULL, hasc);
+                    if (lane == 0) n_lookups += __popc(lines_mask);
+                }
+#pragma unroll 1
+                for (uint32_t i = 0; i < 16; i++) {
+                    const uint32_t e = (e0 + i) & 15u;               // the exact ending first: it is valid for every combo
+                    uint64_t k2 = kbase;
+                    const uint32_t extra = ftab_ending(e, task_q, L, k2);
+                    const bool ok = hasc && extra <= budget;
+                    FtabEntry t; t.sp = 0; t.width = 0;
+                    if (ok) { const uint2 v = __ldg(reinterpret_cast<const uint2*>(tab + ((idx & ~15u) | e))); t.sp = v.x; t.width = v.y; }
+                    const bool push = ok && t.width != 0;
+                    const uint32_t pmask = __ballot_sync(FULL, push);
+                    if (pmask) {
+                        const uint32_t np = __popc(pmask);
+                        if (count + np > (uint32_t)CAP) {
+                            if (spill_count + 32u > scap) { if (lane == 0) atomicOr(a.error_flag, GSX_KERR_SPILL_OVERFLOW); }
+                            else {
+                                const uint32_t slot = (head + lane) & (CAP - 1), si = spill_count + lane;
+                                s_base[si] = r_sp[slot]; s_base[scap + si] = r_ep[slot]; s_base[2 * scap + si] = r_tlm[slot]; s_key[si] = r_key[slot];
+                                spill_count += 32u; if (lane == 0) n_spilled += 32;
+                            }
+                            __syncwarp();
+                            head = (head + 32u) & (CAP - 1); count -= 32u;
+                        }
+                        if (push) {
+                            const uint32_t w = (head + count + __popc(pmask & lt_mask)) & (CAP - 1);
+                            r_sp[w] = t.sp; r_ep[w] = t.sp + t.width - 1u; r_key[w] = k2;
+                            r_tlm[w] = cur_task | ((j + extra) << 24) | (L << 27);
+                        }
+                        __syncwarp();
+                        count += np;
+                    }
+                }
+                cursor += 32u;
+                if (cursor >= a.n_combos) cur_task = 0xFFFFFFFFu;
             }
             uint32_t take = count < n_need ? count : n_need;
             uint32_t rank = __popc(need_mask & lt_mask);
@@ -401,7 +507,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) search_fast_kernel(SearchArg
         }
         const uint32_t act = __ballot_sync(FULL, has);
         if (act == 0) {
-            if (count == 0 && spill_count == 0 && !tasks_remain) break;
+            if (count == 0 && spill_count == 0 && !tasks_remain && cur_task == 0xFFFFFFFFu) break;
             continue;
         }
         // ---- occurrence lookups -----------------------------------------------------------------------------

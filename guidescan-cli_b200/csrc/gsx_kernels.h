@@ -33,6 +33,8 @@ struct SearchArgs {
     uint32_t pampack;                  // 3 bits per PAM character in consumption order (4 = N wildcard, 5 = never matches)
     uint32_t plen;
     uint32_t pin_width;                // packed-block loads of intervals at least this wide ask L2 to keep the line (evict_last)
+    const uint64_t* combos;            // k-mer jump table enumeration: substitution combos over the first ftab_L - 2 characters
+    uint32_t n_combos;
 };
 
 struct LocateArgs {
@@ -61,6 +63,8 @@ struct SpecArgs {
 
 cudaError_t upload_cfd_tables();
 // packed 32-byte blocks (src) -> 128-byte lines with look-ahead planes t1..t6 (dst must hold n_blocks * 128 bytes)
+// k-mer jump table of depth L for one strand; tab and tmp must each hold 4^L entries of 8 bytes; result ends up in tab
+cudaError_t launch_build_ftab(const DevStrand& st, uint32_t L, void* tab, void* tmp, cudaStream_t s);
 cudaError_t launch_build_lookahead(const DevStrand& src, unsigned char* lines, uint32_t n_blocks, cudaStream_t s);
 int search_grid_warps(bool wide, int variant, int sm_count);
 cudaError_t launch_search(const SearchArgs& a, bool wide, int variant, int sm_count, cudaStream_t s, int* warps_total);

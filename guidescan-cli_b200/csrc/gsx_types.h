@@ -55,6 +55,8 @@ struct DevStrand {
     uint32_t C[5];                 // C[A],C[C],C[G],C[T],C[N]: rows whose suffix starts with a smaller symbol
     uint32_t exc_lo, exc_hi;       // first / last exception row (fast reject)
     uint32_t blk_shift;            // log2 of the byte stride between OccBlocks in `blocks` (5 = packed)
+    const void* ftab;              // optional k-mer jump table: 4^ftab_L FtabEntry {sp, width} (gsx_core.h), nullptr if absent
+    uint32_t ftab_L;
     const unsigned char* lines;    // optional second copy, one 128-byte line per 64 rows: OccBlock + six look-ahead symbol
                                    // planes (see build_lookahead_kernel); nullptr if absent
 };

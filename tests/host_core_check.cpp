@@ -33,7 +33,7 @@ static DevStrand view_of(const HostStrand& h) {
     d.n_rows = h.n_rows.data(); d.n = (uint32_t)h.n; d.n_exc = (uint32_t)h.exc_rows.size(); d.n_nrows = (uint32_t)h.n_rows.size();
     d.sa_shift = h.sa_shift; for (int c = 0; c < 5; c++) d.C[c] = h.C[c];
     d.exc_lo = h.exc_rows.empty() ? 0xFFFFFFFFu : h.exc_rows.front(); d.exc_hi = h.exc_rows.empty() ? 0 : h.exc_rows.back();
-    d.blk_shift = 5; d.lines = nullptr;
+    d.blk_shift = 5; d.lines = nullptr; d.ftab = nullptr; d.ftab_L = 0;
     return d;
 }
 
@@ -67,6 +67,29 @@ static void build_look(const DevStrand& st, std::vector<uint64_t>& look) {
     }
 }
 
+// k-mer jump table (what build_ftab does on the device), built on the host level by level
+static uint32_t g_ftab_L = 0;
+static std::vector<FtabEntry> g_ftab[2];
+static uint64_t g_pow5[32];
+
+static void build_ftab_host(const DevStrand& st, uint32_t L, std::vector<FtabEntry>& tab) {
+    std::vector<FtabEntry> cur(1); cur[0] = {0, st.n};
+    for (uint32_t d = 0; d < L; d++) {
+        std::vector<FtabEntry> nxt(cur.size() * 4);
+        for (size_t e = 0; e < cur.size(); e++) {
+            uint32_t os[4] = {0, 0, 0, 0}, oe[4] = {0, 0, 0, 0};
+            if (cur[e].width) {
+                uint32_t sp = cur[e].sp, e1 = sp + cur[e].width;
+                const OccBlock& b0 = st.blocks[sp >> 6]; const OccBlock& b1 = st.blocks[e1 >> 6];
+                block_occ(st, b0.cnt, b0.hi, b0.lo, sp, os); block_occ(st, b1.cnt, b1.hi, b1.lo, e1, oe);
+            }
+            for (uint32_t s = 0; s < 4; s++) nxt[e * 4 + s] = {st.C[s] + os[s], oe[s] - os[s]};
+        }
+        cur.swap(nxt);
+    }
+    tab.swap(cur);
+}
+
 template <bool WIDE>
 static void dfs(const DevStrand st[2], const Prepared& prep, uint32_t task, uint32_t M, uint32_t R, uint32_t D, bool counting,
                 uint64_t* count, std::vector<MatchRec>& out, uint64_t* nodes) {
@@ -74,8 +97,28 @@ static void dfs(const DevStrand st[2], const Prepared& prep, uint32_t task, uint
     const GuideRec& g = prep.recs[task >> 1];
     ExpandCtx cx{&s, &g, &prep.pamsets[g.pamset], M, R, D};
     std::vector<Node> stack;
-    Node root{}; root.sp = 0; root.ep = s.n - 1; root.task = task;
-    stack.push_back(root);
+    if (!WIDE && g_ftab_L && g.qlen >= g_ftab_L && prep.fast_ok) {
+        // the table phase of search_fast_kernel: every pattern within the budget of the first L characters
+        const uint32_t L = g_ftab_L; const uint64_t q = prep.gq[task >> 1];
+        const uint32_t gidx = ftab_exact_index(q, L);
+        static std::vector<uint64_t> combos; static uint32_t combos_M = ~0u;
+        if (combos_M != M) { combos = ftab_combos(L - 2, M); combos_M = M; }
+        for (uint64_t combo : combos) {
+            uint32_t idx, j; uint64_t key;
+            ftab_apply(combo, q, L, gidx, g_pow5, idx, key, j);
+            for (uint32_t e = 0; e < 16; e++) {
+                uint64_t k2 = key; uint32_t extra = ftab_ending(e, q, L, k2);
+                if (j + extra > M) continue;
+                const FtabEntry& t = g_ftab[task & 1][(idx & ~15u) | e];
+                if (!t.width) continue;
+                Node nd{}; nd.sp = t.sp; nd.ep = t.sp + t.width - 1; nd.key_lo = k2; nd.task = task; nd.meta = meta_make(L, j + extra, 0, 0, 0, 0, 0);
+                stack.push_back(nd);
+            }
+        }
+    } else {
+        Node root{}; root.sp = 0; root.ep = s.n - 1; root.task = task;
+        stack.push_back(root);
+    }
     while (!stack.empty()) {
         Node nd = stack.back(); stack.pop_back();
         (*nodes)++;
@@ -114,6 +157,7 @@ int main(int argc, char** argv) {
         else if (a == "--dna") p.dna_bulges = atoi(argv[++i]); else if (a == "-t") p.threshold = atoi(argv[++i]);
         else if (a == "--start") p.start = 1; else if (a == "--max") p.max_off_targets = atoll(argv[++i]);
         else if (a == "--lookahead") g_prune = true;
+        else if (a == "--ftab") g_ftab_L = atoi(argv[++i]);
         else if (a == "--sam") sam = true; else if (a == "--succinct") complete = false; else if (a == "-a") alts.push_back(argv[++i]);
         else { fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
     }
@@ -138,6 +182,10 @@ int main(int argc, char** argv) {
     Prepared prep;
     if (gsx_prepare_guides(gg.data(), n, &p, prep)) { fprintf(stderr, "%s\n", gsx_last_error()); return 1; }
     const uint32_t n_dist = p.mismatches + 1;
+    if (g_ftab_L) {
+        g_pow5[0] = 1; for (int i = 1; i < 32; i++) g_pow5[i] = g_pow5[i - 1] * 5ull;
+        build_ftab_host(st[0], g_ftab_L, g_ftab[0]); build_ftab_host(st[1], g_ftab_L, g_ftab[1]);
+    }
     if (g_prune) {
         if (!prep.fast_ok) { fprintf(stderr, "--lookahead needs a fast-path batch (one PAM, ACGT guides, no bulges)\n"); return 2; }
         build_look(st[0], g_look[0]); build_look(st[1], g_look[1]);

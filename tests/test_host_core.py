@@ -50,9 +50,10 @@ def test_lookahead_pruning_keeps_output_and_cuts_nodes(harness, tmp_path, m):
     O.ref_index(fa, os.path.join(d, "la"), cwd=d)
     O.Index(fa).enumerate_file(O.make_opts(mismatches=m), gcsv, os.path.join(d, "o.out"), nthreads=4)
     nodes = {}
-    for tag, extra in (("plain", []), ("look", ["--lookahead"])):
+    for tag, extra in (("plain", []), ("look", ["--lookahead"]), ("ftab", ["--ftab", "7"]), ("both", ["--lookahead", "--ftab", "8"])):
         out = os.path.join(d, tag + ".out")
         r = subprocess.run([harness, os.path.join(d, "la"), gcsv, out, "-m", str(m)] + extra, capture_output=True, text=True, check=True)
         assert open(out, "rb").read() == open(os.path.join(d, "o.out"), "rb").read()
         nodes[tag] = int(r.stderr.split(" guides, ")[1].split(" nodes")[0])
     assert nodes["look"] < 0.8 * nodes["plain"], nodes
+    assert nodes["ftab"] < nodes["plain"] and nodes["both"] < nodes["look"], nodes

@@ -180,22 +180,27 @@ def test_gpu_built_index_with_repeats_and_dense_samples(gsx, tmp_path):
         r.close(); ix.close()
 
 
-@pytest.fixture(scope="module", params=["lookahead", "packed"])
+LAYOUTS = {"full": {"GSX_LOOKAHEAD": "1", "GSX_FTAB": "-1"}, "lookahead": {"GSX_LOOKAHEAD": "1", "GSX_FTAB": "0"},
+           "ftab": {"GSX_LOOKAHEAD": "0", "GSX_FTAB": "8"}, "packed": {"GSX_LOOKAHEAD": "0", "GSX_FTAB": "0"}}
+
+
+@pytest.fixture(scope="module", params=list(LAYOUTS))
 def seeded_case(gsx, tmp_path_factory, request):
     """1.5 Mb uniform genome, 400 NGG guides: eligible for the specialised search kernel (one PAM, ACGT guides, no N);
-    once with 128-byte lines + look-ahead planes (default), once with packed 32-byte blocks"""
+    index layouts: packed blocks only / + look-ahead lines / + k-mer jump table / both (the default)"""
     import oracle as O
     import synth
     d = str(tmp_path_factory.mktemp("fast"))
     synth.make_dataset(d, 1_500_000, 5, 400, seed=21, name="f")
     fa, gcsv = os.path.join(d, "f.fa"), os.path.join(d, "f.guides.csv")
-    old = os.environ.get("GSX_LOOKAHEAD")
-    os.environ["GSX_LOOKAHEAD"] = "1" if request.param == "lookahead" else "0"
+    old = {k: os.environ.get(k) for k in LAYOUTS[request.param]}
+    os.environ.update(LAYOUTS[request.param])
     ix = gsx.Index.build(fa, devices=[0])
-    if old is None:
-        os.environ.pop("GSX_LOOKAHEAD")
-    else:
-        os.environ["GSX_LOOKAHEAD"] = old
+    for k, v in old.items():
+        if v is None:
+            os.environ.pop(k)
+        else:
+            os.environ[k] = v
     oix = O.Index(fa)
     yield d, gcsv, ix, oix, request.param
     ix.close()
@@ -220,12 +225,11 @@ def test_fast_and_general_kernels_agree_with_oracle(gsx, seeded_case, monkeypatc
         assert open(out, "rb").read() == want
         nodes[force_general] = (ctr["nodes"], ctr["lookups"], ctr["matches"], ctr["hits"])
     assert nodes["0"][2:] == nodes["1"][2:]  # same matches and hits whichever kernel walks the tree
-    if layout == "packed" or kw["mismatches"] == 0:
-        assert nodes["0"][0] <= nodes["1"][0]
-    else:
-        assert nodes["0"][0] < nodes["1"][0]     # look-ahead pruning expands fewer nodes
+    assert nodes["0"][0] <= nodes["1"][0]
     if layout == "packed":
-        assert nodes["0"] == nodes["1"]          # without it: same tree, same lookups
+        assert nodes["0"] == nodes["1"]          # no pruning, no jump table: same tree, same lookups
+    elif kw["mismatches"] >= 2:
+        assert nodes["0"][0] < nodes["1"][0]     # look-ahead pruning / the jump table expand fewer nodes
 
 
 @pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
