@@ -40,6 +40,15 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_traffic(args):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture of this same workload."""
+    p = os.path.join(ROOT, "profiles", "search_traffic.json")
+    key = "%dmb_%d_m%d" % (int(args.genome_mb), args.guides_per_step, args.mismatches)
+    if os.path.exists(p):
+        return json.load(open(p)).get(key)
+    return None
+
+
 def random_gather_peak():
     p = os.path.join(ROOT, "profiles", "random_gather_peak.json")
     if os.path.exists(p):
@@ -241,6 +250,7 @@ def run_gsx(args):
         launch_ms = search_ms / args.steps
         achieved = alg_bytes_per_launch / (launch_ms * 1e-3) / 1e9
         rg = random_gather_peak()
+        tr = measured_traffic(args)
         line = {
             "metric": METRIC, "value": total_guides / (dev_ms * 1e-3), "unit": "guides/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -254,7 +264,8 @@ def run_gsx(args):
             "e2e": {"value": total_guides / e2e_s, "unit": "guides/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": int(d2h_bytes),
                     "ms_per_step": e2e_s * 1e3 / args.steps},
             "gpu_launches": int(ctr_tot["launches"]),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": tr["dram_bytes_per_launch"] if tr else None,
+                         "traffic_source": tr["source"] if tr else None,
                          "kernel": "search_fast_kernel" if not os.environ.get("GSX_FORCE_GENERAL", "0") == "1" else "search_kernel", "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes_per_launch, "lookups_per_guide": lookups / total_guides,
                          "nodes_per_guide": nodes / total_guides, "launch_ms": launch_ms,

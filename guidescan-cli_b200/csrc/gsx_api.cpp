@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -374,8 +375,10 @@ int gsx_prepare_guides(const gsx_guide* guides, size_t n, const gsx_params* p, g
     out.fast_ok = !out.wide && set_of.size() == 1 && out.pamsets[0].n_pams == 1 && n > 0;
     if (out.fast_ok) {
         out.gq.resize(n);
+        out.min_qlen = 255;
         for (size_t i = 0; i < n && out.fast_ok; i++) {
             const GuideRec& r = out.recs[i];
+            out.min_qlen = std::min<uint32_t>(out.min_qlen, r.qlen);
             if (r.qlen > 29) { out.fast_ok = false; break; }
             uint64_t v = (uint64_t)r.qlen << 58;
             for (uint32_t l = 0; l < r.qlen; l++) { if (r.q[l] > 3) { out.fast_ok = false; break; } v |= (uint64_t)r.q[l] << (2 * l); }
@@ -446,9 +449,45 @@ static void run_device_job(DeviceJob* job) {
             a.pin_width = w >= 4.0e9 ? 0xFFFFFFFFu : (uint32_t)std::max(256.0, w);
             a.combos = nullptr; a.n_combos = 0;
         }
+        // slice-major front end (sweep_kernel) for large batches: needs the jump table and the look-ahead lines
+        const uint32_t ftab_L = di.st[0].d.ftab_L;
+        uint32_t sweep_sb = 0;
+        bool use_sweep = use_fast && ftab_L >= 6 && di.st[1].d.ftab_L == ftab_L && di.st[0].d.lines && di.st[1].d.lines && env_int("GSX_SWEEP", 1) &&
+                         n >= (uint32_t)env_int("GSX_SWEEP_MIN", 8192) && prep.min_qlen >= ftab_L && p.mismatches <= 4 && p.threshold <= 4;
+        if (use_sweep) {
+            const double per_strand = 8.0 * std::pow(4.0, (double)ftab_L) + (double)(di.st[0].d.n / 64 + 1) * 128.0;
+            const double target = (double)env_int("GSX_SWEEP_SLICE_MB", 32) * 1e6;
+            sweep_sb = 1; while (sweep_sb < ftab_L - 3 && per_strand / std::pow(4.0, (double)sweep_sb) > target) sweep_sb++;
+            if (env_int("GSX_SWEEP_SB", 0) > 0) sweep_sb = (uint32_t)env_int("GSX_SWEEP_SB", 0);
+            if (sweep_sb < 1 || sweep_sb + 3 > ftab_L) use_sweep = false;
+            if (2.0 * std::pow(4.0, (double)sweep_sb) * ((n + 31) / 32) >= 4.0e9) use_sweep = false;
+        }
+        uint64_t queue_cap = std::max<uint64_t>((uint64_t)n * 1024, 1u << 20);
+        if (env_int("GSX_QUEUE_CAP", 0) > 0) queue_cap = (uint64_t)env_int("GSX_QUEUE_CAP", 0);
+        SeedNode* d_queue = nullptr;
+        uint64_t n_launches = 0;
+        // fast path launch: [sweep_kernel ->] search_fast_kernel.  d_ctrs: [3] seed queue count, [4] sweep work-unit counter
+        auto launch_fast = [&](SearchArgs& m, cudaEvent_t ev_mid) {
+            if (use_sweep) {
+                SweepArgs w{};
+                std::vector<uint32_t> masks;
+                sweep_make_plan(ftab_L, sweep_sb, m.p.M, w.plan, masks);
+                uint32_t* d_masks = B.alloc<uint32_t>(masks.size());
+                CK(cudaMemcpyAsync(d_masks, masks.data(), masks.size() * 4, cudaMemcpyHostToDevice, s)); CK(cudaStreamSynchronize(s));
+                if (!d_queue) d_queue = B.alloc<SeedNode>(queue_cap);
+                w.st[0] = m.st[0]; w.st[1] = m.st[1]; w.gq = m.gq; w.skip = m.skip; w.n_guides = n; w.masks = d_masks;
+                w.M = m.p.M; w.plen = m.plen; w.pampack = m.pampack; w.counting = m.p.counting;
+                w.queue = d_queue; w.queue_cap = (uint32_t)queue_cap; w.queue_count = d_ctrs + 3; w.item_counter = d_ctrs + 4;
+                w.error_flag = d_ctrs + 2; w.stats = d_stats;
+                CK(launch_sweep(w, env_int("GSX_SWEEP_VARIANT", 0), di.sm_count, s)); n_launches++;
+                m.seeds = d_queue; m.n_seeds = d_ctrs + 3; m.seed_cap = (uint32_t)queue_cap; m.combos = nullptr; m.n_combos = 0;
+            }
+            if (ev_mid) CK(cudaEventRecord(ev_mid, s));
+            CK(launch_search_fast(m, variant_f, di.sm_count, s)); n_launches++;
+        };
+        auto grow_queue = [&]() { B.free_one(d_queue); d_queue = nullptr; queue_cap *= 4; if (queue_cap > (1ull << 31)) throw std::runtime_error("seed queue keeps overflowing"); };
 
         CK(cudaEventRecord(ev[0], s));
-        uint64_t n_launches = 0;
         // ---- threshold prefilter (process.hpp:66-76): mismatch-only counting search, guide dropped if > 1 site -----
         if (p.threshold > 0) {
             unsigned long long* d_gcount = B.alloc<unsigned long long>(n, true, s);
@@ -460,18 +499,18 @@ static void run_device_job(DeviceJob* job) {
                 CK(cudaMemsetAsync(d_ctrs, 0, 8 * sizeof(uint32_t), s));
                 CK(cudaMemsetAsync(d_gcount, 0, (size_t)n * 8, s));
                 SearchArgs c = a; c.p.M = (uint32_t)p.threshold; c.p.R = c.p.D = 0; c.p.counting = 1; c.p.match_cap = 0; c.p.spill_cap = spill_cap;
-                if (use_fast && di.st[0].d.ftab_L) {
-                    std::vector<uint64_t> cb = ftab_combos(di.st[0].d.ftab_L - 2, c.p.M);
+                if (use_fast && ftab_L && !use_sweep) {
+                    std::vector<uint64_t> cb = ftab_combos(ftab_L - 2, c.p.M);
                     uint64_t* d_cb = B.alloc<uint64_t>(cb.size());
                     CK(cudaMemcpyAsync(d_cb, cb.data(), cb.size() * 8, cudaMemcpyHostToDevice, s)); CK(cudaStreamSynchronize(s));
                     c.combos = d_cb; c.n_combos = (uint32_t)cb.size();
                 }
                 c.guide_count = d_gcount; c.spill = d_spill; c.skip = nullptr; c.matches = nullptr;
-                if (use_fast) CK(launch_search_fast(c, variant_f, di.sm_count, s)); else CK(launch_search(c, false, variant_n, di.sm_count, s, nullptr));
-                n_launches++;
+                if (use_fast) launch_fast(c, nullptr); else { CK(launch_search(c, false, variant_n, di.sm_count, s, nullptr)); n_launches++; }
                 uint32_t h[3]; CK(cudaMemcpyAsync(h, d_ctrs, sizeof h, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s));
                 B.free_one(d_spill);
                 if (h[2] & GSX_KERR_WATCHDOG) throw std::runtime_error("search kernel watchdog tripped");
+                if (h[2] & GSX_KERR_QUEUE_OVERFLOW) { grow_queue(); if (h[2] & GSX_KERR_SPILL_OVERFLOW) spill_cap *= 4; continue; }
                 if (h[2] & GSX_KERR_SPILL_OVERFLOW) { spill_cap *= 4; continue; }
                 break;
             }
@@ -487,8 +526,8 @@ static void run_device_job(DeviceJob* job) {
         if (env_int("GSX_MATCH_CAP", 0) > 0) match_cap = (uint64_t)env_int("GSX_MATCH_CAP", 0);      // tests: force the retry path
         if (env_int("GSX_SPILL_CAP", 0) > 0) spill_cap = (uint32_t)env_int("GSX_SPILL_CAP", 0);
         MatchRec* d_matches = nullptr; uint32_t* d_spill = nullptr; uint32_t n_matches = 0;
-        if (use_fast && di.st[0].d.ftab_L) {
-            std::vector<uint64_t> cb = ftab_combos(di.st[0].d.ftab_L - 2, p.mismatches);
+        if (use_fast && ftab_L && !use_sweep) {
+            std::vector<uint64_t> cb = ftab_combos(ftab_L - 2, p.mismatches);
             uint64_t* d_cb = B.alloc<uint64_t>(cb.size());
             CK(cudaMemcpyAsync(d_cb, cb.data(), cb.size() * 8, cudaMemcpyHostToDevice, s)); CK(cudaStreamSynchronize(s));
             a.combos = d_cb; a.n_combos = (uint32_t)cb.size();
@@ -505,13 +544,14 @@ static void run_device_job(DeviceJob* job) {
             SearchArgs m = a; m.p.M = p.mismatches; m.p.R = p.rna_bulges; m.p.D = p.dna_bulges; m.p.counting = 0;
             m.p.match_cap = (uint32_t)match_cap; m.p.spill_cap = spill_cap; m.spill = d_spill; m.matches = d_matches;
             m.skip = p.threshold > 0 ? d_dropped : nullptr;
-            if (use_fast) CK(launch_search_fast(m, variant_f, di.sm_count, s)); else CK(launch_search(m, wide, variant, di.sm_count, s, nullptr));
-            n_launches++;
-            uint32_t h[3]; CK(cudaMemcpyAsync(h, d_ctrs, sizeof h, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s));
+            CK(cudaEventRecord(ev[6], s));
+            if (use_fast) launch_fast(m, ev[7]); else { CK(cudaEventRecord(ev[7], s)); CK(launch_search(m, wide, variant, di.sm_count, s, nullptr)); n_launches++; }
+            uint32_t h[4]; CK(cudaMemcpyAsync(h, d_ctrs, sizeof h, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s));
             B.free_one(d_spill);
             if (h[2] & GSX_KERR_WATCHDOG) throw std::runtime_error("search kernel watchdog tripped");
-            if (h[2] & (GSX_KERR_MATCH_OVERFLOW | GSX_KERR_SPILL_OVERFLOW)) {
+            if (h[2] & (GSX_KERR_MATCH_OVERFLOW | GSX_KERR_SPILL_OVERFLOW | GSX_KERR_QUEUE_OVERFLOW)) {
                 B.free_one(d_matches);
+                if (h[2] & GSX_KERR_QUEUE_OVERFLOW) grow_queue();
                 if (h[2] & GSX_KERR_MATCH_OVERFLOW) match_cap = std::max<uint64_t>(match_cap * 2, (uint64_t)h[1] + (h[1] >> 2));
                 if (h[2] & GSX_KERR_SPILL_OVERFLOW) spill_cap *= 4;
                 if (match_cap > (1ull << 31)) throw std::runtime_error("more than 2^31 matches in one batch; lower the batch size");
@@ -584,6 +624,7 @@ static void run_device_job(DeviceJob* job) {
         CK(cudaEventElapsedTime(&ms, ev[3], ev[4])); job->ctr.ms_score = ms;
         CK(cudaEventElapsedTime(&ms, ev[0], ev[4])); job->ctr.ms_total_device = ms;
         CK(cudaEventElapsedTime(&ms, ev[4], ev[5])); job->ctr.ms_d2h = ms;
+        CK(cudaEventElapsedTime(&ms, ev[6], ev[7])); job->ctr.ms_sweep = ms; job->ctr.seeds = st[6];
         job->ctr.nodes = st[0]; job->ctr.lookups = st[1]; job->ctr.spills = st[2]; job->ctr.lf_steps = st[3];
         job->ctr.matches = n_matches; job->ctr.hits = nh; job->ctr.launches = n_launches;
         for (auto& e : ev) cudaEventDestroy(e);
@@ -650,7 +691,8 @@ extern "C" int gsx_enumerate(const gsx_index* ix, const gsx_guide* guides, size_
         r->part_g0.push_back(g); r->part_h0.push_back(h); g += j.out.n_guides; h += j.out.n_hits;
         r->parts.push_back(std::move(j.out));
         gsx_counters& c = r->counters;
-        c.nodes += j.ctr.nodes; c.lookups += j.ctr.lookups; c.matches += j.ctr.matches; c.hits += j.ctr.hits; c.lf_steps += j.ctr.lf_steps; c.spills += j.ctr.spills; c.launches += j.ctr.launches;
+        c.nodes += j.ctr.nodes; c.lookups += j.ctr.lookups; c.matches += j.ctr.matches; c.hits += j.ctr.hits; c.lf_steps += j.ctr.lf_steps; c.spills += j.ctr.spills; c.launches += j.ctr.launches; c.seeds += j.ctr.seeds;
+        c.ms_sweep = std::max(c.ms_sweep, j.ctr.ms_sweep);
         c.ms_search = std::max(c.ms_search, j.ctr.ms_search); c.ms_arrange = std::max(c.ms_arrange, j.ctr.ms_arrange);
         c.ms_locate = std::max(c.ms_locate, j.ctr.ms_locate); c.ms_score = std::max(c.ms_score, j.ctr.ms_score);
         c.ms_total_device = std::max(c.ms_total_device, j.ctr.ms_total_device); c.ms_h2d = std::max(c.ms_h2d, j.ctr.ms_h2d); c.ms_d2h = std::max(c.ms_d2h, j.ctr.ms_d2h);

@@ -398,35 +398,134 @@ GSX_HD uint32_t viable_children(const uint64_t hi[7], const uint64_t lo[7], uint
     return ((alive & ~h0 & ~l0) ? 1u : 0u) | ((alive & ~h0 & l0) ? 2u : 0u) | ((alive & h0 & ~l0) ? 4u : 0u) | ((alive & h0 & l0) ? 8u : 0u);
 }
 
-// ---- k-mer jump table (specialised search kernel) -----------------------------------------------------------------
+// Sweep-kernel variant of the same test, sector by sector: can ANY row of [sp, ep] (inside one block or two adjacent
+// ones) still reach the final level?  ld(block, k, w) fetches 32-byte sector k of the block's 128-byte line as four
+// 64-bit words: k = 0 the OccBlock {cnt01, cnt23, hi, lo}, k = 1..3 the planes {hi_(2k-1), lo_(2k-1), hi_2k, lo_2k}.
+// Sectors are fetched only while some row is alive.  Intervals spanning more than two blocks are not examined (true).
+// `sectors` receives the number of sectors fetched.
+template <class LoadSector>
+GSX_HD bool node_viable(LoadSector ld, uint32_t sp, uint32_t ep, uint32_t lvl, uint32_t qlen, uint32_t total, uint64_t q,
+                        uint32_t pampack, uint32_t budget, uint32_t& sectors) {
+    const uint32_t e1 = ep + 1u, bs = sp >> 6, be = e1 >> 6;
+    if (be - bs > 1u) return true;
+    const uint32_t left = total - lvl;
+    const uint64_t B0 = (budget & 1u) ? ~0ull : 0ull, B1 = (budget & 2u) ? ~0ull : 0ull, B2 = (budget & 4u) ? ~0ull : 0ull;
+    for (uint32_t part = 0; part < 2u; part++) {
+        if (part == 1u && (be == bs || (e1 & 63u) == 0u)) break;
+        const uint32_t r0 = part ? 0u : (sp & 63u), r1 = part ? (ep & 63u) : (be != bs ? 63u : (ep & 63u));
+        uint64_t alive = (r1 == 63u ? ~0ull : ((1ull << (r1 + 1u)) - 1ull)) & ~((1ull << r0) - 1ull);
+        uint64_t c0 = 0, c1 = 0, c2 = 0;
+        for (uint32_t k = 0; k < 4u && alive; k++) {
+            const uint32_t j0 = k ? 2u * k - 1u : 0u, nj = k ? 2u : 1u;
+            if (j0 >= left) break;
+            uint64_t w[4];
+            ld(bs + part, k, w); sectors++;
+            for (uint32_t u = 0; u < nj; u++) {
+                const uint32_t j = j0 + u;
+                if (j >= left) break;
+                const uint64_t hi = k ? w[2u * u] : w[2], lo = k ? w[2u * u + 1u] : w[3];
+                const uint32_t Lv = lvl + j;
+                uint32_t sym; bool proto = Lv < qlen, wild = false, kill = false;
+                if (proto) sym = (uint32_t)(q >> (2u * Lv)) & 3u;
+                else { const uint32_t pc = (pampack >> (3u * (Lv - qlen))) & 7u; sym = pc & 3u; wild = pc == 4u; kill = pc > 4u; }
+                const uint64_t eq = ~(hi ^ ((sym & 2u) ? ~0ull : 0ull)) & ~(lo ^ ((sym & 1u) ? ~0ull : 0ull));
+                if (proto) {
+                    const uint64_t mis = ~eq;
+                    const uint64_t k0 = c0 & mis; c0 ^= mis;
+                    const uint64_t k1 = c1 & k0; c1 ^= k0;
+                    c2 ^= k1;
+                } else if (kill) alive = 0;
+                else if (!wild) alive &= eq;
+            }
+            const uint64_t gt = (c2 & ~B2) | (~(c2 ^ B2) & ((c1 & ~B1) | (~(c1 ^ B1) & (c0 & ~B0))));
+            alive &= ~gt;
+        }
+        if (alive) return true;
+    }
+    return false;
+}
+
+// ---- k-mer jump table (specialised search kernels) ------------------------------------------------------------------
 // ftab[s][e] = SA interval of the L-character pattern whose consumed characters c_0 .. c_{L-1} give the index
-// e = sum c_i * 4^(L-1-i)  (the LAST consumed character is the least significant digit, so the 16 patterns that differ
-// only in their last two characters share one 128-byte line).  Instead of walking the top L levels of the tree, the
-// kernel enumerates every pattern within the mismatch budget of the guide's first L characters -- one "combo" per
-// choice of substituted positions among the first L-2 characters, times the 16 endings -- and starts the tree search
-// from the surviving level-L intervals.  Same nodes at level L, same keys, as the level-by-level search.
+// e = sum c_i * 4^i.  The LAST consumed character is the first character of the pattern in text order, so e is the
+// lexicographic rank of the pattern among all L-mers and sp is non-decreasing in e: a contiguous range of table entries
+// covers a contiguous range of BWT rows (the slice-major kernel relies on it).  With the 2-bit codes of a guide packed
+// at bits 2i of q, the guide's own entry is simply q & (4^L - 1).  The 16 patterns that differ only in their first two
+// consumed characters share one 128-byte line.
+// Instead of walking the top L levels of the tree, the kernels enumerate every pattern within the mismatch budget of
+// the guide's first L characters and start the tree search from the surviving level-L intervals.  Same nodes at level L,
+// same keys, as the level-by-level search.
 struct FtabEntry { uint32_t sp, width; };
 
-// combo word: bits 0..2 = number of substitutions j, then j fields of 6 bits: position (4 bits, < L-2) | sub << 4
-// (sub = 1..3: the substituted symbol is (c_p + sub) & 3)
+GSX_HD uint32_t ftab_exact_index(uint64_t q, uint32_t L) { return L >= 16 ? (uint32_t)q : (uint32_t)q & ((1u << (2u * L)) - 1u); }
+
+// DFS kernel enumeration: one "combo" per choice of substituted positions among characters 2 .. L-1, times the 16
+// beginnings (characters 0 and 1).
+// combo word: bits 0..2 = number of substitutions j, then j fields of 6 bits: p (4 bits, character p + 2) | sub << 4
+// (sub = 1..3: the substituted symbol is (c + sub) & 3)
 GSX_HD void ftab_apply(uint64_t combo, uint64_t q, uint32_t L, uint32_t gidx, const uint64_t* pow5,
                        uint32_t& idx, uint64_t& key, uint32_t& j) {
     j = (uint32_t)(combo & 7u); idx = gidx; key = 0;
     for (uint32_t t = 0; t < j; t++) {
-        const uint32_t f = (uint32_t)(combo >> (3u + 6u * t)) & 63u, p = f & 15u, sub = f >> 4;
+        const uint32_t f = (uint32_t)(combo >> (3u + 6u * t)) & 63u, p = (f & 15u) + 2u, sub = f >> 4;
         const uint32_t c = (uint32_t)(q >> (2u * p)) & 3u, s2 = (c + sub) & 3u;
-        idx += (uint32_t)((int32_t)(s2 - c) << (2u * (L - 1u - p)));
+        idx += (uint32_t)((int32_t)(s2 - c) << (2u * p));
         key += (uint64_t)(1u + s2) * pow5[L - 1u - p];
     }
 }
-// ending e (0..15) of a combo: symbols of positions L-2 and L-1; returns the extra mismatches and adds their key digits
-GSX_HD uint32_t ftab_ending(uint32_t e, uint64_t q, uint32_t L, uint64_t& key) {
-    const uint32_t sa = e >> 2, sb = e & 3u;
-    const uint32_t ca = (uint32_t)(q >> (2u * (L - 2u))) & 3u, cb = (uint32_t)(q >> (2u * (L - 1u))) & 3u;
+// beginning e (0..15) of a combo: e & 3 = symbol of character 0, e >> 2 = symbol of character 1; returns the extra
+// mismatches and adds their key digits
+GSX_HD uint32_t ftab_beginning(uint32_t e, uint64_t q, uint32_t L, const uint64_t* pow5, uint64_t& key) {
+    const uint32_t s0 = e & 3u, s1 = e >> 2;
+    const uint32_t c0 = (uint32_t)q & 3u, c1 = (uint32_t)(q >> 2) & 3u;
     uint32_t extra = 0;
-    if (sa != ca) { extra++; key += (uint64_t)(1u + sa) * 5ull; }
-    if (sb != cb) { extra++; key += (uint64_t)(1u + sb); }
+    if (s0 != c0) { extra++; key += (uint64_t)(1u + s0) * pow5[L - 1u]; }
+    if (s1 != c1) { extra++; key += (uint64_t)(1u + s1) * pow5[L - 2u]; }
     return extra;
+}
+
+// narrow string key (base 5, first consumed character most significant) of the L-character pattern with table index idx
+GSX_HD uint64_t ftab_key(uint32_t idx, uint64_t q, uint32_t L) {
+    uint64_t key = 0;
+    for (uint32_t i = 0; i < L; i++) {
+        const uint32_t c = (idx >> (2u * i)) & 3u, g = (uint32_t)(q >> (2u * i)) & 3u;
+        key = key * 5ull + (c == g ? 0u : 1u + c);
+    }
+    return key;
+}
+
+// ---- slice-major enumeration (sweep kernel) ----------------------------------------------------------------------
+// A slice fixes the last `sb` consumed characters of the pattern (the top 2*sb bits of the table index): its table
+// entries and the BWT rows they point to are both contiguous and small enough to stay in L2 while every guide of the
+// batch visits them.  For one guide and one slice with h substitutions inside the slice characters, the patterns are
+// numbered t = 0 .. n-1:  group j = 0 .. B (B = M - h) holds the xor-masks with exactly j substituted characters among
+// characters 2 .. L-sb-1 (`masks`, sorted by j, group j starting at mask_off[j]), each combined with the nb(B - j)
+// beginnings whose own substitutions fit the rest of the budget: nb(0) = 1 (exact), nb(1) = 7 (exact or one of the two
+// characters changed), nb(>=2) = 16.  Substitutions are xor-encoded: symbol' = symbol ^ x, x = 1..3.
+GSX_HD uint32_t sweep_nb(uint32_t b) { return b == 0 ? 1u : (b == 1 ? 7u : 16u); }
+GSX_HD uint32_t sweep_beginning(uint32_t nb, uint32_t i) {            // xor value for characters 0 (bits 0..1) and 1 (bits 2..3)
+    if (nb == 16u) return i;
+    if (nb == 1u) return 0u;
+    return i < 4u ? i : (i - 3u) << 2;                                  // 0,1,2,3,4,8,12
+}
+// substitutions between the guide's slice characters and slice beta
+GSX_HD uint32_t sweep_slice_distance(uint64_t q, uint32_t L, uint32_t sb, uint32_t beta) {
+    const uint32_t top = (uint32_t)(q >> (2u * (L - sb))) & ((1u << (2u * sb)) - 1u);
+    const uint32_t x = top ^ beta;
+    return popc64((uint64_t)((x | (x >> 1)) & 0x55555555u));
+}
+// pattern t of (guide q, slice beta, budget B): table index and total mismatches so far (h + j + extra - h is returned
+// as `used`, the substitutions outside the slice characters)
+GSX_HD uint32_t sweep_pattern(const SweepPlan& pl, const uint32_t* masks, uint64_t q, uint32_t beta, uint32_t B, uint32_t t, uint32_t& used) {
+    uint32_t j = 0;
+    while (j < B && t >= pl.cum[B][j + 1]) j++;
+    const uint32_t r = t - pl.cum[B][j], nb = sweep_nb(B - j);
+    const uint32_t mi = nb == 16u ? (r >> 4) : (nb == 7u ? r / 7u : r), bi = r - mi * nb;
+    const uint32_t ex = sweep_beginning(nb, bi);
+    used = j + ((ex & 3u) ? 1u : 0u) + ((ex >> 2) ? 1u : 0u);
+    const uint32_t low_bits = 2u * (pl.L - pl.sb);
+    const uint32_t low = ((uint32_t)q & ((1u << low_bits) - 1u)) ^ masks[pl.mask_off[j] + mi] ^ ex;
+    return (beta << low_bits) | low;
 }
 
 // ordering of the matches of one guide: bucket (mismatches) ascending, forward index before reverse index, string order

@@ -105,13 +105,14 @@ struct Prepared {
     // fast-path description (search_fast_kernel): valid when fast_ok
     bool fast_ok = false;
     std::vector<uint64_t> gq;      // per guide: 2-bit symbols in consumption order | qlen << 58
-    uint32_t pampack = 0, plen = 0;
+    uint32_t pampack = 0, plen = 0, min_qlen = 0;
 };
 
 // every way to substitute at most M of the first n_pos characters (k-mer jump table enumeration, gsx_core.h)
 std::vector<uint64_t> ftab_combos(uint32_t n_pos, uint32_t M);
-// table index of the guide's first L characters (2-bit codes c_i at bits 2i of q): sum c_i * 4^(L-1-i)
-inline uint32_t ftab_exact_index(uint64_t q, uint32_t L) { uint32_t e = 0; for (uint32_t i = 0; i < L; i++) e = (e << 2) | (uint32_t)((q >> (2 * i)) & 3); return e; }
+// slice-major enumeration plan (gsx_core.h SweepPlan): xor-masks over characters 2 .. L-sb-1 with at most M substitutions,
+// sorted by substitution count, and the cumulative pattern counts per remaining budget
+void sweep_make_plan(uint32_t L, uint32_t sb, uint32_t M, SweepPlan& plan, std::vector<uint32_t>& masks);
 }  // namespace gsx
 
 struct gsx_result {

@@ -5,6 +5,7 @@
 // wt_pc::serialize (wt_pc.hpp:656-671) + SA samples + ISA samples + byte_alphabet.  Field layout verified
 // against real files: SURVEY.md App. B.
 #include "gsx_host.h"
+#include "gsx_core.h"
 #include <algorithm>
 #include <cctype>
 #include <cstdio>
@@ -200,7 +201,42 @@ std::vector<uint64_t> ftab_combos(uint32_t n_pos, uint32_t M) {
         for (uint32_t p = start; p < n_pos; p++) { pos.push_back(p); go(p + 1, n_pos, M, pos, out); pos.pop_back(); }
     } };
     Rec::go(0, n_pos, M, pos, out);
+    // by number of substitutions: the 32 combos a warp handles in one table step then share their remaining budget, and
+    // a step whose combos have none left only looks at the exact ending
+    std::stable_sort(out.begin(), out.end(), [](uint64_t x, uint64_t y) { return (x & 7u) < (y & 7u); });
     return out;
+}
+
+void sweep_make_plan(uint32_t L, uint32_t sb, uint32_t M, SweepPlan& plan, std::vector<uint32_t>& masks) {
+    memset(&plan, 0, sizeof plan);
+    plan.L = L; plan.sb = sb; plan.M = M;
+    const uint32_t lo = 2, hi = L - sb;                     // characters lo .. hi-1 carry the masks
+    masks.clear();
+    std::vector<uint32_t> pos;
+    for (uint32_t j = 0; j <= M; j++) {
+        plan.mask_off[j] = (uint32_t)masks.size();
+        if (j > hi - lo) continue;
+        // all position subsets of size j (increasing), each with 3^j xor values
+        pos.assign(j, 0); for (uint32_t t = 0; t < j; t++) pos[t] = lo + t;
+        for (;;) {
+            uint32_t n_sub = 1; for (uint32_t t = 0; t < j; t++) n_sub *= 3;
+            for (uint32_t code = 0; code < n_sub; code++) {
+                uint32_t m = 0, c = code;
+                for (uint32_t t = 0; t < j; t++) { m |= (1u + c % 3u) << (2u * pos[t]); c /= 3u; }
+                masks.push_back(m);
+            }
+            int t = (int)j - 1;
+            while (t >= 0 && pos[t] == hi - j + t) t--;
+            if (t < 0) break;
+            pos[t]++; for (uint32_t u = t + 1; u < j; u++) pos[u] = pos[u - 1] + 1;
+        }
+    }
+    plan.mask_off[M + 1] = (uint32_t)masks.size();
+    for (uint32_t B = 0; B <= M; B++) {
+        uint32_t acc = 0;
+        for (uint32_t j = 0; j <= B; j++) { plan.cum[B][j] = acc; acc += (plan.mask_off[j + 1] - plan.mask_off[j]) * sweep_nb(B - j); }
+        plan.cum[B][B + 1] = acc;
+    }
 }
 
 // ---- native cache format (<prefix>.gsx): a flat dump of the HBM layout ----------------------------------------

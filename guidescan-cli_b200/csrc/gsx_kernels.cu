@@ -285,7 +285,9 @@ int search_grid_warps(bool wide, int variant, int sm_count) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// k-mer jump table: one backward-search expansion per entry and level (children of entry e are entries 4e .. 4e+3)
+// k-mer jump table: one backward-search expansion per entry and level.  Entry e of level d (e = sum c_i 4^i over the d
+// consumed characters) has the children e + s * 4^d: the last consumed character is the most significant digit, which
+// keeps sp monotone in the index (gsx_core.h)
 // ---------------------------------------------------------------------------------------------------------
 __global__ void ftab_expand_kernel(DevStrand st, const FtabEntry* __restrict__ cur, FtabEntry* __restrict__ nxt, uint32_t n_cur) {
     for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n_cur; e += gridDim.x * blockDim.x) {
@@ -300,10 +302,8 @@ __global__ void ftab_expand_kernel(DevStrand st, const FtabEntry* __restrict__ c
             uint32_t c1[4] = {B1.c0, B1.c1, B1.c2, B1.c3};
             block_occ(st, c1, B1.hi, B1.lo, e1, oe);
         }
-        FtabEntry o[4];
-        for (int s = 0; s < 4; s++) { o[s].sp = st.C[s] + os[s]; o[s].width = oe[s] - os[s]; }
-        reinterpret_cast<uint4*>(nxt)[2 * (size_t)e] = make_uint4(o[0].sp, o[0].width, o[1].sp, o[1].width);
-        reinterpret_cast<uint4*>(nxt)[2 * (size_t)e + 1] = make_uint4(o[2].sp, o[2].width, o[3].sp, o[3].width);
+        for (int s = 0; s < 4; s++)
+            reinterpret_cast<uint2*>(nxt)[(size_t)e + (size_t)s * n_cur] = make_uint2(st.C[s] + os[s], oe[s] - os[s]);
     }
 }
 __global__ void ftab_root_kernel(FtabEntry* t, uint32_t n) { if (threadIdx.x == 0 && blockIdx.x == 0) { t[0].sp = 0; t[0].width = n; } }
@@ -401,6 +401,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) search_fast_kernel(SearchArg
     uint32_t cur_task = 0xFFFFFFFFu, cursor = 0, task_gidx = 0; uint64_t task_q = 0;
     unsigned long long n_nodes = 0, n_lookups = 0, n_spilled = 0;     // accumulated by lane 0 only
     const uint32_t M = a.p.M, plen = a.plen;
+    uint32_t n_seeds = 0;
+    if (a.seeds) { n_seeds = *a.n_seeds; if (n_seeds > a.seed_cap) n_seeds = a.seed_cap; }
     uint32_t iters = 0;
     uint64_t pol_keep, pol_stream;
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
@@ -420,7 +422,23 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) search_fast_kernel(SearchArg
                 __syncwarp();
                 count += take; spill_count -= take;
             }
-            if (count < n_need && cur_task == 0xFFFFFFFFu && tasks_remain) {
+            if (count < n_need && tasks_remain && a.seeds) {
+                // tasks are the level-L nodes the sweep kernel let through, 32 at a time (count < 32 <= CAP - 32: room)
+                uint32_t t = 0;
+                if (lane == 0) t = atomicAdd(a.task_counter, 32u);
+                t = __shfl_sync(FULL, t, 0);
+                if (t >= n_seeds) tasks_remain = false;
+                else {
+                    const uint32_t i = t + lane;
+                    if (i < n_seeds) {
+                        const SeedNode sn = a.seeds[i];
+                        const uint32_t slot = (head + count + lane) & (CAP - 1);
+                        r_sp[slot] = sn.sp; r_ep[slot] = sn.ep; r_tlm[slot] = sn.tlm; r_key[slot] = sn.key;
+                    }
+                    __syncwarp();
+                    count += (n_seeds - t < 32u) ? (n_seeds - t) : 32u;
+                }
+            } else if (count < n_need && cur_task == 0xFFFFFFFFu && tasks_remain) {
                 uint32_t t = 0;
                 if (lane == 0) t = atomicAdd(a.task_counter, 1u);
                 t = __shfl_sync(FULL, t, 0);
@@ -431,9 +449,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) search_fast_kernel(SearchArg
                     if (L && (uint32_t)(tq >> 58) >= L && a.n_combos) {
                         // start the task from the k-mer jump table: exact index of its first L characters
                         cur_task = t; cursor = 0; task_q = tq;
-                        uint32_t e = 0;
-                        for (uint32_t i = 0; i < L; i++) e = (e << 2) | ((uint32_t)(tq >> (2u * i)) & 3u);
-                        task_gidx = e;
+                        task_gidx = ftab_exact_index(tq, L);
                     } else {
                         if (lane == 0) {
                             uint32_t slot = (head + count) & (CAP - 1);
@@ -445,8 +461,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) search_fast_kernel(SearchArg
                 }
             }
             if (count < n_need && cur_task != 0xFFFFFFFFu) {
-                // one table step: lane = one substitution combo over the first L-2 characters = one 128-byte line of
-                // 16 endings; every ending within the remaining budget whose interval is non-empty becomes a level-L node
+                // one table step: lane = one substitution combo over characters 2 .. L-1 = one 128-byte line of 16
+                // beginnings; every beginning within the remaining budget whose interval is non-empty becomes a level-L node
                 const bool s1t = (cur_task & 1u) != 0;
                 const uint32_t L = s1t ? a.st[1].ftab_L : a.st[0].ftab_L;
                 const FtabEntry* tab = reinterpret_cast<const FtabEntry*>(s1t ? a.st[1].ftab : a.st[0].ftab);
@@ -455,16 +471,16 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) search_fast_kernel(SearchArg
                 uint32_t idx = 0, j = 0; uint64_t kbase = 0;
                 if (hasc) ftab_apply(__ldg(a.combos + ci), task_q, L, task_gidx, c_pow5, idx, kbase, j);
                 const uint32_t budget = M - j;                       // combos hold at most M substitutions
-                const uint32_t e0 = (((uint32_t)(task_q >> (2u * (L - 2u))) & 3u) << 2) | ((uint32_t)(task_q >> (2u * (L - 1u))) & 3u);
+                const uint32_t e0 = (uint32_t)task_q & 15u;
                 {
                     const uint32_t lines_mask = __ballot_sync(FULL, hasc);
                     if (lane == 0) n_lookups += __popc(lines_mask);
                 }
 #pragma unroll 1
                 for (uint32_t i = 0; i < 16; i++) {
-                    const uint32_t e = (e0 + i) & 15u;               // the exact ending first: it is valid for every combo
+                    const uint32_t e = (e0 + i) & 15u;               // the exact beginning first: it is valid for every combo
                     uint64_t k2 = kbase;
-                    const uint32_t extra = ftab_ending(e, task_q, L, k2);
+                    const uint32_t extra = ftab_beginning(e, task_q, L, c_pow5, k2);
                     const bool ok = hasc && extra <= budget;
                     FtabEntry t; t.sp = 0; t.width = 0;
                     if (ok) { const uint2 v = __ldg(reinterpret_cast<const uint2*>(tab + ((idx & ~15u) | e))); t.sp = v.x; t.width = v.y; }
@@ -490,6 +506,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) search_fast_kernel(SearchArg
                         __syncwarp();
                         count += np;
                     }
+                    if (!__any_sync(FULL, hasc && budget != 0u)) break;      // no budget left anywhere: only the exact beginning counts
                 }
                 cursor += 32u;
                 if (cursor >= a.n_combos) cur_task = 0xFFFFFFFFu;
@@ -515,7 +532,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) search_fast_kernel(SearchArg
         uint32_t os0 = 0, os1 = 0, os2 = 0, os3 = 0, oe0 = 0, oe1 = 0, oe2 = 0, oe3 = 0;
         bool two = false;
         uint64_t phi[7] = {0, 0, 0, 0, 0, 0, 0}, plo[7] = {0, 0, 0, 0, 0, 0, 0};      // look-ahead planes (LOOK only)
-        bool narrow = false;
+        bool narrow = false; uint32_t vm = 15u;
         const uint32_t lvl = tlm >> 27, mm = (tlm >> 24) & 7u, qlen = (uint32_t)(q >> 58);
         if (has) {
             const OccBlock* blocks = s1 ? a.st[1].blocks : a.st[0].blocks;
@@ -523,21 +540,31 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) search_fast_kernel(SearchArg
             const uint32_t e1 = ep + 1u, bs = sp >> 6, be = e1 >> 6;
             two = be != bs;
             Blk B0, B1;
-            if (LOOK && !two) {
-                // all rows of the interval sit in one block: read its own 128-byte line (OccBlock + as many look-ahead
-                // planes as the remaining levels can use -- same line, so no further DRAM traffic); streaming in L2
+            if (LOOK && be - bs <= 1u) {
+                // all rows of the interval sit in one block or in two adjacent ones: read the block's own 128-byte line
+                // (OccBlock + as many look-ahead planes as the remaining levels can use -- same line, so no further DRAM
+                // traffic) and find the children that can still reach the final level; streaming in L2
                 narrow = true;
-                const unsigned char* line = (s1 ? a.st[1].lines : a.st[0].lines) + ((size_t)bs << 7);
-                B0 = ld_block_hint(line, pol_stream);
+                const unsigned char* lines = s1 ? a.st[1].lines : a.st[0].lines;
                 const uint32_t left = qlen + plen - lvl;
-                if (left > 1) { Blk P = ld_block_hint(line + 32, pol_stream);
-                                phi[1] = ((uint64_t)P.c1 << 32) | P.c0; plo[1] = ((uint64_t)P.c3 << 32) | P.c2; phi[2] = P.hi; plo[2] = P.lo; }
-                if (left > 3) { Blk P = ld_block_hint(line + 64, pol_stream);
-                                phi[3] = ((uint64_t)P.c1 << 32) | P.c0; plo[3] = ((uint64_t)P.c3 << 32) | P.c2; phi[4] = P.hi; plo[4] = P.lo; }
-                if (left > 5) { Blk P = ld_block_hint(line + 96, pol_stream);
-                                phi[5] = ((uint64_t)P.c1 << 32) | P.c0; plo[5] = ((uint64_t)P.c3 << 32) | P.c2; phi[6] = P.hi; plo[6] = P.lo; }
-                phi[0] = B0.hi; plo[0] = B0.lo;
-                B1 = B0;
+                uint32_t r_lo = sp, r_hi = two ? 63u : ep;            // rows of the current part (low 6 bits matter)
+                vm = 0;
+#pragma unroll 1
+                for (uint32_t part = 0; part < (two ? 2u : 1u); part++) {
+                    const unsigned char* line = lines + ((size_t)(bs + part) << 7);
+                    const Blk B = ld_block_hint(line, pol_stream);
+                    if (part == 0) B0 = B;
+                    B1 = B;
+                    if (part == 1) { if ((e1 & 63u) == 0u) break; r_lo = 0; r_hi = ep; }   // ep is the last row of block bs
+                    if (left > 1) { Blk P = ld_block_hint(line + 32, pol_stream);
+                                    phi[1] = ((uint64_t)P.c1 << 32) | P.c0; plo[1] = ((uint64_t)P.c3 << 32) | P.c2; phi[2] = P.hi; plo[2] = P.lo; }
+                    if (left > 3) { Blk P = ld_block_hint(line + 64, pol_stream);
+                                    phi[3] = ((uint64_t)P.c1 << 32) | P.c0; plo[3] = ((uint64_t)P.c3 << 32) | P.c2; phi[4] = P.hi; plo[4] = P.lo; }
+                    if (left > 5) { Blk P = ld_block_hint(line + 96, pol_stream);
+                                    phi[5] = ((uint64_t)P.c1 << 32) | P.c0; plo[5] = ((uint64_t)P.c3 << 32) | P.c2; phi[6] = P.hi; plo[6] = P.lo; }
+                    phi[0] = B.hi; plo[0] = B.lo;
+                    vm |= viable_children(phi, plo, r_lo, r_hi, lvl, qlen, qlen + plen, q, a.pampack, M - mm);
+                }
             } else {
                 // packed blocks: 256 rows per line; the top of the tree is shared by all guides -> keep it in L2
                 const uint64_t pol = (ep - sp >= a.pin_width) ? pol_keep : pol_stream;
@@ -574,7 +601,6 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) search_fast_kernel(SearchArg
         bool v0 = has && w0 && (c == 0u || allow), v1 = has && w1 && (c == 1u || allow);
         bool v2 = has && w2 && (c == 2u || allow), v3 = has && w3 && (c == 3u || allow);
         if (LOOK && narrow) {        // drop children that cannot survive the next (up to) seven characters
-            const uint32_t vm = viable_children(phi, plo, sp, ep, lvl, qlen, qlen + plen, q, a.pampack, M - mm);
             v0 = v0 && (vm & 1u); v1 = v1 && (vm & 2u); v2 = v2 && (vm & 4u); v3 = v3 && (vm & 8u);
         }
         const uint32_t C0 = s1 ? a.st[1].C[0] : a.st[0].C[0], C1 = s1 ? a.st[1].C[1] : a.st[0].C[1];
@@ -682,6 +708,132 @@ int search_fast_grid_warps(int variant, int sm_count) {
     GSX_FAST_VARIANTS(X)
 #undef X
     return -1;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// search, slice-major front end (large batches on the fast path).  The random-access cost of the search is dominated by
+// two kinds of reads per (guide, strand): ~6.6 k jump-table lines and ~10.7 k level-L look-ahead lines (3.1 Gb, m = 3),
+// uniformly scattered over 2 GB + 6 GB per strand -- every one a DRAM line fetch and a TLB miss.  Across a batch of
+// 50 k guides each of those lines is wanted by 10-20 different guides.  The sweep kernel therefore turns the loops
+// inside out: the grid walks the index slice by slice (a slice = all patterns sharing their last `sb` consumed
+// characters = a contiguous range of table entries AND of BWT rows, ~32 MB, L2-resident), and inside a slice it visits
+// every guide of the batch, enumerates that guide's patterns that fall into the slice (gsx_core.h sweep_pattern), reads
+// their table entries and look-ahead lines from L2, and keeps the level-L nodes with a row that can still reach the
+// final level (node_viable).  Survivors (~1 %) go to a queue; search_fast_kernel continues from them (a.seeds).
+// Work unit = (strand, slice, block of 32 guides), handed out slice-major through one counter, so that all warps work
+// on the same one or two slices at any time.  Inside a unit the 32 guides' pattern lists are flattened over the lanes.
+// ---------------------------------------------------------------------------------------------------------
+struct DevSectorLoader {
+    const unsigned char* lines;
+    __device__ __forceinline__ void operator()(uint32_t block, uint32_t k, uint64_t w[4]) const {
+        const Blk b = ld_block(reinterpret_cast<const OccBlock*>(lines + ((size_t)block << 7) + (k << 5)));      // LDG.E.256
+        w[0] = ((uint64_t)b.c1 << 32) | b.c0; w[1] = ((uint64_t)b.c3 << 32) | b.c2; w[2] = b.hi; w[3] = b.lo;
+    }
+};
+
+template <int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) sweep_kernel(SweepArgs a) {
+    __shared__ SweepPlan s_plan;
+    for (int i = threadIdx.x; i < (int)(sizeof(SweepPlan) / 4); i += blockDim.x)
+        reinterpret_cast<uint32_t*>(&s_plan)[i] = reinterpret_cast<const uint32_t*>(&a.plan)[i];
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31u, FULL = 0xffffffffu, lt_mask = (1u << lane) - 1u;
+    const uint32_t L = s_plan.L, sb = s_plan.sb, M = a.M;
+    const uint32_t n_slices = 1u << (2u * sb), n_gb = (a.n_guides + 31u) >> 5;
+    const uint64_t items_per_strand = (uint64_t)n_slices * n_gb, n_items = 2ull * items_per_strand;
+    unsigned long long n_nodes = 0, n_lookups = 0, n_patterns = 0, n_sectors = 0, n_seeds = 0;
+    for (;;) {
+        uint32_t item = 0;
+        if (lane == 0) item = atomicAdd(a.item_counter, 1u);
+        item = __shfl_sync(FULL, item, 0);
+        if ((uint64_t)item >= n_items) break;
+        const uint32_t strand = (uint64_t)item >= items_per_strand ? 1u : 0u;
+        const uint32_t rem = item - (strand ? (uint32_t)items_per_strand : 0u);
+        const uint32_t beta = rem / n_gb, gb = rem - beta * n_gb;
+        const uint32_t g = gb * 32u + lane;
+        const bool valid = g < a.n_guides && !(a.skip && a.skip[g]);
+        const uint64_t q = valid ? __ldg(a.gq + g) : 0ull;
+        const uint32_t h = sweep_slice_distance(q, L, sb, beta);
+        const int B = (valid && h <= M) ? (int)(M - h) : -1;
+        const uint32_t n_pat = B >= 0 ? s_plan.cum[B][B + 1] : 0u;
+        uint32_t incl = n_pat;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(FULL, incl, o); if (lane >= (uint32_t)o) incl += y; }
+        const uint32_t excl = incl - n_pat, T = __shfl_sync(FULL, incl, 31);
+        const FtabEntry* tab = reinterpret_cast<const FtabEntry*>(strand ? a.st[1].ftab : a.st[0].ftab);
+        DevSectorLoader ld; ld.lines = strand ? a.st[1].lines : a.st[0].lines;
+        for (uint32_t base = 0; base < T; base += 32u) {
+            const uint32_t it = base + lane;
+            const bool active = it < T;
+            uint32_t o = 0;                                   // owner = largest lane whose first pattern is <= it
+#pragma unroll
+            for (uint32_t step = 16u; step; step >>= 1) {
+                const uint32_t cand = o + step;
+                const uint32_t v = __shfl_sync(FULL, excl, cand & 31u);
+                if (cand < 32u && v <= it) o = cand;
+            }
+            const uint64_t oq = __shfl_sync(FULL, q, o);
+            const int oB = __shfl_sync(FULL, B, o);
+            const uint32_t oexcl = __shfl_sync(FULL, excl, o);
+            bool emit = false; uint32_t sp = 0, ep = 0, idx = 0, mm = 0;
+            if (active) {
+                uint32_t used;
+                idx = sweep_pattern(s_plan, a.masks, oq, beta, (uint32_t)oB, it - oexcl, used);
+                mm = M - (uint32_t)oB + used;
+                const uint2 e = __ldg(reinterpret_cast<const uint2*>(tab + idx));
+                n_patterns++;
+                if (((idx ^ (uint32_t)oq) & 15u) == 0u) n_lookups++;         // one table line per 16 beginnings
+                if (e.y) {
+                    sp = e.x; ep = e.x + e.y - 1u;
+                    uint32_t sectors = 0;
+                    const uint32_t qlen = (uint32_t)(oq >> 58);
+                    emit = node_viable(ld, sp, ep, L, qlen, qlen + a.plen, oq, a.pampack, M - mm, sectors);
+                    n_nodes++; n_sectors += sectors;
+                    n_lookups += ((ep + 1u) >> 6) != (sp >> 6) ? 2u : 1u;
+                }
+            }
+            const uint32_t emask = __ballot_sync(FULL, emit);
+            if (emask) {
+                uint32_t qbase = 0; const int leader = __ffs(emask) - 1;
+                if ((int)lane == leader) qbase = atomicAdd(a.queue_count, (uint32_t)__popc(emask));
+                qbase = __shfl_sync(FULL, qbase, leader);
+                if (emit) {
+                    const uint32_t slot = qbase + __popc(emask & lt_mask);
+                    if (slot < a.queue_cap) {
+                        SeedNode sn; sn.sp = sp; sn.ep = ep; sn.key = ftab_key(idx, oq, L);
+                        sn.tlm = (((gb * 32u + o) << 1) | strand) | (mm << 24) | (L << 27); sn.pad = 0;
+                        a.queue[slot] = sn;
+                        n_seeds++;
+                    } else atomicOr(a.error_flag, GSX_KERR_QUEUE_OVERFLOW);
+                }
+            }
+        }
+    }
+    for (int o = 16; o; o >>= 1) {
+        n_nodes += __shfl_xor_sync(FULL, n_nodes, o); n_lookups += __shfl_xor_sync(FULL, n_lookups, o);
+        n_patterns += __shfl_xor_sync(FULL, n_patterns, o); n_sectors += __shfl_xor_sync(FULL, n_sectors, o);
+        n_seeds += __shfl_xor_sync(FULL, n_seeds, o);
+    }
+    if (lane == 0) {
+        atomicAdd(a.stats + 0, n_nodes); atomicAdd(a.stats + 1, n_lookups); atomicAdd(a.stats + 4, n_patterns);
+        atomicAdd(a.stats + 5, n_sectors); atomicAdd(a.stats + 6, n_seeds);
+    }
+}
+
+template <int WARPS, int MINB>
+static cudaError_t launch_sweep_t(const SweepArgs& a, int sm_count, cudaStream_t s) {
+    sweep_kernel<WARPS, MINB><<<sm_count * MINB, WARPS * 32, 0, s>>>(a);
+    return cudaGetLastError();
+}
+cudaError_t launch_sweep(const SweepArgs& a, int variant, int sm_count, cudaStream_t s) {
+    switch (variant) {
+    case 0: return launch_sweep_t<8, 3>(a, sm_count, s);      // 768 thr/SM
+    case 1: return launch_sweep_t<8, 2>(a, sm_count, s);      // 512 thr/SM
+    case 2: return launch_sweep_t<8, 4>(a, sm_count, s);      // 1024 thr/SM
+    case 3: return launch_sweep_t<8, 6>(a, sm_count, s);      // 1536 thr/SM
+    case 4: return launch_sweep_t<8, 8>(a, sm_count, s);      // 2048 thr/SM
+    }
+    return cudaErrorInvalidValue;
 }
 
 // ---------------------------------------------------------------------------------------------------------

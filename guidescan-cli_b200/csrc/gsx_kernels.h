@@ -9,8 +9,12 @@ namespace gsx {
 enum : uint32_t {
     GSX_KERR_MATCH_OVERFLOW = 1,   // match arena too small: host retries with a larger one
     GSX_KERR_SPILL_OVERFLOW = 2,   // a warp's global spill stack is full: host retries with a larger one
-    GSX_KERR_WATCHDOG = 4          // iteration cap hit (never expected)
+    GSX_KERR_WATCHDOG = 4,         // iteration cap hit (never expected)
+    GSX_KERR_QUEUE_OVERFLOW = 8    // seed queue of the sweep kernel too small: host retries with a larger one
 };
+
+// level-L node that survived the sweep kernel's filter: the DFS kernel continues from it
+struct alignas(8) SeedNode { uint32_t sp, ep; uint64_t key; uint32_t tlm, pad; };
 
 struct SearchArgs {
     DevStrand st[2];
@@ -33,8 +37,25 @@ struct SearchArgs {
     uint32_t pampack;                  // 3 bits per PAM character in consumption order (4 = N wildcard, 5 = never matches)
     uint32_t plen;
     uint32_t pin_width;                // packed-block loads of intervals at least this wide ask L2 to keep the line (evict_last)
-    const uint64_t* combos;            // k-mer jump table enumeration: substitution combos over the first ftab_L - 2 characters
+    const uint64_t* combos;            // k-mer jump table enumeration: substitution combos over characters 2 .. ftab_L - 1
     uint32_t n_combos;
+    const SeedNode* seeds;             // if set: the tasks are these level-L nodes (written by sweep_kernel), not (guide, strand) roots
+    const uint32_t* n_seeds;           // device word: number of seeds written (may exceed seed_cap if the queue overflowed)
+    uint32_t seed_cap;
+};
+
+struct SweepArgs {
+    DevStrand st[2];
+    const uint64_t* gq;                // as SearchArgs::gq
+    const uint8_t* skip;
+    uint32_t n_guides;
+    SweepPlan plan;
+    const uint32_t* masks;
+    uint32_t M, plen, pampack;
+    uint32_t counting;                 // unused by the filter itself; kept for symmetry
+    SeedNode* queue; uint32_t queue_cap;
+    uint32_t* queue_count; uint32_t* item_counter; uint32_t* error_flag;
+    unsigned long long* stats;         // [0] nodes [1] lookups [4] patterns [5] sectors [6] seeds
 };
 
 struct LocateArgs {
@@ -70,6 +91,7 @@ int search_grid_warps(bool wide, int variant, int sm_count);
 cudaError_t launch_search(const SearchArgs& a, bool wide, int variant, int sm_count, cudaStream_t s, int* warps_total);
 int search_fast_grid_warps(int variant, int sm_count);
 cudaError_t launch_search_fast(const SearchArgs& a, int variant, int sm_count, cudaStream_t s);
+cudaError_t launch_sweep(const SweepArgs& a, int variant, int sm_count, cudaStream_t s);
 cudaError_t launch_scan(const uint32_t* in, uint32_t* out, uint32_t n, cudaStream_t s);
 cudaError_t launch_scatter(const MatchRec* m, uint32_t n, const uint32_t* moff, uint32_t* cursor, uint32_t* by_guide, cudaStream_t s);
 cudaError_t launch_order(const MatchRec* m, const uint32_t* moff, const uint32_t* by_guide, uint32_t n_guides, uint32_t n_dist,

@@ -102,6 +102,13 @@ struct alignas(8) MatchRec {
 
 struct Chrom { uint64_t start; uint64_t length; };
 
+// slice-major enumeration plan of the sweep kernel (gsx_core.h)
+struct SweepPlan {
+    uint32_t L, sb, M;
+    uint32_t mask_off[kMaxDist + 2];                // start of group j in `masks`; mask_off[M + 1] = total
+    uint32_t cum[kMaxDist + 1][kMaxDist + 2];       // cum[B][j] = patterns of groups < j under budget B; cum[B][B + 1] = n(B)
+};
+
 // node meta word
 constexpr uint32_t META_LVL_MASK = 63u;           // bits 0..5   guide positions + PAM characters consumed
 constexpr uint32_t META_MM_SHIFT = 6;             // bits 6..8

@@ -99,6 +99,8 @@ typedef struct {
     double   ms_search, ms_arrange, ms_locate, ms_score, ms_total_device;   /* CUDA-event times, max over devices */
     double   ms_h2d, ms_d2h;
     uint64_t launches;         /* kernels launched by this library for the call (all devices) */
+    double   ms_sweep;         /* part of ms_search spent in the slice-major front end (0 if it did not run) */
+    uint64_t seeds;            /* level-L nodes the front end handed to the tree search */
 } gsx_counters;
 
 /* ---- index ------------------------------------------------------------------------------------------- */

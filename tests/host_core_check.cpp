@@ -127,11 +127,18 @@ static void dfs(const DevStrand st[2], const Prepared& prep, uint32_t task, uint
         block_occ(s, b0.cnt, b0.hi, b0.lo, nd.sp, os);
         block_occ(s, b1.cnt, b1.hi, b1.lo, nd.ep + 1, oe);
         uint32_t vmask = 15;
-        if (g_prune && !WIDE && (nd.sp >> 6) == ((nd.ep + 1) >> 6)) {       // the pruning step of search_fast_kernel
+        if (g_prune && !WIDE && ((nd.ep + 1) >> 6) - (nd.sp >> 6) <= 1u) {       // the pruning step of search_fast_kernel
             const std::vector<uint64_t>& lk = g_look[task & 1];
-            uint64_t hi[7], lo[7]; hi[0] = b0.hi; lo[0] = b0.lo;
-            for (int j = 1; j <= 6; j++) { hi[j] = lk[(size_t)(nd.sp >> 6) * 12 + 2 * (j - 1)]; lo[j] = lk[(size_t)(nd.sp >> 6) * 12 + 2 * (j - 1) + 1]; }
-            vmask = viable_children(hi, lo, nd.sp, nd.ep, meta_lvl(nd.meta), g.qlen, g.qlen + prep.plen, prep.gq[task >> 1], prep.pampack, M - meta_mm(nd.meta));
+            const uint32_t bs = nd.sp >> 6, e1 = nd.ep + 1, be = e1 >> 6;
+            vmask = 0;
+            for (uint32_t part = 0; part < (be != bs ? 2u : 1u); part++) {
+                if (part == 1 && (e1 & 63u) == 0) break;
+                const uint32_t b = bs + part;
+                const uint32_t r_lo = part ? 0u : nd.sp, r_hi = part ? nd.ep : (be != bs ? 63u : nd.ep);
+                uint64_t hi[7], lo[7]; hi[0] = s.blocks[b].hi; lo[0] = s.blocks[b].lo;
+                for (int j = 1; j <= 6; j++) { hi[j] = lk[(size_t)b * 12 + 2 * (j - 1)]; lo[j] = lk[(size_t)b * 12 + 2 * (j - 1) + 1]; }
+                vmask |= viable_children(hi, lo, r_lo, r_hi, meta_lvl(nd.meta), g.qlen, g.qlen + prep.plen, prep.gq[task >> 1], prep.pampack, M - meta_mm(nd.meta));
+            }
         }
         for (int cand = 0; cand < CAND_END; cand++) {
             if (!WIDE && cand > CAND_FORK) break;
