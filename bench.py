@@ -200,7 +200,11 @@ def run_gsx(args):
         # items: "f<k>" = specialised kernel variant k, "g<k>" = general kernel variant k
         for item in args.sweep_variants.split(","):
             name, _, pin = item.partition("@")          # "f1@64": specialised kernel variant 1 with a 64 MB L2 residency budget
-            env = {"GSX_FORCE_GENERAL": "1", "GSX_SEARCH_VARIANT": name[1:]} if name[0] == "g" else {"GSX_FORCE_GENERAL": "0", "GSX_FAST_VARIANT": name[1:]}
+            if name[0] == "s":                          # "s5v2": slice-major front end, 5 slice characters, sweep kernel variant 2; "s0": off
+                sb, _, var = name[1:].partition("v")
+                env = {"GSX_FORCE_GENERAL": "0", "GSX_SWEEP": "0" if sb == "0" else "1", "GSX_SWEEP_SB": sb, "GSX_SWEEP_VARIANT": var or "0"}
+            else:
+                env = {"GSX_FORCE_GENERAL": "1", "GSX_SEARCH_VARIANT": name[1:]} if name[0] == "g" else {"GSX_FORCE_GENERAL": "0", "GSX_FAST_VARIANT": name[1:]}
             if pin:
                 env["GSX_L2_PIN_MB"] = pin
             else:
@@ -211,8 +215,9 @@ def run_gsx(args):
                 r = ix.enumerate_raw(steps[0][0], per, params); c = r.counters(); r.close()
                 best = c if best is None or c["ms_search"] < best["ms_search"] else best
             log(json.dumps({"variant": item, "ms_search": best["ms_search"], "guides_per_s_search": per / best["ms_search"] * 1e3,
-                            "glookups_per_s": best["lookups"] / best["ms_search"] / 1e6, "spills": best["spills"], "nodes": best["nodes"]}))
-        for k in ("GSX_FORCE_GENERAL", "GSX_SEARCH_VARIANT", "GSX_FAST_VARIANT", "GSX_L2_PIN_MB"):
+                            "glookups_per_s": best["lookups"] / best["ms_search"] / 1e6, "spills": best["spills"], "nodes": best["nodes"],
+                            "ms_sweep": best["ms_sweep"], "seeds": best["seeds"], "lookups": best["lookups"]}))
+        for k in ("GSX_FORCE_GENERAL", "GSX_SEARCH_VARIANT", "GSX_FAST_VARIANT", "GSX_L2_PIN_MB", "GSX_SWEEP", "GSX_SWEEP_SB", "GSX_SWEEP_VARIANT"):
             os.environ.pop(k, None)
         apply_variant(args)
     for s in range(args.warmup):
@@ -266,13 +271,14 @@ def run_gsx(args):
             "gpu_launches": int(ctr_tot["launches"]),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": tr["dram_bytes_per_launch"] if tr else None,
                          "traffic_source": tr["source"] if tr else None,
-                         "kernel": "search_fast_kernel" if not os.environ.get("GSX_FORCE_GENERAL", "0") == "1" else "search_kernel", "peak_source": peak_src,
+                         "kernel": ("sweep_kernel + search_fast_kernel" if ctr_tot["seeds"] else "search_fast_kernel") if not os.environ.get("GSX_FORCE_GENERAL", "0") == "1" else "search_kernel", "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes_per_launch, "lookups_per_guide": lookups / total_guides,
                          "nodes_per_guide": nodes / total_guides, "launch_ms": launch_ms,
                          "random_sector_peak_gbs": rg["gb_per_s"] if rg else None,
                          "frac_of_random_sector_peak": (achieved / rg["gb_per_s"]) if rg else None},
             "counters": {"hits_per_guide": hits / total_guides, "spills": ctr_tot["spills"], "lf_steps": ctr_tot["lf_steps"],
-                         "ms_search": ctr_tot["ms_search"] / args.steps, "ms_arrange": ctr_tot["ms_arrange"] / args.steps,
+                         "ms_search": ctr_tot["ms_search"] / args.steps, "ms_sweep": ctr_tot["ms_sweep"] / args.steps,
+                         "seeds_per_guide": ctr_tot["seeds"] / (per * args.steps), "ms_arrange": ctr_tot["ms_arrange"] / args.steps,
                          "ms_locate": ctr_tot["ms_locate"] / args.steps, "ms_score": ctr_tot["ms_score"] / args.steps,
                          "ms_d2h": ctr_tot["ms_d2h"] / args.steps},
             "clocks": clocks,

@@ -332,18 +332,26 @@ int gsx_prepare_guides(const gsx_guide* guides, size_t n, const gsx_params* p, g
     out.recs.resize(n);
     size_t max_total = 0;
     const bool bulges = p->rna_bulges || p->dna_bulges;
+    uint8_t sym_tab[256], csym_tab[256];                          // symbol code of a character / of its complement
+    for (int c = 0; c < 256; c++) { sym_tab[c] = sym_of((char)c); csym_tab[c] = sym_of(complement_char((char)c)); }
+    const char* last_pam = nullptr; int last_set = -1; size_t last_mp = 0;
     for (size_t i = 0; i < n; i++) {
         const char* seq = guides[i].seq ? guides[i].seq : "";
         const char* pam = guides[i].pam ? guides[i].pam : "";
-        size_t sl = strlen(seq), pl = strlen(pam);
+        size_t sl = strlen(seq);
         if (sl == 0 || sl > (size_t)kMaxQ) return fail(GSX_ERR_ARG, "guide sequence length must be 1..32");
-        if (pl > (size_t)kMaxPamLen) return fail(GSX_ERR_ARG, "PAM longer than 8");
         GuideRec& r = out.recs[i];
         memset(&r, 0, sizeof r);
         r.qlen = (uint8_t)sl; r.seqlen = (uint8_t)sl;
         memcpy(r.seq, seq, sl);
-        for (size_t l = 0; l < sl; l++)       // consumption order: process.hpp:63, index.hpp:214
-            r.q[l] = p->start ? sym_of(seq[sl - 1 - l]) : sym_of(complement_char(seq[l]));
+        if (p->start) for (size_t l = 0; l < sl; l++) r.q[l] = sym_tab[(unsigned char)seq[sl - 1 - l]];
+        else for (size_t l = 0; l < sl; l++) r.q[l] = csym_tab[(unsigned char)seq[l]];       // consumption order: process.hpp:63, index.hpp:214
+        if (last_pam && (pam == last_pam || strcmp(pam, last_pam) == 0)) {                       // same PAM column value as the previous guide
+            r.pamset = (uint8_t)last_set; max_total = std::max(max_total, sl + last_mp);
+            continue;
+        }
+        size_t pl = strlen(pam);
+        if (pl > (size_t)kMaxPamLen) return fail(GSX_ERR_ARG, "PAM longer than 8");
         auto it = set_of.find(pam);
         if (it == set_of.end()) {
             if (set_of.size() >= (size_t)kMaxPamSets) return fail(GSX_ERR_ARG, "more than 16 distinct PAM column values in one call");
@@ -368,6 +376,7 @@ int gsx_prepare_guides(const gsx_guide* guides, size_t n, const gsx_params* p, g
         size_t mp = 0; const PamSet& ps = out.pamsets[r.pamset];
         for (int k = 0; k < ps.n_pams; k++) mp = std::max<size_t>(mp, ps.plen[k]);
         max_total = std::max(max_total, sl + mp);
+        last_pam = pam; last_set = it->second; last_mp = mp;
     }
     out.wide = bulges || max_total > 27;
     if (max_total + p->dna_bulges > 32) return fail(GSX_ERR_ARG, "guide + PAM + DNA bulges longer than 32 characters");
@@ -456,7 +465,7 @@ static void run_device_job(DeviceJob* job) {
                          n >= (uint32_t)env_int("GSX_SWEEP_MIN", 8192) && prep.min_qlen >= ftab_L && p.mismatches <= 4 && p.threshold <= 4;
         if (use_sweep) {
             const double per_strand = 8.0 * std::pow(4.0, (double)ftab_L) + (double)(di.st[0].d.n / 64 + 1) * 128.0;
-            const double target = (double)env_int("GSX_SWEEP_SLICE_MB", 32) * 1e6;
+            const double target = (double)env_int("GSX_SWEEP_SLICE_MB", 12) * 1e6;
             sweep_sb = 1; while (sweep_sb < ftab_L - 3 && per_strand / std::pow(4.0, (double)sweep_sb) > target) sweep_sb++;
             if (env_int("GSX_SWEEP_SB", 0) > 0) sweep_sb = (uint32_t)env_int("GSX_SWEEP_SB", 0);
             if (sweep_sb < 1 || sweep_sb + 3 > ftab_L) use_sweep = false;

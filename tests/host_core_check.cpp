@@ -18,6 +18,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -83,11 +84,62 @@ static void build_ftab_host(const DevStrand& st, uint32_t L, std::vector<FtabEnt
                 const OccBlock& b0 = st.blocks[sp >> 6]; const OccBlock& b1 = st.blocks[e1 >> 6];
                 block_occ(st, b0.cnt, b0.hi, b0.lo, sp, os); block_occ(st, b1.cnt, b1.hi, b1.lo, e1, oe);
             }
-            for (uint32_t s = 0; s < 4; s++) nxt[e * 4 + s] = {st.C[s] + os[s], oe[s] - os[s]};
+            for (uint32_t s = 0; s < 4; s++) nxt[e + s * cur.size()] = {st.C[s] + os[s], oe[s] - os[s]};
         }
         cur.swap(nxt);
     }
     tab.swap(cur);
+}
+
+// slice-major front end (what sweep_kernel does): per task, the level-L nodes that pass node_viable
+static uint32_t g_sweep_sb = 0;
+static std::map<uint32_t, std::vector<std::vector<Node>>> g_seeds_by_M;
+struct HostSectorLoader {
+    const DevStrand* st; const std::vector<uint64_t>* look;
+    void operator()(uint32_t b, uint32_t k, uint64_t w[4]) const {
+        if (k == 0) { const OccBlock& o = st->blocks[b]; w[0] = ((uint64_t)o.cnt[1] << 32) | o.cnt[0]; w[1] = ((uint64_t)o.cnt[3] << 32) | o.cnt[2]; w[2] = o.hi; w[3] = o.lo; }
+        else for (int u = 0; u < 4; u++) w[u] = (*look)[(size_t)b * 12 + 4 * (k - 1) + u];      // hi_(2k-1), lo_(2k-1), hi_2k, lo_2k
+    }
+};
+static void sweep_host(const DevStrand st[2], const Prepared& prep, uint32_t M) {
+    const uint32_t L = g_ftab_L, sb = g_sweep_sb; const size_t n = prep.recs.size();
+    SweepPlan plan; std::vector<uint32_t> masks; sweep_make_plan(L, sb, M, plan, masks);
+    std::vector<std::vector<Node>>& g_seeds = g_seeds_by_M[M]; g_seeds.assign(2 * n, {});
+    static std::vector<uint64_t> combos; combos = ftab_combos(L - 2, M);
+    for (uint32_t strand = 0; strand < 2; strand++) {
+        HostSectorLoader ld{&st[strand], &g_look[strand]};
+        std::vector<std::vector<std::pair<uint32_t, uint32_t>>> seen(n);
+        for (uint32_t beta = 0; beta < (1u << (2 * sb)); beta++)
+            for (size_t g = 0; g < n; g++) {
+                const uint64_t q = prep.gq[g]; const uint32_t qlen = (uint32_t)(q >> 58);
+                if (qlen < L) { fprintf(stderr, "--sweep needs guides of at least L characters\n"); exit(2); }
+                const uint32_t h = sweep_slice_distance(q, L, sb, beta);
+                if (h > M) continue;
+                const uint32_t B = M - h, n_pat = plan.cum[B][B + 1];
+                for (uint32_t t = 0; t < n_pat; t++) {
+                    uint32_t used; const uint32_t idx = sweep_pattern(plan, masks.data(), q, beta, B, t, used);
+                    const uint32_t mm = h + used;
+                    seen[g].push_back({idx, mm});
+                    const FtabEntry& e = g_ftab[strand][idx];
+                    if (!e.width) continue;
+                    uint32_t sectors = 0;
+                    if (!node_viable(ld, e.sp, e.sp + e.width - 1, L, qlen, qlen + prep.plen, q, prep.pampack, M - mm, sectors)) continue;
+                    Node nd{}; nd.sp = e.sp; nd.ep = e.sp + e.width - 1; nd.key_lo = ftab_key(idx, q, L); nd.task = (uint32_t)(2 * g + strand);
+                    nd.meta = meta_make(L, mm, 0, 0, 0, 0, 0);
+                    g_seeds[2 * g + strand].push_back(nd);
+                }
+            }
+        // the slice-major enumeration must visit exactly the patterns (and mismatch counts) of the per-guide enumeration
+        for (size_t g = 0; g < n; g++) {
+            std::vector<std::pair<uint32_t, uint32_t>> want; const uint64_t q = prep.gq[g];
+            for (uint64_t combo : combos) {
+                uint32_t idx, j; uint64_t key; ftab_apply(combo, q, L, ftab_exact_index(q, L), g_pow5, idx, key, j);
+                for (uint32_t e = 0; e < 16; e++) { uint64_t k2 = key; uint32_t extra = ftab_beginning(e, q, L, g_pow5, k2); if (j + extra <= M) want.push_back({(idx & ~15u) | e, j + extra}); }
+            }
+            std::sort(want.begin(), want.end()); std::sort(seen[g].begin(), seen[g].end());
+            if (want != seen[g]) { fprintf(stderr, "sweep enumeration differs from the per-guide enumeration for guide %zu (%zu vs %zu patterns)\n", g, seen[g].size(), want.size()); exit(3); }
+        }
+    }
 }
 
 template <bool WIDE>
@@ -97,7 +149,10 @@ static void dfs(const DevStrand st[2], const Prepared& prep, uint32_t task, uint
     const GuideRec& g = prep.recs[task >> 1];
     ExpandCtx cx{&s, &g, &prep.pamsets[g.pamset], M, R, D};
     std::vector<Node> stack;
-    if (!WIDE && g_ftab_L && g.qlen >= g_ftab_L && prep.fast_ok) {
+    if (!WIDE && g_sweep_sb && prep.fast_ok) {
+        if (!g_seeds_by_M.count(M)) sweep_host(st, prep, M);
+        stack = g_seeds_by_M[M][task];
+    } else if (!WIDE && g_ftab_L && g.qlen >= g_ftab_L && prep.fast_ok) {
         // the table phase of search_fast_kernel: every pattern within the budget of the first L characters
         const uint32_t L = g_ftab_L; const uint64_t q = prep.gq[task >> 1];
         const uint32_t gidx = ftab_exact_index(q, L);
@@ -107,7 +162,7 @@ static void dfs(const DevStrand st[2], const Prepared& prep, uint32_t task, uint
             uint32_t idx, j; uint64_t key;
             ftab_apply(combo, q, L, gidx, g_pow5, idx, key, j);
             for (uint32_t e = 0; e < 16; e++) {
-                uint64_t k2 = key; uint32_t extra = ftab_ending(e, q, L, k2);
+                uint64_t k2 = key; uint32_t extra = ftab_beginning(e, q, L, g_pow5, k2);
                 if (j + extra > M) continue;
                 const FtabEntry& t = g_ftab[task & 1][(idx & ~15u) | e];
                 if (!t.width) continue;
@@ -165,6 +220,7 @@ int main(int argc, char** argv) {
         else if (a == "--start") p.start = 1; else if (a == "--max") p.max_off_targets = atoll(argv[++i]);
         else if (a == "--lookahead") g_prune = true;
         else if (a == "--ftab") g_ftab_L = atoi(argv[++i]);
+        else if (a == "--sweep") g_sweep_sb = atoi(argv[++i]);
         else if (a == "--sam") sam = true; else if (a == "--succinct") complete = false; else if (a == "-a") alts.push_back(argv[++i]);
         else { fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
     }
@@ -193,6 +249,7 @@ int main(int argc, char** argv) {
         g_pow5[0] = 1; for (int i = 1; i < 32; i++) g_pow5[i] = g_pow5[i - 1] * 5ull;
         build_ftab_host(st[0], g_ftab_L, g_ftab[0]); build_ftab_host(st[1], g_ftab_L, g_ftab[1]);
     }
+    if (g_sweep_sb && (!g_prune || !g_ftab_L || !prep.fast_ok || g_sweep_sb + 3 > g_ftab_L)) { fprintf(stderr, "--sweep SB needs --lookahead, --ftab L >= SB + 3 and a fast-path batch\n"); return 2; }
     if (g_prune) {
         if (!prep.fast_ok) { fprintf(stderr, "--lookahead needs a fast-path batch (one PAM, ACGT guides, no bulges)\n"); return 2; }
         build_look(st[0], g_look[0]); build_look(st[1], g_look[1]);

@@ -50,7 +50,9 @@ def test_lookahead_pruning_keeps_output_and_cuts_nodes(harness, tmp_path, m):
     O.ref_index(fa, os.path.join(d, "la"), cwd=d)
     O.Index(fa).enumerate_file(O.make_opts(mismatches=m), gcsv, os.path.join(d, "o.out"), nthreads=4)
     nodes = {}
-    for tag, extra in (("plain", []), ("look", ["--lookahead"]), ("ftab", ["--ftab", "7"]), ("both", ["--lookahead", "--ftab", "8"])):
+    for tag, extra in (("plain", []), ("look", ["--lookahead"]), ("ftab", ["--ftab", "7"]), ("both", ["--lookahead", "--ftab", "8"]),
+                       ("sweep1", ["--lookahead", "--ftab", "8", "--sweep", "1"]), ("sweep3", ["--lookahead", "--ftab", "8", "--sweep", "3"]),
+                       ("sweep5", ["--lookahead", "--ftab", "9", "--sweep", "5"])):
         out = os.path.join(d, tag + ".out")
         r = subprocess.run([harness, os.path.join(d, "la"), gcsv, out, "-m", str(m)] + extra, capture_output=True, text=True, check=True)
         assert open(out, "rb").read() == open(os.path.join(d, "o.out"), "rb").read()
@@ -59,3 +61,5 @@ def test_lookahead_pruning_keeps_output_and_cuts_nodes(harness, tmp_path, m):
     # on a genome this small the pruned walk already dies near the root, so the table need not beat it; it must beat
     # the plain walk, and pruning must help behind the table as well
     assert nodes["ftab"] < nodes["plain"] and nodes["both"] < nodes["ftab"], nodes
+    # the slice-major front end filters level-L nodes before the walk expands them
+    assert nodes["sweep1"] < nodes["both"] and nodes["sweep3"] == nodes["sweep1"], nodes

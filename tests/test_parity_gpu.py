@@ -244,3 +244,48 @@ def test_every_fast_kernel_variant(gsx, seeded_case, monkeypatch, variant):
     out = os.path.join(d, "v.out")
     ix.enumerate_file(gcsv, out, gsx.make_params(mismatches=4))
     assert open(out, "rb").read() == open(want, "rb").read()
+
+
+@pytest.mark.parametrize("kw", [dict(mismatches=3), dict(mismatches=4, max_off_targets=3), dict(mismatches=2, threshold=1),
+                                dict(mismatches=0), dict(mismatches=1, threshold=3), dict(mismatches=3, fmt="sam")])
+@pytest.mark.parametrize("sb", [1, 2, 4, 6])
+def test_slice_major_front_end_agrees_with_oracle(gsx, seeded_case, monkeypatch, kw, sb):
+    """sweep_kernel (slice-major enumeration + look-ahead filter) feeding search_fast_kernel through the seed queue:
+    same text as the oracle for every slice width, fewer expanded nodes than the per-guide table walk"""
+    import oracle as O
+    d, gcsv, ix, oix, layout = seeded_case
+    if layout != "full":
+        pytest.skip("the front end needs the jump table and the look-ahead lines")
+    fmt = kw.get("fmt", "csv")
+    want = os.path.join(d, "o.out")
+    oix.enumerate_file(O.make_opts(**kw), gcsv, want, nthreads=8)
+    want = open(want, "rb").read()
+    p = gsx.make_params(mismatches=kw["mismatches"], threshold=kw.get("threshold", -1), max_off_targets=kw.get("max_off_targets", -1))
+    res = {}
+    for sweep in ("0", "1"):
+        monkeypatch.setenv("GSX_SWEEP", sweep); monkeypatch.setenv("GSX_SWEEP_MIN", "1"); monkeypatch.setenv("GSX_SWEEP_SB", str(sb))
+        out = os.path.join(d, "s%s.out" % sweep)
+        _, ctr = ix.enumerate_file(gcsv, out, p, fmt=fmt)
+        assert open(out, "rb").read() == want
+        res[sweep] = ctr
+    assert res["0"]["seeds"] == 0
+    if "threshold" not in kw:          # (with a threshold every guide may be dropped before the main pass)
+        assert res["1"]["seeds"] > 0
+    assert (res["1"]["matches"], res["1"]["hits"]) == (res["0"]["matches"], res["0"]["hits"])
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
+def test_every_sweep_kernel_variant_and_queue_overflow(gsx, seeded_case, monkeypatch, variant):
+    import oracle as O
+    d, gcsv, ix, oix, layout = seeded_case
+    if layout != "full":
+        pytest.skip("the front end needs the jump table and the look-ahead lines")
+    monkeypatch.setenv("GSX_SWEEP", "1"); monkeypatch.setenv("GSX_SWEEP_MIN", "1"); monkeypatch.setenv("GSX_SWEEP_VARIANT", str(variant))
+    monkeypatch.setenv("GSX_QUEUE_CAP", "64" if variant % 2 else "0")        # 64: forces the grow-and-retry path
+    monkeypatch.setenv("GSX_SPILL_CAP", "64" if variant == 3 else "2048")
+    want = os.path.join(d, "o4.out")
+    oix.enumerate_file(O.make_opts(mismatches=4), gcsv, want, nthreads=8)
+    out = os.path.join(d, "sv.out")
+    _, ctr = ix.enumerate_file(gcsv, out, gsx.make_params(mismatches=4))
+    assert ctr["seeds"] > 0
+    assert open(out, "rb").read() == open(want, "rb").read()
