@@ -488,7 +488,7 @@ static void run_device_job(DeviceJob* job) {
                 w.M = m.p.M; w.plen = m.plen; w.pampack = m.pampack; w.counting = m.p.counting;
                 w.queue = d_queue; w.queue_cap = (uint32_t)queue_cap; w.queue_count = d_ctrs + 3; w.item_counter = d_ctrs + 4;
                 w.error_flag = d_ctrs + 2; w.stats = d_stats;
-                CK(launch_sweep(w, env_int("GSX_SWEEP_VARIANT", 0), di.sm_count, s)); n_launches++;
+                CK(launch_sweep(w, env_int("GSX_SWEEP_VARIANT", 2), di.sm_count, s)); n_launches++;
                 m.seeds = d_queue; m.n_seeds = d_ctrs + 3; m.seed_cap = (uint32_t)queue_cap; m.combos = nullptr; m.n_combos = 0;
             }
             if (ev_mid) CK(cudaEventRecord(ev_mid, s));

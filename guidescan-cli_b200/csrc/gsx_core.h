@@ -398,49 +398,169 @@ GSX_HD uint32_t viable_children(const uint64_t hi[7], const uint64_t lo[7], uint
     return ((alive & ~h0 & ~l0) ? 1u : 0u) | ((alive & ~h0 & l0) ? 2u : 0u) | ((alive & h0 & ~l0) ? 4u : 0u) | ((alive & h0 & l0) ? 8u : 0u);
 }
 
-// Sweep-kernel variant of the same test, sector by sector: can ANY row of [sp, ep] (inside one block or two adjacent
-// ones) still reach the final level?  ld(block, k, w) fetches 32-byte sector k of the block's 128-byte line as four
-// 64-bit words: k = 0 the OccBlock {cnt01, cnt23, hi, lo}, k = 1..3 the planes {hi_(2k-1), lo_(2k-1), hi_2k, lo_2k}.
-// Sectors are fetched only while some row is alive.  Intervals spanning more than two blocks are not examined (true).
-// `sectors` receives the number of sectors fetched.
-template <class LoadSector>
+// Sweep-kernel variant of the same test: can ANY row of [sp, ep] (inside one block or two adjacent ones) still reach the
+// final level?  ld(block, k, w) fetches 32-byte sector k of the block's 128-byte line as four 64-bit words: k = 0 the
+// OccBlock {cnt01, cnt23, hi, lo}, k = 1..3 the planes {hi_(2k-1), lo_(2k-1), hi_2k, lo_2k}.  Sectors are fetched in
+// pairs (0,1) then (2,3) -- two independent loads in flight -- and the second pair only while some row is alive.
+// State: u[r] = rows with at most budget - r mismatches so far (r = 0 .. NB-1, NB > budget), so u[0] = rows still alive;
+// one plane costs one and-or per mask.  Intervals spanning more than two blocks are not examined (true).
+template <int NB, class LoadSector>
 GSX_HD bool node_viable(LoadSector ld, uint32_t sp, uint32_t ep, uint32_t lvl, uint32_t qlen, uint32_t total, uint64_t q,
                         uint32_t pampack, uint32_t budget, uint32_t& sectors) {
     const uint32_t e1 = ep + 1u, bs = sp >> 6, be = e1 >> 6;
     if (be - bs > 1u) return true;
     const uint32_t left = total - lvl;
-    const uint64_t B0 = (budget & 1u) ? ~0ull : 0ull, B1 = (budget & 2u) ? ~0ull : 0ull, B2 = (budget & 4u) ? ~0ull : 0ull;
+    for (uint32_t part = 0; part < 2u; part++) {
+        if (part == 1u && (be == bs || (e1 & 63u) == 0u)) break;
+        const uint32_t r0 = part ? 0u : (sp & 63u), r1 = part ? (ep & 63u) : (be != bs ? 63u : (ep & 63u));
+        const uint64_t rows = (r1 == 63u ? ~0ull : ((1ull << (r1 + 1u)) - 1ull)) & ~((1ull << r0) - 1ull);
+        uint64_t u[NB];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int r = 0; r < NB; r++) u[r] = budget >= (uint32_t)r ? rows : 0ull;
+        for (uint32_t pair = 0; pair < 2u; pair++) {
+            const uint32_t j0 = pair ? 3u : 0u;
+            if (j0 >= left || !u[0]) break;
+            uint64_t wa[4], wb[4] = {0, 0, 0, 0};
+            ld(bs + part, 2u * pair, wa); sectors++;
+            if ((pair ? 5u : 1u) < left) { ld(bs + part, 2u * pair + 1u, wb); sectors++; }
+            // planes of this pair: pair 0 -> t0 (OccBlock), t1, t2 ; pair 1 -> t3, t4, t5, t6
+            const uint64_t ph[4] = {pair ? wa[0] : wa[2], pair ? wa[2] : wb[0], pair ? wb[0] : wb[2], wb[2]};
+            const uint64_t pl[4] = {pair ? wa[1] : wa[3], pair ? wa[3] : wb[1], pair ? wb[1] : wb[3], wb[3]};
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (uint32_t t = 0; t < 4u; t++) {
+                const uint32_t j = j0 + t;
+                if (j >= left || (pair == 0u && t == 3u)) break;
+                const uint32_t Lv = lvl + j;
+                uint32_t sym; const bool proto = Lv < qlen; bool wild = false, kill = false;
+                if (proto) sym = (uint32_t)(q >> (2u * Lv)) & 3u;
+                else { const uint32_t pc = (pampack >> (3u * (Lv - qlen))) & 7u; sym = pc & 3u; wild = pc == 4u; kill = pc > 4u; }
+                const uint64_t eq = ~(ph[t] ^ ((sym & 2u) ? ~0ull : 0ull)) & ~(pl[t] ^ ((sym & 1u) ? ~0ull : 0ull));
+                if (proto) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+                    for (int r = 0; r + 1 < NB; r++) u[r] = (u[r] & eq) | u[r + 1];
+                    u[NB - 1] &= eq;
+                } else if (!wild) {
+                    const uint64_t keep = kill ? 0ull : eq;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+                    for (int r = 0; r < NB; r++) u[r] &= keep;
+                }
+            }
+        }
+        if (u[0]) return true;
+    }
+    return false;
+}
+
+// The same test for a node with no budget left (9 of 10 level-L nodes at m = 3): a row survives a protospacer plane only
+// if its symbol equals the query character, so one mask is enough.
+template <class LoadSector>
+GSX_HD bool node_viable_exact(LoadSector ld, uint32_t sp, uint32_t ep, uint32_t lvl, uint32_t qlen, uint32_t total, uint64_t q,
+                              uint32_t pampack, uint32_t& sectors) {
+    const uint32_t e1 = ep + 1u, bs = sp >> 6, be = e1 >> 6;
+    if (be - bs > 1u) return true;
+    const uint32_t left = total - lvl;
     for (uint32_t part = 0; part < 2u; part++) {
         if (part == 1u && (be == bs || (e1 & 63u) == 0u)) break;
         const uint32_t r0 = part ? 0u : (sp & 63u), r1 = part ? (ep & 63u) : (be != bs ? 63u : (ep & 63u));
         uint64_t alive = (r1 == 63u ? ~0ull : ((1ull << (r1 + 1u)) - 1ull)) & ~((1ull << r0) - 1ull);
-        uint64_t c0 = 0, c1 = 0, c2 = 0;
-        for (uint32_t k = 0; k < 4u && alive; k++) {
-            const uint32_t j0 = k ? 2u * k - 1u : 0u, nj = k ? 2u : 1u;
-            if (j0 >= left) break;
-            uint64_t w[4];
-            ld(bs + part, k, w); sectors++;
-            for (uint32_t u = 0; u < nj; u++) {
-                const uint32_t j = j0 + u;
-                if (j >= left) break;
-                const uint64_t hi = k ? w[2u * u] : w[2], lo = k ? w[2u * u + 1u] : w[3];
-                const uint32_t Lv = lvl + j;
-                uint32_t sym; bool proto = Lv < qlen, wild = false, kill = false;
-                if (proto) sym = (uint32_t)(q >> (2u * Lv)) & 3u;
-                else { const uint32_t pc = (pampack >> (3u * (Lv - qlen))) & 7u; sym = pc & 3u; wild = pc == 4u; kill = pc > 4u; }
-                const uint64_t eq = ~(hi ^ ((sym & 2u) ? ~0ull : 0ull)) & ~(lo ^ ((sym & 1u) ? ~0ull : 0ull));
-                if (proto) {
-                    const uint64_t mis = ~eq;
-                    const uint64_t k0 = c0 & mis; c0 ^= mis;
-                    const uint64_t k1 = c1 & k0; c1 ^= k0;
-                    c2 ^= k1;
-                } else if (kill) alive = 0;
-                else if (!wild) alive &= eq;
-            }
-            const uint64_t gt = (c2 & ~B2) | (~(c2 ^ B2) & ((c1 & ~B1) | (~(c1 ^ B1) & (c0 & ~B0))));
-            alive &= ~gt;
+        uint64_t wa[4], wb[4] = {0, 0, 0, 0};
+#define GSX_EXACT_PLANE(J, HI, LO)                                                                                     \
+        if ((J) < left) {                                                                                             \
+            const uint32_t Lv = lvl + (J);                                                                            \
+            uint32_t pc = Lv < qlen ? ((uint32_t)(q >> (2u * Lv)) & 3u) : ((pampack >> (3u * (Lv - qlen))) & 7u);       \
+            if (pc < 4u) alive &= ~((HI) ^ ((pc & 2u) ? ~0ull : 0ull)) & ~((LO) ^ ((pc & 1u) ? ~0ull : 0ull));         \
+            else if (pc > 4u) alive = 0;                                                                              \
         }
+        ld(bs + part, 0u, wa); sectors++;
+        if (1u < left) { ld(bs + part, 1u, wb); sectors++; }
+        GSX_EXACT_PLANE(0u, wa[2], wa[3]) GSX_EXACT_PLANE(1u, wb[0], wb[1]) GSX_EXACT_PLANE(2u, wb[2], wb[3])
+        if (alive && 3u < left) {
+            ld(bs + part, 2u, wa); sectors++;
+            if (5u < left) { ld(bs + part, 3u, wb); sectors++; }
+            GSX_EXACT_PLANE(3u, wa[0], wa[1]) GSX_EXACT_PLANE(4u, wa[2], wa[3]) GSX_EXACT_PLANE(5u, wb[0], wb[1]) GSX_EXACT_PLANE(6u, wb[2], wb[3])
+        }
+#undef GSX_EXACT_PLANE
         if (alive) return true;
+    }
+    return false;
+}
+
+// ---- the same row filter as a resumable step (sweep kernel, continuation form) ------------------------------------------
+// Lanes of a warp disagree on how far a node has to be examined (second sector pair: 1 node in 6; second block: 1 in 6),
+// so the sweep kernel examines every node for ONE step -- one block, one sector pair -- and parks the nodes that need
+// another step in a per-warp buffer that is drained 32 at a time, all lanes busy.
+//   codes: per guide, 3 bits per plane j = 0..6 of what a row must show at level L + j: 0..3 = that symbol (protospacer:
+//          anything else costs one mismatch; PAM: anything else kills the row), 4 = PAM wildcard, 5 = kills every row,
+//          7 = no such level.
+//   node_step: fetch sector pair `stage` (0: sectors 0,1 = planes t0,t1,t2; 1: sectors 2,3 = planes t3..t6) of `block`
+//          and advance the masks u[r] = rows with at most budget - r mismatches so far.
+GSX_HD uint32_t sweep_codes(uint64_t q, uint32_t L, uint32_t plen, uint32_t pampack) {
+    const uint32_t qlen = (uint32_t)(q >> 58);
+    uint32_t codes = 0;
+    for (uint32_t j = 0; j < 7u; j++) {
+        const uint32_t Lv = L + j;
+        uint32_t c;
+        if (Lv < qlen) c = (uint32_t)(q >> (2u * Lv)) & 3u;
+        else if (Lv < qlen + plen) { c = (pampack >> (3u * (Lv - qlen))) & 7u; if (c > 4u) c = 5u; c |= 8u; }     // bit 3: PAM level
+        else c = 7u;
+        codes |= c << (4u * j);
+    }
+    return codes;
+}
+GSX_HD bool sweep_has_stage1(uint32_t codes) { return ((codes >> 12) & 15u) != 7u; }
+
+template <int NB, class LoadSector>
+GSX_HD void node_step(LoadSector ld, uint32_t block, uint32_t stage, uint32_t codes, uint64_t u[NB], uint32_t& sectors) {
+    uint64_t wa[4], wb[4];
+    ld(block, 2u * stage, wa); ld(block, 2u * stage + 1u, wb); sectors += 2u;
+    const uint64_t ph[4] = {stage ? wa[0] : wa[2], stage ? wa[2] : wb[0], stage ? wb[0] : wb[2], wb[2]};
+    const uint64_t pl[4] = {stage ? wa[1] : wa[3], stage ? wa[3] : wb[1], stage ? wb[1] : wb[3], wb[3]};
+    const uint32_t cs = stage ? (codes >> 12) : ((codes & 0xFFFu) | 0x7000u);             // stage 0 has three planes: the fourth "does not exist"
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (uint32_t t = 0; t < 4u; t++) {
+        const uint32_t c = (cs >> (4u * t)) & 15u;
+        if (c == 7u || c == 12u) continue;                                       // no such level / PAM wildcard
+        const uint32_t sym = c & 3u;
+        uint64_t eq = ~(ph[t] ^ ((sym & 2u) ? ~0ull : 0ull)) & ~(pl[t] ^ ((sym & 1u) ? ~0ull : 0ull));
+        if (c < 4u) {                                                            // protospacer: a differing row loses one unit of budget
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (int r = 0; r + 1 < NB; r++) u[r] = (u[r] & eq) | u[r + 1];
+            u[NB - 1] &= eq;
+        } else {
+            if (c == 13u) eq = 0ull;                                             // PAM character that can never match
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (int r = 0; r < NB; r++) u[r] &= eq;
+        }
+    }
+}
+// whole-node form of the same thing (reference semantics for the tests; the kernel interleaves the steps of many nodes)
+template <int NB, class LoadSector>
+GSX_HD bool node_viable_steps(LoadSector ld, uint32_t sp, uint32_t ep, uint32_t codes, uint32_t budget, uint32_t& sectors) {
+    const uint32_t e1 = ep + 1u, bs = sp >> 6, be = e1 >> 6;
+    if (be - bs > 1u) return true;
+    for (uint32_t part = 0; part < 2u; part++) {
+        if (part == 1u && (be == bs || (e1 & 63u) == 0u)) break;
+        const uint32_t r0 = part ? 0u : (sp & 63u), r1 = part ? (ep & 63u) : (be != bs ? 63u : (ep & 63u));
+        const uint64_t rows = (r1 == 63u ? ~0ull : ((1ull << (r1 + 1u)) - 1ull)) & ~((1ull << r0) - 1ull);
+        uint64_t u[NB];
+        for (int r = 0; r < NB; r++) u[r] = budget >= (uint32_t)r ? rows : 0ull;
+        node_step<NB>(ld, bs + part, 0u, codes, u, sectors);
+        if (u[0] && sweep_has_stage1(codes)) node_step<NB>(ld, bs + part, 1u, codes, u, sectors);
+        if (u[0]) return true;
     }
     return false;
 }
@@ -513,6 +633,14 @@ GSX_HD uint32_t sweep_slice_distance(uint64_t q, uint32_t L, uint32_t sb, uint32
     const uint32_t top = (uint32_t)(q >> (2u * (L - sb))) & ((1u << (2u * sb)) - 1u);
     const uint32_t x = top ^ beta;
     return popc64((uint64_t)((x | (x >> 1)) & 0x55555555u));
+}
+// The patterns of the last group (j = B, exact beginning: nothing of the budget is left afterwards) are enumerated apart
+// from the others, because they are nine tenths of all patterns and need far less arithmetic (node_viable_exact):
+//   zero-budget pattern t = 0 .. mask_off[B+1] - mask_off[B] - 1   -> sweep_pattern_zero
+//   other pattern       t = 0 .. cum[B][B] - 1                      -> sweep_pattern (group j < B)
+GSX_HD uint32_t sweep_pattern_zero(const SweepPlan& pl, const uint32_t* masks, uint64_t q, uint32_t beta, uint32_t B, uint32_t t) {
+    const uint32_t low_bits = 2u * (pl.L - pl.sb);
+    return (beta << low_bits) | (((uint32_t)q & ((1u << low_bits) - 1u)) ^ masks[pl.mask_off[B] + t]);
 }
 // pattern t of (guide q, slice beta, budget B): table index and total mismatches so far (h + j + extra - h is returned
 // as `used`, the substitutions outside the slice characters)

@@ -433,7 +433,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) search_fast_kernel(SearchArg
                     if (i < n_seeds) {
                         const SeedNode sn = a.seeds[i];
                         const uint32_t slot = (head + count + lane) & (CAP - 1);
-                        r_sp[slot] = sn.sp; r_ep[slot] = sn.ep; r_tlm[slot] = sn.tlm; r_key[slot] = sn.key;
+                        r_sp[slot] = sn.sp; r_ep[slot] = sn.ep; r_tlm[slot] = sn.tlm;
+                        r_key[slot] = ftab_key(sn.idx, __ldg(a.gq + ((sn.tlm & 0xFFFFFFu) >> 1)), sn.tlm >> 27);
                     }
                     __syncwarp();
                     count += (n_seeds - t < 32u) ? (n_seeds - t) : 32u;
@@ -731,17 +732,178 @@ struct DevSectorLoader {
     }
 };
 
-template <int WARPS, int MINB>
+struct SweepStats { uint32_t nodes, lookups, patterns, sectors, seeds; };
+
+// per-warp buffer of nodes that need another filter step (gsx_core.h node_step): 64 records in shared memory
+//   idx    table index of the pattern (sp, ep are re-read from the table if the node survives)
+//   blockw block to examine | (ep & 63) << 26 (last row of the node inside its second block)
+//   meta   plane codes (28 bits) | stage << 28 | part << 29 | has-second-block << 30
+//   tlm    task | mismatches << 24 | remaining budget << 27
+//   u[r]   row masks of the filter
+template <int NB>
+struct ContBuf {
+    uint32_t* idx; uint32_t* blockw; uint32_t* meta; uint32_t* tlm; uint64_t* u;      // u[r * 64 + slot]
+    uint32_t count;                                                                    // warp-uniform
+};
+constexpr uint32_t CONT_STAGE = 1u << 28, CONT_PART = 1u << 29, CONT_HASB = 1u << 30;
+
+template <int NB>
+__device__ __forceinline__ void cont_push(ContBuf<NB>& cb, uint32_t lane, bool want, uint32_t idx, uint32_t blockw, uint32_t meta, uint32_t tlm, const uint64_t u[NB]) {
+    const uint32_t m = __ballot_sync(0xffffffffu, want);
+    if (want) {
+        const uint32_t slot = cb.count + __popc(m & ((1u << lane) - 1u));
+        cb.idx[slot] = idx; cb.blockw[slot] = blockw; cb.meta[slot] = meta; cb.tlm[slot] = tlm;
+#pragma unroll
+        for (int r = 0; r < NB; r++) cb.u[r * 64 + slot] = u[r];
+    }
+    cb.count += __popc(m);
+    __syncwarp();
+}
+
+__device__ __forceinline__ void sweep_emit(const SweepArgs& a, uint32_t lane, bool emit, uint32_t sp, uint32_t ep, uint32_t idx, uint32_t tlm, SweepStats& st) {
+    const uint32_t emask = __ballot_sync(0xffffffffu, emit);
+    if (!emask) return;
+    uint32_t qbase = 0; const int leader = __ffs(emask) - 1;
+    if ((int)lane == leader) qbase = atomicAdd(a.queue_count, (uint32_t)__popc(emask));
+    qbase = __shfl_sync(0xffffffffu, qbase, leader);
+    if (emit) {
+        const uint32_t slot = qbase + __popc(emask & ((1u << lane) - 1u));
+        if (slot < a.queue_cap) {
+            SeedNode sn; sn.sp = sp; sn.ep = ep; sn.idx = idx; sn.tlm = (tlm & 0x07FFFFFFu) | (a.plan.L << 27);
+            a.queue[slot] = sn;
+            st.seeds++;
+        } else atomicOr(a.error_flag, GSX_KERR_QUEUE_OVERFLOW);
+    }
+}
+
+// drain up to 32 parked nodes: one more filter step each, all lanes busy
+template <int NB>
+__device__ __forceinline__ void cont_process(const SweepArgs& a, ContBuf<NB>& cb, uint32_t lane, SweepStats& st) {
+    const uint32_t n = cb.count < 32u ? cb.count : 32u;
+    const bool mine = lane < n;
+    uint32_t idx = 0, blockw = 0, meta = 0, tlm = 0; uint64_t u[NB];
+#pragma unroll
+    for (int r = 0; r < NB; r++) u[r] = 0;
+    if (mine) {
+        const uint32_t slot = cb.count - n + lane;
+        idx = cb.idx[slot]; blockw = cb.blockw[slot]; meta = cb.meta[slot]; tlm = cb.tlm[slot];
+#pragma unroll
+        for (int r = 0; r < NB; r++) u[r] = cb.u[r * 64 + slot];
+    }
+    __syncwarp();
+    cb.count -= n;
+    const uint32_t strand = tlm & 1u, codes = meta & 0x0FFFFFFFu, stage = (meta & CONT_STAGE) ? 1u : 0u;
+    DevSectorLoader ld; ld.lines = strand ? a.st[1].lines : a.st[0].lines;
+    uint32_t sectors = 0;
+    if (mine) node_step<NB>(ld, blockw & 0x03FFFFFFu, stage, codes, u, sectors);
+    st.sectors += sectors;
+    const bool alive = mine && u[0] != 0ull;
+    const bool again = alive && stage == 0u && sweep_has_stage1(codes);                  // second sector pair of the same block
+    const bool second = mine && !alive && !(meta & CONT_PART) && (meta & CONT_HASB);     // first block is dead: try the second one
+    const bool emit = alive && !again;
+    uint32_t sp = 0, ep = 0;
+    if (emit) {
+        const FtabEntry* tab = reinterpret_cast<const FtabEntry*>(strand ? a.st[1].ftab : a.st[0].ftab);
+        const uint2 e = __ldg(reinterpret_cast<const uint2*>(tab + idx)); sp = e.x; ep = e.x + e.y - 1u;
+    }
+    sweep_emit(a, lane, emit, sp, ep, idx, tlm, st);
+    if (second) {
+        const uint32_t rB = blockw >> 26, budget = (tlm >> 27) & 7u;
+        const uint64_t rows = rB == 63u ? ~0ull : ((1ull << (rB + 1u)) - 1ull);
+#pragma unroll
+        for (int r = 0; r < NB; r++) u[r] = budget >= (uint32_t)r ? rows : 0ull;
+        blockw = (blockw & 0x03FFFFFFu) + 1u; meta = (meta & ~CONT_STAGE) | CONT_PART;
+    }
+    if (again) meta |= CONT_STAGE;
+    cont_push<NB>(cb, lane, again || second, idx, blockw, meta, tlm, u);
+}
+
+// one flattened pass over the patterns of 32 guides in one slice: lane g owns n_mine patterns of guide (gb * 32 + g);
+// ZERO = the zero-budget group (sweep_pattern_zero, one filter mask), else the groups with budget left
+template <bool ZERO, int NB>
+__device__ __forceinline__ void sweep_pass(const SweepArgs& a, const SweepPlan& pl, ContBuf<NB>& cb, uint32_t lane, uint32_t strand, uint32_t beta, uint32_t gb,
+                                           uint32_t qlow, uint32_t codes, int B, uint32_t n_mine, SweepStats& st) {
+    const uint32_t FULL = 0xffffffffu, M = a.M;
+    const FtabEntry* tab = reinterpret_cast<const FtabEntry*>(strand ? a.st[1].ftab : a.st[0].ftab);
+    DevSectorLoader ld; ld.lines = strand ? a.st[1].lines : a.st[0].lines;
+    uint32_t incl = n_mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(FULL, incl, o); if (lane >= (uint32_t)o) incl += y; }
+    const uint32_t excl = incl - n_mine, T = __shfl_sync(FULL, incl, 31);
+    for (uint32_t base = 0; base < T; base += 32u) {
+        while (cb.count >= 32u) cont_process<NB>(a, cb, lane, st);
+        const uint32_t it = base + lane;
+        const bool active = it < T;
+        uint32_t o = 0;                                   // owner = largest lane whose first pattern is <= it
+#pragma unroll
+        for (uint32_t step = 16u; step; step >>= 1) {
+            const uint32_t cand = o + step;
+            const uint32_t v = __shfl_sync(FULL, excl, cand & 31u);
+            if (cand < 32u && v <= it) o = cand;
+        }
+        const uint32_t oq = __shfl_sync(FULL, qlow, o), ocodes = __shfl_sync(FULL, codes, o), oexcl = __shfl_sync(FULL, excl, o);
+        const int oB = __shfl_sync(FULL, B, o);
+        bool emit = false, park = false; uint32_t sp = 0, ep = 0, idx = 0, mm = M, blockw = 0, meta = 0;
+        uint64_t u[NB];
+#pragma unroll
+        for (int r = 0; r < NB; r++) u[r] = 0;
+        if (active) {
+            if (ZERO) idx = sweep_pattern_zero(pl, a.masks, (uint64_t)oq, beta, (uint32_t)oB, it - oexcl);
+            else { uint32_t used; idx = sweep_pattern(pl, a.masks, (uint64_t)oq, beta, (uint32_t)oB, it - oexcl, used); mm = M - (uint32_t)oB + used; }
+            const uint2 e = __ldg(reinterpret_cast<const uint2*>(tab + idx));
+            st.patterns++;
+            if (((idx ^ oq) & 15u) == 0u) st.lookups++;                       // one table line per 16 beginnings
+            if (e.y) {
+                sp = e.x; ep = e.x + e.y - 1u;
+                const uint32_t e1 = ep + 1u, bs = sp >> 6, be = e1 >> 6;
+                st.nodes++; st.lookups += be != bs ? 2u : 1u;
+                if (be - bs > 1u) emit = true;                                // too wide for the filter: the tree search takes it as is
+                else {
+                    const uint32_t r0 = sp & 63u, r1 = be != bs ? 63u : (ep & 63u);
+                    const uint64_t rows = (r1 == 63u ? ~0ull : ((1ull << (r1 + 1u)) - 1ull)) & ~((1ull << r0) - 1ull);
+                    const bool hasB = be != bs && (e1 & 63u) != 0u;
+                    uint32_t sectors = 0;
+                    if (ZERO) { uint64_t v[1] = {rows}; node_step<1>(ld, bs, 0u, ocodes, v, sectors); u[0] = v[0]; }
+                    else {
+#pragma unroll
+                        for (int r = 0; r < NB; r++) u[r] = (M - mm) >= (uint32_t)r ? rows : 0ull;
+                        node_step<NB>(ld, bs, 0u, ocodes, u, sectors);
+                    }
+                    st.sectors += sectors;
+                    blockw = bs | ((ep & 63u) << 26); meta = ocodes | (hasB ? CONT_HASB : 0u);
+                    if (u[0]) { if (sweep_has_stage1(ocodes)) { park = true; meta |= CONT_STAGE; } else emit = true; }
+                    else if (hasB) {                                          // nothing left in the first block: park the second one
+                        const uint32_t rB = ep & 63u;
+                        const uint64_t rowsB = rB == 63u ? ~0ull : ((1ull << (rB + 1u)) - 1ull);
+#pragma unroll
+                        for (int r = 0; r < NB; r++) u[r] = (M - mm) >= (uint32_t)r ? rowsB : 0ull;
+                        park = true; blockw += 1u; meta |= CONT_PART;
+                    }
+                }
+            }
+        }
+        const uint32_t tlm = (((gb * 32u + o) << 1) | strand) | (mm << 24) | ((M - mm) << 27);
+        sweep_emit(a, lane, emit, sp, ep, idx, tlm, st);
+        cont_push<NB>(cb, lane, park, idx, blockw, meta, tlm, u);
+    }
+}
+
+template <int WARPS, int MINB, int NB>
 __global__ void __launch_bounds__(WARPS * 32, MINB) sweep_kernel(SweepArgs a) {
     __shared__ SweepPlan s_plan;
+    __shared__ uint32_t s_c32[WARPS][4][64];
+    __shared__ uint64_t s_cu[WARPS][NB][64];
     for (int i = threadIdx.x; i < (int)(sizeof(SweepPlan) / 4); i += blockDim.x)
         reinterpret_cast<uint32_t*>(&s_plan)[i] = reinterpret_cast<const uint32_t*>(&a.plan)[i];
     __syncthreads();
-    const uint32_t lane = threadIdx.x & 31u, FULL = 0xffffffffu, lt_mask = (1u << lane) - 1u;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, FULL = 0xffffffffu;
+    ContBuf<NB> cb;
+    cb.idx = s_c32[warp][0]; cb.blockw = s_c32[warp][1]; cb.meta = s_c32[warp][2]; cb.tlm = s_c32[warp][3]; cb.u = &s_cu[warp][0][0]; cb.count = 0;
     const uint32_t L = s_plan.L, sb = s_plan.sb, M = a.M;
     const uint32_t n_slices = 1u << (2u * sb), n_gb = (a.n_guides + 31u) >> 5;
     const uint64_t items_per_strand = (uint64_t)n_slices * n_gb, n_items = 2ull * items_per_strand;
     unsigned long long n_nodes = 0, n_lookups = 0, n_patterns = 0, n_sectors = 0, n_seeds = 0;
+    SweepStats st = {0, 0, 0, 0, 0};
     for (;;) {
         uint32_t item = 0;
         if (lane == 0) item = atomicAdd(a.item_counter, 1u);
@@ -755,60 +917,15 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) sweep_kernel(SweepArgs a) {
         const uint64_t q = valid ? __ldg(a.gq + g) : 0ull;
         const uint32_t h = sweep_slice_distance(q, L, sb, beta);
         const int B = (valid && h <= M) ? (int)(M - h) : -1;
-        const uint32_t n_pat = B >= 0 ? s_plan.cum[B][B + 1] : 0u;
-        uint32_t incl = n_pat;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(FULL, incl, o); if (lane >= (uint32_t)o) incl += y; }
-        const uint32_t excl = incl - n_pat, T = __shfl_sync(FULL, incl, 31);
-        const FtabEntry* tab = reinterpret_cast<const FtabEntry*>(strand ? a.st[1].ftab : a.st[0].ftab);
-        DevSectorLoader ld; ld.lines = strand ? a.st[1].lines : a.st[0].lines;
-        for (uint32_t base = 0; base < T; base += 32u) {
-            const uint32_t it = base + lane;
-            const bool active = it < T;
-            uint32_t o = 0;                                   // owner = largest lane whose first pattern is <= it
-#pragma unroll
-            for (uint32_t step = 16u; step; step >>= 1) {
-                const uint32_t cand = o + step;
-                const uint32_t v = __shfl_sync(FULL, excl, cand & 31u);
-                if (cand < 32u && v <= it) o = cand;
-            }
-            const uint64_t oq = __shfl_sync(FULL, q, o);
-            const int oB = __shfl_sync(FULL, B, o);
-            const uint32_t oexcl = __shfl_sync(FULL, excl, o);
-            bool emit = false; uint32_t sp = 0, ep = 0, idx = 0, mm = 0;
-            if (active) {
-                uint32_t used;
-                idx = sweep_pattern(s_plan, a.masks, oq, beta, (uint32_t)oB, it - oexcl, used);
-                mm = M - (uint32_t)oB + used;
-                const uint2 e = __ldg(reinterpret_cast<const uint2*>(tab + idx));
-                n_patterns++;
-                if (((idx ^ (uint32_t)oq) & 15u) == 0u) n_lookups++;         // one table line per 16 beginnings
-                if (e.y) {
-                    sp = e.x; ep = e.x + e.y - 1u;
-                    uint32_t sectors = 0;
-                    const uint32_t qlen = (uint32_t)(oq >> 58);
-                    emit = node_viable(ld, sp, ep, L, qlen, qlen + a.plen, oq, a.pampack, M - mm, sectors);
-                    n_nodes++; n_sectors += sectors;
-                    n_lookups += ((ep + 1u) >> 6) != (sp >> 6) ? 2u : 1u;
-                }
-            }
-            const uint32_t emask = __ballot_sync(FULL, emit);
-            if (emask) {
-                uint32_t qbase = 0; const int leader = __ffs(emask) - 1;
-                if ((int)lane == leader) qbase = atomicAdd(a.queue_count, (uint32_t)__popc(emask));
-                qbase = __shfl_sync(FULL, qbase, leader);
-                if (emit) {
-                    const uint32_t slot = qbase + __popc(emask & lt_mask);
-                    if (slot < a.queue_cap) {
-                        SeedNode sn; sn.sp = sp; sn.ep = ep; sn.key = ftab_key(idx, oq, L);
-                        sn.tlm = (((gb * 32u + o) << 1) | strand) | (mm << 24) | (L << 27); sn.pad = 0;
-                        a.queue[slot] = sn;
-                        n_seeds++;
-                    } else atomicOr(a.error_flag, GSX_KERR_QUEUE_OVERFLOW);
-                }
-            }
-        }
+        const uint32_t codes = sweep_codes(q, L, a.plen, a.pampack);
+        // the zero-budget group first (most of the patterns, cheapest arithmetic), then the groups with budget left
+        sweep_pass<true, NB>(a, s_plan, cb, lane, strand, beta, gb, (uint32_t)q, codes, B, B >= 0 ? s_plan.mask_off[B + 1] - s_plan.mask_off[B] : 0u, st);
+        sweep_pass<false, NB>(a, s_plan, cb, lane, strand, beta, gb, (uint32_t)q, codes, B, B >= 0 ? s_plan.cum[B][B] : 0u, st);
+        n_nodes += st.nodes; n_lookups += st.lookups; n_patterns += st.patterns; n_sectors += st.sectors; n_seeds += st.seeds;
+        st = {0, 0, 0, 0, 0};
     }
+    while (cb.count) cont_process<NB>(a, cb, lane, st);
+    n_sectors += st.sectors; n_seeds += st.seeds;
     for (int o = 16; o; o >>= 1) {
         n_nodes += __shfl_xor_sync(FULL, n_nodes, o); n_lookups += __shfl_xor_sync(FULL, n_lookups, o);
         n_patterns += __shfl_xor_sync(FULL, n_patterns, o); n_sectors += __shfl_xor_sync(FULL, n_sectors, o);
@@ -822,7 +939,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) sweep_kernel(SweepArgs a) {
 
 template <int WARPS, int MINB>
 static cudaError_t launch_sweep_t(const SweepArgs& a, int sm_count, cudaStream_t s) {
-    sweep_kernel<WARPS, MINB><<<sm_count * MINB, WARPS * 32, 0, s>>>(a);
+    // NB = number of budget masks of the row filter: at most 3 mismatches (the default) or at most 4
+    if (a.M <= 3) sweep_kernel<WARPS, MINB, 4><<<sm_count * MINB, WARPS * 32, 0, s>>>(a);
+    else if (a.M <= 4) sweep_kernel<WARPS, MINB, 5><<<sm_count * MINB, WARPS * 32, 0, s>>>(a);
+    else return cudaErrorInvalidValue;
     return cudaGetLastError();
 }
 cudaError_t launch_sweep(const SweepArgs& a, int variant, int sm_count, cudaStream_t s) {

@@ -14,7 +14,7 @@ enum : uint32_t {
 };
 
 // level-L node that survived the sweep kernel's filter: the DFS kernel continues from it
-struct alignas(8) SeedNode { uint32_t sp, ep; uint64_t key; uint32_t tlm, pad; };
+struct alignas(16) SeedNode { uint32_t sp, ep, idx, tlm; };      // idx: table index of its pattern (gives the string key)
 
 struct SearchArgs {
     DevStrand st[2];

@@ -115,18 +115,30 @@ static void sweep_host(const DevStrand st[2], const Prepared& prep, uint32_t M) 
                 if (qlen < L) { fprintf(stderr, "--sweep needs guides of at least L characters\n"); exit(2); }
                 const uint32_t h = sweep_slice_distance(q, L, sb, beta);
                 if (h > M) continue;
-                const uint32_t B = M - h, n_pat = plan.cum[B][B + 1];
-                for (uint32_t t = 0; t < n_pat; t++) {
-                    uint32_t used; const uint32_t idx = sweep_pattern(plan, masks.data(), q, beta, B, t, used);
-                    const uint32_t mm = h + used;
-                    seen[g].push_back({idx, mm});
-                    const FtabEntry& e = g_ftab[strand][idx];
-                    if (!e.width) continue;
-                    uint32_t sectors = 0;
-                    if (!node_viable(ld, e.sp, e.sp + e.width - 1, L, qlen, qlen + prep.plen, q, prep.pampack, M - mm, sectors)) continue;
-                    Node nd{}; nd.sp = e.sp; nd.ep = e.sp + e.width - 1; nd.key_lo = ftab_key(idx, q, L); nd.task = (uint32_t)(2 * g + strand);
-                    nd.meta = meta_make(L, mm, 0, 0, 0, 0, 0);
-                    g_seeds[2 * g + strand].push_back(nd);
+                const uint32_t B = M - h;
+                for (int zero = 1; zero >= 0; zero--) {
+                    const uint32_t n_pat = zero ? plan.mask_off[B + 1] - plan.mask_off[B] : plan.cum[B][B];
+                    for (uint32_t t = 0; t < n_pat; t++) {
+                        uint32_t used = B;
+                        const uint32_t idx = zero ? sweep_pattern_zero(plan, masks.data(), q, beta, B, t) : sweep_pattern(plan, masks.data(), q, beta, B, t, used);
+                        const uint32_t mm = h + used;
+                        seen[g].push_back({idx, mm});
+                        const FtabEntry& e = g_ftab[strand][idx];
+                        if (!e.width) continue;
+                        uint32_t sectors = 0;
+                        const bool ok = zero ? node_viable_exact(ld, e.sp, e.sp + e.width - 1, L, qlen, qlen + prep.plen, q, prep.pampack, sectors)
+                                             : node_viable<kMaxDist>(ld, e.sp, e.sp + e.width - 1, L, qlen, qlen + prep.plen, q, prep.pampack, M - mm, sectors);
+                        {   // the resumable form the kernel runs (node_step) must agree with the whole-node forms
+                            uint32_t s2 = 0;
+                            const bool ok2 = node_viable_steps<kMaxDist>(ld, e.sp, e.sp + e.width - 1, sweep_codes(q, L, prep.plen, prep.pampack), M - mm, s2);
+                            if (ok2 != ok) { fprintf(stderr, "node_step disagrees with node_viable (idx %u zero %d ok %d ok2 %d sp %u w %u budget %u codes %x)\n", idx, zero, (int)ok, (int)ok2, e.sp, e.width, M - mm, sweep_codes(q, L, prep.plen, prep.pampack)); exit(3); }
+                            if (zero) { uint32_t s3 = 0; if (node_viable_steps<1>(ld, e.sp, e.sp + e.width - 1, sweep_codes(q, L, prep.plen, prep.pampack), 0, s3) != ok) { fprintf(stderr, "node_step<1> disagrees (idx %u)\n", idx); exit(3); } }
+                        }
+                        if (!ok) continue;
+                        Node nd{}; nd.sp = e.sp; nd.ep = e.sp + e.width - 1; nd.key_lo = ftab_key(idx, q, L); nd.task = (uint32_t)(2 * g + strand);
+                        nd.meta = meta_make(L, mm, 0, 0, 0, 0, 0);
+                        g_seeds[2 * g + strand].push_back(nd);
+                    }
                 }
             }
         // the slice-major enumeration must visit exactly the patterns (and mismatch counts) of the per-guide enumeration
