@@ -72,7 +72,7 @@ static void upload_index(gsx_index* ix, const int* devices, int n_devices) {
             for (int c = 0; c < 5; c++) d.d.C[c] = h.C[c];
             d.d.exc_lo = h.exc_rows.empty() ? 0xFFFFFFFFu : h.exc_rows.front();
             d.d.exc_hi = h.exc_rows.empty() ? 0u : h.exc_rows.back();
-            d.d.blk_shift = 5; d.d.lines = nullptr; d.d.ftab = nullptr; d.d.ftab_L = 0;
+            d.d.blk_shift = 5; d.d.lines = nullptr; d.d.filt = nullptr; d.d.ftab = nullptr; d.d.ftab_L = 0;
             {
                 // k-mer jump table: depth L such that a level-L interval still holds a handful of rows
                 int L = env_int("GSX_FTAB", -1);
@@ -96,6 +96,13 @@ static void upload_index(gsx_index* ix, const int* devices, int n_devices) {
                 CK(launch_build_lookahead(d.d, (unsigned char*)d.lines, nb, 0));
                 CK(cudaDeviceSynchronize());
                 d.d.lines = (const unsigned char*)d.lines; di.bytes += (uint64_t)nb * 128;
+                if (d.d.ftab && env_int("GSX_SWEEP_FILTER", 1)) {
+                    // third copy of the symbol planes, regrouped per 32 rows for the slice-major front end (sweep_kernel)
+                    CK(cudaMalloc(&d.filt, (size_t)nb * 128));
+                    CK(launch_build_filter((const unsigned char*)d.lines, (unsigned char*)d.filt, nb, 0));
+                    CK(cudaDeviceSynchronize());
+                    d.d.filt = (const unsigned char*)d.filt; di.bytes += (uint64_t)nb * 128;
+                }
             }
         }
         di.chroms = (Chrom*)upload(ix->chroms, di.bytes);
@@ -105,7 +112,7 @@ static void upload_index(gsx_index* ix, const int* devices, int n_devices) {
 
 static void free_device_index(DeviceIndex& di) {
     cudaSetDevice(di.device);
-    for (int s = 0; s < 2; s++) { cudaFree(di.st[s].blocks); cudaFree(di.st[s].lines); cudaFree(di.st[s].ftab); cudaFree(di.st[s].sa); cudaFree(di.st[s].exc_rows); cudaFree(di.st[s].exc_lf); cudaFree(di.st[s].n_rows); }
+    for (int s = 0; s < 2; s++) { cudaFree(di.st[s].blocks); cudaFree(di.st[s].lines); cudaFree(di.st[s].filt); cudaFree(di.st[s].ftab); cudaFree(di.st[s].sa); cudaFree(di.st[s].exc_rows); cudaFree(di.st[s].exc_lf); cudaFree(di.st[s].n_rows); }
     cudaFree(di.chroms);
 }
 
@@ -461,7 +468,7 @@ static void run_device_job(DeviceJob* job) {
         // slice-major front end (sweep_kernel) for large batches: needs the jump table and the look-ahead lines
         const uint32_t ftab_L = di.st[0].d.ftab_L;
         uint32_t sweep_sb = 0;
-        bool use_sweep = use_fast && ftab_L >= 6 && di.st[1].d.ftab_L == ftab_L && di.st[0].d.lines && di.st[1].d.lines && env_int("GSX_SWEEP", 1) &&
+        bool use_sweep = use_fast && ftab_L >= 6 && di.st[1].d.ftab_L == ftab_L && di.st[0].d.filt && di.st[1].d.filt && env_int("GSX_SWEEP", 1) &&
                          n >= (uint32_t)env_int("GSX_SWEEP_MIN", 8192) && prep.min_qlen >= ftab_L && p.mismatches <= 4 && p.threshold <= 4;
         if (use_sweep) {
             const double per_strand = 8.0 * std::pow(4.0, (double)ftab_L) + (double)(di.st[0].d.n / 64 + 1) * 128.0;

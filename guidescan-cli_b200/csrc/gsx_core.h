@@ -494,14 +494,14 @@ GSX_HD bool node_viable_exact(LoadSector ld, uint32_t sp, uint32_t ep, uint32_t 
 }
 
 // ---- the same row filter as a resumable step (sweep kernel, continuation form) ------------------------------------------
-// Lanes of a warp disagree on how far a node has to be examined (second sector pair: 1 node in 6; second block: 1 in 6),
-// so the sweep kernel examines every node for ONE step -- one block, one sector pair -- and parks the nodes that need
+// Lanes of a warp disagree on how far a node has to be examined (second sector: 1 node in 20; second group: 1 in 3),
+// so the sweep kernel examines every node for ONE step -- one 32-row group, one sector -- and parks the nodes that need
 // another step in a per-warp buffer that is drained 32 at a time, all lanes busy.
 //   codes: per guide, 3 bits per plane j = 0..6 of what a row must show at level L + j: 0..3 = that symbol (protospacer:
 //          anything else costs one mismatch; PAM: anything else kills the row), 4 = PAM wildcard, 5 = kills every row,
 //          7 = no such level.
-//   node_step: fetch sector pair `stage` (0: sectors 0,1 = planes t0,t1,t2; 1: sectors 2,3 = planes t3..t6) of `block`
-//          and advance the masks u[r] = rows with at most budget - r mismatches so far.
+//   node_step: fetch sector `stage` (0: planes t0..t3; 1: planes t4..t6) of one 32-row group of the filter array
+//          (DevStrand::filt) and advance the masks u[r] = rows with at most budget - r mismatches so far.
 GSX_HD uint32_t sweep_codes(uint64_t q, uint32_t L, uint32_t plen, uint32_t pampack) {
     const uint32_t qlen = (uint32_t)(q >> 58);
     uint32_t codes = 0;
@@ -515,15 +515,15 @@ GSX_HD uint32_t sweep_codes(uint64_t q, uint32_t L, uint32_t plen, uint32_t pamp
     }
     return codes;
 }
-GSX_HD bool sweep_has_stage1(uint32_t codes) { return ((codes >> 12) & 15u) != 7u; }
+GSX_HD bool sweep_has_stage1(uint32_t codes) { return ((codes >> 16) & 15u) != 7u; }
 
+// ld(group, k, w): sector k (0: t0..t3, 1: t4..t6) of 32-row group `group` of the filter array as eight 32-bit words
+// {hi, lo} x 4.  u[r] = rows (bit i = row 32 * group + i) with at most budget - r mismatches so far.
 template <int NB, class LoadSector>
-GSX_HD void node_step(LoadSector ld, uint32_t block, uint32_t stage, uint32_t codes, uint64_t u[NB], uint32_t& sectors) {
-    uint64_t wa[4], wb[4];
-    ld(block, 2u * stage, wa); ld(block, 2u * stage + 1u, wb); sectors += 2u;
-    const uint64_t ph[4] = {stage ? wa[0] : wa[2], stage ? wa[2] : wb[0], stage ? wb[0] : wb[2], wb[2]};
-    const uint64_t pl[4] = {stage ? wa[1] : wa[3], stage ? wa[3] : wb[1], stage ? wb[1] : wb[3], wb[3]};
-    const uint32_t cs = stage ? (codes >> 12) : ((codes & 0xFFFu) | 0x7000u);             // stage 0 has three planes: the fourth "does not exist"
+GSX_HD void node_step(LoadSector ld, uint32_t group, uint32_t stage, uint32_t codes, uint32_t u[NB], uint32_t& sectors) {
+    uint32_t w[8];
+    ld(group, stage, w); sectors++;
+    const uint32_t cs = stage ? ((codes >> 16) | 0x7000u) : codes;               // stage 1 has three planes: the fourth "does not exist"
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
@@ -531,7 +531,7 @@ GSX_HD void node_step(LoadSector ld, uint32_t block, uint32_t stage, uint32_t co
         const uint32_t c = (cs >> (4u * t)) & 15u;
         if (c == 7u || c == 12u) continue;                                       // no such level / PAM wildcard
         const uint32_t sym = c & 3u;
-        uint64_t eq = ~(ph[t] ^ ((sym & 2u) ? ~0ull : 0ull)) & ~(pl[t] ^ ((sym & 1u) ? ~0ull : 0ull));
+        uint32_t eq = ~(w[2u * t] ^ ((sym & 2u) ? ~0u : 0u)) & ~(w[2u * t + 1u] ^ ((sym & 1u) ? ~0u : 0u));
         if (c < 4u) {                                                            // protospacer: a differing row loses one unit of budget
 #if defined(__CUDA_ARCH__)
 #pragma unroll
@@ -539,7 +539,7 @@ GSX_HD void node_step(LoadSector ld, uint32_t block, uint32_t stage, uint32_t co
             for (int r = 0; r + 1 < NB; r++) u[r] = (u[r] & eq) | u[r + 1];
             u[NB - 1] &= eq;
         } else {
-            if (c == 13u) eq = 0ull;                                             // PAM character that can never match
+            if (c == 13u) eq = 0u;                                               // PAM character that can never match
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
@@ -547,19 +547,21 @@ GSX_HD void node_step(LoadSector ld, uint32_t block, uint32_t stage, uint32_t co
         }
     }
 }
-// whole-node form of the same thing (reference semantics for the tests; the kernel interleaves the steps of many nodes)
+GSX_HD uint32_t rows_mask32(uint32_t r0, uint32_t r1) { return (r1 == 31u ? ~0u : ((1u << (r1 + 1u)) - 1u)) & ~((1u << r0) - 1u); }
+
+// whole-node form of the same thing (reference semantics for the tests; the kernel interleaves the steps of many nodes).
+// Nodes spanning more than two 32-row groups are not examined (true).
 template <int NB, class LoadSector>
 GSX_HD bool node_viable_steps(LoadSector ld, uint32_t sp, uint32_t ep, uint32_t codes, uint32_t budget, uint32_t& sectors) {
-    const uint32_t e1 = ep + 1u, bs = sp >> 6, be = e1 >> 6;
-    if (be - bs > 1u) return true;
+    const uint32_t e1 = ep + 1u, gs = sp >> 5, ge = e1 >> 5;
+    if (ge - gs > 1u) return true;
     for (uint32_t part = 0; part < 2u; part++) {
-        if (part == 1u && (be == bs || (e1 & 63u) == 0u)) break;
-        const uint32_t r0 = part ? 0u : (sp & 63u), r1 = part ? (ep & 63u) : (be != bs ? 63u : (ep & 63u));
-        const uint64_t rows = (r1 == 63u ? ~0ull : ((1ull << (r1 + 1u)) - 1ull)) & ~((1ull << r0) - 1ull);
-        uint64_t u[NB];
-        for (int r = 0; r < NB; r++) u[r] = budget >= (uint32_t)r ? rows : 0ull;
-        node_step<NB>(ld, bs + part, 0u, codes, u, sectors);
-        if (u[0] && sweep_has_stage1(codes)) node_step<NB>(ld, bs + part, 1u, codes, u, sectors);
+        if (part == 1u && (ge == gs || (e1 & 31u) == 0u)) break;
+        const uint32_t rows = part ? rows_mask32(0u, ep & 31u) : rows_mask32(sp & 31u, ge != gs ? 31u : (ep & 31u));
+        uint32_t u[NB];
+        for (int r = 0; r < NB; r++) u[r] = budget >= (uint32_t)r ? rows : 0u;
+        node_step<NB>(ld, gs + part, 0u, codes, u, sectors);
+        if (u[0] && sweep_has_stage1(codes)) node_step<NB>(ld, gs + part, 1u, codes, u, sectors);
         if (u[0]) return true;
     }
     return false;

@@ -365,6 +365,27 @@ __global__ void build_lookahead_kernel(DevStrand st, unsigned char* __restrict__
     }
 }
 
+// row-filter array of the sweep kernel: the planes t0..t6 of each look-ahead line, regrouped per 32 rows so that ONE
+// 32-byte load gives four characters of look-ahead (DevStrand::filt)
+__global__ void build_filter_kernel(const unsigned char* __restrict__ lines, unsigned char* __restrict__ filt, uint32_t n_blocks) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < 2ull * n_blocks; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t b = (uint32_t)(i >> 1), half = (uint32_t)(i & 1);
+        const uint64_t* line = reinterpret_cast<const uint64_t*>(lines + (size_t)b * 128);
+        uint32_t out[16];
+        for (int j = 0; j < 7; j++) {
+            const uint64_t hi = j == 0 ? line[2] : line[4 + 2 * (j - 1)], lo = j == 0 ? line[3] : line[5 + 2 * (j - 1)];
+            out[2 * j] = (uint32_t)(hi >> (32 * half)); out[2 * j + 1] = (uint32_t)(lo >> (32 * half));
+        }
+        out[14] = out[15] = 0;
+        uint4* dst = reinterpret_cast<uint4*>(filt + i * 64);
+        for (int k = 0; k < 4; k++) dst[k] = make_uint4(out[4 * k], out[4 * k + 1], out[4 * k + 2], out[4 * k + 3]);
+    }
+}
+cudaError_t launch_build_filter(const unsigned char* lines, unsigned char* filt, uint32_t n_blocks, cudaStream_t s) {
+    build_filter_kernel<<<148 * 16, 256, 0, s>>>(lines, filt, n_blocks);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_build_lookahead(const DevStrand& src, unsigned char* lines, uint32_t n_blocks, cudaStream_t s) {
     build_lookahead_kernel<<<148 * 16, 256, 0, s>>>(src, lines, n_blocks);
     return cudaGetLastError();
@@ -725,10 +746,11 @@ int search_fast_grid_warps(int variant, int sm_count) {
 // on the same one or two slices at any time.  Inside a unit the 32 guides' pattern lists are flattened over the lanes.
 // ---------------------------------------------------------------------------------------------------------
 struct DevSectorLoader {
-    const unsigned char* lines;
-    __device__ __forceinline__ void operator()(uint32_t block, uint32_t k, uint64_t w[4]) const {
-        const Blk b = ld_block(reinterpret_cast<const OccBlock*>(lines + ((size_t)block << 7) + (k << 5)));      // LDG.E.256
-        w[0] = ((uint64_t)b.c1 << 32) | b.c0; w[1] = ((uint64_t)b.c3 << 32) | b.c2; w[2] = b.hi; w[3] = b.lo;
+    const unsigned char* filt;
+    __device__ __forceinline__ void operator()(uint32_t group, uint32_t k, uint32_t w[8]) const {
+        asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"                                       // LDG.E.256
+                     : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+                     : "l"(filt + ((size_t)group << 6) + (k << 5)));
     }
 };
 
@@ -736,19 +758,19 @@ struct SweepStats { uint32_t nodes, lookups, patterns, sectors, seeds; };
 
 // per-warp buffer of nodes that need another filter step (gsx_core.h node_step): 64 records in shared memory
 //   idx    table index of the pattern (sp, ep are re-read from the table if the node survives)
-//   blockw block to examine | (ep & 63) << 26 (last row of the node inside its second block)
+//   blockw 32-row group to examine | (ep & 31) << 27 (last row of the node inside its second group)
 //   meta   plane codes (28 bits) | stage << 28 | part << 29 | has-second-block << 30
 //   tlm    task | mismatches << 24 | remaining budget << 27
 //   u[r]   row masks of the filter
 template <int NB>
 struct ContBuf {
-    uint32_t* idx; uint32_t* blockw; uint32_t* meta; uint32_t* tlm; uint64_t* u;      // u[r * 64 + slot]
+    uint32_t* idx; uint32_t* blockw; uint32_t* meta; uint32_t* tlm; uint32_t* u;      // u[r * 64 + slot]
     uint32_t count;                                                                    // warp-uniform
 };
 constexpr uint32_t CONT_STAGE = 1u << 28, CONT_PART = 1u << 29, CONT_HASB = 1u << 30;
 
 template <int NB>
-__device__ __forceinline__ void cont_push(ContBuf<NB>& cb, uint32_t lane, bool want, uint32_t idx, uint32_t blockw, uint32_t meta, uint32_t tlm, const uint64_t u[NB]) {
+__device__ __forceinline__ void cont_push(ContBuf<NB>& cb, uint32_t lane, bool want, uint32_t idx, uint32_t blockw, uint32_t meta, uint32_t tlm, const uint32_t u[NB]) {
     const uint32_t m = __ballot_sync(0xffffffffu, want);
     if (want) {
         const uint32_t slot = cb.count + __popc(m & ((1u << lane) - 1u));
@@ -781,7 +803,7 @@ template <int NB>
 __device__ __forceinline__ void cont_process(const SweepArgs& a, ContBuf<NB>& cb, uint32_t lane, SweepStats& st) {
     const uint32_t n = cb.count < 32u ? cb.count : 32u;
     const bool mine = lane < n;
-    uint32_t idx = 0, blockw = 0, meta = 0, tlm = 0; uint64_t u[NB];
+    uint32_t idx = 0, blockw = 0, meta = 0, tlm = 0; uint32_t u[NB];
 #pragma unroll
     for (int r = 0; r < NB; r++) u[r] = 0;
     if (mine) {
@@ -793,13 +815,13 @@ __device__ __forceinline__ void cont_process(const SweepArgs& a, ContBuf<NB>& cb
     __syncwarp();
     cb.count -= n;
     const uint32_t strand = tlm & 1u, codes = meta & 0x0FFFFFFFu, stage = (meta & CONT_STAGE) ? 1u : 0u;
-    DevSectorLoader ld; ld.lines = strand ? a.st[1].lines : a.st[0].lines;
+    DevSectorLoader ld; ld.filt = strand ? a.st[1].filt : a.st[0].filt;
     uint32_t sectors = 0;
-    if (mine) node_step<NB>(ld, blockw & 0x03FFFFFFu, stage, codes, u, sectors);
+    if (mine) node_step<NB>(ld, blockw & 0x07FFFFFFu, stage, codes, u, sectors);
     st.sectors += sectors;
-    const bool alive = mine && u[0] != 0ull;
-    const bool again = alive && stage == 0u && sweep_has_stage1(codes);                  // second sector pair of the same block
-    const bool second = mine && !alive && !(meta & CONT_PART) && (meta & CONT_HASB);     // first block is dead: try the second one
+    const bool alive = mine && u[0] != 0u;
+    const bool again = alive && stage == 0u && sweep_has_stage1(codes);                  // second sector of the same group
+    const bool second = mine && !alive && !(meta & CONT_PART) && (meta & CONT_HASB);     // first group is dead: try the second one
     const bool emit = alive && !again;
     uint32_t sp = 0, ep = 0;
     if (emit) {
@@ -808,11 +830,10 @@ __device__ __forceinline__ void cont_process(const SweepArgs& a, ContBuf<NB>& cb
     }
     sweep_emit(a, lane, emit, sp, ep, idx, tlm, st);
     if (second) {
-        const uint32_t rB = blockw >> 26, budget = (tlm >> 27) & 7u;
-        const uint64_t rows = rB == 63u ? ~0ull : ((1ull << (rB + 1u)) - 1ull);
+        const uint32_t budget = (tlm >> 27) & 7u, rows = rows_mask32(0u, blockw >> 27);
 #pragma unroll
-        for (int r = 0; r < NB; r++) u[r] = budget >= (uint32_t)r ? rows : 0ull;
-        blockw = (blockw & 0x03FFFFFFu) + 1u; meta = (meta & ~CONT_STAGE) | CONT_PART;
+        for (int r = 0; r < NB; r++) u[r] = budget >= (uint32_t)r ? rows : 0u;
+        blockw = (blockw & 0x07FFFFFFu) + 1u; meta = (meta & ~CONT_STAGE) | CONT_PART;
     }
     if (again) meta |= CONT_STAGE;
     cont_push<NB>(cb, lane, again || second, idx, blockw, meta, tlm, u);
@@ -825,7 +846,7 @@ __device__ __forceinline__ void sweep_pass(const SweepArgs& a, const SweepPlan& 
                                            uint32_t qlow, uint32_t codes, int B, uint32_t n_mine, SweepStats& st) {
     const uint32_t FULL = 0xffffffffu, M = a.M;
     const FtabEntry* tab = reinterpret_cast<const FtabEntry*>(strand ? a.st[1].ftab : a.st[0].ftab);
-    DevSectorLoader ld; ld.lines = strand ? a.st[1].lines : a.st[0].lines;
+    DevSectorLoader ld; ld.filt = strand ? a.st[1].filt : a.st[0].filt;
     uint32_t incl = n_mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(FULL, incl, o); if (lane >= (uint32_t)o) incl += y; }
@@ -844,7 +865,7 @@ __device__ __forceinline__ void sweep_pass(const SweepArgs& a, const SweepPlan& 
         const uint32_t oq = __shfl_sync(FULL, qlow, o), ocodes = __shfl_sync(FULL, codes, o), oexcl = __shfl_sync(FULL, excl, o);
         const int oB = __shfl_sync(FULL, B, o);
         bool emit = false, park = false; uint32_t sp = 0, ep = 0, idx = 0, mm = M, blockw = 0, meta = 0;
-        uint64_t u[NB];
+        uint32_t u[NB];
 #pragma unroll
         for (int r = 0; r < NB; r++) u[r] = 0;
         if (active) {
@@ -855,28 +876,26 @@ __device__ __forceinline__ void sweep_pass(const SweepArgs& a, const SweepPlan& 
             if (((idx ^ oq) & 15u) == 0u) st.lookups++;                       // one table line per 16 beginnings
             if (e.y) {
                 sp = e.x; ep = e.x + e.y - 1u;
-                const uint32_t e1 = ep + 1u, bs = sp >> 6, be = e1 >> 6;
-                st.nodes++; st.lookups += be != bs ? 2u : 1u;
-                if (be - bs > 1u) emit = true;                                // too wide for the filter: the tree search takes it as is
+                const uint32_t e1 = ep + 1u, gs = sp >> 5, ge = e1 >> 5;
+                st.nodes++; st.lookups += (e1 >> 6) != (sp >> 6) ? 2u : 1u;
+                if (ge - gs > 1u) emit = true;                                // too wide for the filter: the tree search takes it as is
                 else {
-                    const uint32_t r0 = sp & 63u, r1 = be != bs ? 63u : (ep & 63u);
-                    const uint64_t rows = (r1 == 63u ? ~0ull : ((1ull << (r1 + 1u)) - 1ull)) & ~((1ull << r0) - 1ull);
-                    const bool hasB = be != bs && (e1 & 63u) != 0u;
+                    const uint32_t rows = rows_mask32(sp & 31u, ge != gs ? 31u : (ep & 31u));
+                    const bool hasB = ge != gs && (e1 & 31u) != 0u;
                     uint32_t sectors = 0;
-                    if (ZERO) { uint64_t v[1] = {rows}; node_step<1>(ld, bs, 0u, ocodes, v, sectors); u[0] = v[0]; }
+                    if (ZERO) { uint32_t v[1] = {rows}; node_step<1>(ld, gs, 0u, ocodes, v, sectors); u[0] = v[0]; }
                     else {
 #pragma unroll
-                        for (int r = 0; r < NB; r++) u[r] = (M - mm) >= (uint32_t)r ? rows : 0ull;
-                        node_step<NB>(ld, bs, 0u, ocodes, u, sectors);
+                        for (int r = 0; r < NB; r++) u[r] = (M - mm) >= (uint32_t)r ? rows : 0u;
+                        node_step<NB>(ld, gs, 0u, ocodes, u, sectors);
                     }
                     st.sectors += sectors;
-                    blockw = bs | ((ep & 63u) << 26); meta = ocodes | (hasB ? CONT_HASB : 0u);
+                    blockw = gs | ((ep & 31u) << 27); meta = ocodes | (hasB ? CONT_HASB : 0u);
                     if (u[0]) { if (sweep_has_stage1(ocodes)) { park = true; meta |= CONT_STAGE; } else emit = true; }
-                    else if (hasB) {                                          // nothing left in the first block: park the second one
-                        const uint32_t rB = ep & 63u;
-                        const uint64_t rowsB = rB == 63u ? ~0ull : ((1ull << (rB + 1u)) - 1ull);
+                    else if (hasB) {                                          // nothing left in the first group: park the second one
+                        const uint32_t rowsB = rows_mask32(0u, ep & 31u);
 #pragma unroll
-                        for (int r = 0; r < NB; r++) u[r] = (M - mm) >= (uint32_t)r ? rowsB : 0ull;
+                        for (int r = 0; r < NB; r++) u[r] = (M - mm) >= (uint32_t)r ? rowsB : 0u;
                         park = true; blockw += 1u; meta |= CONT_PART;
                     }
                 }
@@ -892,7 +911,7 @@ template <int WARPS, int MINB, int NB>
 __global__ void __launch_bounds__(WARPS * 32, MINB) sweep_kernel(SweepArgs a) {
     __shared__ SweepPlan s_plan;
     __shared__ uint32_t s_c32[WARPS][4][64];
-    __shared__ uint64_t s_cu[WARPS][NB][64];
+    __shared__ uint32_t s_cu[WARPS][NB][64];
     for (int i = threadIdx.x; i < (int)(sizeof(SweepPlan) / 4); i += blockDim.x)
         reinterpret_cast<uint32_t*>(&s_plan)[i] = reinterpret_cast<const uint32_t*>(&a.plan)[i];
     __syncthreads();

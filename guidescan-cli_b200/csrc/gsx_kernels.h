@@ -87,6 +87,8 @@ cudaError_t upload_cfd_tables();
 // k-mer jump table of depth L for one strand; tab and tmp must each hold 4^L entries of 8 bytes; result ends up in tab
 cudaError_t launch_build_ftab(const DevStrand& st, uint32_t L, void* tab, void* tmp, cudaStream_t s);
 cudaError_t launch_build_lookahead(const DevStrand& src, unsigned char* lines, uint32_t n_blocks, cudaStream_t s);
+// look-ahead lines -> row-filter array of the sweep kernel (filt must hold n_blocks * 128 bytes)
+cudaError_t launch_build_filter(const unsigned char* lines, unsigned char* filt, uint32_t n_blocks, cudaStream_t s);
 int search_grid_warps(bool wide, int variant, int sm_count);
 cudaError_t launch_search(const SearchArgs& a, bool wide, int variant, int sm_count, cudaStream_t s, int* warps_total);
 int search_fast_grid_warps(int variant, int sm_count);

@@ -59,6 +59,10 @@ struct DevStrand {
     uint32_t ftab_L;
     const unsigned char* lines;    // optional second copy, one 128-byte line per 64 rows: OccBlock + six look-ahead symbol
                                    // planes (see build_lookahead_kernel); nullptr if absent
+    const unsigned char* filt;     // optional row-filter array of the sweep kernel, 64 bytes per 32 rows: sector 0 = the 2-bit
+                                   // symbols t0..t3 of those rows as 32-bit plane pairs (hi, lo), sector 1 = t4..t6 (+ 8 bytes of
+                                   // padding): the next seven characters a backward search from each row would consume, four of
+                                   // them behind ONE 32-byte load (see build_filter_kernel); nullptr if absent
 };
 
 GSX_HD const OccBlock* block_ptr(const DevStrand& st, uint32_t b) {
