@@ -72,7 +72,7 @@ static void upload_index(gsx_index* ix, const int* devices, int n_devices) {
             for (int c = 0; c < 5; c++) d.d.C[c] = h.C[c];
             d.d.exc_lo = h.exc_rows.empty() ? 0xFFFFFFFFu : h.exc_rows.front();
             d.d.exc_hi = h.exc_rows.empty() ? 0u : h.exc_rows.back();
-            d.d.blk_shift = 5; d.d.lines = nullptr; d.d.filt = nullptr; d.d.ftab = nullptr; d.d.ftab_L = 0;
+            d.d.blk_shift = 5; d.d.lines = nullptr; d.d.sum0 = nullptr; d.d.sum1 = nullptr; d.d.ftab = nullptr; d.d.ftab_L = 0;
             {
                 // k-mer jump table: depth L such that a level-L interval still holds a handful of rows
                 int L = env_int("GSX_FTAB", -1);
@@ -96,12 +96,13 @@ static void upload_index(gsx_index* ix, const int* devices, int n_devices) {
                 CK(launch_build_lookahead(d.d, (unsigned char*)d.lines, nb, 0));
                 CK(cudaDeviceSynchronize());
                 d.d.lines = (const unsigned char*)d.lines; di.bytes += (uint64_t)nb * 128;
-                if (d.d.ftab && env_int("GSX_SWEEP_FILTER", 1)) {
-                    // third copy of the symbol planes, regrouped per 32 rows for the slice-major front end (sweep_kernel)
-                    CK(cudaMalloc(&d.filt, (size_t)nb * 128));
-                    CK(launch_build_filter((const unsigned char*)d.lines, (unsigned char*)d.filt, nb, 0));
+                if (d.d.ftab && env_int("GSX_SWEEP_SUMMARY", 1)) {
+                    // pattern summaries for the slice-major front end (sweep_kernel): 2 x 32 bytes per jump-table entry
+                    const uint64_t n_entries = 1ull << (2 * d.d.ftab_L);
+                    CK(cudaMalloc(&d.sum0, n_entries * 32)); CK(cudaMalloc(&d.sum1, n_entries * 32));
+                    CK(launch_build_summary(d.ftab, (const unsigned char*)d.lines, (unsigned char*)d.sum0, (unsigned char*)d.sum1, n_entries, 0));
                     CK(cudaDeviceSynchronize());
-                    d.d.filt = (const unsigned char*)d.filt; di.bytes += (uint64_t)nb * 128;
+                    d.d.sum0 = (const unsigned char*)d.sum0; d.d.sum1 = (const unsigned char*)d.sum1; di.bytes += n_entries * 64;
                 }
             }
         }
@@ -112,7 +113,7 @@ static void upload_index(gsx_index* ix, const int* devices, int n_devices) {
 
 static void free_device_index(DeviceIndex& di) {
     cudaSetDevice(di.device);
-    for (int s = 0; s < 2; s++) { cudaFree(di.st[s].blocks); cudaFree(di.st[s].lines); cudaFree(di.st[s].filt); cudaFree(di.st[s].ftab); cudaFree(di.st[s].sa); cudaFree(di.st[s].exc_rows); cudaFree(di.st[s].exc_lf); cudaFree(di.st[s].n_rows); }
+    for (int s = 0; s < 2; s++) { cudaFree(di.st[s].blocks); cudaFree(di.st[s].lines); cudaFree(di.st[s].sum0); cudaFree(di.st[s].sum1); cudaFree(di.st[s].ftab); cudaFree(di.st[s].sa); cudaFree(di.st[s].exc_rows); cudaFree(di.st[s].exc_lf); cudaFree(di.st[s].n_rows); }
     cudaFree(di.chroms);
 }
 
@@ -468,10 +469,10 @@ static void run_device_job(DeviceJob* job) {
         // slice-major front end (sweep_kernel) for large batches: needs the jump table and the look-ahead lines
         const uint32_t ftab_L = di.st[0].d.ftab_L;
         uint32_t sweep_sb = 0;
-        bool use_sweep = use_fast && ftab_L >= 6 && di.st[1].d.ftab_L == ftab_L && di.st[0].d.filt && di.st[1].d.filt && env_int("GSX_SWEEP", 1) &&
+        bool use_sweep = use_fast && ftab_L >= 6 && di.st[1].d.ftab_L == ftab_L && di.st[0].d.sum0 && di.st[1].d.sum0 && env_int("GSX_SWEEP", 1) &&
                          n >= (uint32_t)env_int("GSX_SWEEP_MIN", 8192) && prep.min_qlen >= ftab_L && p.mismatches <= 4 && p.threshold <= 4;
         if (use_sweep) {
-            const double per_strand = 8.0 * std::pow(4.0, (double)ftab_L) + (double)(di.st[0].d.n / 64 + 1) * 128.0;
+            const double per_strand = 40.0 * std::pow(4.0, (double)ftab_L);                  // sum0 + the part of sum1 that is touched
             const double target = (double)env_int("GSX_SWEEP_SLICE_MB", 12) * 1e6;
             sweep_sb = 1; while (sweep_sb < ftab_L - 3 && per_strand / std::pow(4.0, (double)sweep_sb) > target) sweep_sb++;
             if (env_int("GSX_SWEEP_SB", 0) > 0) sweep_sb = (uint32_t)env_int("GSX_SWEEP_SB", 0);
@@ -486,12 +487,12 @@ static void run_device_job(DeviceJob* job) {
         auto launch_fast = [&](SearchArgs& m, cudaEvent_t ev_mid) {
             if (use_sweep) {
                 SweepArgs w{};
-                std::vector<uint32_t> masks;
-                sweep_make_plan(ftab_L, sweep_sb, m.p.M, w.plan, masks);
-                uint32_t* d_masks = B.alloc<uint32_t>(masks.size());
-                CK(cudaMemcpyAsync(d_masks, masks.data(), masks.size() * 4, cudaMemcpyHostToDevice, s)); CK(cudaStreamSynchronize(s));
+                std::vector<uint32_t> xtab;
+                sweep_make_plan(ftab_L, sweep_sb, m.p.M, w.plan, xtab);
+                uint32_t* d_xtab = B.alloc<uint32_t>(xtab.size());
+                CK(cudaMemcpyAsync(d_xtab, xtab.data(), xtab.size() * 4, cudaMemcpyHostToDevice, s)); CK(cudaStreamSynchronize(s));
                 if (!d_queue) d_queue = B.alloc<SeedNode>(queue_cap);
-                w.st[0] = m.st[0]; w.st[1] = m.st[1]; w.gq = m.gq; w.skip = m.skip; w.n_guides = n; w.masks = d_masks;
+                w.st[0] = m.st[0]; w.st[1] = m.st[1]; w.gq = m.gq; w.skip = m.skip; w.n_guides = n; w.xtab = d_xtab;
                 w.M = m.p.M; w.plen = m.plen; w.pampack = m.pampack; w.counting = m.p.counting;
                 w.queue = d_queue; w.queue_cap = (uint32_t)queue_cap; w.queue_count = d_ctrs + 3; w.item_counter = d_ctrs + 4;
                 w.error_flag = d_ctrs + 2; w.stats = d_stats;

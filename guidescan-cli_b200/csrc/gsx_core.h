@@ -493,15 +493,16 @@ GSX_HD bool node_viable_exact(LoadSector ld, uint32_t sp, uint32_t ep, uint32_t 
     return false;
 }
 
-// ---- the same row filter as a resumable step (sweep kernel, continuation form) ------------------------------------------
-// Lanes of a warp disagree on how far a node has to be examined (second sector: 1 node in 20; second group: 1 in 3),
-// so the sweep kernel examines every node for ONE step -- one 32-row group, one sector -- and parks the nodes that need
-// another step in a per-warp buffer that is drained 32 at a time, all lanes busy.
-//   codes: per guide, 3 bits per plane j = 0..6 of what a row must show at level L + j: 0..3 = that symbol (protospacer:
-//          anything else costs one mismatch; PAM: anything else kills the row), 4 = PAM wildcard, 5 = kills every row,
-//          7 = no such level.
-//   node_step: fetch sector `stage` (0: planes t0..t3; 1: planes t4..t6) of one 32-row group of the filter array
-//          (DevStrand::filt) and advance the masks u[r] = rows with at most budget - r mismatches so far.
+// ---- the row filter of the sweep kernel --------------------------------------------------------------------------------
+// The sweep kernel never walks the interval of a level-L pattern: it reads the pattern's SUMMARY (DevStrand::sum0/sum1, indexed
+// like the jump table) -- the next seven characters of every row of the interval as bit planes -- and tests all rows at once.
+//   codes: per guide, 4 bits per plane j = 0..6 of what a row must show at level L + j: 0..3 = that symbol in the
+//          protospacer (anything else costs one mismatch), 8..11 = that symbol in the PAM (anything else kills the row),
+//          12 = PAM wildcard, 13 = kills every row, 7 = no such level.
+//   u[r]:  rows with at most budget - r mismatches so far (r = 0 .. NB-1, NB > budget); u[0] = rows still alive.
+//   summary_step: stage 0 = sum0 (valid rows + planes t0,t1,t2), stage 1 = sum1 (planes t3..t6); lanes of a warp disagree on
+//          whether stage 1 is needed (1 node in 6), so the kernel parks those nodes in a per-warp buffer and drains it 32 at
+//          a time, all lanes busy.
 GSX_HD uint32_t sweep_codes(uint64_t q, uint32_t L, uint32_t plen, uint32_t pampack) {
     const uint32_t qlen = (uint32_t)(q >> 58);
     uint32_t codes = 0;
@@ -515,19 +516,16 @@ GSX_HD uint32_t sweep_codes(uint64_t q, uint32_t L, uint32_t plen, uint32_t pamp
     }
     return codes;
 }
-GSX_HD bool sweep_has_stage1(uint32_t codes) { return ((codes >> 16) & 15u) != 7u; }
+GSX_HD bool sweep_has_stage1(uint32_t codes) { return ((codes >> 12) & 15u) != 7u; }
+enum : uint32_t { SUM_WIDE = 1u, SUM_TWO_BLOCKS = 2u };
 
-// ld(group, k, w): sector k (0: t0..t3, 1: t4..t6) of 32-row group `group` of the filter array as eight 32-bit words
-// {hi, lo} x 4.  u[r] = rows (bit i = row 32 * group + i) with at most budget - r mismatches so far.
-template <int NB, class LoadSector>
-GSX_HD void node_step(LoadSector ld, uint32_t group, uint32_t stage, uint32_t codes, uint32_t u[NB], uint32_t& sectors) {
-    uint32_t w[8];
-    ld(group, stage, w); sectors++;
-    const uint32_t cs = stage ? ((codes >> 16) | 0x7000u) : codes;               // stage 1 has three planes: the fourth "does not exist"
+template <int NB>
+GSX_HD void summary_planes(const uint32_t* w, uint32_t n_planes, uint32_t cs, uint32_t u[NB]) {
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
     for (uint32_t t = 0; t < 4u; t++) {
+        if (t >= n_planes) break;
         const uint32_t c = (cs >> (4u * t)) & 15u;
         if (c == 7u || c == 12u) continue;                                       // no such level / PAM wildcard
         const uint32_t sym = c & 3u;
@@ -547,24 +545,54 @@ GSX_HD void node_step(LoadSector ld, uint32_t group, uint32_t stage, uint32_t co
         }
     }
 }
-GSX_HD uint32_t rows_mask32(uint32_t r0, uint32_t r1) { return (r1 == 31u ? ~0u : ((1u << (r1 + 1u)) - 1u)) & ~((1u << r0) - 1u); }
-
-// whole-node form of the same thing (reference semantics for the tests; the kernel interleaves the steps of many nodes).
-// Nodes spanning more than two 32-row groups are not examined (true).
-template <int NB, class LoadSector>
-GSX_HD bool node_viable_steps(LoadSector ld, uint32_t sp, uint32_t ep, uint32_t codes, uint32_t budget, uint32_t& sectors) {
-    const uint32_t e1 = ep + 1u, gs = sp >> 5, ge = e1 >> 5;
-    if (ge - gs > 1u) return true;
-    for (uint32_t part = 0; part < 2u; part++) {
-        if (part == 1u && (ge == gs || (e1 & 31u) == 0u)) break;
-        const uint32_t rows = part ? rows_mask32(0u, ep & 31u) : rows_mask32(sp & 31u, ge != gs ? 31u : (ep & 31u));
-        uint32_t u[NB];
-        for (int r = 0; r < NB; r++) u[r] = budget >= (uint32_t)r ? rows : 0u;
-        node_step<NB>(ld, gs + part, 0u, codes, u, sectors);
-        if (u[0] && sweep_has_stage1(codes)) node_step<NB>(ld, gs + part, 1u, codes, u, sectors);
-        if (u[0]) return true;
-    }
-    return false;
+// ld(stage, idx, w): the eight 32-bit words of sum0[idx] (stage 0) or sum1[idx] (stage 1).
+// stage 0 initialises u from the valid-row mask and returns the info word; an empty interval leaves u all zero.
+template <int NB, class LoadSummary>
+GSX_HD uint32_t summary_step0(LoadSummary ld, uint32_t idx, uint32_t codes, uint32_t budget, uint32_t u[NB], uint32_t& valid) {
+    uint32_t w[8];
+    ld(0u, idx, w);
+    valid = w[0];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int r = 0; r < NB; r++) u[r] = budget >= (uint32_t)r ? valid : 0u;
+    summary_planes<NB>(w + 2, 3u, codes, u);
+    return w[1];
+}
+template <int NB, class LoadSummary>
+GSX_HD void summary_step1(LoadSummary ld, uint32_t idx, uint32_t codes, uint32_t u[NB]) {
+    uint32_t w[8];
+    ld(1u, idx, w);
+    summary_planes<NB>(w, 4u, codes >> 12, u);
+}
+// whole-node form (reference semantics for the tests): can any row of the pattern's interval still reach the final level?
+template <int NB, class LoadSummary>
+GSX_HD bool summary_viable(LoadSummary ld, uint32_t idx, uint32_t codes, uint32_t budget) {
+    uint32_t u[NB], valid;
+    const uint32_t info = summary_step0<NB>(ld, idx, codes, budget, u, valid);
+    if (info & SUM_WIDE) return true;
+    if (u[0] && sweep_has_stage1(codes)) summary_step1<NB>(ld, idx, codes, u);
+    return u[0] != 0u;
+}
+// builds the two summary sectors of one table entry from the look-ahead lines; plane(b, j, hi) = 64-bit plane of t_j
+// (hi or lo half of the 2-bit symbol) of 64-row block b
+template <class Plane>
+GSX_HD void summary_build(Plane plane, uint32_t sp, uint32_t width, uint32_t s0[8], uint32_t s1[8]) {
+    for (int i = 0; i < 8; i++) s0[i] = s1[i] = 0u;
+    if (width == 0u) return;
+    const uint32_t e1 = sp + width;
+    uint32_t info = ((e1 >> 6) != (sp >> 6)) ? SUM_TWO_BLOCKS : 0u;
+    if (width > 32u) { s0[0] = ~0u; s0[1] = info | SUM_WIDE; return; }
+    const uint32_t valid = width == 32u ? ~0u : ((1u << width) - 1u);
+    const uint32_t b = sp >> 6, r0 = sp & 63u, nA = (64u - r0) < width ? (64u - r0) : width;      // rows taken from block b
+    s0[0] = valid; s0[1] = info;
+    for (uint32_t j = 0; j < 7u; j++)
+        for (uint32_t h = 0; h < 2u; h++) {
+            uint64_t bits = plane(b, j, h != 0u) >> r0;
+            if (nA < width) bits |= plane(b + 1u, j, h != 0u) << nA;
+            const uint32_t v = (uint32_t)bits & valid;
+            if (j < 3u) s0[2u + 2u * j + (h ? 0u : 1u)] = v; else s1[2u * (j - 3u) + (h ? 0u : 1u)] = v;   // hi first, then lo
+        }
 }
 
 // ---- k-mer jump table (specialised search kernels) ------------------------------------------------------------------
@@ -620,42 +648,22 @@ GSX_HD uint64_t ftab_key(uint32_t idx, uint64_t q, uint32_t L) {
 // A slice fixes the last `sb` consumed characters of the pattern (the top 2*sb bits of the table index): its table
 // entries and the BWT rows they point to are both contiguous and small enough to stay in L2 while every guide of the
 // batch visits them.  For one guide and one slice with h substitutions inside the slice characters, the patterns are
-// numbered t = 0 .. n-1:  group j = 0 .. B (B = M - h) holds the xor-masks with exactly j substituted characters among
-// characters 2 .. L-sb-1 (`masks`, sorted by j, group j starting at mask_off[j]), each combined with the nb(B - j)
-// beginnings whose own substitutions fit the rest of the budget: nb(0) = 1 (exact), nb(1) = 7 (exact or one of the two
-// characters changed), nb(>=2) = 16.  Substitutions are xor-encoded: symbol' = symbol ^ x, x = 1..3.
-GSX_HD uint32_t sweep_nb(uint32_t b) { return b == 0 ? 1u : (b == 1 ? 7u : 16u); }
-GSX_HD uint32_t sweep_beginning(uint32_t nb, uint32_t i) {            // xor value for characters 0 (bits 0..1) and 1 (bits 2..3)
-    if (nb == 16u) return i;
-    if (nb == 1u) return 0u;
-    return i < 4u ? i : (i - 3u) << 2;                                  // 0,1,2,3,4,8,12
-}
+// listed in an xor table built on the host (sweep_make_plan): entry = xor value over characters 0 .. L-sb-1 (2 bits per
+// character; symbol' = symbol ^ x, x = 1..3) | number of substituted characters << 28.  Pass 1 lists the patterns that use
+// the budget B = M - h up (exactly B substitutions) -- nine tenths of all patterns at m = 3, and the cheapest to test
+// (one row mask); pass 0 the patterns that keep some budget (fewer than B).
 // substitutions between the guide's slice characters and slice beta
 GSX_HD uint32_t sweep_slice_distance(uint64_t q, uint32_t L, uint32_t sb, uint32_t beta) {
     const uint32_t top = (uint32_t)(q >> (2u * (L - sb))) & ((1u << (2u * sb)) - 1u);
     const uint32_t x = top ^ beta;
     return popc64((uint64_t)((x | (x >> 1)) & 0x55555555u));
 }
-// The patterns of the last group (j = B, exact beginning: nothing of the budget is left afterwards) are enumerated apart
-// from the others, because they are nine tenths of all patterns and need far less arithmetic (node_viable_exact):
-//   zero-budget pattern t = 0 .. mask_off[B+1] - mask_off[B] - 1   -> sweep_pattern_zero
-//   other pattern       t = 0 .. cum[B][B] - 1                      -> sweep_pattern (group j < B)
-GSX_HD uint32_t sweep_pattern_zero(const SweepPlan& pl, const uint32_t* masks, uint64_t q, uint32_t beta, uint32_t B, uint32_t t) {
+// pattern t of (guide q, slice beta, budget B) in pass `zero`: table index; `used` = substitutions outside the slice characters
+GSX_HD uint32_t sweep_pattern(const SweepPlan& pl, const uint32_t* xtab, uint32_t zero, uint64_t q, uint32_t beta, uint32_t B, uint32_t t, uint32_t& used) {
+    const uint32_t w = xtab[pl.xoff[zero][B] + t];
+    used = w >> 28;
     const uint32_t low_bits = 2u * (pl.L - pl.sb);
-    return (beta << low_bits) | (((uint32_t)q & ((1u << low_bits) - 1u)) ^ masks[pl.mask_off[B] + t]);
-}
-// pattern t of (guide q, slice beta, budget B): table index and total mismatches so far (h + j + extra - h is returned
-// as `used`, the substitutions outside the slice characters)
-GSX_HD uint32_t sweep_pattern(const SweepPlan& pl, const uint32_t* masks, uint64_t q, uint32_t beta, uint32_t B, uint32_t t, uint32_t& used) {
-    uint32_t j = 0;
-    while (j < B && t >= pl.cum[B][j + 1]) j++;
-    const uint32_t r = t - pl.cum[B][j], nb = sweep_nb(B - j);
-    const uint32_t mi = nb == 16u ? (r >> 4) : (nb == 7u ? r / 7u : r), bi = r - mi * nb;
-    const uint32_t ex = sweep_beginning(nb, bi);
-    used = j + ((ex & 3u) ? 1u : 0u) + ((ex >> 2) ? 1u : 0u);
-    const uint32_t low_bits = 2u * (pl.L - pl.sb);
-    const uint32_t low = ((uint32_t)q & ((1u << low_bits) - 1u)) ^ masks[pl.mask_off[j] + mi] ^ ex;
-    return (beta << low_bits) | low;
+    return (beta << low_bits) | (((uint32_t)q & ((1u << low_bits) - 1u)) ^ (w & 0x0FFFFFFFu));
 }
 
 // ordering of the matches of one guide: bucket (mismatches) ascending, forward index before reverse index, string order

@@ -46,7 +46,7 @@ bool load_gsx(const std::string& prefix, HostIndex& ix, std::string& err);
 
 struct DeviceStrand {
     DevStrand d{};
-    void* blocks = nullptr; void* lines = nullptr; void* filt = nullptr; void* ftab = nullptr; void* sa = nullptr; void* exc_rows = nullptr; void* exc_lf = nullptr; void* n_rows = nullptr;
+    void* blocks = nullptr; void* lines = nullptr; void* sum0 = nullptr; void* sum1 = nullptr; void* ftab = nullptr; void* sa = nullptr; void* exc_rows = nullptr; void* exc_lf = nullptr; void* n_rows = nullptr;
 };
 struct DeviceIndex {
     int device = 0;
@@ -110,9 +110,9 @@ struct Prepared {
 
 // every way to substitute at most M of the first n_pos characters (k-mer jump table enumeration, gsx_core.h)
 std::vector<uint64_t> ftab_combos(uint32_t n_pos, uint32_t M);
-// slice-major enumeration plan (gsx_core.h SweepPlan): xor-masks over characters 2 .. L-sb-1 with at most M substitutions,
-// sorted by substitution count, and the cumulative pattern counts per remaining budget
-void sweep_make_plan(uint32_t L, uint32_t sb, uint32_t M, SweepPlan& plan, std::vector<uint32_t>& masks);
+// slice-major enumeration plan (gsx_core.h sweep_pattern): the xor table of every way to substitute at most M of the
+// characters outside the slice, listed per pass and budget
+void sweep_make_plan(uint32_t L, uint32_t sb, uint32_t M, SweepPlan& plan, std::vector<uint32_t>& xtab);
 }  // namespace gsx
 
 struct gsx_result {

@@ -207,35 +207,37 @@ std::vector<uint64_t> ftab_combos(uint32_t n_pos, uint32_t M) {
     return out;
 }
 
-void sweep_make_plan(uint32_t L, uint32_t sb, uint32_t M, SweepPlan& plan, std::vector<uint32_t>& masks) {
+void sweep_make_plan(uint32_t L, uint32_t sb, uint32_t M, SweepPlan& plan, std::vector<uint32_t>& xtab) {
     memset(&plan, 0, sizeof plan);
     plan.L = L; plan.sb = sb; plan.M = M;
-    const uint32_t lo = 2, hi = L - sb;                     // characters lo .. hi-1 carry the masks
-    masks.clear();
+    const uint32_t n_pos = L - sb;                          // characters 0 .. n_pos-1 lie outside the slice
+    // every xor value with at most M substituted characters, grouped by their number
+    std::vector<std::vector<uint32_t>> by_count(M + 1);
     std::vector<uint32_t> pos;
-    for (uint32_t j = 0; j <= M; j++) {
-        plan.mask_off[j] = (uint32_t)masks.size();
-        if (j > hi - lo) continue;
-        // all position subsets of size j (increasing), each with 3^j xor values
-        pos.assign(j, 0); for (uint32_t t = 0; t < j; t++) pos[t] = lo + t;
+    for (uint32_t j = 0; j <= M && j <= n_pos; j++) {
+        pos.assign(j, 0); for (uint32_t t = 0; t < j; t++) pos[t] = t;
         for (;;) {
             uint32_t n_sub = 1; for (uint32_t t = 0; t < j; t++) n_sub *= 3;
             for (uint32_t code = 0; code < n_sub; code++) {
                 uint32_t m = 0, c = code;
                 for (uint32_t t = 0; t < j; t++) { m |= (1u + c % 3u) << (2u * pos[t]); c /= 3u; }
-                masks.push_back(m);
+                by_count[j].push_back(m | (j << 28));
             }
             int t = (int)j - 1;
-            while (t >= 0 && pos[t] == hi - j + t) t--;
+            while (t >= 0 && pos[t] == n_pos - j + t) t--;
             if (t < 0) break;
             pos[t]++; for (uint32_t u = t + 1; u < j; u++) pos[u] = pos[u - 1] + 1;
         }
     }
-    plan.mask_off[M + 1] = (uint32_t)masks.size();
+    xtab.clear();
     for (uint32_t B = 0; B <= M; B++) {
-        uint32_t acc = 0;
-        for (uint32_t j = 0; j <= B; j++) { plan.cum[B][j] = acc; acc += (plan.mask_off[j + 1] - plan.mask_off[j]) * sweep_nb(B - j); }
-        plan.cum[B][B + 1] = acc;
+        plan.xoff[1][B] = (uint32_t)xtab.size(); xtab.insert(xtab.end(), by_count[B].begin(), by_count[B].end());
+        plan.xcnt[1][B] = (uint32_t)xtab.size() - plan.xoff[1][B];
+    }
+    for (uint32_t B = 0; B <= M; B++) {
+        plan.xoff[0][B] = (uint32_t)xtab.size();
+        for (uint32_t j = 0; j < B; j++) xtab.insert(xtab.end(), by_count[j].begin(), by_count[j].end());
+        plan.xcnt[0][B] = (uint32_t)xtab.size() - plan.xoff[0][B];
     }
 }
 

@@ -365,24 +365,29 @@ __global__ void build_lookahead_kernel(DevStrand st, unsigned char* __restrict__
     }
 }
 
-// row-filter array of the sweep kernel: the planes t0..t6 of each look-ahead line, regrouped per 32 rows so that ONE
-// 32-byte load gives four characters of look-ahead (DevStrand::filt)
-__global__ void build_filter_kernel(const unsigned char* __restrict__ lines, unsigned char* __restrict__ filt, uint32_t n_blocks) {
-    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < 2ull * n_blocks; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t b = (uint32_t)(i >> 1), half = (uint32_t)(i & 1);
-        const uint64_t* line = reinterpret_cast<const uint64_t*>(lines + (size_t)b * 128);
-        uint32_t out[16];
-        for (int j = 0; j < 7; j++) {
-            const uint64_t hi = j == 0 ? line[2] : line[4 + 2 * (j - 1)], lo = j == 0 ? line[3] : line[5 + 2 * (j - 1)];
-            out[2 * j] = (uint32_t)(hi >> (32 * half)); out[2 * j + 1] = (uint32_t)(lo >> (32 * half));
-        }
-        out[14] = out[15] = 0;
-        uint4* dst = reinterpret_cast<uint4*>(filt + i * 64);
-        for (int k = 0; k < 4; k++) dst[k] = make_uint4(out[4 * k], out[4 * k + 1], out[4 * k + 2], out[4 * k + 3]);
+// pattern summaries of the sweep kernel (DevStrand::sum0/sum1): one thread per jump-table entry gathers the rows of its
+// interval from the look-ahead lines (at most two lines for the <= 32 rows it keeps)
+struct DevPlane {
+    const unsigned char* lines;
+    __device__ __forceinline__ uint64_t operator()(uint32_t b, uint32_t j, bool hi) const {
+        const uint64_t* line = reinterpret_cast<const uint64_t*>(lines + ((size_t)b << 7));
+        return __ldg(j == 0 ? line + (hi ? 2 : 3) : line + 4 + 2 * (j - 1) + (hi ? 0 : 1));
+    }
+};
+__global__ void build_summary_kernel(const FtabEntry* __restrict__ tab, const unsigned char* __restrict__ lines, unsigned char* __restrict__ sum0,
+                                     unsigned char* __restrict__ sum1, uint64_t n_entries) {
+    DevPlane plane; plane.lines = lines;
+    for (uint64_t e = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; e < n_entries; e += (uint64_t)gridDim.x * blockDim.x) {
+        const FtabEntry t = tab[e];
+        uint32_t s0[8], s1[8];
+        summary_build(plane, t.sp, t.width, s0, s1);
+        uint4* d0 = reinterpret_cast<uint4*>(sum0 + e * 32); uint4* d1 = reinterpret_cast<uint4*>(sum1 + e * 32);
+        d0[0] = make_uint4(s0[0], s0[1], s0[2], s0[3]); d0[1] = make_uint4(s0[4], s0[5], s0[6], s0[7]);
+        d1[0] = make_uint4(s1[0], s1[1], s1[2], s1[3]); d1[1] = make_uint4(s1[4], s1[5], s1[6], s1[7]);
     }
 }
-cudaError_t launch_build_filter(const unsigned char* lines, unsigned char* filt, uint32_t n_blocks, cudaStream_t s) {
-    build_filter_kernel<<<148 * 16, 256, 0, s>>>(lines, filt, n_blocks);
+cudaError_t launch_build_summary(const void* tab, const unsigned char* lines, unsigned char* sum0, unsigned char* sum1, uint64_t n_entries, cudaStream_t s) {
+    build_summary_kernel<<<148 * 16, 256, 0, s>>>((const FtabEntry*)tab, lines, sum0, sum1, n_entries);
     return cudaGetLastError();
 }
 
@@ -745,36 +750,34 @@ int search_fast_grid_warps(int variant, int sm_count) {
 // Work unit = (strand, slice, block of 32 guides), handed out slice-major through one counter, so that all warps work
 // on the same one or two slices at any time.  Inside a unit the 32 guides' pattern lists are flattened over the lanes.
 // ---------------------------------------------------------------------------------------------------------
-struct DevSectorLoader {
-    const unsigned char* filt;
-    __device__ __forceinline__ void operator()(uint32_t group, uint32_t k, uint32_t w[8]) const {
+struct DevSummaryLoader {
+    const unsigned char* sum0; const unsigned char* sum1;
+    __device__ __forceinline__ void operator()(uint32_t stage, uint32_t idx, uint32_t w[8]) const {
         asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"                                       // LDG.E.256
                      : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
-                     : "l"(filt + ((size_t)group << 6) + (k << 5)));
+                     : "l"((stage ? sum1 : sum0) + ((size_t)idx << 5)));
     }
 };
 
 struct SweepStats { uint32_t nodes, lookups, patterns, sectors, seeds; };
 
-// per-warp buffer of nodes that need another filter step (gsx_core.h node_step): 64 records in shared memory
-//   idx    table index of the pattern (sp, ep are re-read from the table if the node survives)
-//   blockw 32-row group to examine | (ep & 31) << 27 (last row of the node inside its second group)
-//   meta   plane codes (28 bits) | stage << 28 | part << 29 | has-second-block << 30
+// per-warp buffer of nodes that need the second summary sector (gsx_core.h summary_step1): 64 records in shared memory
+//   idx    table index of the pattern (sp, ep are read from the jump table if the node survives)
+//   codes  plane codes of its guide
 //   tlm    task | mismatches << 24 | remaining budget << 27
-//   u[r]   row masks of the filter
+//   u[r]   row masks of the filter after stage 0
 template <int NB>
 struct ContBuf {
-    uint32_t* idx; uint32_t* blockw; uint32_t* meta; uint32_t* tlm; uint32_t* u;      // u[r * 64 + slot]
-    uint32_t count;                                                                    // warp-uniform
+    uint32_t* idx; uint32_t* codes; uint32_t* tlm; uint32_t* u;      // u[r * 64 + slot]
+    uint32_t count;                                                  // warp-uniform
 };
-constexpr uint32_t CONT_STAGE = 1u << 28, CONT_PART = 1u << 29, CONT_HASB = 1u << 30;
 
 template <int NB>
-__device__ __forceinline__ void cont_push(ContBuf<NB>& cb, uint32_t lane, bool want, uint32_t idx, uint32_t blockw, uint32_t meta, uint32_t tlm, const uint32_t u[NB]) {
+__device__ __forceinline__ void cont_push(ContBuf<NB>& cb, uint32_t lane, bool want, uint32_t idx, uint32_t codes, uint32_t tlm, const uint32_t u[NB]) {
     const uint32_t m = __ballot_sync(0xffffffffu, want);
     if (want) {
         const uint32_t slot = cb.count + __popc(m & ((1u << lane) - 1u));
-        cb.idx[slot] = idx; cb.blockw[slot] = blockw; cb.meta[slot] = meta; cb.tlm[slot] = tlm;
+        cb.idx[slot] = idx; cb.codes[slot] = codes; cb.tlm[slot] = tlm;
 #pragma unroll
         for (int r = 0; r < NB; r++) cb.u[r * 64 + slot] = u[r];
     }
@@ -782,7 +785,8 @@ __device__ __forceinline__ void cont_push(ContBuf<NB>& cb, uint32_t lane, bool w
     __syncwarp();
 }
 
-__device__ __forceinline__ void sweep_emit(const SweepArgs& a, uint32_t lane, bool emit, uint32_t sp, uint32_t ep, uint32_t idx, uint32_t tlm, SweepStats& st) {
+// surviving level-L node -> seed queue; sp / ep come from the jump table (only survivors ever read it)
+__device__ __forceinline__ void sweep_emit(const SweepArgs& a, uint32_t lane, bool emit, uint32_t idx, uint32_t tlm, SweepStats& st) {
     const uint32_t emask = __ballot_sync(0xffffffffu, emit);
     if (!emask) return;
     uint32_t qbase = 0; const int leader = __ffs(emask) - 1;
@@ -791,62 +795,46 @@ __device__ __forceinline__ void sweep_emit(const SweepArgs& a, uint32_t lane, bo
     if (emit) {
         const uint32_t slot = qbase + __popc(emask & ((1u << lane) - 1u));
         if (slot < a.queue_cap) {
-            SeedNode sn; sn.sp = sp; sn.ep = ep; sn.idx = idx; sn.tlm = (tlm & 0x07FFFFFFu) | (a.plan.L << 27);
+            const FtabEntry* tab = reinterpret_cast<const FtabEntry*>((tlm & 1u) ? a.st[1].ftab : a.st[0].ftab);
+            const uint2 e = __ldg(reinterpret_cast<const uint2*>(tab + idx));
+            SeedNode sn; sn.sp = e.x; sn.ep = e.x + e.y - 1u; sn.idx = idx; sn.tlm = (tlm & 0x07FFFFFFu) | (a.plan.L << 27);
             a.queue[slot] = sn;
             st.seeds++;
         } else atomicOr(a.error_flag, GSX_KERR_QUEUE_OVERFLOW);
     }
 }
 
-// drain up to 32 parked nodes: one more filter step each, all lanes busy
+// drain up to 32 parked nodes: second summary sector, all lanes busy
 template <int NB>
 __device__ __forceinline__ void cont_process(const SweepArgs& a, ContBuf<NB>& cb, uint32_t lane, SweepStats& st) {
     const uint32_t n = cb.count < 32u ? cb.count : 32u;
     const bool mine = lane < n;
-    uint32_t idx = 0, blockw = 0, meta = 0, tlm = 0; uint32_t u[NB];
+    uint32_t idx = 0, codes = 0, tlm = 0; uint32_t u[NB];
 #pragma unroll
     for (int r = 0; r < NB; r++) u[r] = 0;
     if (mine) {
         const uint32_t slot = cb.count - n + lane;
-        idx = cb.idx[slot]; blockw = cb.blockw[slot]; meta = cb.meta[slot]; tlm = cb.tlm[slot];
+        idx = cb.idx[slot]; codes = cb.codes[slot]; tlm = cb.tlm[slot];
 #pragma unroll
         for (int r = 0; r < NB; r++) u[r] = cb.u[r * 64 + slot];
     }
     __syncwarp();
     cb.count -= n;
-    const uint32_t strand = tlm & 1u, codes = meta & 0x0FFFFFFFu, stage = (meta & CONT_STAGE) ? 1u : 0u;
-    DevSectorLoader ld; ld.filt = strand ? a.st[1].filt : a.st[0].filt;
-    uint32_t sectors = 0;
-    if (mine) node_step<NB>(ld, blockw & 0x07FFFFFFu, stage, codes, u, sectors);
-    st.sectors += sectors;
-    const bool alive = mine && u[0] != 0u;
-    const bool again = alive && stage == 0u && sweep_has_stage1(codes);                  // second sector of the same group
-    const bool second = mine && !alive && !(meta & CONT_PART) && (meta & CONT_HASB);     // first group is dead: try the second one
-    const bool emit = alive && !again;
-    uint32_t sp = 0, ep = 0;
-    if (emit) {
-        const FtabEntry* tab = reinterpret_cast<const FtabEntry*>(strand ? a.st[1].ftab : a.st[0].ftab);
-        const uint2 e = __ldg(reinterpret_cast<const uint2*>(tab + idx)); sp = e.x; ep = e.x + e.y - 1u;
+    if (mine) {
+        DevSummaryLoader ld; ld.sum0 = nullptr; ld.sum1 = (tlm & 1u) ? a.st[1].sum1 : a.st[0].sum1;
+        summary_step1<NB>(ld, idx, codes, u);
+        st.sectors++;
     }
-    sweep_emit(a, lane, emit, sp, ep, idx, tlm, st);
-    if (second) {
-        const uint32_t budget = (tlm >> 27) & 7u, rows = rows_mask32(0u, blockw >> 27);
-#pragma unroll
-        for (int r = 0; r < NB; r++) u[r] = budget >= (uint32_t)r ? rows : 0u;
-        blockw = (blockw & 0x07FFFFFFu) + 1u; meta = (meta & ~CONT_STAGE) | CONT_PART;
-    }
-    if (again) meta |= CONT_STAGE;
-    cont_push<NB>(cb, lane, again || second, idx, blockw, meta, tlm, u);
+    sweep_emit(a, lane, mine && u[0] != 0u, idx, tlm, st);
 }
 
 // one flattened pass over the patterns of 32 guides in one slice: lane g owns n_mine patterns of guide (gb * 32 + g);
-// ZERO = the zero-budget group (sweep_pattern_zero, one filter mask), else the groups with budget left
+// ZERO = the patterns that use their budget up (one filter mask), else the patterns with budget left
 template <bool ZERO, int NB>
 __device__ __forceinline__ void sweep_pass(const SweepArgs& a, const SweepPlan& pl, ContBuf<NB>& cb, uint32_t lane, uint32_t strand, uint32_t beta, uint32_t gb,
                                            uint32_t qlow, uint32_t codes, int B, uint32_t n_mine, SweepStats& st) {
     const uint32_t FULL = 0xffffffffu, M = a.M;
-    const FtabEntry* tab = reinterpret_cast<const FtabEntry*>(strand ? a.st[1].ftab : a.st[0].ftab);
-    DevSectorLoader ld; ld.filt = strand ? a.st[1].filt : a.st[0].filt;
+    DevSummaryLoader ld; ld.sum0 = strand ? a.st[1].sum0 : a.st[0].sum0; ld.sum1 = nullptr;
     uint32_t incl = n_mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(FULL, incl, o); if (lane >= (uint32_t)o) incl += y; }
@@ -864,70 +852,53 @@ __device__ __forceinline__ void sweep_pass(const SweepArgs& a, const SweepPlan& 
         }
         const uint32_t oq = __shfl_sync(FULL, qlow, o), ocodes = __shfl_sync(FULL, codes, o), oexcl = __shfl_sync(FULL, excl, o);
         const int oB = __shfl_sync(FULL, B, o);
-        bool emit = false, park = false; uint32_t sp = 0, ep = 0, idx = 0, mm = M, blockw = 0, meta = 0;
+        bool emit = false, park = false; uint32_t idx = 0, mm = M;
         uint32_t u[NB];
 #pragma unroll
         for (int r = 0; r < NB; r++) u[r] = 0;
         if (active) {
-            if (ZERO) idx = sweep_pattern_zero(pl, a.masks, (uint64_t)oq, beta, (uint32_t)oB, it - oexcl);
-            else { uint32_t used; idx = sweep_pattern(pl, a.masks, (uint64_t)oq, beta, (uint32_t)oB, it - oexcl, used); mm = M - (uint32_t)oB + used; }
-            const uint2 e = __ldg(reinterpret_cast<const uint2*>(tab + idx));
-            st.patterns++;
+            uint32_t used;
+            idx = sweep_pattern(pl, a.xtab, ZERO ? 1u : 0u, (uint64_t)oq, beta, (uint32_t)oB, it - oexcl, used);
+            if (!ZERO) mm = M - (uint32_t)oB + used;                          // (the other pass always ends at M)
+            uint32_t valid, info;
+            if (ZERO) { uint32_t v[1]; info = summary_step0<1>(ld, idx, ocodes, 0u, v, valid); u[0] = v[0]; }
+            else info = summary_step0<NB>(ld, idx, ocodes, M - mm, u, valid);
+            st.patterns++; st.sectors++;
             if (((idx ^ oq) & 15u) == 0u) st.lookups++;                       // one table line per 16 beginnings
-            if (e.y) {
-                sp = e.x; ep = e.x + e.y - 1u;
-                const uint32_t e1 = ep + 1u, gs = sp >> 5, ge = e1 >> 5;
-                st.nodes++; st.lookups += (e1 >> 6) != (sp >> 6) ? 2u : 1u;
-                if (ge - gs > 1u) emit = true;                                // too wide for the filter: the tree search takes it as is
-                else {
-                    const uint32_t rows = rows_mask32(sp & 31u, ge != gs ? 31u : (ep & 31u));
-                    const bool hasB = ge != gs && (e1 & 31u) != 0u;
-                    uint32_t sectors = 0;
-                    if (ZERO) { uint32_t v[1] = {rows}; node_step<1>(ld, gs, 0u, ocodes, v, sectors); u[0] = v[0]; }
-                    else {
-#pragma unroll
-                        for (int r = 0; r < NB; r++) u[r] = (M - mm) >= (uint32_t)r ? rows : 0u;
-                        node_step<NB>(ld, gs, 0u, ocodes, u, sectors);
-                    }
-                    st.sectors += sectors;
-                    blockw = gs | ((ep & 31u) << 27); meta = ocodes | (hasB ? CONT_HASB : 0u);
-                    if (u[0]) { if (sweep_has_stage1(ocodes)) { park = true; meta |= CONT_STAGE; } else emit = true; }
-                    else if (hasB) {                                          // nothing left in the first group: park the second one
-                        const uint32_t rowsB = rows_mask32(0u, ep & 31u);
-#pragma unroll
-                        for (int r = 0; r < NB; r++) u[r] = (M - mm) >= (uint32_t)r ? rowsB : 0u;
-                        park = true; blockw += 1u; meta |= CONT_PART;
-                    }
-                }
+            if (valid) {
+                st.nodes++; st.lookups += (info & SUM_TWO_BLOCKS) ? 2u : 1u;
+                if (info & SUM_WIDE) emit = true;                             // not summarised: the tree search takes it as is
+                else if (u[0]) { if (sweep_has_stage1(ocodes)) park = true; else emit = true; }
             }
         }
         const uint32_t tlm = (((gb * 32u + o) << 1) | strand) | (mm << 24) | ((M - mm) << 27);
-        sweep_emit(a, lane, emit, sp, ep, idx, tlm, st);
-        cont_push<NB>(cb, lane, park, idx, blockw, meta, tlm, u);
+        sweep_emit(a, lane, emit, idx, tlm, st);
+        cont_push<NB>(cb, lane, park, idx, ocodes, tlm, u);
     }
 }
 
 template <int WARPS, int MINB, int NB>
 __global__ void __launch_bounds__(WARPS * 32, MINB) sweep_kernel(SweepArgs a) {
     __shared__ SweepPlan s_plan;
-    __shared__ uint32_t s_c32[WARPS][4][64];
+    __shared__ uint32_t s_c32[WARPS][3][64];
     __shared__ uint32_t s_cu[WARPS][NB][64];
     for (int i = threadIdx.x; i < (int)(sizeof(SweepPlan) / 4); i += blockDim.x)
         reinterpret_cast<uint32_t*>(&s_plan)[i] = reinterpret_cast<const uint32_t*>(&a.plan)[i];
     __syncthreads();
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, FULL = 0xffffffffu;
     ContBuf<NB> cb;
-    cb.idx = s_c32[warp][0]; cb.blockw = s_c32[warp][1]; cb.meta = s_c32[warp][2]; cb.tlm = s_c32[warp][3]; cb.u = &s_cu[warp][0][0]; cb.count = 0;
+    cb.idx = s_c32[warp][0]; cb.codes = s_c32[warp][1]; cb.tlm = s_c32[warp][2]; cb.u = &s_cu[warp][0][0]; cb.count = 0;
     const uint32_t L = s_plan.L, sb = s_plan.sb, M = a.M;
     const uint32_t n_slices = 1u << (2u * sb), n_gb = (a.n_guides + 31u) >> 5;
     const uint64_t items_per_strand = (uint64_t)n_slices * n_gb, n_items = 2ull * items_per_strand;
     unsigned long long n_nodes = 0, n_lookups = 0, n_patterns = 0, n_sectors = 0, n_seeds = 0;
     SweepStats st = {0, 0, 0, 0, 0};
+    uint32_t next_item = 0;
+    if (lane == 0) next_item = atomicAdd(a.item_counter, 1u);
     for (;;) {
-        uint32_t item = 0;
-        if (lane == 0) item = atomicAdd(a.item_counter, 1u);
-        item = __shfl_sync(FULL, item, 0);
+        const uint32_t item = __shfl_sync(FULL, next_item, 0);
         if ((uint64_t)item >= n_items) break;
+        if (lane == 0) next_item = atomicAdd(a.item_counter, 1u);            // fetched while this unit is being worked on
         const uint32_t strand = (uint64_t)item >= items_per_strand ? 1u : 0u;
         const uint32_t rem = item - (strand ? (uint32_t)items_per_strand : 0u);
         const uint32_t beta = rem / n_gb, gb = rem - beta * n_gb;
@@ -937,9 +908,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) sweep_kernel(SweepArgs a) {
         const uint32_t h = sweep_slice_distance(q, L, sb, beta);
         const int B = (valid && h <= M) ? (int)(M - h) : -1;
         const uint32_t codes = sweep_codes(q, L, a.plen, a.pampack);
-        // the zero-budget group first (most of the patterns, cheapest arithmetic), then the groups with budget left
-        sweep_pass<true, NB>(a, s_plan, cb, lane, strand, beta, gb, (uint32_t)q, codes, B, B >= 0 ? s_plan.mask_off[B + 1] - s_plan.mask_off[B] : 0u, st);
-        sweep_pass<false, NB>(a, s_plan, cb, lane, strand, beta, gb, (uint32_t)q, codes, B, B >= 0 ? s_plan.cum[B][B] : 0u, st);
+        // the patterns without budget left first (most of them, cheapest arithmetic), then the others
+        sweep_pass<true, NB>(a, s_plan, cb, lane, strand, beta, gb, (uint32_t)q, codes, B, B >= 0 ? s_plan.xcnt[1][B] : 0u, st);
+        sweep_pass<false, NB>(a, s_plan, cb, lane, strand, beta, gb, (uint32_t)q, codes, B, B >= 0 ? s_plan.xcnt[0][B] : 0u, st);
         n_nodes += st.nodes; n_lookups += st.lookups; n_patterns += st.patterns; n_sectors += st.sectors; n_seeds += st.seeds;
         st = {0, 0, 0, 0, 0};
     }

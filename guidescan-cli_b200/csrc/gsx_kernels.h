@@ -50,7 +50,7 @@ struct SweepArgs {
     const uint8_t* skip;
     uint32_t n_guides;
     SweepPlan plan;
-    const uint32_t* masks;
+    const uint32_t* xtab;              // gsx_core.h sweep_pattern
     uint32_t M, plen, pampack;
     uint32_t counting;                 // unused by the filter itself; kept for symmetry
     SeedNode* queue; uint32_t queue_cap;
@@ -87,8 +87,8 @@ cudaError_t upload_cfd_tables();
 // k-mer jump table of depth L for one strand; tab and tmp must each hold 4^L entries of 8 bytes; result ends up in tab
 cudaError_t launch_build_ftab(const DevStrand& st, uint32_t L, void* tab, void* tmp, cudaStream_t s);
 cudaError_t launch_build_lookahead(const DevStrand& src, unsigned char* lines, uint32_t n_blocks, cudaStream_t s);
-// look-ahead lines -> row-filter array of the sweep kernel (filt must hold n_blocks * 128 bytes)
-cudaError_t launch_build_filter(const unsigned char* lines, unsigned char* filt, uint32_t n_blocks, cudaStream_t s);
+// jump table + look-ahead lines -> pattern summaries of the sweep kernel (sum0, sum1: 32 bytes per table entry each)
+cudaError_t launch_build_summary(const void* tab, const unsigned char* lines, unsigned char* sum0, unsigned char* sum1, uint64_t n_entries, cudaStream_t s);
 int search_grid_warps(bool wide, int variant, int sm_count);
 cudaError_t launch_search(const SearchArgs& a, bool wide, int variant, int sm_count, cudaStream_t s, int* warps_total);
 int search_fast_grid_warps(int variant, int sm_count);

@@ -59,10 +59,14 @@ struct DevStrand {
     uint32_t ftab_L;
     const unsigned char* lines;    // optional second copy, one 128-byte line per 64 rows: OccBlock + six look-ahead symbol
                                    // planes (see build_lookahead_kernel); nullptr if absent
-    const unsigned char* filt;     // optional row-filter array of the sweep kernel, 64 bytes per 32 rows: sector 0 = the 2-bit
-                                   // symbols t0..t3 of those rows as 32-bit plane pairs (hi, lo), sector 1 = t4..t6 (+ 8 bytes of
-                                   // padding): the next seven characters a backward search from each row would consume, four of
-                                   // them behind ONE 32-byte load (see build_filter_kernel); nullptr if absent
+    const unsigned char* sum0;     // optional pattern summaries of the sweep kernel, 32 bytes per jump-table entry (same index):
+    const unsigned char* sum1;     //   sum0[e] = {valid rows (bit i = row sp + i, i < 32), info, hi/lo planes of t0, t1, t2}
+                                   //   sum1[e] = {hi/lo planes of t3, t4, t5, t6}
+                                   // t_j = the character a backward search from that row consumes j steps ahead (as in `lines`),
+                                   // aligned to the START of the entry's interval, so one 32-byte load indexed by the pattern
+                                   // itself replaces the table entry + look-ahead line reads.  info bit 0: the interval has more
+                                   // than 32 rows (not summarised: such a node goes to the tree search unexamined), bit 1: it
+                                   // straddles two 64-row blocks (statistics only); nullptr if absent (see build_summary_kernel)
 };
 
 GSX_HD const OccBlock* block_ptr(const DevStrand& st, uint32_t b) {
@@ -109,8 +113,10 @@ struct Chrom { uint64_t start; uint64_t length; };
 // slice-major enumeration plan of the sweep kernel (gsx_core.h)
 struct SweepPlan {
     uint32_t L, sb, M;
-    uint32_t mask_off[kMaxDist + 2];                // start of group j in `masks`; mask_off[M + 1] = total
-    uint32_t cum[kMaxDist + 1][kMaxDist + 2];       // cum[B][j] = patterns of groups < j under budget B; cum[B][B + 1] = n(B)
+    // xoff[z][B] = start, in the xor table, of the patterns of pass z (0: patterns that keep some budget, 1: patterns that
+    // use the budget up) under budget B; xcnt[z][B] = their number
+    uint32_t xoff[2][kMaxDist + 1];
+    uint32_t xcnt[2][kMaxDist + 1];
 };
 
 // node meta word

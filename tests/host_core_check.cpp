@@ -101,18 +101,23 @@ struct HostSectorLoader {            // whole 64-row lines (node_viable / node_v
         else for (int u = 0; u < 4; u++) w[u] = (*look)[(size_t)b * 12 + 4 * (k - 1) + u];      // hi_(2k-1), lo_(2k-1), hi_2k, lo_2k
     }
 };
-struct HostFilterLoader {            // 32-row groups of the filter array (what build_filter_kernel writes): node_step
+// pattern summaries (what build_summary_kernel writes), built on the host through the same summary_build
+static std::vector<uint32_t> g_sum0[2], g_sum1[2];
+struct HostPlane {
     const DevStrand* st; const std::vector<uint64_t>* look;
-    void operator()(uint32_t group, uint32_t k, uint32_t w[8]) const {
-        const uint32_t b = group >> 1, half = group & 1;
-        for (uint32_t t = 0; t < 4; t++) {
-            const uint32_t j = 4 * k + t;
-            uint64_t hi = 0, lo = 0;
-            if (j == 0) { hi = st->blocks[b].hi; lo = st->blocks[b].lo; }
-            else if (j <= 6) { hi = (*look)[(size_t)b * 12 + 2 * (j - 1)]; lo = (*look)[(size_t)b * 12 + 2 * (j - 1) + 1]; }
-            w[2 * t] = (uint32_t)(hi >> (32 * half)); w[2 * t + 1] = (uint32_t)(lo >> (32 * half));
-        }
+    uint64_t operator()(uint32_t b, uint32_t j, bool hi) const {
+        if (j == 0) return hi ? st->blocks[b].hi : st->blocks[b].lo;
+        return (*look)[(size_t)b * 12 + 2 * (j - 1) + (hi ? 0 : 1)];
     }
+};
+static void build_summaries_host(const DevStrand& st, const std::vector<uint64_t>& look, const std::vector<FtabEntry>& tab, std::vector<uint32_t>& s0, std::vector<uint32_t>& s1) {
+    s0.assign(tab.size() * 8, 0); s1.assign(tab.size() * 8, 0);
+    HostPlane plane{&st, &look};
+    for (size_t e = 0; e < tab.size(); e++) summary_build(plane, tab[e].sp, tab[e].width, &s0[e * 8], &s1[e * 8]);
+}
+struct HostSummaryLoader {
+    const std::vector<uint32_t>* s0; const std::vector<uint32_t>* s1;
+    void operator()(uint32_t stage, uint32_t idx, uint32_t w[8]) const { for (int i = 0; i < 8; i++) w[i] = (stage ? *s1 : *s0)[(size_t)idx * 8 + i]; }
 };
 static void sweep_host(const DevStrand st[2], const Prepared& prep, uint32_t M) {
     const uint32_t L = g_ftab_L, sb = g_sweep_sb; const size_t n = prep.recs.size();
@@ -120,7 +125,7 @@ static void sweep_host(const DevStrand st[2], const Prepared& prep, uint32_t M) 
     std::vector<std::vector<Node>>& g_seeds = g_seeds_by_M[M]; g_seeds.assign(2 * n, {});
     static std::vector<uint64_t> combos; combos = ftab_combos(L - 2, M);
     for (uint32_t strand = 0; strand < 2; strand++) {
-        HostSectorLoader ld{&st[strand], &g_look[strand]}; HostFilterLoader ldf{&st[strand], &g_look[strand]};
+        HostSectorLoader ld{&st[strand], &g_look[strand]}; HostSummaryLoader lds{&g_sum0[strand], &g_sum1[strand]};
         std::vector<std::vector<std::pair<uint32_t, uint32_t>>> seen(n);
         for (uint32_t beta = 0; beta < (1u << (2 * sb)); beta++)
             for (size_t g = 0; g < n; g++) {
@@ -130,10 +135,11 @@ static void sweep_host(const DevStrand st[2], const Prepared& prep, uint32_t M) 
                 if (h > M) continue;
                 const uint32_t B = M - h;
                 for (int zero = 1; zero >= 0; zero--) {
-                    const uint32_t n_pat = zero ? plan.mask_off[B + 1] - plan.mask_off[B] : plan.cum[B][B];
+                    const uint32_t n_pat = plan.xcnt[zero][B];
                     for (uint32_t t = 0; t < n_pat; t++) {
                         uint32_t used = B;
-                        const uint32_t idx = zero ? sweep_pattern_zero(plan, masks.data(), q, beta, B, t) : sweep_pattern(plan, masks.data(), q, beta, B, t, used);
+                        const uint32_t idx = sweep_pattern(plan, masks.data(), (uint32_t)zero, q, beta, B, t, used);
+                        if (zero && used != B) { fprintf(stderr, "pass 1 pattern keeps budget\n"); exit(3); }
                         const uint32_t mm = h + used;
                         seen[g].push_back({idx, mm});
                         const FtabEntry& e = g_ftab[strand][idx];
@@ -141,13 +147,11 @@ static void sweep_host(const DevStrand st[2], const Prepared& prep, uint32_t M) 
                         uint32_t sectors = 0;
                         const bool ok = zero ? node_viable_exact(ld, e.sp, e.sp + e.width - 1, L, qlen, qlen + prep.plen, q, prep.pampack, sectors)
                                              : node_viable<kMaxDist>(ld, e.sp, e.sp + e.width - 1, L, qlen, qlen + prep.plen, q, prep.pampack, M - mm, sectors);
-                        bool ok2;
-                        {   // the resumable form the kernel runs (node_step) must agree with the whole-node forms
-                            uint32_t s2 = 0;
-                            ok2 = node_viable_steps<kMaxDist>(ldf, e.sp, e.sp + e.width - 1, sweep_codes(q, L, prep.plen, prep.pampack), M - mm, s2);
-                            if (ok2 != ok && !(ok2 && (((e.sp + e.width) >> 5) - (e.sp >> 5)) > 1u)) {      /* (a node over three 32-row groups is passed through unexamined) */ fprintf(stderr, "node_step disagrees with node_viable (idx %u zero %d ok %d ok2 %d sp %u w %u budget %u codes %x)\n", idx, zero, (int)ok, (int)ok2, e.sp, e.width, M - mm, sweep_codes(q, L, prep.plen, prep.pampack)); exit(3); }
-                            if (zero) { uint32_t s3 = 0; if (node_viable_steps<1>(ldf, e.sp, e.sp + e.width - 1, sweep_codes(q, L, prep.plen, prep.pampack), 0, s3) != ok) { fprintf(stderr, "node_step<1> disagrees (idx %u)\n", idx); exit(3); } }
-                        }
+                        // what the kernel runs (summary_step0/1 over the pattern summaries) must agree with the row-by-row forms
+                        const uint32_t codes = sweep_codes(q, L, prep.plen, prep.pampack);
+                        const bool ok2 = summary_viable<kMaxDist>(lds, idx, codes, M - mm);
+                        if (e.width <= 32 ? ok2 != ok : !ok2) { fprintf(stderr, "summary filter disagrees with node_viable (idx %u zero %d ok %d ok2 %d sp %u w %u budget %u)\n", idx, zero, (int)ok, (int)ok2, e.sp, e.width, M - mm); exit(3); }
+                        if (zero && summary_viable<1>(lds, idx, codes, 0) != ok2) { fprintf(stderr, "summary filter <1> disagrees (idx %u)\n", idx); exit(3); }
                         if (!ok2) continue;
                         Node nd{}; nd.sp = e.sp; nd.ep = e.sp + e.width - 1; nd.key_lo = ftab_key(idx, q, L); nd.task = (uint32_t)(2 * g + strand);
                         nd.meta = meta_make(L, mm, 0, 0, 0, 0, 0);
@@ -280,6 +284,7 @@ int main(int argc, char** argv) {
         if (!prep.fast_ok) { fprintf(stderr, "--lookahead needs a fast-path batch (one PAM, ACGT guides, no bulges)\n"); return 2; }
         build_look(st[0], g_look[0]); build_look(st[1], g_look[1]);
     }
+    if (g_sweep_sb) for (int s = 0; s < 2; s++) build_summaries_host(st[s], g_look[s], g_ftab[s], g_sum0[s], g_sum1[s]);
 
     // ---- search + order + expand (what search_kernel / order_matches_kernel / expand_hits_kernel do) ----------------
     std::vector<uint8_t> dropped(n, 0);

@@ -52,7 +52,9 @@ def test_lookahead_pruning_keeps_output_and_cuts_nodes(harness, tmp_path, m):
     nodes = {}
     for tag, extra in (("plain", []), ("look", ["--lookahead"]), ("ftab", ["--ftab", "7"]), ("both", ["--lookahead", "--ftab", "8"]),
                        ("sweep1", ["--lookahead", "--ftab", "8", "--sweep", "1"]), ("sweep3", ["--lookahead", "--ftab", "8", "--sweep", "3"]),
-                       ("sweep5", ["--lookahead", "--ftab", "9", "--sweep", "5"])):
+                       ("sweep5", ["--lookahead", "--ftab", "9", "--sweep", "5"]),
+                       # shallow tables: intervals of ~24 and ~98 rows, i.e. summaries with and without the "wide" pass-through
+                       ("sweepw", ["--lookahead", "--ftab", "7", "--sweep", "2"]), ("sweepww", ["--lookahead", "--ftab", "6", "--sweep", "1"])):
         out = os.path.join(d, tag + ".out")
         r = subprocess.run([harness, os.path.join(d, "la"), gcsv, out, "-m", str(m)] + extra, capture_output=True, text=True, check=True)
         assert open(out, "rb").read() == open(os.path.join(d, "o.out"), "rb").read()
