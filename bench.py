@@ -202,7 +202,9 @@ def run_gsx(args):
             name, _, pin = item.partition("@")          # "f1@64": specialised kernel variant 1 with a 64 MB L2 residency budget
             if name[0] == "s":                          # "s5v2": slice-major front end, 5 slice characters, sweep kernel variant 2; "s0": off
                 sb, _, var = name[1:].partition("v")
-                env = {"GSX_FORCE_GENERAL": "0", "GSX_SWEEP": "0" if sb == "0" else "1", "GSX_SWEEP_SB": sb, "GSX_SWEEP_VARIANT": var or "0"}
+                var, _, parts = var.partition("p")          # "s5v2p4": ... each (slice, 32 guides) unit cut into 4 work units
+                env = {"GSX_FORCE_GENERAL": "0", "GSX_SWEEP": "0" if sb == "0" else "1", "GSX_SWEEP_SB": sb, "GSX_SWEEP_VARIANT": var or "0",
+                       "GSX_SWEEP_PARTS": parts or "0"}
             else:
                 env = {"GSX_FORCE_GENERAL": "1", "GSX_SEARCH_VARIANT": name[1:]} if name[0] == "g" else {"GSX_FORCE_GENERAL": "0", "GSX_FAST_VARIANT": name[1:]}
             if pin:
@@ -217,7 +219,7 @@ def run_gsx(args):
             log(json.dumps({"variant": item, "ms_search": best["ms_search"], "guides_per_s_search": per / best["ms_search"] * 1e3,
                             "glookups_per_s": best["lookups"] / best["ms_search"] / 1e6, "spills": best["spills"], "nodes": best["nodes"],
                             "ms_sweep": best["ms_sweep"], "seeds": best["seeds"], "lookups": best["lookups"]}))
-        for k in ("GSX_FORCE_GENERAL", "GSX_SEARCH_VARIANT", "GSX_FAST_VARIANT", "GSX_L2_PIN_MB", "GSX_SWEEP", "GSX_SWEEP_SB", "GSX_SWEEP_VARIANT"):
+        for k in ("GSX_FORCE_GENERAL", "GSX_SEARCH_VARIANT", "GSX_FAST_VARIANT", "GSX_L2_PIN_MB", "GSX_SWEEP", "GSX_SWEEP_SB", "GSX_SWEEP_VARIANT", "GSX_SWEEP_PARTS"):
             os.environ.pop(k, None)
         apply_variant(args)
     for s in range(args.warmup):
@@ -280,7 +282,8 @@ def run_gsx(args):
                          "ms_search": ctr_tot["ms_search"] / args.steps, "ms_sweep": ctr_tot["ms_sweep"] / args.steps,
                          "seeds_per_guide": ctr_tot["seeds"] / (per * args.steps), "ms_arrange": ctr_tot["ms_arrange"] / args.steps,
                          "ms_locate": ctr_tot["ms_locate"] / args.steps, "ms_score": ctr_tot["ms_score"] / args.steps,
-                         "ms_d2h": ctr_tot["ms_d2h"] / args.steps},
+                         "ms_d2h": ctr_tot["ms_d2h"] / args.steps, "ms_h2d": ctr_tot["ms_h2d"] / args.steps,
+                         "ms_host_prepare": ctr_tot["ms_prepare"] / args.steps, "ms_call_wall": ctr_tot["ms_wall"] / args.steps},
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -477,7 +477,7 @@ static void run_device_job(DeviceJob* job) {
             sweep_sb = 1; while (sweep_sb < ftab_L - 3 && per_strand / std::pow(4.0, (double)sweep_sb) > target) sweep_sb++;
             if (env_int("GSX_SWEEP_SB", 0) > 0) sweep_sb = (uint32_t)env_int("GSX_SWEEP_SB", 0);
             if (sweep_sb < 1 || sweep_sb + 3 > ftab_L) use_sweep = false;
-            if (2.0 * std::pow(4.0, (double)sweep_sb) * ((n + 31) / 32) >= 4.0e9) use_sweep = false;
+            if (2.0 * std::pow(4.0, (double)sweep_sb) * ((n + 31) / 32) * 8.0 >= 4.0e9) use_sweep = false;
         }
         uint64_t queue_cap = std::max<uint64_t>((uint64_t)n * 1024, 1u << 20);
         if (env_int("GSX_QUEUE_CAP", 0) > 0) queue_cap = (uint64_t)env_int("GSX_QUEUE_CAP", 0);
@@ -493,7 +493,15 @@ static void run_device_job(DeviceJob* job) {
                 CK(cudaMemcpyAsync(d_xtab, xtab.data(), xtab.size() * 4, cudaMemcpyHostToDevice, s)); CK(cudaStreamSynchronize(s));
                 if (!d_queue) d_queue = B.alloc<SeedNode>(queue_cap);
                 w.st[0] = m.st[0]; w.st[1] = m.st[1]; w.gq = m.gq; w.skip = m.skip; w.n_guides = n; w.xtab = d_xtab;
-                w.M = m.p.M; w.plen = m.plen; w.pampack = m.pampack; w.counting = m.p.counting;
+                w.M = m.p.M; w.plen = m.plen; w.pampack = m.pampack;
+                {   // enough work units per slice that the whole grid stays within about one slice (L2 residency)
+                    const int sv = env_int("GSX_SWEEP_VARIANT", 2);
+                    const uint32_t warps = (uint32_t)di.sm_count * 8u * (sv == 0 ? 3u : sv == 1 ? 2u : sv == 2 ? 4u : sv == 3 ? 6u : sv == 5 ? 5u : 8u);
+                    const uint32_t n_gb = (n + 31) / 32;
+                    uint32_t parts = (warps + n_gb - 1) / n_gb; if (parts < 1) parts = 1; if (parts > 8) parts = 8;
+                    if (env_int("GSX_SWEEP_PARTS", 0) > 0) parts = (uint32_t)env_int("GSX_SWEEP_PARTS", 0);
+                    w.parts = parts;
+                }
                 w.queue = d_queue; w.queue_cap = (uint32_t)queue_cap; w.queue_count = d_ctrs + 3; w.item_counter = d_ctrs + 4;
                 w.error_flag = d_ctrs + 2; w.stats = d_stats;
                 CK(launch_sweep(w, env_int("GSX_SWEEP_VARIANT", 2), di.sm_count, s)); n_launches++;
@@ -689,8 +697,10 @@ extern "C" int gsx_enumerate(const gsx_index* ix, const gsx_guide* guides, size_
     *out = nullptr;
     if (ix->dev.empty()) return fail(GSX_ERR_NO_DEVICE, "index is not resident on any device");
     if (n_guides >= (1ull << 30)) return fail(GSX_ERR_ARG, "too many guides in one call");
+    const auto t_call = std::chrono::steady_clock::now();
     Prepared prep;
     if (int rc = gsx_prepare_guides(guides, n_guides, p, prep)) return rc;
+    const double ms_prepare = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call).count();
     const size_t nd = ix->dev.size();
     // guides are independent: contiguous shards per device, no data-path collective
     std::vector<DeviceJob> jobs(nd);
@@ -715,6 +725,8 @@ extern "C" int gsx_enumerate(const gsx_index* ix, const gsx_guide* guides, size_
         c.ms_total_device = std::max(c.ms_total_device, j.ctr.ms_total_device); c.ms_h2d = std::max(c.ms_h2d, j.ctr.ms_h2d); c.ms_d2h = std::max(c.ms_d2h, j.ctr.ms_d2h);
     }
     gsx_build_view(r);
+    r->counters.ms_prepare = ms_prepare;
+    r->counters.ms_wall = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call).count();
     *out = r;
     return GSX_OK;
 }

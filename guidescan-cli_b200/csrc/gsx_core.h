@@ -500,9 +500,9 @@ GSX_HD bool node_viable_exact(LoadSector ld, uint32_t sp, uint32_t ep, uint32_t 
 //          protospacer (anything else costs one mismatch), 8..11 = that symbol in the PAM (anything else kills the row),
 //          12 = PAM wildcard, 13 = kills every row, 7 = no such level.
 //   u[r]:  rows with at most budget - r mismatches so far (r = 0 .. NB-1, NB > budget); u[0] = rows still alive.
-//   summary_step: stage 0 = sum0 (valid rows + planes t0,t1,t2), stage 1 = sum1 (planes t3..t6); lanes of a warp disagree on
-//          whether stage 1 is needed (1 node in 6), so the kernel parks those nodes in a per-warp buffer and drains it 32 at
-//          a time, all lanes busy.
+//   One 32-byte sector holds all seven levels for 16 rows (sum0: rows 0..15 of the interval, sum1: rows 16..31), so a single
+//          load settles nine nodes out of ten; lanes whose node has more than 16 rows and found nothing among the first 16
+//          park it in a per-warp buffer that is drained 32 at a time, all lanes busy.
 GSX_HD uint32_t sweep_codes(uint64_t q, uint32_t L, uint32_t plen, uint32_t pampack) {
     const uint32_t qlen = (uint32_t)(q >> 58);
     uint32_t codes = 0;
@@ -516,20 +516,30 @@ GSX_HD uint32_t sweep_codes(uint64_t q, uint32_t L, uint32_t plen, uint32_t pamp
     }
     return codes;
 }
-GSX_HD bool sweep_has_stage1(uint32_t codes) { return ((codes >> 12) & 15u) != 7u; }
-enum : uint32_t { SUM_WIDE = 1u, SUM_TWO_BLOCKS = 2u };
+enum : uint32_t { SUM_WIDE16 = 1u << 16, SUM_WIDE32 = 1u << 17, SUM_TWO_BLOCKS = 1u << 18 };
 
-template <int NB>
-GSX_HD void summary_planes(const uint32_t* w, uint32_t n_planes, uint32_t cs, uint32_t u[NB]) {
+// One summary sector = header word + seven plane words.  header: bits 0..15 = valid rows (bit i = row i of the sector's 16
+// rows), SUM_WIDE16 = the interval has more than 16 rows (rows 16..31 are in sum1), SUM_WIDE32 = more than 32 rows (not
+// summarised: such a node goes to the tree search unexamined), SUM_TWO_BLOCKS = it straddles two 64-row blocks (statistics
+// only).  plane word j: bits 0..15 = high bit of the 2-bit symbol t_j of each row, bits 16..31 = its low bit.
+// summary_eval: u[r] = rows with at most budget - r mismatches after all seven levels; returns the header.
+template <int NB, class LoadSummary>
+GSX_HD uint32_t summary_eval(LoadSummary ld, uint32_t stage, uint32_t idx, uint32_t codes, uint32_t budget, uint32_t u[NB]) {
+    uint32_t w[8];
+    ld(stage, idx, w);
+    const uint32_t valid = w[0] & 0xFFFFu;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-    for (uint32_t t = 0; t < 4u; t++) {
-        if (t >= n_planes) break;
-        const uint32_t c = (cs >> (4u * t)) & 15u;
+    for (int r = 0; r < NB; r++) u[r] = budget >= (uint32_t)r ? valid : 0u;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (uint32_t j = 0; j < 7u; j++) {
+        const uint32_t c = (codes >> (4u * j)) & 15u;
         if (c == 7u || c == 12u) continue;                                       // no such level / PAM wildcard
-        const uint32_t sym = c & 3u;
-        uint32_t eq = ~(w[2u * t] ^ ((sym & 2u) ? ~0u : 0u)) & ~(w[2u * t + 1u] ^ ((sym & 1u) ? ~0u : 0u));
+        const uint32_t x = w[1u + j] ^ (((c & 2u) ? 0xFFFFu : 0u) | ((c & 1u) ? 0xFFFF0000u : 0u));
+        uint32_t eq = ~(x | (x >> 16)) & 0xFFFFu;                                // rows whose symbol is the wanted one
         if (c < 4u) {                                                            // protospacer: a differing row loses one unit of budget
 #if defined(__CUDA_ARCH__)
 #pragma unroll
@@ -544,34 +554,16 @@ GSX_HD void summary_planes(const uint32_t* w, uint32_t n_planes, uint32_t cs, ui
             for (int r = 0; r < NB; r++) u[r] &= eq;
         }
     }
-}
-// ld(stage, idx, w): the eight 32-bit words of sum0[idx] (stage 0) or sum1[idx] (stage 1).
-// stage 0 initialises u from the valid-row mask and returns the info word; an empty interval leaves u all zero.
-template <int NB, class LoadSummary>
-GSX_HD uint32_t summary_step0(LoadSummary ld, uint32_t idx, uint32_t codes, uint32_t budget, uint32_t u[NB], uint32_t& valid) {
-    uint32_t w[8];
-    ld(0u, idx, w);
-    valid = w[0];
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-    for (int r = 0; r < NB; r++) u[r] = budget >= (uint32_t)r ? valid : 0u;
-    summary_planes<NB>(w + 2, 3u, codes, u);
-    return w[1];
-}
-template <int NB, class LoadSummary>
-GSX_HD void summary_step1(LoadSummary ld, uint32_t idx, uint32_t codes, uint32_t u[NB]) {
-    uint32_t w[8];
-    ld(1u, idx, w);
-    summary_planes<NB>(w, 4u, codes >> 12, u);
+    return w[0];
 }
 // whole-node form (reference semantics for the tests): can any row of the pattern's interval still reach the final level?
 template <int NB, class LoadSummary>
 GSX_HD bool summary_viable(LoadSummary ld, uint32_t idx, uint32_t codes, uint32_t budget) {
-    uint32_t u[NB], valid;
-    const uint32_t info = summary_step0<NB>(ld, idx, codes, budget, u, valid);
-    if (info & SUM_WIDE) return true;
-    if (u[0] && sweep_has_stage1(codes)) summary_step1<NB>(ld, idx, codes, u);
+    uint32_t u[NB];
+    const uint32_t head = summary_eval<NB>(ld, 0u, idx, codes, budget, u);
+    if ((head & SUM_WIDE32) || u[0]) return true;
+    if (!(head & SUM_WIDE16)) return false;
+    summary_eval<NB>(ld, 1u, idx, codes, budget, u);
     return u[0] != 0u;
 }
 // builds the two summary sectors of one table entry from the look-ahead lines; plane(b, j, hi) = 64-bit plane of t_j
@@ -581,18 +573,21 @@ GSX_HD void summary_build(Plane plane, uint32_t sp, uint32_t width, uint32_t s0[
     for (int i = 0; i < 8; i++) s0[i] = s1[i] = 0u;
     if (width == 0u) return;
     const uint32_t e1 = sp + width;
-    uint32_t info = ((e1 >> 6) != (sp >> 6)) ? SUM_TWO_BLOCKS : 0u;
-    if (width > 32u) { s0[0] = ~0u; s0[1] = info | SUM_WIDE; return; }
+    const uint32_t flags = (((e1 >> 6) != (sp >> 6)) ? SUM_TWO_BLOCKS : 0u) | (width > 16u ? SUM_WIDE16 : 0u) | (width > 32u ? SUM_WIDE32 : 0u);
+    if (width > 32u) { s0[0] = 0xFFFFu | flags; return; }
     const uint32_t valid = width == 32u ? ~0u : ((1u << width) - 1u);
     const uint32_t b = sp >> 6, r0 = sp & 63u, nA = (64u - r0) < width ? (64u - r0) : width;      // rows taken from block b
-    s0[0] = valid; s0[1] = info;
-    for (uint32_t j = 0; j < 7u; j++)
+    s0[0] = (valid & 0xFFFFu) | flags; s1[0] = (valid >> 16) | flags;
+    for (uint32_t j = 0; j < 7u; j++) {
+        uint32_t v[2];
         for (uint32_t h = 0; h < 2u; h++) {
-            uint64_t bits = plane(b, j, h != 0u) >> r0;
-            if (nA < width) bits |= plane(b + 1u, j, h != 0u) << nA;
-            const uint32_t v = (uint32_t)bits & valid;
-            if (j < 3u) s0[2u + 2u * j + (h ? 0u : 1u)] = v; else s1[2u * (j - 3u) + (h ? 0u : 1u)] = v;   // hi first, then lo
+            uint64_t bits = plane(b, j, h == 0u) >> r0;
+            if (nA < width) bits |= plane(b + 1u, j, h == 0u) << nA;
+            v[h] = (uint32_t)bits & valid;                                       // v[0] = high bits, v[1] = low bits of rows 0..31
         }
+        s0[1u + j] = (v[0] & 0xFFFFu) | (v[1] << 16);
+        s1[1u + j] = (v[0] >> 16) | (v[1] & 0xFFFF0000u);
+    }
 }
 
 // ---- k-mer jump table (specialised search kernels) ------------------------------------------------------------------

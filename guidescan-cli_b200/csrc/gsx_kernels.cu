@@ -761,25 +761,21 @@ struct DevSummaryLoader {
 
 struct SweepStats { uint32_t nodes, lookups, patterns, sectors, seeds; };
 
-// per-warp buffer of nodes that need the second summary sector (gsx_core.h summary_step1): 64 records in shared memory
+// per-warp buffer of nodes whose first 16 rows are dead but which have more (gsx_core.h summary_eval, stage 1): 64 records
+// in shared memory
 //   idx    table index of the pattern (sp, ep are read from the jump table if the node survives)
 //   codes  plane codes of its guide
 //   tlm    task | mismatches << 24 | remaining budget << 27
-//   u[r]   row masks of the filter after stage 0
-template <int NB>
 struct ContBuf {
-    uint32_t* idx; uint32_t* codes; uint32_t* tlm; uint32_t* u;      // u[r * 64 + slot]
+    uint32_t* idx; uint32_t* codes; uint32_t* tlm;
     uint32_t count;                                                  // warp-uniform
 };
 
-template <int NB>
-__device__ __forceinline__ void cont_push(ContBuf<NB>& cb, uint32_t lane, bool want, uint32_t idx, uint32_t codes, uint32_t tlm, const uint32_t u[NB]) {
+__device__ __forceinline__ void cont_push(ContBuf& cb, uint32_t lane, bool want, uint32_t idx, uint32_t codes, uint32_t tlm) {
     const uint32_t m = __ballot_sync(0xffffffffu, want);
     if (want) {
         const uint32_t slot = cb.count + __popc(m & ((1u << lane) - 1u));
         cb.idx[slot] = idx; cb.codes[slot] = codes; cb.tlm[slot] = tlm;
-#pragma unroll
-        for (int r = 0; r < NB; r++) cb.u[r * 64 + slot] = u[r];
     }
     cb.count += __popc(m);
     __syncwarp();
@@ -804,45 +800,43 @@ __device__ __forceinline__ void sweep_emit(const SweepArgs& a, uint32_t lane, bo
     }
 }
 
-// drain up to 32 parked nodes: second summary sector, all lanes busy
+// drain up to 32 parked nodes: rows 16..31 of their intervals, all lanes busy
 template <int NB>
-__device__ __forceinline__ void cont_process(const SweepArgs& a, ContBuf<NB>& cb, uint32_t lane, SweepStats& st) {
+__device__ __forceinline__ void cont_process(const SweepArgs& a, ContBuf& cb, uint32_t lane, SweepStats& st) {
     const uint32_t n = cb.count < 32u ? cb.count : 32u;
     const bool mine = lane < n;
     uint32_t idx = 0, codes = 0, tlm = 0; uint32_t u[NB];
 #pragma unroll
     for (int r = 0; r < NB; r++) u[r] = 0;
-    if (mine) {
-        const uint32_t slot = cb.count - n + lane;
-        idx = cb.idx[slot]; codes = cb.codes[slot]; tlm = cb.tlm[slot];
-#pragma unroll
-        for (int r = 0; r < NB; r++) u[r] = cb.u[r * 64 + slot];
-    }
+    if (mine) { const uint32_t slot = cb.count - n + lane; idx = cb.idx[slot]; codes = cb.codes[slot]; tlm = cb.tlm[slot]; }
     __syncwarp();
     cb.count -= n;
     if (mine) {
         DevSummaryLoader ld; ld.sum0 = nullptr; ld.sum1 = (tlm & 1u) ? a.st[1].sum1 : a.st[0].sum1;
-        summary_step1<NB>(ld, idx, codes, u);
+        summary_eval<NB>(ld, 1u, idx, codes, (tlm >> 27) & 7u, u);
         st.sectors++;
     }
     sweep_emit(a, lane, mine && u[0] != 0u, idx, tlm, st);
 }
 
-// one flattened pass over the patterns of 32 guides in one slice: lane g owns n_mine patterns of guide (gb * 32 + g);
+// one flattened pass over the patterns of 32 guides in one slice: lane g owns n_mine patterns of guide (gb * 32 + g), of
+// which this work unit handles the range [part / parts, (part + 1) / parts);
 // ZERO = the patterns that use their budget up (one filter mask), else the patterns with budget left
 template <bool ZERO, int NB>
-__device__ __forceinline__ void sweep_pass(const SweepArgs& a, const SweepPlan& pl, ContBuf<NB>& cb, uint32_t lane, uint32_t strand, uint32_t beta, uint32_t gb,
-                                           uint32_t qlow, uint32_t codes, int B, uint32_t n_mine, SweepStats& st) {
+__device__ __forceinline__ void sweep_pass(const SweepArgs& a, const SweepPlan& pl, ContBuf& cb, uint32_t lane, uint32_t strand, uint32_t beta, uint32_t gb,
+                                           uint32_t part, uint32_t qlow, uint32_t codes, int B, uint32_t n_mine, SweepStats& st) {
     const uint32_t FULL = 0xffffffffu, M = a.M;
     DevSummaryLoader ld; ld.sum0 = strand ? a.st[1].sum0 : a.st[0].sum0; ld.sum1 = nullptr;
     uint32_t incl = n_mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(FULL, incl, o); if (lane >= (uint32_t)o) incl += y; }
     const uint32_t excl = incl - n_mine, T = __shfl_sync(FULL, incl, 31);
-    for (uint32_t base = 0; base < T; base += 32u) {
+    const uint32_t per = ((T + a.parts - 1u) / a.parts + 31u) & ~31u;                      // patterns per part, whole warp steps
+    const uint32_t t_begin = part * per, t_end = (t_begin + per < T) ? t_begin + per : T;
+    for (uint32_t base = t_begin; base < t_end; base += 32u) {
         while (cb.count >= 32u) cont_process<NB>(a, cb, lane, st);
         const uint32_t it = base + lane;
-        const bool active = it < T;
+        const bool active = it < t_end;
         uint32_t o = 0;                                   // owner = largest lane whose first pattern is <= it
 #pragma unroll
         for (uint32_t step = 16u; step; step >>= 1) {
@@ -853,27 +847,24 @@ __device__ __forceinline__ void sweep_pass(const SweepArgs& a, const SweepPlan& 
         const uint32_t oq = __shfl_sync(FULL, qlow, o), ocodes = __shfl_sync(FULL, codes, o), oexcl = __shfl_sync(FULL, excl, o);
         const int oB = __shfl_sync(FULL, B, o);
         bool emit = false, park = false; uint32_t idx = 0, mm = M;
-        uint32_t u[NB];
-#pragma unroll
-        for (int r = 0; r < NB; r++) u[r] = 0;
         if (active) {
             uint32_t used;
             idx = sweep_pattern(pl, a.xtab, ZERO ? 1u : 0u, (uint64_t)oq, beta, (uint32_t)oB, it - oexcl, used);
             if (!ZERO) mm = M - (uint32_t)oB + used;                          // (the other pass always ends at M)
-            uint32_t valid, info;
-            if (ZERO) { uint32_t v[1]; info = summary_step0<1>(ld, idx, ocodes, 0u, v, valid); u[0] = v[0]; }
-            else info = summary_step0<NB>(ld, idx, ocodes, M - mm, u, valid);
+            uint32_t head, alive;
+            if (ZERO) { uint32_t v[1]; head = summary_eval<1>(ld, 0u, idx, ocodes, 0u, v); alive = v[0]; }
+            else { uint32_t u[NB]; head = summary_eval<NB>(ld, 0u, idx, ocodes, M - mm, u); alive = u[0]; }
             st.patterns++; st.sectors++;
             if (((idx ^ oq) & 15u) == 0u) st.lookups++;                       // one table line per 16 beginnings
-            if (valid) {
-                st.nodes++; st.lookups += (info & SUM_TWO_BLOCKS) ? 2u : 1u;
-                if (info & SUM_WIDE) emit = true;                             // not summarised: the tree search takes it as is
-                else if (u[0]) { if (sweep_has_stage1(ocodes)) park = true; else emit = true; }
+            if (head & 0xFFFFu) {
+                st.nodes++; st.lookups += (head & SUM_TWO_BLOCKS) ? 2u : 1u;
+                emit = alive != 0u || (head & SUM_WIDE32) != 0u;              // (more than 32 rows: not summarised, the tree search takes it)
+                park = !emit && (head & SUM_WIDE16) != 0u;
             }
         }
         const uint32_t tlm = (((gb * 32u + o) << 1) | strand) | (mm << 24) | ((M - mm) << 27);
         sweep_emit(a, lane, emit, idx, tlm, st);
-        cont_push<NB>(cb, lane, park, idx, ocodes, tlm, u);
+        cont_push(cb, lane, park, idx, ocodes, tlm);
     }
 }
 
@@ -881,26 +872,25 @@ template <int WARPS, int MINB, int NB>
 __global__ void __launch_bounds__(WARPS * 32, MINB) sweep_kernel(SweepArgs a) {
     __shared__ SweepPlan s_plan;
     __shared__ uint32_t s_c32[WARPS][3][64];
-    __shared__ uint32_t s_cu[WARPS][NB][64];
     for (int i = threadIdx.x; i < (int)(sizeof(SweepPlan) / 4); i += blockDim.x)
         reinterpret_cast<uint32_t*>(&s_plan)[i] = reinterpret_cast<const uint32_t*>(&a.plan)[i];
     __syncthreads();
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, FULL = 0xffffffffu;
-    ContBuf<NB> cb;
-    cb.idx = s_c32[warp][0]; cb.codes = s_c32[warp][1]; cb.tlm = s_c32[warp][2]; cb.u = &s_cu[warp][0][0]; cb.count = 0;
+    ContBuf cb;
+    cb.idx = s_c32[warp][0]; cb.codes = s_c32[warp][1]; cb.tlm = s_c32[warp][2]; cb.count = 0;
     const uint32_t L = s_plan.L, sb = s_plan.sb, M = a.M;
     const uint32_t n_slices = 1u << (2u * sb), n_gb = (a.n_guides + 31u) >> 5;
-    const uint64_t items_per_strand = (uint64_t)n_slices * n_gb, n_items = 2ull * items_per_strand;
+    const uint64_t items_per_strand = (uint64_t)n_slices * n_gb * a.parts, n_items = 2ull * items_per_strand;
     unsigned long long n_nodes = 0, n_lookups = 0, n_patterns = 0, n_sectors = 0, n_seeds = 0;
     SweepStats st = {0, 0, 0, 0, 0};
-    uint32_t next_item = 0;
-    if (lane == 0) next_item = atomicAdd(a.item_counter, 1u);
     for (;;) {
-        const uint32_t item = __shfl_sync(FULL, next_item, 0);
+        uint32_t item = 0;
+        if (lane == 0) item = atomicAdd(a.item_counter, 1u);
+        item = __shfl_sync(FULL, item, 0);
         if ((uint64_t)item >= n_items) break;
-        if (lane == 0) next_item = atomicAdd(a.item_counter, 1u);            // fetched while this unit is being worked on
         const uint32_t strand = (uint64_t)item >= items_per_strand ? 1u : 0u;
-        const uint32_t rem = item - (strand ? (uint32_t)items_per_strand : 0u);
+        uint32_t rem = item - (strand ? (uint32_t)items_per_strand : 0u);
+        const uint32_t part = rem % a.parts; rem /= a.parts;
         const uint32_t beta = rem / n_gb, gb = rem - beta * n_gb;
         const uint32_t g = gb * 32u + lane;
         const bool valid = g < a.n_guides && !(a.skip && a.skip[g]);
@@ -909,8 +899,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) sweep_kernel(SweepArgs a) {
         const int B = (valid && h <= M) ? (int)(M - h) : -1;
         const uint32_t codes = sweep_codes(q, L, a.plen, a.pampack);
         // the patterns without budget left first (most of them, cheapest arithmetic), then the others
-        sweep_pass<true, NB>(a, s_plan, cb, lane, strand, beta, gb, (uint32_t)q, codes, B, B >= 0 ? s_plan.xcnt[1][B] : 0u, st);
-        sweep_pass<false, NB>(a, s_plan, cb, lane, strand, beta, gb, (uint32_t)q, codes, B, B >= 0 ? s_plan.xcnt[0][B] : 0u, st);
+        sweep_pass<true, NB>(a, s_plan, cb, lane, strand, beta, gb, part, (uint32_t)q, codes, B, B >= 0 ? s_plan.xcnt[1][B] : 0u, st);
+        sweep_pass<false, NB>(a, s_plan, cb, lane, strand, beta, gb, part, (uint32_t)q, codes, B, B >= 0 ? s_plan.xcnt[0][B] : 0u, st);
         n_nodes += st.nodes; n_lookups += st.lookups; n_patterns += st.patterns; n_sectors += st.sectors; n_seeds += st.seeds;
         st = {0, 0, 0, 0, 0};
     }
@@ -942,6 +932,7 @@ cudaError_t launch_sweep(const SweepArgs& a, int variant, int sm_count, cudaStre
     case 2: return launch_sweep_t<8, 4>(a, sm_count, s);      // 1024 thr/SM
     case 3: return launch_sweep_t<8, 6>(a, sm_count, s);      // 1536 thr/SM
     case 4: return launch_sweep_t<8, 8>(a, sm_count, s);      // 2048 thr/SM
+    case 5: return launch_sweep_t<8, 5>(a, sm_count, s);      // 1280 thr/SM
     }
     return cudaErrorInvalidValue;
 }

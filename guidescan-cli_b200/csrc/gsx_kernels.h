@@ -52,7 +52,7 @@ struct SweepArgs {
     SweepPlan plan;
     const uint32_t* xtab;              // gsx_core.h sweep_pattern
     uint32_t M, plen, pampack;
-    uint32_t counting;                 // unused by the filter itself; kept for symmetry
+    uint32_t parts;                    // each (slice, 32 guides) unit is cut into this many work units (keeps all warps on the same slices)
     SeedNode* queue; uint32_t queue_cap;
     uint32_t* queue_count; uint32_t* item_counter; uint32_t* error_flag;
     unsigned long long* stats;         // [0] nodes [1] lookups [4] patterns [5] sectors [6] seeds

@@ -60,13 +60,11 @@ struct DevStrand {
     const unsigned char* lines;    // optional second copy, one 128-byte line per 64 rows: OccBlock + six look-ahead symbol
                                    // planes (see build_lookahead_kernel); nullptr if absent
     const unsigned char* sum0;     // optional pattern summaries of the sweep kernel, 32 bytes per jump-table entry (same index):
-    const unsigned char* sum1;     //   sum0[e] = {valid rows (bit i = row sp + i, i < 32), info, hi/lo planes of t0, t1, t2}
-                                   //   sum1[e] = {hi/lo planes of t3, t4, t5, t6}
-                                   // t_j = the character a backward search from that row consumes j steps ahead (as in `lines`),
-                                   // aligned to the START of the entry's interval, so one 32-byte load indexed by the pattern
-                                   // itself replaces the table entry + look-ahead line reads.  info bit 0: the interval has more
-                                   // than 32 rows (not summarised: such a node goes to the tree search unexamined), bit 1: it
-                                   // straddles two 64-row blocks (statistics only); nullptr if absent (see build_summary_kernel)
+    const unsigned char* sum1;     //   sum0[e] = header + the seven look-ahead symbols t0..t6 of rows sp .. sp+15 of the entry's
+                                   //   interval as 16-bit plane pairs, sum1[e] = the same for rows sp+16 .. sp+31 (gsx_core.h
+                                   //   summary_eval).  t_j = the character a backward search from that row consumes j steps ahead
+                                   //   (as in `lines`).  One 32-byte load indexed by the pattern itself replaces the table entry
+                                   //   + look-ahead line reads; nullptr if absent (see build_summary_kernel)
 };
 
 GSX_HD const OccBlock* block_ptr(const DevStrand& st, uint32_t b) {

@@ -101,6 +101,8 @@ typedef struct {
     uint64_t launches;         /* kernels launched by this library for the call (all devices) */
     double   ms_sweep;         /* part of ms_search spent in the slice-major front end (0 if it did not run) */
     uint64_t seeds;            /* level-L nodes the front end handed to the tree search */
+    double   ms_prepare;       /* host: guide validation / packing before the first device call */
+    double   ms_wall;          /* host: wall time of the whole gsx_enumerate call */
 } gsx_counters;
 
 /* ---- index ------------------------------------------------------------------------------------------- */
