@@ -338,11 +338,13 @@ def cpu_baseline(args, g, chroms, kmers, workdir, steps=1, sample=None, ix=None)
     own = ix is None
     if own:
         import gsx
+        os.environ.update({"GSX_FTAB": "0", "GSX_LOOKAHEAD": "0"})        # only the BWT and the SA samples are exported
         ix = gsx.Index.build_from_text(g, chroms, sa_shift=6, devices=[int(os.environ.get("LOCAL_RANK", 0))])
     b0, b1 = ix.export_bwt(0), ix.export_bwt(1)
     (s0, sh0), (s1, sh1) = ix.export_sa_samples(0), ix.export_sa_samples(1)
-    if sh0 != 6:
-        raise RuntimeError("cpu_baseline port needs SA samples every 64 rows")
+    if sh0 > 6 or sh1 != sh0:
+        raise RuntimeError("cpu_baseline port needs SA samples at least every 64 rows")
+    s0, s1 = np.ascontiguousarray(s0[::1 << (6 - sh0)]), np.ascontiguousarray(s1[::1 << (6 - sh0)])        # the oracle keeps the reference's density (every 64th row)
     oix = O.Index.from_bwt(b0, s0, b1, s1, chroms)
     del b0, b1
     log("cpu_baseline: oracle index imported in %.1f s" % (time.time() - t0))
@@ -402,12 +404,12 @@ def main():
     ap.add_argument("--impl", default="gsx", choices=["gsx", "reference"])
     ap.add_argument("--genome-mb", type=float, default=float(os.environ.get("GSX_BENCH_GENOME_MB", 3100)))
     ap.add_argument("--n-chr", type=int, default=24)
-    ap.add_argument("--guides-per-step", type=int, default=int(os.environ.get("GSX_BENCH_GUIDES", 50000)))
+    ap.add_argument("--guides-per-step", type=int, default=int(os.environ.get("GSX_BENCH_GUIDES", 200000)))
     ap.add_argument("--ref-max-mb", type=float, default=200.0)
     ap.add_argument("--plant-guides", type=int, default=2000)
     ap.add_argument("--mismatches", type=int, default=3)
     ap.add_argument("--seed", type=int, default=3)
-    ap.add_argument("--sa-shift", type=int, default=6)
+    ap.add_argument("--sa-shift", type=int, default=2, help="SA sample density 2^k rows (the reference samples every 64th row; the index keeps every 4th)")
     ap.add_argument("--cpu-sample", type=int, default=8000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sweep-variants", default="")

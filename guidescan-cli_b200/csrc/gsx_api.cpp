@@ -329,6 +329,9 @@ struct DevBufs {
     ~DevBufs() { for (auto& q : ptrs) pool_put(device, q.first, q.second); }
 };
 
+static std::mutex g_recs_mu;
+static std::vector<std::vector<GuideRec>> g_recs_free;          // record arrays of released results, reused by later calls
+
 int gsx_prepare_guides(const gsx_guide* guides, size_t n, const gsx_params* p, gsx::Prepared& out) {
     if (p->max_bulge_size != 1) return fail(GSX_ERR_ARG, "max_bulge_size must be 1 (the reference hard-wires it: process.hpp:82-87)");
     if (p->mismatches >= (uint32_t)kMaxDist) return fail(GSX_ERR_ARG, "mismatches must be <= 7");
@@ -337,70 +340,90 @@ int gsx_prepare_guides(const gsx_guide* guides, size_t n, const gsx_params* p, g
     if (p->n_alt_pams + 1 > (uint32_t)kMaxPams) return fail(GSX_ERR_ARG, "too many alternative PAMs (max 7)");
     memset(out.pamsets, 0, sizeof out.pamsets);
     std::map<std::string, int> set_of;
+    {   // a record array released by an earlier result, if any: fresh multi-megabyte allocations cost more in page faults
+        // than the packing itself
+        std::lock_guard<std::mutex> lk(g_recs_mu);
+        if (!g_recs_free.empty()) { out.recs = std::move(g_recs_free.back()); g_recs_free.pop_back(); }
+    }
     out.recs.resize(n);
-    size_t max_total = 0;
+    std::vector<uint8_t> setid(n);
     const bool bulges = p->rna_bulges || p->dna_bulges;
     uint8_t sym_tab[256], csym_tab[256];                          // symbol code of a character / of its complement
     for (int c = 0; c < 256; c++) { sym_tab[c] = sym_of((char)c); csym_tab[c] = sym_of(complement_char((char)c)); }
-    const char* last_pam = nullptr; int last_set = -1; size_t last_mp = 0;
-    for (size_t i = 0; i < n; i++) {
-        const char* seq = guides[i].seq ? guides[i].seq : "";
-        const char* pam = guides[i].pam ? guides[i].pam : "";
-        size_t sl = strlen(seq);
-        if (sl == 0 || sl > (size_t)kMaxQ) return fail(GSX_ERR_ARG, "guide sequence length must be 1..32");
-        GuideRec& r = out.recs[i];
-        memset(&r, 0, sizeof r);
-        r.qlen = (uint8_t)sl; r.seqlen = (uint8_t)sl;
-        memcpy(r.seq, seq, sl);
-        if (p->start) for (size_t l = 0; l < sl; l++) r.q[l] = sym_tab[(unsigned char)seq[sl - 1 - l]];
-        else for (size_t l = 0; l < sl; l++) r.q[l] = csym_tab[(unsigned char)seq[l]];       // consumption order: process.hpp:63, index.hpp:214
-        if (last_pam && (pam == last_pam || strcmp(pam, last_pam) == 0)) {                       // same PAM column value as the previous guide
-            r.pamset = (uint8_t)last_set; max_total = std::max(max_total, sl + last_mp);
-            continue;
-        }
-        size_t pl = strlen(pam);
-        if (pl > (size_t)kMaxPamLen) return fail(GSX_ERR_ARG, "PAM longer than 8");
-        auto it = set_of.find(pam);
-        if (it == set_of.end()) {
-            if (set_of.size() >= (size_t)kMaxPamSets) return fail(GSX_ERR_ARG, "more than 16 distinct PAM column values in one call");
-            int id = (int)set_of.size();
-            PamSet& ps = out.pamsets[id];
-            std::vector<std::string> pams;                                   // process.hpp:51-56
-            if (pl == 0) pams.push_back("");
-            else { for (uint32_t a = 0; a < p->n_alt_pams; a++) pams.push_back(p->alt_pams[a] ? p->alt_pams[a] : ""); pams.push_back(pam); }
-            ps.n_pams = (uint8_t)pams.size(); ps.kpam_len = (uint8_t)pl;
-            for (size_t k = 0; k < pams.size(); k++) {
-                const std::string& s = pams[k];
-                if (s.size() > (size_t)kMaxPamLen) return fail(GSX_ERR_ARG, "alternative PAM longer than 8");
-                if (s.empty() && pams.size() > 1) return fail(GSX_ERR_ARG, "empty alternative PAM");
-                ps.plen[k] = (uint8_t)s.size();
-                for (size_t j = 0; j < s.size(); j++)
-                    ps.sym[k][j] = p->start ? sym_of(s[s.size() - 1 - j]) : sym_of(complement_char(s[j]));
+    // pass 1 (sequential, light): PAM column values -> PAM sets (process.hpp:51-56)
+    size_t set_mp[kMaxPamSets] = {0};
+    {
+        const char* last_pam = nullptr; int last_set = -1;
+        for (size_t i = 0; i < n; i++) {
+            const char* pam = guides[i].pam ? guides[i].pam : "";
+            if (last_pam && (pam == last_pam || strcmp(pam, last_pam) == 0)) { setid[i] = (uint8_t)last_set; continue; }
+            size_t pl = strlen(pam);
+            if (pl > (size_t)kMaxPamLen) return fail(GSX_ERR_ARG, "PAM longer than 8");
+            auto it = set_of.find(pam);
+            if (it == set_of.end()) {
+                if (set_of.size() >= (size_t)kMaxPamSets) return fail(GSX_ERR_ARG, "more than 16 distinct PAM column values in one call");
+                int id = (int)set_of.size();
+                PamSet& ps = out.pamsets[id];
+                std::vector<std::string> pams;
+                if (pl == 0) pams.push_back("");
+                else { for (uint32_t a = 0; a < p->n_alt_pams; a++) pams.push_back(p->alt_pams[a] ? p->alt_pams[a] : ""); pams.push_back(pam); }
+                ps.n_pams = (uint8_t)pams.size(); ps.kpam_len = (uint8_t)pl;
+                for (size_t k = 0; k < pams.size(); k++) {
+                    const std::string& s = pams[k];
+                    if (s.size() > (size_t)kMaxPamLen) return fail(GSX_ERR_ARG, "alternative PAM longer than 8");
+                    if (s.empty() && pams.size() > 1) return fail(GSX_ERR_ARG, "empty alternative PAM");
+                    ps.plen[k] = (uint8_t)s.size();
+                    for (size_t j = 0; j < s.size(); j++)
+                        ps.sym[k][j] = p->start ? sym_of(s[s.size() - 1 - j]) : sym_of(complement_char(s[j]));
+                    set_mp[id] = std::max(set_mp[id], s.size());
+                }
+                out.max_pams = std::max<uint32_t>(out.max_pams, ps.n_pams);
+                it = set_of.emplace(pam, id).first;
             }
-            out.max_pams = std::max<uint32_t>(out.max_pams, ps.n_pams);
-            it = set_of.emplace(pam, id).first;
+            setid[i] = (uint8_t)it->second;
+            last_pam = pam; last_set = it->second;
         }
-        r.pamset = (uint8_t)it->second;
-        size_t mp = 0; const PamSet& ps = out.pamsets[r.pamset];
-        for (int k = 0; k < ps.n_pams; k++) mp = std::max<size_t>(mp, ps.plen[k]);
-        max_total = std::max(max_total, sl + mp);
-        last_pam = pam; last_set = it->second; last_mp = mp;
+    }
+    // pass 2 (parallel over chunks of guides): symbol packing in consumption order (process.hpp:63, index.hpp:214)
+    out.gq.resize(n);
+    struct Chunk { size_t max_total = 0; uint32_t min_qlen = 255; bool bad_len = false, fast = true; };
+    const size_t n_thr = std::max<size_t>(1, std::min<size_t>({(size_t)8, n / 16384, (size_t)std::max(1u, std::thread::hardware_concurrency())}));
+    std::vector<Chunk> chunks(n_thr);
+    auto work = [&](size_t t) {
+        Chunk c;                                                               // (local: the chunk array shares cache lines)
+        struct Publish { Chunk& dst; Chunk& src; ~Publish() { dst = src; } } publish{chunks[t], c};
+        for (size_t i = n * t / n_thr, e = n * (t + 1) / n_thr; i < e; i++) {
+            const char* seq = guides[i].seq ? guides[i].seq : "";
+            const size_t sl = strlen(seq);
+            if (sl == 0 || sl > (size_t)kMaxQ) { c.bad_len = true; return; }
+            GuideRec& r = out.recs[i];
+            memset(&r, 0, sizeof r);
+            r.qlen = (uint8_t)sl; r.seqlen = (uint8_t)sl; r.pamset = setid[i];
+            memcpy(r.seq, seq, sl);
+            uint64_t v = (uint64_t)sl << 58; bool acgt = true;
+            for (size_t l = 0; l < sl; l++) {
+                const uint8_t sy = p->start ? sym_tab[(unsigned char)seq[sl - 1 - l]] : csym_tab[(unsigned char)seq[l]];
+                r.q[l] = sy;
+                if (sy > 3) acgt = false; else if (l < 29) v |= (uint64_t)sy << (2 * l);
+            }
+            out.gq[i] = v;
+            if (!acgt || sl > 29) c.fast = false;
+            c.max_total = std::max(c.max_total, sl + set_mp[r.pamset]);
+            c.min_qlen = std::min<uint32_t>(c.min_qlen, (uint32_t)sl);
+        }
+    };
+    if (n_thr == 1) work(0);
+    else { std::vector<std::thread> th; for (size_t t = 0; t < n_thr; t++) th.emplace_back(work, t); for (auto& x : th) x.join(); }
+    size_t max_total = 0; bool all_fast = true; out.min_qlen = 255;
+    for (const Chunk& c : chunks) {
+        if (c.bad_len) return fail(GSX_ERR_ARG, "guide sequence length must be 1..32");
+        max_total = std::max(max_total, c.max_total); all_fast = all_fast && c.fast; out.min_qlen = std::min(out.min_qlen, c.min_qlen);
     }
     out.wide = bulges || max_total > 27;
     if (max_total + p->dna_bulges > 32) return fail(GSX_ERR_ARG, "guide + PAM + DNA bulges longer than 32 characters");
     // fast path: no bulges, one PAM pattern for every guide, ACGT-only guides of at most 29 nt
-    out.fast_ok = !out.wide && set_of.size() == 1 && out.pamsets[0].n_pams == 1 && n > 0;
+    out.fast_ok = !out.wide && set_of.size() == 1 && out.pamsets[0].n_pams == 1 && n > 0 && all_fast;
     if (out.fast_ok) {
-        out.gq.resize(n);
-        out.min_qlen = 255;
-        for (size_t i = 0; i < n && out.fast_ok; i++) {
-            const GuideRec& r = out.recs[i];
-            out.min_qlen = std::min<uint32_t>(out.min_qlen, r.qlen);
-            if (r.qlen > 29) { out.fast_ok = false; break; }
-            uint64_t v = (uint64_t)r.qlen << 58;
-            for (uint32_t l = 0; l < r.qlen; l++) { if (r.q[l] > 3) { out.fast_ok = false; break; } v |= (uint64_t)r.q[l] << (2 * l); }
-            out.gq[i] = v;
-        }
         const PamSet& ps = out.pamsets[0];
         out.plen = ps.plen[0]; out.pampack = 0;
         for (uint32_t j = 0; j < ps.plen[0]; j++) out.pampack |= (uint32_t)ps.sym[0][j] << (3 * j);
@@ -473,7 +496,7 @@ static void run_device_job(DeviceJob* job) {
                          n >= (uint32_t)env_int("GSX_SWEEP_MIN", 8192) && prep.min_qlen >= ftab_L && p.mismatches <= 4 && p.threshold <= 4;
         if (use_sweep) {
             const double per_strand = 40.0 * std::pow(4.0, (double)ftab_L);                  // sum0 + the part of sum1 that is touched
-            const double target = (double)env_int("GSX_SWEEP_SLICE_MB", 12) * 1e6;
+            const double target = (double)env_int("GSX_SWEEP_SLICE_MB", n >= 131072 ? 40 : 12) * 1e6;       // (larger batches: fewer, fatter slices)
             sweep_sb = 1; while (sweep_sb < ftab_L - 3 && per_strand / std::pow(4.0, (double)sweep_sb) > target) sweep_sb++;
             if (env_int("GSX_SWEEP_SB", 0) > 0) sweep_sb = (uint32_t)env_int("GSX_SWEEP_SB", 0);
             if (sweep_sb < 1 || sweep_sb + 3 > ftab_L) use_sweep = false;
@@ -498,12 +521,14 @@ static void run_device_job(DeviceJob* job) {
                     const int sv = env_int("GSX_SWEEP_VARIANT", 2);
                     const uint32_t warps = (uint32_t)di.sm_count * 8u * (sv == 0 ? 3u : sv == 1 ? 2u : sv == 2 ? 4u : sv == 3 ? 6u : sv == 5 ? 5u : 8u);
                     const uint32_t n_gb = (n + 31) / 32;
-                    uint32_t parts = (warps + n_gb - 1) / n_gb; if (parts < 1) parts = 1; if (parts > 8) parts = 8;
+                    uint32_t parts = 1; (void)warps; (void)n_gb;                   // measured: cutting the units does not pay (profiles/r01r_*)
                     if (env_int("GSX_SWEEP_PARTS", 0) > 0) parts = (uint32_t)env_int("GSX_SWEEP_PARTS", 0);
                     w.parts = parts;
                 }
                 w.queue = d_queue; w.queue_cap = (uint32_t)queue_cap; w.queue_count = d_ctrs + 3; w.item_counter = d_ctrs + 4;
                 w.error_flag = d_ctrs + 2; w.stats = d_stats;
+                w.gtab = B.alloc<uint32_t>((size_t)n * 20);
+                CK(launch_sweep_guides(w, s)); n_launches++;
                 CK(launch_sweep(w, env_int("GSX_SWEEP_VARIANT", 2), di.sm_count, s)); n_launches++;
                 m.seeds = d_queue; m.n_seeds = d_ctrs + 3; m.seed_cap = (uint32_t)queue_cap; m.combos = nullptr; m.n_combos = 0;
             }
@@ -750,5 +775,9 @@ extern "C" int gsx_result_match_sequence(const gsx_result* r, size_t hit, char* 
 extern "C" void gsx_result_free(gsx_result* r) {
     if (!r) return;
     for (auto& p : r->parts) p.release();
+    {
+        std::lock_guard<std::mutex> lk(g_recs_mu);
+        if (g_recs_free.size() < 4 && r->guides.capacity()) g_recs_free.push_back(std::move(r->guides));
+    }
     delete r;
 }

@@ -556,6 +556,60 @@ GSX_HD uint32_t summary_eval(LoadSummary ld, uint32_t stage, uint32_t idx, uint3
     }
     return w[0];
 }
+// The same evaluation with the per-guide part hoisted out (what the sweep kernel runs): per plane j two masks such that
+// y_j = (w_j & A_j) ^ X_j has a set bit in either half exactly for the rows that differ from the wanted symbol
+// (wildcard / absent level: A = X = 0; never-matching PAM character: A = 0, X = ~0); pflags bit j = plane j is a
+// protospacer level (a differing row loses one unit of budget instead of dying).
+//   gm[0..6] = A, gm[7..13] = X, gm[14] = pflags
+GSX_HD void summary_masks(uint32_t codes, uint32_t gm[15]) {
+    uint32_t pflags = 0;
+    for (uint32_t j = 0; j < 7u; j++) {
+        const uint32_t c = (codes >> (4u * j)) & 15u;
+        uint32_t A = ~0u, X = ((c & 2u) ? 0xFFFFu : 0u) | ((c & 1u) ? 0xFFFF0000u : 0u);
+        if (c == 7u || c == 12u) { A = 0u; X = 0u; }
+        else if (c == 13u) { A = 0u; X = ~0u; }
+        else if (c < 4u) pflags |= 1u << j;
+        gm[j] = A; gm[7u + j] = X;
+    }
+    gm[14] = pflags;
+}
+// no budget left: every differing row dies, whatever the level
+GSX_HD uint32_t summary_eval_exact(const uint32_t w[8], const uint32_t gm[15]) {
+    uint32_t acc = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (uint32_t j = 0; j < 7u; j++) acc |= (w[1u + j] & gm[j]) ^ gm[7u + j];
+    return w[0] & 0xFFFFu & ~(acc | (acc >> 16));
+}
+template <int NB>
+GSX_HD void summary_eval_masks(const uint32_t w[8], const uint32_t gm[15], uint32_t budget, uint32_t u[NB]) {
+    const uint32_t valid = w[0] & 0xFFFFu;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int r = 0; r < NB; r++) u[r] = budget >= (uint32_t)r ? valid : 0u;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (uint32_t j = 0; j < 7u; j++) {
+        const uint32_t y = (w[1u + j] & gm[j]) ^ gm[7u + j];
+        const uint32_t eq = ~(y | (y >> 16));
+        if ((gm[14] >> j) & 1u) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (int r = 0; r + 1 < NB; r++) u[r] = (u[r] & eq) | u[r + 1];
+            u[NB - 1] &= eq;
+        } else {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (int r = 0; r < NB; r++) u[r] &= eq;
+        }
+    }
+}
+
 // whole-node form (reference semantics for the tests): can any row of the pattern's interval still reach the final level?
 template <int NB, class LoadSummary>
 GSX_HD bool summary_viable(LoadSummary ld, uint32_t idx, uint32_t codes, uint32_t budget) {

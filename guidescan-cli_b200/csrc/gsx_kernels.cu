@@ -750,6 +750,8 @@ int search_fast_grid_warps(int variant, int sm_count) {
 // Work unit = (strand, slice, block of 32 guides), handed out slice-major through one counter, so that all warps work
 // on the same one or two slices at any time.  Inside a unit the 32 guides' pattern lists are flattened over the lanes.
 // ---------------------------------------------------------------------------------------------------------
+static inline int grid_for_n(uint32_t n, int threads, int cap) { long b = ((long)n + threads - 1) / threads; if (b < 1) b = 1; if (b > cap) b = cap; return (int)b; }
+
 struct DevSummaryLoader {
     const unsigned char* sum0; const unsigned char* sum1;
     __device__ __forceinline__ void operator()(uint32_t stage, uint32_t idx, uint32_t w[8]) const {
@@ -819,52 +821,84 @@ __device__ __forceinline__ void cont_process(const SweepArgs& a, ContBuf& cb, ui
     sweep_emit(a, lane, mine && u[0] != 0u, idx, tlm, st);
 }
 
+// per-guide constants of the sweep (20 words): written once per call by sweep_guides_kernel, copied to shared memory by
+// each work unit, read back by whichever lanes end up working on that guide's patterns
+//   [0..6] A, [7..13] X, [14] pflags (gsx_core.h summary_masks)   [15] low 2(L-sb) bits of the packed guide
+//   [16] plane codes   per work unit: [17] first pattern number (prefix sum)  [18] xor-table offset  [19] remaining budget
+constexpr int GT_WORDS = 20, GT_QLOW = 15, GT_CODES = 16, GT_EXCL = 17, GT_XOFF = 18, GT_B = 19;
+
+__global__ void sweep_guides_kernel(SweepArgs a, uint32_t* __restrict__ gtab) {
+    for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < a.n_guides; g += gridDim.x * blockDim.x) {
+        const uint64_t q = a.gq[g];
+        uint32_t t[GT_WORDS];
+        const uint32_t codes = sweep_codes(q, a.plan.L, a.plen, a.pampack);
+        summary_masks(codes, t);
+        t[GT_QLOW] = (uint32_t)q & ((1u << (2u * (a.plan.L - a.plan.sb))) - 1u);
+        t[GT_CODES] = codes; t[GT_EXCL] = t[GT_XOFF] = t[GT_B] = 0;
+        uint4* dst = reinterpret_cast<uint4*>(gtab + (size_t)g * GT_WORDS);
+        for (int k = 0; k < GT_WORDS / 4; k++) dst[k] = make_uint4(t[4 * k], t[4 * k + 1], t[4 * k + 2], t[4 * k + 3]);
+    }
+}
+
 // one flattened pass over the patterns of 32 guides in one slice: lane g owns n_mine patterns of guide (gb * 32 + g), of
-// which this work unit handles the range [part / parts, (part + 1) / parts);
+// which this work unit handles the range [part / parts, (part + 1) / parts); sg = the warp's guide table in shared memory
+// (33 rows: row 32 holds the total as the sentinel of the owner search);
 // ZERO = the patterns that use their budget up (one filter mask), else the patterns with budget left
 template <bool ZERO, int NB>
-__device__ __forceinline__ void sweep_pass(const SweepArgs& a, const SweepPlan& pl, ContBuf& cb, uint32_t lane, uint32_t strand, uint32_t beta, uint32_t gb,
-                                           uint32_t part, uint32_t qlow, uint32_t codes, int B, uint32_t n_mine, SweepStats& st) {
+__device__ __forceinline__ void sweep_pass(const SweepArgs& a, const SweepPlan& pl, ContBuf& cb, uint32_t* sg, uint32_t lane, uint32_t strand, uint32_t beta,
+                                           uint32_t gb, uint32_t part, int B, SweepStats& st) {
     const uint32_t FULL = 0xffffffffu, M = a.M;
-    DevSummaryLoader ld; ld.sum0 = strand ? a.st[1].sum0 : a.st[0].sum0; ld.sum1 = nullptr;
+    const unsigned char* sum0 = strand ? a.st[1].sum0 : a.st[0].sum0;
+    const uint32_t n_mine = B >= 0 ? pl.xcnt[ZERO ? 1 : 0][B] : 0u;
     uint32_t incl = n_mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(FULL, incl, o); if (lane >= (uint32_t)o) incl += y; }
-    const uint32_t excl = incl - n_mine, T = __shfl_sync(FULL, incl, 31);
+    const uint32_t T = __shfl_sync(FULL, incl, 31);
+    if (T == 0u) return;
+    __syncwarp();
+    sg[lane * GT_WORDS + GT_EXCL] = incl - n_mine; sg[lane * GT_WORDS + GT_XOFF] = B >= 0 ? pl.xoff[ZERO ? 1 : 0][B] : 0u;
+    sg[lane * GT_WORDS + GT_B] = B >= 0 ? (uint32_t)B : 0u;
+    if (lane == 31) sg[32 * GT_WORDS + GT_EXCL] = T;
+    __syncwarp();
     const uint32_t per = ((T + a.parts - 1u) / a.parts + 31u) & ~31u;                      // patterns per part, whole warp steps
     const uint32_t t_begin = part * per, t_end = (t_begin + per < T) ? t_begin + per : T;
+    const uint32_t low_bits = 2u * (pl.L - pl.sb);
+    uint32_t cur = 0;                                                                      // owner of the step's first pattern (warp-uniform)
     for (uint32_t base = t_begin; base < t_end; base += 32u) {
         while (cb.count >= 32u) cont_process<NB>(a, cb, lane, st);
         const uint32_t it = base + lane;
         const bool active = it < t_end;
-        uint32_t o = 0;                                   // owner = largest lane whose first pattern is <= it
-#pragma unroll
-        for (uint32_t step = 16u; step; step >>= 1) {
-            const uint32_t cand = o + step;
-            const uint32_t v = __shfl_sync(FULL, excl, cand & 31u);
-            if (cand < 32u && v <= it) o = cand;
-        }
-        const uint32_t oq = __shfl_sync(FULL, qlow, o), ocodes = __shfl_sync(FULL, codes, o), oexcl = __shfl_sync(FULL, excl, o);
-        const int oB = __shfl_sync(FULL, B, o);
-        bool emit = false, park = false; uint32_t idx = 0, mm = M;
+        uint32_t o = cur;                                 // owner = largest lane whose first pattern is <= it
+        if (active) while (sg[(o + 1u) * GT_WORDS + GT_EXCL] <= it) o++;
+        cur = __shfl_sync(FULL, o, (t_end - base > 32u) ? 31u : (t_end - 1u - base));      // owner of the step's last pattern
+        bool emit = false, park = false; uint32_t idx = 0, mm = M, codes = 0;
         if (active) {
-            uint32_t used;
-            idx = sweep_pattern(pl, a.xtab, ZERO ? 1u : 0u, (uint64_t)oq, beta, (uint32_t)oB, it - oexcl, used);
-            if (!ZERO) mm = M - (uint32_t)oB + used;                          // (the other pass always ends at M)
-            uint32_t head, alive;
-            if (ZERO) { uint32_t v[1]; head = summary_eval<1>(ld, 0u, idx, ocodes, 0u, v); alive = v[0]; }
-            else { uint32_t u[NB]; head = summary_eval<NB>(ld, 0u, idx, ocodes, M - mm, u); alive = u[0]; }
-            st.patterns++; st.sectors++;
-            if (((idx ^ oq) & 15u) == 0u) st.lookups++;                       // one table line per 16 beginnings
-            if (head & 0xFFFFu) {
-                st.nodes++; st.lookups += (head & SUM_TWO_BLOCKS) ? 2u : 1u;
-                emit = alive != 0u || (head & SUM_WIDE32) != 0u;              // (more than 32 rows: not summarised, the tree search takes it)
-                park = !emit && (head & SUM_WIDE16) != 0u;
+            const uint4* gp = reinterpret_cast<const uint4*>(sg + o * GT_WORDS);
+            const uint4 g0 = gp[0], g1 = gp[1], g2 = gp[2], g3 = gp[3], g4 = gp[4];
+            const uint32_t gm[15] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w, g2.x, g2.y, g2.z, g2.w, g3.x, g3.y, g3.z};
+            const uint32_t qlow = g3.w, oexcl = g4.y, oB = g4.w;
+            codes = g4.x;
+            const uint32_t xw = __ldg(a.xtab + g4.z + (it - oexcl));
+            idx = (beta << low_bits) | (qlow ^ (xw & 0x0FFFFFFFu));
+            if (!ZERO) mm = M - oB + (xw >> 28);                              // (the other pass always ends at M)
+            uint32_t w[8];
+            asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"                                   // LDG.E.256
+                         : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+                         : "l"(sum0 + ((size_t)idx << 5)));
+            uint32_t alive;
+            if (ZERO) alive = summary_eval_exact(w, gm);
+            else { uint32_t u[NB]; summary_eval_masks<NB>(w, gm, M - mm, u); alive = u[0]; }
+            st.patterns++;
+            if (((idx ^ qlow) & 15u) == 0u) st.lookups++;                     // one table line per 16 beginnings
+            if (w[0] & 0xFFFFu) {
+                st.nodes++; st.lookups += (w[0] & SUM_TWO_BLOCKS) ? 2u : 1u;
+                emit = alive != 0u || (w[0] & SUM_WIDE32) != 0u;              // (more than 32 rows: not summarised, the tree search takes it)
+                park = !emit && (w[0] & SUM_WIDE16) != 0u;
             }
         }
         const uint32_t tlm = (((gb * 32u + o) << 1) | strand) | (mm << 24) | ((M - mm) << 27);
         sweep_emit(a, lane, emit, idx, tlm, st);
-        cont_push(cb, lane, park, idx, ocodes, tlm);
+        cont_push(cb, lane, park, idx, codes, tlm);
     }
 }
 
@@ -872,12 +906,14 @@ template <int WARPS, int MINB, int NB>
 __global__ void __launch_bounds__(WARPS * 32, MINB) sweep_kernel(SweepArgs a) {
     __shared__ SweepPlan s_plan;
     __shared__ uint32_t s_c32[WARPS][3][64];
+    __shared__ __align__(16) uint32_t s_g[WARPS][33 * GT_WORDS];
     for (int i = threadIdx.x; i < (int)(sizeof(SweepPlan) / 4); i += blockDim.x)
         reinterpret_cast<uint32_t*>(&s_plan)[i] = reinterpret_cast<const uint32_t*>(&a.plan)[i];
     __syncthreads();
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, FULL = 0xffffffffu;
     ContBuf cb;
     cb.idx = s_c32[warp][0]; cb.codes = s_c32[warp][1]; cb.tlm = s_c32[warp][2]; cb.count = 0;
+    uint32_t* sg = s_g[warp];
     const uint32_t L = s_plan.L, sb = s_plan.sb, M = a.M;
     const uint32_t n_slices = 1u << (2u * sb), n_gb = (a.n_guides + 31u) >> 5;
     const uint64_t items_per_strand = (uint64_t)n_slices * n_gb * a.parts, n_items = 2ull * items_per_strand;
@@ -894,13 +930,19 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) sweep_kernel(SweepArgs a) {
         const uint32_t beta = rem / n_gb, gb = rem - beta * n_gb;
         const uint32_t g = gb * 32u + lane;
         const bool valid = g < a.n_guides && !(a.skip && a.skip[g]);
-        const uint64_t q = valid ? __ldg(a.gq + g) : 0ull;
-        const uint32_t h = sweep_slice_distance(q, L, sb, beta);
-        const int B = (valid && h <= M) ? (int)(M - h) : -1;
-        const uint32_t codes = sweep_codes(q, L, a.plen, a.pampack);
+        int B = -1;
+        __syncwarp();
+        if (valid) {                                                           // this guide's row of the table -> shared memory
+            const uint4* src = reinterpret_cast<const uint4*>(a.gtab + (size_t)g * GT_WORDS);
+            uint4* dst = reinterpret_cast<uint4*>(sg + lane * GT_WORDS);
+            const uint4 v0 = __ldg(src), v1 = __ldg(src + 1), v2 = __ldg(src + 2), v3 = __ldg(src + 3), v4 = __ldg(src + 4);
+            dst[0] = v0; dst[1] = v1; dst[2] = v2; dst[3] = v3; dst[4] = v4;
+            const uint32_t h = sweep_slice_distance(__ldg(a.gq + g), L, sb, beta);
+            if (h <= M) B = (int)(M - h);
+        }
         // the patterns without budget left first (most of them, cheapest arithmetic), then the others
-        sweep_pass<true, NB>(a, s_plan, cb, lane, strand, beta, gb, part, (uint32_t)q, codes, B, B >= 0 ? s_plan.xcnt[1][B] : 0u, st);
-        sweep_pass<false, NB>(a, s_plan, cb, lane, strand, beta, gb, part, (uint32_t)q, codes, B, B >= 0 ? s_plan.xcnt[0][B] : 0u, st);
+        sweep_pass<true, NB>(a, s_plan, cb, sg, lane, strand, beta, gb, part, B, st);
+        sweep_pass<false, NB>(a, s_plan, cb, sg, lane, strand, beta, gb, part, B, st);
         n_nodes += st.nodes; n_lookups += st.lookups; n_patterns += st.patterns; n_sectors += st.sectors; n_seeds += st.seeds;
         st = {0, 0, 0, 0, 0};
     }
@@ -915,6 +957,11 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) sweep_kernel(SweepArgs a) {
         atomicAdd(a.stats + 0, n_nodes); atomicAdd(a.stats + 1, n_lookups); atomicAdd(a.stats + 4, n_patterns);
         atomicAdd(a.stats + 5, n_sectors); atomicAdd(a.stats + 6, n_seeds);
     }
+}
+
+cudaError_t launch_sweep_guides(const SweepArgs& a, cudaStream_t s) {
+    sweep_guides_kernel<<<grid_for_n(a.n_guides, 256, 148 * 8), 256, 0, s>>>(a, a.gtab);
+    return cudaGetLastError();
 }
 
 template <int WARPS, int MINB>

@@ -51,6 +51,7 @@ struct SweepArgs {
     uint32_t n_guides;
     SweepPlan plan;
     const uint32_t* xtab;              // gsx_core.h sweep_pattern
+    uint32_t* gtab;                    // n_guides * 20 words: per-guide constants, written by launch_sweep_guides
     uint32_t M, plen, pampack;
     uint32_t parts;                    // each (slice, 32 guides) unit is cut into this many work units (keeps all warps on the same slices)
     SeedNode* queue; uint32_t queue_cap;
@@ -93,6 +94,7 @@ int search_grid_warps(bool wide, int variant, int sm_count);
 cudaError_t launch_search(const SearchArgs& a, bool wide, int variant, int sm_count, cudaStream_t s, int* warps_total);
 int search_fast_grid_warps(int variant, int sm_count);
 cudaError_t launch_search_fast(const SearchArgs& a, int variant, int sm_count, cudaStream_t s);
+cudaError_t launch_sweep_guides(const SweepArgs& a, cudaStream_t s);      // per-guide filter masks (before launch_sweep)
 cudaError_t launch_sweep(const SweepArgs& a, int variant, int sm_count, cudaStream_t s);
 cudaError_t launch_scan(const uint32_t* in, uint32_t* out, uint32_t n, cudaStream_t s);
 cudaError_t launch_scatter(const MatchRec* m, uint32_t n, const uint32_t* moff, uint32_t* cursor, uint32_t* by_guide, cudaStream_t s);

@@ -151,6 +151,17 @@ static void sweep_host(const DevStrand st[2], const Prepared& prep, uint32_t M) 
                         const uint32_t codes = sweep_codes(q, L, prep.plen, prep.pampack);
                         const bool ok2 = summary_viable<kMaxDist>(lds, idx, codes, M - mm);
                         if (e.width <= 32 ? ok2 != ok : !ok2) { fprintf(stderr, "summary filter disagrees with node_viable (idx %u zero %d ok %d ok2 %d sp %u w %u budget %u)\n", idx, zero, (int)ok, (int)ok2, e.sp, e.width, M - mm); exit(3); }
+                        {   // the hoisted-mask forms the kernel's main loop uses
+                            uint32_t gm[15], w[8], u1[kMaxDist], u2[kMaxDist];
+                            summary_masks(codes, gm);
+                            for (uint32_t stage = 0; stage < 2; stage++) {
+                                lds(stage, idx, w);
+                                summary_eval<kMaxDist>(lds, stage, idx, codes, M - mm, u1);
+                                summary_eval_masks<kMaxDist>(w, gm, M - mm, u2);
+                                for (int r = 0; r < kMaxDist; r++) if ((u1[r] & 0xFFFFu) != (u2[r] & 0xFFFFu)) { fprintf(stderr, "summary_eval_masks disagrees (idx %u stage %u r %d)\n", idx, stage, r); exit(3); }
+                                if (zero && summary_eval_exact(w, gm) != (u1[0] & 0xFFFFu)) { fprintf(stderr, "summary_eval_exact disagrees (idx %u stage %u)\n", idx, stage); exit(3); }
+                            }
+                        }
                         if (zero && summary_viable<1>(lds, idx, codes, 0) != ok2) { fprintf(stderr, "summary filter <1> disagrees (idx %u)\n", idx); exit(3); }
                         if (!ok2) continue;
                         Node nd{}; nd.sp = e.sp; nd.ep = e.sp + e.width - 1; nd.key_lo = ftab_key(idx, q, L); nd.task = (uint32_t)(2 * g + strand);
