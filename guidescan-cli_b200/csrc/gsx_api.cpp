@@ -21,6 +21,7 @@ using namespace gsx;
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+int gsx_set_error(int code, const std::string& msg) { return fail(code, msg); }      // for the other translation units
 
 struct CudaError : std::runtime_error { using std::runtime_error::runtime_error; };
 #define CK(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) throw CudaError(std::string(#call) + ": " + cudaGetErrorString(e__)); } while (0)

@@ -61,7 +61,7 @@ EXPORTS = ["gsx_params_default", "gsx_index_open", "gsx_index_build", "gsx_index
            "gsx_index_n_chromosomes", "gsx_index_chromosome_name", "gsx_index_chromosome_length", "gsx_index_device_bytes",
            "gsx_index_n_devices", "gsx_index_rank", "gsx_index_locate", "gsx_index_export_bwt", "gsx_index_export_sa_samples", "gsx_enumerate", "gsx_result_view_get",
            "gsx_result_counters", "gsx_result_match_sequence", "gsx_result_free", "gsx_format_rows", "gsx_format_header",
-           "gsx_enumerate_file", "gsx_free", "gsx_last_error", "gsx_version", "gsx_device_count"]
+           "gsx_enumerate_file", "gsx_generate_kmers", "gsx_free", "gsx_last_error", "gsx_version", "gsx_device_count"]
 
 _L.gsx_last_error.restype = C.c_char_p
 _L.gsx_version.restype = C.c_char_p
@@ -95,6 +95,8 @@ _L.gsx_format_header.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_voi
 _L.gsx_enumerate_file.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.POINTER(Params), C.c_int, C.c_int, C.c_size_t,
                                   C.POINTER(C.c_size_t), C.POINTER(Counters)]
 _L.gsx_free.argtypes = [C.c_void_p]
+_L.gsx_generate_kmers.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_uint32, C.c_uint64, C.c_char_p, C.c_int, C.c_int,
+                                  C.POINTER(C.c_uint64)]
 
 
 class GsxError(RuntimeError):
@@ -110,6 +112,14 @@ def _ck(code, where):
 
 def device_count() -> int:
     return _L.gsx_device_count()
+
+
+def generate_kmers(fasta: str, out_csv: str, pam="NGG", kmer_length=20, min_chr_length=0, prefix="", start=False, device=0) -> int:
+    """scripts/generate_kmers.py of the reference (same options, same text), PAM scan on the GPU.  Returns the row count."""
+    n = C.c_uint64()
+    _ck(_L.gsx_generate_kmers(fasta.encode(), out_csv.encode(), pam.encode(), kmer_length, min_chr_length, prefix.encode(),
+                              int(bool(start)), device, C.byref(n)), "gsx_generate_kmers")
+    return n.value
 
 
 def make_params(mismatches=3, rna_bulges=0, dna_bulges=0, threshold=-1, start=False, max_off_targets=-1,

@@ -164,6 +164,14 @@ int gsx_format_header(const gsx_index*, int format_sam, int complete, char** buf
  * src/guidescan.cxx:181-258).  Returns the number of guides through *n_guides. */
 int gsx_enumerate_file(const gsx_index*, const char* kmers_csv, const char* out_path, const gsx_params*,
                        int format_sam, int complete, size_t batch_guides, size_t* n_guides, gsx_counters* counters);
+/* ---- genome-wide guide generation -------------------------------------------------------------------- */
+/* What the reference's scripts/generate_kmers.py prints (reference scripts/generate_kmers.py:55-136): every k-mer next to an
+ * occurrence of `pam` (N = any base) on either strand of every FASTA record of at least min_chr_length bases, as the guides
+ * CSV that gsx_enumerate_file / `guidescan enumerate -f` reads.  `start` != 0: the PAM precedes the k-mer (--start).  The PAM
+ * scan and the ordered compaction run on `device`; text identical to the script's.  *n_kmers (may be NULL) = rows written. */
+int gsx_generate_kmers(const char* fasta_path, const char* out_csv_path, const char* pam, uint32_t kmer_length,
+                       uint64_t min_chr_length, const char* prefix, int start, int device, uint64_t* n_kmers);
+
 void gsx_free(void*);
 
 const char* gsx_last_error(void);
