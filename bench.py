@@ -105,7 +105,10 @@ def dist_setup(n_gpus):
         import torch
         import torch.distributed as dist_mod
         torch.cuda.set_device(local)
-        dist_mod.init_process_group(backend="nccl" if torch.cuda.is_available() else "gloo")
+        if torch.cuda.is_available():
+            dist_mod.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
+        else:
+            dist_mod.init_process_group(backend="gloo")
         dist = dist_mod
     return rank, world, local, dist
 

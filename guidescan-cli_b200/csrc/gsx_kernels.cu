@@ -840,63 +840,50 @@ __global__ void sweep_guides_kernel(SweepArgs a, uint32_t* __restrict__ gtab) {
     }
 }
 
-// one flattened pass over the patterns of 32 guides in one slice: lane g owns n_mine patterns of guide (gb * 32 + g), of
-// which this work unit handles the range [part / parts, (part + 1) / parts); sg = the warp's guide table in shared memory
-// (33 rows: row 32 holds the total as the sentinel of the owner search);
-// ZERO = the patterns that use their budget up (one filter mask), else the patterns with budget left
+// one pattern of one guide against its summary sector; EXACT = no budget left (one row mask)
+template <bool EXACT, int NB>
+__device__ __forceinline__ void sweep_test(const SweepArgs& a, const unsigned char* sum0, uint32_t idx, uint32_t qlow, const uint32_t gm[15],
+                                           uint32_t budget, bool& emit, bool& park, SweepStats& st) {
+    uint32_t w[8];
+    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"                                           // LDG.E.256
+                 : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+                 : "l"(sum0 + ((size_t)idx << 5)));
+    uint32_t alive;
+    if (EXACT) alive = summary_eval_exact(w, gm);
+    else { uint32_t u[NB]; summary_eval_masks<NB>(w, gm, budget, u); alive = u[0]; }
+    st.patterns++; st.sectors++;
+    if (((idx ^ qlow) & 15u) == 0u) st.lookups++;                             // one table line per 16 beginnings
+    if (w[0] & 0xFFFFu) {
+        st.nodes++; st.lookups += (w[0] & SUM_TWO_BLOCKS) ? 2u : 1u;
+        emit = alive != 0u || (w[0] & SUM_WIDE32) != 0u;                      // (more than 32 rows: not summarised, the tree search takes it)
+        park = !emit && (w[0] & SUM_WIDE16) != 0u;
+    }
+}
+
+// all patterns of ONE guide (lane `o` of the unit) in one pass, 32 per step: the guide's masks sit in registers, the xor
+// table is read with unit stride, nothing is looked up per lane but the summary sector itself
 template <bool ZERO, int NB>
-__device__ __forceinline__ void sweep_pass(const SweepArgs& a, const SweepPlan& pl, ContBuf& cb, uint32_t* sg, uint32_t lane, uint32_t strand, uint32_t beta,
-                                           uint32_t gb, uint32_t part, int B, SweepStats& st) {
-    const uint32_t FULL = 0xffffffffu, M = a.M;
+__device__ __forceinline__ void sweep_run(const SweepArgs& a, const SweepPlan& pl, ContBuf& cb, const uint32_t* sg, uint32_t lane, uint32_t strand,
+                                          uint32_t hi_bits, uint32_t guide, uint32_t o, uint32_t B, SweepStats& st) {
+    const uint32_t M = a.M, n = pl.xcnt[ZERO ? 1 : 0][B];
+    if (n == 0u) return;
+    const uint32_t* xt = a.xtab + pl.xoff[ZERO ? 1 : 0][B];
     const unsigned char* sum0 = strand ? a.st[1].sum0 : a.st[0].sum0;
-    const uint32_t n_mine = B >= 0 ? pl.xcnt[ZERO ? 1 : 0][B] : 0u;
-    uint32_t incl = n_mine;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(FULL, incl, o); if (lane >= (uint32_t)o) incl += y; }
-    const uint32_t T = __shfl_sync(FULL, incl, 31);
-    if (T == 0u) return;
-    __syncwarp();
-    sg[lane * GT_WORDS + GT_EXCL] = incl - n_mine; sg[lane * GT_WORDS + GT_XOFF] = B >= 0 ? pl.xoff[ZERO ? 1 : 0][B] : 0u;
-    sg[lane * GT_WORDS + GT_B] = B >= 0 ? (uint32_t)B : 0u;
-    if (lane == 31) sg[32 * GT_WORDS + GT_EXCL] = T;
-    __syncwarp();
-    const uint32_t per = ((T + a.parts - 1u) / a.parts + 31u) & ~31u;                      // patterns per part, whole warp steps
-    const uint32_t t_begin = part * per, t_end = (t_begin + per < T) ? t_begin + per : T;
-    const uint32_t low_bits = 2u * (pl.L - pl.sb);
-    uint32_t cur = 0;                                                                      // owner of the step's first pattern (warp-uniform)
-    for (uint32_t base = t_begin; base < t_end; base += 32u) {
+    const uint4* gp = reinterpret_cast<const uint4*>(sg + o * GT_WORDS);       // same address in every lane: broadcast
+    const uint4 g0 = gp[0], g1 = gp[1], g2 = gp[2], g3 = gp[3];
+    const uint32_t gm[15] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w, g2.x, g2.y, g2.z, g2.w, g3.x, g3.y, g3.z};
+    const uint32_t qlow = g3.w, codes = sg[o * GT_WORDS + GT_CODES];
+    for (uint32_t base = 0; base < n; base += 32u) {
         while (cb.count >= 32u) cont_process<NB>(a, cb, lane, st);
-        const uint32_t it = base + lane;
-        const bool active = it < t_end;
-        uint32_t o = cur;                                 // owner = largest lane whose first pattern is <= it
-        if (active) while (sg[(o + 1u) * GT_WORDS + GT_EXCL] <= it) o++;
-        cur = __shfl_sync(FULL, o, (t_end - base > 32u) ? 31u : (t_end - 1u - base));      // owner of the step's last pattern
-        bool emit = false, park = false; uint32_t idx = 0, mm = M, codes = 0;
-        if (active) {
-            const uint4* gp = reinterpret_cast<const uint4*>(sg + o * GT_WORDS);
-            const uint4 g0 = gp[0], g1 = gp[1], g2 = gp[2], g3 = gp[3], g4 = gp[4];
-            const uint32_t gm[15] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w, g2.x, g2.y, g2.z, g2.w, g3.x, g3.y, g3.z};
-            const uint32_t qlow = g3.w, oexcl = g4.y, oB = g4.w;
-            codes = g4.x;
-            const uint32_t xw = __ldg(a.xtab + g4.z + (it - oexcl));
-            idx = (beta << low_bits) | (qlow ^ (xw & 0x0FFFFFFFu));
-            if (!ZERO) mm = M - oB + (xw >> 28);                              // (the other pass always ends at M)
-            uint32_t w[8];
-            asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"                                   // LDG.E.256
-                         : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
-                         : "l"(sum0 + ((size_t)idx << 5)));
-            uint32_t alive;
-            if (ZERO) alive = summary_eval_exact(w, gm);
-            else { uint32_t u[NB]; summary_eval_masks<NB>(w, gm, M - mm, u); alive = u[0]; }
-            st.patterns++;
-            if (((idx ^ qlow) & 15u) == 0u) st.lookups++;                     // one table line per 16 beginnings
-            if (w[0] & 0xFFFFu) {
-                st.nodes++; st.lookups += (w[0] & SUM_TWO_BLOCKS) ? 2u : 1u;
-                emit = alive != 0u || (w[0] & SUM_WIDE32) != 0u;              // (more than 32 rows: not summarised, the tree search takes it)
-                park = !emit && (w[0] & SUM_WIDE16) != 0u;
-            }
+        const uint32_t t = base + lane;
+        bool emit = false, park = false; uint32_t idx = 0, mm = M;
+        if (t < n) {
+            const uint32_t xw = __ldg(xt + t);
+            idx = hi_bits | (qlow ^ (xw & 0x0FFFFFFFu));
+            if (!ZERO) mm = M - B + (xw >> 28);                               // (the other pass always ends at M)
+            sweep_test<ZERO, NB>(a, sum0, idx, qlow, gm, M - mm, emit, park, st);
         }
-        const uint32_t tlm = (((gb * 32u + o) << 1) | strand) | (mm << 24) | ((M - mm) << 27);
+        const uint32_t tlm = ((guide << 1) | strand) | (mm << 24) | ((M - mm) << 27);
         sweep_emit(a, lane, emit, idx, tlm, st);
         cont_push(cb, lane, park, idx, codes, tlm);
     }
@@ -916,7 +903,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) sweep_kernel(SweepArgs a) {
     uint32_t* sg = s_g[warp];
     const uint32_t L = s_plan.L, sb = s_plan.sb, M = a.M;
     const uint32_t n_slices = 1u << (2u * sb), n_gb = (a.n_guides + 31u) >> 5;
-    const uint64_t items_per_strand = (uint64_t)n_slices * n_gb * a.parts, n_items = 2ull * items_per_strand;
+    const uint64_t items_per_strand = (uint64_t)n_slices * n_gb, n_items = 2ull * items_per_strand;
     unsigned long long n_nodes = 0, n_lookups = 0, n_patterns = 0, n_sectors = 0, n_seeds = 0;
     SweepStats st = {0, 0, 0, 0, 0};
     for (;;) {
@@ -925,8 +912,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) sweep_kernel(SweepArgs a) {
         item = __shfl_sync(FULL, item, 0);
         if ((uint64_t)item >= n_items) break;
         const uint32_t strand = (uint64_t)item >= items_per_strand ? 1u : 0u;
-        uint32_t rem = item - (strand ? (uint32_t)items_per_strand : 0u);
-        const uint32_t part = rem % a.parts; rem /= a.parts;
+        const uint32_t rem = item - (strand ? (uint32_t)items_per_strand : 0u);
         const uint32_t beta = rem / n_gb, gb = rem - beta * n_gb;
         const uint32_t g = gb * 32u + lane;
         const bool valid = g < a.n_guides && !(a.skip && a.skip[g]);
@@ -940,9 +926,33 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) sweep_kernel(SweepArgs a) {
             const uint32_t h = sweep_slice_distance(__ldg(a.gq + g), L, sb, beta);
             if (h <= M) B = (int)(M - h);
         }
-        // the patterns without budget left first (most of them, cheapest arithmetic), then the others
-        sweep_pass<true, NB>(a, s_plan, cb, sg, lane, strand, beta, gb, part, B, st);
-        sweep_pass<false, NB>(a, s_plan, cb, sg, lane, strand, beta, gb, part, B, st);
+        __syncwarp();
+        const uint32_t hi_bits = beta << (2u * (L - sb));
+        // (1) guides whose only pattern in this slice is the unsubstituted one (budget 0), and the unsubstituted pattern of
+        //     the guides with budget 1: one pattern per lane, each lane with its own guide's masks
+        {
+            bool emit = false, park = false; uint32_t idx = 0, codes = 0;
+            if (B == 0 || B == 1) {
+                const uint4* gp = reinterpret_cast<const uint4*>(sg + lane * GT_WORDS);
+                const uint4 g0 = gp[0], g1 = gp[1], g2 = gp[2], g3 = gp[3];
+                const uint32_t gm[15] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w, g2.x, g2.y, g2.z, g2.w, g3.x, g3.y, g3.z};
+                codes = sg[lane * GT_WORDS + GT_CODES];
+                idx = hi_bits | g3.w;
+                sweep_test<false, NB>(a, strand ? a.st[1].sum0 : a.st[0].sum0, idx, g3.w, gm, (uint32_t)B, emit, park, st);
+            }
+            const uint32_t tlm = ((g << 1) | strand) | ((M - (uint32_t)(B > 0 ? B : 0)) << 24) | ((uint32_t)(B > 0 ? B : 0) << 27);
+            sweep_emit(a, lane, emit, idx, tlm, st);
+            cont_push(cb, lane, park, idx, codes, tlm);
+        }
+        // (2) guides with budget left after the slice characters, one at a time: first the patterns that use the budget up
+        //     (most of them, cheapest arithmetic), then -- from budget 2 on -- the ones that keep some
+        uint32_t todo = __ballot_sync(FULL, B >= 1);
+        while (todo) {
+            const uint32_t o = (uint32_t)__ffs(todo) - 1u; todo &= todo - 1u;
+            const uint32_t Bo = (uint32_t)__shfl_sync(FULL, B, o);
+            sweep_run<true, NB>(a, s_plan, cb, sg, lane, strand, hi_bits, gb * 32u + o, o, Bo, st);
+            if (Bo >= 2u) sweep_run<false, NB>(a, s_plan, cb, sg, lane, strand, hi_bits, gb * 32u + o, o, Bo, st);
+        }
         n_nodes += st.nodes; n_lookups += st.lookups; n_patterns += st.patterns; n_sectors += st.sectors; n_seeds += st.seeds;
         st = {0, 0, 0, 0, 0};
     }
