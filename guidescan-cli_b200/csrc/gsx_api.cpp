@@ -497,7 +497,7 @@ static void run_device_job(DeviceJob* job) {
                          n >= (uint32_t)env_int("GSX_SWEEP_MIN", 8192) && prep.min_qlen >= ftab_L && p.mismatches <= 4 && p.threshold <= 4;
         if (use_sweep) {
             const double per_strand = 40.0 * std::pow(4.0, (double)ftab_L);                  // sum0 + the part of sum1 that is touched
-            const double target = (double)env_int("GSX_SWEEP_SLICE_MB", n >= 131072 ? 40 : 12) * 1e6;       // (larger batches: fewer, fatter slices)
+            const double target = (double)env_int("GSX_SWEEP_SLICE_MB", 12) * 1e6;
             sweep_sb = 1; while (sweep_sb < ftab_L - 3 && per_strand / std::pow(4.0, (double)sweep_sb) > target) sweep_sb++;
             if (env_int("GSX_SWEEP_SB", 0) > 0) sweep_sb = (uint32_t)env_int("GSX_SWEEP_SB", 0);
             if (sweep_sb < 1 || sweep_sb + 3 > ftab_L) use_sweep = false;
@@ -516,7 +516,7 @@ static void run_device_job(DeviceJob* job) {
                 uint32_t* d_xtab = B.alloc<uint32_t>(xtab.size());
                 CK(cudaMemcpyAsync(d_xtab, xtab.data(), xtab.size() * 4, cudaMemcpyHostToDevice, s)); CK(cudaStreamSynchronize(s));
                 if (!d_queue) d_queue = B.alloc<SeedNode>(queue_cap);
-                w.st[0] = m.st[0]; w.st[1] = m.st[1]; w.gq = m.gq; w.skip = m.skip; w.n_guides = n; w.xtab = d_xtab;
+                w.st[0] = m.st[0]; w.st[1] = m.st[1]; w.gq = m.gq; w.skip = m.skip; w.n_guides = n; w.xtab = d_xtab; w.n_xtab = (uint32_t)xtab.size();
                 w.M = m.p.M; w.plen = m.plen; w.pampack = m.pampack;
                 {   // enough work units per slice that the whole grid stays within about one slice (L2 residency)
                     const int sv = env_int("GSX_SWEEP_VARIANT", 2);
@@ -576,7 +576,7 @@ static void run_device_job(DeviceJob* job) {
         uint32_t spill_cap = wide ? 8192 : 2048;
         if (env_int("GSX_MATCH_CAP", 0) > 0) match_cap = (uint64_t)env_int("GSX_MATCH_CAP", 0);      // tests: force the retry path
         if (env_int("GSX_SPILL_CAP", 0) > 0) spill_cap = (uint32_t)env_int("GSX_SPILL_CAP", 0);
-        MatchRec* d_matches = nullptr; uint32_t* d_spill = nullptr; uint32_t n_matches = 0;
+        MatchRec* d_matches = nullptr; uint32_t* d_spill = nullptr; uint32_t n_matches = 0, n_seeds_used = 0;
         if (use_fast && ftab_L && !use_sweep) {
             std::vector<uint64_t> cb = ftab_combos(ftab_L - 2, p.mismatches);
             uint64_t* d_cb = B.alloc<uint64_t>(cb.size());
@@ -608,7 +608,7 @@ static void run_device_job(DeviceJob* job) {
                 if (match_cap > (1ull << 31)) throw std::runtime_error("more than 2^31 matches in one batch; lower the batch size");
                 continue;
             }
-            n_matches = h[1];
+            n_matches = h[1]; n_seeds_used = use_sweep ? h[3] : 0;
             break;
         }
         CK(cudaEventRecord(ev[1], s));
@@ -675,7 +675,7 @@ static void run_device_job(DeviceJob* job) {
         CK(cudaEventElapsedTime(&ms, ev[3], ev[4])); job->ctr.ms_score = ms;
         CK(cudaEventElapsedTime(&ms, ev[0], ev[4])); job->ctr.ms_total_device = ms;
         CK(cudaEventElapsedTime(&ms, ev[4], ev[5])); job->ctr.ms_d2h = ms;
-        CK(cudaEventElapsedTime(&ms, ev[6], ev[7])); job->ctr.ms_sweep = ms; job->ctr.seeds = st[6];
+        CK(cudaEventElapsedTime(&ms, ev[6], ev[7])); job->ctr.ms_sweep = ms; job->ctr.seeds = n_seeds_used;
         job->ctr.nodes = st[0]; job->ctr.lookups = st[1]; job->ctr.spills = st[2]; job->ctr.lf_steps = st[3];
         job->ctr.matches = n_matches; job->ctr.hits = nh; job->ctr.launches = n_launches;
         for (auto& e : ev) cudaEventDestroy(e);

@@ -738,17 +738,20 @@ int search_fast_grid_warps(int variant, int sm_count) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// search, slice-major front end (large batches on the fast path).  The random-access cost of the search is dominated by
-// two kinds of reads per (guide, strand): ~6.6 k jump-table lines and ~10.7 k level-L look-ahead lines (3.1 Gb, m = 3),
-// uniformly scattered over 2 GB + 6 GB per strand -- every one a DRAM line fetch and a TLB miss.  Across a batch of
-// 50 k guides each of those lines is wanted by 10-20 different guides.  The sweep kernel therefore turns the loops
-// inside out: the grid walks the index slice by slice (a slice = all patterns sharing their last `sb` consumed
-// characters = a contiguous range of table entries AND of BWT rows, ~32 MB, L2-resident), and inside a slice it visits
-// every guide of the batch, enumerates that guide's patterns that fall into the slice (gsx_core.h sweep_pattern), reads
-// their table entries and look-ahead lines from L2, and keeps the level-L nodes with a row that can still reach the
-// final level (node_viable).  Survivors (~1 %) go to a queue; search_fast_kernel continues from them (a.seeds).
-// Work unit = (strand, slice, block of 32 guides), handed out slice-major through one counter, so that all warps work
-// on the same one or two slices at any time.  Inside a unit the 32 guides' pattern lists are flattened over the lanes.
+// search, slice-major front end (large batches on the fast path).  After the jump table and the look-ahead planes, what is
+// left of the search is one question per candidate pattern -- "does any row of this 14-mer's interval continue with the
+// guide's next characters and a PAM?" -- asked ~10.7 k times per guide and strand (3.1 Gb, m = 3) and answered by one
+// 32-byte pattern summary each (DevStrand::sum0; gsx_core.h summary_eval*).  Guide by guide those reads are uniformly
+// scattered over 17 GB: every one a DRAM line fetch and a TLB miss.  But a batch of 50-200 k guides wants every summary
+// line several times.  The sweep kernel therefore turns the loops inside out: the grid walks the index slice by slice
+// (a slice = all patterns sharing their last `sb` consumed characters = a contiguous 1/4^sb of the table and of the
+// summaries, L2-resident), and inside a slice it visits every guide of the batch and tests that guide's patterns that
+// fall into the slice (xor table of substitution choices, gsx_core.h sweep_pattern).  Survivors (~1 %) go to a queue;
+// search_fast_kernel continues from them (a.seeds).
+// Work unit = (strand, slice, block of 32 guides), handed out slice-major through one counter, so that all warps work on
+// the same few slices at any time.  Inside a unit: (1) one lane-parallel step for the guides whose only pattern in the
+// slice is the unsubstituted one, (2) the guides with budget left one at a time, all 32 lanes on the same guide -- its
+// filter masks in registers, the xor table read with unit stride from shared memory, two summary loads in flight per lane.
 // ---------------------------------------------------------------------------------------------------------
 static inline int grid_for_n(uint32_t n, int threads, int cap) { long b = ((long)n + threads - 1) / threads; if (b < 1) b = 1; if (b > cap) b = cap; return (int)b; }
 
@@ -761,7 +764,7 @@ struct DevSummaryLoader {
     }
 };
 
-struct SweepStats { uint32_t nodes, lookups, patterns, sectors, seeds; };
+struct SweepStats { uint32_t nodes, lookups; };          // per lane; everything else is derived (patterns per run, seeds = queue length)
 
 // per-warp buffer of nodes whose first 16 rows are dead but which have more (gsx_core.h summary_eval, stage 1): 64 records
 // in shared memory
@@ -797,7 +800,6 @@ __device__ __forceinline__ void sweep_emit(const SweepArgs& a, uint32_t lane, bo
             const uint2 e = __ldg(reinterpret_cast<const uint2*>(tab + idx));
             SeedNode sn; sn.sp = e.x; sn.ep = e.x + e.y - 1u; sn.idx = idx; sn.tlm = (tlm & 0x07FFFFFFu) | (a.plan.L << 27);
             a.queue[slot] = sn;
-            st.seeds++;
         } else atomicOr(a.error_flag, GSX_KERR_QUEUE_OVERFLOW);
     }
 }
@@ -816,7 +818,6 @@ __device__ __forceinline__ void cont_process(const SweepArgs& a, ContBuf& cb, ui
     if (mine) {
         DevSummaryLoader ld; ld.sum0 = nullptr; ld.sum1 = (tlm & 1u) ? a.st[1].sum1 : a.st[0].sum1;
         summary_eval<NB>(ld, 1u, idx, codes, (tlm >> 27) & 7u, u);
-        st.sectors++;
     }
     sweep_emit(a, lane, mine && u[0] != 0u, idx, tlm, st);
 }
@@ -825,6 +826,8 @@ __device__ __forceinline__ void cont_process(const SweepArgs& a, ContBuf& cb, ui
 // each work unit, read back by whichever lanes end up working on that guide's patterns
 //   [0..6] A, [7..13] X, [14] pflags (gsx_core.h summary_masks)   [15] low 2(L-sb) bits of the packed guide
 //   [16] plane codes   per work unit: [17] first pattern number (prefix sum)  [18] xor-table offset  [19] remaining budget
+constexpr int CB_SLOTS = 64;          // parked nodes per warp: drained below 32 before every step, which adds at most 32
+constexpr int XT_SMEM = 4352;          // words of shared memory for the xor table (17 KB)
 constexpr int GT_WORDS = 20, GT_QLOW = 15, GT_CODES = 16, GT_EXCL = 17, GT_XOFF = 18, GT_B = 19;
 
 __global__ void sweep_guides_kernel(SweepArgs a, uint32_t* __restrict__ gtab) {
@@ -840,18 +843,18 @@ __global__ void sweep_guides_kernel(SweepArgs a, uint32_t* __restrict__ gtab) {
     }
 }
 
-// one pattern of one guide against its summary sector; EXACT = no budget left (one row mask)
-template <bool EXACT, int NB>
-__device__ __forceinline__ void sweep_test(const SweepArgs& a, const unsigned char* sum0, uint32_t idx, uint32_t qlow, const uint32_t gm[15],
-                                           uint32_t budget, bool& emit, bool& park, SweepStats& st) {
-    uint32_t w[8];
+__device__ __forceinline__ void sweep_load(const unsigned char* sum0, uint32_t idx, uint32_t w[8]) {
     asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"                                           // LDG.E.256
                  : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
                  : "l"(sum0 + ((size_t)idx << 5)));
+}
+// one pattern of one guide against its summary sector; EXACT = no budget left (one row mask)
+template <bool EXACT, int NB>
+__device__ __forceinline__ void sweep_judge(const uint32_t w[8], uint32_t idx, uint32_t qlow, const uint32_t gm[15], uint32_t budget,
+                                            bool& emit, bool& park, SweepStats& st) {
     uint32_t alive;
     if (EXACT) alive = summary_eval_exact(w, gm);
     else { uint32_t u[NB]; summary_eval_masks<NB>(w, gm, budget, u); alive = u[0]; }
-    st.patterns++; st.sectors++;
     if (((idx ^ qlow) & 15u) == 0u) st.lookups++;                             // one table line per 16 beginnings
     if (w[0] & 0xFFFFu) {
         st.nodes++; st.lookups += (w[0] & SUM_TWO_BLOCKS) ? 2u : 1u;
@@ -861,29 +864,33 @@ __device__ __forceinline__ void sweep_test(const SweepArgs& a, const unsigned ch
 }
 
 // all patterns of ONE guide (lane `o` of the unit) in one pass, 32 per step: the guide's masks sit in registers, the xor
-// table is read with unit stride, nothing is looked up per lane but the summary sector itself
+// table (shared memory when it fits) is read with unit stride, nothing is looked up per lane but the summary sector itself.
+// (Two summary loads in flight per lane were tried and lost to register pressure: profiles/r01x_*.)
 template <bool ZERO, int NB>
-__device__ __forceinline__ void sweep_run(const SweepArgs& a, const SweepPlan& pl, ContBuf& cb, const uint32_t* sg, uint32_t lane, uint32_t strand,
-                                          uint32_t hi_bits, uint32_t guide, uint32_t o, uint32_t B, SweepStats& st) {
+__device__ __forceinline__ void sweep_run(const SweepArgs& a, const SweepPlan& pl, ContBuf& cb, const uint32_t* sg, const uint32_t* xtab, uint32_t lane,
+                                          uint32_t strand, uint32_t hi_bits, uint32_t guide, uint32_t o, uint32_t B, SweepStats& st) {
     const uint32_t M = a.M, n = pl.xcnt[ZERO ? 1 : 0][B];
     if (n == 0u) return;
-    const uint32_t* xt = a.xtab + pl.xoff[ZERO ? 1 : 0][B];
+    const uint32_t* xt = xtab + pl.xoff[ZERO ? 1 : 0][B];
     const unsigned char* sum0 = strand ? a.st[1].sum0 : a.st[0].sum0;
     const uint4* gp = reinterpret_cast<const uint4*>(sg + o * GT_WORDS);       // same address in every lane: broadcast
     const uint4 g0 = gp[0], g1 = gp[1], g2 = gp[2], g3 = gp[3];
     const uint32_t gm[15] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w, g2.x, g2.y, g2.z, g2.w, g3.x, g3.y, g3.z};
     const uint32_t qlow = g3.w, codes = sg[o * GT_WORDS + GT_CODES];
+    const uint32_t tl = (guide << 1) | strand;
     for (uint32_t base = 0; base < n; base += 32u) {
         while (cb.count >= 32u) cont_process<NB>(a, cb, lane, st);
         const uint32_t t = base + lane;
         bool emit = false, park = false; uint32_t idx = 0, mm = M;
         if (t < n) {
-            const uint32_t xw = __ldg(xt + t);
+            const uint32_t xw = xt[t];
             idx = hi_bits | (qlow ^ (xw & 0x0FFFFFFFu));
-            if (!ZERO) mm = M - B + (xw >> 28);                               // (the other pass always ends at M)
-            sweep_test<ZERO, NB>(a, sum0, idx, qlow, gm, M - mm, emit, park, st);
+            if (!ZERO) mm = M - B + (xw >> 28);                               // (pass 1 always ends at M)
+            uint32_t w[8];
+            sweep_load(sum0, idx, w);
+            sweep_judge<ZERO, NB>(w, idx, qlow, gm, M - mm, emit, park, st);
         }
-        const uint32_t tlm = ((guide << 1) | strand) | (mm << 24) | ((M - mm) << 27);
+        const uint32_t tlm = tl | (mm << 24) | ((M - mm) << 27);
         sweep_emit(a, lane, emit, idx, tlm, st);
         cont_push(cb, lane, park, idx, codes, tlm);
     }
@@ -892,10 +899,14 @@ __device__ __forceinline__ void sweep_run(const SweepArgs& a, const SweepPlan& p
 template <int WARPS, int MINB, int NB>
 __global__ void __launch_bounds__(WARPS * 32, MINB) sweep_kernel(SweepArgs a) {
     __shared__ SweepPlan s_plan;
-    __shared__ uint32_t s_c32[WARPS][3][64];
+    __shared__ uint32_t s_c32[WARPS][3][CB_SLOTS];
     __shared__ __align__(16) uint32_t s_g[WARPS][33 * GT_WORDS];
+    __shared__ uint32_t s_xtab[XT_SMEM];                  // the xor table, when it fits (it does for up to 3 mismatches)
     for (int i = threadIdx.x; i < (int)(sizeof(SweepPlan) / 4); i += blockDim.x)
         reinterpret_cast<uint32_t*>(&s_plan)[i] = reinterpret_cast<const uint32_t*>(&a.plan)[i];
+    const bool xt_shared = a.n_xtab <= (uint32_t)XT_SMEM;
+    if (xt_shared) for (uint32_t i = threadIdx.x; i < a.n_xtab; i += blockDim.x) s_xtab[i] = a.xtab[i];
+    const uint32_t* xtab = xt_shared ? s_xtab : a.xtab;
     __syncthreads();
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, FULL = 0xffffffffu;
     ContBuf cb;
@@ -904,8 +915,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) sweep_kernel(SweepArgs a) {
     const uint32_t L = s_plan.L, sb = s_plan.sb, M = a.M;
     const uint32_t n_slices = 1u << (2u * sb), n_gb = (a.n_guides + 31u) >> 5;
     const uint64_t items_per_strand = (uint64_t)n_slices * n_gb, n_items = 2ull * items_per_strand;
-    unsigned long long n_nodes = 0, n_lookups = 0, n_patterns = 0, n_sectors = 0, n_seeds = 0;
-    SweepStats st = {0, 0, 0, 0, 0};
+    SweepStats st = {0, 0};
     for (;;) {
         uint32_t item = 0;
         if (lane == 0) item = atomicAdd(a.item_counter, 1u);
@@ -938,7 +948,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) sweep_kernel(SweepArgs a) {
                 const uint32_t gm[15] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w, g2.x, g2.y, g2.z, g2.w, g3.x, g3.y, g3.z};
                 codes = sg[lane * GT_WORDS + GT_CODES];
                 idx = hi_bits | g3.w;
-                sweep_test<false, NB>(a, strand ? a.st[1].sum0 : a.st[0].sum0, idx, g3.w, gm, (uint32_t)B, emit, park, st);
+                uint32_t w[8];
+                sweep_load(strand ? a.st[1].sum0 : a.st[0].sum0, idx, w);
+                sweep_judge<false, NB>(w, idx, g3.w, gm, (uint32_t)B, emit, park, st);
             }
             const uint32_t tlm = ((g << 1) | strand) | ((M - (uint32_t)(B > 0 ? B : 0)) << 24) | ((uint32_t)(B > 0 ? B : 0) << 27);
             sweep_emit(a, lane, emit, idx, tlm, st);
@@ -950,23 +962,14 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) sweep_kernel(SweepArgs a) {
         while (todo) {
             const uint32_t o = (uint32_t)__ffs(todo) - 1u; todo &= todo - 1u;
             const uint32_t Bo = (uint32_t)__shfl_sync(FULL, B, o);
-            sweep_run<true, NB>(a, s_plan, cb, sg, lane, strand, hi_bits, gb * 32u + o, o, Bo, st);
-            if (Bo >= 2u) sweep_run<false, NB>(a, s_plan, cb, sg, lane, strand, hi_bits, gb * 32u + o, o, Bo, st);
+            sweep_run<true, NB>(a, s_plan, cb, sg, xtab, lane, strand, hi_bits, gb * 32u + o, o, Bo, st);
+            if (Bo >= 2u) sweep_run<false, NB>(a, s_plan, cb, sg, xtab, lane, strand, hi_bits, gb * 32u + o, o, Bo, st);
         }
-        n_nodes += st.nodes; n_lookups += st.lookups; n_patterns += st.patterns; n_sectors += st.sectors; n_seeds += st.seeds;
-        st = {0, 0, 0, 0, 0};
     }
     while (cb.count) cont_process<NB>(a, cb, lane, st);
-    n_sectors += st.sectors; n_seeds += st.seeds;
-    for (int o = 16; o; o >>= 1) {
-        n_nodes += __shfl_xor_sync(FULL, n_nodes, o); n_lookups += __shfl_xor_sync(FULL, n_lookups, o);
-        n_patterns += __shfl_xor_sync(FULL, n_patterns, o); n_sectors += __shfl_xor_sync(FULL, n_sectors, o);
-        n_seeds += __shfl_xor_sync(FULL, n_seeds, o);
-    }
-    if (lane == 0) {
-        atomicAdd(a.stats + 0, n_nodes); atomicAdd(a.stats + 1, n_lookups); atomicAdd(a.stats + 4, n_patterns);
-        atomicAdd(a.stats + 5, n_sectors); atomicAdd(a.stats + 6, n_seeds);
-    }
+    unsigned long long n_nodes = st.nodes, n_lookups = st.lookups;
+    for (int o = 16; o; o >>= 1) { n_nodes += __shfl_xor_sync(FULL, n_nodes, o); n_lookups += __shfl_xor_sync(FULL, n_lookups, o); }
+    if (lane == 0) { atomicAdd(a.stats + 0, n_nodes); atomicAdd(a.stats + 1, n_lookups); }
 }
 
 cudaError_t launch_sweep_guides(const SweepArgs& a, cudaStream_t s) {

@@ -51,6 +51,7 @@ struct SweepArgs {
     uint32_t n_guides;
     SweepPlan plan;
     const uint32_t* xtab;              // gsx_core.h sweep_pattern
+    uint32_t n_xtab;
     uint32_t* gtab;                    // n_guides * 20 words: per-guide constants, written by launch_sweep_guides
     uint32_t M, plen, pampack;
     uint32_t parts;                    // each (slice, 32 guides) unit is cut into this many work units (keeps all warps on the same slices)

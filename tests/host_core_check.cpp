@@ -91,6 +91,107 @@ static void build_ftab_host(const DevStrand& st, uint32_t L, std::vector<FtabEnt
     tab.swap(cur);
 }
 
+// ---- independent statement of the sweep kernel's row filter, row block by row block over the 128-byte look-ahead lines
+// (the product evaluates the same predicate from its pattern summaries: gsx_core.h summary_eval*; the harness checks that
+// both agree on every pattern it visits) --------------------------------------------------------------------------------
+namespace gsx {
+// can ANY row of [sp, ep] (inside one block or two adjacent ones) still reach the
+// final level?  ld(block, k, w) fetches 32-byte sector k of the block's 128-byte line as four 64-bit words: k = 0 the
+// OccBlock {cnt01, cnt23, hi, lo}, k = 1..3 the planes {hi_(2k-1), lo_(2k-1), hi_2k, lo_2k}.  Sectors are fetched in
+// pairs (0,1) then (2,3) -- two independent loads in flight -- and the second pair only while some row is alive.
+// State: u[r] = rows with at most budget - r mismatches so far (r = 0 .. NB-1, NB > budget), so u[0] = rows still alive;
+// one plane costs one and-or per mask.  Intervals spanning more than two blocks are not examined (true).
+template <int NB, class LoadSector>
+GSX_HD bool node_viable(LoadSector ld, uint32_t sp, uint32_t ep, uint32_t lvl, uint32_t qlen, uint32_t total, uint64_t q,
+                        uint32_t pampack, uint32_t budget, uint32_t& sectors) {
+    const uint32_t e1 = ep + 1u, bs = sp >> 6, be = e1 >> 6;
+    if (be - bs > 1u) return true;
+    const uint32_t left = total - lvl;
+    for (uint32_t part = 0; part < 2u; part++) {
+        if (part == 1u && (be == bs || (e1 & 63u) == 0u)) break;
+        const uint32_t r0 = part ? 0u : (sp & 63u), r1 = part ? (ep & 63u) : (be != bs ? 63u : (ep & 63u));
+        const uint64_t rows = (r1 == 63u ? ~0ull : ((1ull << (r1 + 1u)) - 1ull)) & ~((1ull << r0) - 1ull);
+        uint64_t u[NB];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int r = 0; r < NB; r++) u[r] = budget >= (uint32_t)r ? rows : 0ull;
+        for (uint32_t pair = 0; pair < 2u; pair++) {
+            const uint32_t j0 = pair ? 3u : 0u;
+            if (j0 >= left || !u[0]) break;
+            uint64_t wa[4], wb[4] = {0, 0, 0, 0};
+            ld(bs + part, 2u * pair, wa); sectors++;
+            if ((pair ? 5u : 1u) < left) { ld(bs + part, 2u * pair + 1u, wb); sectors++; }
+            // planes of this pair: pair 0 -> t0 (OccBlock), t1, t2 ; pair 1 -> t3, t4, t5, t6
+            const uint64_t ph[4] = {pair ? wa[0] : wa[2], pair ? wa[2] : wb[0], pair ? wb[0] : wb[2], wb[2]};
+            const uint64_t pl[4] = {pair ? wa[1] : wa[3], pair ? wa[3] : wb[1], pair ? wb[1] : wb[3], wb[3]};
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (uint32_t t = 0; t < 4u; t++) {
+                const uint32_t j = j0 + t;
+                if (j >= left || (pair == 0u && t == 3u)) break;
+                const uint32_t Lv = lvl + j;
+                uint32_t sym; const bool proto = Lv < qlen; bool wild = false, kill = false;
+                if (proto) sym = (uint32_t)(q >> (2u * Lv)) & 3u;
+                else { const uint32_t pc = (pampack >> (3u * (Lv - qlen))) & 7u; sym = pc & 3u; wild = pc == 4u; kill = pc > 4u; }
+                const uint64_t eq = ~(ph[t] ^ ((sym & 2u) ? ~0ull : 0ull)) & ~(pl[t] ^ ((sym & 1u) ? ~0ull : 0ull));
+                if (proto) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+                    for (int r = 0; r + 1 < NB; r++) u[r] = (u[r] & eq) | u[r + 1];
+                    u[NB - 1] &= eq;
+                } else if (!wild) {
+                    const uint64_t keep = kill ? 0ull : eq;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+                    for (int r = 0; r < NB; r++) u[r] &= keep;
+                }
+            }
+        }
+        if (u[0]) return true;
+    }
+    return false;
+}
+
+// The same test for a node with no budget left (9 of 10 level-L nodes at m = 3): a row survives a protospacer plane only
+// if its symbol equals the query character, so one mask is enough.
+template <class LoadSector>
+GSX_HD bool node_viable_exact(LoadSector ld, uint32_t sp, uint32_t ep, uint32_t lvl, uint32_t qlen, uint32_t total, uint64_t q,
+                              uint32_t pampack, uint32_t& sectors) {
+    const uint32_t e1 = ep + 1u, bs = sp >> 6, be = e1 >> 6;
+    if (be - bs > 1u) return true;
+    const uint32_t left = total - lvl;
+    for (uint32_t part = 0; part < 2u; part++) {
+        if (part == 1u && (be == bs || (e1 & 63u) == 0u)) break;
+        const uint32_t r0 = part ? 0u : (sp & 63u), r1 = part ? (ep & 63u) : (be != bs ? 63u : (ep & 63u));
+        uint64_t alive = (r1 == 63u ? ~0ull : ((1ull << (r1 + 1u)) - 1ull)) & ~((1ull << r0) - 1ull);
+        uint64_t wa[4], wb[4] = {0, 0, 0, 0};
+#define GSX_EXACT_PLANE(J, HI, LO)                                                                                     \
+        if ((J) < left) {                                                                                             \
+            const uint32_t Lv = lvl + (J);                                                                            \
+            uint32_t pc = Lv < qlen ? ((uint32_t)(q >> (2u * Lv)) & 3u) : ((pampack >> (3u * (Lv - qlen))) & 7u);       \
+            if (pc < 4u) alive &= ~((HI) ^ ((pc & 2u) ? ~0ull : 0ull)) & ~((LO) ^ ((pc & 1u) ? ~0ull : 0ull));         \
+            else if (pc > 4u) alive = 0;                                                                              \
+        }
+        ld(bs + part, 0u, wa); sectors++;
+        if (1u < left) { ld(bs + part, 1u, wb); sectors++; }
+        GSX_EXACT_PLANE(0u, wa[2], wa[3]) GSX_EXACT_PLANE(1u, wb[0], wb[1]) GSX_EXACT_PLANE(2u, wb[2], wb[3])
+        if (alive && 3u < left) {
+            ld(bs + part, 2u, wa); sectors++;
+            if (5u < left) { ld(bs + part, 3u, wb); sectors++; }
+            GSX_EXACT_PLANE(3u, wa[0], wa[1]) GSX_EXACT_PLANE(4u, wa[2], wa[3]) GSX_EXACT_PLANE(5u, wb[0], wb[1]) GSX_EXACT_PLANE(6u, wb[2], wb[3])
+        }
+#undef GSX_EXACT_PLANE
+        if (alive) return true;
+    }
+    return false;
+}
+
+}  // namespace gsx
+
 // slice-major front end (what sweep_kernel does): per task, the level-L nodes that pass node_viable
 static uint32_t g_sweep_sb = 0;
 static std::map<uint32_t, std::vector<std::vector<Node>>> g_seeds_by_M;

@@ -35,6 +35,14 @@ def opts_of(args):
 
 
 @pytest.fixture(scope="module")
+def gsx():
+    import gsx as g
+    if g.device_count() < 1:
+        pytest.fail("no CUDA device: the product has no CPU path")
+    return g
+
+
+@pytest.fixture(scope="module")
 def fasta(tmp_path_factory):
     p = str(tmp_path_factory.mktemp("kmers") / "kmers.fa")
     open(p, "wb").write(gzip.open(os.path.join(GOLD, "kmers.fa.gz"), "rb").read())

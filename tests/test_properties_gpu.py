@@ -11,7 +11,7 @@ for a, b in zip(b"ACGTN", b"TGCAN"):
     COMP[a] = b
 
 
-def _run_case(G, n_chr, n_guides, seed, n_plant, brute_guides):
+def _run_case(G, n_chr, n_guides, seed, n_plant, brute_guides, extra=None):
     import gsx
     import synth
     g = synth.make_genome(G, seed)
@@ -106,7 +106,10 @@ def _run_case(G, n_chr, n_guides, seed, n_plant, brute_guides):
         b, n = int(first[gidx]), int(ga["n_hits"][gidx])
         assert set(ab[b:b + n].tolist()) == want
     ctr = r.counters()
-    r.close(); ix.close()
+    r.close()
+    if extra is not None:
+        extra(gsx, ix, g, chroms, kmers)
+    ix.close()
     return ctr
 
 
@@ -116,7 +119,44 @@ def test_config1_size_120mb_100k_guides():
     assert ctr["nodes"] > 100_000 * 2_000      # sanity only: the count depends on the index layout (jump table, look-ahead)
 
 
+def _oracle_samples_at_full_size(gsx, ix, g, chroms, kmers):
+    """Small samples of BASELINE.json configs[2], [3] and [4] on the SAME 3.1 Gb index, byte for byte against the CPU oracle
+    (oracle/gs_oracle.c over the FM-index exported from the device builder): no bulges / m=3+rna1+dna1 (deep, skewed
+    backtracking through the general kernel) / m=4 with the NAG alt-PAM, SAM complete mode."""
+    import os
+    import sys
+    import tempfile
+    from conftest import ROOT
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as O
+    b0, b1 = ix.export_bwt(0), ix.export_bwt(1)
+    (s0, sh0), (s1, sh1) = ix.export_sa_samples(0), ix.export_sa_samples(1)
+    assert sh0 == 6 and sh1 == 6
+    oix = O.Index.from_bwt(b0, s0, b1, s1, chroms)
+    del b0, b1
+    cases = [("cfg2", 64, dict(mismatches=3), {}),
+             ("cfg3", 6, dict(mismatches=3, rna_bulges=1, dna_bulges=1), {}),
+             ("cfg4", 24, dict(mismatches=4, alt_pams=("NAG",), fmt="sam"), {})]
+    with tempfile.TemporaryDirectory() as d:
+        for tag, n, kw, _ in cases:
+            gcsv = os.path.join(d, tag + ".csv")
+            with open(gcsv, "w") as f:
+                f.write("id,sequence,pam,chromosome,position,sense\n")
+                for i in range(n):
+                    f.write("g%d,%s,NGG,chr1,1,%s\n" % (i, kmers[1000 + i, :20].tobytes().decode(), "+-"[i & 1]))
+            want, got = os.path.join(d, tag + ".o"), os.path.join(d, tag + ".g")
+            oix.enumerate_file(O.make_opts(**kw), gcsv, want, nthreads=os.cpu_count() or 4)
+            p = gsx.make_params(mismatches=kw["mismatches"], rna_bulges=kw.get("rna_bulges", 0), dna_bulges=kw.get("dna_bulges", 0),
+                                alt_pams=kw.get("alt_pams", ()))
+            ix.enumerate_file(gcsv, got, p, fmt=kw.get("fmt", "csv"))
+            a, b = open(got, "rb").read(), open(want, "rb").read()
+            assert a == b, "%s: GPU output differs from the oracle at 3.1 Gb" % tag
+            assert a.count(b"\n") > n
+    oix.close()
+
+
 def test_config2_size_3100mb():
-    """BASELINE.json configs[2] genome size (3.1 Gb); 200k guides keep the host-side verification short"""
-    ctr = _run_case(3_100_000_000, 24, 200_000, seed=3, n_plant=1000, brute_guides=0)
+    """BASELINE.json configs[2] genome size (3.1 Gb); 200k guides keep the host-side verification short.  The same index then
+    serves small oracle-checked samples of configs[2..4] (bulges, alt PAM, m=4, SAM)."""
+    ctr = _run_case(3_100_000_000, 24, 200_000, seed=3, n_plant=1000, brute_guides=0, extra=_oracle_samples_at_full_size)
     assert ctr["nodes"] > 200_000 * 4_000
