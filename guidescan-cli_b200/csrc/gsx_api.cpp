@@ -676,6 +676,7 @@ static void run_device_job(DeviceJob* job) {
         CK(cudaEventElapsedTime(&ms, ev[0], ev[4])); job->ctr.ms_total_device = ms;
         CK(cudaEventElapsedTime(&ms, ev[4], ev[5])); job->ctr.ms_d2h = ms;
         CK(cudaEventElapsedTime(&ms, ev[6], ev[7])); job->ctr.ms_sweep = ms; job->ctr.seeds = n_seeds_used;
+        job->ctr.sectors = use_sweep ? st[5] + st[7] : st[1];
         job->ctr.nodes = st[0]; job->ctr.lookups = st[1]; job->ctr.spills = st[2]; job->ctr.lf_steps = st[3];
         job->ctr.matches = n_matches; job->ctr.hits = nh; job->ctr.launches = n_launches;
         for (auto& e : ev) cudaEventDestroy(e);
@@ -744,7 +745,7 @@ extern "C" int gsx_enumerate(const gsx_index* ix, const gsx_guide* guides, size_
         r->part_g0.push_back(g); r->part_h0.push_back(h); g += j.out.n_guides; h += j.out.n_hits;
         r->parts.push_back(std::move(j.out));
         gsx_counters& c = r->counters;
-        c.nodes += j.ctr.nodes; c.lookups += j.ctr.lookups; c.matches += j.ctr.matches; c.hits += j.ctr.hits; c.lf_steps += j.ctr.lf_steps; c.spills += j.ctr.spills; c.launches += j.ctr.launches; c.seeds += j.ctr.seeds;
+        c.nodes += j.ctr.nodes; c.lookups += j.ctr.lookups; c.matches += j.ctr.matches; c.hits += j.ctr.hits; c.lf_steps += j.ctr.lf_steps; c.spills += j.ctr.spills; c.launches += j.ctr.launches; c.seeds += j.ctr.seeds; c.sectors += j.ctr.sectors;
         c.ms_sweep = std::max(c.ms_sweep, j.ctr.ms_sweep);
         c.ms_search = std::max(c.ms_search, j.ctr.ms_search); c.ms_arrange = std::max(c.ms_arrange, j.ctr.ms_arrange);
         c.ms_locate = std::max(c.ms_locate, j.ctr.ms_locate); c.ms_score = std::max(c.ms_score, j.ctr.ms_score);

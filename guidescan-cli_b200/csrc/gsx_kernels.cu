@@ -703,7 +703,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) search_fast_kernel(SearchArg
         if (total) { __syncwarp(); count += total; }
         has = kept; sp = nsp; ep = nep; tlm = ntlm; key = nkey;
     }
-    if (lane == 0) { atomicAdd(a.stats + 0, n_nodes); atomicAdd(a.stats + 1, n_lookups); atomicAdd(a.stats + 2, n_spilled); }
+    if (lane == 0) { atomicAdd(a.stats + 0, n_nodes); atomicAdd(a.stats + 1, n_lookups); atomicAdd(a.stats + 2, n_spilled); atomicAdd(a.stats + 7, n_lookups); }
 }
 
 template <int WARPS, int CAP, int MINB, bool LOOK>
@@ -764,7 +764,7 @@ struct DevSummaryLoader {
     }
 };
 
-struct SweepStats { uint32_t nodes, lookups; };          // per lane; everything else is derived (patterns per run, seeds = queue length)
+struct SweepStats { uint32_t nodes, lookups, sectors; };  // nodes, lookups: per lane; sectors (32-byte summary loads issued): warp-uniform
 
 // per-warp buffer of nodes whose first 16 rows are dead but which have more (gsx_core.h summary_eval, stage 1): 64 records
 // in shared memory
@@ -814,7 +814,7 @@ __device__ __forceinline__ void cont_process(const SweepArgs& a, ContBuf& cb, ui
     for (int r = 0; r < NB; r++) u[r] = 0;
     if (mine) { const uint32_t slot = cb.count - n + lane; idx = cb.idx[slot]; codes = cb.codes[slot]; tlm = cb.tlm[slot]; }
     __syncwarp();
-    cb.count -= n;
+    cb.count -= n; st.sectors += n;
     if (mine) {
         DevSummaryLoader ld; ld.sum0 = nullptr; ld.sum1 = (tlm & 1u) ? a.st[1].sum1 : a.st[0].sum1;
         summary_eval<NB>(ld, 1u, idx, codes, (tlm >> 27) & 7u, u);
@@ -878,6 +878,7 @@ __device__ __forceinline__ void sweep_run(const SweepArgs& a, const SweepPlan& p
     const uint32_t gm[15] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w, g2.x, g2.y, g2.z, g2.w, g3.x, g3.y, g3.z};
     const uint32_t qlow = g3.w, codes = sg[o * GT_WORDS + GT_CODES];
     const uint32_t tl = (guide << 1) | strand;
+    st.sectors += n;
     for (uint32_t base = 0; base < n; base += 32u) {
         while (cb.count >= 32u) cont_process<NB>(a, cb, lane, st);
         const uint32_t t = base + lane;
@@ -915,7 +916,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) sweep_kernel(SweepArgs a) {
     const uint32_t L = s_plan.L, sb = s_plan.sb, M = a.M;
     const uint32_t n_slices = 1u << (2u * sb), n_gb = (a.n_guides + 31u) >> 5;
     const uint64_t items_per_strand = (uint64_t)n_slices * n_gb, n_items = 2ull * items_per_strand;
-    SweepStats st = {0, 0};
+    SweepStats st = {0, 0, 0};
     for (;;) {
         uint32_t item = 0;
         if (lane == 0) item = atomicAdd(a.item_counter, 1u);
@@ -942,6 +943,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) sweep_kernel(SweepArgs a) {
         //     the guides with budget 1: one pattern per lane, each lane with its own guide's masks
         {
             bool emit = false, park = false; uint32_t idx = 0, codes = 0;
+            st.sectors += __popc(__ballot_sync(FULL, B == 0 || B == 1));
             if (B == 0 || B == 1) {
                 const uint4* gp = reinterpret_cast<const uint4*>(sg + lane * GT_WORDS);
                 const uint4 g0 = gp[0], g1 = gp[1], g2 = gp[2], g3 = gp[3];
@@ -969,7 +971,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) sweep_kernel(SweepArgs a) {
     while (cb.count) cont_process<NB>(a, cb, lane, st);
     unsigned long long n_nodes = st.nodes, n_lookups = st.lookups;
     for (int o = 16; o; o >>= 1) { n_nodes += __shfl_xor_sync(FULL, n_nodes, o); n_lookups += __shfl_xor_sync(FULL, n_lookups, o); }
-    if (lane == 0) { atomicAdd(a.stats + 0, n_nodes); atomicAdd(a.stats + 1, n_lookups); }
+    if (lane == 0) { atomicAdd(a.stats + 0, n_nodes); atomicAdd(a.stats + 1, n_lookups); atomicAdd(a.stats + 5, (unsigned long long)st.sectors); }
 }
 
 cudaError_t launch_sweep_guides(const SweepArgs& a, cudaStream_t s) {

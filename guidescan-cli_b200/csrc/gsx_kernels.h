@@ -28,7 +28,7 @@ struct SearchArgs {
     unsigned long long* guide_count;   // per guide, counting pass only
     uint32_t* task_counter;
     uint32_t* spill;                   // warps_total * spill_cap * node_words u32
-    unsigned long long* stats;         // [0] nodes [1] lookups [2] spilled nodes [3] LF steps
+    unsigned long long* stats;         // [0] nodes [1] lookups [2] spilled nodes [3] LF steps [7] lookups of search_fast_kernel alone
     uint32_t* error_flag;
     uint32_t max_iters;
     uint32_t max_pams;
@@ -57,7 +57,7 @@ struct SweepArgs {
     uint32_t parts;                    // each (slice, 32 guides) unit is cut into this many work units (keeps all warps on the same slices)
     SeedNode* queue; uint32_t queue_cap;
     uint32_t* queue_count; uint32_t* item_counter; uint32_t* error_flag;
-    unsigned long long* stats;         // [0] nodes [1] lookups [4] patterns [5] sectors [6] seeds
+    unsigned long long* stats;         // [0] nodes [1] lookups (reference unit) [5] summary sectors loaded
 };
 
 struct LocateArgs {

@@ -91,7 +91,7 @@ typedef struct {
 /* Work counters of one gsx_enumerate call (all devices summed). */
 typedef struct {
     uint64_t nodes;            /* search-tree nodes expanded by the search kernel */
-    uint64_t lookups;          /* occurrence-block (32 B sector) lookups issued by the search kernel */
+    uint64_t lookups;          /* occurrence-block lookups in the reference's unit (1 per jump-table line, 1-2 per node) */
     uint64_t matches;          /* SA intervals emitted (before de-duplication) */
     uint64_t hits;             /* located rows */
     uint64_t lf_steps;         /* LF steps of the locate kernel */
@@ -103,6 +103,7 @@ typedef struct {
     uint64_t seeds;            /* level-L nodes the front end handed to the tree search */
     double   ms_prepare;       /* host: guide validation / packing before the first device call */
     double   ms_wall;          /* host: wall time of the whole gsx_enumerate call */
+    uint64_t sectors;          /* 32-byte index sectors the search kernels actually requested (= lookups when the front end is off) */
 } gsx_counters;
 
 /* ---- index ------------------------------------------------------------------------------------------- */
