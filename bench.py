@@ -102,6 +102,7 @@ def dist_setup(n_gpus):
     local = int(os.environ.get("LOCAL_RANK", 0))
     dist = None
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("GSX_NCCL_DEBUG", "WARN")     # (the VERSION banner would land on stdout, next to the JSON line)
         import torch
         import torch.distributed as dist_mod
         torch.cuda.set_device(local)

@@ -73,7 +73,7 @@ static void upload_index(gsx_index* ix, const int* devices, int n_devices) {
             for (int c = 0; c < 5; c++) d.d.C[c] = h.C[c];
             d.d.exc_lo = h.exc_rows.empty() ? 0xFFFFFFFFu : h.exc_rows.front();
             d.d.exc_hi = h.exc_rows.empty() ? 0u : h.exc_rows.back();
-            d.d.blk_shift = 5; d.d.lines = nullptr; d.d.sum0 = nullptr; d.d.sum1 = nullptr; d.d.ftab = nullptr; d.d.ftab_L = 0;
+            d.d.blk_shift = 5; d.d.lines = nullptr; d.d.sum0 = nullptr; d.d.sum1 = nullptr; d.d.sum2 = nullptr; d.d.ftab = nullptr; d.d.ftab_L = 0;
             {
                 // k-mer jump table: depth L such that a level-L interval still holds a handful of rows
                 int L = env_int("GSX_FTAB", -1);
@@ -91,20 +91,27 @@ static void upload_index(gsx_index* ix, const int* devices, int n_devices) {
             }
             if (env_int("GSX_LOOKAHEAD", 1)) {
                 // second copy for narrow intervals: one 128-byte line per 64 rows = OccBlock + look-ahead planes t1..t6,
-                // derived on the device by LF walks over the packed blocks
+                // derived on the device by LF walks over the packed blocks (t7, t8 into a scratch array for the summaries)
                 const uint32_t nb = (uint32_t)h.blocks.size();
+                const bool summaries = d.d.ftab && env_int("GSX_SWEEP_SUMMARY", 1);
+                void* tail = nullptr;
                 CK(cudaMalloc(&d.lines, (size_t)nb * 128));
-                CK(launch_build_lookahead(d.d, (unsigned char*)d.lines, nb, 0));
+                if (summaries && env_int("GSX_SWEEP_TAIL", 1)) CK(cudaMalloc(&tail, (size_t)nb * 32));
+                CK(launch_build_lookahead(d.d, (unsigned char*)d.lines, (unsigned char*)tail, nb, 0));
                 CK(cudaDeviceSynchronize());
                 d.d.lines = (const unsigned char*)d.lines; di.bytes += (uint64_t)nb * 128;
-                if (d.d.ftab && env_int("GSX_SWEEP_SUMMARY", 1)) {
-                    // pattern summaries for the slice-major front end (sweep_kernel): 2 x 32 bytes per jump-table entry
+                if (summaries) {
+                    // pattern summaries for the slice-major front end (sweep_kernel): 2 x 32 (+ 16) bytes per jump-table entry
                     const uint64_t n_entries = 1ull << (2 * d.d.ftab_L);
                     CK(cudaMalloc(&d.sum0, n_entries * 32)); CK(cudaMalloc(&d.sum1, n_entries * 32));
-                    CK(launch_build_summary(d.ftab, (const unsigned char*)d.lines, (unsigned char*)d.sum0, (unsigned char*)d.sum1, n_entries, 0));
+                    if (tail) CK(cudaMalloc(&d.sum2, n_entries * 16));
+                    CK(launch_build_summary(d.ftab, (const unsigned char*)d.lines, (const unsigned char*)tail, (unsigned char*)d.sum0,
+                                            (unsigned char*)d.sum1, (unsigned char*)d.sum2, n_entries, 0));
                     CK(cudaDeviceSynchronize());
-                    d.d.sum0 = (const unsigned char*)d.sum0; d.d.sum1 = (const unsigned char*)d.sum1; di.bytes += n_entries * 64;
+                    d.d.sum0 = (const unsigned char*)d.sum0; d.d.sum1 = (const unsigned char*)d.sum1; d.d.sum2 = (const unsigned char*)d.sum2;
+                    di.bytes += n_entries * (tail ? 80 : 64);
                 }
+                cudaFree(tail);
             }
         }
         di.chroms = (Chrom*)upload(ix->chroms, di.bytes);
@@ -114,7 +121,7 @@ static void upload_index(gsx_index* ix, const int* devices, int n_devices) {
 
 static void free_device_index(DeviceIndex& di) {
     cudaSetDevice(di.device);
-    for (int s = 0; s < 2; s++) { cudaFree(di.st[s].blocks); cudaFree(di.st[s].lines); cudaFree(di.st[s].sum0); cudaFree(di.st[s].sum1); cudaFree(di.st[s].ftab); cudaFree(di.st[s].sa); cudaFree(di.st[s].exc_rows); cudaFree(di.st[s].exc_lf); cudaFree(di.st[s].n_rows); }
+    for (int s = 0; s < 2; s++) { cudaFree(di.st[s].blocks); cudaFree(di.st[s].lines); cudaFree(di.st[s].sum0); cudaFree(di.st[s].sum1); cudaFree(di.st[s].sum2); cudaFree(di.st[s].ftab); cudaFree(di.st[s].sa); cudaFree(di.st[s].exc_rows); cudaFree(di.st[s].exc_lf); cudaFree(di.st[s].n_rows); }
     cudaFree(di.chroms);
 }
 

@@ -421,6 +421,21 @@ GSX_HD uint32_t sweep_codes(uint64_t q, uint32_t L, uint32_t plen, uint32_t pamp
     }
     return codes;
 }
+// the same for the two levels behind them (L + 7, L + 8): 4 bits each
+GSX_HD uint32_t sweep_codes2(uint64_t q, uint32_t L, uint32_t plen, uint32_t pampack) {
+    const uint32_t qlen = (uint32_t)(q >> 58);
+    uint32_t codes = 0;
+    for (uint32_t j = 0; j < 2u; j++) {
+        const uint32_t Lv = L + 7u + j;
+        uint32_t c;
+        if (Lv < qlen) c = (uint32_t)(q >> (2u * Lv)) & 3u;
+        else if (Lv < qlen + plen) { c = (pampack >> (3u * (Lv - qlen))) & 7u; if (c > 4u) c = 5u; c |= 8u; }
+        else c = 7u;
+        codes |= c << (4u * j);
+    }
+    return codes;
+}
+GSX_HD bool sweep_has_tail(uint32_t codes2) { return (codes2 & 15u) != 7u; }
 enum : uint32_t { SUM_WIDE16 = 1u << 16, SUM_WIDE32 = 1u << 17, SUM_TWO_BLOCKS = 1u << 18 };
 
 // One summary sector = header word + seven plane words.  header: bits 0..15 = valid rows (bit i = row i of the sector's 16
@@ -515,21 +530,55 @@ GSX_HD void summary_eval_masks(const uint32_t w[8], const uint32_t gm[15], uint3
     }
 }
 
+// levels L + 7 and L + 8 for the rows that survived the first seven: t = sum2[e] = {hi7, lo7, hi8, lo8} over rows 0..31,
+// half = which 16 of them the masks u[] describe
+template <int NB>
+GSX_HD void summary_tail(const uint32_t t[4], uint32_t half, uint32_t codes2, uint32_t u[NB]) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (uint32_t j = 0; j < 2u; j++) {
+        const uint32_t c = (codes2 >> (4u * j)) & 15u;
+        if (c == 7u || c == 12u) continue;
+        const uint32_t hi = (t[2u * j] >> (16u * half)) & 0xFFFFu, lo = (t[2u * j + 1u] >> (16u * half)) & 0xFFFFu;
+        uint32_t eq = ~((hi ^ ((c & 2u) ? 0xFFFFu : 0u)) | (lo ^ ((c & 1u) ? 0xFFFFu : 0u))) & 0xFFFFu;
+        if (c < 4u) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (int r = 0; r + 1 < NB; r++) u[r] = (u[r] & eq) | u[r + 1];
+            u[NB - 1] &= eq;
+        } else {
+            if (c == 13u) eq = 0u;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (int r = 0; r < NB; r++) u[r] &= eq;
+        }
+    }
+}
+
 // whole-node form (reference semantics for the tests): can any row of the pattern's interval still reach the final level?
 template <int NB, class LoadSummary>
-GSX_HD bool summary_viable(LoadSummary ld, uint32_t idx, uint32_t codes, uint32_t budget) {
-    uint32_t u[NB];
+GSX_HD bool summary_viable(LoadSummary ld, uint32_t idx, uint32_t codes, uint32_t codes2, uint32_t budget) {
+    uint32_t u[NB], t[8];
     const uint32_t head = summary_eval<NB>(ld, 0u, idx, codes, budget, u);
-    if ((head & SUM_WIDE32) || u[0]) return true;
+    if (head & SUM_WIDE32) return true;
+    const bool tail = sweep_has_tail(codes2);
+    if (tail) ld(2u, idx, t);
+    if (u[0] && tail) summary_tail<NB>(t, 0u, codes2, u);
+    if (u[0]) return true;
     if (!(head & SUM_WIDE16)) return false;
     summary_eval<NB>(ld, 1u, idx, codes, budget, u);
+    if (u[0] && tail) summary_tail<NB>(t, 1u, codes2, u);
     return u[0] != 0u;
 }
-// builds the two summary sectors of one table entry from the look-ahead lines; plane(b, j, hi) = 64-bit plane of t_j
-// (hi or lo half of the 2-bit symbol) of 64-row block b
+// builds the summary sectors of one table entry from the look-ahead planes; plane(b, j, hi) = 64-bit plane of t_j
+// (hi or lo half of the 2-bit symbol) of 64-row block b, j = 0..6 (and 7, 8 with_tail)
 template <class Plane>
-GSX_HD void summary_build(Plane plane, uint32_t sp, uint32_t width, uint32_t s0[8], uint32_t s1[8]) {
+GSX_HD void summary_build(Plane plane, bool with_tail, uint32_t sp, uint32_t width, uint32_t s0[8], uint32_t s1[8], uint32_t s2[4]) {
     for (int i = 0; i < 8; i++) s0[i] = s1[i] = 0u;
+    for (int i = 0; i < 4; i++) s2[i] = 0u;
     if (width == 0u) return;
     const uint32_t e1 = sp + width;
     const uint32_t flags = (((e1 >> 6) != (sp >> 6)) ? SUM_TWO_BLOCKS : 0u) | (width > 16u ? SUM_WIDE16 : 0u) | (width > 32u ? SUM_WIDE32 : 0u);
@@ -547,6 +596,13 @@ GSX_HD void summary_build(Plane plane, uint32_t sp, uint32_t width, uint32_t s0[
         s0[1u + j] = (v[0] & 0xFFFFu) | (v[1] << 16);
         s1[1u + j] = (v[0] >> 16) | (v[1] & 0xFFFF0000u);
     }
+    if (with_tail)
+        for (uint32_t j = 7; j < 9u; j++)
+            for (uint32_t h = 0; h < 2u; h++) {
+                uint64_t bits = plane(b, j, h == 0u) >> r0;
+                if (nA < width) bits |= plane(b + 1u, j, h == 0u) << nA;
+                s2[2u * (j - 7u) + h] = (uint32_t)bits & valid;
+            }
 }
 
 // ---- k-mer jump table (specialised search kernels) ------------------------------------------------------------------

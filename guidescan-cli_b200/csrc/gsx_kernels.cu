@@ -325,8 +325,9 @@ cudaError_t launch_build_ftab(const DevStrand& st, uint32_t L, void* tab, void* 
 
 // ---------------------------------------------------------------------------------------------------------
 // look-ahead planes: t_j(r) = BWT[LF^j(r)], j = 1..6, stored behind each OccBlock in its own 128-byte line
+// (optionally also j = 7, 8 into `tail`, a scratch array the pattern summaries are built from)
 // ---------------------------------------------------------------------------------------------------------
-__global__ void build_lookahead_kernel(DevStrand st, unsigned char* __restrict__ lines, uint32_t n_blocks) {
+__global__ void build_lookahead_kernel(DevStrand st, unsigned char* __restrict__ lines, unsigned char* __restrict__ tail, uint32_t n_blocks) {
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5, n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     for (uint64_t hb = warp; hb < 2ull * n_blocks; hb += n_warps) {          // one warp per half block (32 rows)
@@ -337,7 +338,7 @@ __global__ void build_lookahead_kernel(DevStrand st, unsigned char* __restrict__
         const bool valid = row64 < st.n;
         uint32_t cur = valid ? (uint32_t)row64 : 0u;
         uint32_t steps = 0;
-        for (int j = 1; j <= 6; j++) {
+        for (int j = 1; j <= (tail ? 8 : 6); j++) {
             uint32_t sym = 0;
             if (valid) {
                 bool exc = false;
@@ -356,8 +357,8 @@ __global__ void build_lookahead_kernel(DevStrand st, unsigned char* __restrict__
                 sym = block_sym(nb->hi, nb->lo, cur);                   // exception rows read as code 0
             }
             const uint32_t mh = __ballot_sync(0xffffffffu, valid && (sym & 2u)), ml = __ballot_sync(0xffffffffu, valid && (sym & 1u));
-            if (lane == 0) {
-                uint32_t* p = reinterpret_cast<uint32_t*>(line + 32 + 16 * (j - 1));
+            if (lane == 0) {                                             // t7, t8 go to their own array (32 bytes per block)
+                uint32_t* p = reinterpret_cast<uint32_t*>(j <= 6 ? line + 32 + 16 * (j - 1) : tail + (size_t)b * 32 + 16 * (j - 7));
                 p[half] = mh; p[2 + half] = ml;                          // hi plane = words 0,1 ; lo plane = words 2,3
             }
         }
@@ -368,31 +369,34 @@ __global__ void build_lookahead_kernel(DevStrand st, unsigned char* __restrict__
 // pattern summaries of the sweep kernel (DevStrand::sum0/sum1): one thread per jump-table entry gathers the rows of its
 // interval from the look-ahead lines (at most two lines for the <= 32 rows it keeps)
 struct DevPlane {
-    const unsigned char* lines;
+    const unsigned char* lines; const unsigned char* tail;
     __device__ __forceinline__ uint64_t operator()(uint32_t b, uint32_t j, bool hi) const {
+        if (j >= 7u) return __ldg(reinterpret_cast<const uint64_t*>(tail + ((size_t)b << 5)) + 2 * (j - 7) + (hi ? 0 : 1));
         const uint64_t* line = reinterpret_cast<const uint64_t*>(lines + ((size_t)b << 7));
         return __ldg(j == 0 ? line + (hi ? 2 : 3) : line + 4 + 2 * (j - 1) + (hi ? 0 : 1));
     }
 };
-__global__ void build_summary_kernel(const FtabEntry* __restrict__ tab, const unsigned char* __restrict__ lines, unsigned char* __restrict__ sum0,
-                                     unsigned char* __restrict__ sum1, uint64_t n_entries) {
-    DevPlane plane; plane.lines = lines;
+__global__ void build_summary_kernel(const FtabEntry* __restrict__ tab, const unsigned char* __restrict__ lines, const unsigned char* __restrict__ tail,
+                                     unsigned char* __restrict__ sum0, unsigned char* __restrict__ sum1, unsigned char* __restrict__ sum2, uint64_t n_entries) {
+    DevPlane plane; plane.lines = lines; plane.tail = tail;
     for (uint64_t e = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; e < n_entries; e += (uint64_t)gridDim.x * blockDim.x) {
         const FtabEntry t = tab[e];
-        uint32_t s0[8], s1[8];
-        summary_build(plane, t.sp, t.width, s0, s1);
+        uint32_t s0[8], s1[8], s2[4];
+        summary_build(plane, tail != nullptr, t.sp, t.width, s0, s1, s2);
         uint4* d0 = reinterpret_cast<uint4*>(sum0 + e * 32); uint4* d1 = reinterpret_cast<uint4*>(sum1 + e * 32);
         d0[0] = make_uint4(s0[0], s0[1], s0[2], s0[3]); d0[1] = make_uint4(s0[4], s0[5], s0[6], s0[7]);
         d1[0] = make_uint4(s1[0], s1[1], s1[2], s1[3]); d1[1] = make_uint4(s1[4], s1[5], s1[6], s1[7]);
+        if (tail) *reinterpret_cast<uint4*>(sum2 + e * 16) = make_uint4(s2[0], s2[1], s2[2], s2[3]);
     }
 }
-cudaError_t launch_build_summary(const void* tab, const unsigned char* lines, unsigned char* sum0, unsigned char* sum1, uint64_t n_entries, cudaStream_t s) {
-    build_summary_kernel<<<148 * 16, 256, 0, s>>>((const FtabEntry*)tab, lines, sum0, sum1, n_entries);
+cudaError_t launch_build_summary(const void* tab, const unsigned char* lines, const unsigned char* tail, unsigned char* sum0, unsigned char* sum1,
+                                 unsigned char* sum2, uint64_t n_entries, cudaStream_t s) {
+    build_summary_kernel<<<148 * 16, 256, 0, s>>>((const FtabEntry*)tab, lines, tail, sum0, sum1, sum2, n_entries);
     return cudaGetLastError();
 }
 
-cudaError_t launch_build_lookahead(const DevStrand& src, unsigned char* lines, uint32_t n_blocks, cudaStream_t s) {
-    build_lookahead_kernel<<<148 * 16, 256, 0, s>>>(src, lines, n_blocks);
+cudaError_t launch_build_lookahead(const DevStrand& src, unsigned char* lines, unsigned char* tail, uint32_t n_blocks, cudaStream_t s) {
+    build_lookahead_kernel<<<148 * 16, 256, 0, s>>>(src, lines, tail, n_blocks);
     return cudaGetLastError();
 }
 
@@ -763,6 +767,10 @@ struct DevSummaryLoader {
                      : "l"((stage ? sum1 : sum0) + ((size_t)idx << 5)));
     }
 };
+__device__ __forceinline__ void load_tail(const unsigned char* sum2, uint32_t idx, uint32_t t[4]) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(sum2 + ((size_t)idx << 4)));
+    t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w;
+}
 
 struct SweepStats { uint32_t nodes, lookups, sectors; };  // nodes, lookups: per lane; sectors (32-byte summary loads issued): warp-uniform
 
@@ -772,15 +780,15 @@ struct SweepStats { uint32_t nodes, lookups, sectors; };  // nodes, lookups: per
 //   codes  plane codes of its guide
 //   tlm    task | mismatches << 24 | remaining budget << 27
 struct ContBuf {
-    uint32_t* idx; uint32_t* codes; uint32_t* tlm;
+    uint32_t* idx; uint32_t* codes; uint32_t* tlm; uint32_t* codes2;
     uint32_t count;                                                  // warp-uniform
 };
 
-__device__ __forceinline__ void cont_push(ContBuf& cb, uint32_t lane, bool want, uint32_t idx, uint32_t codes, uint32_t tlm) {
+__device__ __forceinline__ void cont_push(ContBuf& cb, uint32_t lane, bool want, uint32_t idx, uint32_t codes, uint32_t codes2, uint32_t tlm) {
     const uint32_t m = __ballot_sync(0xffffffffu, want);
     if (want) {
         const uint32_t slot = cb.count + __popc(m & ((1u << lane) - 1u));
-        cb.idx[slot] = idx; cb.codes[slot] = codes; cb.tlm[slot] = tlm;
+        cb.idx[slot] = idx; cb.codes[slot] = codes; cb.tlm[slot] = tlm; cb.codes2[slot] = codes2;
     }
     cb.count += __popc(m);
     __syncwarp();
@@ -809,15 +817,17 @@ template <int NB>
 __device__ __forceinline__ void cont_process(const SweepArgs& a, ContBuf& cb, uint32_t lane, SweepStats& st) {
     const uint32_t n = cb.count < 32u ? cb.count : 32u;
     const bool mine = lane < n;
-    uint32_t idx = 0, codes = 0, tlm = 0; uint32_t u[NB];
+    uint32_t idx = 0, codes = 0, codes2 = 0x77u, tlm = 0; uint32_t u[NB];
 #pragma unroll
     for (int r = 0; r < NB; r++) u[r] = 0;
-    if (mine) { const uint32_t slot = cb.count - n + lane; idx = cb.idx[slot]; codes = cb.codes[slot]; tlm = cb.tlm[slot]; }
+    if (mine) { const uint32_t slot = cb.count - n + lane; idx = cb.idx[slot]; codes = cb.codes[slot]; tlm = cb.tlm[slot]; codes2 = cb.codes2[slot]; }
     __syncwarp();
     cb.count -= n; st.sectors += n;
     if (mine) {
         DevSummaryLoader ld; ld.sum0 = nullptr; ld.sum1 = (tlm & 1u) ? a.st[1].sum1 : a.st[0].sum1;
         summary_eval<NB>(ld, 1u, idx, codes, (tlm >> 27) & 7u, u);
+        const unsigned char* sum2 = (tlm & 1u) ? a.st[1].sum2 : a.st[0].sum2;
+        if (u[0] && sum2 && sweep_has_tail(codes2)) { uint32_t t[4]; load_tail(sum2, idx, t); summary_tail<NB>(t, 1u, codes2, u); }
     }
     sweep_emit(a, lane, mine && u[0] != 0u, idx, tlm, st);
 }
@@ -825,10 +835,10 @@ __device__ __forceinline__ void cont_process(const SweepArgs& a, ContBuf& cb, ui
 // per-guide constants of the sweep (20 words): written once per call by sweep_guides_kernel, copied to shared memory by
 // each work unit, read back by whichever lanes end up working on that guide's patterns
 //   [0..6] A, [7..13] X, [14] pflags (gsx_core.h summary_masks)   [15] low 2(L-sb) bits of the packed guide
-//   [16] plane codes   per work unit: [17] first pattern number (prefix sum)  [18] xor-table offset  [19] remaining budget
+//   [16] plane codes of levels L .. L+6   [17] of levels L+7, L+8
 constexpr int CB_SLOTS = 64;          // parked nodes per warp: drained below 32 before every step, which adds at most 32
 constexpr int XT_SMEM = 4352;          // words of shared memory for the xor table (17 KB)
-constexpr int GT_WORDS = 20, GT_QLOW = 15, GT_CODES = 16, GT_EXCL = 17, GT_XOFF = 18, GT_B = 19;
+constexpr int GT_WORDS = 20, GT_QLOW = 15, GT_CODES = 16, GT_CODES2 = 17;
 
 __global__ void sweep_guides_kernel(SweepArgs a, uint32_t* __restrict__ gtab) {
     for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < a.n_guides; g += gridDim.x * blockDim.x) {
@@ -837,7 +847,7 @@ __global__ void sweep_guides_kernel(SweepArgs a, uint32_t* __restrict__ gtab) {
         const uint32_t codes = sweep_codes(q, a.plan.L, a.plen, a.pampack);
         summary_masks(codes, t);
         t[GT_QLOW] = (uint32_t)q & ((1u << (2u * (a.plan.L - a.plan.sb))) - 1u);
-        t[GT_CODES] = codes; t[GT_EXCL] = t[GT_XOFF] = t[GT_B] = 0;
+        t[GT_CODES] = codes; t[GT_CODES2] = sweep_codes2(q, a.plan.L, a.plen, a.pampack); t[18] = t[19] = 0;
         uint4* dst = reinterpret_cast<uint4*>(gtab + (size_t)g * GT_WORDS);
         for (int k = 0; k < GT_WORDS / 4; k++) dst[k] = make_uint4(t[4 * k], t[4 * k + 1], t[4 * k + 2], t[4 * k + 3]);
     }
@@ -850,11 +860,18 @@ __device__ __forceinline__ void sweep_load(const unsigned char* sum0, uint32_t i
 }
 // one pattern of one guide against its summary sector; EXACT = no budget left (one row mask)
 template <bool EXACT, int NB>
-__device__ __forceinline__ void sweep_judge(const uint32_t w[8], uint32_t idx, uint32_t qlow, const uint32_t gm[15], uint32_t budget,
-                                            bool& emit, bool& park, SweepStats& st) {
+__device__ __forceinline__ void sweep_judge(const uint32_t w[8], const unsigned char* sum2, uint32_t idx, uint32_t qlow, const uint32_t gm[15],
+                                            uint32_t codes2, uint32_t budget, bool& emit, bool& park, SweepStats& st) {
     uint32_t alive;
-    if (EXACT) alive = summary_eval_exact(w, gm);
-    else { uint32_t u[NB]; summary_eval_masks<NB>(w, gm, budget, u); alive = u[0]; }
+    const bool tail = sum2 && sweep_has_tail(codes2) && !(w[0] & SUM_WIDE32);
+    if (EXACT) {
+        alive = summary_eval_exact(w, gm);
+        if (alive && tail) { uint32_t t[4], v[1] = {alive}; load_tail(sum2, idx, t); summary_tail<1>(t, 0u, codes2, v); alive = v[0]; }
+    } else {
+        uint32_t u[NB]; summary_eval_masks<NB>(w, gm, budget, u);
+        if (u[0] && tail) { uint32_t t[4]; load_tail(sum2, idx, t); summary_tail<NB>(t, 0u, codes2, u); }
+        alive = u[0];
+    }
     if (((idx ^ qlow) & 15u) == 0u) st.lookups++;                             // one table line per 16 beginnings
     if (w[0] & 0xFFFFu) {
         st.nodes++; st.lookups += (w[0] & SUM_TWO_BLOCKS) ? 2u : 1u;
@@ -876,7 +893,8 @@ __device__ __forceinline__ void sweep_run(const SweepArgs& a, const SweepPlan& p
     const uint4* gp = reinterpret_cast<const uint4*>(sg + o * GT_WORDS);       // same address in every lane: broadcast
     const uint4 g0 = gp[0], g1 = gp[1], g2 = gp[2], g3 = gp[3];
     const uint32_t gm[15] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w, g2.x, g2.y, g2.z, g2.w, g3.x, g3.y, g3.z};
-    const uint32_t qlow = g3.w, codes = sg[o * GT_WORDS + GT_CODES];
+    const uint32_t qlow = g3.w, codes = sg[o * GT_WORDS + GT_CODES], codes2 = sg[o * GT_WORDS + GT_CODES2];
+    const unsigned char* sum2 = strand ? a.st[1].sum2 : a.st[0].sum2;
     const uint32_t tl = (guide << 1) | strand;
     st.sectors += n;
     for (uint32_t base = 0; base < n; base += 32u) {
@@ -889,18 +907,18 @@ __device__ __forceinline__ void sweep_run(const SweepArgs& a, const SweepPlan& p
             if (!ZERO) mm = M - B + (xw >> 28);                               // (pass 1 always ends at M)
             uint32_t w[8];
             sweep_load(sum0, idx, w);
-            sweep_judge<ZERO, NB>(w, idx, qlow, gm, M - mm, emit, park, st);
+            sweep_judge<ZERO, NB>(w, sum2, idx, qlow, gm, codes2, M - mm, emit, park, st);
         }
         const uint32_t tlm = tl | (mm << 24) | ((M - mm) << 27);
         sweep_emit(a, lane, emit, idx, tlm, st);
-        cont_push(cb, lane, park, idx, codes, tlm);
+        cont_push(cb, lane, park, idx, codes, codes2, tlm);
     }
 }
 
 template <int WARPS, int MINB, int NB>
 __global__ void __launch_bounds__(WARPS * 32, MINB) sweep_kernel(SweepArgs a) {
     __shared__ SweepPlan s_plan;
-    __shared__ uint32_t s_c32[WARPS][3][CB_SLOTS];
+    __shared__ uint32_t s_c32[WARPS][4][CB_SLOTS];
     __shared__ __align__(16) uint32_t s_g[WARPS][33 * GT_WORDS];
     __shared__ uint32_t s_xtab[XT_SMEM];                  // the xor table, when it fits (it does for up to 3 mismatches)
     for (int i = threadIdx.x; i < (int)(sizeof(SweepPlan) / 4); i += blockDim.x)
@@ -911,7 +929,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) sweep_kernel(SweepArgs a) {
     __syncthreads();
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, FULL = 0xffffffffu;
     ContBuf cb;
-    cb.idx = s_c32[warp][0]; cb.codes = s_c32[warp][1]; cb.tlm = s_c32[warp][2]; cb.count = 0;
+    cb.idx = s_c32[warp][0]; cb.codes = s_c32[warp][1]; cb.tlm = s_c32[warp][2]; cb.codes2 = s_c32[warp][3]; cb.count = 0;
     uint32_t* sg = s_g[warp];
     const uint32_t L = s_plan.L, sb = s_plan.sb, M = a.M;
     const uint32_t n_slices = 1u << (2u * sb), n_gb = (a.n_guides + 31u) >> 5;
@@ -942,21 +960,21 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) sweep_kernel(SweepArgs a) {
         // (1) guides whose only pattern in this slice is the unsubstituted one (budget 0), and the unsubstituted pattern of
         //     the guides with budget 1: one pattern per lane, each lane with its own guide's masks
         {
-            bool emit = false, park = false; uint32_t idx = 0, codes = 0;
+            bool emit = false, park = false; uint32_t idx = 0, codes = 0, codes2 = 0x77u;
             st.sectors += __popc(__ballot_sync(FULL, B == 0 || B == 1));
             if (B == 0 || B == 1) {
                 const uint4* gp = reinterpret_cast<const uint4*>(sg + lane * GT_WORDS);
                 const uint4 g0 = gp[0], g1 = gp[1], g2 = gp[2], g3 = gp[3];
                 const uint32_t gm[15] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w, g2.x, g2.y, g2.z, g2.w, g3.x, g3.y, g3.z};
-                codes = sg[lane * GT_WORDS + GT_CODES];
+                codes = sg[lane * GT_WORDS + GT_CODES]; codes2 = sg[lane * GT_WORDS + GT_CODES2];
                 idx = hi_bits | g3.w;
                 uint32_t w[8];
                 sweep_load(strand ? a.st[1].sum0 : a.st[0].sum0, idx, w);
-                sweep_judge<false, NB>(w, idx, g3.w, gm, (uint32_t)B, emit, park, st);
+                sweep_judge<false, NB>(w, strand ? a.st[1].sum2 : a.st[0].sum2, idx, g3.w, gm, codes2, (uint32_t)B, emit, park, st);
             }
             const uint32_t tlm = ((g << 1) | strand) | ((M - (uint32_t)(B > 0 ? B : 0)) << 24) | ((uint32_t)(B > 0 ? B : 0) << 27);
             sweep_emit(a, lane, emit, idx, tlm, st);
-            cont_push(cb, lane, park, idx, codes, tlm);
+            cont_push(cb, lane, park, idx, codes, codes2, tlm);
         }
         // (2) guides with budget left after the slice characters, one at a time: first the patterns that use the budget up
         //     (most of them, cheapest arithmetic), then -- from budget 2 on -- the ones that keep some

@@ -88,9 +88,11 @@ cudaError_t upload_cfd_tables();
 // packed 32-byte blocks (src) -> 128-byte lines with look-ahead planes t1..t6 (dst must hold n_blocks * 128 bytes)
 // k-mer jump table of depth L for one strand; tab and tmp must each hold 4^L entries of 8 bytes; result ends up in tab
 cudaError_t launch_build_ftab(const DevStrand& st, uint32_t L, void* tab, void* tmp, cudaStream_t s);
-cudaError_t launch_build_lookahead(const DevStrand& src, unsigned char* lines, uint32_t n_blocks, cudaStream_t s);
+// (tail: optional scratch of n_blocks * 32 bytes receiving the planes t7, t8)
+cudaError_t launch_build_lookahead(const DevStrand& src, unsigned char* lines, unsigned char* tail, uint32_t n_blocks, cudaStream_t s);
 // jump table + look-ahead lines -> pattern summaries of the sweep kernel (sum0, sum1: 32 bytes per table entry each)
-cudaError_t launch_build_summary(const void* tab, const unsigned char* lines, unsigned char* sum0, unsigned char* sum1, uint64_t n_entries, cudaStream_t s);
+cudaError_t launch_build_summary(const void* tab, const unsigned char* lines, const unsigned char* tail, unsigned char* sum0, unsigned char* sum1,
+                                 unsigned char* sum2, uint64_t n_entries, cudaStream_t s);      // sum2: 16 bytes per entry, with tail only
 int search_grid_warps(bool wide, int variant, int sm_count);
 cudaError_t launch_search(const SearchArgs& a, bool wide, int variant, int sm_count, cudaStream_t s, int* warps_total);
 int search_fast_grid_warps(int variant, int sm_count);

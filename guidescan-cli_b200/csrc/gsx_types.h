@@ -60,6 +60,8 @@ struct DevStrand {
     const unsigned char* lines;    // optional second copy, one 128-byte line per 64 rows: OccBlock + six look-ahead symbol
                                    // planes (see build_lookahead_kernel); nullptr if absent
     const unsigned char* sum0;     // optional pattern summaries of the sweep kernel, 32 bytes per jump-table entry (same index):
+    const unsigned char* sum2;     //   (sum2[e], 16 bytes: the two further symbols t7, t8 of rows sp .. sp+31 as 32-bit plane pairs -- for a
+                                   //   20-nt guide at L = 14 these are the two fixed PAM characters; read only by the few survivors)
     const unsigned char* sum1;     //   sum0[e] = header + the seven look-ahead symbols t0..t6 of rows sp .. sp+15 of the entry's
                                    //   interval as 16-bit plane pairs, sum1[e] = the same for rows sp+16 .. sp+31 (gsx_core.h
                                    //   summary_eval).  t_j = the character a backward search from that row consumes j steps ahead

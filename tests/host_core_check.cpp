@@ -42,12 +42,13 @@ static DevStrand view_of(const HostStrand& h) {
 static std::vector<uint64_t> g_look[2];     // 12 words per block: hi1, lo1, ..., hi6, lo6
 static bool g_prune = false;
 
-static void build_look(const DevStrand& st, std::vector<uint64_t>& look) {
+static std::vector<uint64_t> g_tail[2];     // 4 words per block: hi7, lo7, hi8, lo8 (the scratch planes the summaries' sum2 is built from)
+static void build_look(const DevStrand& st, std::vector<uint64_t>& look, std::vector<uint64_t>& tail) {
     const uint32_t nb = st.n / 64 + 1;
-    look.assign((size_t)nb * 12, 0);
+    look.assign((size_t)nb * 12, 0); tail.assign((size_t)nb * 4, 0);
     for (uint32_t row = 0; row < st.n; row++) {
         uint32_t cur = row;
-        for (int j = 1; j <= 6; j++) {
+        for (int j = 1; j <= 8; j++) {
             // cur = LF(cur)
             bool exc = false;
             if (st.n_exc && cur >= st.exc_lo && cur <= st.exc_hi) {
@@ -62,8 +63,9 @@ static void build_look(const DevStrand& st, std::vector<uint64_t>& look) {
             }
             const OccBlock& c = st.blocks[cur >> 6];
             uint32_t sy = block_sym(c.hi, c.lo, cur);       // exception rows read as code 0, as on the device
-            look[(size_t)(row >> 6) * 12 + 2 * (j - 1)] |= (uint64_t)(sy >> 1) << (row & 63);
-            look[(size_t)(row >> 6) * 12 + 2 * (j - 1) + 1] |= (uint64_t)(sy & 1) << (row & 63);
+            uint64_t* dst = j <= 6 ? &look[(size_t)(row >> 6) * 12 + 2 * (j - 1)] : &tail[(size_t)(row >> 6) * 4 + 2 * (j - 7)];
+            dst[0] |= (uint64_t)(sy >> 1) << (row & 63);
+            dst[1] |= (uint64_t)(sy & 1) << (row & 63);
         }
     }
 }
@@ -203,30 +205,55 @@ struct HostSectorLoader {            // whole 64-row lines (node_viable / node_v
     }
 };
 // pattern summaries (what build_summary_kernel writes), built on the host through the same summary_build
-static std::vector<uint32_t> g_sum0[2], g_sum1[2];
+static std::vector<uint32_t> g_sum0[2], g_sum1[2], g_sum2[2];
 struct HostPlane {
-    const DevStrand* st; const std::vector<uint64_t>* look;
+    const DevStrand* st; const std::vector<uint64_t>* look; const std::vector<uint64_t>* tail;
     uint64_t operator()(uint32_t b, uint32_t j, bool hi) const {
         if (j == 0) return hi ? st->blocks[b].hi : st->blocks[b].lo;
+        if (j >= 7) return (*tail)[(size_t)b * 4 + 2 * (j - 7) + (hi ? 0 : 1)];
         return (*look)[(size_t)b * 12 + 2 * (j - 1) + (hi ? 0 : 1)];
     }
 };
-static void build_summaries_host(const DevStrand& st, const std::vector<uint64_t>& look, const std::vector<FtabEntry>& tab, std::vector<uint32_t>& s0, std::vector<uint32_t>& s1) {
-    s0.assign(tab.size() * 8, 0); s1.assign(tab.size() * 8, 0);
-    HostPlane plane{&st, &look};
-    for (size_t e = 0; e < tab.size(); e++) summary_build(plane, tab[e].sp, tab[e].width, &s0[e * 8], &s1[e * 8]);
+static void build_summaries_host(const DevStrand& st, const std::vector<uint64_t>& look, const std::vector<uint64_t>& tail, const std::vector<FtabEntry>& tab,
+                                 std::vector<uint32_t>& s0, std::vector<uint32_t>& s1, std::vector<uint32_t>& s2) {
+    s0.assign(tab.size() * 8, 0); s1.assign(tab.size() * 8, 0); s2.assign(tab.size() * 4, 0);
+    HostPlane plane{&st, &look, &tail};
+    for (size_t e = 0; e < tab.size(); e++) summary_build(plane, true, tab[e].sp, tab[e].width, &s0[e * 8], &s1[e * 8], &s2[e * 4]);
 }
 struct HostSummaryLoader {
-    const std::vector<uint32_t>* s0; const std::vector<uint32_t>* s1;
-    void operator()(uint32_t stage, uint32_t idx, uint32_t w[8]) const { for (int i = 0; i < 8; i++) w[i] = (stage ? *s1 : *s0)[(size_t)idx * 8 + i]; }
+    const std::vector<uint32_t>* s0; const std::vector<uint32_t>* s1; const std::vector<uint32_t>* s2;
+    void operator()(uint32_t stage, uint32_t idx, uint32_t w[8]) const {
+        if (stage == 2) { for (int i = 0; i < 4; i++) w[i] = (*s2)[(size_t)idx * 4 + i]; return; }
+        for (int i = 0; i < 8; i++) w[i] = (stage ? *s1 : *s0)[(size_t)idx * 8 + i];
+    }
 };
+// independent statement of what the full filter decides: follow ONE row for up to n_levels characters (LF walk over the
+// packed blocks; a non-ACGT row reads as code 0 and steps through its precomputed LF target, as on the device)
+static bool row_reaches(const DevStrand& st, uint32_t row, uint32_t lvl, uint32_t n_levels, uint64_t q, uint32_t plen, uint32_t pampack, uint32_t budget) {
+    const uint32_t qlen = (uint32_t)(q >> 58);
+    uint32_t cur = row, mm = 0;
+    for (uint32_t j = 0; j < n_levels && lvl + j < qlen + plen; j++) {
+        const uint32_t Lv = lvl + j;
+        const OccBlock& b = st.blocks[cur >> 6];
+        const uint32_t sy = block_sym(b.hi, b.lo, cur);
+        if (Lv < qlen) { if (sy != ((uint32_t)(q >> (2 * Lv)) & 3u) && ++mm > budget) return false; }
+        else { const uint32_t pc = (pampack >> (3 * (Lv - qlen))) & 7u; if (pc > 4u || (pc < 4u && pc != sy)) return false; }
+        bool exc = false;
+        if (st.n_exc && cur >= st.exc_lo && cur <= st.exc_hi) {
+            uint32_t k = lower_bound_u32(st.exc_rows, st.n_exc, cur);
+            if (k < st.n_exc && st.exc_rows[k] == cur) { cur = st.exc_lf[k]; exc = true; }
+        }
+        if (!exc) { uint32_t o[4]; block_occ(st, b.cnt, b.hi, b.lo, cur, o); cur = st.C[sy] + o[sy]; }
+    }
+    return true;
+}
 static void sweep_host(const DevStrand st[2], const Prepared& prep, uint32_t M) {
     const uint32_t L = g_ftab_L, sb = g_sweep_sb; const size_t n = prep.recs.size();
     SweepPlan plan; std::vector<uint32_t> masks; sweep_make_plan(L, sb, M, plan, masks);
     std::vector<std::vector<Node>>& g_seeds = g_seeds_by_M[M]; g_seeds.assign(2 * n, {});
     static std::vector<uint64_t> combos; combos = ftab_combos(L - 2, M);
     for (uint32_t strand = 0; strand < 2; strand++) {
-        HostSectorLoader ld{&st[strand], &g_look[strand]}; HostSummaryLoader lds{&g_sum0[strand], &g_sum1[strand]};
+        HostSectorLoader ld{&st[strand], &g_look[strand]}; HostSummaryLoader lds{&g_sum0[strand], &g_sum1[strand], &g_sum2[strand]};
         std::vector<std::vector<std::pair<uint32_t, uint32_t>>> seen(n);
         for (uint32_t beta = 0; beta < (1u << (2 * sb)); beta++)
             for (size_t g = 0; g < n; g++) {
@@ -250,8 +277,16 @@ static void sweep_host(const DevStrand st[2], const Prepared& prep, uint32_t M) 
                                              : node_viable<kMaxDist>(ld, e.sp, e.sp + e.width - 1, L, qlen, qlen + prep.plen, q, prep.pampack, M - mm, sectors);
                         // what the kernel runs (summary_step0/1 over the pattern summaries) must agree with the row-by-row forms
                         const uint32_t codes = sweep_codes(q, L, prep.plen, prep.pampack);
-                        const bool ok2 = summary_viable<kMaxDist>(lds, idx, codes, M - mm);
-                        if (e.width <= 32 ? ok2 != ok : !ok2) { fprintf(stderr, "summary filter disagrees with node_viable (idx %u zero %d ok %d ok2 %d sp %u w %u budget %u)\n", idx, zero, (int)ok, (int)ok2, e.sp, e.width, M - mm); exit(3); }
+                        const uint32_t codes2 = sweep_codes2(q, L, prep.plen, prep.pampack);
+                        const bool ok7 = summary_viable<kMaxDist>(lds, idx, codes, 0x77u, M - mm);          // seven levels only
+                        const bool ok2 = summary_viable<kMaxDist>(lds, idx, codes, codes2, M - mm);         // + levels L+7, L+8 (sum2)
+                        if (e.width <= 32) {                                                                // against single-row LF walks
+                            bool any9 = false, any7 = false;
+                            for (uint32_t r = 0; r < e.width; r++) { any9 = any9 || row_reaches(st[strand], e.sp + r, L, 9, q, prep.plen, prep.pampack, M - mm);
+                                                                     any7 = any7 || row_reaches(st[strand], e.sp + r, L, 7, q, prep.plen, prep.pampack, M - mm); }
+                            if (any9 != ok2 || any7 != ok7) { fprintf(stderr, "summary filter disagrees with the row walks (idx %u: %d/%d vs %d/%d)\n", idx, (int)ok7, (int)ok2, (int)any7, (int)any9); exit(3); }
+                        } else if (!ok2) { fprintf(stderr, "summary filter dropped a node of more than 32 rows (idx %u)\n", idx); exit(3); }
+                        if (e.width <= 32 ? ok7 != ok : !ok7) { fprintf(stderr, "summary filter disagrees with node_viable (idx %u zero %d ok %d ok7 %d sp %u w %u budget %u)\n", idx, zero, (int)ok, (int)ok7, e.sp, e.width, M - mm); exit(3); }
                         {   // the hoisted-mask forms the kernel's main loop uses
                             uint32_t gm[15], w[8], u1[kMaxDist], u2[kMaxDist];
                             summary_masks(codes, gm);
@@ -263,7 +298,7 @@ static void sweep_host(const DevStrand st[2], const Prepared& prep, uint32_t M) 
                                 if (zero && summary_eval_exact(w, gm) != (u1[0] & 0xFFFFu)) { fprintf(stderr, "summary_eval_exact disagrees (idx %u stage %u)\n", idx, stage); exit(3); }
                             }
                         }
-                        if (zero && summary_viable<1>(lds, idx, codes, 0) != ok2) { fprintf(stderr, "summary filter <1> disagrees (idx %u)\n", idx); exit(3); }
+                        if (zero && summary_viable<1>(lds, idx, codes, codes2, 0) != ok2) { fprintf(stderr, "summary filter <1> disagrees (idx %u)\n", idx); exit(3); }
                         if (!ok2) continue;
                         Node nd{}; nd.sp = e.sp; nd.ep = e.sp + e.width - 1; nd.key_lo = ftab_key(idx, q, L); nd.task = (uint32_t)(2 * g + strand);
                         nd.meta = meta_make(L, mm, 0, 0, 0, 0, 0);
@@ -394,9 +429,9 @@ int main(int argc, char** argv) {
     if (g_sweep_sb && (!g_prune || !g_ftab_L || !prep.fast_ok || g_sweep_sb + 3 > g_ftab_L)) { fprintf(stderr, "--sweep SB needs --lookahead, --ftab L >= SB + 3 and a fast-path batch\n"); return 2; }
     if (g_prune) {
         if (!prep.fast_ok) { fprintf(stderr, "--lookahead needs a fast-path batch (one PAM, ACGT guides, no bulges)\n"); return 2; }
-        build_look(st[0], g_look[0]); build_look(st[1], g_look[1]);
+        build_look(st[0], g_look[0], g_tail[0]); build_look(st[1], g_look[1], g_tail[1]);
     }
-    if (g_sweep_sb) for (int s = 0; s < 2; s++) build_summaries_host(st[s], g_look[s], g_ftab[s], g_sum0[s], g_sum1[s]);
+    if (g_sweep_sb) for (int s = 0; s < 2; s++) build_summaries_host(st[s], g_look[s], g_tail[s], g_ftab[s], g_sum0[s], g_sum1[s], g_sum2[s]);
 
     // ---- search + order + expand (what search_kernel / order_matches_kernel / expand_hits_kernel do) ----------------
     std::vector<uint8_t> dropped(n, 0);
