@@ -206,6 +206,8 @@ def run_gsx(args):
             name, _, pin = item.partition("@")          # "f1@64": specialised kernel variant 1 with a 64 MB L2 residency budget
             if name[0] == "s":                          # "s5v2": slice-major front end, 5 slice characters, sweep kernel variant 2; "s0": off
                 sb, _, var = name[1:].partition("v")
+                var, _, lmode = var.partition("l")          # "s5v2l1": ... summary loads with cache policy 1 (GSX_SWEEP_LOAD)
+                os.environ["GSX_SWEEP_LOAD"] = lmode or "2"
                 var, _, parts = var.partition("p")          # "s5v2p4": ... each (slice, 32 guides) unit cut into 4 work units
                 env = {"GSX_FORCE_GENERAL": "0", "GSX_SWEEP": "0" if sb == "0" else "1", "GSX_SWEEP_SB": sb, "GSX_SWEEP_VARIANT": var or "0",
                        "GSX_SWEEP_PARTS": parts or "0"}
@@ -223,7 +225,7 @@ def run_gsx(args):
             log(json.dumps({"variant": item, "ms_search": best["ms_search"], "guides_per_s_search": per / best["ms_search"] * 1e3,
                             "glookups_per_s": best["lookups"] / best["ms_search"] / 1e6, "spills": best["spills"], "nodes": best["nodes"],
                             "ms_sweep": best["ms_sweep"], "seeds": best["seeds"], "lookups": best["lookups"]}))
-        for k in ("GSX_FORCE_GENERAL", "GSX_SEARCH_VARIANT", "GSX_FAST_VARIANT", "GSX_L2_PIN_MB", "GSX_SWEEP", "GSX_SWEEP_SB", "GSX_SWEEP_VARIANT", "GSX_SWEEP_PARTS"):
+        for k in ("GSX_FORCE_GENERAL", "GSX_SEARCH_VARIANT", "GSX_FAST_VARIANT", "GSX_L2_PIN_MB", "GSX_SWEEP", "GSX_SWEEP_SB", "GSX_SWEEP_VARIANT", "GSX_SWEEP_PARTS", "GSX_SWEEP_LOAD"):
             os.environ.pop(k, None)
         apply_variant(args)
     for s in range(args.warmup):

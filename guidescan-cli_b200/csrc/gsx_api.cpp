@@ -524,7 +524,7 @@ static void run_device_job(DeviceJob* job) {
                 CK(cudaMemcpyAsync(d_xtab, xtab.data(), xtab.size() * 4, cudaMemcpyHostToDevice, s)); CK(cudaStreamSynchronize(s));
                 if (!d_queue) d_queue = B.alloc<SeedNode>(queue_cap);
                 w.st[0] = m.st[0]; w.st[1] = m.st[1]; w.gq = m.gq; w.skip = m.skip; w.n_guides = n; w.xtab = d_xtab; w.n_xtab = (uint32_t)xtab.size();
-                w.M = m.p.M; w.plen = m.plen; w.pampack = m.pampack;
+                w.M = m.p.M; w.plen = m.plen; w.pampack = m.pampack; w.load_mode = (uint32_t)env_int("GSX_SWEEP_LOAD", 2);
                 {   // enough work units per slice that the whole grid stays within about one slice (L2 residency)
                     const int sv = env_int("GSX_SWEEP_VARIANT", 2);
                     const uint32_t warps = (uint32_t)di.sm_count * 8u * (sv == 0 ? 3u : sv == 1 ? 2u : sv == 2 ? 4u : sv == 3 ? 6u : sv == 5 ? 5u : 8u);

@@ -853,10 +853,19 @@ __global__ void sweep_guides_kernel(SweepArgs a, uint32_t* __restrict__ gtab) {
     }
 }
 
-__device__ __forceinline__ void sweep_load(const unsigned char* sum0, uint32_t idx, uint32_t w[8]) {
-    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"                                           // LDG.E.256
-                 : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
-                 : "l"(sum0 + ((size_t)idx << 5)));
+__device__ __forceinline__ void sweep_load(const unsigned char* sum0, uint32_t idx, uint32_t w[8], uint32_t mode = 0) {
+    if (mode == 1)
+        asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+                     : "l"(sum0 + ((size_t)idx << 5)));
+    else if (mode == 2)
+        asm volatile("ld.global.cg.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+                     : "l"(sum0 + ((size_t)idx << 5)));
+    else
+        asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"                                       // LDG.E.256
+                     : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+                     : "l"(sum0 + ((size_t)idx << 5)));
 }
 // one pattern of one guide against its summary sector; EXACT = no budget left (one row mask)
 template <bool EXACT, int NB>
@@ -906,7 +915,7 @@ __device__ __forceinline__ void sweep_run(const SweepArgs& a, const SweepPlan& p
             idx = hi_bits | (qlow ^ (xw & 0x0FFFFFFFu));
             if (!ZERO) mm = M - B + (xw >> 28);                               // (pass 1 always ends at M)
             uint32_t w[8];
-            sweep_load(sum0, idx, w);
+            sweep_load(sum0, idx, w, a.load_mode);
             sweep_judge<ZERO, NB>(w, sum2, idx, qlow, gm, codes2, M - mm, emit, park, st);
         }
         const uint32_t tlm = tl | (mm << 24) | ((M - mm) << 27);

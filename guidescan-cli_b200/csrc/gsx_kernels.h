@@ -54,7 +54,8 @@ struct SweepArgs {
     uint32_t n_xtab;
     uint32_t* gtab;                    // n_guides * 20 words: per-guide constants, written by launch_sweep_guides
     uint32_t M, plen, pampack;
-    uint32_t parts;                    // each (slice, 32 guides) unit is cut into this many work units (keeps all warps on the same slices)
+    uint32_t parts;                    // (unused: cutting the work units was measured and did not pay)
+    uint32_t load_mode;                // cache policy of the summary loads: 0 ld.global.nc, 1 + L1::no_allocate, 2 ld.global.cg
     SeedNode* queue; uint32_t queue_cap;
     uint32_t* queue_count; uint32_t* item_counter; uint32_t* error_flag;
     unsigned long long* stats;         // [0] nodes [1] lookups (reference unit) [5] summary sectors loaded
