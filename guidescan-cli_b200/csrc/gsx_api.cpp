@@ -427,14 +427,23 @@ int gsx_prepare_guides(const gsx_guide* guides, size_t n, const gsx_params* p, g
         if (c.bad_len) return fail(GSX_ERR_ARG, "guide sequence length must be 1..32");
         max_total = std::max(max_total, c.max_total); all_fast = all_fast && c.fast; out.min_qlen = std::min(out.min_qlen, c.min_qlen);
     }
-    out.wide = bulges || max_total > 27;
+    // PAMs of different lengths inside one set give match strings of different lengths: only the left-aligned (wide) key
+    // orders those as std::string does
+    bool same_plen = true;
+    for (size_t k = 0; k < set_of.size(); k++) for (int j = 1; j < out.pamsets[k].n_pams; j++) same_plen = same_plen && out.pamsets[k].plen[j] == out.pamsets[k].plen[0];
+    out.wide = bulges || max_total > 27 || !same_plen;
     if (max_total + p->dna_bulges > 32) return fail(GSX_ERR_ARG, "guide + PAM + DNA bulges longer than 32 characters");
-    // fast path: no bulges, one PAM pattern for every guide, ACGT-only guides of at most 29 nt
-    out.fast_ok = !out.wide && set_of.size() == 1 && out.pamsets[0].n_pams == 1 && n > 0 && all_fast;
+    // fast path: no bulges, the same PAM list for every guide (alternative PAMs = one search pass each), ACGT-only guides of
+    // at most 29 nt
+    out.fast_ok = !out.wide && set_of.size() == 1 && n > 0 && all_fast;
     if (out.fast_ok) {
         const PamSet& ps = out.pamsets[0];
-        out.plen = ps.plen[0]; out.pampack = 0;
-        for (uint32_t j = 0; j < ps.plen[0]; j++) out.pampack |= (uint32_t)ps.sym[0][j] << (3 * j);
+        out.n_fast_pams = ps.n_pams;
+        for (uint32_t k = 0; k < ps.n_pams; k++) {
+            out.plens[k] = ps.plen[k]; out.pampacks[k] = 0;
+            for (uint32_t j = 0; j < ps.plen[k]; j++) out.pampacks[k] |= (uint32_t)ps.sym[k][j] << (3 * j);
+        }
+        out.plen = out.plens[0]; out.pampack = out.pampacks[0];
     }
     return GSX_OK;
 }
@@ -543,6 +552,15 @@ static void run_device_job(DeviceJob* job) {
             if (ev_mid) CK(cudaEventRecord(ev_mid, s));
             CK(launch_search_fast(m, variant_f, di.sm_count, s)); n_launches++;
         };
+        // alternative PAMs (process.hpp:51-56): the searches of the PAMs are independent and their matches are collected in
+        // the same per-guide sets, so each PAM gets its own pass over the same arenas; only the work counters start over
+        auto run_fast_all_pams = [&](SearchArgs& m, cudaEvent_t ev_mid) {
+            for (uint32_t k = 0; k < prep.n_fast_pams; k++) {
+                m.pampack = prep.pampacks[k]; m.plen = prep.plens[k];
+                if (k) { CK(cudaMemsetAsync(d_ctrs, 0, 4, s)); CK(cudaMemsetAsync(d_ctrs + 3, 0, 8, s)); }      // task / seed-queue / work-unit counters
+                launch_fast(m, k == 0 ? ev_mid : nullptr);
+            }
+        };
         auto grow_queue = [&]() { B.free_one(d_queue); d_queue = nullptr; queue_cap *= 4; if (queue_cap > (1ull << 31)) throw std::runtime_error("seed queue keeps overflowing"); };
 
         CK(cudaEventRecord(ev[0], s));
@@ -564,7 +582,7 @@ static void run_device_job(DeviceJob* job) {
                     c.combos = d_cb; c.n_combos = (uint32_t)cb.size();
                 }
                 c.guide_count = d_gcount; c.spill = d_spill; c.skip = nullptr; c.matches = nullptr;
-                if (use_fast) launch_fast(c, nullptr); else { CK(launch_search(c, false, variant_n, di.sm_count, s, nullptr)); n_launches++; }
+                if (use_fast) run_fast_all_pams(c, nullptr); else { CK(launch_search(c, false, variant_n, di.sm_count, s, nullptr)); n_launches++; }
                 uint32_t h[3]; CK(cudaMemcpyAsync(h, d_ctrs, sizeof h, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s));
                 B.free_one(d_spill);
                 if (h[2] & GSX_KERR_WATCHDOG) throw std::runtime_error("search kernel watchdog tripped");
@@ -603,7 +621,7 @@ static void run_device_job(DeviceJob* job) {
             m.p.match_cap = (uint32_t)match_cap; m.p.spill_cap = spill_cap; m.spill = d_spill; m.matches = d_matches;
             m.skip = p.threshold > 0 ? d_dropped : nullptr;
             CK(cudaEventRecord(ev[6], s));
-            if (use_fast) launch_fast(m, ev[7]); else { CK(cudaEventRecord(ev[7], s)); CK(launch_search(m, wide, variant, di.sm_count, s, nullptr)); n_launches++; }
+            if (use_fast) run_fast_all_pams(m, ev[7]); else { CK(cudaEventRecord(ev[7], s)); CK(launch_search(m, wide, variant, di.sm_count, s, nullptr)); n_launches++; }
             uint32_t h[4]; CK(cudaMemcpyAsync(h, d_ctrs, sizeof h, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s));
             B.free_one(d_spill);
             if (h[2] & GSX_KERR_WATCHDOG) throw std::runtime_error("search kernel watchdog tripped");

@@ -105,7 +105,8 @@ struct Prepared {
     // fast-path description (search_fast_kernel): valid when fast_ok
     bool fast_ok = false;
     std::vector<uint64_t> gq;      // per guide: 2-bit symbols in consumption order | qlen << 58
-    uint32_t pampack = 0, plen = 0, min_qlen = 0;
+    uint32_t pampack = 0, plen = 0, min_qlen = 0;      // (first PAM of the list)
+    uint32_t n_fast_pams = 0, pampacks[kMaxPams] = {0}, plens[kMaxPams] = {0};      // every PAM of the (single) PAM set: one search pass each
 };
 
 // every way to substitute at most M of the first n_pos characters (k-mer jump table enumeration, gsx_core.h)

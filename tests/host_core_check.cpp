@@ -426,6 +426,7 @@ int main(int argc, char** argv) {
         g_pow5[0] = 1; for (int i = 1; i < 32; i++) g_pow5[i] = g_pow5[i - 1] * 5ull;
         build_ftab_host(st[0], g_ftab_L, g_ftab[0]); build_ftab_host(st[1], g_ftab_L, g_ftab[1]);
     }
+    if ((g_prune || g_ftab_L || g_sweep_sb) && prep.n_fast_pams > 1) { fprintf(stderr, "--lookahead / --ftab / --sweep mirror the single-PAM passes: no -a here\n"); return 2; }
     if (g_sweep_sb && (!g_prune || !g_ftab_L || !prep.fast_ok || g_sweep_sb + 3 > g_ftab_L)) { fprintf(stderr, "--sweep SB needs --lookahead, --ftab L >= SB + 3 and a fast-path batch\n"); return 2; }
     if (g_prune) {
         if (!prep.fast_ok) { fprintf(stderr, "--lookahead needs a fast-path batch (one PAM, ACGT guides, no bulges)\n"); return 2; }
