@@ -187,7 +187,7 @@ def run_gsx(args):
     os.makedirs(workdir, exist_ok=True)
     g, chroms, pos, kmers = make_workload(args, world)
     ix, how = build_index(gsx, g, chroms, local, args, workdir)
-    params = gsx.make_params(mismatches=args.mismatches)
+    params = gsx.make_params(mismatches=args.mismatches, alt_pams=tuple(args.alt_pam), rna_bulges=args.rna_bulges, dna_bulges=args.dna_bulges)
     per = args.guides_per_step
     # host buffers of every step's guides for this rank (pinned memory is allocated inside the library for results)
     steps = []
@@ -274,7 +274,7 @@ def run_gsx(args):
             "config": {"workload": "%.0f Mb uniform-random synthetic genome (seed %d, %d chr, planted 1-4 mismatch copies), "
                                    "%d NGG 20-mer guides per GPU per step, mismatches=%d, both strand indexes, locate + CFD + specificity"
                                    % (args.genome_mb, args.seed, args.n_chr, per, args.mismatches),
-                       "genome_mb": args.genome_mb, "guides_per_gpu_per_step": per, "mismatches": args.mismatches,
+                       "genome_mb": args.genome_mb, "guides_per_gpu_per_step": per, "mismatches": args.mismatches, "alt_pams": list(args.alt_pam), "rna_bulges": args.rna_bulges, "dna_bulges": args.dna_bulges,
                        "index": how, "sa_sample_rows": 1 << args.sa_shift, "parallelism": "guides sharded x%d, index replicated" % world,
                        "l2": "index (%.2f GB) is far larger than L2; every step uses new guides" % (ix.device_bytes / 1e9)},
             "e2e": {"value": total_guides / e2e_s, "unit": "guides/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": int(d2h_bytes),
@@ -338,7 +338,8 @@ def cpu_baseline(args, g, chroms, kmers, workdir, steps=1, sample=None, ix=None)
         best = None
         for _ in range(steps):
             t0 = time.time()
-            O.ref_enumerate(prefix, gcsv, out, mismatches=args.mismatches, threads=cores)
+            O.ref_enumerate(prefix, gcsv, out, mismatches=args.mismatches, alt_pams=tuple(args.alt_pam), rna_bulges=args.rna_bulges,
+                            dna_bulges=args.dna_bulges, threads=cores)
             dt = time.time() - t0
             best = dt if best is None else min(best, dt)
         return {"value": n / best, "unit": "guides/s", "cores": cores, "kind": "reference", "out": out, "csv": gcsv,
@@ -361,7 +362,7 @@ def cpu_baseline(args, g, chroms, kmers, workdir, steps=1, sample=None, ix=None)
     best = None
     for _ in range(steps):
         t0 = time.time()
-        oix.enumerate_file(O.make_opts(mismatches=args.mismatches), gcsv, out, nthreads=cores)
+        oix.enumerate_file(O.make_opts(mismatches=args.mismatches, alt_pams=tuple(args.alt_pam), rna_bulges=args.rna_bulges, dna_bulges=args.dna_bulges), gcsv, out, nthreads=cores)
         dt = time.time() - t0
         best = dt if best is None else min(best, dt)
     oix.close()
@@ -375,7 +376,7 @@ def cpu_baseline(args, g, chroms, kmers, workdir, steps=1, sample=None, ix=None)
 def parity_on_sample(ix, gsx, cb, args):
     """the CPU arm's CSV for the sample must equal the GPU arm's, byte for byte"""
     out = cb["out"] + ".gpu"
-    ix.enumerate_file(cb["csv"], out, gsx.make_params(mismatches=args.mismatches))
+    ix.enumerate_file(cb["csv"], out, gsx.make_params(mismatches=args.mismatches, alt_pams=tuple(args.alt_pam), rna_bulges=args.rna_bulges, dna_bulges=args.dna_bulges))
     a, b = open(out, "rb").read(), open(cb["out"], "rb").read()
     if cb["kind"] == "reference":      # the reference interleaves per-guide blocks by thread timing: compare sorted lines
         a, b = b"\n".join(sorted(a.split(b"\n"))), b"\n".join(sorted(b.split(b"\n")))
@@ -418,6 +419,9 @@ def main():
     ap.add_argument("--ref-max-mb", type=float, default=200.0)
     ap.add_argument("--plant-guides", type=int, default=2000)
     ap.add_argument("--mismatches", type=int, default=3)
+    ap.add_argument("--alt-pam", action="append", default=[], help="alternative PAM (repeatable), e.g. --alt-pam NAG (BASELINE configs[4])")
+    ap.add_argument("--rna-bulges", type=int, default=0)
+    ap.add_argument("--dna-bulges", type=int, default=0)
     ap.add_argument("--seed", type=int, default=3)
     ap.add_argument("--sa-shift", type=int, default=2, help="SA sample density 2^k rows (the reference samples every 64th row; the index keeps every 4th)")
     ap.add_argument("--cpu-sample", type=int, default=8000)
