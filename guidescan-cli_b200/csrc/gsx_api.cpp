@@ -648,7 +648,8 @@ static void run_device_job(DeviceJob* job) {
         uint32_t* d_cbd = B.alloc<uint32_t>((size_t)n * n_dist, true, s);
         CK(launch_scan(d_nmatch, d_moff, n, s)); n_launches += 2 + (n_matches ? 1 : 0);
         CK(launch_scatter(d_matches, n_matches, d_moff, d_cursor, d_by_guide, s));
-        CK(launch_order(d_matches, d_moff, d_by_guide, n, n_dist, d_sorted, d_sorted_off, d_nhits, d_cbd, s));
+        CK(launch_order(d_matches, d_moff, d_by_guide, n, n_dist, d_sorted, d_sorted_off, d_nhits, d_cbd,
+                        env_int("GSX_ORDER_CTA", (uint64_t)n_matches > (uint64_t)n * 256 ? 1 : 0) != 0, s));
         {   // total hits can exceed 2^32 only for absurd inputs; the scan is 32-bit, so check with a 64-bit host sum
             CK(cudaMemcpyAsync(H.n_hits_of, d_nhits, (size_t)n * 4, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s));
             uint64_t tot = 0; for (uint32_t i = 0; i < n; i++) tot += H.n_hits_of[i];

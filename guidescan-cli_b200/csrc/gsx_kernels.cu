@@ -1104,6 +1104,46 @@ __global__ void order_matches_kernel(const MatchRec* matches, const uint32_t* gu
     }
 }
 
+// the same for guides with thousands of matches (bulges): one CTA per guide, the O(s^2) rank sort spread over all its
+// threads, then warp 0 lays out the hit offsets
+__global__ void order_matches_cta_kernel(const MatchRec* matches, const uint32_t* guide_moff, const uint32_t* by_guide,
+                                         uint32_t n_guides, uint32_t n_dist, uint32_t* sorted, uint32_t* sorted_off,
+                                         uint32_t* guide_nhits, uint32_t* count_by_distance) {
+    const uint32_t lane = threadIdx.x & 31;
+    for (uint32_t g = blockIdx.x; g < n_guides; g += gridDim.x) {
+        const uint32_t b = guide_moff[g], s = guide_moff[g + 1] - b;
+        for (uint32_t i = threadIdx.x; i < s; i += blockDim.x) {
+            const uint32_t mi = by_guide[b + i];
+            const MatchRec x = matches[mi];
+            uint32_t rank = 0; bool dup = false;
+            for (uint32_t j = 0; j < s; j++) {
+                const uint32_t mj = by_guide[b + j];
+                if (mj == mi) continue;
+                int c = match_cmp(matches[mj], x);
+                if (c < 0) rank++;
+                else if (c == 0) { if (mj < mi) { rank++; dup = true; } }
+            }
+            sorted[b + rank] = dup ? (mi | 0x80000000u) : mi;
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            uint32_t running = 0;
+            for (uint32_t base = 0; base < s; base += 32) {
+                uint32_t i = base + lane;
+                uint32_t w = 0, d = 0;
+                if (i < s) { uint32_t e = sorted[b + i]; if (!(e & 0x80000000u)) { w = matches[e].width; d = matches[e].info & 0xffu; } }
+                uint32_t x = w;
+                for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= (uint32_t)o) x += y; }
+                if (i < s) sorted_off[b + i] = running + x - w;
+                if (w && d < n_dist) atomicAdd(count_by_distance + (size_t)g * n_dist + d, w);
+                running += __shfl_sync(0xffffffffu, x, 31);
+            }
+            if (lane == 0) guide_nhits[g] = running;
+        }
+        __syncthreads();
+    }
+}
+
 // one warp per sorted match: write its rows
 __global__ void expand_hits_kernel(const MatchRec* matches, const uint32_t* guide_moff, const uint32_t* sorted,
                                    const uint32_t* sorted_off, const uint32_t* guide_hoff, uint32_t n_guides,
@@ -1187,8 +1227,9 @@ cudaError_t launch_scatter(const MatchRec* m, uint32_t n, const uint32_t* moff, 
     scatter_matches_kernel<<<grid_for(n, 256, 148 * 8), 256, 0, s>>>(m, n, moff, cursor, by_guide); return cudaGetLastError();
 }
 cudaError_t launch_order(const MatchRec* m, const uint32_t* moff, const uint32_t* by_guide, uint32_t n_guides, uint32_t n_dist,
-                         uint32_t* sorted, uint32_t* sorted_off, uint32_t* nhits, uint32_t* cbd, cudaStream_t s) {
-    order_matches_kernel<<<grid_for(n_guides * 32u, 256, 148 * 8), 256, 0, s>>>(m, moff, by_guide, n_guides, n_dist, sorted, sorted_off, nhits, cbd);
+                         uint32_t* sorted, uint32_t* sorted_off, uint32_t* nhits, uint32_t* cbd, bool many_per_guide, cudaStream_t s) {
+    if (many_per_guide) order_matches_cta_kernel<<<grid_for(n_guides, 1, 148 * 8), 256, 0, s>>>(m, moff, by_guide, n_guides, n_dist, sorted, sorted_off, nhits, cbd);
+    else order_matches_kernel<<<grid_for(n_guides * 32u, 256, 148 * 8), 256, 0, s>>>(m, moff, by_guide, n_guides, n_dist, sorted, sorted_off, nhits, cbd);
     return cudaGetLastError();
 }
 cudaError_t launch_expand(const MatchRec* m, const uint32_t* moff, const uint32_t* sorted, const uint32_t* sorted_off, const uint32_t* hoff,

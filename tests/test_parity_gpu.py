@@ -63,6 +63,17 @@ def test_gpu_matches_reference_golden(gsx, gpu_index, golden_dir, tmp_path, case
     assert open(out, "rb").read() == golden_output(case, variant)
 
 
+@pytest.mark.parametrize("case,variant", [("g200k", "m0_r2_d2_csv"), ("g150kN", "m1_r1_d1_csv"), ("g200k", "m3_csv"), ("g150kN", "m1_r1_d1_sam_succinct")])
+def test_cta_per_guide_match_ordering(gsx, gpu_index, golden_dir, tmp_path, monkeypatch, case, variant):
+    """order_matches_cta_kernel (chosen by itself when a batch averages hundreds of matches per guide, i.e. with bulges),
+    forced here on golden cases with many and with few matches per guide"""
+    monkeypatch.setenv("GSX_ORDER_CTA", "1")
+    kw = golden_manifest()["cases"][case]["variants"][variant]["opts"]
+    out = os.path.join(tmp_path, "g.out")
+    gpu_index(case).enumerate_file(golden_dir[case][1], out, _params(gsx, kw), fmt=kw.get("fmt", "csv"), mode=kw.get("mode", "complete"))
+    assert open(out, "rb").read() == golden_output(case, variant)
+
+
 @pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
 def test_every_search_kernel_variant(gsx, gpu_index, golden_dir, tmp_path, variant, monkeypatch):
     monkeypatch.setenv("GSX_SEARCH_VARIANT", str(variant))
