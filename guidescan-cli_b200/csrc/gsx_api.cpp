@@ -448,6 +448,47 @@ int gsx_prepare_guides(const gsx_guide* guides, size_t n, const gsx_params* p, g
     return GSX_OK;
 }
 
+// Small batches on the general kernel: a (guide, strand) task occupies one warp, so a few hundred guides would leave most
+// of the grid idle while a bulge search runs for seconds.  The roots are therefore expanded on the host, breadth first and
+// through the kernels' own node arithmetic (gsx_core.h make_child over the host copy of the blocks), until there are enough
+// nodes for every warp; the kernel then takes those nodes as its tasks.  Same tree, same matches.
+static DevStrand host_view(const HostStrand& h) {
+    DevStrand d{};
+    d.blocks = h.blocks.data(); d.sa_samples = h.sa_samples.data(); d.exc_rows = h.exc_rows.data(); d.exc_lf = h.exc_lf.data();
+    d.n_rows = h.n_rows.data(); d.n = (uint32_t)h.n; d.n_exc = (uint32_t)h.exc_rows.size(); d.n_nrows = (uint32_t)h.n_rows.size();
+    d.sa_shift = h.sa_shift; for (int c = 0; c < 5; c++) d.C[c] = h.C[c];
+    d.exc_lo = h.exc_rows.empty() ? 0xFFFFFFFFu : h.exc_rows.front(); d.exc_hi = h.exc_rows.empty() ? 0u : h.exc_rows.back();
+    d.blk_shift = 5;
+    return d;
+}
+template <bool WIDE>
+static std::vector<Node> expand_roots(const gsx_index* ix, const Prepared& prep, size_t g0, uint32_t n, uint32_t M, uint32_t R, uint32_t D,
+                                      size_t want, uint32_t max_depth) {
+    const DevStrand st[2] = {host_view(ix->host.st[0]), host_view(ix->host.st[1])};
+    std::vector<Node> cur;
+    for (uint32_t t = 0; t < 2 * n; t++) { Node r{}; r.sp = 0; r.ep = st[t & 1].n - 1; r.task = t; cur.push_back(r); }
+    for (uint32_t depth = 0; depth < max_depth && cur.size() < want; depth++) {
+        std::vector<Node> nxt; nxt.reserve(cur.size() * 4);
+        for (const Node& nd : cur) {
+            const DevStrand& s = st[nd.task & 1];
+            const GuideRec& g = prep.recs[g0 + (nd.task >> 1)];
+            ExpandCtx cx{&s, &g, &prep.pamsets[g.pamset], M, R, D};
+            uint32_t os[4], oe[4];
+            const OccBlock& b0 = s.blocks[nd.sp >> 6]; const OccBlock& b1 = s.blocks[(nd.ep + 1) >> 6];
+            block_occ(s, b0.cnt, b0.hi, b0.lo, nd.sp, os); block_occ(s, b1.cnt, b1.hi, b1.lo, nd.ep + 1, oe);
+            for (int cand = 0; cand < CAND_END; cand++) {
+                if (!WIDE && cand > CAND_FORK) break;
+                Node ch; bool emit;
+                if (!make_child<WIDE>(cand, nd, cx, os, oe, ch, emit)) continue;
+                if (emit) return cur;            // a finished alignment this close to the root (very short guide): keep the last complete level
+                nxt.push_back(ch);
+            }
+        }
+        cur.swap(nxt);
+    }
+    return cur;
+}
+
 struct DeviceJob {
     const gsx_index* ix = nullptr; int slot = 0;
     const Prepared* prep = nullptr; const gsx_params* p = nullptr;
@@ -608,6 +649,18 @@ static void run_device_job(DeviceJob* job) {
             CK(cudaMemcpyAsync(d_cb, cb.data(), cb.size() * 8, cudaMemcpyHostToDevice, s)); CK(cudaStreamSynchronize(s));
             a.combos = d_cb; a.n_combos = (uint32_t)cb.size();
         }
+        Node* d_gseeds = nullptr; uint32_t n_gseeds = 0;
+        if (!use_fast && env_int("GSX_EXPAND_ROOTS", 1)) {
+            const int gw = search_grid_warps(wide, variant, di.sm_count);
+            if (gw > 0 && (uint64_t)2 * n < (uint64_t)4 * gw) {                     // fewer tasks than the grid can keep busy
+                const std::vector<Node> gs = wide ? expand_roots<true>(job->ix, prep, job->g0, n, p.mismatches, p.rna_bulges, p.dna_bulges, (size_t)8 * gw, 6)
+                                                  : expand_roots<false>(job->ix, prep, job->g0, n, p.mismatches, p.rna_bulges, p.dna_bulges, (size_t)8 * gw, 6);
+                if (gs.size() > (size_t)2 * n) {
+                    d_gseeds = B.alloc<Node>(gs.size()); n_gseeds = (uint32_t)gs.size();
+                    CK(cudaMemcpyAsync(d_gseeds, gs.data(), gs.size() * sizeof(Node), cudaMemcpyHostToDevice, s)); CK(cudaStreamSynchronize(s));
+                }
+            }
+        }
         for (int attempt = 0;; attempt++) {
             if (attempt > 12) throw std::runtime_error("search arenas keep overflowing");
             int warps = use_fast ? search_fast_grid_warps(variant_f, di.sm_count) : search_grid_warps(wide, variant, di.sm_count);
@@ -620,6 +673,7 @@ static void run_device_job(DeviceJob* job) {
             SearchArgs m = a; m.p.M = p.mismatches; m.p.R = p.rna_bulges; m.p.D = p.dna_bulges; m.p.counting = 0;
             m.p.match_cap = (uint32_t)match_cap; m.p.spill_cap = spill_cap; m.spill = d_spill; m.matches = d_matches;
             m.skip = p.threshold > 0 ? d_dropped : nullptr;
+            m.gseeds = d_gseeds; m.n_gseeds = n_gseeds;
             CK(cudaEventRecord(ev[6], s));
             if (use_fast) run_fast_all_pams(m, ev[7]); else { CK(cudaEventRecord(ev[7], s)); CK(launch_search(m, wide, variant, di.sm_count, s, nullptr)); n_launches++; }
             uint32_t h[4]; CK(cudaMemcpyAsync(h, d_ctrs, sizeof h, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s));

@@ -141,7 +141,20 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) search_kernel(SearchArgs a) 
                 __syncwarp();
                 count += take; spill_count -= take;
             }
-            if (count < n_need && tasks_remain) {                    // start one more (guide, strand) task
+            if (count < n_need && tasks_remain && a.gseeds) {        // tasks = pre-expanded nodes, 32 at a time (count < 32 <= CAP - 32)
+                uint32_t t = 0;
+                if (lane == 0) t = atomicAdd(a.task_counter, 32u);
+                t = __shfl_sync(FULL, t, 0);
+                if (t >= a.n_gseeds) tasks_remain = false;
+                else {
+                    const uint32_t i = t + lane;
+                    const bool ok = i < a.n_gseeds && !(a.skip && a.skip[a.gseeds[i].task >> 1]);
+                    const uint32_t m = __ballot_sync(FULL, ok);
+                    if (ok) ring.store(head + count + __popc(m & lt_mask), a.gseeds[i]);
+                    __syncwarp();
+                    count += __popc(m);
+                }
+            } else if (count < n_need && tasks_remain) {             // start one more (guide, strand) task
                 uint32_t t = 0;
                 if (lane == 0) t = atomicAdd(a.task_counter, 1u);
                 t = __shfl_sync(FULL, t, 0);

@@ -39,6 +39,8 @@ struct SearchArgs {
     uint32_t pin_width;                // packed-block loads of intervals at least this wide ask L2 to keep the line (evict_last)
     const uint64_t* combos;            // k-mer jump table enumeration: substitution combos over characters 2 .. ftab_L - 1
     uint32_t n_combos;
+    const Node* gseeds;                // general kernel, if set: the tasks are these nodes (roots expanded a few levels on the host
+    uint32_t n_gseeds;                 // so that a small batch still gives every warp work), not (guide, strand) roots
     const SeedNode* seeds;             // if set: the tasks are these level-L nodes (written by sweep_kernel), not (guide, strand) roots
     const uint32_t* n_seeds;           // device word: number of seeds written (may exceed seed_cap if the queue overflowed)
     uint32_t seed_cap;
