@@ -394,7 +394,7 @@ int gsx_prepare_guides(const gsx_guide* guides, size_t n, const gsx_params* p, g
     }
     // pass 2 (parallel over chunks of guides): symbol packing in consumption order (process.hpp:63, index.hpp:214)
     out.gq.resize(n);
-    struct Chunk { size_t max_total = 0; uint32_t min_qlen = 255; bool bad_len = false, fast = true; };
+    struct Chunk { size_t max_total = 0; uint32_t min_qlen = 255, max_qlen = 0; bool bad_len = false, fast = true; };
     const size_t n_thr = std::max<size_t>(1, std::min<size_t>({(size_t)8, n / 16384, (size_t)std::max(1u, std::thread::hardware_concurrency())}));
     std::vector<Chunk> chunks(n_thr);
     auto work = [&](size_t t) {
@@ -417,7 +417,7 @@ int gsx_prepare_guides(const gsx_guide* guides, size_t n, const gsx_params* p, g
             out.gq[i] = v;
             if (!acgt || sl > 29) c.fast = false;
             c.max_total = std::max(c.max_total, sl + set_mp[r.pamset]);
-            c.min_qlen = std::min<uint32_t>(c.min_qlen, (uint32_t)sl);
+            c.min_qlen = std::min<uint32_t>(c.min_qlen, (uint32_t)sl); c.max_qlen = std::max<uint32_t>(c.max_qlen, (uint32_t)sl);
         }
     };
     if (n_thr == 1) work(0);
@@ -426,6 +426,7 @@ int gsx_prepare_guides(const gsx_guide* guides, size_t n, const gsx_params* p, g
     for (const Chunk& c : chunks) {
         if (c.bad_len) return fail(GSX_ERR_ARG, "guide sequence length must be 1..32");
         max_total = std::max(max_total, c.max_total); all_fast = all_fast && c.fast; out.min_qlen = std::min(out.min_qlen, c.min_qlen);
+        out.max_qlen = std::max(out.max_qlen, c.max_qlen);
     }
     // PAMs of different lengths inside one set give match strings of different lengths: only the left-aligned (wide) key
     // orders those as std::string does
@@ -436,7 +437,12 @@ int gsx_prepare_guides(const gsx_guide* guides, size_t n, const gsx_params* p, g
     // fast path: no bulges, the same PAM list for every guide (alternative PAMs = one search pass each), ACGT-only guides of
     // at most 29 nt
     out.fast_ok = !out.wide && set_of.size() == 1 && n > 0 && all_fast;
-    if (out.fast_ok) {
+    // bulges: the same batch with every guide replaced by its edited guides (gsx_core.h variant_rewrite), if those are few
+    // enough to be worth it and still fit the narrow keys
+    out.variant_ok = bulges && set_of.size() == 1 && n > 0 && all_fast && same_plen && max_total + p->dna_bulges <= 27 &&
+                     out.max_qlen + p->dna_bulges <= 29 && p->rna_bulges + p->dna_bulges <= 4 && env_int("GSX_VARIANTS", 1) &&
+                     bulge_variant_count(out.max_qlen, p->rna_bulges, p->dna_bulges) <= (uint64_t)env_int("GSX_VARIANTS_MAX", 8192);
+    if (out.fast_ok || out.variant_ok) {
         const PamSet& ps = out.pamsets[0];
         out.n_fast_pams = ps.n_pams;
         for (uint32_t k = 0; k < ps.n_pams; k++) {

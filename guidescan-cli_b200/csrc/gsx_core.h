@@ -209,6 +209,60 @@ GSX_HD void fill_match(MatchRec& m, const Node& ch, bool wide) {
     m.info = meta_mm(ch.meta) | (meta_dna(ch.meta) << 8) | (meta_rna(ch.meta) << 16) | (len << 24);
 }
 
+// ---- bulges as edited guides -----------------------------------------------------------------------------------------
+// With max_bulge_size = 1 (hard-wired by the reference, process.hpp:82-87) the bulge-aware recursion (index.hpp:250-375)
+// reduces to: walk the guide in consumption order; before position lvl >= 1 (and once more after the last position, before
+// the PAM) any number of DNA bulges may consume one arbitrary genome character each, written in lower case, at no mismatch
+// cost; position lvl >= 1 may be skipped without consuming anything (RNA bulge, written '.'); every such step needs budget
+// (dna < D, rna < R), nothing else -- `state` / `curr_bulge_size` only ever matter for bulges longer than one.
+// Hence: alignments of the guide with bulges = union, over every op list within the budgets, of the MISMATCH-ONLY
+// alignments of an edited guide (skipped positions removed, inserted positions holding a concrete character that must
+// match exactly).  The edited guides run through the specialised kernels like any other guide; variant_rewrite turns
+// their matches back into the reference's strings.  Different op lists can spell the same string (then with the same
+// counts and the same interval): the collector's de-duplication on the string takes care of it, as std::set does.
+//   op byte (up to four per variant, first op in the low byte, 0 = none): lvl | kind << 5 | sym << 6
+//     kind 0 = RNA bulge: guide position lvl is skipped;  kind 1 = DNA bulge: genome symbol sym consumed before position lvl
+//   ops are ordered by lvl, DNA bulges of a level before its skip.
+GSX_HD uint32_t variant_op(uint32_t lvl, uint32_t kind, uint32_t sym) { return lvl | (kind << 5) | (sym << 6); }
+
+// the edited guide: 2-bit symbols in consumption order | length << 58; q = the guide's own symbols (all < 4)
+GSX_HD uint64_t variant_pack(const uint8_t* q, uint32_t qlen, uint32_t desc) {
+    uint64_t v = 0; uint32_t n = 0;
+    for (uint32_t lvl = 0; lvl <= qlen; lvl++) {
+        while ((desc & 0xFFu) && (desc & 31u) == lvl && (desc & 32u)) { v |= (uint64_t)((desc >> 6) & 3u) << (2u * n); n++; desc >>= 8; }
+        if (lvl == qlen) break;
+        if ((desc & 0xFFu) && (desc & 31u) == lvl) { desc >>= 8; continue; }              // skipped
+        v |= (uint64_t)(q[lvl] & 3u) << (2u * n); n++;
+    }
+    return v | ((uint64_t)n << 58);
+}
+
+// match of an edited guide (narrow key over its own characters) -> match of the guide itself (wide key, bulge counts);
+// false if an inserted position was matched by substitution (that alignment belongs to the variant holding the other symbol)
+GSX_HD bool variant_rewrite(const MatchRec& in, const GuideRec& g, uint32_t desc, uint32_t real_task, MatchRec& out) {
+    const uint32_t vlen = in.info >> 24;
+    uint8_t dg[40];
+    { uint64_t k = in.key_lo; for (uint32_t i = vlen; i-- > 0;) { dg[i] = (uint8_t)(k % 5ull); k /= 5ull; } }
+    Node acc; acc.key_lo = acc.key_hi = 0;
+    uint32_t vl = 0, len = 0, dna = 0, rna = 0;
+    const uint32_t qlen = g.qlen;
+    for (uint32_t lvl = 0; lvl <= qlen; lvl++) {
+        while ((desc & 0xFFu) && (desc & 31u) == lvl && (desc & 32u)) {
+            if (dg[vl] != 0) return false;
+            key_append<true>(acc, 7u + ((desc >> 6) & 3u)); vl++; len++; dna++; desc >>= 8;
+        }
+        if (lvl == qlen) break;
+        if ((desc & 0xFFu) && (desc & 31u) == lvl) { key_append<true>(acc, 1u); len++; rna++; desc >>= 8; continue; }
+        const uint32_t d = dg[vl++];
+        key_append<true>(acc, d == 0 ? wide_upper_digit(g.q[lvl]) : 6u + d); len++;
+    }
+    for (; vl < vlen; vl++) { const uint32_t d = dg[vl]; key_append<true>(acc, d < 3u ? 2u + d : (d == 3u ? 5u : 6u)); len++; }   // PAM: A,C,G,N,T
+    key_left_align(acc.key_hi, acc.key_lo, len);
+    out.key_hi = acc.key_hi; out.key_lo = acc.key_lo; out.task = real_task; out.sp = in.sp; out.width = in.width;
+    out.info = (in.info & 0xffu) | (dna << 8) | (rna << 16) | (len << 24);
+    return true;
+}
+
 // ---- decoding a match back into the reference's match.sequence ---------------------------------------------
 GSX_HD char sym_char(uint32_t s) { return s == 0 ? 'A' : s == 1 ? 'C' : s == 2 ? 'G' : s == 3 ? 'T' : s == 4 ? 'N' : '?'; }
 GSX_HD char complement_char(char c) {                                               // sequences.cxx:14-28

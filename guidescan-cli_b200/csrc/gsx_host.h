@@ -107,6 +107,10 @@ struct Prepared {
     std::vector<uint64_t> gq;      // per guide: 2-bit symbols in consumption order | qlen << 58
     uint32_t pampack = 0, plen = 0, min_qlen = 0;      // (first PAM of the list)
     uint32_t n_fast_pams = 0, pampacks[kMaxPams] = {0}, plens[kMaxPams] = {0};      // every PAM of the (single) PAM set: one search pass each
+    // bulges on the specialised kernels: every guide is replaced by its edited guides (gsx_core.h variant_rewrite); valid when
+    // the batch would be a fast-path batch without its bulges and the edited guides are few enough
+    bool variant_ok = false;
+    uint32_t max_qlen = 0;
 };
 
 // every way to substitute at most M of the first n_pos characters (k-mer jump table enumeration, gsx_core.h)
@@ -114,6 +118,9 @@ std::vector<uint64_t> ftab_combos(uint32_t n_pos, uint32_t M);
 // slice-major enumeration plan (gsx_core.h sweep_pattern): the xor table of every way to substitute at most M of the
 // characters outside the slice, listed per pass and budget
 void sweep_make_plan(uint32_t L, uint32_t sb, uint32_t M, SweepPlan& plan, std::vector<uint32_t>& xtab);
+// bulges as edited guides (gsx_core.h variant_op): every op list within the budgets; their number
+std::vector<uint32_t> bulge_variants(uint32_t qlen, uint32_t R, uint32_t D);
+uint64_t bulge_variant_count(uint32_t qlen, uint32_t R, uint32_t D);
 }  // namespace gsx
 
 struct gsx_result {

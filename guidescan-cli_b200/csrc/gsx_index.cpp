@@ -207,6 +207,30 @@ std::vector<uint64_t> ftab_combos(uint32_t n_pos, uint32_t M) {
     return out;
 }
 
+// every op list (gsx_core.h variant_op) with at most R RNA bulges and D DNA bulges for a guide of qlen characters, in the
+// canonical order (by level; the DNA bulges of a level, in sequence, before its skip); the empty list comes last of its
+// branch like everything else, order is irrelevant.  R + D <= 4.
+std::vector<uint32_t> bulge_variants(uint32_t qlen, uint32_t R, uint32_t D) {
+    std::vector<uint32_t> out;
+    struct Rec { static void go(uint32_t lvl, uint32_t qlen, uint32_t r, uint32_t d, uint32_t desc, uint32_t nops, std::vector<uint32_t>& out) {
+        if (lvl > qlen) { out.push_back(desc); return; }
+        if (d && nops < 4) for (uint32_t sym = 0; sym < 4; sym++) go(lvl, qlen, r, d - 1, desc | (variant_op(lvl, 1, sym) << (8 * nops)), nops + 1, out);
+        if (lvl < qlen && r && nops < 4) go(lvl + 1, qlen, r - 1, d, desc | (variant_op(lvl, 0, 0) << (8 * nops)), nops + 1, out);
+        go(lvl + 1, qlen, r, d, desc, nops, out);
+    } };
+    if (R + D <= 4 && qlen >= 1 && qlen < 32) Rec::go(1, qlen, R, D, 0, 0, out);
+    return out;
+}
+uint64_t bulge_variant_count(uint32_t qlen, uint32_t R, uint32_t D) {
+    // skips: subsets of positions 1 .. qlen-1 of size <= R; inserts: sequences of <= D (slot, symbol) with slots non-decreasing
+    // = multisets of slots (qlen of them) times 4^k
+    auto choose = [](uint64_t n, uint64_t k) { if (k > n) return (uint64_t)0; uint64_t v = 1; for (uint64_t i = 0; i < k; i++) v = v * (n - i) / (i + 1); return v; };
+    uint64_t skips = 0, ins = 0;
+    for (uint32_t k = 0; k <= R; k++) skips += choose(qlen ? qlen - 1 : 0, k);
+    for (uint32_t k = 0; k <= D; k++) ins += choose(qlen + k - 1, k) << (2 * k);
+    return skips * ins;
+}
+
 void sweep_make_plan(uint32_t L, uint32_t sb, uint32_t M, SweepPlan& plan, std::vector<uint32_t>& xtab) {
     memset(&plan, 0, sizeof plan);
     plan.L = L; plan.sb = sb; plan.M = M;

@@ -41,6 +41,7 @@ static DevStrand view_of(const HostStrand& h) {
 // look-ahead planes t1..t6 per 64-row block (what build_lookahead_kernel writes behind each OccBlock), built on the host
 static std::vector<uint64_t> g_look[2];     // 12 words per block: hi1, lo1, ..., hi6, lo6
 static bool g_prune = false;
+static bool g_variants = false;  // bulges through edited guides (gsx_core.h variant_rewrite), as gsx_enumerate does when Prepared::variant_ok
 
 static std::vector<uint64_t> g_tail[2];     // 4 words per block: hi7, lo7, hi8, lo8 (the scratch planes the summaries' sum2 is built from)
 static void build_look(const DevStrand& st, std::vector<uint64_t>& look, std::vector<uint64_t>& tail) {
@@ -398,6 +399,7 @@ int main(int argc, char** argv) {
         else if (a == "--lookahead") g_prune = true;
         else if (a == "--ftab") g_ftab_L = atoi(argv[++i]);
         else if (a == "--sweep") g_sweep_sb = atoi(argv[++i]);
+        else if (a == "--variants") g_variants = true;
         else if (a == "--sam") sam = true; else if (a == "--succinct") complete = false; else if (a == "-a") alts.push_back(argv[++i]);
         else { fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
     }
@@ -422,14 +424,35 @@ int main(int argc, char** argv) {
     Prepared prep;
     if (gsx_prepare_guides(gg.data(), n, &p, prep)) { fprintf(stderr, "%s\n", gsx_last_error()); return 1; }
     const uint32_t n_dist = p.mismatches + 1;
+    // bulges as edited guides: one mismatch-only batch holding every variant of every guide
+    Prepared vprep; std::vector<uint32_t> vdesc, voff(n + 1, 0);
+    if (g_variants) {
+        if (!prep.variant_ok) { fprintf(stderr, "--variants: not a variant batch (wide %d, max_qlen %u, min_qlen %u, PAM passes %u)\n", (int)prep.wide, prep.max_qlen, prep.min_qlen, prep.n_fast_pams); return 4; }
+        memcpy(vprep.pamsets, prep.pamsets, sizeof prep.pamsets); vprep.max_pams = prep.max_pams; vprep.wide = false; vprep.fast_ok = true;
+        vprep.pampack = prep.pampack; vprep.plen = prep.plen; vprep.n_fast_pams = prep.n_fast_pams;
+        for (int k = 0; k < kMaxPams; k++) { vprep.pampacks[k] = prep.pampacks[k]; vprep.plens[k] = prep.plens[k]; }
+        for (size_t g = 0; g < n; g++) {
+            const GuideRec& r = prep.recs[g];
+            if (bulge_variant_count(r.qlen, p.rna_bulges, p.dna_bulges) != bulge_variants(r.qlen, p.rna_bulges, p.dna_bulges).size()) { fprintf(stderr, "variant count formula is off\n"); return 3; }
+            for (uint32_t desc : bulge_variants(r.qlen, p.rna_bulges, p.dna_bulges)) {
+                const uint64_t v = variant_pack(r.q, r.qlen, desc);
+                GuideRec e = r; e.qlen = (uint8_t)(v >> 58);
+                for (uint32_t l = 0; l < e.qlen; l++) e.q[l] = (uint8_t)((v >> (2 * l)) & 3u);
+                vprep.recs.push_back(e); vprep.gq.push_back(v); vdesc.push_back(desc);
+            }
+            voff[g + 1] = (uint32_t)vdesc.size();
+        }
+        vprep.min_qlen = 255; for (const GuideRec& e : vprep.recs) vprep.min_qlen = std::min<uint32_t>(vprep.min_qlen, e.qlen);
+    }
+    const Prepared& fprep = g_variants ? vprep : prep;          // the batch the specialised-kernel mirrors (--lookahead / --ftab / --sweep) work on
     if (g_ftab_L) {
         g_pow5[0] = 1; for (int i = 1; i < 32; i++) g_pow5[i] = g_pow5[i - 1] * 5ull;
         build_ftab_host(st[0], g_ftab_L, g_ftab[0]); build_ftab_host(st[1], g_ftab_L, g_ftab[1]);
     }
-    if ((g_prune || g_ftab_L || g_sweep_sb) && prep.n_fast_pams > 1) { fprintf(stderr, "--lookahead / --ftab / --sweep mirror the single-PAM passes: no -a here\n"); return 2; }
-    if (g_sweep_sb && (!g_prune || !g_ftab_L || !prep.fast_ok || g_sweep_sb + 3 > g_ftab_L)) { fprintf(stderr, "--sweep SB needs --lookahead, --ftab L >= SB + 3 and a fast-path batch\n"); return 2; }
+    if ((g_prune || g_ftab_L || g_sweep_sb) && fprep.n_fast_pams > 1) { fprintf(stderr, "--lookahead / --ftab / --sweep mirror the single-PAM passes: no -a here\n"); return 2; }
+    if (g_sweep_sb && (!g_prune || !g_ftab_L || !fprep.fast_ok || g_sweep_sb + 3 > g_ftab_L)) { fprintf(stderr, "--sweep SB needs --lookahead, --ftab L >= SB + 3 and a fast-path batch\n"); return 2; }
     if (g_prune) {
-        if (!prep.fast_ok) { fprintf(stderr, "--lookahead needs a fast-path batch (one PAM, ACGT guides, no bulges)\n"); return 2; }
+        if (!fprep.fast_ok) { fprintf(stderr, "--lookahead needs a fast-path batch (one PAM, ACGT guides, no bulges)\n"); return 2; }
         build_look(st[0], g_look[0], g_tail[0]); build_look(st[1], g_look[1], g_tail[1]);
     }
     if (g_sweep_sb) for (int s = 0; s < 2; s++) build_summaries_host(st[s], g_look[s], g_tail[s], g_ftab[s], g_sum0[s], g_sum1[s], g_sum2[s]);
@@ -447,6 +470,15 @@ int main(int argc, char** argv) {
             if (count > 1) { dropped[g] = 1; continue; }
         }
         std::vector<MatchRec> ms;
+        if (g_variants) {
+            std::vector<MatchRec> tmp;
+            for (uint32_t v = voff[g]; v < voff[g + 1]; v++)
+                for (uint32_t s = 0; s < 2; s++) {
+                    tmp.clear();
+                    dfs<false>(st, vprep, 2 * v + s, p.mismatches, 0, 0, false, nullptr, tmp, &nodes);
+                    for (const MatchRec& m : tmp) { MatchRec o; if (variant_rewrite(m, prep.recs[g], vdesc[v], (uint32_t)(2 * g + s), o)) ms.push_back(o); }
+                }
+        } else
         for (uint32_t s = 0; s < 2; s++) {
             if (prep.wide) dfs<true>(st, prep, (uint32_t)(2 * g + s), p.mismatches, p.rna_bulges, p.dna_bulges, false, nullptr, ms, &nodes);
             else dfs<false>(st, prep, (uint32_t)(2 * g + s), p.mismatches, p.rna_bulges, p.dna_bulges, false, nullptr, ms, &nodes);

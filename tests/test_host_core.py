@@ -65,3 +65,42 @@ def test_lookahead_pruning_keeps_output_and_cuts_nodes(harness, tmp_path, m):
     assert nodes["ftab"] < nodes["plain"] and nodes["both"] < nodes["ftab"], nodes
     # the slice-major front end filters level-L nodes before the walk expands them
     assert nodes["sweep1"] < nodes["both"] and nodes["sweep3"] == nodes["sweep1"], nodes
+
+
+def _golden_subset(case, tmp_path, keep):
+    """guides file restricted to rows satisfying keep(fields) + the matching slice of a golden output"""
+    lines = open(os.path.join(ROOT, "tests", "golden", case + ".guides.csv")).read().splitlines()
+    rows = [l for l in lines[1:] if keep(l.split(","))]
+    path = os.path.join(tmp_path, "subset.csv")
+    with open(path, "w") as f:
+        f.write("\n".join([lines[0]] + rows) + "\n")
+    ids = {l.split(",")[0] for l in rows}
+
+    def slice_of(text: str, sam: bool) -> str:
+        out = []
+        for i, l in enumerate(text.splitlines(True)):
+            if (sam and l.startswith("@")) or (not sam and i == 0) or l.split("\t" if sam else ",", 1)[0] in ids:
+                out.append(l)
+        return "".join(out)
+    return path, slice_of
+
+
+BULGE_VARIANTS = [v for c, v in golden_cases() if c == "g200k" and ("_r" in v or "_d" in v)]
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("variant", BULGE_VARIANTS)
+@pytest.mark.parametrize("mirror", ["root", "table"])
+def test_bulges_as_edited_guides_match_golden(harness, golden_dir, golden_index, tmp_path, monkeypatch, variant, mirror):
+    """gsx_core.h variant_pack / variant_rewrite + gsx_host.h bulge_variants: the bulge search restated as mismatch-only
+    searches of edited guides (what gsx_enumerate runs on the specialised kernels when Prepared::variant_ok) gives the
+    reference's text byte for byte -- including two bulges of each kind, alternative PAMs and guides of 19-21 nt."""
+    kw = golden_manifest()["cases"]["g200k"]["variants"][variant]["opts"]
+    if mirror == "table" and (kw.get("alt_pams") or kw.get("rna_bulges", 0) + kw.get("dna_bulges", 0) > 2):
+        pytest.skip("the table / look-ahead mirrors run single-PAM passes; the 600k-variant case runs once")
+    monkeypatch.setenv("GSX_VARIANTS_MAX", "100000000")
+    gcsv, slice_of = _golden_subset("g200k", str(tmp_path), lambda f: f[2] == "NGG" and set(f[1]) <= set("ACGT"))
+    out = os.path.join(tmp_path, "h.out")
+    extra = ["--variants"] + (["--lookahead", "--ftab", "7"] if mirror == "table" else [])
+    subprocess.check_call([harness, golden_index["g200k"], gcsv, out] + variant_cli_args(kw) + extra, stderr=subprocess.DEVNULL)
+    assert open(out).read() == slice_of(golden_output("g200k", variant).decode(), kw.get("fmt") == "sam")
