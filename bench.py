@@ -290,7 +290,7 @@ def run_gsx(args):
                          "frac_of_random_sector_peak": (achieved / rg["gb_per_s"]) if rg else None},
             "counters": {"hits_per_guide": hits / total_guides, "spills": ctr_tot["spills"], "lf_steps": ctr_tot["lf_steps"],
                          "ms_search": ctr_tot["ms_search"] / args.steps, "ms_sweep": ctr_tot["ms_sweep"] / args.steps,
-                         "seeds_per_guide": ctr_tot["seeds"] / (per * args.steps), "ms_arrange": ctr_tot["ms_arrange"] / args.steps,
+                         "seeds_per_guide": ctr_tot["seeds"] / (per * args.steps), "edited_guides_per_guide": ctr_tot.get("edited_guides", 0) / (per * args.steps), "ms_arrange": ctr_tot["ms_arrange"] / args.steps,
                          "ms_locate": ctr_tot["ms_locate"] / args.steps, "ms_score": ctr_tot["ms_score"] / args.steps,
                          "ms_d2h": ctr_tot["ms_d2h"] / args.steps, "ms_h2d": ctr_tot["ms_h2d"] / args.steps,
                          "ms_host_prepare": ctr_tot["ms_prepare"] / args.steps, "ms_call_wall": ctr_tot["ms_wall"] / args.steps},

@@ -539,8 +539,10 @@ static void run_device_job(DeviceJob* job) {
         a.guide_nmatch = d_nmatch; a.max_iters = 1u << 28; a.max_pams = prep.max_pams;
         a.p.n_tasks = 2 * n;
         // fast path (search_fast_kernel) when the batch and the index allow it; GSX_FORCE_GENERAL=1 keeps the general kernel
-        const bool use_fast = prep.fast_ok && !env_int("GSX_FORCE_GENERAL", 0) && n < (1u << 23) &&
+        const bool use_fast = (prep.fast_ok || prep.variant_ok) && !env_int("GSX_FORCE_GENERAL", 0) && n < (1u << 23) &&
                               di.st[0].d.n_exc == 1 && di.st[1].d.n_exc == 1 && di.st[0].d.n_nrows == 0 && di.st[1].d.n_nrows == 0;
+        // bulges: the search runs over the guides' edited forms (gsx_core.h variant_rewrite), in chunks, on the same kernels
+        const bool use_variants = use_fast && prep.variant_ok;
         const int variant_f = env_int("GSX_FAST_VARIANT", di.st[0].d.lines ? 1 : 0);
         if (use_fast) {
             uint64_t* d_gq = B.alloc<uint64_t>(n);
@@ -555,43 +557,47 @@ static void run_device_job(DeviceJob* job) {
         }
         // slice-major front end (sweep_kernel) for large batches: needs the jump table and the look-ahead lines
         const uint32_t ftab_L = di.st[0].d.ftab_L;
-        uint32_t sweep_sb = 0;
-        bool use_sweep = use_fast && ftab_L >= 6 && di.st[1].d.ftab_L == ftab_L && di.st[0].d.sum0 && di.st[1].d.sum0 && env_int("GSX_SWEEP", 1) &&
-                         n >= (uint32_t)env_int("GSX_SWEEP_MIN", 8192) && prep.min_qlen >= ftab_L && p.mismatches <= 4 && p.threshold <= 4;
-        if (use_sweep) {
+        // slice width (characters) for a batch of ng guides no shorter than min_qlen, 0 = no sweep
+        auto plan_sweep = [&](uint32_t ng, uint32_t min_qlen, uint32_t M) -> uint32_t {
+            bool ok = use_fast && ftab_L >= 6 && di.st[1].d.ftab_L == ftab_L && di.st[0].d.sum0 && di.st[1].d.sum0 && env_int("GSX_SWEEP", 1) &&
+                      ng >= (uint32_t)env_int("GSX_SWEEP_MIN", 8192) && min_qlen >= ftab_L && M <= 4;
+            if (!ok) return 0;
             const double per_strand = 40.0 * std::pow(4.0, (double)ftab_L);                  // sum0 + the part of sum1 that is touched
             const double target = (double)env_int("GSX_SWEEP_SLICE_MB", 12) * 1e6;
-            sweep_sb = 1; while (sweep_sb < ftab_L - 3 && per_strand / std::pow(4.0, (double)sweep_sb) > target) sweep_sb++;
-            if (env_int("GSX_SWEEP_SB", 0) > 0) sweep_sb = (uint32_t)env_int("GSX_SWEEP_SB", 0);
-            if (sweep_sb < 1 || sweep_sb + 3 > ftab_L) use_sweep = false;
-            if (2.0 * std::pow(4.0, (double)sweep_sb) * ((n + 31) / 32) * 8.0 >= 4.0e9) use_sweep = false;
-        }
+            uint32_t sb = 1; while (sb < ftab_L - 3 && per_strand / std::pow(4.0, (double)sb) > target) sb++;
+            if (env_int("GSX_SWEEP_SB", 0) > 0) sb = (uint32_t)env_int("GSX_SWEEP_SB", 0);
+            if (sb < 1 || sb + 3 > ftab_L) return 0;
+            if (2.0 * std::pow(4.0, (double)sb) * ((ng + 31) / 32) * 8.0 >= 4.0e9) return 0;
+            return sb;
+        };
+        const uint32_t sweep_sb = use_variants ? 0u : plan_sweep(n, prep.min_qlen, std::max<uint32_t>(p.mismatches, p.threshold > 0 ? (uint32_t)p.threshold : 0u));
+        bool use_sweep = sweep_sb != 0;
         uint64_t queue_cap = std::max<uint64_t>((uint64_t)n * 1024, 1u << 20);
         if (env_int("GSX_QUEUE_CAP", 0) > 0) queue_cap = (uint64_t)env_int("GSX_QUEUE_CAP", 0);
         SeedNode* d_queue = nullptr;
         uint64_t n_launches = 0;
-        // fast path launch: [sweep_kernel ->] search_fast_kernel.  d_ctrs: [3] seed queue count, [4] sweep work-unit counter
-        auto launch_fast = [&](SearchArgs& m, cudaEvent_t ev_mid) {
-            if (use_sweep) {
+        uint32_t* d_xtab = nullptr; uint32_t xtab_M = ~0u, xtab_sb = 0, n_xtab = 0; SweepPlan xplan{};
+        uint32_t* d_gtab = nullptr; size_t gtab_cap = 0;
+        // fast path launch over ng guides (m.gq): [sweep_kernel ->] search_fast_kernel.  d_ctrs: [3] seed queue count, [4] sweep work-unit counter
+        auto launch_fast = [&](SearchArgs& m, uint32_t ng, uint32_t sb, cudaEvent_t ev_mid) {
+            if (sb) {
                 SweepArgs w{};
-                std::vector<uint32_t> xtab;
-                sweep_make_plan(ftab_L, sweep_sb, m.p.M, w.plan, xtab);
-                uint32_t* d_xtab = B.alloc<uint32_t>(xtab.size());
-                CK(cudaMemcpyAsync(d_xtab, xtab.data(), xtab.size() * 4, cudaMemcpyHostToDevice, s)); CK(cudaStreamSynchronize(s));
-                if (!d_queue) d_queue = B.alloc<SeedNode>(queue_cap);
-                w.st[0] = m.st[0]; w.st[1] = m.st[1]; w.gq = m.gq; w.skip = m.skip; w.n_guides = n; w.xtab = d_xtab; w.n_xtab = (uint32_t)xtab.size();
-                w.M = m.p.M; w.plen = m.plen; w.pampack = m.pampack; w.load_mode = (uint32_t)env_int("GSX_SWEEP_LOAD", 2);
-                {   // enough work units per slice that the whole grid stays within about one slice (L2 residency)
-                    const int sv = env_int("GSX_SWEEP_VARIANT", 2);
-                    const uint32_t warps = (uint32_t)di.sm_count * 8u * (sv == 0 ? 3u : sv == 1 ? 2u : sv == 2 ? 4u : sv == 3 ? 6u : sv == 5 ? 5u : 8u);
-                    const uint32_t n_gb = (n + 31) / 32;
-                    uint32_t parts = 1; (void)warps; (void)n_gb;                   // measured: cutting the units does not pay (profiles/r01r_*)
-                    if (env_int("GSX_SWEEP_PARTS", 0) > 0) parts = (uint32_t)env_int("GSX_SWEEP_PARTS", 0);
-                    w.parts = parts;
+                if (xtab_M != m.p.M || xtab_sb != sb) {
+                    std::vector<uint32_t> xtab;
+                    sweep_make_plan(ftab_L, sb, m.p.M, xplan, xtab);
+                    if (d_xtab) B.free_one(d_xtab);
+                    d_xtab = B.alloc<uint32_t>(xtab.size()); n_xtab = (uint32_t)xtab.size(); xtab_M = m.p.M; xtab_sb = sb;
+                    CK(cudaMemcpyAsync(d_xtab, xtab.data(), xtab.size() * 4, cudaMemcpyHostToDevice, s)); CK(cudaStreamSynchronize(s));
                 }
+                w.plan = xplan;
+                if (!d_queue) d_queue = B.alloc<SeedNode>(queue_cap);
+                w.st[0] = m.st[0]; w.st[1] = m.st[1]; w.gq = m.gq; w.skip = m.skip; w.n_guides = ng; w.xtab = d_xtab; w.n_xtab = n_xtab;
+                w.M = m.p.M; w.plen = m.plen; w.pampack = m.pampack; w.load_mode = (uint32_t)env_int("GSX_SWEEP_LOAD", 2);
+                w.parts = 1;                                                       // measured: cutting the units does not pay (profiles/r01r_*)
                 w.queue = d_queue; w.queue_cap = (uint32_t)queue_cap; w.queue_count = d_ctrs + 3; w.item_counter = d_ctrs + 4;
                 w.error_flag = d_ctrs + 2; w.stats = d_stats;
-                w.gtab = B.alloc<uint32_t>((size_t)n * 20);
+                if (gtab_cap < ng) { if (d_gtab) B.free_one(d_gtab); d_gtab = B.alloc<uint32_t>((size_t)ng * 20); gtab_cap = ng; }
+                w.gtab = d_gtab;
                 CK(launch_sweep_guides(w, s)); n_launches++;
                 CK(launch_sweep(w, env_int("GSX_SWEEP_VARIANT", 2), di.sm_count, s)); n_launches++;
                 m.seeds = d_queue; m.n_seeds = d_ctrs + 3; m.seed_cap = (uint32_t)queue_cap; m.combos = nullptr; m.n_combos = 0;
@@ -601,11 +607,11 @@ static void run_device_job(DeviceJob* job) {
         };
         // alternative PAMs (process.hpp:51-56): the searches of the PAMs are independent and their matches are collected in
         // the same per-guide sets, so each PAM gets its own pass over the same arenas; only the work counters start over
-        auto run_fast_all_pams = [&](SearchArgs& m, cudaEvent_t ev_mid) {
+        auto run_fast_all_pams = [&](SearchArgs& m, uint32_t ng, uint32_t sb, cudaEvent_t ev_mid) {
             for (uint32_t k = 0; k < prep.n_fast_pams; k++) {
                 m.pampack = prep.pampacks[k]; m.plen = prep.plens[k];
                 if (k) { CK(cudaMemsetAsync(d_ctrs, 0, 4, s)); CK(cudaMemsetAsync(d_ctrs + 3, 0, 8, s)); }      // task / seed-queue / work-unit counters
-                launch_fast(m, k == 0 ? ev_mid : nullptr);
+                launch_fast(m, ng, sb, k == 0 ? ev_mid : nullptr);
             }
         };
         auto grow_queue = [&]() { B.free_one(d_queue); d_queue = nullptr; queue_cap *= 4; if (queue_cap > (1ull << 31)) throw std::runtime_error("seed queue keeps overflowing"); };
@@ -622,14 +628,15 @@ static void run_device_job(DeviceJob* job) {
                 CK(cudaMemsetAsync(d_ctrs, 0, 8 * sizeof(uint32_t), s));
                 CK(cudaMemsetAsync(d_gcount, 0, (size_t)n * 8, s));
                 SearchArgs c = a; c.p.M = (uint32_t)p.threshold; c.p.R = c.p.D = 0; c.p.counting = 1; c.p.match_cap = 0; c.p.spill_cap = spill_cap;
-                if (use_fast && ftab_L && !use_sweep) {
+                const uint32_t sb_thr = plan_sweep(n, prep.min_qlen, c.p.M);
+                if (use_fast && ftab_L && !sb_thr) {
                     std::vector<uint64_t> cb = ftab_combos(ftab_L - 2, c.p.M);
                     uint64_t* d_cb = B.alloc<uint64_t>(cb.size());
                     CK(cudaMemcpyAsync(d_cb, cb.data(), cb.size() * 8, cudaMemcpyHostToDevice, s)); CK(cudaStreamSynchronize(s));
                     c.combos = d_cb; c.n_combos = (uint32_t)cb.size();
                 }
                 c.guide_count = d_gcount; c.spill = d_spill; c.skip = nullptr; c.matches = nullptr;
-                if (use_fast) run_fast_all_pams(c, nullptr); else { CK(launch_search(c, false, variant_n, di.sm_count, s, nullptr)); n_launches++; }
+                if (use_fast) run_fast_all_pams(c, n, sb_thr, nullptr); else { CK(launch_search(c, false, variant_n, di.sm_count, s, nullptr)); n_launches++; }
                 uint32_t h[3]; CK(cudaMemcpyAsync(h, d_ctrs, sizeof h, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s));
                 B.free_one(d_spill);
                 if (h[2] & GSX_KERR_WATCHDOG) throw std::runtime_error("search kernel watchdog tripped");
@@ -649,12 +656,106 @@ static void run_device_job(DeviceJob* job) {
         if (env_int("GSX_MATCH_CAP", 0) > 0) match_cap = (uint64_t)env_int("GSX_MATCH_CAP", 0);      // tests: force the retry path
         if (env_int("GSX_SPILL_CAP", 0) > 0) spill_cap = (uint32_t)env_int("GSX_SPILL_CAP", 0);
         MatchRec* d_matches = nullptr; uint32_t* d_spill = nullptr; uint32_t n_matches = 0, n_seeds_used = 0;
-        if (use_fast && ftab_L && !use_sweep) {
+        if (use_fast && ftab_L && (!use_sweep || use_variants)) {
             std::vector<uint64_t> cb = ftab_combos(ftab_L - 2, p.mismatches);
             uint64_t* d_cb = B.alloc<uint64_t>(cb.size());
             CK(cudaMemcpyAsync(d_cb, cb.data(), cb.size() * 8, cudaMemcpyHostToDevice, s)); CK(cudaStreamSynchronize(s));
             a.combos = d_cb; a.n_combos = (uint32_t)cb.size();
         }
+        if (use_variants) {
+            // ---- bulges as edited guides: chunks of guides whose edited forms fill one launch of the specialised kernels ----
+            const uint32_t R = p.rna_bulges, D = p.dna_bulges;
+            std::vector<uint32_t> descs, doff(kMaxQ + 2, 0), dcnt(kMaxQ + 2, 0);
+            for (uint32_t ql = prep.min_qlen; ql <= prep.max_qlen; ql++) {
+                const std::vector<uint32_t> v = bulge_variants(ql, R, D);
+                doff[ql] = (uint32_t)descs.size(); dcnt[ql] = (uint32_t)v.size(); descs.insert(descs.end(), v.begin(), v.end());
+            }
+            uint32_t* d_descs = B.alloc<uint32_t>(descs.size()); uint32_t* d_doff = B.alloc<uint32_t>(doff.size());
+            CK(cudaMemcpyAsync(d_descs, descs.data(), descs.size() * 4, cudaMemcpyHostToDevice, s));
+            CK(cudaMemcpyAsync(d_doff, doff.data(), doff.size() * 4, cudaMemcpyHostToDevice, s));
+            std::vector<uint8_t> h_dropped(n, 0);
+            if (p.threshold > 0) CK(cudaMemcpyAsync(h_dropped.data(), d_dropped, n, cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+            const uint32_t chunk_v = (uint32_t)std::min<int64_t>(std::max<int64_t>(env_int("GSX_VARIANT_CHUNK", 262144), 1), (1 << 22));
+            const uint32_t vmin_qlen = prep.min_qlen > R ? prep.min_qlen - R : 0;
+            const int warps = search_fast_grid_warps(variant_f, di.sm_count);
+            if (warps <= 0) throw std::runtime_error("unknown search kernel variant");
+            if (d_queue) { B.free_one(d_queue); d_queue = nullptr; }               // (sized by the threshold pass)
+            queue_cap = std::max<uint64_t>((uint64_t)chunk_v * 256, 1u << 20);
+            if (env_int("GSX_QUEUE_CAP", 0) > 0) queue_cap = (uint64_t)env_int("GSX_QUEUE_CAP", 0);
+            uint64_t vmatch_cap = std::max<uint64_t>((uint64_t)chunk_v * 48, 1u << 18);
+            match_cap = std::max<uint64_t>(1u << 18, std::min<uint64_t>((uint64_t)n * dcnt[prep.max_qlen] * 12, 1u << 26));
+            if (env_int("GSX_MATCH_CAP", 0) > 0) vmatch_cap = match_cap = (uint64_t)env_int("GSX_MATCH_CAP", 0);
+            spill_cap = 2048; if (env_int("GSX_SPILL_CAP", 0) > 0) spill_cap = (uint32_t)env_int("GSX_SPILL_CAP", 0);
+            uint64_t* d_vq = B.alloc<uint64_t>(chunk_v + 1); uint32_t* d_vdesc = B.alloc<uint32_t>(chunk_v + 1); uint32_t* d_vguide = B.alloc<uint32_t>(chunk_v + 1);
+            uint32_t* d_vnmatch = B.alloc<uint32_t>(chunk_v + 1);
+            uint32_t* d_voff = nullptr; size_t voff_cap = 0;
+            MatchRec* d_vmatches = B.alloc<MatchRec>(vmatch_cap);
+            d_matches = B.alloc<MatchRec>(match_cap);
+            CK(cudaMemsetAsync(d_ctrs, 0, 8 * sizeof(uint32_t), s));             // [5]: matches in the final arena
+            CK(cudaMemsetAsync(d_nmatch, 0, (size_t)(n + 1) * 4, s));
+            CK(cudaMemsetAsync(d_stats, 0, 8 * sizeof(unsigned long long), s));
+            CK(cudaEventRecord(ev[6], s)); CK(cudaEventRecord(ev[7], s));
+            std::vector<uint32_t> voff;
+            uint32_t n_final = 0;
+            for (uint32_t c0 = 0; c0 < n;) {
+                // guides c0 .. c1-1: as many as fit the chunk (at least one); guides dropped by the threshold pass have no edited forms
+                voff.assign(1, 0); uint32_t c1 = c0;
+                while (c1 < n) {
+                    const uint32_t cnt = h_dropped[c1] ? 0u : dcnt[prep.recs[job->g0 + c1].qlen];
+                    if (voff.back() + cnt > chunk_v && c1 > c0) break;
+                    if (cnt > chunk_v) throw std::runtime_error("GSX_VARIANT_CHUNK is smaller than the edited forms of one guide");
+                    voff.push_back(voff.back() + cnt); c1++;
+                }
+                const uint32_t n_g = c1 - c0, n_v = voff.back();
+                job->ctr.edited_guides += n_v;
+                if (n_v) {
+                    if (voff_cap < voff.size()) { if (d_voff) B.free_one(d_voff); voff_cap = std::max<size_t>(voff.size(), 4096); d_voff = B.alloc<uint32_t>(voff_cap); }
+                    CK(cudaMemcpyAsync(d_voff, voff.data(), voff.size() * 4, cudaMemcpyHostToDevice, s));
+                    CK(launch_variant_expand(d_guides, c0, n_g, n_v, d_voff, d_descs, d_doff, d_vq, d_vdesc, d_vguide, s)); n_launches++;
+                    const uint32_t sb = plan_sweep(n_v, vmin_qlen, p.mismatches);
+                    if (sb) use_sweep = true;
+                    for (int attempt = 0;; attempt++) {
+                        if (attempt > 12) throw std::runtime_error("search arenas keep overflowing");
+                        d_spill = B.alloc<uint32_t>((size_t)warps * spill_cap * 6);
+                        CK(cudaMemsetAsync(d_ctrs, 0, 5 * sizeof(uint32_t), s));
+                        SearchArgs m = a; m.p.M = p.mismatches; m.p.R = m.p.D = 0; m.p.counting = 0; m.p.n_tasks = 2 * n_v;
+                        m.p.match_cap = (uint32_t)vmatch_cap; m.p.spill_cap = spill_cap; m.spill = d_spill; m.matches = d_vmatches;
+                        m.skip = nullptr; m.gq = d_vq; m.guide_nmatch = d_vnmatch; m.guides = nullptr;
+                        run_fast_all_pams(m, n_v, sb, nullptr);
+                        uint32_t h[4]; CK(cudaMemcpyAsync(h, d_ctrs, sizeof h, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s));
+                        B.free_one(d_spill);
+                        if (h[2] & GSX_KERR_WATCHDOG) throw std::runtime_error("search kernel watchdog tripped");
+                        if (h[2] & (GSX_KERR_MATCH_OVERFLOW | GSX_KERR_SPILL_OVERFLOW | GSX_KERR_QUEUE_OVERFLOW)) {
+                            if (h[2] & GSX_KERR_QUEUE_OVERFLOW) grow_queue();
+                            if (h[2] & GSX_KERR_MATCH_OVERFLOW) {
+                                B.free_one(d_vmatches); vmatch_cap = std::max<uint64_t>(vmatch_cap * 2, (uint64_t)h[1] + (h[1] >> 2));
+                                if (vmatch_cap > (1ull << 31)) throw std::runtime_error("more than 2^31 matches in one chunk; lower GSX_VARIANT_CHUNK");
+                                d_vmatches = B.alloc<MatchRec>(vmatch_cap);
+                            }
+                            if (h[2] & GSX_KERR_SPILL_OVERFLOW) spill_cap *= 4;
+                            continue;
+                        }
+                        n_seeds_used += sb ? h[3] : 0;
+                        // room for every match of the chunk in the final arena, then rewrite (cannot overflow any more)
+                        if ((uint64_t)n_final + h[1] > match_cap) {
+                            const uint64_t cap2 = std::max<uint64_t>(match_cap * 2, ((uint64_t)n_final + h[1]) * 2);
+                            if (cap2 > (1ull << 31)) throw std::runtime_error("more than 2^31 matches in one batch; lower the batch size");
+                            MatchRec* bigger = B.alloc<MatchRec>(cap2);
+                            CK(cudaMemcpyAsync(bigger, d_matches, (size_t)n_final * sizeof(MatchRec), cudaMemcpyDeviceToDevice, s));
+                            CK(cudaStreamSynchronize(s));
+                            B.free_one(d_matches); d_matches = bigger; match_cap = cap2;
+                        }
+                        CK(launch_variant_rewrite(d_vmatches, h[1], d_guides, d_vdesc, d_vguide, d_matches, (uint32_t)match_cap, d_ctrs + 5, d_nmatch, d_ctrs + 2, s));
+                        n_launches++;
+                        CK(cudaMemcpyAsync(&n_final, d_ctrs + 5, 4, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s));
+                        break;
+                    }
+                }
+                c0 = c1;
+            }
+            n_matches = n_final;
+        } else {
         Node* d_gseeds = nullptr; uint32_t n_gseeds = 0;
         if (!use_fast && env_int("GSX_EXPAND_ROOTS", 1)) {
             const int gw = search_grid_warps(wide, variant, di.sm_count);
@@ -681,7 +782,7 @@ static void run_device_job(DeviceJob* job) {
             m.skip = p.threshold > 0 ? d_dropped : nullptr;
             m.gseeds = d_gseeds; m.n_gseeds = n_gseeds;
             CK(cudaEventRecord(ev[6], s));
-            if (use_fast) run_fast_all_pams(m, ev[7]); else { CK(cudaEventRecord(ev[7], s)); CK(launch_search(m, wide, variant, di.sm_count, s, nullptr)); n_launches++; }
+            if (use_fast) run_fast_all_pams(m, n, sweep_sb, ev[7]); else { CK(cudaEventRecord(ev[7], s)); CK(launch_search(m, wide, variant, di.sm_count, s, nullptr)); n_launches++; }
             uint32_t h[4]; CK(cudaMemcpyAsync(h, d_ctrs, sizeof h, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s));
             B.free_one(d_spill);
             if (h[2] & GSX_KERR_WATCHDOG) throw std::runtime_error("search kernel watchdog tripped");
@@ -696,6 +797,7 @@ static void run_device_job(DeviceJob* job) {
             n_matches = h[1]; n_seeds_used = use_sweep ? h[3] : 0;
             break;
         }
+        }
         CK(cudaEventRecord(ev[1], s));
         // ---- arrange --------------------------------------------------------------------------------------------------
         uint32_t* d_moff = B.alloc<uint32_t>(n + 1);
@@ -707,9 +809,18 @@ static void run_device_job(DeviceJob* job) {
         uint32_t* d_hoff = B.alloc<uint32_t>(n + 1);
         uint32_t* d_cbd = B.alloc<uint32_t>((size_t)n * n_dist, true, s);
         CK(launch_scan(d_nmatch, d_moff, n, s)); n_launches += 2 + (n_matches ? 1 : 0);
-        CK(launch_scatter(d_matches, n_matches, d_moff, d_cursor, d_by_guide, s));
-        CK(launch_order(d_matches, d_moff, d_by_guide, n, n_dist, d_sorted, d_sorted_off, d_nhits, d_cbd,
-                        env_int("GSX_ORDER_CTA", (uint64_t)n_matches > (uint64_t)n * 256 ? 1 : 0) != 0, s));
+        // thousands of matches per guide (bulges): global radix sort (gsx_arrange.cu); otherwise the per-guide rank sort
+        // (GSX_ORDER: 0 warp per guide, 1 CTA per guide, 2 radix sort)
+        const int order_mode = env_int("GSX_ORDER", env_int("GSX_ORDER_CTA", 0) ? 1 : ((uint64_t)n_matches > (uint64_t)n * 256 ? 2 : 0));
+        if (order_mode == 2) {
+            const size_t sb_bytes = order_sorted_scratch_bytes(n_matches);
+            void* scratch = B.alloc<unsigned char>(sb_bytes);
+            CK(launch_order_sorted(d_matches, n_matches, d_moff, n, n_dist, d_sorted, d_sorted_off, d_nhits, d_cbd, scratch, sb_bytes, s));
+            n_launches += 30;                                                     // keys, radix passes, flags, scan, offsets, counts
+        } else {
+            CK(launch_scatter(d_matches, n_matches, d_moff, d_cursor, d_by_guide, s));
+            CK(launch_order(d_matches, d_moff, d_by_guide, n, n_dist, d_sorted, d_sorted_off, d_nhits, d_cbd, order_mode == 1, s));
+        }
         {   // total hits can exceed 2^32 only for absurd inputs; the scan is 32-bit, so check with a 64-bit host sum
             CK(cudaMemcpyAsync(H.n_hits_of, d_nhits, (size_t)n * 4, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s));
             uint64_t tot = 0; for (uint32_t i = 0; i < n; i++) tot += H.n_hits_of[i];
@@ -831,7 +942,7 @@ extern "C" int gsx_enumerate(const gsx_index* ix, const gsx_guide* guides, size_
         r->part_g0.push_back(g); r->part_h0.push_back(h); g += j.out.n_guides; h += j.out.n_hits;
         r->parts.push_back(std::move(j.out));
         gsx_counters& c = r->counters;
-        c.nodes += j.ctr.nodes; c.lookups += j.ctr.lookups; c.matches += j.ctr.matches; c.hits += j.ctr.hits; c.lf_steps += j.ctr.lf_steps; c.spills += j.ctr.spills; c.launches += j.ctr.launches; c.seeds += j.ctr.seeds; c.sectors += j.ctr.sectors;
+        c.nodes += j.ctr.nodes; c.lookups += j.ctr.lookups; c.matches += j.ctr.matches; c.hits += j.ctr.hits; c.lf_steps += j.ctr.lf_steps; c.spills += j.ctr.spills; c.launches += j.ctr.launches; c.seeds += j.ctr.seeds; c.sectors += j.ctr.sectors; c.edited_guides += j.ctr.edited_guides;
         c.ms_sweep = std::max(c.ms_sweep, j.ctr.ms_sweep);
         c.ms_search = std::max(c.ms_search, j.ctr.ms_search); c.ms_arrange = std::max(c.ms_arrange, j.ctr.ms_arrange);
         c.ms_locate = std::max(c.ms_locate, j.ctr.ms_locate); c.ms_score = std::max(c.ms_score, j.ctr.ms_score);

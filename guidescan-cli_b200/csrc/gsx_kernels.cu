@@ -1040,6 +1040,68 @@ cudaError_t launch_sweep(const SweepArgs& a, int variant, int sm_count, cudaStre
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// bulges as edited guides (gsx_core.h variant_rewrite): a bulge batch is searched as a mismatch-only batch holding every
+// edited form of every guide -- which puts it on the sweep / jump-table kernels above instead of the general tree walk --
+// and its matches are rewritten into the guides' own (wide-key) matches afterwards.
+// ---------------------------------------------------------------------------------------------------------
+// one thread per edited guide v of the chunk: which guide, which op list; the packed edited guide for the search kernels
+//   voff[0..n_g]: first edited guide of each guide of the chunk;  doff[qlen]: start of the op lists for guides of that length
+__global__ void variant_expand_kernel(const GuideRec* __restrict__ guides, uint32_t g_first, uint32_t n_g, const uint32_t* __restrict__ voff,
+                                      const uint32_t* __restrict__ descs, const uint32_t* __restrict__ doff,
+                                      uint64_t* __restrict__ vq, uint32_t* __restrict__ vdesc, uint32_t* __restrict__ vguide) {
+    const uint32_t n_v = voff[n_g];
+    for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < n_v; v += gridDim.x * blockDim.x) {
+        uint32_t lo = 0, hi = n_g;                                   // last guide with voff <= v
+        while (hi - lo > 1u) { const uint32_t mid = (lo + hi) >> 1; if (voff[mid] <= v) lo = mid; else hi = mid; }
+        const GuideRec& g = guides[g_first + lo];
+        const uint32_t desc = descs[doff[g.qlen] + (v - voff[lo])];
+        vq[v] = variant_pack(g.q, g.qlen, desc); vdesc[v] = desc; vguide[v] = g_first + lo;
+    }
+}
+cudaError_t launch_variant_expand(const GuideRec* guides, uint32_t g_first, uint32_t n_g, uint32_t n_v, const uint32_t* voff, const uint32_t* descs,
+                                  const uint32_t* doff, uint64_t* vq, uint32_t* vdesc, uint32_t* vguide, cudaStream_t s) {
+    if (!n_v) return cudaSuccess;
+    long b = ((long)n_v + 255) / 256; if (b > 148 * 8) b = 148 * 8;
+    variant_expand_kernel<<<(int)b, 256, 0, s>>>(guides, g_first, n_g, voff, descs, doff, vq, vdesc, vguide);
+    return cudaGetLastError();
+}
+
+// matches of the edited guides -> matches of the guides (appended to `out`); alignments that substituted an inserted
+// character are dropped
+__global__ void variant_rewrite_kernel(const MatchRec* __restrict__ vm, uint32_t n_vm, const GuideRec* __restrict__ guides,
+                                       const uint32_t* __restrict__ vdesc, const uint32_t* __restrict__ vguide,
+                                       MatchRec* __restrict__ out, uint32_t out_cap, uint32_t* out_count, uint32_t* guide_nmatch, uint32_t* error_flag) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t n_round = (n_vm + 31u) & ~31u;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+        MatchRec o; bool ok = false; uint32_t g = 0;
+        if (i < n_vm) {
+            const MatchRec m = vm[i];
+            const uint32_t v = m.task >> 1;
+            g = vguide[v];
+            ok = variant_rewrite(m, guides[g], vdesc[v], (g << 1) | (m.task & 1u), o);
+        }
+        const uint32_t mask = __ballot_sync(0xffffffffu, ok);
+        if (!mask) continue;
+        uint32_t base = 0; const int leader = __ffs(mask) - 1;
+        if ((int)lane == leader) base = atomicAdd(out_count, (uint32_t)__popc(mask));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (ok) {
+            const uint32_t slot = base + __popc(mask & ((1u << lane) - 1u));
+            if (slot < out_cap) { out[slot] = o; atomicAdd(guide_nmatch + g, 1u); }
+            else atomicOr(error_flag, GSX_KERR_MATCH_OVERFLOW);
+        }
+    }
+}
+cudaError_t launch_variant_rewrite(const MatchRec* vm, uint32_t n_vm, const GuideRec* guides, const uint32_t* vdesc, const uint32_t* vguide,
+                                   MatchRec* out, uint32_t out_cap, uint32_t* out_count, uint32_t* guide_nmatch, uint32_t* error_flag, cudaStream_t s) {
+    if (!n_vm) return cudaSuccess;
+    long b = ((long)n_vm + 255) / 256; if (b > 148 * 8) b = 148 * 8;
+    variant_rewrite_kernel<<<(int)b, 256, 0, s>>>(vm, n_vm, guides, vdesc, vguide, out, out_cap, out_count, guide_nmatch, error_flag);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // arrange: group by guide, order, de-duplicate, expand
 // ---------------------------------------------------------------------------------------------------------
 // exclusive scan of in[0..n) into out[0..n], out[n] = total; one block

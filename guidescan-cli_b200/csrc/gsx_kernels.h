@@ -102,6 +102,16 @@ int search_fast_grid_warps(int variant, int sm_count);
 cudaError_t launch_search_fast(const SearchArgs& a, int variant, int sm_count, cudaStream_t s);
 cudaError_t launch_sweep_guides(const SweepArgs& a, cudaStream_t s);      // per-guide filter masks (before launch_sweep)
 cudaError_t launch_sweep(const SweepArgs& a, int variant, int sm_count, cudaStream_t s);
+// bulges as edited guides (gsx_core.h variant_rewrite)
+cudaError_t launch_variant_expand(const GuideRec* guides, uint32_t g_first, uint32_t n_g, uint32_t n_v, const uint32_t* voff, const uint32_t* descs,
+                                  const uint32_t* doff, uint64_t* vq, uint32_t* vdesc, uint32_t* vguide, cudaStream_t s);
+cudaError_t launch_variant_rewrite(const MatchRec* vm, uint32_t n_vm, const GuideRec* guides, const uint32_t* vdesc, const uint32_t* vguide,
+                                   MatchRec* out, uint32_t out_cap, uint32_t* out_count, uint32_t* guide_nmatch, uint32_t* error_flag, cudaStream_t s);
+// ordering of batches with thousands of matches per guide (gsx_arrange.cu): three stable radix-sort passes instead of the
+// per-guide rank sort; same outputs as launch_order.  scratch: order_sorted_scratch_bytes(n_matches) bytes
+size_t order_sorted_scratch_bytes(uint32_t n_matches);
+cudaError_t launch_order_sorted(const MatchRec* m, uint32_t n_matches, const uint32_t* moff, uint32_t n_guides, uint32_t n_dist,
+                                uint32_t* sorted, uint32_t* sorted_off, uint32_t* nhits, uint32_t* cbd, void* scratch, size_t scratch_bytes, cudaStream_t s);
 cudaError_t launch_scan(const uint32_t* in, uint32_t* out, uint32_t n, cudaStream_t s);
 cudaError_t launch_scatter(const MatchRec* m, uint32_t n, const uint32_t* moff, uint32_t* cursor, uint32_t* by_guide, cudaStream_t s);
 cudaError_t launch_order(const MatchRec* m, const uint32_t* moff, const uint32_t* by_guide, uint32_t n_guides, uint32_t n_dist,

@@ -46,7 +46,8 @@ class Counters(C.Structure):
                 ("lf_steps", C.c_uint64), ("spills", C.c_uint64), ("ms_search", C.c_double), ("ms_arrange", C.c_double),
                 ("ms_locate", C.c_double), ("ms_score", C.c_double), ("ms_total_device", C.c_double),
                 ("ms_h2d", C.c_double), ("ms_d2h", C.c_double), ("launches", C.c_uint64),
-                ("ms_sweep", C.c_double), ("seeds", C.c_uint64), ("ms_prepare", C.c_double), ("ms_wall", C.c_double), ("sectors", C.c_uint64)]
+                ("ms_sweep", C.c_double), ("seeds", C.c_uint64), ("ms_prepare", C.c_double), ("ms_wall", C.c_double), ("sectors", C.c_uint64),
+                ("edited_guides", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -104,6 +104,7 @@ typedef struct {
     double   ms_prepare;       /* host: guide validation / packing before the first device call */
     double   ms_wall;          /* host: wall time of the whole gsx_enumerate call */
     uint64_t sectors;          /* 32-byte index sectors the search kernels actually requested (= lookups when the front end is off) */
+    uint64_t edited_guides;    /* bulge batches searched through edited guides (gsx_core.h variant_rewrite): how many of them; else 0 */
 } gsx_counters;
 
 /* ---- index ------------------------------------------------------------------------------------------- */

@@ -74,6 +74,79 @@ def test_cta_per_guide_match_ordering(gsx, gpu_index, golden_dir, tmp_path, monk
     assert open(out, "rb").read() == golden_output(case, variant)
 
 
+def _ngg_subset(tmp_path):
+    """the g200k golden guides a bulge batch may hold to run through edited guides: one PAM column value, ACGT only"""
+    from test_host_core import _golden_subset
+    return _golden_subset("g200k", str(tmp_path), lambda f: f[2] == "NGG" and set(f[1]) <= set("ACGT"))
+
+
+BULGE_GOLDEN = [v for c, v in golden_cases() if c == "g200k" and ("_r" in v or "_d" in v)]
+
+
+@pytest.mark.parametrize("variant", BULGE_GOLDEN)
+@pytest.mark.parametrize("mode", ["default", "sweep", "chunks"])
+def test_bulges_through_edited_guides_golden(gsx, gpu_index, tmp_path, monkeypatch, variant, mode):
+    """Bulge batches on the specialised kernels (gsx_api.cpp use_variants: variant_expand -> [sweep ->] search_fast ->
+    variant_rewrite -> radix-sort ordering) against the reference's golden text; guides of 19-21 nt, alternative PAMs,
+    two bulges of each kind; with the slice-major front end forced on, and with chunks of a few guides."""
+    kw = golden_manifest()["cases"]["g200k"]["variants"][variant]["opts"]
+    big = kw.get("rna_bulges", 0) + kw.get("dna_bulges", 0) > 2
+    if big and mode != "default":
+        pytest.skip("the 600k-variants-per-guide case runs once")
+    monkeypatch.setenv("GSX_VARIANTS_MAX", "100000000")
+    if mode == "sweep":
+        monkeypatch.setenv("GSX_SWEEP_MIN", "1")
+    if mode == "chunks":
+        monkeypatch.setenv("GSX_VARIANT_CHUNK", "7000"); monkeypatch.setenv("GSX_MATCH_CAP", "300"); monkeypatch.setenv("GSX_SPILL_CAP", "64")
+        monkeypatch.setenv("GSX_QUEUE_CAP", "512"); monkeypatch.setenv("GSX_SWEEP_MIN", "4000")
+    gcsv, slice_of = _ngg_subset(tmp_path)
+    out = os.path.join(tmp_path, "g.out")
+    _, ctr = gpu_index("g200k").enumerate_file(gcsv, out, _params(gsx, kw), fmt=kw.get("fmt", "csv"), mode=kw.get("mode", "complete"))
+    assert ctr["edited_guides"] > 0
+    assert open(out).read() == slice_of(golden_output("g200k", variant).decode(), kw.get("fmt") == "sam")
+    # the general kernel on the same batch
+    monkeypatch.setenv("GSX_VARIANTS", "0")
+    if not big:
+        _, ctr = gpu_index("g200k").enumerate_file(gcsv, out, _params(gsx, kw), fmt=kw.get("fmt", "csv"), mode=kw.get("mode", "complete"))
+        assert ctr["edited_guides"] == 0
+        assert open(out).read() == slice_of(golden_output("g200k", variant).decode(), kw.get("fmt") == "sam")
+
+
+@pytest.mark.parametrize("opts", [dict(mismatches=2, rna_bulges=1, dna_bulges=1), dict(mismatches=3, rna_bulges=1), dict(mismatches=1, dna_bulges=2),
+                                  dict(mismatches=2, rna_bulges=2, threshold=1), dict(mismatches=2, rna_bulges=1, dna_bulges=1, alt_pams=("NAG",), max_off_targets=5)])
+def test_bulges_through_edited_guides_vs_oracle(gsx, tmp_path, opts):
+    """seeded 2 Mb genome, 60 guides with planted copies, CSV and SAM, against the CPU oracle"""
+    import oracle as O
+    import synth
+    d = str(tmp_path)
+    synth.make_dataset(d, 2_000_000, 5, 60, seed=77, name="b")
+    fa, gcsv = os.path.join(d, "b.fa"), os.path.join(d, "b.guides.csv")
+    if not O.have_ref():
+        pytest.skip("needs oracle/_ref/guidescan to build the index files")
+    O.ref_index(fa, os.path.join(d, "b"), cwd=d)
+    ix = gsx.Index.open(os.path.join(d, "b"), devices=[0])
+    oix = O.Index(fa)
+    for fmt in ("csv", "sam"):
+        out = os.path.join(d, "g." + fmt)
+        _, ctr = ix.enumerate_file(gcsv, out, _params(gsx, opts), fmt=fmt)
+        assert ctr["edited_guides"] > 0
+        oix.enumerate_file(O.make_opts(fmt=fmt, **opts), gcsv, os.path.join(d, "o." + fmt), nthreads=8)
+        assert open(out, "rb").read() == open(os.path.join(d, "o." + fmt), "rb").read()
+    ix.close()
+
+
+@pytest.mark.parametrize("case,variant", [("g200k", "m0_r2_d2_csv"), ("g150kN", "m1_r1_d1_csv"), ("g200k", "m3_csv"), ("g150kN", "m3_altNAG_sam"),
+                                          ("g200k", "m4_max2_csv"), ("g150kN", "m1_r1_d1_sam_succinct"), ("g200k", "m3_thr1_csv")])
+def test_radix_sort_match_ordering(gsx, gpu_index, golden_dir, tmp_path, monkeypatch, case, variant):
+    """launch_order_sorted (gsx_arrange.cu; chosen by itself above 256 matches per guide), forced on golden cases with many
+    and with few matches per guide, dropped guides, duplicate strings (alternative PAMs)"""
+    monkeypatch.setenv("GSX_ORDER", "2")
+    kw = golden_manifest()["cases"][case]["variants"][variant]["opts"]
+    out = os.path.join(tmp_path, "g.out")
+    gpu_index(case).enumerate_file(golden_dir[case][1], out, _params(gsx, kw), fmt=kw.get("fmt", "csv"), mode=kw.get("mode", "complete"))
+    assert open(out, "rb").read() == golden_output(case, variant)
+
+
 @pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
 def test_every_search_kernel_variant(gsx, gpu_index, golden_dir, tmp_path, variant, monkeypatch):
     monkeypatch.setenv("GSX_SEARCH_VARIANT", str(variant))
