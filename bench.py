@@ -407,7 +407,7 @@ def apply_variant(args):
             os.environ.update({"GSX_FORCE_GENERAL": "0", "GSX_FAST_VARIANT": args.variant[1:]})
 
 
-def main():
+def parse_args(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -429,7 +429,11 @@ def main():
     ap.add_argument("--sweep-variants", default="")
     ap.add_argument("--variant", default=None, help="f<k> specialised kernel variant k, g<k> general kernel variant k")
     ap.add_argument("--workdir", default=os.environ.get("GSX_BENCH_DIR", "/tmp/gsx_bench"))
-    args = ap.parse_args()
+    return ap.parse_args(argv)
+
+
+def main():
+    args = parse_args()
     apply_variant(args)
     if args.impl == "reference":
         run_reference(args)

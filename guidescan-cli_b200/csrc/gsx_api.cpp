@@ -696,23 +696,27 @@ static void run_device_job(DeviceJob* job) {
             CK(cudaMemsetAsync(d_nmatch, 0, (size_t)(n + 1) * 4, s));
             CK(cudaMemsetAsync(d_stats, 0, 8 * sizeof(unsigned long long), s));
             CK(cudaEventRecord(ev[6], s)); CK(cudaEventRecord(ev[7], s));
-            std::vector<uint32_t> voff;
+            std::vector<uint32_t> seg;                                             // {first edited guide, guide, first op list} per segment
             uint32_t n_final = 0;
-            for (uint32_t c0 = 0; c0 < n;) {
-                // guides c0 .. c1-1: as many as fit the chunk (at least one); guides dropped by the threshold pass have no edited forms
-                voff.assign(1, 0); uint32_t c1 = c0;
-                while (c1 < n) {
-                    const uint32_t cnt = h_dropped[c1] ? 0u : dcnt[prep.recs[job->g0 + c1].qlen];
-                    if (voff.back() + cnt > chunk_v && c1 > c0) break;
-                    if (cnt > chunk_v) throw std::runtime_error("GSX_VARIANT_CHUNK is smaller than the edited forms of one guide");
-                    voff.push_back(voff.back() + cnt); c1++;
+            uint32_t c0 = 0, f0 = 0;                                               // next guide, and how many of its op lists are done
+            while (c0 < n) {
+                // as many guides as fit the chunk; a guide with more edited forms than a chunk holds is cut into runs of op lists;
+                // guides dropped by the threshold pass have no edited forms
+                seg.clear(); uint32_t n_v = 0;
+                while (c0 < n && n_v < chunk_v) {
+                    const uint32_t cnt = h_dropped[c0] ? 0u : dcnt[prep.recs[job->g0 + c0].qlen];
+                    const uint32_t take = std::min<uint32_t>(cnt - f0, chunk_v - n_v);
+                    if (take) { seg.push_back(n_v); seg.push_back(c0); seg.push_back(f0); n_v += take; }
+                    f0 += take;
+                    if (f0 == cnt) { c0++; f0 = 0; } else break;                   // chunk full in the middle of a guide
                 }
-                const uint32_t n_g = c1 - c0, n_v = voff.back();
+                const uint32_t n_seg = (uint32_t)(seg.size() / 3);
+                seg.push_back(n_v);
                 job->ctr.edited_guides += n_v;
                 if (n_v) {
-                    if (voff_cap < voff.size()) { if (d_voff) B.free_one(d_voff); voff_cap = std::max<size_t>(voff.size(), 4096); d_voff = B.alloc<uint32_t>(voff_cap); }
-                    CK(cudaMemcpyAsync(d_voff, voff.data(), voff.size() * 4, cudaMemcpyHostToDevice, s));
-                    CK(launch_variant_expand(d_guides, c0, n_g, n_v, d_voff, d_descs, d_doff, d_vq, d_vdesc, d_vguide, s)); n_launches++;
+                    if (voff_cap < seg.size()) { if (d_voff) B.free_one(d_voff); voff_cap = std::max<size_t>(seg.size(), 4096); d_voff = B.alloc<uint32_t>(voff_cap); }
+                    CK(cudaMemcpyAsync(d_voff, seg.data(), seg.size() * 4, cudaMemcpyHostToDevice, s));
+                    CK(launch_variant_expand(d_guides, n_seg, n_v, d_voff, d_descs, d_doff, d_vq, d_vdesc, d_vguide, s)); n_launches++;
                     const uint32_t sb = plan_sweep(n_v, vmin_qlen, p.mismatches);
                     if (sb) use_sweep = true;
                     for (int attempt = 0;; attempt++) {
@@ -752,7 +756,6 @@ static void run_device_job(DeviceJob* job) {
                         break;
                     }
                 }
-                c0 = c1;
             }
             n_matches = n_final;
         } else {

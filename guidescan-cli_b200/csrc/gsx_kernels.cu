@@ -982,6 +982,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) sweep_kernel(SweepArgs a) {
         // (1) guides whose only pattern in this slice is the unsubstituted one (budget 0), and the unsubstituted pattern of
         //     the guides with budget 1: one pattern per lane, each lane with its own guide's masks
         {
+            // (the previous unit may have left up to 63 parked nodes and this step can park 32 more: make room first -- batches
+            // of near-identical guides, e.g. the edited forms of one guide, park in every lane at once)
+            while (cb.count >= 32u) cont_process<NB>(a, cb, lane, st);
             bool emit = false, park = false; uint32_t idx = 0, codes = 0, codes2 = 0x77u;
             st.sectors += __popc(__ballot_sync(FULL, B == 0 || B == 1));
             if (B == 0 || B == 1) {
@@ -1045,24 +1048,27 @@ cudaError_t launch_sweep(const SweepArgs& a, int variant, int sm_count, cudaStre
 // and its matches are rewritten into the guides' own (wide-key) matches afterwards.
 // ---------------------------------------------------------------------------------------------------------
 // one thread per edited guide v of the chunk: which guide, which op list; the packed edited guide for the search kernels
-//   voff[0..n_g]: first edited guide of each guide of the chunk;  doff[qlen]: start of the op lists for guides of that length
-__global__ void variant_expand_kernel(const GuideRec* __restrict__ guides, uint32_t g_first, uint32_t n_g, const uint32_t* __restrict__ voff,
+//   seg[3 * i ..]: {first edited guide of segment i within the chunk, its guide, index of its first op list among the guide's};
+//   a segment = a run of op lists of one guide (a guide whose edited forms exceed a chunk spans several);
+//   seg[3 * n_seg] = number of edited guides of the chunk;  doff[qlen]: start of the op lists for guides of that length
+__global__ void variant_expand_kernel(const GuideRec* __restrict__ guides, uint32_t n_seg, const uint32_t* __restrict__ seg,
                                       const uint32_t* __restrict__ descs, const uint32_t* __restrict__ doff,
                                       uint64_t* __restrict__ vq, uint32_t* __restrict__ vdesc, uint32_t* __restrict__ vguide) {
-    const uint32_t n_v = voff[n_g];
+    const uint32_t n_v = seg[3u * n_seg];
     for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < n_v; v += gridDim.x * blockDim.x) {
-        uint32_t lo = 0, hi = n_g;                                   // last guide with voff <= v
-        while (hi - lo > 1u) { const uint32_t mid = (lo + hi) >> 1; if (voff[mid] <= v) lo = mid; else hi = mid; }
-        const GuideRec& g = guides[g_first + lo];
-        const uint32_t desc = descs[doff[g.qlen] + (v - voff[lo])];
-        vq[v] = variant_pack(g.q, g.qlen, desc); vdesc[v] = desc; vguide[v] = g_first + lo;
+        uint32_t lo = 0, hi = n_seg;                                 // last segment starting at or before v
+        while (hi - lo > 1u) { const uint32_t mid = (lo + hi) >> 1; if (seg[3u * mid] <= v) lo = mid; else hi = mid; }
+        const uint32_t gi = seg[3u * lo + 1u];
+        const GuideRec& g = guides[gi];
+        const uint32_t desc = descs[doff[g.qlen] + seg[3u * lo + 2u] + (v - seg[3u * lo])];
+        vq[v] = variant_pack(g.q, g.qlen, desc); vdesc[v] = desc; vguide[v] = gi;
     }
 }
-cudaError_t launch_variant_expand(const GuideRec* guides, uint32_t g_first, uint32_t n_g, uint32_t n_v, const uint32_t* voff, const uint32_t* descs,
+cudaError_t launch_variant_expand(const GuideRec* guides, uint32_t n_seg, uint32_t n_v, const uint32_t* seg, const uint32_t* descs,
                                   const uint32_t* doff, uint64_t* vq, uint32_t* vdesc, uint32_t* vguide, cudaStream_t s) {
     if (!n_v) return cudaSuccess;
     long b = ((long)n_v + 255) / 256; if (b > 148 * 8) b = 148 * 8;
-    variant_expand_kernel<<<(int)b, 256, 0, s>>>(guides, g_first, n_g, voff, descs, doff, vq, vdesc, vguide);
+    variant_expand_kernel<<<(int)b, 256, 0, s>>>(guides, n_seg, seg, descs, doff, vq, vdesc, vguide);
     return cudaGetLastError();
 }
 

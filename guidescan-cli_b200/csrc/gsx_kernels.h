@@ -103,7 +103,7 @@ cudaError_t launch_search_fast(const SearchArgs& a, int variant, int sm_count, c
 cudaError_t launch_sweep_guides(const SweepArgs& a, cudaStream_t s);      // per-guide filter masks (before launch_sweep)
 cudaError_t launch_sweep(const SweepArgs& a, int variant, int sm_count, cudaStream_t s);
 // bulges as edited guides (gsx_core.h variant_rewrite)
-cudaError_t launch_variant_expand(const GuideRec* guides, uint32_t g_first, uint32_t n_g, uint32_t n_v, const uint32_t* voff, const uint32_t* descs,
+cudaError_t launch_variant_expand(const GuideRec* guides, uint32_t n_seg, uint32_t n_v, const uint32_t* seg, const uint32_t* descs,
                                   const uint32_t* doff, uint64_t* vq, uint32_t* vdesc, uint32_t* vguide, cudaStream_t s);
 cudaError_t launch_variant_rewrite(const MatchRec* vm, uint32_t n_vm, const GuideRec* guides, const uint32_t* vdesc, const uint32_t* vguide,
                                    MatchRec* out, uint32_t out_cap, uint32_t* out_count, uint32_t* guide_nmatch, uint32_t* error_flag, cudaStream_t s);
