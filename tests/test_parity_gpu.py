@@ -119,7 +119,8 @@ def test_bulges_through_edited_guides_vs_oracle(gsx, tmp_path, opts):
     import oracle as O
     import synth
     d = str(tmp_path)
-    synth.make_dataset(d, 2_000_000, 5, 60, seed=77, name="b")
+    # (threshold case: copies at distance 1 would drop every guide, so plant from distance 2 on and a few guides survive)
+    synth.make_dataset(d, 2_000_000, 5, 60, seed=77, name="b", plant_dists=(2, 3, 4) if opts.get("threshold") else (1, 2, 3, 4))
     fa, gcsv = os.path.join(d, "b.fa"), os.path.join(d, "b.guides.csv")
     if not O.have_ref():
         pytest.skip("needs oracle/_ref/guidescan to build the index files")
