@@ -519,13 +519,32 @@ static void run_device_job(DeviceJob* job) {
         H.specificity = H.alloc<float>(n); H.perfect = H.alloc<uint8_t>(n); H.cbd = H.alloc<uint32_t>((size_t)n * n_dist);
         if (n == 0) { H.hoff[0] = 0; cudaStreamDestroy(s); return; }
 
-        auto t_h2d0 = std::chrono::steady_clock::now();
+        // fast path (search_fast_kernel) when the batch and the index allow it; GSX_FORCE_GENERAL=1 keeps the general kernel
+        const bool use_fast = (prep.fast_ok || prep.variant_ok) && !env_int("GSX_FORCE_GENERAL", 0) && n < (1u << 23) &&
+                              di.st[0].d.n_exc == 1 && di.st[1].d.n_exc == 1 && di.st[0].d.n_nrows == 0 && di.st[1].d.n_nrows == 0;
+        // bulges: the search runs over the guides' edited forms (gsx_core.h variant_rewrite), in chunks, on the same kernels
+        const bool use_variants = use_fast && prep.variant_ok;
+        // The specialised kernels read the packed guides (8 bytes each) only; the 80-byte records are needed from the locate stage
+        // on.  Their upload (pageable host memory: the call blocks the host) is issued on a second stream AFTER the first search
+        // launch, so that it runs under the search instead of in front of it.
+        const bool late_guides = use_fast && !use_variants && env_int("GSX_LATE_GUIDES", 1) != 0;
+        cudaStream_t s2; CK(cudaStreamCreate(&s2));
+        cudaEvent_t ev_guides; CK(cudaEventCreateWithFlags(&ev_guides, cudaEventDisableTiming));
         GuideRec* d_guides = B.alloc<GuideRec>(n);
         PamSet* d_pamsets = B.alloc<PamSet>(kMaxPamSets);
-        CK(cudaMemcpyAsync(d_guides, prep.recs.data() + job->g0, (size_t)n * sizeof(GuideRec), cudaMemcpyHostToDevice, s));
+        bool guides_up = false;
+        auto upload_guides = [&](cudaStream_t st) {
+            if (guides_up) return;
+            const auto t0 = std::chrono::steady_clock::now();
+            CK(cudaMemcpyAsync(d_guides, prep.recs.data() + job->g0, (size_t)n * sizeof(GuideRec), cudaMemcpyHostToDevice, st));
+            CK(cudaEventRecord(ev_guides, st));
+            job->ctr.ms_h2d += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            guides_up = true;
+        };
+        auto t_h2d0 = std::chrono::steady_clock::now();
         CK(cudaMemcpyAsync(d_pamsets, prep.pamsets, sizeof(prep.pamsets), cudaMemcpyHostToDevice, s));
-        CK(cudaStreamSynchronize(s));
-        job->ctr.ms_h2d = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_h2d0).count();
+        job->ctr.ms_h2d = 0;
+        if (!late_guides) upload_guides(s);
 
         uint32_t* d_nmatch = B.alloc<uint32_t>(n + 1, true, s);
         uint8_t* d_dropped = B.alloc<uint8_t>(n, true, s);
@@ -538,15 +557,11 @@ static void run_device_job(DeviceJob* job) {
         a.task_counter = d_ctrs + 0; a.match_count = d_ctrs + 1; a.error_flag = d_ctrs + 2; a.stats = d_stats;
         a.guide_nmatch = d_nmatch; a.max_iters = 1u << 28; a.max_pams = prep.max_pams;
         a.p.n_tasks = 2 * n;
-        // fast path (search_fast_kernel) when the batch and the index allow it; GSX_FORCE_GENERAL=1 keeps the general kernel
-        const bool use_fast = (prep.fast_ok || prep.variant_ok) && !env_int("GSX_FORCE_GENERAL", 0) && n < (1u << 23) &&
-                              di.st[0].d.n_exc == 1 && di.st[1].d.n_exc == 1 && di.st[0].d.n_nrows == 0 && di.st[1].d.n_nrows == 0;
-        // bulges: the search runs over the guides' edited forms (gsx_core.h variant_rewrite), in chunks, on the same kernels
-        const bool use_variants = use_fast && prep.variant_ok;
         const int variant_f = env_int("GSX_FAST_VARIANT", di.st[0].d.lines ? 1 : 0);
         if (use_fast) {
             uint64_t* d_gq = B.alloc<uint64_t>(n);
             CK(cudaMemcpyAsync(d_gq, prep.gq.data() + job->g0, (size_t)n * 8, cudaMemcpyHostToDevice, s));
+            if (late_guides) job->ctr.ms_h2d += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_h2d0).count();
             a.gq = d_gq; a.pampack = prep.pampack; a.plen = prep.plen;
             // L2 residency hint: intervals wide enough that all such blocks of both strands fit the L2 budget
             // (a level-d interval end costs one 128-byte line; lines touched down to level D ~ 2.7 * 4^D per strand)
@@ -637,6 +652,7 @@ static void run_device_job(DeviceJob* job) {
                 }
                 c.guide_count = d_gcount; c.spill = d_spill; c.skip = nullptr; c.matches = nullptr;
                 if (use_fast) run_fast_all_pams(c, n, sb_thr, nullptr); else { CK(launch_search(c, false, variant_n, di.sm_count, s, nullptr)); n_launches++; }
+                upload_guides(s2);
                 uint32_t h[3]; CK(cudaMemcpyAsync(h, d_ctrs, sizeof h, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s));
                 B.free_one(d_spill);
                 if (h[2] & GSX_KERR_WATCHDOG) throw std::runtime_error("search kernel watchdog tripped");
@@ -786,6 +802,7 @@ static void run_device_job(DeviceJob* job) {
             m.gseeds = d_gseeds; m.n_gseeds = n_gseeds;
             CK(cudaEventRecord(ev[6], s));
             if (use_fast) run_fast_all_pams(m, n, sweep_sb, ev[7]); else { CK(cudaEventRecord(ev[7], s)); CK(launch_search(m, wide, variant, di.sm_count, s, nullptr)); n_launches++; }
+            upload_guides(s2);
             uint32_t h[4]; CK(cudaMemcpyAsync(h, d_ctrs, sizeof h, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s));
             B.free_one(d_spill);
             if (h[2] & GSX_KERR_WATCHDOG) throw std::runtime_error("search kernel watchdog tripped");
@@ -802,6 +819,10 @@ static void run_device_job(DeviceJob* job) {
         }
         }
         CK(cudaEventRecord(ev[1], s));
+        // the match arena is final (the host has synchronised on the search): its copy to the host runs on the second stream, under
+        // the arrange / locate / score kernels
+        H.matches = H.alloc<MatchRec>(n_matches); H.n_matches = n_matches;
+        if (n_matches) CK(cudaMemcpyAsync(H.matches, d_matches, (size_t)n_matches * sizeof(MatchRec), cudaMemcpyDeviceToHost, s2));
         // ---- arrange --------------------------------------------------------------------------------------------------
         uint32_t* d_moff = B.alloc<uint32_t>(n + 1);
         uint32_t* d_cursor = B.alloc<uint32_t>(n, true, s);
@@ -837,6 +858,7 @@ static void run_device_job(DeviceJob* job) {
         CK(launch_expand(d_matches, d_moff, d_sorted, d_sorted_off, d_hoff, n, n_matches, d_hit_match, d_hit_row, d_hit_guide, s));
         CK(cudaEventRecord(ev[2], s));
         // ---- locate + coordinates + CFD ------------------------------------------------------------------------------
+        CK(cudaStreamWaitEvent(s, ev_guides, 0));                                     // the guide records (uploaded under the search)
         LocateArgs L{};
         L.st[0] = di.st[0].d; L.st[1] = di.st[1].d; L.matches = d_matches; L.guides = d_guides; L.pamsets = d_pamsets; L.chroms = di.chroms;
         L.hit_match = d_hit_match; L.hit_row = d_hit_row; L.n_hits = nh; L.n_chr = (uint32_t)job->ix->chroms.size(); L.wide = wide;
@@ -857,17 +879,16 @@ static void run_device_job(DeviceJob* job) {
         H.abs_pos = H.alloc<int64_t>(nh); H.sa_row = H.alloc<uint32_t>(nh); H.chr = H.alloc<int32_t>(nh); H.pos1 = H.alloc<uint32_t>(nh);
         H.strand = H.alloc<uint8_t>(nh); H.distance = H.alloc<uint8_t>(nh); H.rna = H.alloc<uint8_t>(nh); H.dna = H.alloc<uint8_t>(nh);
         H.index_id = H.alloc<uint8_t>(nh); H.cfd = H.alloc<float>(nh); H.counted = H.alloc<uint8_t>(nh); H.hit_match = H.alloc<uint32_t>(nh);
-        H.matches = H.alloc<MatchRec>(n_matches); H.n_matches = n_matches;
         auto d2h = [&](void* dst, const void* src, size_t bytes) { if (bytes) CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s)); };
         d2h(H.dropped, d_dropped, n); d2h(H.hoff, d_hoff, (size_t)(n + 1) * 4); d2h(H.specificity, S.specificity, (size_t)n * 4);
         d2h(H.perfect, S.perfect, n); d2h(H.cbd, d_cbd, (size_t)n * n_dist * 4);
         d2h(H.abs_pos, L.abs_pos, (size_t)nh * 8); d2h(H.sa_row, d_hit_row, (size_t)nh * 4); d2h(H.chr, L.chr, (size_t)nh * 4);
         d2h(H.pos1, L.pos1, (size_t)nh * 4); d2h(H.strand, L.strand, nh); d2h(H.distance, L.distance, nh); d2h(H.rna, L.rna, nh);
         d2h(H.dna, L.dna, nh); d2h(H.index_id, L.index_id, nh); d2h(H.cfd, L.cfd, (size_t)nh * 4); d2h(H.counted, S.counted, nh);
-        d2h(H.hit_match, d_hit_match, (size_t)nh * 4); d2h(H.matches, d_matches, (size_t)n_matches * sizeof(MatchRec));
+        d2h(H.hit_match, d_hit_match, (size_t)nh * 4);
         unsigned long long st[8]; d2h(st, d_stats, sizeof st);
         CK(cudaEventRecord(ev[5], s));
-        CK(cudaStreamSynchronize(s));
+        CK(cudaStreamSynchronize(s)); CK(cudaStreamSynchronize(s2));
         float ms;
         CK(cudaEventElapsedTime(&ms, ev[0], ev[1])); job->ctr.ms_search = ms;
         CK(cudaEventElapsedTime(&ms, ev[1], ev[2])); job->ctr.ms_arrange = ms;
@@ -880,7 +901,8 @@ static void run_device_job(DeviceJob* job) {
         job->ctr.nodes = st[0]; job->ctr.lookups = st[1]; job->ctr.spills = st[2]; job->ctr.lf_steps = st[3];
         job->ctr.matches = n_matches; job->ctr.hits = nh; job->ctr.launches = n_launches;
         for (auto& e : ev) cudaEventDestroy(e);
-        cudaStreamDestroy(s);
+        cudaEventDestroy(ev_guides);
+        cudaStreamDestroy(s); cudaStreamDestroy(s2);
     } catch (const CudaError& e) { job->status = GSX_ERR_CUDA; job->err = e.what(); }
     catch (const std::bad_alloc&) { job->status = GSX_ERR_NOMEM; job->err = "out of host memory"; }
     catch (const std::exception& e) { job->status = GSX_ERR_INTERNAL; job->err = e.what(); }
