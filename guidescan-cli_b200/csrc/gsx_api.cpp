@@ -395,7 +395,7 @@ int gsx_prepare_guides(const gsx_guide* guides, size_t n, const gsx_params* p, g
     // pass 2 (parallel over chunks of guides): symbol packing in consumption order (process.hpp:63, index.hpp:214)
     out.gq.resize(n);
     struct Chunk { size_t max_total = 0; uint32_t min_qlen = 255, max_qlen = 0; bool bad_len = false, fast = true; };
-    const size_t n_thr = std::max<size_t>(1, std::min<size_t>({(size_t)8, n / 16384, (size_t)std::max(1u, std::thread::hardware_concurrency())}));
+    const size_t n_thr = std::max<size_t>(1, std::min<size_t>({(size_t)16, n / 8192, (size_t)std::max(1u, std::thread::hardware_concurrency())}));
     std::vector<Chunk> chunks(n_thr);
     auto work = [&](size_t t) {
         Chunk c;                                                               // (local: the chunk array shares cache lines)
