@@ -819,10 +819,7 @@ static void run_device_job(DeviceJob* job) {
         }
         }
         CK(cudaEventRecord(ev[1], s));
-        // the match arena is final (the host has synchronised on the search): its copy to the host runs on the second stream, under
-        // the arrange / locate / score kernels
         H.matches = H.alloc<MatchRec>(n_matches); H.n_matches = n_matches;
-        if (n_matches) CK(cudaMemcpyAsync(H.matches, d_matches, (size_t)n_matches * sizeof(MatchRec), cudaMemcpyDeviceToHost, s2));
         // ---- arrange --------------------------------------------------------------------------------------------------
         uint32_t* d_moff = B.alloc<uint32_t>(n + 1);
         uint32_t* d_cursor = B.alloc<uint32_t>(n, true, s);
@@ -851,6 +848,9 @@ static void run_device_job(DeviceJob* job) {
             if (tot >= (1ull << 32)) throw std::runtime_error("more than 2^32 hits in one batch; lower the batch size");
             H.n_hits = (size_t)tot;
         }
+        // the match arena is final: its copy to the host runs on the second stream, under the expand / locate / score kernels
+        // (issued after the small hit-count read-back above, which would otherwise queue behind it on the copy engine)
+        if (n_matches) CK(cudaMemcpyAsync(H.matches, d_matches, (size_t)n_matches * sizeof(MatchRec), cudaMemcpyDeviceToHost, s2));
         CK(launch_scan(d_nhits, d_hoff, n, s));
         const uint32_t nh = (uint32_t)H.n_hits;
         uint32_t* d_hit_match = B.alloc<uint32_t>(nh); uint32_t* d_hit_row = B.alloc<uint32_t>(nh); uint32_t* d_hit_guide = B.alloc<uint32_t>(nh);

@@ -8,16 +8,25 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
 
 using namespace gsx;
 
+int gsx_set_error(int code, const std::string& msg);      // gsx_api.cpp
+
 namespace {
 thread_local std::string t_err;
 
-inline void put_u64(std::string& s, uint64_t v) { char t[24]; int n = snprintf(t, sizeof t, "%llu", (unsigned long long)v); s.append(t, n); }
+inline void put_u64(std::string& s, uint64_t v) {
+    char t[24]; int n = 24;
+    do { t[--n] = (char)('0' + v % 10); v /= 10; } while (v);
+    s.append(t + n, 24 - n);
+}
 inline void put_float(std::string& s, float f) { char t[64]; int n = snprintf(t, sizeof t, "%f", (double)f); s.append(t, n); }   // std::to_string(float)
 inline void put_hex_le64(std::string& s, uint64_t v) {                                      // printer.hpp:18-88
     static const char H[] = "0123456789abcdef";
@@ -25,23 +34,78 @@ inline void put_hex_le64(std::string& s, uint64_t v) {                          
 }
 std::string revcomp(const std::string& x) { std::string r(x.size(), 'N'); for (size_t i = 0; i < x.size(); i++) r[i] = complement_char(x[x.size() - 1 - i]); return r; }
 
+// match.sequence of hit h complemented as printed (= gsx_result_match_sequence, printer.hpp:232,264), table-driven: the
+// character selects of gsx_core.h decode_match mispredict on every other character when run on a host core
+inline size_t match_sequence_at(const gsx_result* r, uint64_t h, char* out) {
+    static const char UPC[8] = {'T', 'G', 'C', 'A', 'N', '?', '?', '?'};                    // complement of the guide's own symbol
+    static const char LOWC[8] = {0, 't', 'g', 'c', 'a', '?', '?', '?'};                      // digit 1..4 = a,c,g,t -> complement
+    static const char PAMC[8] = {'T', 'G', 'C', 'N', 'A', '?', '?', '?'};                    // PAM digit A,C,G,N,T -> complement
+    static const char WIDEC[16] = {'?', '.', 'T', 'G', 'C', 'N', 'A', 't', 'g', 'c', 'a', '?', '?', '?', '?', '?'};
+    size_t pi = 0;
+    if (r->parts.size() > 1) pi = (size_t)(std::upper_bound(r->part_h0.begin(), r->part_h0.end(), h) - r->part_h0.begin()) - 1;
+    const HostArrays& P = r->parts[pi];
+    const MatchRec& m = P.matches[P.hit_match[h - r->part_h0[pi]]];
+    const uint32_t len = m.info >> 24;
+    if (r->wide) {
+        uint64_t hi = m.key_hi, lo = m.key_lo;
+        for (uint32_t i = 0; i < len; i++) { out[i] = WIDEC[hi >> 60]; hi = (hi << 4) | (lo >> 60); lo <<= 4; }
+        return len;
+    }
+    const GuideRec& g = r->guides[r->part_g0[pi] + (m.task >> 1)];
+    const uint32_t qlen = g.qlen;
+    uint64_t k = m.key_lo;
+    for (uint32_t i = len; i-- > 0;) {
+        const uint32_t d = (uint32_t)(k % 5ull); k /= 5ull;
+        const char proto = d ? LOWC[d] : UPC[g.q[i < kMaxQ ? i : 0] & 7u];
+        out[i] = i < qlen ? proto : PAMC[d];
+    }
+    return len;
+}
+
+inline char* put_u64_at(char* w, uint64_t v) {
+    char t[24]; int n = 24;
+    do { t[--n] = (char)('0' + v % 10); v /= 10; } while (v);
+    memcpy(w, t + n, 24 - n); return w + (24 - n);
+}
+
+// One CSV row per counted hit (printer.hpp:244-300).  Rows are assembled in a local buffer and appended once: at millions of
+// rows per second per thread the per-field std::string appends were the cost.
 void format_csv_guide(const gsx_index* ix, const gsx_result* r, const gsx_guide_row& row, size_t g, const gsx_params* p, bool complete, std::string& out) {
     const gsx_result_view& v = r->view;
     if (v.dropped[g]) return;                                                                // process.hpp:68-70: nothing is printed
-    std::string sequence = p->start ? std::string(row.pam) + row.seq : std::string(row.seq) + row.pam;
+    std::string prefix(row.id); prefix += ",";
+    if (p->start) { prefix += row.pam; prefix += row.seq; } else { prefix += row.seq; prefix += row.pam; }
     const uint64_t b = v.first_hit[g]; const uint32_t n = v.n_hits_of[g];
     if (n == 0) {                                                                            // printer.hpp:190-199
-        out += row.id; out += ","; out += sequence; out += ",NA,NA,NA,0";
+        out += prefix; out += ",NA,NA,NA,0";
         if (complete) out += ",NA,NA,NA";
         out += ",1.0\n";
         return;
     }
+    prefix += ",";
     char sp[64]; int spn = snprintf(sp, sizeof sp, "%f", (double)v.specificity[g]);
     char ms[64];
+    constexpr size_t kLine = 1024;
+    char line[kLine];
+    const bool fits = prefix.size() + 400 < kLine;                                           // (chromosome names are checked per row)
+    if (fits) memcpy(line, prefix.data(), prefix.size());
     for (uint64_t h = b; h < b + n; h++) {
         if (!v.counted[h]) continue;
-        out += row.id; out += ","; out += sequence; out += ",";
-        out += ix->host.chr_names[v.chr[h]]; out += ","; put_u64(out, v.pos1[h]); out += ",";
+        const std::string& chr = ix->host.chr_names[v.chr[h]];
+        if (fits && chr.size() < 256) {
+            char* w = line + prefix.size();
+            memcpy(w, chr.data(), chr.size()); w += chr.size(); *w++ = ',';
+            w = put_u64_at(w, v.pos1[h]); *w++ = ','; *w++ = (char)v.strand[h]; *w++ = ','; w = put_u64_at(w, v.distance[h]);
+            if (complete) {
+                *w++ = ','; w += match_sequence_at(r, h, w);
+                *w++ = ','; w = put_u64_at(w, v.rna_bulges[h]); *w++ = ','; w = put_u64_at(w, v.dna_bulges[h]);
+            }
+            *w++ = ','; memcpy(w, sp, spn); w += spn; *w++ = '\n';
+            out.append(line, (size_t)(w - line));
+            continue;
+        }
+        out += prefix;
+        out += chr; out += ","; put_u64(out, v.pos1[h]); out += ",";
         out.push_back((char)v.strand[h]); out += ","; put_u64(out, v.distance[h]);
         if (complete) {
             gsx_result_match_sequence(r, h, ms, sizeof ms);
@@ -94,7 +158,13 @@ int ret_buf(const std::string& s, char** buf, size_t* len) {
 
 // guides CSV (reference src/genomics/kmer.cxx:9-25 on fast-cpp-csv-parser with trim_chars<' ','\t'>, no quoting):
 // the header must name all six columns (any order); position is parsed but unused downstream.
-struct GuideTable { std::vector<std::string> id, seq, pam; std::vector<uint8_t> positive; };
+// The file is read whole and parsed in place by several host threads (fields trimmed and NUL-terminated inside the buffer):
+// at a few million guides per second of GPU throughput a getline / std::string reader is what a job would wait for.
+struct GuideTable {
+    std::vector<char> buf;
+    std::vector<const char*> id, seq, pam; std::vector<uint8_t> positive;
+    size_t size() const { return id.size(); }
+};
 
 std::string trim(const std::string& s) {
     size_t b = 0, e = s.size();
@@ -104,37 +174,90 @@ std::string trim(const std::string& s) {
 }
 
 bool read_guides_csv(const char* path, GuideTable& t, std::string& err) {
-    FILE* f = fopen(path, "r");
+    FILE* f = fopen(path, "rb");
     if (!f) { err = std::string("cannot open kmers file ") + path; return false; }
-    char* line = nullptr; size_t cap = 0; ssize_t l;
+    {
+        std::vector<char>& b = t.buf; size_t have = 0; b.resize(1 << 20);
+        for (;;) { if (have == b.size()) b.resize(b.size() * 2); size_t got = fread(b.data() + have, 1, b.size() - have, f); if (!got) break; have += got; }
+        b.resize(have + 1); b[have] = 0;
+    }
+    fclose(f);
+    char* const base = t.buf.data(); const size_t total = t.buf.size() - 1;
     static const char* want[6] = {"id", "sequence", "pam", "chromosome", "position", "sense"};
     int col_of[6] = {-1, -1, -1, -1, -1, -1}; int ncol = 0;
-    if ((l = getline(&line, &cap, f)) < 0) { fclose(f); free(line); err = "empty kmers file"; return false; }
+    if (total == 0) { err = "empty kmers file"; return false; }
+    size_t body = 0;
     {
-        std::string h(line, l); while (!h.empty() && (h.back() == '\n' || h.back() == '\r')) h.pop_back();
+        const char* nl = (const char*)memchr(base, '\n', total);
+        size_t l = nl ? (size_t)(nl - base) : total; body = nl ? l + 1 : total;
+        std::string h(base, l); while (!h.empty() && (h.back() == '\n' || h.back() == '\r')) h.pop_back();
         size_t b = 0;
         for (;;) {
             size_t e = h.find(',', b); std::string name = trim(h.substr(b, e == std::string::npos ? std::string::npos : e - b));
             bool known = false;
             for (int k = 0; k < 6; k++) if (name == want[k]) { col_of[k] = ncol; known = true; }
-            if (!known) { fclose(f); free(line); err = "Extra column \"" + name + "\" in header of kmers file"; return false; }
+            if (!known) { err = "Extra column \"" + name + "\" in header of kmers file"; return false; }
             ncol++;
             if (e == std::string::npos) break;
             b = e + 1;
         }
-        for (int k = 0; k < 6; k++) if (col_of[k] < 0) { fclose(f); free(line); err = std::string("Missing column \"") + want[k] + "\" in header of kmers file"; return false; }
+        for (int k = 0; k < 6; k++) if (col_of[k] < 0) { err = std::string("Missing column \"") + want[k] + "\" in header of kmers file"; return false; }
     }
-    std::vector<std::string> fields;
-    while ((l = getline(&line, &cap, f)) >= 0) {
-        std::string s(line, l); while (!s.empty() && (s.back() == '\n' || s.back() == '\r')) s.pop_back();
-        if (s.empty()) continue;
-        fields.clear(); size_t b = 0;
-        for (;;) { size_t e = s.find(',', b); fields.push_back(trim(s.substr(b, e == std::string::npos ? std::string::npos : e - b))); if (e == std::string::npos) break; b = e + 1; }
-        if ((int)fields.size() != ncol) { fclose(f); free(line); err = "wrong number of columns in kmers file line: " + s; return false; }
-        t.id.push_back(fields[col_of[0]]); t.seq.push_back(fields[col_of[1]]); t.pam.push_back(fields[col_of[2]]);
-        t.positive.push_back(fields[col_of[5]] == "+");
+    // body: pieces cut at line starts, one host thread each
+    const size_t len = total - body;
+    const size_t nt = std::max<size_t>(1, std::min<size_t>({(size_t)16, len / (1 << 20), (size_t)std::max(1u, std::thread::hardware_concurrency())}));
+    struct Piece { std::vector<const char*> id, seq, pam; std::vector<uint8_t> positive; bool bad = false; std::string bad_line; };
+    std::vector<Piece> pieces(nt);
+    std::vector<size_t> cut(nt + 1, total);
+    cut[0] = body;
+    for (size_t k = 1; k < nt; k++) {
+        size_t at = body + len * k / nt;
+        if (at < cut[k - 1]) at = cut[k - 1];
+        const char* nl = at < total ? (const char*)memchr(base + at, '\n', total - at) : nullptr;
+        cut[k] = nl ? (size_t)(nl - base) + 1 : total;
     }
-    fclose(f); free(line);
+    auto work = [&](size_t k) {
+        Piece& P = pieces[k];
+        const size_t approx = (cut[k + 1] - cut[k]) / 40 + 16;
+        P.id.reserve(approx); P.seq.reserve(approx); P.pam.reserve(approx); P.positive.reserve(approx);
+        char* fb[32]; char* fe[32];
+        for (size_t at = cut[k]; at < cut[k + 1];) {
+            char* line = base + at;
+            char* nl = (char*)memchr(line, '\n', cut[k + 1] - at);
+            char* end = nl ? nl : base + cut[k + 1];
+            at = (size_t)(end - base) + (nl ? 1 : 0);
+            while (end > line && (end[-1] == '\n' || end[-1] == '\r')) end--;
+            if (end == line) continue;
+            int nf = 0; char* b = line; bool too_many = false;
+            for (;;) {
+                char* e = (char*)memchr(b, ',', (size_t)(end - b));
+                if (nf < 32) { fb[nf] = b; fe[nf] = e ? e : end; } else too_many = true;
+                nf++;
+                if (!e) break;
+                b = e + 1;
+            }
+            if (nf != ncol || too_many) { P.bad = true; P.bad_line.assign(line, end); return; }
+            const int need[4] = {col_of[0], col_of[1], col_of[2], col_of[5]};
+            const char* out[4];
+            for (int q = 0; q < 4; q++) {                                                     // trim_chars<' ', '\t'>, then terminate in place
+                char* x = fb[need[q]]; char* y = fe[need[q]];
+                while (x < y && (*x == ' ' || *x == '\t')) x++;
+                while (y > x && (y[-1] == ' ' || y[-1] == '\t' || y[-1] == '\r')) y--;
+                *y = 0; out[q] = x;
+            }
+            P.id.push_back(out[0]); P.seq.push_back(out[1]); P.pam.push_back(out[2]);
+            P.positive.push_back(out[3][0] == '+' && out[3][1] == 0);
+        }
+    };
+    if (nt == 1) work(0);
+    else { std::vector<std::thread> th; for (size_t k = 0; k < nt; k++) th.emplace_back(work, k); for (auto& x : th) x.join(); }
+    size_t n = 0;
+    for (const Piece& P : pieces) { if (P.bad) { err = "wrong number of columns in kmers file line: " + P.bad_line; return false; } n += P.id.size(); }
+    t.id.reserve(n); t.seq.reserve(n); t.pam.reserve(n); t.positive.reserve(n);
+    for (const Piece& P : pieces) {
+        t.id.insert(t.id.end(), P.id.begin(), P.id.end()); t.seq.insert(t.seq.end(), P.seq.begin(), P.seq.end());
+        t.pam.insert(t.pam.end(), P.pam.begin(), P.pam.end()); t.positive.insert(t.positive.end(), P.positive.begin(), P.positive.end());
+    }
     return true;
 }
 }  // namespace
@@ -153,16 +276,17 @@ extern "C" int gsx_format_header(const gsx_index* ix, int format_sam, int comple
     return ret_buf(s, buf, len);
 }
 
-extern "C" int gsx_format_rows(const gsx_index* ix, const gsx_result* r, const gsx_guide_row* rows, size_t g0, size_t g1,
-                               const gsx_params* p, int format_sam, int complete, char** buf, size_t* len) {
-    if (!ix || !r || !rows || !p || !buf || !len || g1 > r->view.n_guides || g0 > g1) return GSX_ERR_ARG;
-    // guides are independent: format slices on host threads, concatenate in order
+// guides are independent: slices are formatted on host threads into their own buffers, in guide order
+static void format_rows_parts(const gsx_index* ix, const gsx_result* r, const gsx_guide_row* rows, size_t g0, size_t g1,
+                              const gsx_params* p, int format_sam, int complete, std::vector<std::string>& parts) {
     size_t n = g1 - g0;
-    unsigned nt = std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), std::max<size_t>(1, n / 2048));
-    std::vector<std::string> parts(nt);
+    unsigned nt = (unsigned)std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), std::max<size_t>(1, n / 2048));
+    parts.assign(nt, std::string());
     auto work = [&](unsigned t) {
         size_t a = g0 + n * t / nt, b = g0 + n * (t + 1) / nt;
-        std::string& o = parts[t]; o.reserve((b - a) * 256);
+        std::string& o = parts[t];
+        size_t hits = (b > a) ? (size_t)(r->view.first_hit[b - 1] + r->view.n_hits_of[b - 1] - r->view.first_hit[a]) : 0;
+        o.reserve(format_sam ? (b - a) * 256 : hits * 112 + (b - a) * 64);
         for (size_t g = a; g < b; g++) {
             if (format_sam) format_sam_guide(ix, r, rows[g - g0], g, p, complete != 0, o);
             else format_csv_guide(ix, r, rows[g - g0], g, p, complete != 0, o);
@@ -170,6 +294,13 @@ extern "C" int gsx_format_rows(const gsx_index* ix, const gsx_result* r, const g
     };
     if (nt == 1) work(0);
     else { std::vector<std::thread> th; for (unsigned t = 0; t < nt; t++) th.emplace_back(work, t); for (auto& x : th) x.join(); }
+}
+
+extern "C" int gsx_format_rows(const gsx_index* ix, const gsx_result* r, const gsx_guide_row* rows, size_t g0, size_t g1,
+                               const gsx_params* p, int format_sam, int complete, char** buf, size_t* len) {
+    if (!ix || !r || !rows || !p || !buf || !len || g1 > r->view.n_guides || g0 > g1) return GSX_ERR_ARG;
+    std::vector<std::string> parts;
+    format_rows_parts(ix, r, rows, g0, g1, p, format_sam, complete, parts);
     size_t tot = 0; for (auto& s : parts) tot += s.size();
     char* b = (char*)malloc(tot + 1);
     if (!b) return GSX_ERR_NOMEM;
@@ -178,38 +309,95 @@ extern "C" int gsx_format_rows(const gsx_index* ix, const gsx_result* r, const g
     return GSX_OK;
 }
 
+// ---- guides CSV as an ABI object (what genomics::kmer_producer is to the reference, src/genomics/kmer.cxx:9-25) -------------
+struct gsx_guide_table { GuideTable t; };
+
+extern "C" int gsx_guides_csv_open(const char* path, gsx_guide_table** out, size_t* n_guides) {
+    if (!path || !out) return gsx_set_error(GSX_ERR_ARG, "null argument");
+    *out = nullptr;
+    gsx_guide_table* g = new gsx_guide_table(); std::string err;
+    if (!read_guides_csv(path, g->t, err)) { delete g; return gsx_set_error(GSX_ERR_IO, err); }
+    if (n_guides) *n_guides = g->t.size();
+    *out = g;
+    return GSX_OK;
+}
+extern "C" int gsx_guides_csv_row(const gsx_guide_table* g, size_t i, gsx_guide_row* row) {
+    if (!g || !row || i >= g->t.size()) return gsx_set_error(GSX_ERR_ARG, "row out of range");
+    row->id = g->t.id[i]; row->seq = g->t.seq[i]; row->pam = g->t.pam[i]; row->sense_positive = (int)g->t.positive[i];
+    return GSX_OK;
+}
+extern "C" void gsx_guides_csv_close(gsx_guide_table* g) { delete g; }
+
+// Whole-file driver.  Three things overlap: the GPU enumerates batch k+1 (gsx_enumerate on this thread) while a writer thread
+// formats batch k on the host cores and writes it; batches go out in file order.  The reference's counterpart is N worker
+// threads behind one mutex-guarded ofstream (process.hpp:119-126).
 extern "C" int gsx_enumerate_file(const gsx_index* ix, const char* kmers_csv, const char* out_path, const gsx_params* p,
                                   int format_sam, int complete, size_t batch_guides, size_t* n_guides, gsx_counters* counters) {
     if (!ix || !kmers_csv || !out_path || !p) return GSX_ERR_ARG;
     GuideTable t; std::string err;
-    if (!read_guides_csv(kmers_csv, t, err)) { fprintf(stderr, "gsx: %s\n", err.c_str()); return GSX_ERR_IO; }
+    if (!read_guides_csv(kmers_csv, t, err)) { fprintf(stderr, "gsx: %s\n", err.c_str()); return gsx_set_error(GSX_ERR_IO, err); }
     FILE* out = fopen(out_path, "wb");
-    if (!out) { fprintf(stderr, "gsx: cannot write %s\n", out_path); return GSX_ERR_IO; }
+    if (!out) { fprintf(stderr, "gsx: cannot write %s\n", out_path); return gsx_set_error(GSX_ERR_IO, std::string("cannot write ") + out_path); }
+    setvbuf(out, nullptr, _IOFBF, 8 << 20);
     char* buf = nullptr; size_t len = 0;
     gsx_format_header(ix, format_sam, complete, &buf, &len); fwrite(buf, 1, len, out); free(buf);
     gsx_params pp = *p; pp.sam_scoring = format_sam ? 1 : 0;
-    if (batch_guides == 0) batch_guides = 1u << 20;
-    gsx_counters total{}; const size_t n = t.id.size();
-    for (size_t b0 = 0; b0 < n; b0 += batch_guides) {
-        size_t b1 = std::min(n, b0 + batch_guides);
-        std::vector<gsx_guide> g(b1 - b0); std::vector<gsx_guide_row> rows(b1 - b0);
-        for (size_t i = b0; i < b1; i++) {
-            g[i - b0] = {t.seq[i].c_str(), t.pam[i].c_str()};
-            rows[i - b0] = {t.id[i].c_str(), t.seq[i].c_str(), t.pam[i].c_str(), (int)t.positive[i]};
+    const size_t n = t.size();
+    if (batch_guides == 0) {
+        // a batch large enough for the slice-major kernels, small enough that its hits fit the arenas: a guide with bulges has
+        // thousands of edited forms and about ten hits per form
+        const char* e = getenv("GSX_FILE_BATCH");
+        batch_guides = e && *e ? (size_t)atoll(e) : 200000;
+        if (p->rna_bulges || p->dna_bulges) {
+            const uint64_t forms = std::max<uint64_t>(1, bulge_variant_count(n ? (uint32_t)std::min<size_t>(strlen(t.seq[0]), 31) : 20, p->rna_bulges, p->dna_bulges));
+            batch_guides = (size_t)std::min<uint64_t>(batch_guides, std::max<uint64_t>(64, (4u << 20) / forms));
         }
-        gsx_result* r = nullptr;
-        int rc = gsx_enumerate(ix, g.data(), g.size(), &pp, &r);
-        if (rc) { fclose(out); return rc; }
-        rc = gsx_format_rows(ix, r, rows.data(), 0, g.size(), &pp, format_sam, complete, &buf, &len);
-        if (rc) { gsx_result_free(r); fclose(out); return rc; }
-        fwrite(buf, 1, len, out); free(buf);
-        gsx_counters c; gsx_result_counters(r, &c);
-        total.nodes += c.nodes; total.lookups += c.lookups; total.matches += c.matches; total.hits += c.hits; total.lf_steps += c.lf_steps; total.spills += c.spills; total.launches += c.launches;
-        total.ms_search += c.ms_search; total.ms_arrange += c.ms_arrange; total.ms_locate += c.ms_locate; total.ms_score += c.ms_score;
-        total.ms_total_device += c.ms_total_device; total.ms_h2d += c.ms_h2d; total.ms_d2h += c.ms_d2h; total.ms_sweep += c.ms_sweep; total.seeds += c.seeds; total.ms_prepare += c.ms_prepare; total.ms_wall += c.ms_wall; total.sectors += c.sectors; total.edited_guides += c.edited_guides;
-        gsx_result_free(r);
+        if (batch_guides == 0) batch_guides = 1;
     }
-    fclose(out);
+    struct Item { gsx_result* r; size_t b0, b1; };
+    std::mutex mu; std::condition_variable cv;
+    std::deque<Item> queue; bool done = false; int wrc = GSX_OK;
+    gsx_counters total{};
+    std::thread writer([&] {
+        std::vector<gsx_guide_row> rows; std::vector<std::string> parts;
+        for (;;) {
+            Item it;
+            { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return !queue.empty() || done; }); if (queue.empty()) return; it = queue.front(); }
+            if (wrc == GSX_OK) {
+                rows.resize(it.b1 - it.b0);
+                for (size_t i = it.b0; i < it.b1; i++) rows[i - it.b0] = {t.id[i], t.seq[i], t.pam[i], (int)t.positive[i]};
+                format_rows_parts(ix, it.r, rows.data(), 0, rows.size(), &pp, format_sam, complete, parts);
+                for (const std::string& s : parts) if (!s.empty() && fwrite(s.data(), 1, s.size(), out) != s.size()) wrc = GSX_ERR_IO;
+                gsx_counters c; gsx_result_counters(it.r, &c);
+                total.nodes += c.nodes; total.lookups += c.lookups; total.matches += c.matches; total.hits += c.hits; total.lf_steps += c.lf_steps; total.spills += c.spills; total.launches += c.launches;
+                total.ms_search += c.ms_search; total.ms_arrange += c.ms_arrange; total.ms_locate += c.ms_locate; total.ms_score += c.ms_score;
+                total.ms_total_device += c.ms_total_device; total.ms_h2d += c.ms_h2d; total.ms_d2h += c.ms_d2h; total.ms_sweep += c.ms_sweep; total.seeds += c.seeds; total.ms_prepare += c.ms_prepare; total.ms_wall += c.ms_wall; total.sectors += c.sectors; total.edited_guides += c.edited_guides;
+            }
+            gsx_result_free(it.r);
+            { std::lock_guard<std::mutex> lk(mu); queue.pop_front(); }                 // (popped after the work: the producer stays at most two batches ahead)
+            cv.notify_all();
+        }
+    });
+    int rc = GSX_OK; std::string rc_msg;
+    std::vector<gsx_guide> g;
+    for (size_t b0 = 0; b0 < n && rc == GSX_OK; b0 += batch_guides) {
+        size_t b1 = std::min(n, b0 + batch_guides);
+        g.resize(b1 - b0);
+        for (size_t i = b0; i < b1; i++) g[i - b0] = {t.seq[i], t.pam[i]};
+        gsx_result* r = nullptr;
+        rc = gsx_enumerate(ix, g.data(), g.size(), &pp, &r);
+        if (rc) { rc_msg = gsx_last_error(); break; }
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return queue.size() < 2; });
+        queue.push_back({r, b0, b1});
+        lk.unlock(); cv.notify_all();
+    }
+    { std::lock_guard<std::mutex> lk(mu); done = true; }
+    cv.notify_all();
+    writer.join();
+    if (fclose(out) != 0 && wrc == GSX_OK) wrc = GSX_ERR_IO;
+    if (rc) return gsx_set_error(rc, rc_msg);
+    if (wrc) return gsx_set_error(wrc, std::string("cannot write ") + out_path);
     if (n_guides) *n_guides = n;
     if (counters) *counters = total;
     return GSX_OK;

@@ -62,7 +62,7 @@ EXPORTS = ["gsx_params_default", "gsx_index_open", "gsx_index_build", "gsx_index
            "gsx_index_n_chromosomes", "gsx_index_chromosome_name", "gsx_index_chromosome_length", "gsx_index_device_bytes",
            "gsx_index_n_devices", "gsx_index_rank", "gsx_index_locate", "gsx_index_export_bwt", "gsx_index_export_sa_samples", "gsx_enumerate", "gsx_result_view_get",
            "gsx_result_counters", "gsx_result_match_sequence", "gsx_result_free", "gsx_format_rows", "gsx_format_header",
-           "gsx_enumerate_file", "gsx_generate_kmers", "gsx_free", "gsx_last_error", "gsx_version", "gsx_device_count"]
+           "gsx_enumerate_file", "gsx_guides_csv_open", "gsx_guides_csv_row", "gsx_guides_csv_close", "gsx_generate_kmers", "gsx_free", "gsx_last_error", "gsx_version", "gsx_device_count"]
 
 _L.gsx_last_error.restype = C.c_char_p
 _L.gsx_version.restype = C.c_char_p
@@ -96,6 +96,10 @@ _L.gsx_format_header.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_voi
 _L.gsx_enumerate_file.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.POINTER(Params), C.c_int, C.c_int, C.c_size_t,
                                   C.POINTER(C.c_size_t), C.POINTER(Counters)]
 _L.gsx_free.argtypes = [C.c_void_p]
+_L.gsx_guides_csv_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+_L.gsx_guides_csv_row.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(GuideRow)]
+_L.gsx_guides_csv_close.argtypes = [C.c_void_p]
+_L.gsx_guides_csv_close.restype = None
 _L.gsx_generate_kmers.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_uint32, C.c_uint64, C.c_char_p, C.c_int, C.c_int,
                                   C.POINTER(C.c_uint64)]
 
@@ -315,3 +319,17 @@ class Index:
         _ck(_L.gsx_enumerate_file(self.h, kmers_csv.encode(), out_path.encode(), C.byref(params), int(fmt == "sam"),
                                   int(mode == "complete"), batch_guides, C.byref(n), C.byref(c)), "gsx_enumerate_file")
         return n.value, c.as_dict()
+
+
+def read_guides_csv(path: str):
+    """Rows of a guides CSV as (id, sequence, pam, sense_positive) through the library's own reader (host only, no GPU)."""
+    h, n = C.c_void_p(), C.c_size_t()
+    _ck(_L.gsx_guides_csv_open(path.encode(), C.byref(h), C.byref(n)), "gsx_guides_csv_open")
+    try:
+        out, row = [], GuideRow()
+        for i in range(n.value):
+            _ck(_L.gsx_guides_csv_row(h, i, C.byref(row)), "gsx_guides_csv_row")
+            out.append((row.id.decode(), row.seq.decode(), row.pam.decode(), bool(row.sense_positive)))
+        return out
+    finally:
+        _L.gsx_guides_csv_close(h)

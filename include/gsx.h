@@ -166,6 +166,15 @@ int gsx_format_header(const gsx_index*, int format_sam, int complete, char** buf
  * src/guidescan.cxx:181-258).  Returns the number of guides through *n_guides. */
 int gsx_enumerate_file(const gsx_index*, const char* kmers_csv, const char* out_path, const gsx_params*,
                        int format_sam, int complete, size_t batch_guides, size_t* n_guides, gsx_counters* counters);
+/* ---- guides CSV ingest (replaces genomics::kmer_producer, src/genomics/kmer.cxx:9-25 over include/csv.hpp) ----------------
+ * The header must name the six columns id, sequence, pam, chromosome, position, sense (any order, nothing else); fields are
+ * trimmed of spaces and tabs, there is no quoting; `position` is read and ignored, as downstream of the reference.  The file
+ * is read whole and parsed by several host threads; rows keep file order.  Strings returned through gsx_guides_csv_row live
+ * until gsx_guides_csv_close. */
+typedef struct gsx_guide_table gsx_guide_table;
+int  gsx_guides_csv_open(const char* path, gsx_guide_table** out, size_t* n_guides);
+int  gsx_guides_csv_row(const gsx_guide_table*, size_t i, gsx_guide_row* row);
+void gsx_guides_csv_close(gsx_guide_table*);
 /* ---- genome-wide guide generation -------------------------------------------------------------------- */
 /* What the reference's scripts/generate_kmers.py prints (reference scripts/generate_kmers.py:55-136): every k-mer next to an
  * occurrence of `pam` (N = any base) on either strand of every FASTA record of at least min_chr_length bases, as the guides

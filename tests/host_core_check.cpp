@@ -14,6 +14,7 @@
 #include "../guidescan-cli_b200/csrc/gsx_core.h"
 #include "../guidescan-cli_b200/csrc/cfd_tables.h"
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -527,6 +528,13 @@ int main(int argc, char** argv) {
     gsx_format_header(&ix, sam, complete, &buf, &len); fwrite(buf, 1, len, out); gsx_free(buf);
     if (gsx_format_rows(&ix, &res, rows.data(), 0, n, &p, sam, complete, &buf, &len)) { fprintf(stderr, "format failed\n"); return 1; }
     fwrite(buf, 1, len, out); gsx_free(buf); fclose(out);
+    if (const char* reps = getenv("GSX_TIME_FORMAT")) {          // formatter throughput on one host thread (rows are those of this run, repeated)
+        const int R = atoi(reps); size_t bytes = 0, lines = 0;
+        const auto t0 = std::chrono::steady_clock::now();
+        for (int i = 0; i < R; i++) { gsx_format_rows(&ix, &res, rows.data(), 0, n, &p, sam, complete, &buf, &len); bytes += len; if (i == 0) for (size_t k = 0; k < len; k++) lines += buf[k] == '\n'; gsx_free(buf); }
+        const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        fprintf(stderr, "format: %.1f MB/s, %.2f M lines/s, %.2f M guides/s on one thread (%zu lines per pass)\n", bytes / sec / 1e6, lines * (double)R / sec / 1e6, n * (double)R / sec / 1e6, lines);
+    }
     fprintf(stderr, "host_core_check: %zu guides, %llu nodes, %u hits, %u LF steps\n", n, (unsigned long long)nodes, nh, steps);
     return 0;
 }

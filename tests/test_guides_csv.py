@@ -1,0 +1,87 @@
+"""Guides CSV ingest (gsx_guides_csv_open, csrc/gsx_format.cpp::read_guides_csv) on the host: same rows, trimming and error
+behaviour as the reference's kmer_producer (src/genomics/kmer.cxx:9-25 over fast-cpp-csv-parser with trim_chars<' ','\\t'>,
+ignore_no_column, no quoting).  No GPU."""
+import os
+import random
+
+import pytest
+
+from conftest import ROOT
+
+
+@pytest.fixture(scope="module")
+def gsx():
+    import gsx as g
+    return g
+
+
+def _restate(text):
+    """what the reference's reader yields: header names any order, fields trimmed of spaces/tabs, blank lines skipped"""
+    lines = text.split("\n")
+    hdr = [h.strip(" \t\r") for h in lines[0].rstrip("\r").split(",")]
+    rows = []
+    for l in lines[1:]:
+        l = l.rstrip("\r\n")
+        if not l:
+            continue
+        f = [x.strip(" \t\r") for x in l.split(",")]
+        assert len(f) == len(hdr)
+        d = dict(zip(hdr, f))
+        rows.append((d["id"], d["sequence"], d["pam"], d["sense"] == "+"))
+    return rows
+
+
+@pytest.mark.parametrize("case", ["g200k", "g150kN"])
+def test_golden_guides_files(gsx, case):
+    path = os.path.join(ROOT, "tests", "golden", case + ".guides.csv")
+    assert gsx.read_guides_csv(path) == _restate(open(path).read())
+
+
+def test_column_order_trimming_crlf_blank_lines_no_final_newline(gsx, tmp_path):
+    text = ("sense , pam,position,\tid ,chromosome,sequence\r\n"
+            "+,NGG,12, g0 ,chr1, ACGTACGTACGTACGTACGT \r\n"
+            "\r\n"
+            "-,\tNAG ,,g1,,TTTTACGTACGTACGTACGA\n"
+            "\n"
+            " + ,,7,g2,chr2,ACGT")
+    p = os.path.join(tmp_path, "a.csv")
+    open(p, "w", newline="").write(text)
+    assert gsx.read_guides_csv(p) == [("g0", "ACGTACGTACGTACGTACGT", "NGG", True), ("g1", "TTTTACGTACGTACGTACGA", "NAG", False),
+                                     ("g2", "ACGT", "", True)]
+    assert gsx.read_guides_csv(p) == _restate(text)
+
+
+@pytest.mark.parametrize("text,msg", [
+    ("id,sequence,pam,chromosome,position\ng,ACGT,NGG,chr1,1\n", 'Missing column "sense"'),
+    ("id,sequence,pam,chromosome,position,sense,score\n", 'Extra column "score"'),
+    ("id,sequence,pam,chromosome,position,sense\ng0,ACGT,NGG,chr1,1,+\ng1,ACGT,NGG,chr1,+\n", "wrong number of columns in kmers file line: g1,ACGT,NGG,chr1,+"),
+    ("id,sequence,pam,chromosome,position,sense\ng0,ACGT,NGG,chr1,1,+,9\n", "wrong number of columns"),
+    ("", "empty kmers file"),
+])
+def test_error_behaviour(gsx, tmp_path, text, msg):
+    p = os.path.join(tmp_path, "bad.csv")
+    open(p, "w").write(text)
+    with pytest.raises(gsx.GsxError) as e:
+        gsx.read_guides_csv(p)
+    assert msg in str(e.value)
+    with pytest.raises(gsx.GsxError):
+        gsx.read_guides_csv(os.path.join(tmp_path, "missing.csv"))
+
+
+def test_large_file_parsed_by_several_threads(gsx, tmp_path):
+    """~16 MB = 15 pieces, so every piece boundary lands in the middle of some line; a bad line late in the file is still reported"""
+    rnd = random.Random(5)
+    rows = ["id,sequence,pam,chromosome,position,sense"]
+    for i in range(300_000):
+        rows.append("chr%d:%d:%s,%s,NGG,chr%d,%d,%s" % (i % 24, i * 7, "+-"[i & 1], "".join(rnd.choice("ACGT") for _ in range(20)), i % 24, i * 7, "+-"[i & 1]))
+    text = "\n".join(rows) + "\n"
+    assert len(text) > 15 << 20
+    p = os.path.join(tmp_path, "big.csv")
+    open(p, "w").write(text)
+    got = gsx.read_guides_csv(p)
+    assert len(got) == 300_000 and got == _restate(text)
+    rows[250_001] = "oops,ACGT"
+    open(p, "w").write("\n".join(rows) + "\n")
+    with pytest.raises(gsx.GsxError) as e:
+        gsx.read_guides_csv(p)
+    assert "wrong number of columns in kmers file line: oops,ACGT" in str(e.value)
