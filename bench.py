@@ -296,6 +296,8 @@ def run_gsx(args):
                          "ms_host_prepare": ctr_tot["ms_prepare"] / args.steps, "ms_call_wall": ctr_tot["ms_wall"] / args.steps},
             "clocks": clocks,
         }
+        if world == 1 and not args.no_file_e2e:
+            line["file_e2e"] = file_e2e(ix, gsx, params, args, kmers, workdir, per * args.steps, hits / total_guides)
         if world == 1 and not args.no_cpu_baseline:
             cb = cpu_baseline(args, g, chroms, kmers, workdir, ix=ix)
             line["parity_on_cpu_sample"] = parity_on_sample(ix, gsx, cb, args)
@@ -305,6 +307,22 @@ def run_gsx(args):
     ix.close()
     if dist is not None:
         dist.destroy_process_group()
+
+
+def file_e2e(ix, gsx, params, args, kmers, workdir, n_max, hits_per_guide):
+    """SURVEY 8(d) secondary metric: the same guides through the whole-file driver the CLI uses (gsx_enumerate_file) -- guides
+    CSV ingest, enumerate in batches, CSV text of every hit written to a file -- wall clock, index resident."""
+    n = int(max(64, min(n_max, 1.2e9 / (hits_per_guide * 90.0 + 60.0))))        # about 1 GB of text at most
+    gcsv, out = os.path.join(workdir, "file_e2e.csv"), os.path.join(workdir, "file_e2e.out")
+    write_sample_csv(gcsv, kmers, n)
+    ix.enumerate_file(gcsv, out, params)                                          # warm-up: arenas, page cache of the output file
+    t0 = time.perf_counter()
+    _, ctr = ix.enumerate_file(gcsv, out, params)
+    dt = time.perf_counter() - t0
+    size = os.path.getsize(out)
+    os.remove(out)
+    return {"value": n / dt, "unit": "guides/s", "guides": n, "seconds": dt, "output_bytes": size, "output_mb_per_s": size / dt / 1e6,
+            "device_ms": ctr["ms_total_device"], "what": "gsx_enumerate_file: guides CSV in, CSV text out (complete mode), host threads format batch k while the GPU runs batch k+1"}
 
 
 def write_sample_csv(path, kmers, n):
@@ -426,6 +444,7 @@ def parse_args(argv=None):
     ap.add_argument("--sa-shift", type=int, default=2, help="SA sample density 2^k rows (the reference samples every 64th row; the index keeps every 4th)")
     ap.add_argument("--cpu-sample", type=int, default=8000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-file-e2e", action="store_true")
     ap.add_argument("--sweep-variants", default="")
     ap.add_argument("--variant", default=None, help="f<k> specialised kernel variant k, g<k> general kernel variant k")
     ap.add_argument("--workdir", default=os.environ.get("GSX_BENCH_DIR", "/tmp/gsx_bench"))
