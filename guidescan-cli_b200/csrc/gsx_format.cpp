@@ -280,12 +280,25 @@ extern "C" int gsx_format_header(const gsx_index* ix, int format_sam, int comple
 static void format_rows_parts(const gsx_index* ix, const gsx_result* r, const gsx_guide_row* rows, size_t g0, size_t g1,
                               const gsx_params* p, int format_sam, int complete, std::vector<std::string>& parts) {
     size_t n = g1 - g0;
-    unsigned nt = (unsigned)std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), std::max<size_t>(1, n / 2048));
+    // slices of about equal numbers of ROWS (a guide with bulges has thousands of hits, a plain one about ten), cut at guides
+    const gsx_result_view& v = r->view;
+    const uint64_t h0 = n ? v.first_hit[g0] : 0, h1 = n ? v.first_hit[g1 - 1] + v.n_hits_of[g1 - 1] : 0;
+    unsigned nt = (unsigned)std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), std::max<size_t>({(size_t)1, n / 2048, (size_t)((h1 - h0) / 32768)}));
+    if (const char* e = getenv("GSX_FORMAT_THREADS")) if (*e) nt = (unsigned)std::max(1, atoi(e));      // tests
+    if (nt > n) nt = (unsigned)std::max<size_t>(1, n);
+    std::vector<size_t> cut(nt + 1, g1);
+    cut[0] = g0;
+    for (unsigned t = 1; t < nt; t++) {
+        const uint64_t target = h0 + (h1 - h0) * t / nt + (uint64_t)n * t / nt;               // rows + guides: guides without hits still cost a row
+        size_t lo = cut[t - 1], hi = g1;                                                     // first guide whose (first_hit + index) reaches the target
+        while (lo < hi) { const size_t mid = lo + (hi - lo) / 2; if (v.first_hit[mid] + (mid - g0) < target) lo = mid + 1; else hi = mid; }
+        cut[t] = lo;
+    }
     parts.assign(nt, std::string());
     auto work = [&](unsigned t) {
-        size_t a = g0 + n * t / nt, b = g0 + n * (t + 1) / nt;
+        size_t a = cut[t], b = cut[t + 1];
         std::string& o = parts[t];
-        size_t hits = (b > a) ? (size_t)(r->view.first_hit[b - 1] + r->view.n_hits_of[b - 1] - r->view.first_hit[a]) : 0;
+        size_t hits = (b > a) ? (size_t)(v.first_hit[b - 1] + v.n_hits_of[b - 1] - v.first_hit[a]) : 0;
         o.reserve(format_sam ? (b - a) * 256 : hits * 112 + (b - a) * 64);
         for (size_t g = a; g < b; g++) {
             if (format_sam) format_sam_guide(ix, r, rows[g - g0], g, p, complete != 0, o);

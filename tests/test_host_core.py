@@ -104,3 +104,17 @@ def test_bulges_as_edited_guides_match_golden(harness, golden_dir, golden_index,
     extra = ["--variants"] + (["--lookahead", "--ftab", "7"] if mirror == "table" else [])
     subprocess.check_call([harness, golden_index["g200k"], gcsv, out] + variant_cli_args(kw) + extra, stderr=subprocess.DEVNULL)
     assert open(out).read() == slice_of(golden_output("g200k", variant).decode(), kw.get("fmt") == "sam")
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("threads", [2, 3, 7, 64])
+@pytest.mark.parametrize("case,variant", [("g200k", "m3_csv"), ("g200k", "m1_r1_d1_csv"), ("g150kN", "m3_altNAG_sam"), ("g200k", "m3_thr1_csv"),
+                                          ("g150kN", "m4_max2_csv")])
+def test_formatter_slices_by_rows_keep_the_text(harness, golden_dir, golden_index, tmp_path, monkeypatch, case, variant, threads):
+    """gsx_format_rows cuts the guides into slices of about equal numbers of rows, one host thread each (bulge batches have
+    thousands of rows per guide); forced here on small golden cases, incl. more threads than guides with hits"""
+    monkeypatch.setenv("GSX_FORMAT_THREADS", str(threads))
+    kw = golden_manifest()["cases"][case]["variants"][variant]["opts"]
+    out = os.path.join(tmp_path, "h.out")
+    subprocess.check_call([harness, golden_index[case], golden_dir[case][1], out] + variant_cli_args(kw), stderr=subprocess.DEVNULL)
+    assert open(out, "rb").read() == golden_output(case, variant)
