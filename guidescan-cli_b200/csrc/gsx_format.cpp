@@ -360,11 +360,12 @@ extern "C" int gsx_enumerate_file(const gsx_index* ix, const char* kmers_csv, co
         // a batch large enough for the slice-major kernels, small enough that its hits fit the arenas: a guide with bulges has
         // thousands of edited forms and about ten hits per form
         const char* e = getenv("GSX_FILE_BATCH");
-        batch_guides = e && *e ? (size_t)atoll(e) : 200000;
+        batch_guides = e && *e ? (size_t)atoll(e) : 200000;                                   // per device
         if (p->rna_bulges || p->dna_bulges) {
             const uint64_t forms = std::max<uint64_t>(1, bulge_variant_count(n ? (uint32_t)std::min<size_t>(strlen(t.seq[0]), 31) : 20, p->rna_bulges, p->dna_bulges));
             batch_guides = (size_t)std::min<uint64_t>(batch_guides, std::max<uint64_t>(64, (4u << 20) / forms));
         }
+        batch_guides *= (size_t)std::max(1, gsx_index_n_devices(ix));                         // (guides are sharded over the index's devices)
         if (batch_guides == 0) batch_guides = 1;
     }
     struct Item { gsx_result* r; size_t b0, b1; };
