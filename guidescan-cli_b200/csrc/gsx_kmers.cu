@@ -17,9 +17,11 @@
 #include <thrust/iterator/counting_iterator.h>
 #include <cuda_runtime.h>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <string>
+#include <thread>
 #include <vector>
 
 int gsx_set_error(int code, const std::string& msg);      // gsx_api.cpp
@@ -104,6 +106,8 @@ extern "C" int gsx_generate_kmers(const char* fasta_path, const char* out_csv_pa
         std::vector<uint32_t> hpos;
         std::string buf; buf.reserve(1 << 22);
         fputs("id,sequence,pam,chromosome,position,sense\n", out);
+        size_t rows_per_thread = 65536;                                                      // (tests lower it to reach the threaded writer on small inputs)
+        if (const char* e = getenv("GSX_KMERS_ROWS_PER_THREAD")) if (*e && atoll(e) > 0) rows_per_thread = (size_t)atoll(e);
 
         auto process = [&](const std::string& name, std::string& seq) {
             if (seq.size() < min_chr_length || seq.empty()) return;
@@ -128,15 +132,31 @@ extern "C" int gsx_generate_kmers(const char* fasta_path, const char* out_csv_pa
                     uint32_t n = 0; KCK(cudaMemcpy(&n, D.count, 4, cudaMemcpyDeviceToHost));
                     hpos.resize(n);
                     if (n) KCK(cudaMemcpy(hpos.data(), D.pos, (size_t)n * 4, cudaMemcpyDeviceToHost));
-                    for (uint32_t i : hpos) {
-                        const uint32_t a = (uint32_t)((int64_t)i + kmer_off);              // first base of the k-mer on the + strand
-                        const uint32_t pos1 = a + 1u - (before ? 0u : plen);                 // = (before ? i - k : i) + 1
-                        char num[16]; const int nl = snprintf(num, sizeof num, "%u", pos1);
-                        buf += prefix; buf += name; buf += ':'; buf.append(num, nl); buf += ':'; buf += fwd ? '+' : '-'; buf += ',';
-                        if (fwd) buf.append(seq, a, k);
-                        else for (uint32_t j = 0; j < k; j++) buf += comp(seq[a + k - 1 - j]);
-                        buf += ','; buf += pam; buf += ','; buf += name; buf += ','; buf.append(num, nl); buf += ','; buf += fwd ? '+' : '-'; buf += '\n';
-                        if (buf.size() > (1u << 22) - 256) { fwrite(buf.data(), 1, buf.size(), out); buf.clear(); }
+                    // rows of positions [lo, hi) appended to o (find_kmers + the print loop of the script)
+                    auto format_rows = [&](size_t lo, size_t hi, std::string& o, bool flush) {
+                        for (size_t q = lo; q < hi; q++) {
+                            const uint32_t i = hpos[q];
+                            const uint32_t a = (uint32_t)((int64_t)i + kmer_off);              // first base of the k-mer on the + strand
+                            const uint32_t pos1 = a + 1u - (before ? 0u : plen);                 // = (before ? i - k : i) + 1
+                            char num[16]; const int nl = snprintf(num, sizeof num, "%u", pos1);
+                            o += prefix; o += name; o += ':'; o.append(num, nl); o += ':'; o += fwd ? '+' : '-'; o += ',';
+                            if (fwd) o.append(seq, a, k);
+                            else for (uint32_t j = 0; j < k; j++) o += comp(seq[a + k - 1 - j]);
+                            o += ','; o += pam; o += ','; o += name; o += ','; o.append(num, nl); o += ','; o += fwd ? '+' : '-'; o += '\n';
+                            if (flush && o.size() > (1u << 22) - 256) { fwrite(o.data(), 1, o.size(), out); o.clear(); }
+                        }
+                    };
+                    const size_t nt = std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), n / rows_per_thread);
+                    if (nt < 2) format_rows(0, n, buf, true);
+                    else {
+                        // many rows (a whole chromosome of PAM sites): slices on host threads, written in order behind what is buffered
+                        fwrite(buf.data(), 1, buf.size(), out); buf.clear();
+                        std::vector<std::string> parts(nt); std::vector<std::thread> th;
+                        const size_t row_bytes = 2 * (prefix.size() + name.size()) + 2 * 11 + k + pam.size() + 16;
+                        for (size_t t = 0; t < nt; t++)
+                            th.emplace_back([&, t] { const size_t lo = (size_t)n * t / nt, hi = (size_t)n * (t + 1) / nt; parts[t].reserve((hi - lo) * row_bytes); format_rows(lo, hi, parts[t], false); });
+                        for (auto& x : th) x.join();
+                        for (const std::string& o : parts) fwrite(o.data(), 1, o.size(), out);
                     }
                     total += n;
                 }
@@ -152,7 +172,12 @@ extern "C" int gsx_generate_kmers(const char* fasta_path, const char* out_csv_pa
                 size_t b = 1; while (b < l.size() && isspace((unsigned char)l[b])) b++;
                 size_t e = b; while (e < l.size() && !isspace((unsigned char)l[e])) e++;
                 name = l.substr(b, e - b); seq.clear(); have_rec = true;
-            } else if (have_rec) for (char c : l) if (!isspace((unsigned char)c)) seq += c;
+            } else if (have_rec) {
+                size_t e = l.size(); while (e && isspace((unsigned char)l[e - 1])) e--;
+                bool inner = false; for (size_t q = 0; q < e; q++) if (isspace((unsigned char)l[q])) { inner = true; break; }
+                if (!inner) seq.append(l, 0, e);                                            // the usual line: one block
+                else for (size_t q = 0; q < e; q++) if (!isspace((unsigned char)l[q])) seq += l[q];
+            }
         };
         while (fgets(chunk, sizeof chunk, in)) {
             line += chunk;

@@ -61,8 +61,11 @@ def test_oracle_restatement_matches_reference_script(fasta, name):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("rows_per_thread", [0, 3])
 @pytest.mark.parametrize("name", sorted(variants()))
-def test_gpu_kmer_generation_matches_reference_script(gsx, fasta, tmp_path, name):
+def test_gpu_kmer_generation_matches_reference_script(gsx, fasta, tmp_path, monkeypatch, name, rows_per_thread):
+    if rows_per_thread:        # the threaded row writer (chromosomes with more than 65536 sites per PAM), reached on the small goldens
+        monkeypatch.setenv("GSX_KMERS_ROWS_PER_THREAD", str(rows_per_thread))
     kw = opts_of(variants()[name]["args"])
     out = str(tmp_path / "k.csv")
     n = gsx.generate_kmers(fasta, out, **kw)
