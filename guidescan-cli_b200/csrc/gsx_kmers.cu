@@ -106,7 +106,7 @@ extern "C" int gsx_generate_kmers(const char* fasta_path, const char* out_csv_pa
         std::vector<uint32_t> hpos;
         std::string buf; buf.reserve(1 << 22);
         fputs("id,sequence,pam,chromosome,position,sense\n", out);
-        size_t rows_per_thread = 65536;                                                      // (tests lower it to reach the threaded writer on small inputs)
+        size_t rows_per_thread = 16384;                                                      // (tests lower it to reach the threaded writer on small inputs)
         if (const char* e = getenv("GSX_KMERS_ROWS_PER_THREAD")) if (*e && atoll(e) > 0) rows_per_thread = (size_t)atoll(e);
 
         auto process = [&](const std::string& name, std::string& seq) {
