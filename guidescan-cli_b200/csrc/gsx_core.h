@@ -683,7 +683,7 @@ GSX_HD void ftab_apply(uint64_t combo, uint64_t q, uint32_t L, uint32_t gidx, co
     for (uint32_t t = 0; t < j; t++) {
         const uint32_t f = (uint32_t)(combo >> (3u + 6u * t)) & 63u, p = (f & 15u) + 2u, sub = f >> 4;
         const uint32_t c = (uint32_t)(q >> (2u * p)) & 3u, s2 = (c + sub) & 3u;
-        idx += (uint32_t)((int32_t)(s2 - c) << (2u * p));
+        idx += (s2 - c) << (2u * p);                                            // (mod 2^32: a smaller symbol subtracts)
         key += (uint64_t)(1u + s2) * pow5[L - 1u - p];
     }
 }
