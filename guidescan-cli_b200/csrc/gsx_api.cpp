@@ -495,6 +495,22 @@ static std::vector<Node> expand_roots(const gsx_index* ix, const Prepared& prep,
     return cur;
 }
 
+// streams and events of one device job: released on every path out of run_device_job (errors included); in-flight copies are
+// waited for first, because the buffers they touch go back to the allocation pools right after
+struct JobStreams {
+    cudaStream_t s = nullptr, s2 = nullptr;
+    cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}, ev_guides = nullptr;
+    ~JobStreams() {
+        if (s) cudaStreamSynchronize(s);
+        if (s2) cudaStreamSynchronize(s2);
+        for (auto& e : ev) if (e) cudaEventDestroy(e);
+        if (ev_guides) cudaEventDestroy(ev_guides);
+        if (s) cudaStreamDestroy(s);
+        if (s2) cudaStreamDestroy(s2);
+        cudaGetLastError();                                      // (a failed job must not leave a sticky error code for the next call's first check)
+    }
+};
+
 struct DeviceJob {
     const gsx_index* ix = nullptr; int slot = 0;
     const Prepared* prep = nullptr; const gsx_params* p = nullptr;
@@ -511,13 +527,16 @@ static void run_device_job(DeviceJob* job) {
         const uint32_t n = (uint32_t)(job->g1 - job->g0);
         const uint32_t n_dist = p.mismatches + 1;
         CK(cudaSetDevice(di.device));
-        cudaStream_t s; CK(cudaStreamCreate(&s));
-        cudaEvent_t ev[8]; for (auto& e : ev) CK(cudaEventCreate(&e));
         DevBufs B(di.device);
+        JobStreams js;                                           // (declared after the buffer holder: destroyed -- synchronised -- before it)
+        CK(cudaStreamCreate(&js.s)); CK(cudaStreamCreate(&js.s2));
+        for (auto& e : js.ev) CK(cudaEventCreate(&e));
+        CK(cudaEventCreateWithFlags(&js.ev_guides, cudaEventDisableTiming));
+        const cudaStream_t s = js.s, s2 = js.s2; cudaEvent_t* const ev = js.ev; const cudaEvent_t ev_guides = js.ev_guides;
         HostArrays& H = job->out; H.n_guides = n;
         H.dropped = H.alloc<uint8_t>(n); H.n_hits_of = H.alloc<uint32_t>(n); H.hoff = H.alloc<uint32_t>(n + 1);
         H.specificity = H.alloc<float>(n); H.perfect = H.alloc<uint8_t>(n); H.cbd = H.alloc<uint32_t>((size_t)n * n_dist);
-        if (n == 0) { H.hoff[0] = 0; cudaStreamDestroy(s); return; }
+        if (n == 0) { H.hoff[0] = 0; return; }
 
         // fast path (search_fast_kernel) when the batch and the index allow it; GSX_FORCE_GENERAL=1 keeps the general kernel
         const bool use_fast = (prep.fast_ok || prep.variant_ok) && !env_int("GSX_FORCE_GENERAL", 0) && n < (1u << 23) &&
@@ -528,8 +547,6 @@ static void run_device_job(DeviceJob* job) {
         // on.  Their upload (pageable host memory: the call blocks the host) is issued on a second stream AFTER the first search
         // launch, so that it runs under the search instead of in front of it.
         const bool late_guides = use_fast && !use_variants && env_int("GSX_LATE_GUIDES", 1) != 0;
-        cudaStream_t s2; CK(cudaStreamCreate(&s2));
-        cudaEvent_t ev_guides; CK(cudaEventCreateWithFlags(&ev_guides, cudaEventDisableTiming));
         GuideRec* d_guides = B.alloc<GuideRec>(n);
         PamSet* d_pamsets = B.alloc<PamSet>(kMaxPamSets);
         bool guides_up = false;
@@ -900,9 +917,6 @@ static void run_device_job(DeviceJob* job) {
         job->ctr.sectors = use_sweep ? st[5] + st[7] : st[1];
         job->ctr.nodes = st[0]; job->ctr.lookups = st[1]; job->ctr.spills = st[2]; job->ctr.lf_steps = st[3];
         job->ctr.matches = n_matches; job->ctr.hits = nh; job->ctr.launches = n_launches;
-        for (auto& e : ev) cudaEventDestroy(e);
-        cudaEventDestroy(ev_guides);
-        cudaStreamDestroy(s); cudaStreamDestroy(s2);
     } catch (const CudaError& e) { job->status = GSX_ERR_CUDA; job->err = e.what(); }
     catch (const std::bad_alloc&) { job->status = GSX_ERR_NOMEM; job->err = "out of host memory"; }
     catch (const std::exception& e) { job->status = GSX_ERR_INTERNAL; job->err = e.what(); }
