@@ -639,7 +639,18 @@ static void run_device_job(DeviceJob* job) {
         };
         // alternative PAMs (process.hpp:51-56): the searches of the PAMs are independent and their matches are collected in
         // the same per-guide sets, so each PAM gets its own pass over the same arenas; only the work counters start over
+        // GSX_FUSED_PAMS=1 (off by default: written at the end of round 1, mirrored on the host, not yet run on a GPU): the PAMs in
+        // ONE pass -- search with the filter PAM, keep the alignments whose PAM characters spell a real PAM (gsx_core.h fused_pam_ok)
+        const bool fuse_pams = prep.n_fast_pams > 1 && variant_f == 1 && env_int("GSX_FUSED_PAMS", 0) != 0;
         auto run_fast_all_pams = [&](SearchArgs& m, uint32_t ng, uint32_t sb, cudaEvent_t ev_mid) {
+            m.n_fused = 0;
+            if (fuse_pams && !m.p.counting) {
+                m.n_fused = prep.n_fast_pams;
+                for (uint32_t k = 0; k < prep.n_fast_pams; k++) m.fused_pams[k] = prep.pampacks[k];
+                m.plen = prep.plens[0]; m.pampack = fused_filter_pampack(prep.pampacks, prep.n_fast_pams, prep.plens[0]);
+                launch_fast(m, ng, sb, ev_mid);
+                return;
+            }
             for (uint32_t k = 0; k < prep.n_fast_pams; k++) {
                 m.pampack = prep.pampacks[k]; m.plen = prep.plens[k];
                 if (k) { CK(cudaMemsetAsync(d_ctrs, 0, 4, s)); CK(cudaMemsetAsync(d_ctrs + 3, 0, 8, s)); }      // task / seed-queue / work-unit counters

@@ -730,6 +730,38 @@ GSX_HD uint32_t sweep_pattern(const SweepPlan& pl, const uint32_t* xtab, uint32_
     return (beta << low_bits) | (((uint32_t)q & ((1u << low_bits) - 1u)) ^ (w & 0x0FFFFFFFu));
 }
 
+// ---- several alternative PAMs in one pass (specialised kernels, optional) ----------------------------------------------
+// The reference searches the PAMs of a guide one after the other into the same std::set (process.hpp:51-56, index.hpp:210-212),
+// so the result is the union of the per-PAM match sets.  One pass finds the same union: search with the FILTER PAM -- the
+// common character where all PAMs agree, the wildcard where they differ -- and keep a finished alignment only if the PAM
+// characters it consumed spell one of the real PAMs.  (Counting passes keep one pass per PAM: the reference's threshold
+// counter counts a site once per PAM it satisfies.)
+//   packs[k]: 3 bits per PAM character in consumption order (0..3 symbol, 4 = N wildcard, 5 = never matches); equal lengths
+GSX_HD uint32_t fused_filter_pampack(const uint32_t* packs, uint32_t n, uint32_t plen) {
+    uint32_t out = 0;
+    for (uint32_t j = 0; j < plen; j++) {
+        const uint32_t c0 = (packs[0] >> (3u * j)) & 7u;
+        bool same = true;
+        for (uint32_t k = 1; k < n; k++) same = same && (((packs[k] >> (3u * j)) & 7u) == c0);
+        out |= (same ? c0 : 4u) << (3u * j);
+    }
+    return out;
+}
+// key: narrow string key whose last plen digits are the consumed PAM characters (A,C,G,N,T = 0..4, gsx_core.h key_append)
+GSX_HD bool fused_pam_ok(uint64_t key, uint32_t plen, const uint32_t* packs, uint32_t n) {
+    uint32_t dg[kMaxPamLen];
+    for (uint32_t j = plen; j-- > 0;) { dg[j] = (uint32_t)(key % 5ull); key /= 5ull; }
+    for (uint32_t k = 0; k < n; k++) {
+        bool ok = true;
+        for (uint32_t j = 0; j < plen; j++) {
+            const uint32_t pc = (packs[k] >> (3u * j)) & 7u;
+            ok = ok && (pc == 4u || (pc < 4u && dg[j] == (pc < 3u ? pc : 4u)));
+        }
+        if (ok) return true;
+    }
+    return false;
+}
+
 // ordering of the matches of one guide: bucket (mismatches) ascending, forward index before reverse index, string order
 GSX_HD int match_cmp(const MatchRec& x, const MatchRec& y) {
     uint32_t bx = ((x.info & 0xffu) << 1) | (x.task & 1u), by = ((y.info & 0xffu) << 1) | (y.task & 1u);

@@ -422,7 +422,7 @@ cudaError_t launch_build_lookahead(const DevStrand& src, unsigned char* lines, u
 //   * strand-dependent constants (block base, C[], sentinel row) are selected from the parameter bank, no shared copy
 //   * all four children are evaluated branch-free; siblings are compacted with two ballots (push count bit 0 / bit 1)
 // ---------------------------------------------------------------------------------------------------------
-template <int WARPS, int CAP, int MINB, bool LOOK>
+template <int WARPS, int CAP, int MINB, bool LOOK, bool FUSED = false>
 __global__ void __launch_bounds__(WARPS * 32, MINB) search_fast_kernel(SearchArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -660,7 +660,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) search_fast_kernel(SearchArg
         if (__any_sync(FULL, final_lvl && (v0 || v1 || v2 || v3))) {
 #define GSX_EMIT(s)                                                                                                   \
             {                                                                                                         \
-                const bool e = final_lvl && v##s;                                                                      \
+                const bool e = final_lvl && v##s && (!FUSED || fused_pam_ok(key5 + GSX_CH_DIGIT(s), plen, a.fused_pams, a.n_fused)); \
                 const uint32_t emask = __ballot_sync(FULL, e);                                                         \
                 if (emask) {                                                                                          \
                     if (a.p.counting) {                                                                               \
@@ -723,10 +723,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) search_fast_kernel(SearchArg
     if (lane == 0) { atomicAdd(a.stats + 0, n_nodes); atomicAdd(a.stats + 1, n_lookups); atomicAdd(a.stats + 2, n_spilled); atomicAdd(a.stats + 7, n_lookups); }
 }
 
-template <int WARPS, int CAP, int MINB, bool LOOK>
+template <int WARPS, int CAP, int MINB, bool LOOK, bool FUSED = false>
 static cudaError_t launch_fast_t(const SearchArgs& a, int sm_count, cudaStream_t s) {
     size_t smem = (size_t)WARPS * CAP * 20;
-    auto k = search_fast_kernel<WARPS, CAP, MINB, LOOK>;
+    auto k = search_fast_kernel<WARPS, CAP, MINB, LOOK, FUSED>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     k<<<sm_count * MINB, WARPS * 32, smem, s>>>(a);
@@ -742,6 +742,10 @@ static cudaError_t launch_fast_t(const SearchArgs& a, int sm_count, cudaStream_t
 
 cudaError_t launch_search_fast(const SearchArgs& a, int variant, int sm_count, cudaStream_t s) {
     const bool look = a.st[0].lines != nullptr && a.st[1].lines != nullptr;
+    if (a.n_fused) {                  // several PAMs in one pass: the default occupancy variant only
+        if (variant != 1 || a.p.counting) return cudaErrorInvalidValue;
+        return look ? launch_fast_t<8, 256, 3, true, true>(a, sm_count, s) : launch_fast_t<8, 256, 3, false, true>(a, sm_count, s);
+    }
 #define X(V, WARPS, CAP, MINB) if (variant == V) return look ? launch_fast_t<WARPS, CAP, MINB, true>(a, sm_count, s) : launch_fast_t<WARPS, CAP, MINB, false>(a, sm_count, s);
     GSX_FAST_VARIANTS(X)
 #undef X

@@ -44,6 +44,9 @@ struct SearchArgs {
     const SeedNode* seeds;             // if set: the tasks are these level-L nodes (written by sweep_kernel), not (guide, strand) roots
     const uint32_t* n_seeds;           // device word: number of seeds written (may exceed seed_cap if the queue overflowed)
     uint32_t seed_cap;
+    // several alternative PAMs in one pass (gsx_core.h fused_pam_ok): pampack above is then the filter PAM; 0 = off
+    uint32_t n_fused;
+    uint32_t fused_pams[kMaxPams];
 };
 
 struct SweepArgs {

@@ -42,6 +42,7 @@ static DevStrand view_of(const HostStrand& h) {
 // look-ahead planes t1..t6 per 64-row block (what build_lookahead_kernel writes behind each OccBlock), built on the host
 static std::vector<uint64_t> g_look[2];     // 12 words per block: hi1, lo1, ..., hi6, lo6
 static bool g_prune = false;
+static bool g_fused = false;     // alternative PAMs in one pass (gsx_core.h fused_pam_ok), as gsx_enumerate does under GSX_FUSED_PAMS=1
 static bool g_variants = false;  // bulges through edited guides (gsx_core.h variant_rewrite), as gsx_enumerate does when Prepared::variant_ok
 
 static std::vector<uint64_t> g_tail[2];     // 4 words per block: hi7, lo7, hi8, lo8 (the scratch planes the summaries' sum2 is built from)
@@ -401,6 +402,7 @@ int main(int argc, char** argv) {
         else if (a == "--ftab") g_ftab_L = atoi(argv[++i]);
         else if (a == "--sweep") g_sweep_sb = atoi(argv[++i]);
         else if (a == "--variants") g_variants = true;
+        else if (a == "--fused") g_fused = true;
         else if (a == "--sam") sam = true; else if (a == "--succinct") complete = false; else if (a == "-a") alts.push_back(argv[++i]);
         else { fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
     }
@@ -445,7 +447,23 @@ int main(int argc, char** argv) {
         }
         vprep.min_qlen = 255; for (const GuideRec& e : vprep.recs) vprep.min_qlen = std::min<uint32_t>(vprep.min_qlen, e.qlen);
     }
-    const Prepared& fprep = g_variants ? vprep : prep;          // the batch the specialised-kernel mirrors (--lookahead / --ftab / --sweep) work on
+    // alternative PAMs in one pass: the batch is searched with the single filter PAM, finished alignments are kept if their PAM
+    // characters spell one of the real PAMs
+    Prepared mprep; uint32_t fused_n = 0, fused_packs[kMaxPams] = {0}, fused_plen = 0;
+    {
+        const Prepared& src = g_variants ? vprep : prep;
+        if (g_fused && src.n_fast_pams > 1 && (src.fast_ok || g_variants)) {
+            mprep = src;
+            fused_n = src.n_fast_pams; fused_plen = src.plens[0];
+            for (uint32_t k = 0; k < fused_n; k++) fused_packs[k] = src.pampacks[k];
+            const uint32_t filt = fused_filter_pampack(fused_packs, fused_n, fused_plen);
+            PamSet& ps = mprep.pamsets[0];
+            ps.n_pams = 1; ps.plen[0] = (uint8_t)fused_plen;
+            for (uint32_t j = 0; j < fused_plen; j++) ps.sym[0][j] = (uint8_t)((filt >> (3 * j)) & 7u);
+            mprep.max_pams = 1; mprep.n_fast_pams = 1; mprep.pampack = filt; mprep.pampacks[0] = filt; mprep.plen = fused_plen; mprep.fast_ok = true;
+        } else if (g_fused) { fprintf(stderr, "--fused: needs a fast-path batch with alternative PAMs\n"); return 4; }
+    }
+    const Prepared& fprep = fused_n ? mprep : (g_variants ? vprep : prep);          // the batch the specialised-kernel mirrors (--lookahead / --ftab / --sweep) work on
     if (g_ftab_L) {
         g_pow5[0] = 1; for (int i = 1; i < 32; i++) g_pow5[i] = g_pow5[i - 1] * 5ull;
         build_ftab_host(st[0], g_ftab_L, g_ftab[0]); build_ftab_host(st[1], g_ftab_L, g_ftab[1]);
@@ -476,12 +494,20 @@ int main(int argc, char** argv) {
             for (uint32_t v = voff[g]; v < voff[g + 1]; v++)
                 for (uint32_t s = 0; s < 2; s++) {
                     tmp.clear();
-                    dfs<false>(st, vprep, 2 * v + s, p.mismatches, 0, 0, false, nullptr, tmp, &nodes);
-                    for (const MatchRec& m : tmp) { MatchRec o; if (variant_rewrite(m, prep.recs[g], vdesc[v], (uint32_t)(2 * g + s), o)) ms.push_back(o); }
+                    dfs<false>(st, fprep, 2 * v + s, p.mismatches, 0, 0, false, nullptr, tmp, &nodes);
+                    for (const MatchRec& m : tmp) {
+                        if (fused_n && !fused_pam_ok(m.key_lo, fused_plen, fused_packs, fused_n)) continue;
+                        MatchRec o; if (variant_rewrite(m, prep.recs[g], vdesc[v], (uint32_t)(2 * g + s), o)) ms.push_back(o);
+                    }
                 }
         } else
         for (uint32_t s = 0; s < 2; s++) {
             if (prep.wide) dfs<true>(st, prep, (uint32_t)(2 * g + s), p.mismatches, p.rna_bulges, p.dna_bulges, false, nullptr, ms, &nodes);
+            else if (fused_n) {
+                std::vector<MatchRec> tmp;
+                dfs<false>(st, fprep, (uint32_t)(2 * g + s), p.mismatches, 0, 0, false, nullptr, tmp, &nodes);
+                for (const MatchRec& m : tmp) if (fused_pam_ok(m.key_lo, fused_plen, fused_packs, fused_n)) ms.push_back(m);
+            }
             else dfs<false>(st, prep, (uint32_t)(2 * g + s), p.mismatches, p.rna_bulges, p.dna_bulges, false, nullptr, ms, &nodes);
         }
         std::stable_sort(ms.begin(), ms.end(), [](const MatchRec& a, const MatchRec& b) { return match_cmp(a, b) < 0; });

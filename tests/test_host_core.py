@@ -118,3 +118,23 @@ def test_formatter_slices_by_rows_keep_the_text(harness, golden_dir, golden_inde
     out = os.path.join(tmp_path, "h.out")
     subprocess.check_call([harness, golden_index[case], golden_dir[case][1], out] + variant_cli_args(kw), stderr=subprocess.DEVNULL)
     assert open(out, "rb").read() == golden_output(case, variant)
+
+
+ALT_PAM_VARIANTS = [v for c, v in golden_cases() if c == "g200k" and "alt" in v]
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("variant", ALT_PAM_VARIANTS)
+@pytest.mark.parametrize("mirror", ["root", "table", "sweep"])
+def test_alternative_pams_in_one_pass_match_golden(harness, golden_dir, golden_index, tmp_path, variant, mirror):
+    """gsx_core.h fused_filter_pampack / fused_pam_ok: one search with the filter PAM (wildcard where the PAMs differ) + a check
+    of the consumed PAM characters gives the union of the per-PAM searches -- two and three PAMs (with cross combinations
+    that spell no real PAM), also together with bulges through edited guides.  (The GPU path behind GSX_FUSED_PAMS=1.)"""
+    kw = golden_manifest()["cases"]["g200k"]["variants"][variant]["opts"]
+    bulges = kw.get("rna_bulges") or kw.get("dna_bulges")
+    gcsv, slice_of = _golden_subset("g200k", str(tmp_path), lambda f: f[2] == "NGG" and set(f[1]) <= set("ACGT"))
+    out = os.path.join(tmp_path, "h.out")
+    extra = ["--fused"] + (["--variants"] if bulges else []) + {"root": [], "table": ["--lookahead", "--ftab", "7"],
+                                                                "sweep": ["--lookahead", "--ftab", "8", "--sweep", "2"]}[mirror]
+    subprocess.check_call([harness, golden_index["g200k"], gcsv, out] + variant_cli_args(kw) + extra, stderr=subprocess.DEVNULL)
+    assert open(out).read() == slice_of(golden_output("g200k", variant).decode(), kw.get("fmt") == "sam")

@@ -148,6 +148,19 @@ def test_radix_sort_match_ordering(gsx, gpu_index, golden_dir, tmp_path, monkeyp
     assert open(out, "rb").read() == golden_output(case, variant)
 
 
+@pytest.mark.skipif(os.environ.get("GSX_TEST_PENDING") != "1", reason="GSX_FUSED_PAMS path: host-verified at the end of round 1, first GPU run pending (set GSX_TEST_PENDING=1)")
+@pytest.mark.parametrize("variant", [v for c, v in golden_cases() if c == "g200k" and "alt" in v])
+@pytest.mark.parametrize("sweep", ["0", "1"])
+def test_alternative_pams_in_one_pass(gsx, gpu_index, tmp_path, monkeypatch, variant, sweep):
+    """search_fast_kernel<..., FUSED>: all PAMs in one pass (filter PAM + check of the consumed PAM characters)"""
+    monkeypatch.setenv("GSX_FUSED_PAMS", "1"); monkeypatch.setenv("GSX_SWEEP", sweep); monkeypatch.setenv("GSX_SWEEP_MIN", "1")
+    kw = golden_manifest()["cases"]["g200k"]["variants"][variant]["opts"]
+    gcsv, slice_of = _ngg_subset(tmp_path)
+    out = os.path.join(tmp_path, "g.out")
+    gpu_index("g200k").enumerate_file(gcsv, out, _params(gsx, kw), fmt=kw.get("fmt", "csv"), mode=kw.get("mode", "complete"))
+    assert open(out).read() == slice_of(golden_output("g200k", variant).decode(), kw.get("fmt") == "sam")
+
+
 @pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
 def test_every_search_kernel_variant(gsx, gpu_index, golden_dir, tmp_path, variant, monkeypatch):
     monkeypatch.setenv("GSX_SEARCH_VARIANT", str(variant))
