@@ -66,6 +66,11 @@ static void upload_index(gsx_index* ix, const int* devices, int n_devices) {
             DeviceStrand& d = di.st[s];
             d.blocks = upload(h.blocks, di.bytes); d.sa = upload(h.sa_samples, di.bytes);
             d.exc_rows = upload(h.exc_rows, di.bytes); d.exc_lf = upload(h.exc_lf, di.bytes); d.n_rows = upload(h.n_rows, di.bytes);
+            {
+                std::vector<uint32_t> map((h.blocks.size() + 31) / 32 + 1, 0u);
+                for (uint32_t row : h.exc_rows) { const uint32_t b = row >> 6; map[b >> 5] |= 1u << (b & 31u); }
+                d.exc_map = upload(map, di.bytes);
+            }
             d.d.blocks = (const OccBlock*)d.blocks; d.d.sa_samples = (const uint32_t*)d.sa;
             d.d.exc_rows = (const uint32_t*)d.exc_rows; d.d.exc_lf = (const uint32_t*)d.exc_lf; d.d.n_rows = (const uint32_t*)d.n_rows;
             d.d.n = (uint32_t)h.n; d.d.n_exc = (uint32_t)h.exc_rows.size(); d.d.n_nrows = (uint32_t)h.n_rows.size();
@@ -121,7 +126,7 @@ static void upload_index(gsx_index* ix, const int* devices, int n_devices) {
 
 static void free_device_index(DeviceIndex& di) {
     cudaSetDevice(di.device);
-    for (int s = 0; s < 2; s++) { cudaFree(di.st[s].blocks); cudaFree(di.st[s].lines); cudaFree(di.st[s].sum0); cudaFree(di.st[s].sum1); cudaFree(di.st[s].sum2); cudaFree(di.st[s].ftab); cudaFree(di.st[s].sa); cudaFree(di.st[s].exc_rows); cudaFree(di.st[s].exc_lf); cudaFree(di.st[s].n_rows); }
+    for (int s = 0; s < 2; s++) { cudaFree(di.st[s].blocks); cudaFree(di.st[s].lines); cudaFree(di.st[s].sum0); cudaFree(di.st[s].sum1); cudaFree(di.st[s].sum2); cudaFree(di.st[s].ftab); cudaFree(di.st[s].sa); cudaFree(di.st[s].exc_rows); cudaFree(di.st[s].exc_lf); cudaFree(di.st[s].n_rows); cudaFree(di.st[s].exc_map); }
     cudaFree(di.chroms);
 }
 
@@ -539,8 +544,12 @@ static void run_device_job(DeviceJob* job) {
         if (n == 0) { H.hoff[0] = 0; return; }
 
         // fast path (search_fast_kernel) when the batch and the index allow it; GSX_FORCE_GENERAL=1 keeps the general kernel
-        const bool use_fast = (prep.fast_ok || prep.variant_ok) && !env_int("GSX_FORCE_GENERAL", 0) && n < (1u << 23) &&
-                              di.st[0].d.n_exc == 1 && di.st[1].d.n_exc == 1 && di.st[0].d.n_nrows == 0 && di.st[1].d.n_nrows == 0;
+        // (an index whose only non-ACGT BWT row is the sentinel; genomes with N / IUPAC characters only under GSX_FAST_ON_N=1:
+        // search_fast_kernel<..., EXC> was written at the end of round 1 and has not run on a GPU yet)
+        const bool plain_index = di.st[0].d.n_exc == 1 && di.st[1].d.n_exc == 1 && di.st[0].d.n_nrows == 0 && di.st[1].d.n_nrows == 0;
+        const bool exc_index = !plain_index && env_int("GSX_FAST_ON_N", 0) != 0 && env_int("GSX_FAST_VARIANT", di.st[0].d.lines ? 1 : 0) == 1 &&
+                               di.st[0].exc_map && di.st[1].exc_map;
+        const bool use_fast = (prep.fast_ok || prep.variant_ok) && !env_int("GSX_FORCE_GENERAL", 0) && n < (1u << 23) && (plain_index || exc_index);
         // bulges: the search runs over the guides' edited forms (gsx_core.h variant_rewrite), in chunks, on the same kernels
         const bool use_variants = use_fast && prep.variant_ok;
         // The specialised kernels read the packed guides (8 bytes each) only; the 80-byte records are needed from the locate stage
@@ -580,6 +589,7 @@ static void run_device_job(DeviceJob* job) {
             CK(cudaMemcpyAsync(d_gq, prep.gq.data() + job->g0, (size_t)n * 8, cudaMemcpyHostToDevice, s));
             if (late_guides) job->ctr.ms_h2d += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_h2d0).count();
             a.gq = d_gq; a.pampack = prep.pampack; a.plen = prep.plen;
+            a.exc = exc_index ? 1u : 0u; a.exc_map[0] = (const uint32_t*)di.st[0].exc_map; a.exc_map[1] = (const uint32_t*)di.st[1].exc_map;
             // L2 residency hint: intervals wide enough that all such blocks of both strands fit the L2 budget
             // (a level-d interval end costs one 128-byte line; lines touched down to level D ~ 2.7 * 4^D per strand)
             const double l2_bytes = (double)env_int("GSX_L2_PIN_MB", 64) * 1e6;

@@ -47,6 +47,7 @@ bool load_gsx(const std::string& prefix, HostIndex& ix, std::string& err);
 struct DeviceStrand {
     DevStrand d{};
     void* blocks = nullptr; void* lines = nullptr; void* sum0 = nullptr; void* sum1 = nullptr; void* sum2 = nullptr; void* ftab = nullptr; void* sa = nullptr; void* exc_rows = nullptr; void* exc_lf = nullptr; void* n_rows = nullptr;
+    void* exc_map = nullptr;      // one bit per 64-row block holding an exception row (SearchArgs::exc_map)
 };
 struct DeviceIndex {
     int device = 0;

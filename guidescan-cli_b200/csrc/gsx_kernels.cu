@@ -422,7 +422,14 @@ cudaError_t launch_build_lookahead(const DevStrand& src, unsigned char* lines, u
 //   * strand-dependent constants (block base, C[], sentinel row) are selected from the parameter bank, no shared copy
 //   * all four children are evaluated branch-free; siblings are compacted with two ballots (push count bit 0 / bit 1)
 // ---------------------------------------------------------------------------------------------------------
-template <int WARPS, int CAP, int MINB, bool LOOK, bool FUSED = false>
+// exception rows (BWT symbol not A/C/G/T) in [i - (i & 63), i): the block's bit of the map first, the table only if it is set
+__device__ __forceinline__ uint32_t exc_before(const uint32_t* __restrict__ map, const uint32_t* __restrict__ rows, uint32_t n_exc, uint32_t i) {
+    const uint32_t b = i >> 6, r = i & 63u;
+    if (r == 0u || !((__ldg(map + (b >> 5)) >> (b & 31u)) & 1u)) return 0u;
+    return lower_bound_u32(rows, n_exc, i) - lower_bound_u32(rows, n_exc, i - r);
+}
+
+template <int WARPS, int CAP, int MINB, bool LOOK, bool FUSED = false, bool EXC = false>
 __global__ void __launch_bounds__(WARPS * 32, MINB) search_fast_kernel(SearchArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -621,6 +628,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) search_fast_kernel(SearchArg
                 uint64_t hi = B0.hi & mask, lo = B0.lo & mask;
                 uint32_t t = __popcll(hi & lo), g = __popcll(hi) - t, c = __popcll(lo) - t;
                 uint32_t aa = r - t - g - c - ((dollar >= sp - r && dollar < sp) ? 1u : 0u);
+                if constexpr (EXC) aa = r - t - g - c - exc_before(s1 ? a.exc_map[1] : a.exc_map[0], s1 ? a.st[1].exc_rows : a.st[0].exc_rows, s1 ? a.st[1].n_exc : a.st[0].n_exc, sp);
                 os0 = B0.c0 + aa; os1 = B0.c1 + c; os2 = B0.c2 + g; os3 = B0.c3 + t;
             }
             {
@@ -628,6 +636,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) search_fast_kernel(SearchArg
                 uint64_t hi = B1.hi & mask, lo = B1.lo & mask;
                 uint32_t t = __popcll(hi & lo), g = __popcll(hi) - t, c = __popcll(lo) - t;
                 uint32_t aa = r - t - g - c - ((dollar >= e1 - r && dollar < e1) ? 1u : 0u);
+                if constexpr (EXC) aa = r - t - g - c - exc_before(s1 ? a.exc_map[1] : a.exc_map[0], s1 ? a.st[1].exc_rows : a.st[0].exc_rows, s1 ? a.st[1].n_exc : a.st[0].n_exc, e1);
                 oe0 = B1.c0 + aa; oe1 = B1.c1 + c; oe2 = B1.c2 + g; oe3 = B1.c3 + t;
             }
         }
@@ -685,6 +694,61 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) search_fast_kernel(SearchArg
             GSX_EMIT(0) GSX_EMIT(1) GSX_EMIT(2) GSX_EMIT(3)
 #undef GSX_EMIT
         }
+        // ---- genome N under a PAM wildcard (EXC only): the reference's PAM stage tries the literal character first, so a
+        //      pattern N also consumes a genome N (index.hpp:139-150); that child lives in the N range of the index ----------
+        if constexpr (EXC) {
+            const uint32_t nn = s1 ? a.st[1].n_nrows : a.st[0].n_nrows;
+            const bool litn = has && !in_proto && c == 4u && nn != 0u;
+            if (__any_sync(FULL, litn)) {
+                uint32_t o_s = 0, wN = 0;
+                if (litn) {
+                    const uint32_t* nr = s1 ? a.st[1].n_rows : a.st[0].n_rows;
+                    o_s = lower_bound_u32(nr, nn, sp); wN = lower_bound_u32(nr, nn, ep + 1u) - o_s;
+                }
+                const bool vN = litn && wN != 0u;
+                const uint32_t spN = (s1 ? a.st[1].C[4] : a.st[0].C[4]) + o_s;
+                const bool eN = vN && final_lvl && (!FUSED || fused_pam_ok(key5 + 3u, plen, a.fused_pams, a.n_fused));
+                const uint32_t emask = __ballot_sync(FULL, eN);
+                if (emask) {
+                    if (a.p.counting) { if (eN) atomicAdd(a.guide_count + ((tlm & 0xFFFFFFu) >> 1), (unsigned long long)wN); }
+                    else {
+                        uint32_t base = 0; const int leader = __ffs(emask) - 1;
+                        if ((int)lane == leader) base = atomicAdd(a.match_count, (uint32_t)__popc(emask));
+                        base = __shfl_sync(FULL, base, leader);
+                        if (eN) {
+                            const uint32_t slot = base + __popc(emask & lt_mask);
+                            if (slot < a.p.match_cap) {
+                                MatchRec m; m.key_hi = 0; m.key_lo = key5 + 3u; m.task = tlm & 0xFFFFFFu; m.sp = spN; m.width = wN;
+                                m.info = ((tlm >> 24) & 7u) | ((lvl + 1u) << 24);
+                                a.matches[slot] = m;
+                                atomicAdd(a.guide_nmatch + ((tlm & 0xFFFFFFu) >> 1), 1u);
+                            } else atomicOr(a.error_flag, GSX_KERR_MATCH_OVERFLOW);
+                        }
+                    }
+                }
+                const bool pN = vN && !final_lvl;
+                const uint32_t pmask = __ballot_sync(FULL, pN);
+                if (pmask) {
+                    const uint32_t np = __popc(pmask);
+                    while (count + np > (uint32_t)CAP) {
+                        if (spill_count + 32u > scap) { if (lane == 0) atomicOr(a.error_flag, GSX_KERR_SPILL_OVERFLOW); }
+                        else {
+                            const uint32_t slot = (head + lane) & (CAP - 1), i = spill_count + lane;
+                            s_base[i] = r_sp[slot]; s_base[scap + i] = r_ep[slot]; s_base[2 * scap + i] = r_tlm[slot]; s_key[i] = r_key[slot];
+                            spill_count += 32u; if (lane == 0) n_spilled += 32;
+                        }
+                        __syncwarp();
+                        head = (head + 32u) & (CAP - 1); count -= 32u;
+                    }
+                    if (pN) {
+                        const uint32_t w = (head + count + __popc(pmask & lt_mask)) & (CAP - 1);
+                        r_sp[w] = spN; r_ep[w] = spN + wN - 1u; r_tlm[w] = tlm1; r_key[w] = key5 + 3u;
+                    }
+                    __syncwarp();
+                    count += np;
+                }
+            }
+        }
         // ---- keep one child in registers, push the siblings ---------------------------------------------------------
         const uint32_t nvalid = final_lvl ? 0u : ((uint32_t)v0 + (uint32_t)v1 + (uint32_t)v2 + (uint32_t)v3);
         const uint32_t pushes = nvalid ? nvalid - 1u : 0u;
@@ -723,10 +787,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) search_fast_kernel(SearchArg
     if (lane == 0) { atomicAdd(a.stats + 0, n_nodes); atomicAdd(a.stats + 1, n_lookups); atomicAdd(a.stats + 2, n_spilled); atomicAdd(a.stats + 7, n_lookups); }
 }
 
-template <int WARPS, int CAP, int MINB, bool LOOK, bool FUSED = false>
+template <int WARPS, int CAP, int MINB, bool LOOK, bool FUSED = false, bool EXC = false>
 static cudaError_t launch_fast_t(const SearchArgs& a, int sm_count, cudaStream_t s) {
     size_t smem = (size_t)WARPS * CAP * 20;
-    auto k = search_fast_kernel<WARPS, CAP, MINB, LOOK, FUSED>;
+    auto k = search_fast_kernel<WARPS, CAP, MINB, LOOK, FUSED, EXC>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     k<<<sm_count * MINB, WARPS * 32, smem, s>>>(a);
@@ -742,8 +806,12 @@ static cudaError_t launch_fast_t(const SearchArgs& a, int sm_count, cudaStream_t
 
 cudaError_t launch_search_fast(const SearchArgs& a, int variant, int sm_count, cudaStream_t s) {
     const bool look = a.st[0].lines != nullptr && a.st[1].lines != nullptr;
-    if (a.n_fused) {                  // several PAMs in one pass: the default occupancy variant only
-        if (variant != 1 || a.p.counting) return cudaErrorInvalidValue;
+    if (a.n_fused || a.exc) {         // several PAMs in one pass / genome with N: the default occupancy variant only
+        if (variant != 1 || (a.n_fused && a.p.counting) || (a.exc && (!a.exc_map[0] || !a.exc_map[1]))) return cudaErrorInvalidValue;
+        if (a.exc) {
+            if (a.n_fused) return look ? launch_fast_t<8, 256, 3, true, true, true>(a, sm_count, s) : launch_fast_t<8, 256, 3, false, true, true>(a, sm_count, s);
+            return look ? launch_fast_t<8, 256, 3, true, false, true>(a, sm_count, s) : launch_fast_t<8, 256, 3, false, false, true>(a, sm_count, s);
+        }
         return look ? launch_fast_t<8, 256, 3, true, true>(a, sm_count, s) : launch_fast_t<8, 256, 3, false, true>(a, sm_count, s);
     }
 #define X(V, WARPS, CAP, MINB) if (variant == V) return look ? launch_fast_t<WARPS, CAP, MINB, true>(a, sm_count, s) : launch_fast_t<WARPS, CAP, MINB, false>(a, sm_count, s);

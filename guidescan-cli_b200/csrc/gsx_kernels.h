@@ -47,6 +47,10 @@ struct SearchArgs {
     // several alternative PAMs in one pass (gsx_core.h fused_pam_ok): pampack above is then the filter PAM; 0 = off
     uint32_t n_fused;
     uint32_t fused_pams[kMaxPams];
+    // genomes with N / IUPAC characters on the specialised tree search (search_fast_kernel<..., EXC>): one bit per 64-row block
+    // that holds a row whose BWT symbol is not A/C/G/T (occ(A) is corrected from the exception table only there); 0 = off
+    uint32_t exc;
+    const uint32_t* exc_map[2];
 };
 
 struct SweepArgs {

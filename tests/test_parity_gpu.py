@@ -161,6 +161,23 @@ def test_alternative_pams_in_one_pass(gsx, gpu_index, tmp_path, monkeypatch, var
     assert open(out).read() == slice_of(golden_output("g200k", variant).decode(), kw.get("fmt") == "sam")
 
 
+@pytest.mark.skipif(os.environ.get("GSX_TEST_PENDING") != "1", reason="GSX_FAST_ON_N path: written at the end of round 1, first GPU run pending (set GSX_TEST_PENDING=1)")
+@pytest.mark.parametrize("variant", [v for c, v in golden_cases() if c == "g150kN"])
+@pytest.mark.parametrize("sweep", ["0", "1"])
+def test_specialised_kernels_on_a_genome_with_n(gsx, gpu_index, tmp_path, monkeypatch, variant, sweep):
+    """search_fast_kernel<..., EXC> (exception-corrected occ(A), literal-N child under a PAM wildcard) behind the sweep / jump
+    table on the golden genome with N runs and a planted literal-N PAM; also with bulges (edited guides) and alternative PAMs"""
+    from test_host_core import _golden_subset
+    monkeypatch.setenv("GSX_FAST_ON_N", "1"); monkeypatch.setenv("GSX_SWEEP", sweep); monkeypatch.setenv("GSX_SWEEP_MIN", "1")
+    monkeypatch.setenv("GSX_VARIANTS_MAX", "100000000")
+    kw = golden_manifest()["cases"]["g150kN"]["variants"][variant]["opts"]
+    gcsv, slice_of = _golden_subset("g150kN", str(tmp_path), lambda f: f[2] == "NGG" and set(f[1]) <= set("ACGT"))
+    out = os.path.join(tmp_path, "g.out")
+    _, ctr = gpu_index("g150kN").enumerate_file(gcsv, out, _params(gsx, kw), fmt=kw.get("fmt", "csv"), mode=kw.get("mode", "complete"))
+    assert ctr["lookups"] > 0
+    assert open(out).read() == slice_of(golden_output("g150kN", variant).decode(), kw.get("fmt") == "sam")
+
+
 @pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
 def test_every_search_kernel_variant(gsx, gpu_index, golden_dir, tmp_path, variant, monkeypatch):
     monkeypatch.setenv("GSX_SEARCH_VARIANT", str(variant))
