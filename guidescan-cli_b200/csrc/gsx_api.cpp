@@ -66,11 +66,7 @@ static void upload_index(gsx_index* ix, const int* devices, int n_devices) {
             DeviceStrand& d = di.st[s];
             d.blocks = upload(h.blocks, di.bytes); d.sa = upload(h.sa_samples, di.bytes);
             d.exc_rows = upload(h.exc_rows, di.bytes); d.exc_lf = upload(h.exc_lf, di.bytes); d.n_rows = upload(h.n_rows, di.bytes);
-            {
-                std::vector<uint32_t> map((h.blocks.size() + 31) / 32 + 1, 0u);
-                for (uint32_t row : h.exc_rows) { const uint32_t b = row >> 6; map[b >> 5] |= 1u << (b & 31u); }
-                d.exc_map = upload(map, di.bytes);
-            }
+            d.exc_map = upload(build_exc_map(h), di.bytes);
             d.d.blocks = (const OccBlock*)d.blocks; d.d.sa_samples = (const uint32_t*)d.sa;
             d.d.exc_rows = (const uint32_t*)d.exc_rows; d.d.exc_lf = (const uint32_t*)d.exc_lf; d.d.n_rows = (const uint32_t*)d.n_rows;
             d.d.n = (uint32_t)h.n; d.d.n_exc = (uint32_t)h.exc_rows.size(); d.d.n_nrows = (uint32_t)h.n_rows.size();

@@ -36,6 +36,15 @@ GSX_HD uint32_t exc_in(const DevStrand& st, uint32_t start, uint32_t i) {
     return lower_bound_u32(st.exc_rows, st.n_exc, i) - lower_bound_u32(st.exc_rows, st.n_exc, start);
 }
 
+// the same count for the block of row i, [i - (i & 63), i), behind a one-bit-per-block map of the blocks that hold any exception
+// row (search_fast_kernel<..., EXC>: on a genome with N almost every block of the A/C/G/T ranges is clean, so the table is
+// searched for a few lookups only)
+GSX_HD uint32_t exc_before(const uint32_t* map, const uint32_t* rows, uint32_t n_exc, uint32_t i) {
+    const uint32_t b = i >> 6, r = i & 63u;
+    if (r == 0u || !((map[b >> 5] >> (b & 31u)) & 1u)) return 0u;
+    return lower_bound_u32(rows, n_exc, i) - lower_bound_u32(rows, n_exc, i - r);
+}
+
 // occurrences of 'N' in BWT[0, i)
 GSX_HD uint32_t rank_n(const DevStrand& st, uint32_t i) { return lower_bound_u32(st.n_rows, st.n_nrows, i); }
 

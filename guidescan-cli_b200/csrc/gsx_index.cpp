@@ -207,6 +207,12 @@ std::vector<uint64_t> ftab_combos(uint32_t n_pos, uint32_t M) {
     return out;
 }
 
+std::vector<uint32_t> build_exc_map(const HostStrand& h) {
+    std::vector<uint32_t> map((h.blocks.size() + 31) / 32 + 1, 0u);
+    for (uint32_t row : h.exc_rows) { const uint32_t b = row >> 6; map[b >> 5] |= 1u << (b & 31u); }
+    return map;
+}
+
 // every op list (gsx_core.h variant_op) with at most R RNA bulges and D DNA bulges for a guide of qlen characters, in the
 // canonical order (by level; the DNA bulges of a level, in sequence, before its skip); the empty list comes last of its
 // branch like everything else, order is irrelevant.  R + D <= 4.

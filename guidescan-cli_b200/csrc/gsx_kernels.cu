@@ -422,13 +422,6 @@ cudaError_t launch_build_lookahead(const DevStrand& src, unsigned char* lines, u
 //   * strand-dependent constants (block base, C[], sentinel row) are selected from the parameter bank, no shared copy
 //   * all four children are evaluated branch-free; siblings are compacted with two ballots (push count bit 0 / bit 1)
 // ---------------------------------------------------------------------------------------------------------
-// exception rows (BWT symbol not A/C/G/T) in [i - (i & 63), i): the block's bit of the map first, the table only if it is set
-__device__ __forceinline__ uint32_t exc_before(const uint32_t* __restrict__ map, const uint32_t* __restrict__ rows, uint32_t n_exc, uint32_t i) {
-    const uint32_t b = i >> 6, r = i & 63u;
-    if (r == 0u || !((__ldg(map + (b >> 5)) >> (b & 31u)) & 1u)) return 0u;
-    return lower_bound_u32(rows, n_exc, i) - lower_bound_u32(rows, n_exc, i - r);
-}
-
 template <int WARPS, int CAP, int MINB, bool LOOK, bool FUSED = false, bool EXC = false>
 __global__ void __launch_bounds__(WARPS * 32, MINB) search_fast_kernel(SearchArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];

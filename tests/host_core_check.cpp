@@ -415,6 +415,16 @@ int main(int argc, char** argv) {
     for (auto l : ix.host.chr_lens) { ix.chroms.push_back({start, l}); start += l; }
     DevStrand st[2] = {view_of(ix.host.st[0]), view_of(ix.host.st[1])};
 
+    // the mapped exception count of search_fast_kernel<..., EXC> against the table search of block_occ, for every row
+    for (int sidx = 0; sidx < 2; sidx++) {
+        const std::vector<uint32_t> map = build_exc_map(ix.host.st[sidx]);
+        const DevStrand& d = st[sidx];
+        for (uint64_t i = 0; i <= d.n; i++) {
+            const uint32_t got = exc_before(map.data(), d.exc_rows, d.n_exc, (uint32_t)i), want = exc_in(d, (uint32_t)i - ((uint32_t)i & 63u), (uint32_t)i);
+            if (got != want) { fprintf(stderr, "exc_before disagrees with exc_in at row %llu of strand %d (%u vs %u)\n", (unsigned long long)i, sidx, got, want); return 3; }
+        }
+    }
+
     // guides file: id,sequence,pam,chromosome,position,sense (fixed column order is enough for the harness)
     std::vector<std::string> ids, seqs, pams; std::vector<int> pos;
     { std::ifstream f(guides_csv); std::string line; std::getline(f, line);
