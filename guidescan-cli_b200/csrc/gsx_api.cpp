@@ -541,7 +541,7 @@ static void run_device_job(DeviceJob* job) {
 
         // fast path (search_fast_kernel) when the batch and the index allow it; GSX_FORCE_GENERAL=1 keeps the general kernel
         // (an index whose only non-ACGT BWT row is the sentinel; genomes with N / IUPAC characters only under GSX_FAST_ON_N=1:
-        // search_fast_kernel<..., EXC> was written at the end of round 1 and has not run on a GPU yet)
+        // search_fast_kernel<..., EXC> was written at the end of round 1; GPU goldens green, not yet run at full genome size)
         const bool plain_index = di.st[0].d.n_exc == 1 && di.st[1].d.n_exc == 1 && di.st[0].d.n_nrows == 0 && di.st[1].d.n_nrows == 0;
         const bool exc_index = !plain_index && env_int("GSX_FAST_ON_N", 0) != 0 && env_int("GSX_FAST_VARIANT", di.st[0].d.lines ? 1 : 0) == 1 &&
                                di.st[0].exc_map && di.st[1].exc_map;
@@ -645,7 +645,7 @@ static void run_device_job(DeviceJob* job) {
         };
         // alternative PAMs (process.hpp:51-56): the searches of the PAMs are independent and their matches are collected in
         // the same per-guide sets, so each PAM gets its own pass over the same arenas; only the work counters start over
-        // GSX_FUSED_PAMS=1 (off by default: written at the end of round 1, mirrored on the host, not yet run on a GPU): the PAMs in
+        // GSX_FUSED_PAMS=1 (off by default: written at the end of round 1; host mirror and GPU goldens green, not yet run at 3.1 Gb): the PAMs in
         // ONE pass -- search with the filter PAM, keep the alignments whose PAM characters spell a real PAM (gsx_core.h fused_pam_ok)
         const bool fuse_pams = prep.n_fast_pams > 1 && variant_f == 1 && env_int("GSX_FUSED_PAMS", 0) != 0;
         auto run_fast_all_pams = [&](SearchArgs& m, uint32_t ng, uint32_t sb, cudaEvent_t ev_mid) {

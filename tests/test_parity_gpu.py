@@ -148,7 +148,6 @@ def test_radix_sort_match_ordering(gsx, gpu_index, golden_dir, tmp_path, monkeyp
     assert open(out, "rb").read() == golden_output(case, variant)
 
 
-@pytest.mark.skipif(os.environ.get("GSX_TEST_PENDING") != "1", reason="GSX_FUSED_PAMS path: host-verified at the end of round 1, first GPU run pending (set GSX_TEST_PENDING=1)")
 @pytest.mark.parametrize("variant", [v for c, v in golden_cases() if c == "g200k" and "alt" in v])
 @pytest.mark.parametrize("sweep", ["0", "1"])
 def test_alternative_pams_in_one_pass(gsx, gpu_index, tmp_path, monkeypatch, variant, sweep):
@@ -161,7 +160,6 @@ def test_alternative_pams_in_one_pass(gsx, gpu_index, tmp_path, monkeypatch, var
     assert open(out).read() == slice_of(golden_output("g200k", variant).decode(), kw.get("fmt") == "sam")
 
 
-@pytest.mark.skipif(os.environ.get("GSX_TEST_PENDING") != "1", reason="GSX_FAST_ON_N path: written at the end of round 1, first GPU run pending (set GSX_TEST_PENDING=1)")
 @pytest.mark.parametrize("variant", [v for c, v in golden_cases() if c == "g150kN"])
 @pytest.mark.parametrize("sweep", ["0", "1"])
 def test_specialised_kernels_on_a_genome_with_n(gsx, gpu_index, tmp_path, monkeypatch, variant, sweep):
