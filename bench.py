@@ -154,6 +154,11 @@ def make_workload(args, world):
     pos, kmers = synth.sample_guides(g, n_total, args.seed)
     n_plant = min(n_total, args.plant_guides)
     synth.plant(g, kmers[:n_plant], args.seed)
+    if args.n_runs:      # runs of N (every real assembly has them): the index then holds exception rows beyond the sentinel
+        rng = np.random.default_rng(args.seed + 3000003)
+        for _ in range(args.n_runs):
+            at = int(rng.integers(1000, G - 100000))
+            g[at:at + int(rng.integers(1, 50000))] = ord("N")
     chroms = synth.chromosome_table(G, args.n_chr)
     log("workload: genome %.1f Mb, %d guides total (%d with planted copies) in %.1f s" % (G / 1e6, n_total, n_plant, time.time() - t0))
     return g, chroms, pos, kmers
@@ -448,6 +453,7 @@ def parse_args(argv=None):
     ap.add_argument("--cpu-sample", type=int, default=8000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-file-e2e", action="store_true")
+    ap.add_argument("--n-runs", type=int, default=0, help="insert this many runs of N (1..50000 bases) into the genome after the guides were sampled and planted")
     ap.add_argument("--sweep-variants", default="")
     ap.add_argument("--variant", default=None, help="f<k> specialised kernel variant k, g<k> general kernel variant k")
     ap.add_argument("--workdir", default=os.environ.get("GSX_BENCH_DIR", "/tmp/gsx_bench"))
