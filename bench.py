@@ -243,15 +243,34 @@ def run_gsx(args):
     dev_ms = search_ms = 0.0
     ctr_tot = {}
     d2h_bytes = 0
-    for s in range(args.warmup, args.warmup + args.steps):
+    acc_lock = threading.Lock()
+
+    def one_step(s):
+        nonlocal dev_ms, search_ms, d2h_bytes
         r = ix.enumerate_raw(steps[s][0], per, params)
         c = r.counters()
-        dev_ms += c["ms_total_device"]; search_ms += c["ms_search"]
-        for k, v in c.items():
-            ctr_tot[k] = ctr_tot.get(k, 0) + v
-        d2h_bytes = r.n_guides * (1 + 4 + 4 + 4 + 1 + 4 * (args.mismatches + 1)) + r.n_hits * (8 + 4 + 4 + 4 + 6 + 4 + 4) + c["matches"] * 32
         spec_sum = float(r.guide_arrays()["specificity"].sum())       # the step's result is read on the host
+        with acc_lock:
+            dev_ms += c["ms_total_device"]; search_ms += c["ms_search"]
+            for k, v in c.items():
+                ctr_tot[k] = ctr_tot.get(k, 0) + v
+            d2h_bytes = r.n_guides * (1 + 4 + 4 + 4 + 1 + 4 * (args.mismatches + 1)) + r.n_hits * (8 + 4 + 4 + 4 + 6 + 4 + 4) + c["matches"] * 32
         r.close()
+        return spec_sum
+
+    timed = list(range(args.warmup, args.warmup + args.steps))
+    if args.e2e_threads <= 1:
+        for s in timed:
+            one_step(s)
+    else:
+        # opt-in: the public call from several host threads (as the reference's own worker threads would make it); the library
+        # serialises the device section (GSX_DEVICE_LOCK) and the rest of one call overlaps another call's kernels
+        os.environ["GSX_DEVICE_LOCK"] = "1"
+        workers = [threading.Thread(target=lambda t=t: [one_step(s) for s in timed[t::args.e2e_threads]]) for t in range(args.e2e_threads)]
+        for w in workers:
+            w.start()
+        for w in workers:
+            w.join()
     barrier_sync(dist, local)
     e2e_s = time.perf_counter() - t0
     clocks = sampler.finish() if sampler else None
@@ -280,7 +299,7 @@ def run_gsx(args):
                                    "%d NGG 20-mer guides per GPU per step, mismatches=%d, both strand indexes, locate + CFD + specificity"
                                    % (args.genome_mb, args.seed, args.n_chr, per, args.mismatches),
                        "genome_mb": args.genome_mb, "guides_per_gpu_per_step": per, "mismatches": args.mismatches, "alt_pams": list(args.alt_pam), "rna_bulges": args.rna_bulges, "dna_bulges": args.dna_bulges,
-                       "index": how, "sa_sample_rows": 1 << args.sa_shift, "parallelism": "guides sharded x%d, index replicated" % world,
+                       "index": how, "sa_sample_rows": 1 << args.sa_shift, "parallelism": "guides sharded x%d, index replicated" % world, "e2e_host_threads": args.e2e_threads,
                        "l2": "index (%.2f GB) is far larger than L2; every step uses new guides" % (ix.device_bytes / 1e9)},
             "e2e": {"value": total_guides / e2e_s, "unit": "guides/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": int(d2h_bytes),
                     "ms_per_step": e2e_s * 1e3 / args.steps},
@@ -453,6 +472,7 @@ def parse_args(argv=None):
     ap.add_argument("--cpu-sample", type=int, default=8000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-file-e2e", action="store_true")
+    ap.add_argument("--e2e-threads", type=int, default=1, help="host threads issuing the timed steps (opt-in; 1 = one call after the other)")
     ap.add_argument("--n-runs", type=int, default=0, help="insert this many runs of N (1..50000 bases) into the genome after the guides were sampled and planted")
     ap.add_argument("--sweep-variants", default="")
     ap.add_argument("--variant", default=None, help="f<k> specialised kernel variant k, g<k> general kernel variant k")

@@ -665,6 +665,12 @@ static void run_device_job(DeviceJob* job) {
         };
         auto grow_queue = [&]() { B.free_one(d_queue); d_queue = nullptr; queue_cap *= 4; if (queue_cap > (1ull << 31)) throw std::runtime_error("seed queue keeps overflowing"); };
 
+        // GSX_DEVICE_LOCK=1 (opt-in, not yet measured): callers on several host threads take turns on the device for the search ..
+        // specificity section, so that one call's guide packing and result copies run under another call's kernels instead of
+        // two sweeps sharing -- and thrashing -- the L2 slices
+        static std::mutex device_mu[64];
+        std::unique_lock<std::mutex> device_turn;
+        if (env_int("GSX_DEVICE_LOCK", 0)) device_turn = std::unique_lock<std::mutex>(device_mu[di.device & 63]);
         CK(cudaEventRecord(ev[0], s));
         // ---- threshold prefilter (process.hpp:66-76): mismatch-only counting search, guide dropped if > 1 site -----
         if (p.threshold > 0) {
@@ -909,6 +915,7 @@ static void run_device_job(DeviceJob* job) {
         S.n_guides = n; S.n_dist = n_dist; S.sam_rule = p.sam_scoring ? 1 : 0; S.max_off_targets = p.max_off_targets;
         CK(launch_specificity(S, s));
         CK(cudaEventRecord(ev[4], s));
+        if (device_turn.owns_lock()) { CK(cudaStreamSynchronize(s)); device_turn.unlock(); }
         // ---- results to host ---------------------------------------------------------------------------------------------
         H.abs_pos = H.alloc<int64_t>(nh); H.sa_row = H.alloc<uint32_t>(nh); H.chr = H.alloc<int32_t>(nh); H.pos1 = H.alloc<uint32_t>(nh);
         H.strand = H.alloc<uint8_t>(nh); H.distance = H.alloc<uint8_t>(nh); H.rna = H.alloc<uint8_t>(nh); H.dna = H.alloc<uint8_t>(nh);
