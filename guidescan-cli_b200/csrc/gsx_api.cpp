@@ -633,7 +633,7 @@ static void run_device_job(DeviceJob* job) {
                 w.M = m.p.M; w.plen = m.plen; w.pampack = m.pampack; w.load_mode = (uint32_t)env_int("GSX_SWEEP_LOAD", 2);
                 w.parts = 1;                                                       // measured: cutting the units does not pay (profiles/r01r_*)
                 w.queue = d_queue; w.queue_cap = (uint32_t)queue_cap; w.queue_count = d_ctrs + 3; w.item_counter = d_ctrs + 4;
-                w.error_flag = d_ctrs + 2; w.stats = d_stats;
+                w.error_flag = d_ctrs + 2; w.stats = d_stats; w.fmask = m.fmask;
                 if (gtab_cap < ng) { if (d_gtab) B.free_one(d_gtab); d_gtab = B.alloc<uint32_t>((size_t)ng * 20); gtab_cap = ng; }
                 w.gtab = d_gtab;
                 CK(launch_sweep_guides(w, s)); n_launches++;
@@ -745,6 +745,8 @@ static void run_device_job(DeviceJob* job) {
             spill_cap = 2048; if (env_int("GSX_SPILL_CAP", 0) > 0) spill_cap = (uint32_t)env_int("GSX_SPILL_CAP", 0);
             uint64_t* d_vq = B.alloc<uint64_t>(chunk_v + 1); uint32_t* d_vdesc = B.alloc<uint32_t>(chunk_v + 1); uint32_t* d_vguide = B.alloc<uint32_t>(chunk_v + 1);
             uint32_t* d_vnmatch = B.alloc<uint32_t>(chunk_v + 1);
+            // GSX_FORCED_SWEEP=1 (opt-in, host-mirrored, not yet run on a GPU): the sweep skips patterns that substitute an inserted position
+            uint32_t* d_vfmask = env_int("GSX_FORCED_SWEEP", 0) ? B.alloc<uint32_t>(chunk_v + 1) : nullptr;
             uint32_t* d_voff = nullptr; size_t voff_cap = 0;
             MatchRec* d_vmatches = B.alloc<MatchRec>(vmatch_cap);
             d_matches = B.alloc<MatchRec>(match_cap);
@@ -772,7 +774,7 @@ static void run_device_job(DeviceJob* job) {
                 if (n_v) {
                     if (voff_cap < seg.size()) { if (d_voff) B.free_one(d_voff); voff_cap = std::max<size_t>(seg.size(), 4096); d_voff = B.alloc<uint32_t>(voff_cap); }
                     CK(cudaMemcpyAsync(d_voff, seg.data(), seg.size() * 4, cudaMemcpyHostToDevice, s));
-                    CK(launch_variant_expand(d_guides, n_seg, n_v, d_voff, d_descs, d_doff, d_vq, d_vdesc, d_vguide, s)); n_launches++;
+                    CK(launch_variant_expand(d_guides, n_seg, n_v, d_voff, d_descs, d_doff, d_vq, d_vdesc, d_vguide, d_vfmask, s)); n_launches++;
                     const uint32_t sb = plan_sweep(n_v, vmin_qlen, p.mismatches);
                     if (sb) use_sweep = true;
                     for (int attempt = 0;; attempt++) {
@@ -781,7 +783,7 @@ static void run_device_job(DeviceJob* job) {
                         CK(cudaMemsetAsync(d_ctrs, 0, 5 * sizeof(uint32_t), s));
                         SearchArgs m = a; m.p.M = p.mismatches; m.p.R = m.p.D = 0; m.p.counting = 0; m.p.n_tasks = 2 * n_v;
                         m.p.match_cap = (uint32_t)vmatch_cap; m.p.spill_cap = spill_cap; m.spill = d_spill; m.matches = d_vmatches;
-                        m.skip = nullptr; m.gq = d_vq; m.guide_nmatch = d_vnmatch; m.guides = nullptr;
+                        m.skip = nullptr; m.gq = d_vq; m.guide_nmatch = d_vnmatch; m.guides = nullptr; m.fmask = d_vfmask;
                         run_fast_all_pams(m, n_v, sb, nullptr);
                         uint32_t h[4]; CK(cudaMemcpyAsync(h, d_ctrs, sizeof h, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s));
                         B.free_one(d_spill);

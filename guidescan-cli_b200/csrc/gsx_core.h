@@ -246,6 +246,22 @@ GSX_HD uint64_t variant_pack(const uint8_t* q, uint32_t qlen, uint32_t desc) {
     return v | ((uint64_t)n << 58);
 }
 
+// inserted (must-match) positions of the edited guide as a mask over the 2-bit fields of a jump-table index: bits 2f, 2f+1 set
+// for every inserted position f < 16.  A pattern that substitutes such a position can only lead to alignments variant_rewrite
+// drops, so the sweep may skip it (sweep_kernel<..., FORCED>).
+GSX_HD uint32_t variant_forced_mask(uint32_t qlen, uint32_t desc) {
+    uint32_t m = 0, n = 0;
+    for (uint32_t lvl = 0; lvl <= qlen; lvl++) {
+        while ((desc & 0xFFu) && (desc & 31u) == lvl && (desc & 32u)) { if (n < 16u) m |= 3u << (2u * n); n++; desc >>= 8; }
+        if (lvl == qlen) break;
+        if ((desc & 0xFFu) && (desc & 31u) == lvl) { desc >>= 8; continue; }
+        n++;
+    }
+    return m;
+}
+// does table index idx keep the guide's own characters at the forced positions?  (the patterns the sweep still has to visit)
+GSX_HD bool forced_kept(uint32_t idx, uint64_t q, uint32_t fmask) { return ((idx ^ (uint32_t)q) & fmask) == 0u; }
+
 // match of an edited guide (narrow key over its own characters) -> match of the guide itself (wide key, bulge counts);
 // false if an inserted position was matched by substitution (that alignment belongs to the variant holding the other symbol)
 GSX_HD bool variant_rewrite(const MatchRec& in, const GuideRec& g, uint32_t desc, uint32_t real_task, MatchRec& out) {

@@ -916,7 +916,7 @@ __device__ __forceinline__ void cont_process(const SweepArgs& a, ContBuf& cb, ui
 //   [16] plane codes of levels L .. L+6   [17] of levels L+7, L+8
 constexpr int CB_SLOTS = 64;          // parked nodes per warp: drained below 32 before every step, which adds at most 32
 constexpr int XT_SMEM = 4352;          // words of shared memory for the xor table (17 KB)
-constexpr int GT_WORDS = 20, GT_QLOW = 15, GT_CODES = 16, GT_CODES2 = 17;
+constexpr int GT_WORDS = 20, GT_QLOW = 15, GT_CODES = 16, GT_CODES2 = 17, GT_FMASK = 18;      // [18] must-match positions of an edited guide (index mask)
 
 __global__ void sweep_guides_kernel(SweepArgs a, uint32_t* __restrict__ gtab) {
     for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < a.n_guides; g += gridDim.x * blockDim.x) {
@@ -925,7 +925,7 @@ __global__ void sweep_guides_kernel(SweepArgs a, uint32_t* __restrict__ gtab) {
         const uint32_t codes = sweep_codes(q, a.plan.L, a.plen, a.pampack);
         summary_masks(codes, t);
         t[GT_QLOW] = (uint32_t)q & ((1u << (2u * (a.plan.L - a.plan.sb))) - 1u);
-        t[GT_CODES] = codes; t[GT_CODES2] = sweep_codes2(q, a.plan.L, a.plen, a.pampack); t[18] = t[19] = 0;
+        t[GT_CODES] = codes; t[GT_CODES2] = sweep_codes2(q, a.plan.L, a.plen, a.pampack); t[GT_FMASK] = a.fmask ? a.fmask[g] : 0u; t[19] = 0;
         uint4* dst = reinterpret_cast<uint4*>(gtab + (size_t)g * GT_WORDS);
         for (int k = 0; k < GT_WORDS / 4; k++) dst[k] = make_uint4(t[4 * k], t[4 * k + 1], t[4 * k + 2], t[4 * k + 3]);
     }
@@ -970,7 +970,7 @@ __device__ __forceinline__ void sweep_judge(const uint32_t w[8], const unsigned 
 // all patterns of ONE guide (lane `o` of the unit) in one pass, 32 per step: the guide's masks sit in registers, the xor
 // table (shared memory when it fits) is read with unit stride, nothing is looked up per lane but the summary sector itself.
 // (Two summary loads in flight per lane were tried and lost to register pressure: profiles/r01x_*.)
-template <bool ZERO, int NB>
+template <bool ZERO, int NB, bool FORCED = false>
 __device__ __forceinline__ void sweep_run(const SweepArgs& a, const SweepPlan& pl, ContBuf& cb, const uint32_t* sg, const uint32_t* xtab, uint32_t lane,
                                           uint32_t strand, uint32_t hi_bits, uint32_t guide, uint32_t o, uint32_t B, SweepStats& st) {
     const uint32_t M = a.M, n = pl.xcnt[ZERO ? 1 : 0][B];
@@ -983,12 +983,16 @@ __device__ __forceinline__ void sweep_run(const SweepArgs& a, const SweepPlan& p
     const uint32_t qlow = g3.w, codes = sg[o * GT_WORDS + GT_CODES], codes2 = sg[o * GT_WORDS + GT_CODES2];
     const unsigned char* sum2 = strand ? a.st[1].sum2 : a.st[0].sum2;
     const uint32_t tl = (guide << 1) | strand;
-    st.sectors += n;
+    uint32_t fm = 0;
+    if constexpr (FORCED) fm = sg[o * GT_WORDS + GT_FMASK] & 0x0FFFFFFFu;      // patterns that substitute a must-match position are skipped
+    if constexpr (!FORCED) st.sectors += n;
     for (uint32_t base = 0; base < n; base += 32u) {
         while (cb.count >= 32u) cont_process<NB>(a, cb, lane, st);
         const uint32_t t = base + lane;
         bool emit = false, park = false; uint32_t idx = 0, mm = M;
-        if (t < n) {
+        bool live = t < n;
+        if constexpr (FORCED) { if (live && (xt[t] & fm)) live = false; st.sectors += __popc(__ballot_sync(0xffffffffu, live)); }
+        if (live) {
             const uint32_t xw = xt[t];
             idx = hi_bits | (qlow ^ (xw & 0x0FFFFFFFu));
             if (!ZERO) mm = M - B + (xw >> 28);                               // (pass 1 always ends at M)
@@ -1002,7 +1006,7 @@ __device__ __forceinline__ void sweep_run(const SweepArgs& a, const SweepPlan& p
     }
 }
 
-template <int WARPS, int MINB, int NB>
+template <int WARPS, int MINB, int NB, bool FORCED = false>
 __global__ void __launch_bounds__(WARPS * 32, MINB) sweep_kernel(SweepArgs a) {
     __shared__ SweepPlan s_plan;
     __shared__ uint32_t s_c32[WARPS][4][CB_SLOTS];
@@ -1041,6 +1045,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) sweep_kernel(SweepArgs a) {
             dst[0] = v0; dst[1] = v1; dst[2] = v2; dst[3] = v3; dst[4] = v4;
             const uint32_t h = sweep_slice_distance(__ldg(a.gq + g), L, sb, beta);
             if (h <= M) B = (int)(M - h);
+            if constexpr (FORCED) {      // the slice substitutes a must-match position of this (edited) guide: nothing to do here
+                const uint32_t top = (uint32_t)(__ldg(a.gq + g) >> (2u * (L - sb))) & ((1u << (2u * sb)) - 1u);
+                if ((top ^ beta) & (v4.z >> (2u * (L - sb)))) B = -1;
+            }
         }
         __syncwarp();
         const uint32_t hi_bits = beta << (2u * (L - sb));
@@ -1072,8 +1080,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) sweep_kernel(SweepArgs a) {
         while (todo) {
             const uint32_t o = (uint32_t)__ffs(todo) - 1u; todo &= todo - 1u;
             const uint32_t Bo = (uint32_t)__shfl_sync(FULL, B, o);
-            sweep_run<true, NB>(a, s_plan, cb, sg, xtab, lane, strand, hi_bits, gb * 32u + o, o, Bo, st);
-            if (Bo >= 2u) sweep_run<false, NB>(a, s_plan, cb, sg, xtab, lane, strand, hi_bits, gb * 32u + o, o, Bo, st);
+            sweep_run<true, NB, FORCED>(a, s_plan, cb, sg, xtab, lane, strand, hi_bits, gb * 32u + o, o, Bo, st);
+            if (Bo >= 2u) sweep_run<false, NB, FORCED>(a, s_plan, cb, sg, xtab, lane, strand, hi_bits, gb * 32u + o, o, Bo, st);
         }
     }
     while (cb.count) cont_process<NB>(a, cb, lane, st);
@@ -1099,7 +1107,14 @@ cudaError_t launch_sweep(const SweepArgs& a, int variant, int sm_count, cudaStre
     switch (variant) {
     case 0: return launch_sweep_t<8, 3>(a, sm_count, s);      // 768 thr/SM
     case 1: return launch_sweep_t<8, 2>(a, sm_count, s);      // 512 thr/SM
-    case 2: return launch_sweep_t<8, 4>(a, sm_count, s);      // 1024 thr/SM
+    case 2:                                                   // 1024 thr/SM
+        if (a.fmask) {                                        // edited guides with their must-match positions: the default variant only
+            if (a.M <= 3) sweep_kernel<8, 4, 4, true><<<sm_count * 4, 8 * 32, 0, s>>>(a);
+            else if (a.M <= 4) sweep_kernel<8, 4, 5, true><<<sm_count * 4, 8 * 32, 0, s>>>(a);
+            else return cudaErrorInvalidValue;
+            return cudaGetLastError();
+        }
+        return launch_sweep_t<8, 4>(a, sm_count, s);
     case 3: return launch_sweep_t<8, 6>(a, sm_count, s);      // 1536 thr/SM
     case 4: return launch_sweep_t<8, 8>(a, sm_count, s);      // 2048 thr/SM
     case 5: return launch_sweep_t<8, 5>(a, sm_count, s);      // 1280 thr/SM
@@ -1118,7 +1133,7 @@ cudaError_t launch_sweep(const SweepArgs& a, int variant, int sm_count, cudaStre
 //   seg[3 * n_seg] = number of edited guides of the chunk;  doff[qlen]: start of the op lists for guides of that length
 __global__ void variant_expand_kernel(const GuideRec* __restrict__ guides, uint32_t n_seg, const uint32_t* __restrict__ seg,
                                       const uint32_t* __restrict__ descs, const uint32_t* __restrict__ doff,
-                                      uint64_t* __restrict__ vq, uint32_t* __restrict__ vdesc, uint32_t* __restrict__ vguide) {
+                                      uint64_t* __restrict__ vq, uint32_t* __restrict__ vdesc, uint32_t* __restrict__ vguide, uint32_t* __restrict__ vfmask) {
     const uint32_t n_v = seg[3u * n_seg];
     for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < n_v; v += gridDim.x * blockDim.x) {
         uint32_t lo = 0, hi = n_seg;                                 // last segment starting at or before v
@@ -1127,13 +1142,14 @@ __global__ void variant_expand_kernel(const GuideRec* __restrict__ guides, uint3
         const GuideRec& g = guides[gi];
         const uint32_t desc = descs[doff[g.qlen] + seg[3u * lo + 2u] + (v - seg[3u * lo])];
         vq[v] = variant_pack(g.q, g.qlen, desc); vdesc[v] = desc; vguide[v] = gi;
+        if (vfmask) vfmask[v] = variant_forced_mask(g.qlen, desc);
     }
 }
 cudaError_t launch_variant_expand(const GuideRec* guides, uint32_t n_seg, uint32_t n_v, const uint32_t* seg, const uint32_t* descs,
-                                  const uint32_t* doff, uint64_t* vq, uint32_t* vdesc, uint32_t* vguide, cudaStream_t s) {
+                                  const uint32_t* doff, uint64_t* vq, uint32_t* vdesc, uint32_t* vguide, uint32_t* vfmask, cudaStream_t s) {
     if (!n_v) return cudaSuccess;
     long b = ((long)n_v + 255) / 256; if (b > 148 * 8) b = 148 * 8;
-    variant_expand_kernel<<<(int)b, 256, 0, s>>>(guides, n_seg, seg, descs, doff, vq, vdesc, vguide);
+    variant_expand_kernel<<<(int)b, 256, 0, s>>>(guides, n_seg, seg, descs, doff, vq, vdesc, vguide, vfmask);
     return cudaGetLastError();
 }
 

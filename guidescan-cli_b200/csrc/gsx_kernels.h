@@ -51,6 +51,9 @@ struct SearchArgs {
     // that holds a row whose BWT symbol is not A/C/G/T (occ(A) is corrected from the exception table only there); 0 = off
     uint32_t exc;
     const uint32_t* exc_map[2];
+    // edited guides (bulges): per guide, the must-match positions as an index mask (gsx_core.h variant_forced_mask); the sweep
+    // skips the patterns that substitute them; nullptr = off
+    const uint32_t* fmask;
 };
 
 struct SweepArgs {
@@ -68,6 +71,7 @@ struct SweepArgs {
     SeedNode* queue; uint32_t queue_cap;
     uint32_t* queue_count; uint32_t* item_counter; uint32_t* error_flag;
     unsigned long long* stats;         // [0] nodes [1] lookups (reference unit) [5] summary sectors loaded
+    const uint32_t* fmask;             // as SearchArgs::fmask (nullptr = off)
 };
 
 struct LocateArgs {
@@ -111,7 +115,7 @@ cudaError_t launch_sweep_guides(const SweepArgs& a, cudaStream_t s);      // per
 cudaError_t launch_sweep(const SweepArgs& a, int variant, int sm_count, cudaStream_t s);
 // bulges as edited guides (gsx_core.h variant_rewrite)
 cudaError_t launch_variant_expand(const GuideRec* guides, uint32_t n_seg, uint32_t n_v, const uint32_t* seg, const uint32_t* descs,
-                                  const uint32_t* doff, uint64_t* vq, uint32_t* vdesc, uint32_t* vguide, cudaStream_t s);
+                                  const uint32_t* doff, uint64_t* vq, uint32_t* vdesc, uint32_t* vguide, uint32_t* vfmask, cudaStream_t s);
 cudaError_t launch_variant_rewrite(const MatchRec* vm, uint32_t n_vm, const GuideRec* guides, const uint32_t* vdesc, const uint32_t* vguide,
                                    MatchRec* out, uint32_t out_cap, uint32_t* out_count, uint32_t* guide_nmatch, uint32_t* error_flag, cudaStream_t s);
 // ordering of batches with thousands of matches per guide (gsx_arrange.cu): three stable radix-sort passes instead of the

@@ -43,6 +43,8 @@ static DevStrand view_of(const HostStrand& h) {
 static std::vector<uint64_t> g_look[2];     // 12 words per block: hi1, lo1, ..., hi6, lo6
 static bool g_prune = false;
 static bool g_fused = false;     // alternative PAMs in one pass (gsx_core.h fused_pam_ok), as gsx_enumerate does under GSX_FUSED_PAMS=1
+static bool g_forced = false;    // the sweep skips patterns that substitute an inserted position of an edited guide (sweep_kernel<..., FORCED>)
+static std::vector<uint32_t> g_vfmask;
 static bool g_variants = false;  // bulges through edited guides (gsx_core.h variant_rewrite), as gsx_enumerate does when Prepared::variant_ok
 
 static std::vector<uint64_t> g_tail[2];     // 4 words per block: hi7, lo7, hi8, lo8 (the scratch planes the summaries' sum2 is built from)
@@ -265,6 +267,7 @@ static void sweep_host(const DevStrand st[2], const Prepared& prep, uint32_t M) 
                 const uint32_t h = sweep_slice_distance(q, L, sb, beta);
                 if (h > M) continue;
                 const uint32_t B = M - h;
+                const uint32_t fm = (g_forced && g < g_vfmask.size() ? g_vfmask[g] : 0u) & (L >= 16 ? ~0u : ((1u << (2 * L)) - 1u));
                 for (int zero = 1; zero >= 0; zero--) {
                     const uint32_t n_pat = plan.xcnt[zero][B];
                     for (uint32_t t = 0; t < n_pat; t++) {
@@ -272,6 +275,7 @@ static void sweep_host(const DevStrand st[2], const Prepared& prep, uint32_t M) 
                         const uint32_t idx = sweep_pattern(plan, masks.data(), (uint32_t)zero, q, beta, B, t, used);
                         if (zero && used != B) { fprintf(stderr, "pass 1 pattern keeps budget\n"); exit(3); }
                         const uint32_t mm = h + used;
+                        if (!forced_kept(idx, q, fm)) continue;              // (the kernel: slice check + xor word check)
                         seen[g].push_back({idx, mm});
                         const FtabEntry& e = g_ftab[strand][idx];
                         if (!e.width) continue;
@@ -314,7 +318,9 @@ static void sweep_host(const DevStrand st[2], const Prepared& prep, uint32_t M) 
             std::vector<std::pair<uint32_t, uint32_t>> want; const uint64_t q = prep.gq[g];
             for (uint64_t combo : combos) {
                 uint32_t idx, j; uint64_t key; ftab_apply(combo, q, L, ftab_exact_index(q, L), g_pow5, idx, key, j);
-                for (uint32_t e = 0; e < 16; e++) { uint64_t k2 = key; uint32_t extra = ftab_beginning(e, q, L, g_pow5, k2); if (j + extra <= M) want.push_back({(idx & ~15u) | e, j + extra}); }
+                for (uint32_t e = 0; e < 16; e++) { uint64_t k2 = key; uint32_t extra = ftab_beginning(e, q, L, g_pow5, k2);
+                    const uint32_t fmg = (g_forced && g < g_vfmask.size() ? g_vfmask[g] : 0u) & (L >= 16 ? ~0u : ((1u << (2 * L)) - 1u));
+                    if (j + extra <= M && forced_kept((idx & ~15u) | e, q, fmg)) want.push_back({(idx & ~15u) | e, j + extra}); }
             }
             std::sort(want.begin(), want.end()); std::sort(seen[g].begin(), seen[g].end());
             if (want != seen[g]) { fprintf(stderr, "sweep enumeration differs from the per-guide enumeration for guide %zu (%zu vs %zu patterns)\n", g, seen[g].size(), want.size()); exit(3); }
@@ -403,6 +409,7 @@ int main(int argc, char** argv) {
         else if (a == "--sweep") g_sweep_sb = atoi(argv[++i]);
         else if (a == "--variants") g_variants = true;
         else if (a == "--fused") g_fused = true;
+        else if (a == "--forced") g_forced = true;
         else if (a == "--sam") sam = true; else if (a == "--succinct") complete = false; else if (a == "-a") alts.push_back(argv[++i]);
         else { fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
     }
@@ -452,6 +459,7 @@ int main(int argc, char** argv) {
                 GuideRec e = r; e.qlen = (uint8_t)(v >> 58);
                 for (uint32_t l = 0; l < e.qlen; l++) e.q[l] = (uint8_t)((v >> (2 * l)) & 3u);
                 vprep.recs.push_back(e); vprep.gq.push_back(v); vdesc.push_back(desc);
+                g_vfmask.push_back(variant_forced_mask(r.qlen, desc));
             }
             voff[g + 1] = (uint32_t)vdesc.size();
         }

@@ -138,3 +138,20 @@ def test_alternative_pams_in_one_pass_match_golden(harness, golden_dir, golden_i
                                                                 "sweep": ["--lookahead", "--ftab", "8", "--sweep", "2"]}[mirror]
     subprocess.check_call([harness, golden_index["g200k"], gcsv, out] + variant_cli_args(kw) + extra, stderr=subprocess.DEVNULL)
     assert open(out).read() == slice_of(golden_output("g200k", variant).decode(), kw.get("fmt") == "sam")
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("variant", [v for v in BULGE_VARIANTS if "_d" in v and "r2" not in v and "alt" not in v])
+def test_sweep_skips_patterns_that_substitute_an_inserted_position(harness, golden_dir, golden_index, tmp_path, variant):
+    """gsx_core.h variant_forced_mask / forced_kept (sweep_kernel<..., FORCED>, GSX_FORCED_SWEEP=1): an inserted position of an
+    edited guide must match exactly, so the sweep need not visit patterns that substitute it -- same text, fewer nodes"""
+    kw = golden_manifest()["cases"]["g200k"]["variants"][variant]["opts"]
+    gcsv, slice_of = _golden_subset("g200k", str(tmp_path), lambda f: f[2] == "NGG" and set(f[1]) <= set("ACGT"))
+    nodes = {}
+    for tag, extra in (("all", []), ("forced", ["--forced"])):
+        out = os.path.join(tmp_path, tag + ".out")
+        r = subprocess.run([harness, golden_index["g200k"], gcsv, out] + variant_cli_args(kw) + ["--variants", "--lookahead", "--ftab", "8", "--sweep", "2"] + extra,
+                           capture_output=True, text=True, check=True)
+        assert open(out).read() == slice_of(golden_output("g200k", variant).decode(), kw.get("fmt") == "sam")
+        nodes[tag] = int(r.stderr.split(" guides, ")[1].split(" nodes")[0])
+    assert nodes["forced"] <= nodes["all"] and (kw.get("mismatches", 3) == 0 or nodes["forced"] < nodes["all"]), nodes

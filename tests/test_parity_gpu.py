@@ -176,6 +176,19 @@ def test_specialised_kernels_on_a_genome_with_n(gsx, gpu_index, tmp_path, monkey
     assert open(out).read() == slice_of(golden_output("g150kN", variant).decode(), kw.get("fmt") == "sam")
 
 
+@pytest.mark.skipif(os.environ.get("GSX_TEST_PENDING") != "1", reason="GSX_FORCED_SWEEP path: host-mirrored at the end of round 1, first GPU run pending (set GSX_TEST_PENDING=1)")
+@pytest.mark.parametrize("variant", [v for v in BULGE_GOLDEN if "_d" in v and "r2" not in v])
+def test_sweep_skips_substituted_insert_positions(gsx, gpu_index, tmp_path, monkeypatch, variant):
+    """sweep_kernel<..., FORCED>: edited guides with their must-match positions, sweep forced on"""
+    monkeypatch.setenv("GSX_FORCED_SWEEP", "1"); monkeypatch.setenv("GSX_SWEEP_MIN", "1")
+    kw = golden_manifest()["cases"]["g200k"]["variants"][variant]["opts"]
+    gcsv, slice_of = _ngg_subset(tmp_path)
+    out = os.path.join(tmp_path, "g.out")
+    _, ctr = gpu_index("g200k").enumerate_file(gcsv, out, _params(gsx, kw), fmt=kw.get("fmt", "csv"), mode=kw.get("mode", "complete"))
+    assert ctr["edited_guides"] > 0
+    assert open(out).read() == slice_of(golden_output("g200k", variant).decode(), kw.get("fmt") == "sam")
+
+
 @pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
 def test_every_search_kernel_variant(gsx, gpu_index, golden_dir, tmp_path, variant, monkeypatch):
     monkeypatch.setenv("GSX_SEARCH_VARIANT", str(variant))

@@ -14,3 +14,11 @@ for on in 0 1; do
   GSX_FAST_ON_N=$on timeout 900 python bench.py --n-runs 300 --guides-per-step 200000 --steps 2 --warmup 3 --cpu-sample 2000 --no-file-e2e > gpurun_out/bench_r2a_nruns_fast$on.json 2> gpurun_out/bench_r2a_nruns_fast$on.err
   tail -2 gpurun_out/bench_r2a_nruns_fast$on.err; cut -c1-400 gpurun_out/bench_r2a_nruns_fast$on.json
 done
+#  4. pending paths: forced-position pruning of the sweep (tests, then the bulge bench with and without it)
+GSX_TEST_PENDING=1 timeout 300 python -m pytest tests/test_parity_gpu.py -m gpu -q -k "substituted_insert" > gpurun_out/pytest_gpu_r2a_pending.log 2>&1; tail -3 gpurun_out/pytest_gpu_r2a_pending.log
+for forced in 0 1; do
+  GSX_FORCED_SWEEP=$forced timeout 600 python bench.py --rna-bulges 1 --dna-bulges 1 --guides-per-step 2048 --steps 2 --warmup 3 --cpu-sample 16 --no-file-e2e > gpurun_out/bench_r2a_cfg3_forced$forced.json 2> gpurun_out/bench_r2a_cfg3_forced$forced.err
+  cut -c1-300 gpurun_out/bench_r2a_cfg3_forced$forced.json
+done
+#  5. headline with two host threads taking turns on the device
+timeout 600 python bench.py --steps 6 --warmup 3 --e2e-threads 2 --no-file-e2e --no-cpu-baseline > gpurun_out/bench_r2a_e2e_threads2.json 2> gpurun_out/bench_r2a_e2e_threads2.err; cut -c1-900 gpurun_out/bench_r2a_e2e_threads2.json
