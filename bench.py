@@ -295,10 +295,7 @@ def run_gsx(args):
             "metric": METRIC, "value": total_guides / (dev_ms * 1e-3), "unit": "guides/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": {"workload": "%.0f Mb uniform-random synthetic genome (seed %d, %d chr, planted 1-4 mismatch copies), "
-                                   "%d NGG 20-mer guides per GPU per step, mismatches=%d, both strand indexes, locate + CFD + specificity"
-                                   % (args.genome_mb, args.seed, args.n_chr, per, args.mismatches),
-                       "genome_mb": args.genome_mb, "guides_per_gpu_per_step": per, "mismatches": args.mismatches, "alt_pams": list(args.alt_pam), "rna_bulges": args.rna_bulges, "dna_bulges": args.dna_bulges,
+            "config": {**workload_config(args),
                        "index": how, "sa_sample_rows": 1 << args.sa_shift, "parallelism": "guides sharded x%d, index replicated" % world, "e2e_host_threads": args.e2e_threads,
                        "l2": "index (%.2f GB) is far larger than L2; every step uses new guides" % (ix.device_bytes / 1e9)},
             "e2e": {"value": total_guides / e2e_s, "unit": "guides/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": int(d2h_bytes),
@@ -350,6 +347,15 @@ def file_e2e(ix, gsx, params, args, kmers, workdir, n_max, hits_per_guide):
     os.remove(out)
     return {"value": n / dt, "unit": "guides/s", "guides": n, "seconds": dt, "output_bytes": size, "output_mb_per_s": size / dt / 1e6,
             "device_ms": ctr["ms_total_device"], "what": "gsx_enumerate_file: guides CSV in, CSV text out (complete mode), host threads format batch k while the GPU runs batch k+1"}
+
+
+def workload_config(args):
+    """the workload both arms are quoted on (BASELINE.json configs[2] shape on one GPU unless options say otherwise)"""
+    return {"workload": "%.0f Mb uniform-random synthetic genome (seed %d, %d chr, planted 1-4 mismatch copies), "
+                        "%d NGG 20-mer guides per GPU per step, mismatches=%d, both strand indexes, locate + CFD + specificity"
+                        % (args.genome_mb, args.seed, args.n_chr, args.guides_per_step, args.mismatches),
+            "genome_mb": args.genome_mb, "guides_per_gpu_per_step": args.guides_per_step, "mismatches": args.mismatches,
+            "alt_pams": list(args.alt_pam), "rna_bulges": args.rna_bulges, "dna_bulges": args.dna_bulges}
 
 
 def write_sample_csv(path, kmers, n):
@@ -439,7 +445,7 @@ def run_reference(args):
     cb.pop("out"); cb.pop("csv")
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "guides/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": "%.0f Mb uniform-random synthetic genome (seed %d), NGG 20-mer guides, mismatches=%d" % (args.genome_mb, args.seed, args.mismatches)},
+            "config": {**workload_config(args), "sample": "the reference arm runs a bounded sample of this workload (cpu_baseline.sample)"},
             "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "guides/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
