@@ -102,7 +102,11 @@ def dist_setup(n_gpus):
     local = int(os.environ.get("LOCAL_RANK", 0))
     dist = None
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("GSX_NCCL_DEBUG", "WARN")     # (the VERSION banner would land on stdout, next to the JSON line)
+        # NCCL carries the barrier and the timing reductions only.  Its INFO lines (rank count, transports) go to a side file so that
+        # stdout holds the JSON line alone; a level set by the caller is respected
+        os.environ.setdefault("NCCL_DEBUG", os.environ.get("GSX_NCCL_DEBUG", "INFO"))
+        os.environ.setdefault("NCCL_DEBUG_FILE", os.path.join(os.environ.get("GSX_BENCH_DIR", "/tmp/gsx_bench"), "nccl_%h_%p.log"))
+        os.makedirs(os.environ.get("GSX_BENCH_DIR", "/tmp/gsx_bench"), exist_ok=True)
         import torch
         import torch.distributed as dist_mod
         torch.cuda.set_device(local)
@@ -243,34 +247,29 @@ def run_gsx(args):
     dev_ms = search_ms = 0.0
     ctr_tot = {}
     d2h_bytes = 0
-    acc_lock = threading.Lock()
-
-    def one_step(s):
-        nonlocal dev_ms, search_ms, d2h_bytes
-        r = ix.enumerate_raw(steps[s][0], per, params)
-        c = r.counters()
-        spec_sum = float(r.guide_arrays()["specificity"].sum())       # the step's result is read on the host
-        with acc_lock:
-            dev_ms += c["ms_total_device"]; search_ms += c["ms_search"]
-            for k, v in c.items():
-                ctr_tot[k] = ctr_tot.get(k, 0) + v
-            d2h_bytes = r.n_guides * (1 + 4 + 4 + 4 + 1 + 4 * (args.mismatches + 1)) + r.n_hits * (8 + 4 + 4 + 4 + 6 + 4 + 4) + c["matches"] * 32
-        r.close()
-        return spec_sum
-
     timed = list(range(args.warmup, args.warmup + args.steps))
-    if args.e2e_threads <= 1:
-        for s in timed:
-            one_step(s)
-    else:
-        # opt-in: the public call from several host threads (as the reference's own worker threads would make it); the library
-        # serialises the device section (GSX_DEVICE_LOCK) and the rest of one call overlaps another call's kernels
-        os.environ["GSX_DEVICE_LOCK"] = "1"
-        workers = [threading.Thread(target=lambda t=t: [one_step(s) for s in timed[t::args.e2e_threads]]) for t in range(args.e2e_threads)]
-        for w in workers:
-            w.start()
-        for w in workers:
-            w.join()
+    # the public call in its two-slot form (gsx_enumerate_start / gsx_enumerate_wait): up to --e2e-pipeline batches in flight, so
+    # that batch k's copies to the host and the read of its result run under batch k+1's kernels (the device section of the
+    # calls takes turns inside the library); 1 = one plain call after the other
+    pend = []
+
+    def finish(h):
+        nonlocal dev_ms, search_ms, d2h_bytes
+        r = ix.enumerate_wait(h)
+        c = r.counters()
+        float(r.guide_arrays()["specificity"].sum())                      # the step's result is read on the host
+        dev_ms += c["ms_total_device"]; search_ms += c["ms_search"]
+        for k, v in c.items():
+            ctr_tot[k] = ctr_tot.get(k, 0) + v
+        d2h_bytes = r.n_guides * (1 + 4 + 4 + 4 + 1 + 4 * (args.mismatches + 1)) + r.n_hits * (8 + 4 + 4 + 4 + 6 + 4 + 4) + c["matches"] * 32
+        r.close()
+
+    for s in timed:
+        pend.append(ix.enumerate_start(steps[s][0], per, params))
+        if len(pend) >= max(1, args.e2e_pipeline):
+            finish(pend.pop(0))
+    while pend:
+        finish(pend.pop(0))
     barrier_sync(dist, local)
     e2e_s = time.perf_counter() - t0
     clocks = sampler.finish() if sampler else None
@@ -296,7 +295,8 @@ def run_gsx(args):
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {**workload_config(args),
-                       "index": how, "sa_sample_rows": 1 << args.sa_shift, "parallelism": "guides sharded x%d, index replicated" % world, "e2e_host_threads": args.e2e_threads,
+                       "index": how, "sa_sample_rows": 1 << args.sa_shift, "parallelism": "guides sharded x%d, index replicated" % world, "e2e_batches_in_flight": max(1, args.e2e_pipeline),
+                       "plant_guides": min(per * world * (args.steps + args.warmup), args.plant_guides), "index_open_seconds": list(ix.open_seconds()),
                        "l2": "index (%.2f GB) is far larger than L2; every step uses new guides" % (ix.device_bytes / 1e9)},
             "e2e": {"value": total_guides / e2e_s, "unit": "guides/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": int(d2h_bytes),
                     "ms_per_step": e2e_s * 1e3 / args.steps},
@@ -351,9 +351,10 @@ def file_e2e(ix, gsx, params, args, kmers, workdir, n_max, hits_per_guide):
 
 def workload_config(args):
     """the workload both arms are quoted on (BASELINE.json configs[2] shape on one GPU unless options say otherwise)"""
-    return {"workload": "%.0f Mb uniform-random synthetic genome (seed %d, %d chr, planted 1-4 mismatch copies), "
+    return {"workload": "%.0f Mb uniform-random synthetic genome (seed %d, %d chr; 1-4 mismatch copies planted for the first %d guides, "
+                        "the other guides' ~12 hits each are the chance hits of a random genome), "
                         "%d NGG 20-mer guides per GPU per step, mismatches=%d, both strand indexes, locate + CFD + specificity"
-                        % (args.genome_mb, args.seed, args.n_chr, args.guides_per_step, args.mismatches),
+                        % (args.genome_mb, args.seed, args.n_chr, args.plant_guides, args.guides_per_step, args.mismatches),
             "genome_mb": args.genome_mb, "guides_per_gpu_per_step": args.guides_per_step, "mismatches": args.mismatches,
             "alt_pams": list(args.alt_pam), "rna_bulges": args.rna_bulges, "dna_bulges": args.dna_bulges}
 
@@ -478,7 +479,7 @@ def parse_args(argv=None):
     ap.add_argument("--cpu-sample", type=int, default=8000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-file-e2e", action="store_true")
-    ap.add_argument("--e2e-threads", type=int, default=1, help="host threads issuing the timed steps (opt-in; 1 = one call after the other)")
+    ap.add_argument("--e2e-pipeline", type=int, default=2, help="batches in flight in the end-to-end loop (gsx_enumerate_start / _wait); 1 = one call after the other")
     ap.add_argument("--n-runs", type=int, default=0, help="insert this many runs of N (1..50000 bases) into the genome after the guides were sampled and planted")
     ap.add_argument("--sweep-variants", default="")
     ap.add_argument("--variant", default=None, help="f<k> specialised kernel variant k, g<k> general kernel variant k")

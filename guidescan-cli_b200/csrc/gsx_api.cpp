@@ -41,12 +41,117 @@ extern "C" void gsx_params_default(gsx_params* p) {
 // ---------------------------------------------------------------------------------------------------------
 // index
 // ---------------------------------------------------------------------------------------------------------
-template <class T> static void* upload(const std::vector<T>& v, uint64_t& bytes) {
+template <class T> static void* upload(const std::vector<T>& v, size_t& n_bytes, uint64_t& total) {
     void* d = nullptr; size_t n = std::max<size_t>(v.size(), 1) * sizeof(T);
     CK(cudaMalloc(&d, n));
     if (!v.empty()) CK(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
-    bytes += n;
+    n_bytes = n; total += n;
     return d;
+}
+
+static double seconds_since(std::chrono::steady_clock::time_point t0) { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
+
+// device pointers of a strand -> the view the kernels take
+static void bind_strand(DeviceStrand& d) {
+    d.d.blocks = (const OccBlock*)d.blocks; d.d.sa_samples = (const uint32_t*)d.sa;
+    d.d.exc_rows = (const uint32_t*)d.exc_rows; d.d.exc_lf = (const uint32_t*)d.exc_lf; d.d.n_rows = (const uint32_t*)d.n_rows;
+    d.d.lines = (const unsigned char*)d.lines; d.d.sum0 = (const unsigned char*)d.sum0; d.d.sum1 = (const unsigned char*)d.sum1;
+    d.d.sum2 = (const unsigned char*)d.sum2; d.d.ftab = d.ftab;
+}
+
+// The whole index on ONE device: the host arrays go up, everything else (jump table, look-ahead lines, pattern summaries: 64 of
+// the 69 GB of a 3.1 Gb genome) is derived there by kernels.
+static void build_device_index(gsx_index* ix, DeviceIndex& di) {
+    CK(cudaSetDevice(di.device));
+    cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, di.device));
+    di.sm_count = prop.multiProcessorCount;
+    CK(upload_cfd_tables());
+    for (int s = 0; s < 2; s++) {
+        const HostStrand& h = ix->host.st[s];
+        DeviceStrand& d = di.st[s];
+        d.blocks = upload(h.blocks, d.blocks_bytes, di.bytes); d.sa = upload(h.sa_samples, d.sa_bytes, di.bytes);
+        d.exc_rows = upload(h.exc_rows, d.exc_rows_bytes, di.bytes); d.exc_lf = upload(h.exc_lf, d.exc_lf_bytes, di.bytes);
+        d.n_rows = upload(h.n_rows, d.n_rows_bytes, di.bytes);
+        d.exc_map = upload(build_exc_map(h), d.exc_map_bytes, di.bytes);
+        bind_strand(d);
+        d.d.n = (uint32_t)h.n; d.d.n_exc = (uint32_t)h.exc_rows.size(); d.d.n_nrows = (uint32_t)h.n_rows.size();
+        d.d.sa_shift = h.sa_shift;
+        for (int c = 0; c < 5; c++) d.d.C[c] = h.C[c];
+        d.d.exc_lo = h.exc_rows.empty() ? 0xFFFFFFFFu : h.exc_rows.front();
+        d.d.exc_hi = h.exc_rows.empty() ? 0u : h.exc_rows.back();
+        d.d.blk_shift = 5; d.d.ftab_L = 0;
+        {
+            // k-mer jump table: depth L such that a level-L interval still holds a handful of rows
+            int L = env_int("GSX_FTAB", -1);
+            if (L < 0) { L = 0; uint64_t v = h.n; while (v >= 4) { v >>= 2; L++; } L -= 1; if (L > 14) L = 14; if (L < 6) L = 0; }
+            if (L > 16) L = 16;
+            if (L >= 4) {
+                void* tmp = nullptr;
+                d.ftab_bytes = (size_t)8 << (2 * L);
+                CK(cudaMalloc(&d.ftab, d.ftab_bytes));
+                CK(cudaMalloc(&tmp, d.ftab_bytes));
+                CK(launch_build_ftab(d.d, (uint32_t)L, d.ftab, tmp, 0));
+                CK(cudaDeviceSynchronize());
+                cudaFree(tmp);
+                d.d.ftab = d.ftab; d.d.ftab_L = (uint32_t)L; di.bytes += d.ftab_bytes;
+            }
+        }
+        if (env_int("GSX_LOOKAHEAD", 1)) {
+            // second copy for narrow intervals: one 128-byte line per 64 rows = OccBlock + look-ahead planes t1..t6,
+            // derived on the device by LF walks over the packed blocks (t7, t8 into a scratch array for the summaries)
+            const uint32_t nb = (uint32_t)h.blocks.size();
+            const bool summaries = d.d.ftab && env_int("GSX_SWEEP_SUMMARY", 1);
+            void* tail = nullptr;
+            d.lines_bytes = (size_t)nb * 128;
+            CK(cudaMalloc(&d.lines, d.lines_bytes));
+            if (summaries && env_int("GSX_SWEEP_TAIL", 1)) CK(cudaMalloc(&tail, (size_t)nb * 32));
+            CK(launch_build_lookahead(d.d, (unsigned char*)d.lines, (unsigned char*)tail, nb, 0));
+            CK(cudaDeviceSynchronize());
+            d.d.lines = (const unsigned char*)d.lines; di.bytes += d.lines_bytes;
+            if (summaries) {
+                // pattern summaries for the slice-major front end (sweep_kernel): 2 x 32 (+ 16) bytes per jump-table entry
+                const uint64_t n_entries = 1ull << (2 * d.d.ftab_L);
+                d.sum0_bytes = d.sum1_bytes = n_entries * 32;
+                CK(cudaMalloc(&d.sum0, d.sum0_bytes)); CK(cudaMalloc(&d.sum1, d.sum1_bytes));
+                if (tail) { d.sum2_bytes = n_entries * 16; CK(cudaMalloc(&d.sum2, d.sum2_bytes)); }
+                CK(launch_build_summary(d.ftab, (const unsigned char*)d.lines, (const unsigned char*)tail, (unsigned char*)d.sum0,
+                                        (unsigned char*)d.sum1, (unsigned char*)d.sum2, n_entries, 0));
+                CK(cudaDeviceSynchronize());
+                di.bytes += n_entries * (tail ? 80 : 64);
+            }
+            cudaFree(tail);
+        }
+        bind_strand(d);
+    }
+    size_t cb = 0;
+    di.chroms = (Chrom*)upload(ix->chroms, cb, di.bytes);
+}
+
+// A further device receives the finished arrays of the first one by peer copies (NVLink / NVSwitch: 69 GB in well under a
+// second per device; staged through the host by the driver where peer access is not available) instead of deriving them
+// again -- 64 of the 69 GB of a 3.1 Gb index are derived data and took ~35 s per device.
+static void replicate_device_index(const gsx_index* ix, const DeviceIndex& src, DeviceIndex& dst, cudaStream_t stream) {
+    CK(cudaSetDevice(dst.device));
+    cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, dst.device));
+    dst.sm_count = prop.multiProcessorCount;
+    CK(upload_cfd_tables());
+    int can = 0;
+    if (cudaDeviceCanAccessPeer(&can, dst.device, src.device) == cudaSuccess && can) {
+        cudaError_t e = cudaDeviceEnablePeerAccess(src.device, 0);
+        if (e != cudaSuccess) cudaGetLastError();                            // (already enabled / not supported: the copy still works)
+    }
+    for (int s = 0; s < 2; s++) {
+        const DeviceStrand& a = src.st[s]; DeviceStrand& d = dst.st[s];
+        d.d = a.d;
+#define GSX_COPY(name) if (a.name) { d.name##_bytes = a.name##_bytes; CK(cudaMalloc(&d.name, d.name##_bytes)); \
+                                     CK(cudaMemcpyPeerAsync(d.name, dst.device, a.name, src.device, d.name##_bytes, stream)); dst.bytes += d.name##_bytes; }
+        GSX_STRAND_ARRAYS(GSX_COPY)
+#undef GSX_COPY
+        bind_strand(d);
+    }
+    const size_t cb = std::max<size_t>(ix->chroms.size(), 1) * sizeof(Chrom);
+    CK(cudaMalloc(&dst.chroms, cb));
+    CK(cudaMemcpyPeerAsync(dst.chroms, dst.device, src.chroms, src.device, cb, stream)); dst.bytes += cb;
 }
 
 static void upload_index(gsx_index* ix, const int* devices, int n_devices) {
@@ -55,75 +160,45 @@ static void upload_index(gsx_index* ix, const int* devices, int n_devices) {
     for (size_t i = 0; i < ix->host.chr_lens.size(); i++) { ix->chroms.push_back({start, ix->host.chr_lens[i]}); start += ix->host.chr_lens[i]; }
     std::vector<int> devs;
     if (!devices || n_devices <= 0) devs.push_back(0); else devs.assign(devices, devices + n_devices);
-    for (int dv : devs) {
-        DeviceIndex di; di.device = dv;
-        CK(cudaSetDevice(dv));
-        cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, dv));
-        di.sm_count = prop.multiProcessorCount;
-        CK(upload_cfd_tables());
-        for (int s = 0; s < 2; s++) {
-            const HostStrand& h = ix->host.st[s];
-            DeviceStrand& d = di.st[s];
-            d.blocks = upload(h.blocks, di.bytes); d.sa = upload(h.sa_samples, di.bytes);
-            d.exc_rows = upload(h.exc_rows, di.bytes); d.exc_lf = upload(h.exc_lf, di.bytes); d.n_rows = upload(h.n_rows, di.bytes);
-            d.exc_map = upload(build_exc_map(h), di.bytes);
-            d.d.blocks = (const OccBlock*)d.blocks; d.d.sa_samples = (const uint32_t*)d.sa;
-            d.d.exc_rows = (const uint32_t*)d.exc_rows; d.d.exc_lf = (const uint32_t*)d.exc_lf; d.d.n_rows = (const uint32_t*)d.n_rows;
-            d.d.n = (uint32_t)h.n; d.d.n_exc = (uint32_t)h.exc_rows.size(); d.d.n_nrows = (uint32_t)h.n_rows.size();
-            d.d.sa_shift = h.sa_shift;
-            for (int c = 0; c < 5; c++) d.d.C[c] = h.C[c];
-            d.d.exc_lo = h.exc_rows.empty() ? 0xFFFFFFFFu : h.exc_rows.front();
-            d.d.exc_hi = h.exc_rows.empty() ? 0u : h.exc_rows.back();
-            d.d.blk_shift = 5; d.d.lines = nullptr; d.d.sum0 = nullptr; d.d.sum1 = nullptr; d.d.sum2 = nullptr; d.d.ftab = nullptr; d.d.ftab_L = 0;
-            {
-                // k-mer jump table: depth L such that a level-L interval still holds a handful of rows
-                int L = env_int("GSX_FTAB", -1);
-                if (L < 0) { L = 0; uint64_t v = h.n; while (v >= 4) { v >>= 2; L++; } L -= 1; if (L > 14) L = 14; if (L < 6) L = 0; }
-                if (L > 16) L = 16;
-                if (L >= 4) {
-                    void* tmp = nullptr;
-                    CK(cudaMalloc(&d.ftab, (size_t)8 << (2 * L)));
-                    CK(cudaMalloc(&tmp, (size_t)8 << (2 * L)));
-                    CK(launch_build_ftab(d.d, (uint32_t)L, d.ftab, tmp, 0));
-                    CK(cudaDeviceSynchronize());
-                    cudaFree(tmp);
-                    d.d.ftab = d.ftab; d.d.ftab_L = (uint32_t)L; di.bytes += (uint64_t)8 << (2 * L);
-                }
-            }
-            if (env_int("GSX_LOOKAHEAD", 1)) {
-                // second copy for narrow intervals: one 128-byte line per 64 rows = OccBlock + look-ahead planes t1..t6,
-                // derived on the device by LF walks over the packed blocks (t7, t8 into a scratch array for the summaries)
-                const uint32_t nb = (uint32_t)h.blocks.size();
-                const bool summaries = d.d.ftab && env_int("GSX_SWEEP_SUMMARY", 1);
-                void* tail = nullptr;
-                CK(cudaMalloc(&d.lines, (size_t)nb * 128));
-                if (summaries && env_int("GSX_SWEEP_TAIL", 1)) CK(cudaMalloc(&tail, (size_t)nb * 32));
-                CK(launch_build_lookahead(d.d, (unsigned char*)d.lines, (unsigned char*)tail, nb, 0));
-                CK(cudaDeviceSynchronize());
-                d.d.lines = (const unsigned char*)d.lines; di.bytes += (uint64_t)nb * 128;
-                if (summaries) {
-                    // pattern summaries for the slice-major front end (sweep_kernel): 2 x 32 (+ 16) bytes per jump-table entry
-                    const uint64_t n_entries = 1ull << (2 * d.d.ftab_L);
-                    CK(cudaMalloc(&d.sum0, n_entries * 32)); CK(cudaMalloc(&d.sum1, n_entries * 32));
-                    if (tail) CK(cudaMalloc(&d.sum2, n_entries * 16));
-                    CK(launch_build_summary(d.ftab, (const unsigned char*)d.lines, (const unsigned char*)tail, (unsigned char*)d.sum0,
-                                            (unsigned char*)d.sum1, (unsigned char*)d.sum2, n_entries, 0));
-                    CK(cudaDeviceSynchronize());
-                    d.d.sum0 = (const unsigned char*)d.sum0; d.d.sum1 = (const unsigned char*)d.sum1; d.d.sum2 = (const unsigned char*)d.sum2;
-                    di.bytes += n_entries * (tail ? 80 : 64);
-                }
-                cudaFree(tail);
-            }
-        }
-        di.chroms = (Chrom*)upload(ix->chroms, di.bytes);
-        ix->dev.push_back(di);
+    ix->dev.clear(); ix->dev.reserve(devs.size());
+    auto t0 = std::chrono::steady_clock::now();
+    {
+        DeviceIndex di; di.device = devs[0];
+        ix->dev.push_back(di);                                               // (in the list first: a failure below frees what was allocated)
+        build_device_index(ix, ix->dev[0]);
     }
+    ix->open_seconds[1] = seconds_since(t0);
+    t0 = std::chrono::steady_clock::now();
+    std::vector<cudaStream_t> streams;
+    struct Cleanup { std::vector<cudaStream_t>& s; ~Cleanup() { for (auto x : s) cudaStreamDestroy(x); } } cleanup{streams};
+    for (size_t k = 1; k < devs.size(); k++) {
+        DeviceIndex di; di.device = devs[k];
+        for (size_t j = 0; j < k; j++) if (ix->dev[j].device == devs[k] && ix->dev[j].alias_of < 0) { di.alias_of = (int)j; break; }
+        ix->dev.push_back(di);
+        DeviceIndex& d = ix->dev.back();
+        if (d.alias_of >= 0) {                                               // the same device named twice: two job slots over one copy
+            const DeviceIndex& a = ix->dev[d.alias_of];
+            d.sm_count = a.sm_count; d.st[0] = a.st[0]; d.st[1] = a.st[1]; d.chroms = a.chroms; d.bytes = a.bytes;
+            continue;
+        }
+        CK(cudaSetDevice(d.device));
+        cudaStream_t st; CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking)); streams.push_back(st);
+        replicate_device_index(ix, ix->dev[0], d, st);                       // (asynchronous: all replicas are filled concurrently)
+    }
+    for (auto st : streams) CK(cudaStreamSynchronize(st));
+    ix->open_seconds[2] = seconds_since(t0);
 }
 
 static void free_device_index(DeviceIndex& di) {
+    if (di.alias_of >= 0) return;
     cudaSetDevice(di.device);
-    for (int s = 0; s < 2; s++) { cudaFree(di.st[s].blocks); cudaFree(di.st[s].lines); cudaFree(di.st[s].sum0); cudaFree(di.st[s].sum1); cudaFree(di.st[s].sum2); cudaFree(di.st[s].ftab); cudaFree(di.st[s].sa); cudaFree(di.st[s].exc_rows); cudaFree(di.st[s].exc_lf); cudaFree(di.st[s].n_rows); cudaFree(di.st[s].exc_map); }
-    cudaFree(di.chroms);
+    cudaDeviceSynchronize();                                                 // (peer copies of a failed open may still be in flight)
+    for (int s = 0; s < 2; s++) {
+#define GSX_FREE(name) cudaFree(di.st[s].name); di.st[s].name = nullptr;
+        GSX_STRAND_ARRAYS(GSX_FREE)
+#undef GSX_FREE
+    }
+    cudaFree(di.chroms); di.chroms = nullptr;
 }
 
 static bool file_exists(const std::string& p) { FILE* f = fopen(p.c_str(), "rb"); if (!f) return false; fclose(f); return true; }
@@ -136,30 +211,55 @@ static int check_devices(const int* devices, int n_devices) {
     return GSX_OK;
 }
 
+// every ABI entry point that can throw runs its body through this: nothing but a status code crosses the boundary
+template <class F> static int guarded(F&& body) {
+    try { return body(); }
+    catch (const CudaError& e) { return fail(GSX_ERR_CUDA, e.what()); }
+    catch (const std::bad_alloc&) { return fail(GSX_ERR_NOMEM, "out of host memory"); }
+    catch (const std::exception& e) { return fail(GSX_ERR_INTERNAL, e.what()); }
+    catch (...) { return fail(GSX_ERR_INTERNAL, "unknown exception"); }
+}
+
+static int upload_or_fail(gsx_index* ix, const int* devices, int n_devices, gsx_index** out) {
+    const int rc = guarded([&] { upload_index(ix, devices, n_devices); return (int)GSX_OK; });
+    if (rc) { const std::string msg = g_err; for (auto& d : ix->dev) free_device_index(d); delete ix; return fail(rc, msg); }
+    *out = ix;
+    return GSX_OK;
+}
+
 extern "C" int gsx_index_open(const char* prefix, const int* devices, int n_devices, gsx_index** out) {
     if (!prefix || !out) return fail(GSX_ERR_ARG, "null argument");
     *out = nullptr;
+    std::string p(prefix);
+    const bool sdsl = file_exists(p + ".forward") || !file_exists(p + ".gsx");
+    if (!sdsl || (file_exists(p + ".gs") && file_exists(p + ".forward") && file_exists(p + ".reverse")))
+        if (int rc = check_devices(devices, n_devices)) return rc;           // (before reading gigabytes; missing files are reported first, as the reference does)
     gsx_index* ix = new gsx_index();
-    std::string p(prefix), err;
-    bool ok;
-    if (file_exists(p + ".forward") || !file_exists(p + ".gsx")) {
-        ok = load_genome_structure(p + ".gs", ix->host, err);
-        if (ok && !file_exists(p + ".forward")) { ok = false; err = "No forward index file " + p + ".forward located."; }
-        if (ok && !file_exists(p + ".reverse")) { ok = false; err = "No forward index file " + p + ".reverse located."; }   // sic: src/guidescan.cxx:205
-        if (ok) {
-            std::string e0, e1; bool ok0 = false, ok1 = false;
-            std::thread t0([&] { ok0 = load_sdsl_strand(p + ".forward", ix->host.st[0], e0); });
-            std::thread t1([&] { ok1 = load_sdsl_strand(p + ".reverse", ix->host.st[1], e1); });
-            t0.join(); t1.join();
-            ok = ok0 && ok1; if (!ok) err = ok0 ? e1 : e0;
-        }
-    } else ok = load_gsx(p, ix->host, err);
-    if (!ok) { delete ix; return fail(GSX_ERR_IO, err); }
-    if (int rc = check_devices(devices, n_devices)) { delete ix; return rc; }
-    try { upload_index(ix, devices, n_devices); }
-    catch (const CudaError& e) { for (auto& d : ix->dev) free_device_index(d); delete ix; return fail(GSX_ERR_CUDA, e.what()); }
-    *out = ix;
-    return GSX_OK;
+    const auto t0 = std::chrono::steady_clock::now();
+    const int rc = guarded([&] {
+        std::string err; bool ok;
+        if (sdsl) {
+            ok = load_genome_structure(p + ".gs", ix->host, err);
+            if (ok && !file_exists(p + ".forward")) { ok = false; err = "No forward index file " + p + ".forward located."; }
+            if (ok && !file_exists(p + ".reverse")) { ok = false; err = "No forward index file " + p + ".reverse located."; }   // sic: src/guidescan.cxx:205
+            if (ok) {
+                std::string e0, e1; bool ok0 = false, ok1 = false;
+                auto load = [&](int s, const char* ext, bool& okx, std::string& ex) {
+                    try { okx = load_sdsl_strand(p + ext, ix->host.st[s], ex); }
+                    catch (const std::exception& e) { okx = false; ex = std::string("malformed index file ") + p + ext + " (" + e.what() + ")"; }
+                };
+                std::thread t0([&] { load(0, ".forward", ok0, e0); });
+                std::thread t1([&] { load(1, ".reverse", ok1, e1); });
+                t0.join(); t1.join();
+                ok = ok0 && ok1; if (!ok) err = ok0 ? e1 : e0;
+            }
+        } else ok = load_gsx(p, ix->host, err);
+        return ok ? (int)GSX_OK : fail(GSX_ERR_IO, err);
+    });
+    if (rc) { delete ix; return rc; }
+    ix->open_seconds[0] = seconds_since(t0);
+    if (int rc2 = check_devices(devices, n_devices)) { delete ix; return rc2; }
+    return upload_or_fail(ix, devices, n_devices, out);
 }
 
 static int build_from_text(gsx_index* ix, std::vector<uint8_t>& seq, uint32_t sa_shift, const char* save_prefix,
@@ -168,6 +268,7 @@ static int build_from_text(gsx_index* ix, std::vector<uint8_t>& seq, uint32_t sa
     if (seq.size() + 1 > 0xFFFFFFFFull) { delete ix; return fail(GSX_ERR_ARG, "genome longer than 2^32 - 2 bases"); }
     if (sa_shift > 12) { delete ix; return fail(GSX_ERR_ARG, "sa_shift must be <= 12"); }
     int dev0 = (devices && n_devices > 0) ? devices[0] : 0;
+    const auto t0 = std::chrono::steady_clock::now();
     if (!build_strand_gpu(dev0, seq.data(), seq.size(), sa_shift, ix->host.st[0], err)) { delete ix; return fail(GSX_ERR_CUDA, err); }
     {   // reverse complement of the whole concatenated genome, in place (seq_io.cxx:65-72)
         size_t n = seq.size();
@@ -176,10 +277,8 @@ static int build_from_text(gsx_index* ix, std::vector<uint8_t>& seq, uint32_t sa
     }
     if (!build_strand_gpu(dev0, seq.data(), seq.size(), sa_shift, ix->host.st[1], err)) { delete ix; return fail(GSX_ERR_CUDA, err); }
     if (save_prefix && !save_gsx(save_prefix, ix->host, err)) { delete ix; return fail(GSX_ERR_IO, err); }
-    try { upload_index(ix, devices, n_devices); }
-    catch (const CudaError& e) { for (auto& d : ix->dev) free_device_index(d); delete ix; return fail(GSX_ERR_CUDA, e.what()); }
-    *out = ix;
-    return GSX_OK;
+    ix->open_seconds[0] = seconds_since(t0);
+    return upload_or_fail(ix, devices, n_devices, out);
 }
 
 extern "C" int gsx_index_build(const char* fasta_path, const char* save_prefix, const int* devices, int n_devices, gsx_index** out) {
@@ -188,8 +287,9 @@ extern "C" int gsx_index_build(const char* fasta_path, const char* save_prefix, 
     if (int rc = check_devices(devices, n_devices)) return rc;
     gsx_index* ix = new gsx_index();
     std::string err; std::vector<uint8_t> seq;
-    if (!read_fasta(fasta_path, seq, ix->host, err)) { delete ix; return fail(GSX_ERR_IO, err); }
-    return build_from_text(ix, seq, 6, save_prefix, devices, n_devices, out);
+    const int rc = guarded([&] { return read_fasta(fasta_path, seq, ix->host, err) ? (int)GSX_OK : fail(GSX_ERR_IO, err); });
+    if (rc) { delete ix; return rc; }
+    return guarded([&] { return build_from_text(ix, seq, 6, save_prefix, devices, n_devices, out); });
 }
 
 extern "C" int gsx_index_build_text(const uint8_t* text, uint64_t length, const char* const* chr_names, const uint64_t* chr_lengths,
@@ -202,8 +302,10 @@ extern "C" int gsx_index_build_text(const uint8_t* text, uint64_t length, const 
     uint64_t tot = 0;
     for (uint32_t i = 0; i < n_chr; i++) { ix->host.chr_names.push_back(chr_names[i]); ix->host.chr_lens.push_back(chr_lengths[i]); tot += chr_lengths[i]; }
     ix->host.genome_length = tot;
-    std::vector<uint8_t> seq(text, text + length);
-    return build_from_text(ix, seq, sa_shift, save_prefix, devices, n_devices, out);
+    return guarded([&] {
+        std::vector<uint8_t> seq(text, text + length);
+        return build_from_text(ix, seq, sa_shift, save_prefix, devices, n_devices, out);
+    });
 }
 
 extern "C" int gsx_index_close(gsx_index* ix) {
@@ -219,6 +321,32 @@ extern "C" const char* gsx_index_chromosome_name(const gsx_index* ix, uint32_t i
 extern "C" uint64_t gsx_index_chromosome_length(const gsx_index* ix, uint32_t i) { return ix->host.chr_lens[i]; }
 extern "C" uint64_t gsx_index_device_bytes(const gsx_index* ix) { return ix->dev.empty() ? 0 : ix->dev[0].bytes; }
 extern "C" int gsx_index_n_devices(const gsx_index* ix) { return (int)ix->dev.size(); }
+extern "C" int gsx_index_open_seconds(const gsx_index* ix, double out[3]) {
+    if (!ix || !out) return fail(GSX_ERR_ARG, "null argument");
+    for (int i = 0; i < 3; i++) out[i] = ix->open_seconds[i];
+    return GSX_OK;
+}
+
+extern "C" int gsx_index_device_checksum(const gsx_index* ix, int slot, uint64_t* out) {
+    if (!ix || !out || slot < 0 || slot >= (int)ix->dev.size()) return fail(GSX_ERR_ARG, "bad argument");
+    return guarded([&] {
+        const DeviceIndex& di = ix->dev[slot];
+        CK(cudaSetDevice(di.device));
+        unsigned long long* d_out = nullptr; CK(cudaMalloc(&d_out, 8)); CK(cudaMemset(d_out, 0, 8));
+        unsigned long long seed = 1;
+        for (int s = 0; s < 2; s++) {
+#define GSX_SUM(name) { seed += 0x100; if (di.st[s].name) CK(launch_checksum(di.st[s].name, di.st[s].name##_bytes, seed, d_out, 0)); }
+            GSX_STRAND_ARRAYS(GSX_SUM)
+#undef GSX_SUM
+        }
+        CK(launch_checksum(di.chroms, ix->chroms.size() * sizeof(Chrom), seed + 0x100, d_out, 0));
+        unsigned long long h = 0; CK(cudaMemcpy(&h, d_out, 8, cudaMemcpyDeviceToHost)); cudaFree(d_out);
+        // the scalars the kernels take by value
+        for (int s = 0; s < 2; s++) { const DevStrand& d = di.st[s].d; h += 31ull * d.n + 131ull * d.n_exc + 17ull * d.sa_shift + 7ull * d.ftab_L; for (int c = 0; c < 5; c++) h = h * 1000003ull + d.C[c]; }
+        *out = h;
+        return (int)GSX_OK;
+    });
+}
 
 static uint8_t sym_of(char c) { return c == 'A' ? SYM_A : c == 'C' ? SYM_C : c == 'G' ? SYM_G : c == 'T' ? SYM_T : c == 'N' ? SYM_N : SYM_X; }
 
@@ -610,7 +738,10 @@ static void run_device_job(DeviceJob* job) {
         };
         const uint32_t sweep_sb = use_variants ? 0u : plan_sweep(n, prep.min_qlen, std::max<uint32_t>(p.mismatches, p.threshold > 0 ? (uint32_t)p.threshold : 0u));
         bool use_sweep = sweep_sb != 0;
-        uint64_t queue_cap = std::max<uint64_t>((uint64_t)n * 1024, 1u << 20);
+        // seed queue of the sweep: 12 survivors per guide measured at m = 3 on 3.1 Gb (two orders of magnitude more at m = 4);
+        // sized with a wide margin, never beyond the 32-bit slot numbers the kernels use; an overflow is retried with 4x the room
+        uint64_t queue_cap = std::max<uint64_t>((uint64_t)n * (p.mismatches >= 4 ? 1024 : 256), 1u << 20);
+        queue_cap = std::min<uint64_t>(queue_cap, 1ull << 30);
         if (env_int("GSX_QUEUE_CAP", 0) > 0) queue_cap = (uint64_t)env_int("GSX_QUEUE_CAP", 0);
         SeedNode* d_queue = nullptr;
         uint64_t n_launches = 0;
@@ -663,14 +794,14 @@ static void run_device_job(DeviceJob* job) {
                 launch_fast(m, ng, sb, k == 0 ? ev_mid : nullptr);
             }
         };
-        auto grow_queue = [&]() { B.free_one(d_queue); d_queue = nullptr; queue_cap *= 4; if (queue_cap > (1ull << 31)) throw std::runtime_error("seed queue keeps overflowing"); };
+        auto grow_queue = [&]() { B.free_one(d_queue); d_queue = nullptr; queue_cap *= 4; if (queue_cap >= (1ull << 32)) throw std::runtime_error("seed queue keeps overflowing"); };
 
-        // GSX_DEVICE_LOCK=1 (opt-in, not yet measured): callers on several host threads take turns on the device for the search ..
-        // specificity section, so that one call's guide packing and result copies run under another call's kernels instead of
-        // two sweeps sharing -- and thrashing -- the L2 slices
+        // Calls from several host threads (the reference's own worker threads, or gsx_enumerate_start) take turns on a device for the
+        // search .. specificity section: one call's guide packing, result copies and host-side assembly then run under the next
+        // call's kernels, instead of two sweeps sharing -- and thrashing -- the L2-resident slices.  GSX_DEVICE_LOCK=0 turns it off.
         static std::mutex device_mu[64];
         std::unique_lock<std::mutex> device_turn;
-        if (env_int("GSX_DEVICE_LOCK", 0)) device_turn = std::unique_lock<std::mutex>(device_mu[di.device & 63]);
+        if (env_int("GSX_DEVICE_LOCK", 1)) device_turn = std::unique_lock<std::mutex>(device_mu[di.device & 63]);
         CK(cudaEventRecord(ev[0], s));
         // ---- threshold prefilter (process.hpp:66-76): mismatch-only counting search, guide dropped if > 1 site -----
         if (p.threshold > 0) {
@@ -981,9 +1112,13 @@ void gsx_build_view(gsx_result* r) {
     v.index_id = r->index_id.data(); v.cfd = r->cfd.data(); v.counted = r->counted.data();
 }
 
+static int enumerate_impl(const gsx_index* ix, const gsx_guide* guides, size_t n_guides, const gsx_params* p, gsx_result** out);
 extern "C" int gsx_enumerate(const gsx_index* ix, const gsx_guide* guides, size_t n_guides, const gsx_params* p, gsx_result** out) {
     if (!ix || !p || !out || (!guides && n_guides)) return fail(GSX_ERR_ARG, "null argument");
     *out = nullptr;
+    return guarded([&] { return enumerate_impl(ix, guides, n_guides, p, out); });
+}
+static int enumerate_impl(const gsx_index* ix, const gsx_guide* guides, size_t n_guides, const gsx_params* p, gsx_result** out) {
     if (ix->dev.empty()) return fail(GSX_ERR_NO_DEVICE, "index is not resident on any device");
     if (n_guides >= (1ull << 30)) return fail(GSX_ERR_ARG, "too many guides in one call");
     const auto t_call = std::chrono::steady_clock::now();
@@ -1018,6 +1153,34 @@ extern "C" int gsx_enumerate(const gsx_index* ix, const gsx_guide* guides, size_
     r->counters.ms_wall = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call).count();
     *out = r;
     return GSX_OK;
+}
+
+// ---- two-slot form: the call runs on a library thread, the caller prepares / consumes another batch meanwhile ----------------
+struct gsx_pending {
+    std::thread th; gsx_result* result = nullptr; int status = GSX_OK; std::string err;
+};
+extern "C" int gsx_enumerate_start(const gsx_index* ix, const gsx_guide* guides, size_t n_guides, const gsx_params* p, gsx_pending** out) {
+    if (!ix || !p || !out || (!guides && n_guides)) return fail(GSX_ERR_ARG, "null argument");
+    *out = nullptr;
+    return guarded([&] {
+        gsx_pending* pd = new gsx_pending();
+        try {
+            pd->th = std::thread([=] {
+                pd->status = gsx_enumerate(ix, guides, n_guides, p, &pd->result);
+                if (pd->status) pd->err = g_err;                            // (the message lives in the worker thread's slot)
+            });
+        } catch (...) { delete pd; throw; }
+        *out = pd;
+        return (int)GSX_OK;
+    });
+}
+extern "C" int gsx_enumerate_wait(gsx_pending* pd, gsx_result** out) {
+    if (!pd || !out) return fail(GSX_ERR_ARG, "null argument");
+    if (pd->th.joinable()) pd->th.join();
+    *out = pd->result;
+    const int rc = pd->status; const std::string msg = pd->err;
+    delete pd;
+    return rc ? fail(rc, msg) : (int)GSX_OK;
 }
 
 extern "C" int gsx_result_view_get(const gsx_result* r, gsx_result_view* view) { if (!r || !view) return fail(GSX_ERR_ARG, "null argument"); *view = r->view; return GSX_OK; }

@@ -44,14 +44,19 @@ bool read_fasta(const std::string& path, std::vector<uint8_t>& seq, HostIndex& i
 bool save_gsx(const std::string& prefix, const HostIndex& ix, std::string& err);
 bool load_gsx(const std::string& prefix, HostIndex& ix, std::string& err);
 
+// the device arrays of one strand index, each with its size in bytes (the replicas on further devices are peer copies)
+//   exc_map: one bit per 64-row block holding an exception row (SearchArgs::exc_map)
+#define GSX_STRAND_ARRAYS(X) X(blocks) X(lines) X(sum0) X(sum1) X(sum2) X(ftab) X(sa) X(exc_rows) X(exc_lf) X(n_rows) X(exc_map)
 struct DeviceStrand {
     DevStrand d{};
-    void* blocks = nullptr; void* lines = nullptr; void* sum0 = nullptr; void* sum1 = nullptr; void* sum2 = nullptr; void* ftab = nullptr; void* sa = nullptr; void* exc_rows = nullptr; void* exc_lf = nullptr; void* n_rows = nullptr;
-    void* exc_map = nullptr;      // one bit per 64-row block holding an exception row (SearchArgs::exc_map)
+#define GSX_DECL(name) void* name = nullptr; size_t name##_bytes = 0;
+    GSX_STRAND_ARRAYS(GSX_DECL)
+#undef GSX_DECL
 };
 struct DeviceIndex {
     int device = 0;
     int sm_count = 148;
+    int alias_of = -1;            // >= 0: this slot names a device that an earlier slot already holds; it shares that slot's arrays
     DeviceStrand st[2];
     Chrom* chroms = nullptr;
     uint64_t bytes = 0;
@@ -66,6 +71,9 @@ struct gsx_index {
     gsx::HostIndex host;
     std::vector<gsx::DeviceIndex> dev;
     std::vector<gsx::Chrom> chroms;
+    // seconds spent by gsx_index_open / gsx_index_build: [0] reading + converting the files (or suffix sorting), [1] upload and
+    // derived arrays (jump table, look-ahead lines, summaries) on the first device, [2] replication to the other devices
+    double open_seconds[3] = {0, 0, 0};
 };
 
 #include "../../include/gsx.h"

@@ -152,7 +152,9 @@ bool load_genome_structure(const std::string& path, HostIndex& ix, std::string& 
         std::string name, len;
         std::getline(fs, name); std::getline(fs, len);
         if (name.empty() || len.empty()) break;
-        ix.chr_names.push_back(name); ix.chr_lens.push_back((uint64_t)std::stoll(len));
+        char* endp = nullptr; const long long v = strtoll(len.c_str(), &endp, 10);
+        if (endp == len.c_str() || v < 0) { err = "malformed genome structure file " + path + " (length \"" + len + "\")"; return false; }
+        ix.chr_names.push_back(name); ix.chr_lens.push_back((uint64_t)v);
         ix.genome_length += ix.chr_lens.back();
     }
     return true;
@@ -275,7 +277,14 @@ void sweep_make_plan(uint32_t L, uint32_t sb, uint32_t M, SweepPlan& plan, std::
 namespace {
 const char kMagic[8] = {'G', 'S', 'X', 'I', 'D', 'X', '0', '2'};
 template <class T> bool wr(FILE* f, const std::vector<T>& v) { uint64_t n = v.size(); return fwrite(&n, 8, 1, f) == 1 && (n == 0 || fwrite(v.data(), sizeof(T), n, f) == n); }
-template <class T> bool rd(FILE* f, std::vector<T>& v) { uint64_t n; if (fread(&n, 8, 1, f) != 1) return false; v.resize(n); return n == 0 || fread(v.data(), sizeof(T), n, f) == n; }
+// (a section longer than what is left of the file is a corrupt header, not an allocation request)
+template <class T> bool rd(FILE* f, std::vector<T>& v) {
+    uint64_t n; if (fread(&n, 8, 1, f) != 1) return false;
+    const off_t at = ftello(f); if (at < 0 || fseeko(f, 0, SEEK_END) != 0) return false;
+    const off_t end = ftello(f); if (fseeko(f, at, SEEK_SET) != 0) return false;
+    if (n > (uint64_t)(end - at) / sizeof(T)) return false;
+    v.resize(n); return n == 0 || fread(v.data(), sizeof(T), n, f) == n;
+}
 }  // namespace
 
 bool save_gsx(const std::string& prefix, const HostIndex& ix, std::string& err) {
@@ -304,8 +313,20 @@ bool load_gsx(const std::string& prefix, HostIndex& ix, std::string& err) {
              rd(f, h.sa_samples) && rd(f, h.exc_rows) && rd(f, h.exc_lf) && rd(f, h.n_rows) && rd(f, h.exc_sym);
     }
     fclose(f);
+    // section sizes must agree with the row count: the kernels index these arrays by row without further checks
+    for (int s = 0; s < 2 && ok; s++) {
+        const HostStrand& h = ix.st[s];
+        ok = h.n >= 1 && h.n <= 0xFFFFFFFFull && h.sa_shift <= 12 && h.blocks.size() == h.n / 64 + 1 &&
+             h.sa_samples.size() == ((h.n - 1) >> h.sa_shift) + 1 && h.exc_lf.size() == h.exc_rows.size() && h.exc_sym.size() == h.exc_rows.size() &&
+             h.n_rows.size() <= h.exc_rows.size() && !h.exc_rows.empty();
+        for (size_t i = 0; ok && i < h.exc_rows.size(); i++) ok = h.exc_rows[i] < h.n && h.exc_lf[i] < h.n && (i == 0 || h.exc_rows[i] > h.exc_rows[i - 1]);
+        for (size_t i = 0; ok && i < h.n_rows.size(); i++) ok = h.n_rows[i] < h.n;
+    }
+    if (ok) ok = ix.st[0].n == ix.st[1].n;
     if (!ok) { err = "malformed " + prefix + ".gsx"; return false; }
-    return load_genome_structure(prefix + ".gs", ix, err);
+    if (!load_genome_structure(prefix + ".gs", ix, err)) return false;
+    if (ix.genome_length + 1 != ix.st[0].n) { err = prefix + ".gs does not describe the genome of " + prefix + ".gsx"; return false; }
+    return true;
 }
 
 }  // namespace gsx

@@ -1410,6 +1410,23 @@ cudaError_t launch_specificity(const SpecArgs& a, cudaStream_t s) {
 cudaError_t launch_threshold(const unsigned long long* gc, uint8_t* dropped, uint32_t n, cudaStream_t s) {
     threshold_kernel<<<grid_for(n, 256, 148 * 4), 256, 0, s>>>(gc, dropped, n); return cudaGetLastError();
 }
+// order-independent 64-bit digest of a device array (4-byte words, each mixed with its position): equal arrays <=> equal digests
+// for all practical purposes; used to check that the index replicas on several devices are byte-identical
+__global__ void checksum_kernel(const uint32_t* __restrict__ p, size_t n_words, unsigned long long seed, unsigned long long* out) {
+    unsigned long long acc = 0;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n_words; i += (size_t)gridDim.x * blockDim.x) {
+        unsigned long long x = (unsigned long long)p[i] + (i + 1) * 0x9E3779B97F4A7C15ull + seed;
+        x ^= x >> 31; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 29; x *= 0x94D049BB133111EBull; x ^= x >> 32;
+        acc += x;
+    }
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
+}
+cudaError_t launch_checksum(const void* p, size_t bytes, unsigned long long seed, unsigned long long* out, cudaStream_t s) {
+    if (bytes < 4) return cudaSuccess;
+    checksum_kernel<<<148 * 8, 256, 0, s>>>(reinterpret_cast<const uint32_t*>(p), bytes / 4, seed, out);
+    return cudaGetLastError();
+}
 cudaError_t launch_rank_query(const DevStrand& st, const uint32_t* rows, const uint8_t* syms, uint32_t n, uint32_t* out, cudaStream_t s) {
     rank_query_kernel<<<grid_for(n, 256, 148 * 8), 256, 0, s>>>(st, rows, syms, n, out); return cudaGetLastError();
 }

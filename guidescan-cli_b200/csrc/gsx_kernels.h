@@ -132,6 +132,7 @@ cudaError_t launch_expand(const MatchRec* m, const uint32_t* moff, const uint32_
 cudaError_t launch_locate_score(const LocateArgs& a, cudaStream_t s);
 cudaError_t launch_specificity(const SpecArgs& a, cudaStream_t s);
 cudaError_t launch_threshold(const unsigned long long* gc, uint8_t* dropped, uint32_t n, cudaStream_t s);
+cudaError_t launch_checksum(const void* p, size_t bytes, unsigned long long seed, unsigned long long* out, cudaStream_t s);      // *out += digest
 cudaError_t launch_rank_query(const DevStrand& st, const uint32_t* rows, const uint8_t* syms, uint32_t n, uint32_t* out, cudaStream_t s);
 cudaError_t launch_locate_query(const DevStrand& st, const uint32_t* rows, uint32_t n, uint32_t* out, cudaStream_t s);
 

@@ -60,7 +60,7 @@ class GuideRow(C.Structure):
 EXPORTS = ["gsx_params_default", "gsx_index_open", "gsx_index_build", "gsx_index_build_text", "gsx_index_close",
            "gsx_index_genome_length",
            "gsx_index_n_chromosomes", "gsx_index_chromosome_name", "gsx_index_chromosome_length", "gsx_index_device_bytes",
-           "gsx_index_n_devices", "gsx_index_rank", "gsx_index_locate", "gsx_index_export_bwt", "gsx_index_export_sa_samples", "gsx_enumerate", "gsx_result_view_get",
+           "gsx_index_n_devices", "gsx_index_open_seconds", "gsx_index_device_checksum", "gsx_enumerate_start", "gsx_enumerate_wait", "gsx_index_rank", "gsx_index_locate", "gsx_index_export_bwt", "gsx_index_export_sa_samples", "gsx_enumerate", "gsx_result_view_get",
            "gsx_result_counters", "gsx_result_match_sequence", "gsx_result_free", "gsx_format_rows", "gsx_format_header",
            "gsx_enumerate_file", "gsx_guides_csv_open", "gsx_guides_csv_row", "gsx_guides_csv_close", "gsx_generate_kmers", "gsx_free", "gsx_last_error", "gsx_version", "gsx_device_count"]
 
@@ -86,6 +86,11 @@ _L.gsx_index_locate.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c
 _L.gsx_index_export_bwt.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
 _L.gsx_index_export_sa_samples.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
 _L.gsx_enumerate.argtypes = [C.c_void_p, C.POINTER(Guide), C.c_size_t, C.POINTER(Params), C.POINTER(C.c_void_p)]
+_L.gsx_enumerate_start.argtypes = [C.c_void_p, C.POINTER(Guide), C.c_size_t, C.POINTER(Params), C.POINTER(C.c_void_p)]
+_L.gsx_enumerate_wait.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+_L.gsx_index_open_seconds.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+_L.gsx_index_n_devices.argtypes = [C.c_void_p]
+_L.gsx_index_device_checksum.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint64)]
 _L.gsx_result_view_get.argtypes = [C.c_void_p, C.POINTER(ResultView)]
 _L.gsx_result_counters.argtypes = [C.c_void_p, C.POINTER(Counters)]
 _L.gsx_result_match_sequence.argtypes = [C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t]
@@ -260,6 +265,21 @@ class Index:
     def device_bytes(self):
         return _L.gsx_index_device_bytes(self.h)
 
+    @property
+    def n_devices(self):
+        return _L.gsx_index_n_devices(self.h)
+
+    def device_checksum(self, slot: int) -> int:
+        out = C.c_uint64()
+        _ck(_L.gsx_index_device_checksum(self.h, slot, C.byref(out)), "gsx_index_device_checksum")
+        return out.value
+
+    def open_seconds(self):
+        """(files / suffix sorting, upload + derived arrays on the first device, replication to the other devices)"""
+        out = (C.c_double * 3)()
+        _ck(_L.gsx_index_open_seconds(self.h, out), "gsx_index_open_seconds")
+        return tuple(out)
+
     def chromosomes(self):
         return [(_L.gsx_index_chromosome_name(self.h, i).decode(), _L.gsx_index_chromosome_length(self.h, i))
                 for i in range(_L.gsx_index_n_chromosomes(self.h))]
@@ -305,6 +325,17 @@ class Index:
         """pre-built ctypes Guide array (bench path: no per-call Python marshalling)"""
         h = C.c_void_p()
         _ck(_L.gsx_enumerate(self.h, guide_array, n, C.byref(params), C.byref(h)), "gsx_enumerate")
+        return Result(h, self)
+
+    def enumerate_start(self, guide_array, n, params):
+        """first half of the two-slot form: returns a handle at once; the arguments must stay alive until enumerate_wait"""
+        h = C.c_void_p()
+        _ck(_L.gsx_enumerate_start(self.h, guide_array, n, C.byref(params), C.byref(h)), "gsx_enumerate_start")
+        return h
+
+    def enumerate_wait(self, pending) -> Result:
+        h = C.c_void_p()
+        _ck(_L.gsx_enumerate_wait(pending, C.byref(h)), "gsx_enumerate_wait")
         return Result(h, self)
 
     def header(self, fmt="csv", mode="complete") -> bytes:

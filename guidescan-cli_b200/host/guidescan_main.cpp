@@ -20,7 +20,7 @@ static void usage() {
             "  enumerate [OPTIONS] INDEX_PREFIX\n"
             "      --start                     Match PAM at start of kmer instead at end (default).\n"
             "      --max-off-targets INT=-1    Maximum number of off-targets to store for each number of mismatches.\n"
-            "      -n,--threads UINT           Host worker threads (formatting); the search runs on the GPU(s).\n"
+            "      -n,--threads UINT           Host worker threads that format the output (default: all cores); the search runs on the GPU(s).\n"
             "      -a,--alt-pam TEXT ...       Alternative PAMs used to find off-targets\n"
             "      -m,--mismatches UINT=3      Number of mismatches to allow when finding off-targets\n"
             "      --rna-bulges UINT=0         Max number of RNA bulges to allow when finding off-targets\n"
@@ -30,7 +30,8 @@ static void usage() {
             "      --mode TEXT:{succinct,complete}  Information to output.\n"
             "      -f,--kmers-file FILE        REQUIRED  File containing kmers to build gRNA database over\n"
             "      -o,--output TEXT            REQUIRED  Output file.\n"
-            "      --gpus INT=1                Number of GPUs to shard the guides over (extension).\n");
+            "      --gpus INT=1                Number of GPUs to shard the guides over (extension): devices 0 .. INT-1.\n"
+            "      --devices LIST              The same with explicit device ordinals, e.g. 0,2,3 (extension).\n");
 }
 
 static std::string lower(std::string s) { std::transform(s.begin(), s.end(), s.begin(), ::tolower); return s; }
@@ -56,13 +57,13 @@ static int do_index(int argc, char** argv) {
 static int do_enumerate(int argc, char** argv) {
     gsx_params p; gsx_params_default(&p);
     std::string index, kmers, output, format = "csv", mode = "complete";
-    std::vector<std::string> alts; int gpus = 1;
+    std::vector<std::string> alts; int gpus = 1; std::vector<int> devs;
     for (int i = 0; i < argc; i++) {
         std::string a = argv[i];
         auto need = [&](const char* name) -> const char* { if (i + 1 >= argc) { fprintf(stderr, "%s: 1 required\n", name); exit(106); } return argv[++i]; };
         if (a == "--start") p.start = 1;
         else if (a == "--max-off-targets") p.max_off_targets = atoll(need("--max-off-targets"));
-        else if (a == "-n" || a == "--threads") need("--threads");
+        else if (a == "-n" || a == "--threads") { const int t = atoi(need("--threads")); if (t > 0) setenv("GSX_FORMAT_THREADS", std::to_string(t).c_str(), 1); }
         else if (a == "-a" || a == "--alt-pam") {          // greedy multi-value, as CLI11 parses it
             while (i + 1 < argc && argv[i + 1][0] != '-') alts.push_back(argv[++i]);
         }
@@ -75,6 +76,10 @@ static int do_enumerate(int argc, char** argv) {
         else if (a == "-f" || a == "--kmers-file") kmers = need("--kmers-file");
         else if (a == "-o" || a == "--output") output = need("--output");
         else if (a == "--gpus") gpus = atoi(need("--gpus"));
+        else if (a == "--devices") {
+            std::string l = need("--devices");
+            for (size_t b = 0; b < l.size();) { size_t e = l.find(',', b); if (e == std::string::npos) e = l.size(); if (e > b) devs.push_back(atoi(l.substr(b, e - b).c_str())); b = e + 1; }
+        }
         else if (a == "-h" || a == "--help") { usage(); return 0; }
         else if (!a.empty() && a[0] == '-') { fprintf(stderr, "The following argument was not expected: %s\n", a.c_str()); return 109; }
         else index = a;
@@ -86,12 +91,15 @@ static int do_enumerate(int argc, char** argv) {
     if (mode != "succinct" && mode != "complete") { fprintf(stderr, "--mode: %s not in {succinct,complete}\n", mode.c_str()); return 105; }
     std::vector<const char*> ap; for (auto& s : alts) ap.push_back(s.c_str());
     p.alt_pams = ap.data(); p.n_alt_pams = (uint32_t)ap.size();
-    std::vector<int> devs; for (int d = 0; d < std::max(1, gpus); d++) devs.push_back(d);
+    if (devs.empty()) for (int d = 0; d < std::max(1, gpus); d++) devs.push_back(d);
     printf("Loading genome index at \"%s\".\n", index.c_str());
     gsx_index* ix = nullptr;
     int rc = gsx_index_open(index.c_str(), devs.data(), (int)devs.size(), &ix);
     if (rc) { fprintf(stderr, "%s\n", gsx_last_error()); return 1; }
-    printf("Successfully loaded genome index.\n");
+    {
+        double t[3] = {0, 0, 0}; gsx_index_open_seconds(ix, t);
+        printf("Successfully loaded genome index. (%zu device(s): files %.2f s, device layout %.2f s, replication %.2f s)\n", devs.size(), t[0], t[1], t[2]);
+    }
     auto t0 = std::chrono::steady_clock::now();
     size_t n = 0; gsx_counters c;
     rc = gsx_enumerate_file(ix, kmers.c_str(), output.c_str(), &p, format == "sam", mode == "complete", 0, &n, &c);

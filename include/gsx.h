@@ -128,6 +128,11 @@ const char* gsx_index_chromosome_name(const gsx_index*, uint32_t i);
 uint64_t    gsx_index_chromosome_length(const gsx_index*, uint32_t i);
 uint64_t    gsx_index_device_bytes(const gsx_index*);
 int         gsx_index_n_devices(const gsx_index*);
+/* Seconds the open / build call spent: out[0] reading and converting the index files (or suffix sorting), out[1] upload and
+ * derived arrays on the first device, out[2] replication to the other devices (peer copies over NVLink, all concurrently). */
+/* 64-bit digest of everything the index holds on its slot-th device (computed there); replicas of one index give equal digests. */
+int         gsx_index_device_checksum(const gsx_index*, int slot, uint64_t* out);
+int         gsx_index_open_seconds(const gsx_index*, double out[3]);
 
 /* Primitive queries (device-evaluated, for parity tests): occ of symbol c in BWT[0,i) = csa.rank_bwt(i,c)
  * (sdsl csa_wt.hpp:270-273) and SA[row] = csa[row] (csa_wt.hpp:333-346), batched. strand 0 = forward index. */
@@ -144,6 +149,15 @@ int gsx_index_export_sa_samples(const gsx_index*, int strand, uint32_t* out, uin
  * Guides are sharded over the index's devices (no collective; each device returns its own arena).
  * Inputs are borrowed for the duration of the call. */
 int gsx_enumerate(const gsx_index*, const gsx_guide* guides, size_t n_guides, const gsx_params*, gsx_result** out);
+/* The same call in two halves, for callers that pipeline batches: gsx_enumerate_start returns at once and the batch runs on a
+ * library thread; gsx_enumerate_wait blocks until it is done, hands out the result (or the error) and releases the handle.
+ * Calls in flight on the same device take turns for its kernels, so batch k's copies to the host and the caller's work on its
+ * result overlap batch k+1's search -- what the reference gets from N worker threads behind one output mutex
+ * (src/guidescan.cxx:241-251, process.hpp:119-126).  `guides`, the strings they point to and `params` stay borrowed until
+ * gsx_enumerate_wait returns. */
+typedef struct gsx_pending gsx_pending;
+int gsx_enumerate_start(const gsx_index*, const gsx_guide* guides, size_t n_guides, const gsx_params*, gsx_pending** out);
+int gsx_enumerate_wait(gsx_pending*, gsx_result** out);
 int gsx_result_view_get(const gsx_result*, gsx_result_view* view);
 int gsx_result_counters(const gsx_result*, gsx_counters* out);
 /* The reference's match.sequence of hit `hit` complemented as it is printed (printer.hpp:232,264); buf >= 48 bytes. */

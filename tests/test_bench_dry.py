@@ -1,5 +1,5 @@
-"""bench.py's own arm assembled without a GPU: the index and the results are stubs, everything else (workload, timed loop on one
-or two host threads, JSON line with roofline / e2e / file_e2e / cpu_baseline / clocks blocks) is the real code.  Guards the
+"""bench.py's own arm assembled without a GPU: the index and the results are stubs, everything else (workload, timed loop with
+one or several batches in flight, JSON line with roofline / e2e / file_e2e / cpu_baseline / clocks blocks) is the real code.  Guards the
 driver-facing contract against runtime errors that only a GPU box would otherwise reveal."""
 import json
 import os
@@ -30,6 +30,15 @@ class _Index:
     def enumerate_raw(self, arr, per, params):
         return _Result(per)
 
+    def enumerate_start(self, arr, per, params):
+        return per
+
+    def enumerate_wait(self, pending):
+        return _Result(pending)
+
+    def open_seconds(self):
+        return (1.0, 2.0, 0.0)
+
     def enumerate_file(self, csv, out, params, **kw):
         open(out, "w").write("x" * 1000)
         return 10, _Result(10).counters()
@@ -49,14 +58,13 @@ class _Clocks:
         return {"sm_mhz": 1, "sm_max_mhz": 1, "reasons": [], "samples": 1}
 
 
-@pytest.mark.parametrize("extra", [[], ["--e2e-threads", "2", "--n-runs", "2"], ["--rna-bulges", "1", "--dna-bulges", "1", "--alt-pam", "NAG"]])
+@pytest.mark.parametrize("extra", [[], ["--e2e-pipeline", "1", "--n-runs", "2"], ["--e2e-pipeline", "3"], ["--rna-bulges", "1", "--dna-bulges", "1", "--alt-pam", "NAG"]])
 def test_own_arm_prints_the_contract_line(monkeypatch, tmp_path, capsys, extra):
     import bench
     monkeypatch.setattr(bench, "build_index", lambda gsx, g, chroms, local, args, workdir: (_Index(), "stub"))
     monkeypatch.setattr(bench, "cpu_baseline", lambda *a, **k: {"value": 1.0, "unit": "guides/s", "cores": 1, "kind": "port", "sample": "stub", "out": "o", "csv": "c"})
     monkeypatch.setattr(bench, "parity_on_sample", lambda *a, **k: True)
     monkeypatch.setattr(bench, "ClockSampler", _Clocks)
-    monkeypatch.delenv("GSX_DEVICE_LOCK", raising=False)
     args = bench.parse_args(["--genome-mb", "1", "--n-chr", "2", "--guides-per-step", "50", "--steps", "4", "--warmup", "3", "--plant-guides", "10",
                              "--workdir", str(tmp_path)] + extra)
     bench.apply_variant(args)
@@ -70,4 +78,3 @@ def test_own_arm_prints_the_contract_line(monkeypatch, tmp_path, capsys, extra):
     assert set(line["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"}
     assert set(line["cpu_baseline"]) >= {"value", "unit", "cores", "kind", "sample"}
     assert line["config"]["workload"].startswith("1 Mb") and line["value"] == pytest.approx(50 * 4 / 4e-3)
-    os.environ.pop("GSX_DEVICE_LOCK", None)         # (set by the threaded form of the bench itself)

@@ -1,0 +1,40 @@
+#!/bin/bash
+# GPU sessions of round 2 (one parameterised script; the per-session scripts of round 1 were folded into this one).
+#   tools/gpu_round2.sh <tag> [pytest] [smoke] [plan <plan.json>] [bench <args...>]
+# pytest: the -m gpu suite (with the formerly pending paths);  smoke: the plan at 120 Mb with small batches first, so that a
+# Python error costs seconds and not an index build;  plan: tools/gpu_session.py on the 3.1 Gb genome;  bench: bench.py with the
+# remaining arguments.  Everything lands in gpurun_out/<tag>*.
+set -x
+tag=$1; shift
+mkdir -p gpurun_out
+while [ $# -gt 0 ]; do
+  case $1 in
+    pytest)
+      GSX_TEST_PENDING=1 timeout 1500 python -m pytest tests -m gpu -q --maxfail 8 --timeout 900 > gpurun_out/${tag}_pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/${tag}_pytest_gpu.log
+      tail -5 gpurun_out/${tag}_pytest_gpu.log; shift;;
+    smoke)
+      plan=$2
+      python - "$plan" > /tmp/smoke_plan.json <<'PY'
+import json, sys
+p = json.load(open(sys.argv[1]))
+for g in p["genomes"]:
+    for e in g["experiments"]:
+        if "guides" in e: e["guides"] = 256 if (e.get("rna_bulges") or e.get("dna_bulges")) else 20000
+        e["steps"], e["warmup"] = min(e.get("steps", 2), 2), 1
+        if "parity_sample" in e: e["parity_sample"] = 4 if (e.get("rna_bulges") or e.get("dna_bulges")) else 64
+        if "file_e2e" in e: e["file_e2e"]["guides"] = 50000
+print(json.dumps(p))
+PY
+      timeout 600 python tools/gpu_session.py --plan /tmp/smoke_plan.json --tag ${tag}_smoke --genome-mb 120 2> gpurun_out/${tag}_smoke.err || { tail -20 gpurun_out/${tag}_smoke.err; echo "SMOKE FAILED"; exit 1; }
+      grep -c '"error"' gpurun_out/${tag}_smoke.jsonl; grep '"error"' gpurun_out/${tag}_smoke.jsonl | cut -c1-600
+      shift;;
+    plan)
+      timeout 2400 python tools/gpu_session.py --plan $2 --tag ${tag} 2> gpurun_out/${tag}.err; tail -3 gpurun_out/${tag}.err
+      cut -c1-420 gpurun_out/${tag}.jsonl; shift 2;;
+    bench)
+      shift
+      timeout 1200 python bench.py "$@" > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; tail -3 gpurun_out/${tag}_bench.err; cut -c1-1200 gpurun_out/${tag}_bench.json
+      break;;
+    *) echo "unknown step $1"; exit 2;;
+  esac
+done

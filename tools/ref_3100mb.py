@@ -1,0 +1,77 @@
+#!/usr/bin/env python
+"""CPU-container job (no GPU): the UNMODIFIED reference at the north-star size.
+
+Builds bench.py's own 3.1 Gb workload (same seed, same planting), runs `oracle/_ref/guidescan index` on it, times
+`oracle/_ref/guidescan enumerate -n <cores>` on the first --sample guides, and writes the figures to
+profiles/r02_reference_3100mb.json (BASELINE.md 2.1 is filled from it).  The index files stay in --workdir for
+tools/ref_index_check (parser of the reference's files vs the genome text) and for the port's timing on the same index.
+
+  python tools/ref_3100mb.py [--workdir /tmp/ref3100] [--sample 8000] [--stage fasta|index|enumerate|all]
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "guidescan-cli_b200"))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--workdir", default="/tmp/ref3100")
+    ap.add_argument("--sample", type=int, default=8000)
+    ap.add_argument("--stage", default="all")
+    ap.add_argument("--mismatches", type=int, default=3)
+    a = ap.parse_args()
+    import bench
+    import oracle as O
+    import synth
+    args = bench.parse_args([])                    # bench.py's defaults = the graded workload
+    os.makedirs(a.workdir, exist_ok=True)
+    tag = "bench_%dmb_s%d" % (int(args.genome_mb), args.seed)
+    fa, prefix = os.path.join(a.workdir, tag + ".fa"), os.path.join(a.workdir, tag)
+    gcsv = os.path.join(a.workdir, "cpu_sample.csv")
+    res_path = os.path.join(ROOT, "profiles", "r02_reference_3100mb.json")
+    res = json.load(open(res_path)) if os.path.exists(res_path) else {}
+    res.update({"workload": bench.workload_config(args)["workload"], "cores": os.cpu_count(),
+                "cpu": [l.split(":")[1].strip() for l in open("/proc/cpuinfo") if l.startswith("model name")][0]})
+    if a.stage in ("all", "fasta") and not os.path.exists(fa):
+        g, chroms, pos, kmers = bench.make_workload(args, 1)
+        synth.write_fasta(fa, g, chroms)
+        bench.write_sample_csv(gcsv, kmers, a.sample)
+        g.tofile(os.path.join(a.workdir, tag + ".text"))           # the planted genome bytes, for ref_index_check
+        del g
+    if a.stage in ("all", "index") and not os.path.exists(prefix + ".reverse"):
+        t0 = time.time()
+        p = subprocess.run([O.REF_BIN, "index", "--index", prefix, fa], cwd=a.workdir,
+                           stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True)
+        dt = time.time() - t0
+        import resource
+        res["index_seconds"] = dt
+        res["index_peak_rss_kb"] = resource.getrusage(resource.RUSAGE_CHILDREN).ru_maxrss      # peak resident set of the single-threaded construction
+        res["index_bytes"] = {s: os.path.getsize(prefix + "." + s) for s in ("forward", "reverse")}
+        json.dump(res, open(res_path, "w"), indent=1)
+        if p.returncode:
+            sys.exit("reference index failed: " + p.stderr[-400:])
+    if a.stage in ("all", "enumerate"):
+        out = os.path.join(a.workdir, "ref.out")
+        cores = os.cpu_count()
+        t0 = time.time()
+        p = subprocess.run([O.REF_BIN, "enumerate", prefix, "-f", gcsv, "-o", out, "-m", str(a.mismatches), "-n", str(cores)],
+                           stdout=subprocess.PIPE, text=True)
+        t1 = time.time()
+        # the log line "Successfully loaded genome index" separates index load from the search
+        lines = p.stdout.splitlines()
+        res["enumerate"] = {"guides": a.sample, "threads": cores, "mismatches": a.mismatches, "wall_seconds": t1 - t0,
+                            "log": [l for l in lines if "Processed:" not in l][-12:], "rows": sum(1 for _ in open(out)) - 1}
+        json.dump(res, open(res_path, "w"), indent=1)
+    print(json.dumps(res))
+
+
+if __name__ == "__main__":
+    main()
