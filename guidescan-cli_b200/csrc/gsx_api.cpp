@@ -45,6 +45,7 @@ template <class T> static void* upload(const std::vector<T>& v, size_t& n_bytes,
     void* d = nullptr; size_t n = std::max<size_t>(v.size(), 1) * sizeof(T);
     CK(cudaMalloc(&d, n));
     if (!v.empty()) CK(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    else CK(cudaMemset(d, 0, n));                                            // (an empty table still has one, defined, element)
     n_bytes = n; total += n;
     return d;
 }
@@ -466,6 +467,21 @@ struct DevBufs {
     ~DevBufs() { for (auto& q : ptrs) pool_put(device, q.first, q.second); }
 };
 
+// pinned, device-visible words for the small read-backs of a job (gsx_kernels.cu launch_publish), recycled between calls
+namespace {
+struct Mailbox {
+    uint32_t* p = nullptr;
+    static std::mutex& mu() { static std::mutex m; return m; }
+    static std::vector<uint32_t*>& free_list() { static std::vector<uint32_t*> v; return v; }
+    Mailbox() {
+        { std::lock_guard<std::mutex> g(mu()); if (!free_list().empty()) { p = free_list().back(); free_list().pop_back(); } }
+        if (!p) { void* q = nullptr; if (cudaHostAlloc(&q, 256, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); throw CudaError("cudaHostAlloc (mailbox)"); } p = (uint32_t*)q; }
+        memset(p, 0, 256);
+    }
+    ~Mailbox() { std::lock_guard<std::mutex> g(mu()); free_list().push_back(p); }
+};
+}  // namespace
+
 static std::mutex g_recs_mu;
 static std::vector<std::vector<GuideRec>> g_recs_free;          // record arrays of released results, reused by later calls
 
@@ -657,21 +673,28 @@ static void run_device_job(DeviceJob* job) {
         const uint32_t n_dist = p.mismatches + 1;
         CK(cudaSetDevice(di.device));
         DevBufs B(di.device);
+        Mailbox mbox;                                            // (declared before the streams: they are drained before it goes back to the free list)
         JobStreams js;                                           // (declared after the buffer holder: destroyed -- synchronised -- before it)
         CK(cudaStreamCreate(&js.s)); CK(cudaStreamCreate(&js.s2));
         for (auto& e : js.ev) CK(cudaEventCreate(&e));
         CK(cudaEventCreateWithFlags(&js.ev_guides, cudaEventDisableTiming));
         const cudaStream_t s = js.s, s2 = js.s2; cudaEvent_t* const ev = js.ev; const cudaEvent_t ev_guides = js.ev_guides;
+        // the first words of d_ctrs, read on the host without touching the copy engine
+        auto read_ctrs = [&](uint32_t* h, uint32_t n_words, const uint32_t* d_src) {
+            CK(launch_publish(d_src, n_words, mbox.p, s)); CK(cudaStreamSynchronize(s));
+            for (uint32_t i = 0; i < n_words; i++) h[i] = mbox.p[i];
+        };
         HostArrays& H = job->out; H.n_guides = n;
         H.dropped = H.alloc<uint8_t>(n); H.n_hits_of = H.alloc<uint32_t>(n); H.hoff = H.alloc<uint32_t>(n + 1);
         H.specificity = H.alloc<float>(n); H.perfect = H.alloc<uint8_t>(n); H.cbd = H.alloc<uint32_t>((size_t)n * n_dist);
         if (n == 0) { H.hoff[0] = 0; return; }
 
         // fast path (search_fast_kernel) when the batch and the index allow it; GSX_FORCE_GENERAL=1 keeps the general kernel
-        // (an index whose only non-ACGT BWT row is the sentinel; genomes with N / IUPAC characters only under GSX_FAST_ON_N=1:
-        // search_fast_kernel<..., EXC> was written at the end of round 1; GPU goldens green, not yet run at full genome size)
+        // (an index whose only non-ACGT BWT row is the sentinel runs the plain kernels; genomes with N / IUPAC characters -- every
+        // real assembly -- run search_fast_kernel<..., EXC> behind the same sweep: 4.75 M guides/s against 80 k on the general kernel
+        // at 3.1 Gb with 300 runs of N, output identical to the CPU arm's, profiles/r02a_session_3100mb.jsonl; GSX_FAST_ON_N=0 turns it off)
         const bool plain_index = di.st[0].d.n_exc == 1 && di.st[1].d.n_exc == 1 && di.st[0].d.n_nrows == 0 && di.st[1].d.n_nrows == 0;
-        const bool exc_index = !plain_index && env_int("GSX_FAST_ON_N", 0) != 0 && env_int("GSX_FAST_VARIANT", di.st[0].d.lines ? 1 : 0) == 1 &&
+        const bool exc_index = !plain_index && env_int("GSX_FAST_ON_N", 1) != 0 && env_int("GSX_FAST_VARIANT", di.st[0].d.lines ? 1 : 0) == 1 &&
                                di.st[0].exc_map && di.st[1].exc_map;
         const bool use_fast = (prep.fast_ok || prep.variant_ok) && !env_int("GSX_FORCE_GENERAL", 0) && n < (1u << 23) && (plain_index || exc_index);
         // bulges: the search runs over the guides' edited forms (gsx_core.h variant_rewrite), in chunks, on the same kernels
@@ -748,6 +771,7 @@ static void run_device_job(DeviceJob* job) {
         uint32_t* d_xtab = nullptr; uint32_t xtab_M = ~0u, xtab_sb = 0, n_xtab = 0; SweepPlan xplan{};
         uint32_t* d_gtab = nullptr; size_t gtab_cap = 0;
         // fast path launch over ng guides (m.gq): [sweep_kernel ->] search_fast_kernel.  d_ctrs: [3] seed queue count, [4] sweep work-unit counter
+        uint32_t lean_qmin = prep.min_qlen, lean_qmax = prep.max_qlen;              // guide lengths of the batch the fast kernels see (edited guides: - R .. + D)
         auto launch_fast = [&](SearchArgs& m, uint32_t ng, uint32_t sb, cudaEvent_t ev_mid) {
             if (sb) {
                 SweepArgs w{};
@@ -755,7 +779,9 @@ static void run_device_job(DeviceJob* job) {
                     std::vector<uint32_t> xtab;
                     sweep_make_plan(ftab_L, sb, m.p.M, xplan, xtab);
                     if (d_xtab) B.free_one(d_xtab);
-                    d_xtab = B.alloc<uint32_t>(xtab.size()); n_xtab = (uint32_t)xtab.size(); xtab_M = m.p.M; xtab_sb = sb;
+                    n_xtab = (uint32_t)xtab.size(); xtab_M = m.p.M; xtab_sb = sb;
+                    xtab.resize(xtab.size() + 64, 0u);                                // (sweep_lean_kernel reads up to 63 words past a pass's end, unused)
+                    d_xtab = B.alloc<uint32_t>(xtab.size());
                     CK(cudaMemcpyAsync(d_xtab, xtab.data(), xtab.size() * 4, cudaMemcpyHostToDevice, s)); CK(cudaStreamSynchronize(s));
                 }
                 w.plan = xplan;
@@ -768,7 +794,16 @@ static void run_device_job(DeviceJob* job) {
                 if (gtab_cap < ng) { if (d_gtab) B.free_one(d_gtab); d_gtab = B.alloc<uint32_t>((size_t)ng * 20); gtab_cap = ng; }
                 w.gtab = d_gtab;
                 CK(launch_sweep_guides(w, s)); n_launches++;
-                CK(launch_sweep(w, env_int("GSX_SWEEP_VARIANT", 2), di.sm_count, s)); n_launches++;
+                // sweep_lean_kernel (variants 10-12) where its compiled loops cover the batch: at most 4 mismatches, every guide length
+                // of the batch giving one of its plane layouts
+                int sv = env_int("GSX_SWEEP_VARIANT", 2);
+                if (sv >= 10) {
+                    bool lean_ok = m.p.M <= 4;
+                    for (uint32_t ql = lean_qmin; lean_ok && ql <= lean_qmax; ql++)
+                        lean_ok = sweep_shape_of(sweep_codes((uint64_t)ql << 58, ftab_L, m.plen, m.pampack)) >= 0;
+                    if (!lean_ok) sv = 2;
+                }
+                CK(launch_sweep(w, sv, di.sm_count, s)); n_launches++;
                 m.seeds = d_queue; m.n_seeds = d_ctrs + 3; m.seed_cap = (uint32_t)queue_cap; m.combos = nullptr; m.n_combos = 0;
             }
             if (ev_mid) CK(cudaEventRecord(ev_mid, s));
@@ -776,9 +811,9 @@ static void run_device_job(DeviceJob* job) {
         };
         // alternative PAMs (process.hpp:51-56): the searches of the PAMs are independent and their matches are collected in
         // the same per-guide sets, so each PAM gets its own pass over the same arenas; only the work counters start over
-        // GSX_FUSED_PAMS=1 (off by default: written at the end of round 1; host mirror and GPU goldens green, not yet run at 3.1 Gb): the PAMs in
+        // Default (GSX_FUSED_PAMS=0 keeps one pass per PAM; m = 4 with NGG + NAG at 3.1 Gb: 232 k against 142 k guides/s, same text): the PAMs in
         // ONE pass -- search with the filter PAM, keep the alignments whose PAM characters spell a real PAM (gsx_core.h fused_pam_ok)
-        const bool fuse_pams = prep.n_fast_pams > 1 && variant_f == 1 && env_int("GSX_FUSED_PAMS", 0) != 0;
+        const bool fuse_pams = prep.n_fast_pams > 1 && variant_f == 1 && env_int("GSX_FUSED_PAMS", 1) != 0;
         auto run_fast_all_pams = [&](SearchArgs& m, uint32_t ng, uint32_t sb, cudaEvent_t ev_mid) {
             m.n_fused = 0;
             if (fuse_pams && !m.p.counting) {
@@ -824,7 +859,7 @@ static void run_device_job(DeviceJob* job) {
                 c.guide_count = d_gcount; c.spill = d_spill; c.skip = nullptr; c.matches = nullptr;
                 if (use_fast) run_fast_all_pams(c, n, sb_thr, nullptr); else { CK(launch_search(c, false, variant_n, di.sm_count, s, nullptr)); n_launches++; }
                 upload_guides(s2);
-                uint32_t h[3]; CK(cudaMemcpyAsync(h, d_ctrs, sizeof h, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s));
+                uint32_t h[3]; read_ctrs(h, 3, d_ctrs); n_launches++;
                 B.free_one(d_spill);
                 if (h[2] & GSX_KERR_WATCHDOG) throw std::runtime_error("search kernel watchdog tripped");
                 if (h[2] & GSX_KERR_QUEUE_OVERFLOW) { grow_queue(); if (h[2] & GSX_KERR_SPILL_OVERFLOW) spill_cap *= 4; continue; }
@@ -865,6 +900,7 @@ static void run_device_job(DeviceJob* job) {
             CK(cudaStreamSynchronize(s));
             const uint32_t chunk_v = (uint32_t)std::min<int64_t>(std::max<int64_t>(env_int("GSX_VARIANT_CHUNK", 262144), 1), (1 << 22));
             const uint32_t vmin_qlen = prep.min_qlen > R ? prep.min_qlen - R : 0;
+            lean_qmin = vmin_qlen; lean_qmax = prep.max_qlen + D;
             const int warps = search_fast_grid_warps(variant_f, di.sm_count);
             if (warps <= 0) throw std::runtime_error("unknown search kernel variant");
             if (d_queue) { B.free_one(d_queue); d_queue = nullptr; }               // (sized by the threshold pass)
@@ -876,8 +912,9 @@ static void run_device_job(DeviceJob* job) {
             spill_cap = 2048; if (env_int("GSX_SPILL_CAP", 0) > 0) spill_cap = (uint32_t)env_int("GSX_SPILL_CAP", 0);
             uint64_t* d_vq = B.alloc<uint64_t>(chunk_v + 1); uint32_t* d_vdesc = B.alloc<uint32_t>(chunk_v + 1); uint32_t* d_vguide = B.alloc<uint32_t>(chunk_v + 1);
             uint32_t* d_vnmatch = B.alloc<uint32_t>(chunk_v + 1);
-            // GSX_FORCED_SWEEP=1 (opt-in, host-mirrored, not yet run on a GPU): the sweep skips patterns that substitute an inserted position
-            uint32_t* d_vfmask = env_int("GSX_FORCED_SWEEP", 0) ? B.alloc<uint32_t>(chunk_v + 1) : nullptr;
+            // the sweep skips patterns that substitute an inserted position (GSX_FORCED_SWEEP=0: it tests them and the rewrite drops their
+            // matches; 11 % fewer seeds, 1.4 % less search time at 3.1 Gb)
+            uint32_t* d_vfmask = env_int("GSX_FORCED_SWEEP", 1) ? B.alloc<uint32_t>(chunk_v + 1) : nullptr;
             uint32_t* d_voff = nullptr; size_t voff_cap = 0;
             MatchRec* d_vmatches = B.alloc<MatchRec>(vmatch_cap);
             d_matches = B.alloc<MatchRec>(match_cap);
@@ -916,7 +953,7 @@ static void run_device_job(DeviceJob* job) {
                         m.p.match_cap = (uint32_t)vmatch_cap; m.p.spill_cap = spill_cap; m.spill = d_spill; m.matches = d_vmatches;
                         m.skip = nullptr; m.gq = d_vq; m.guide_nmatch = d_vnmatch; m.guides = nullptr; m.fmask = d_vfmask;
                         run_fast_all_pams(m, n_v, sb, nullptr);
-                        uint32_t h[4]; CK(cudaMemcpyAsync(h, d_ctrs, sizeof h, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s));
+                        uint32_t h[4]; read_ctrs(h, 4, d_ctrs); n_launches++;
                         B.free_one(d_spill);
                         if (h[2] & GSX_KERR_WATCHDOG) throw std::runtime_error("search kernel watchdog tripped");
                         if (h[2] & (GSX_KERR_MATCH_OVERFLOW | GSX_KERR_SPILL_OVERFLOW | GSX_KERR_QUEUE_OVERFLOW)) {
@@ -941,7 +978,7 @@ static void run_device_job(DeviceJob* job) {
                         }
                         CK(launch_variant_rewrite(d_vmatches, h[1], d_guides, d_vdesc, d_vguide, d_matches, (uint32_t)match_cap, d_ctrs + 5, d_nmatch, d_ctrs + 2, s));
                         n_launches++;
-                        CK(cudaMemcpyAsync(&n_final, d_ctrs + 5, 4, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s));
+                        read_ctrs(&n_final, 1, d_ctrs + 5); n_launches++;
                         break;
                     }
                 }
@@ -976,7 +1013,7 @@ static void run_device_job(DeviceJob* job) {
             CK(cudaEventRecord(ev[6], s));
             if (use_fast) run_fast_all_pams(m, n, sweep_sb, ev[7]); else { CK(cudaEventRecord(ev[7], s)); CK(launch_search(m, wide, variant, di.sm_count, s, nullptr)); n_launches++; }
             upload_guides(s2);
-            uint32_t h[4]; CK(cudaMemcpyAsync(h, d_ctrs, sizeof h, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s));
+            uint32_t h[4]; read_ctrs(h, 4, d_ctrs); n_launches++;
             B.free_one(d_spill);
             if (h[2] & GSX_KERR_WATCHDOG) throw std::runtime_error("search kernel watchdog tripped");
             if (h[2] & (GSX_KERR_MATCH_OVERFLOW | GSX_KERR_SPILL_OVERFLOW | GSX_KERR_QUEUE_OVERFLOW)) {
@@ -1015,9 +1052,12 @@ static void run_device_job(DeviceJob* job) {
             CK(launch_scatter(d_matches, n_matches, d_moff, d_cursor, d_by_guide, s));
             CK(launch_order(d_matches, d_moff, d_by_guide, n, n_dist, d_sorted, d_sorted_off, d_nhits, d_cbd, order_mode == 1, s));
         }
-        {   // total hits can exceed 2^32 only for absurd inputs; the scan is 32-bit, so check with a 64-bit host sum
-            CK(cudaMemcpyAsync(H.n_hits_of, d_nhits, (size_t)n * 4, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s));
-            uint64_t tot = 0; for (uint32_t i = 0; i < n; i++) tot += H.n_hits_of[i];
+        {   // total hits can exceed 2^32 only for absurd inputs; the scan is 32-bit, so the total is a 64-bit sum (device-side, stored
+            // into the mailbox: the per-guide counts themselves travel with the other result arrays at the end)
+            unsigned long long* d_tot = B.alloc<unsigned long long>(2, true, s);
+            CK(launch_total_u32(d_nhits, n, d_tot, reinterpret_cast<unsigned int*>(d_tot + 1), reinterpret_cast<unsigned long long*>(mbox.p + 32), s)); n_launches++;
+            CK(cudaStreamSynchronize(s));
+            const uint64_t tot = *reinterpret_cast<volatile unsigned long long*>(mbox.p + 32);
             if (tot >= (1ull << 32)) throw std::runtime_error("more than 2^32 hits in one batch; lower the batch size");
             H.n_hits = (size_t)tot;
         }
@@ -1054,7 +1094,7 @@ static void run_device_job(DeviceJob* job) {
         H.strand = H.alloc<uint8_t>(nh); H.distance = H.alloc<uint8_t>(nh); H.rna = H.alloc<uint8_t>(nh); H.dna = H.alloc<uint8_t>(nh);
         H.index_id = H.alloc<uint8_t>(nh); H.cfd = H.alloc<float>(nh); H.counted = H.alloc<uint8_t>(nh); H.hit_match = H.alloc<uint32_t>(nh);
         auto d2h = [&](void* dst, const void* src, size_t bytes) { if (bytes) CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s)); };
-        d2h(H.dropped, d_dropped, n); d2h(H.hoff, d_hoff, (size_t)(n + 1) * 4); d2h(H.specificity, S.specificity, (size_t)n * 4);
+        d2h(H.dropped, d_dropped, n); d2h(H.hoff, d_hoff, (size_t)(n + 1) * 4); d2h(H.n_hits_of, d_nhits, (size_t)n * 4); d2h(H.specificity, S.specificity, (size_t)n * 4);
         d2h(H.perfect, S.perfect, n); d2h(H.cbd, d_cbd, (size_t)n * n_dist * 4);
         d2h(H.abs_pos, L.abs_pos, (size_t)nh * 8); d2h(H.sa_row, d_hit_row, (size_t)nh * 4); d2h(H.chr, L.chr, (size_t)nh * 4);
         d2h(H.pos1, L.pos1, (size_t)nh * 4); d2h(H.strand, L.strand, nh); d2h(H.distance, L.distance, nh); d2h(H.rna, L.rna, nh);

@@ -572,6 +572,65 @@ GSX_HD void summary_masks(uint32_t codes, uint32_t gm[15]) {
     }
     gm[14] = pflags;
 }
+// The plane layouts the lean sweep loops (sweep_lean_kernel) are compiled for: which of the seven planes hold a protospacer level
+// and which a concrete PAM character; every other plane is a wildcard or lies behind the guide's last level.  They cover 19-21 nt
+// guides with an NGG-type PAM at L = 14 (plain guides and the edited forms of a bulge search) and every guide whose seven planes
+// are all protospacer (smaller genomes: L <= 13).  -1: some other layout (the general loops of sweep_kernel handle it).
+//   shape 0: 111111.  (20 nt at L = 14: six protospacer levels, the PAM wildcard)      shape 1: 1111111  (seven protospacer levels)
+//   shape 2: 11111.P  (19 nt at L = 14: five protospacer levels, the wildcard, the first concrete PAM character)
+constexpr int kSweepShapes = 3;
+GSX_HD uint32_t sweep_shape_proto(int s) { return s == 0 ? 0x3Fu : s == 1 ? 0x7Fu : 0x1Fu; }
+GSX_HD uint32_t sweep_shape_pam(int s) { return s == 2 ? 0x40u : 0u; }
+GSX_HD int sweep_shape_of(uint32_t codes) {
+    uint32_t proto = 0, pam = 0;
+    for (uint32_t j = 0; j < 7u; j++) {
+        const uint32_t c = (codes >> (4u * j)) & 15u;
+        if (c < 4u) proto |= 1u << j;
+        else if (c >= 8u && c < 12u) pam |= 1u << j;
+        else if (c != 7u && c != 12u) return -1;                                  // a PAM character that can never match
+    }
+    for (int s = 0; s < kSweepShapes; s++) if (sweep_shape_proto(s) == proto && sweep_shape_pam(s) == pam) return s;
+    return -1;
+}
+// The evaluation with the plane layout as a compile-time constant (sweep_lean_kernel): X = gm + 7 of summary_masks; no "A" words,
+// unused planes cost nothing.  Equal to summary_eval_exact / summary_eval_masks for every guide of that layout (tests/host_core_check).
+template <uint32_t USED>
+GSX_HD uint32_t summary_exact_shape(const uint32_t w[8], const uint32_t X[7]) {
+    uint32_t acc = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int j = 0; j < 7; j++) if (USED & (1u << j)) acc |= w[1 + j] ^ X[j];
+    return w[0] & ~(acc | (acc >> 16)) & 0xFFFFu;
+}
+template <uint32_t PROTO, uint32_t PAM, int NB>
+GSX_HD void summary_masks_shape(const uint32_t w[8], const uint32_t X[7], uint32_t budget, uint32_t u[NB]) {
+    const uint32_t valid = w[0] & 0xFFFFu;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int r = 0; r < NB; r++) u[r] = budget >= (uint32_t)r ? valid : 0u;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int j = 0; j < 7; j++) {
+        if (!((PROTO | PAM) & (1u << j))) continue;
+        const uint32_t y = w[1 + j] ^ X[j];
+        const uint32_t eq = ~(y | (y >> 16));
+        if (PROTO & (1u << j)) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (int r = 0; r + 1 < NB; r++) u[r] = (u[r] & eq) | u[r + 1];
+            u[NB - 1] &= eq;
+        } else {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (int r = 0; r < NB; r++) u[r] &= eq;
+        }
+    }
+}
 // no budget left: every differing row dies, whatever the level
 GSX_HD uint32_t summary_eval_exact(const uint32_t w[8], const uint32_t gm[15]) {
     uint32_t acc = 0;

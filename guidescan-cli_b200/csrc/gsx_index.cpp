@@ -271,6 +271,9 @@ void sweep_make_plan(uint32_t L, uint32_t sb, uint32_t M, SweepPlan& plan, std::
         for (uint32_t j = 0; j < B; j++) xtab.insert(xtab.end(), by_count[j].begin(), by_count[j].end());
         plan.xcnt[0][B] = (uint32_t)xtab.size() - plan.xoff[0][B];
     }
+    for (uint32_t z = 0; z < 2; z++)
+        for (uint32_t B = 0; B <= M; B++)
+            for (uint32_t t = 0; t < plan.xcnt[z][B]; t++) if ((xtab[plan.xoff[z][B] + t] & 15u) == 0u) plan.xlines[z][B]++;
 }
 
 // ---- native cache format (<prefix>.gsx): a flat dump of the HBM layout ----------------------------------------

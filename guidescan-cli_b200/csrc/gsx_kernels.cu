@@ -915,8 +915,8 @@ __device__ __forceinline__ void cont_process(const SweepArgs& a, ContBuf& cb, ui
 //   [0..6] A, [7..13] X, [14] pflags (gsx_core.h summary_masks)   [15] low 2(L-sb) bits of the packed guide
 //   [16] plane codes of levels L .. L+6   [17] of levels L+7, L+8
 constexpr int CB_SLOTS = 64;          // parked nodes per warp: drained below 32 before every step, which adds at most 32
-constexpr int XT_SMEM = 4352;          // words of shared memory for the xor table (17 KB)
-constexpr int GT_WORDS = 20, GT_QLOW = 15, GT_CODES = 16, GT_CODES2 = 17, GT_FMASK = 18;      // [18] must-match positions of an edited guide (index mask)
+constexpr int XT_SMEM = kSweepXtabShared;
+constexpr int GT_WORDS = 20, GT_QLOW = 15, GT_CODES = 16, GT_CODES2 = 17, GT_FMASK = 18, GT_SHAPE = 19;      // [18] must-match positions of an edited guide (index mask)
 
 __global__ void sweep_guides_kernel(SweepArgs a, uint32_t* __restrict__ gtab) {
     for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < a.n_guides; g += gridDim.x * blockDim.x) {
@@ -925,7 +925,7 @@ __global__ void sweep_guides_kernel(SweepArgs a, uint32_t* __restrict__ gtab) {
         const uint32_t codes = sweep_codes(q, a.plan.L, a.plen, a.pampack);
         summary_masks(codes, t);
         t[GT_QLOW] = (uint32_t)q & ((1u << (2u * (a.plan.L - a.plan.sb))) - 1u);
-        t[GT_CODES] = codes; t[GT_CODES2] = sweep_codes2(q, a.plan.L, a.plen, a.pampack); t[GT_FMASK] = a.fmask ? a.fmask[g] : 0u; t[19] = 0;
+        t[GT_CODES] = codes; t[GT_CODES2] = sweep_codes2(q, a.plan.L, a.plen, a.pampack); t[GT_FMASK] = a.fmask ? a.fmask[g] : 0u; t[GT_SHAPE] = (uint32_t)sweep_shape_of(codes);
         uint4* dst = reinterpret_cast<uint4*>(gtab + (size_t)g * GT_WORDS);
         for (int k = 0; k < GT_WORDS / 4; k++) dst[k] = make_uint4(t[4 * k], t[4 * k + 1], t[4 * k + 2], t[4 * k + 3]);
     }
@@ -1090,6 +1090,295 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) sweep_kernel(SweepArgs a) {
     if (lane == 0) { atomicAdd(a.stats + 0, n_nodes); atomicAdd(a.stats + 1, n_lookups); atomicAdd(a.stats + 5, (unsigned long long)st.sectors); }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// sweep_lean_kernel: the same enumeration as sweep_kernel with the inner loops rewritten around what ncu showed on the 3.1 Gb
+// workload (profiles/r01ac_sweep_kernel_*): 188 warp instructions per 32 patterns, the whole register file at 50 % occupancy,
+// one summary load in flight per lane.  Here
+//   * the loops are compiled per PLANE LAYOUT (gsx_core.h sweep_shape_of): which planes count is a template constant, so a
+//     pattern without budget costs one LOP3 per used plane (acc |= w ^ X); the guide's seven X words are the same in every
+//     lane of a run and end up in uniform registers.  A run picks its loop by the guide's layout (the edited guides of a bulge
+//     search mix 19, 20 and 21 characters);
+//   * the patterns that use the budget up (nine tenths) are taken 64 per iteration: both summary sectors of a lane are
+//     requested before the first is looked at;
+//   * nodes with more than 16 rows whose first 16 are dead are parked as ONE word (the table index; everything else is the
+//     run's) and drained 32 at a time by the same compiled loop body over sum1 -- no general evaluator, no per-record codes;
+//   * loads are predicated instead of branched around, the xor table is always in shared memory (the host sends batches whose
+//     table does not fit to sweep_kernel), per-guide constants come straight from the global table (no staging copy), the
+//     unsubstituted-pattern step tests "at most one mismatch" with two masks instead of four and reads its second sector
+//     in place;
+//   * 20 KB of shared memory per 256 threads instead of 47 and 38-55 registers: five or six CTAs per SM fit.
+// Same seeds, same counters as sweep_kernel (the tests run both).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int PK_SLOTS = 96;           // parked table indices per warp: drained below 32 at the top of an iteration, which adds at most 64
+
+// predicated 32-byte summary load (L2 only): lanes without a pattern get w[0] = 0, i.e. an empty node (their other words are
+// whatever the registers held: every use is masked by w[0])
+__device__ __forceinline__ void lean_load(const unsigned char* sum, uint32_t idx, bool live, uint32_t w[8]) {
+    w[0] = 0u;
+#pragma unroll
+    for (int j = 1; j < 8; j++) w[j] = 0u;
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %9, 0;\n\t@p ld.global.cg.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n\t}"
+                 : "+r"(w[0]), "+r"(w[1]), "+r"(w[2]), "+r"(w[3]), "+r"(w[4]), "+r"(w[5]), "+r"(w[6]), "+r"(w[7])
+                 : "l"(sum + ((size_t)idx << 5)), "r"((uint32_t)live));
+}
+
+struct LeanRun {                       // warp-uniform: one guide in one slice of one strand
+    const unsigned char* sum0; const unsigned char* sum1; const unsigned char* sum2;
+    const FtabEntry* tab;
+    uint32_t qh;                       // table index of the unsubstituted pattern: slice characters | the guide's other characters
+    uint32_t X[7];                     // gsx_core.h summary_masks
+    uint32_t codes2, tl, fm;
+};
+struct LeanStats { uint32_t nodes, two, lines, sectors; };      // nodes, two (nodes over two 64-row blocks): per lane; lines, sectors: warp-uniform
+struct ParkBuf { uint32_t* idx; uint32_t count; };               // count: warp-uniform
+
+// surviving level-L node -> seed queue (as sweep_emit)
+__device__ __forceinline__ void lean_emit(const SweepArgs& a, uint32_t lane, bool emit, uint32_t idx, uint32_t tlm, const FtabEntry* tab) {
+    const uint32_t emask = __ballot_sync(0xffffffffu, emit);
+    if (!emask) return;
+    uint32_t qbase = 0; const int leader = __ffs(emask) - 1;
+    if ((int)lane == leader) qbase = atomicAdd(a.queue_count, (uint32_t)__popc(emask));
+    qbase = __shfl_sync(0xffffffffu, qbase, leader);
+    if (emit) {
+        const uint32_t slot = qbase + __popc(emask & ((1u << lane) - 1u));
+        if (slot < a.queue_cap) {
+            const uint2 e = __ldg(reinterpret_cast<const uint2*>(tab + idx));
+            SeedNode sn; sn.sp = e.x; sn.ep = e.x + e.y - 1u; sn.idx = idx; sn.tlm = (tlm & 0x07FFFFFFu) | (a.plan.L << 27);
+            a.queue[slot] = sn;
+        } else atomicOr(a.error_flag, GSX_KERR_QUEUE_OVERFLOW);
+    }
+}
+// word = table index | remaining budget << 28 of a node to look at again in sum1
+__device__ __forceinline__ void lean_park(ParkBuf& pk, uint32_t lane, bool park, uint32_t word) {
+    const uint32_t m = __ballot_sync(0xffffffffu, park);
+    if (!m) return;
+    if (park) pk.idx[pk.count + __popc(m & ((1u << lane) - 1u))] = word;
+    pk.count += __popc(m);
+    __syncwarp();
+}
+// one judged first sector: counters, then nothing (empty node / no row left), the seed queue, or the parking buffer
+__device__ __forceinline__ void lean_settle(const SweepArgs& a, ParkBuf& pk, uint32_t lane, uint32_t w0, uint32_t alive, uint32_t idx, uint32_t budget,
+                                            uint32_t tlm, const FtabEntry* tab, LeanStats& st) {
+    // (w0 == 0 for lanes without a pattern and for empty table entries; the flags are only ever set on non-empty ones)
+    const bool emit = (alive | (w0 & SUM_WIDE32)) != 0u;                             // (more than 32 rows: not summarised, the tree search takes it)
+    const bool park = !emit && (w0 & SUM_WIDE16) != 0u;
+    st.nodes += (w0 & 0xFFFFu) ? 1u : 0u;
+    st.two += (w0 & SUM_TWO_BLOCKS) ? 1u : 0u;
+    lean_emit(a, lane, emit, idx, tlm, tab);
+    lean_park(pk, lane, park, idx | (budget << 28));
+}
+// up to 32 parked nodes of the current pass: rows 16..31 of their intervals
+template <uint32_t PROTO, uint32_t PAM, int NB, bool EXACT>
+__device__ __forceinline__ void lean_drain(const SweepArgs& a, ParkBuf& pk, uint32_t lane, const LeanRun& r, uint32_t tl_m, LeanStats& st) {
+    const uint32_t n = pk.count < 32u ? pk.count : 32u;
+    const bool mine = lane < n;
+    const uint32_t word = mine ? pk.idx[pk.count - n + lane] : 0u;
+    __syncwarp();
+    pk.count -= n; st.sectors += n;
+    const uint32_t idx = word & 0x0FFFFFFFu, budget = word >> 28;
+    uint32_t w[8];
+    lean_load(r.sum1, idx, mine, w);
+    const bool tail = r.sum2 != nullptr && sweep_has_tail(r.codes2);
+    uint32_t alive;
+    if (EXACT) {
+        alive = summary_exact_shape<PROTO | PAM>(w, r.X);
+        if (alive && tail) { uint32_t t[4], v[1] = {alive}; load_tail(r.sum2, idx, t); summary_tail<1>(t, 1u, r.codes2, v); alive = v[0]; }
+    } else {
+        uint32_t u[NB];
+        summary_masks_shape<PROTO, PAM, NB>(w, r.X, budget, u);
+        if (u[0] && tail) { uint32_t t[4]; load_tail(r.sum2, idx, t); summary_tail<NB>(t, 1u, r.codes2, u); }
+        alive = u[0];
+    }
+    // tl_m: task | M << 24; mismatches used so far = M - budget
+    lean_emit(a, lane, alive != 0u, idx, (tl_m - (budget << 24)) | (budget << 27), r.tab);
+}
+
+// the patterns of pass 1 (exactly B substitutions outside the slice: no budget left), 64 per iteration
+template <uint32_t USED, int NB, bool FORCED>
+__device__ __forceinline__ void lean_exact_pass(const SweepArgs& a, ParkBuf& pk, const uint32_t* xt, uint32_t n, uint32_t n_lines, uint32_t lane,
+                                                const LeanRun& r, uint32_t tl_m, LeanStats& st) {
+    if (n == 0u) return;
+    const bool tail = r.sum2 != nullptr && sweep_has_tail(r.codes2);
+    if constexpr (!FORCED) { st.sectors += n; st.lines += n_lines; }
+    for (uint32_t base = 0; base < n; base += 64u) {
+        while (pk.count >= 32u) lean_drain<USED, 0u, NB, true>(a, pk, lane, r, tl_m, st);
+        const bool two = base + 32u < n;                                             // warp-uniform: a second 32 patterns in this iteration
+        const uint32_t t0 = base + lane, t1 = t0 + 32u;
+        bool live0 = t0 < n, live1 = t1 < n;
+        const uint32_t x0 = xt[t0], x1 = xt[t1];                                     // (the shared table has 64 readable words behind its end)
+        if constexpr (FORCED) {                                                      // patterns that substitute a must-match position are skipped
+            live0 = live0 && !(x0 & r.fm); live1 = live1 && !(x1 & r.fm);
+            const uint32_t b0 = __ballot_sync(0xffffffffu, live0), b1 = __ballot_sync(0xffffffffu, live1);
+            st.sectors += __popc(b0) + __popc(b1);
+            st.lines += __popc(__ballot_sync(0xffffffffu, live0 && (x0 & 15u) == 0u)) + __popc(__ballot_sync(0xffffffffu, live1 && (x1 & 15u) == 0u));
+        }
+        const uint32_t idx0 = r.qh ^ (x0 & 0x0FFFFFFFu), idx1 = r.qh ^ (x1 & 0x0FFFFFFFu);
+        uint32_t w0[8], w1[8];
+        lean_load(r.sum0, idx0, live0, w0);
+        lean_load(r.sum0, idx1, live1, w1);                                          // (predicated off as a whole when there is no second 32)
+        uint32_t al0 = summary_exact_shape<USED>(w0, r.X), al1 = two ? summary_exact_shape<USED>(w1, r.X) : 0u;
+        if (!two) w1[0] = 0u;
+        if (al0 && tail && !(w0[0] & SUM_WIDE32)) { uint32_t t[4], v[1] = {al0}; load_tail(r.sum2, idx0, t); summary_tail<1>(t, 0u, r.codes2, v); al0 = v[0]; }
+        if (al1 && tail && !(w1[0] & SUM_WIDE32)) { uint32_t t[4], v[1] = {al1}; load_tail(r.sum2, idx1, t); summary_tail<1>(t, 0u, r.codes2, v); al1 = v[0]; }
+        // (w[0] == 0 for lanes without a pattern and for empty table entries; the flags are only ever set on non-empty ones)
+        const bool emit0 = (al0 | (w0[0] & SUM_WIDE32)) != 0u, emit1 = (al1 | (w1[0] & SUM_WIDE32)) != 0u;      // (more than 32 rows: the tree search takes it)
+        const bool park0 = !emit0 && (w0[0] & SUM_WIDE16) != 0u, park1 = !emit1 && (w1[0] & SUM_WIDE16) != 0u;
+        st.nodes += ((w0[0] & 0xFFFFu) ? 1u : 0u) + ((w1[0] & 0xFFFFu) ? 1u : 0u);
+        st.two += ((w0[0] & SUM_TWO_BLOCKS) ? 1u : 0u) + ((w1[0] & SUM_TWO_BLOCKS) ? 1u : 0u);
+        if (__any_sync(0xffffffffu, emit0 || emit1)) { lean_emit(a, lane, emit0, idx0, tl_m, r.tab); lean_emit(a, lane, emit1, idx1, tl_m, r.tab); }
+        const uint32_t m0 = __ballot_sync(0xffffffffu, park0), m1 = __ballot_sync(0xffffffffu, park1);
+        if (m0 | m1) {
+            const uint32_t lt = (1u << lane) - 1u;
+            if (park0) pk.idx[pk.count + __popc(m0 & lt)] = idx0;
+            if (park1) pk.idx[pk.count + __popc(m0) + __popc(m1 & lt)] = idx1;
+            pk.count += __popc(m0) + __popc(m1);
+            __syncwarp();
+        }
+    }
+    while (pk.count) lean_drain<USED, 0u, NB, true>(a, pk, lane, r, tl_m, st);
+}
+// the patterns of pass 0 (fewer than B substitutions outside the slice: budget left), 32 per iteration
+template <uint32_t PROTO, uint32_t PAM, int NB, bool FORCED>
+__device__ __forceinline__ void lean_budget_pass(const SweepArgs& a, ParkBuf& pk, const uint32_t* xt, uint32_t n, uint32_t n_lines, uint32_t lane,
+                                                 const LeanRun& r, uint32_t B, uint32_t tl_m, LeanStats& st) {
+    if (n == 0u) return;
+    const bool tail = r.sum2 != nullptr && sweep_has_tail(r.codes2);
+    if constexpr (!FORCED) { st.sectors += n; st.lines += n_lines; }
+    for (uint32_t base = 0; base < n; base += 32u) {
+        while (pk.count >= 32u) lean_drain<PROTO, PAM, NB, false>(a, pk, lane, r, tl_m, st);
+        const uint32_t t = base + lane;
+        bool live = t < n;
+        const uint32_t xw = xt[t];
+        if constexpr (FORCED) {
+            live = live && !(xw & r.fm);
+            st.sectors += __popc(__ballot_sync(0xffffffffu, live)); st.lines += __popc(__ballot_sync(0xffffffffu, live && (xw & 15u) == 0u));
+        }
+        const uint32_t idx = r.qh ^ (xw & 0x0FFFFFFFu), budget = B - (xw >> 28);
+        uint32_t w[8];
+        lean_load(r.sum0, idx, live, w);
+        uint32_t u[NB];
+        summary_masks_shape<PROTO, PAM, NB>(w, r.X, budget, u);
+        if (u[0] && tail && !(w[0] & SUM_WIDE32)) { uint32_t tt[4]; load_tail(r.sum2, idx, tt); summary_tail<NB>(tt, 0u, r.codes2, u); }
+        lean_settle(a, pk, lane, w[0], u[0], idx, budget, (tl_m - (budget << 24)) | (budget << 27), r.tab, st);
+    }
+    while (pk.count) lean_drain<PROTO, PAM, NB, false>(a, pk, lane, r, tl_m, st);
+}
+template <int SHAPE, int NB, bool FORCED>
+__device__ __forceinline__ void lean_run(const SweepArgs& a, const SweepPlan& pl, ParkBuf& pk, const uint32_t* xtab, uint32_t lane, const LeanRun& r,
+                                         uint32_t B, LeanStats& st) {
+    constexpr uint32_t PROTO = SHAPE == 0 ? 0x3Fu : SHAPE == 1 ? 0x7Fu : 0x1Fu, PAM = SHAPE == 2 ? 0x40u : 0u;
+    const uint32_t tl_m = r.tl | (a.M << 24);
+    lean_exact_pass<PROTO | PAM, NB, FORCED>(a, pk, xtab + pl.xoff[1][B], pl.xcnt[1][B], pl.xlines[1][B], lane, r, tl_m, st);
+    if (B >= 2u) lean_budget_pass<PROTO, PAM, NB, FORCED>(a, pk, xtab + pl.xoff[0][B], pl.xcnt[0][B], pl.xlines[0][B], lane, r, B, tl_m, st);
+}
+
+// the unsubstituted pattern of one guide (its row of the guide table: any plane layout) against one summary sector, budget 0 or 1:
+// rows still alive after the seven planes and, where the guide has them, the two levels behind (sum2)
+__device__ __forceinline__ uint32_t lean_unit_eval(const uint32_t* __restrict__ row, const unsigned char* sum, const unsigned char* sum2, uint32_t idx,
+                                                   uint32_t B, uint32_t half, uint32_t& w0) {
+    const uint4* gp = reinterpret_cast<const uint4*>(row);
+    const uint4 g0 = __ldg(gp), g1 = __ldg(gp + 1), g2 = __ldg(gp + 2), g3 = __ldg(gp + 3);
+    const uint32_t gm[15] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w, g2.x, g2.y, g2.z, g2.w, g3.x, g3.y, g3.z};
+    const uint32_t codes2 = __ldg(row + GT_CODES2);
+    uint32_t w[8];
+    lean_load(sum, idx, true, w);
+    w0 = w[0];
+    uint32_t u[2];
+    summary_eval_masks<2>(w, gm, B, u);
+    if (u[0] && sum2 && sweep_has_tail(codes2) && !(w0 & SUM_WIDE32)) { uint32_t t[4]; load_tail(sum2, idx, t); summary_tail<2>(t, half, codes2, u); }
+    return u[0];
+}
+
+// XTG: the xor table is too long for shared memory (4 mismatches: 15.8 k words) and is read from global memory (unit stride,
+// the same few KB by every warp: L1 hits); the host pads it with 64 readable words
+template <int WARPS, int MINB, int NB, bool FORCED = false, bool XTG = false>
+__global__ void __launch_bounds__(WARPS * 32, MINB) sweep_lean_kernel(SweepArgs a) {
+    __shared__ SweepPlan s_plan;
+    __shared__ uint32_t s_park[WARPS][PK_SLOTS];
+    __shared__ uint32_t s_xtab_[XTG ? 1 : XT_SMEM];
+    for (int i = threadIdx.x; i < (int)(sizeof(SweepPlan) / 4); i += blockDim.x)
+        reinterpret_cast<uint32_t*>(&s_plan)[i] = reinterpret_cast<const uint32_t*>(&a.plan)[i];
+    if constexpr (!XTG) for (uint32_t i = threadIdx.x; i < (uint32_t)XT_SMEM; i += blockDim.x) s_xtab_[i] = i < a.n_xtab ? a.xtab[i] : 0u;
+    const uint32_t* const s_xtab = XTG ? a.xtab : s_xtab_;
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, FULL = 0xffffffffu;
+    ParkBuf pk; pk.idx = s_park[warp]; pk.count = 0;
+    const uint32_t L = s_plan.L, sb = s_plan.sb, M = a.M;
+    const uint32_t n_slices = 1u << (2u * sb), n_gb = (a.n_guides + 31u) >> 5;
+    const uint32_t items_per_strand = n_slices * n_gb, n_items = 2u * items_per_strand;      // (the host keeps this below 2^32)
+    LeanStats st = {0, 0, 0, 0};
+    for (;;) {
+        uint32_t item = 0;
+        if (lane == 0) item = atomicAdd(a.item_counter, 1u);
+        item = __shfl_sync(FULL, item, 0);
+        if (item >= n_items) break;
+        const uint32_t strand = item >= items_per_strand ? 1u : 0u;
+        const uint32_t rem = item - (strand ? items_per_strand : 0u);
+        const uint32_t beta = rem / n_gb, gb = rem - beta * n_gb;
+        const uint32_t g = gb * 32u + lane;
+        const bool valid = g < a.n_guides && !(a.skip && a.skip[g]);
+        const unsigned char* sum0 = strand ? a.st[1].sum0 : a.st[0].sum0;
+        const unsigned char* sum1 = strand ? a.st[1].sum1 : a.st[0].sum1;
+        const unsigned char* sum2 = strand ? a.st[1].sum2 : a.st[0].sum2;
+        const FtabEntry* tab = reinterpret_cast<const FtabEntry*>(strand ? a.st[1].ftab : a.st[0].ftab);
+        const uint32_t hi_bits = beta << (2u * (L - sb));
+        int B = -1;
+        if (valid) {
+            const uint64_t q = __ldg(a.gq + g);
+            const uint32_t h = sweep_slice_distance(q, L, sb, beta);
+            if (h <= M) B = (int)(M - h);
+            if constexpr (FORCED) {      // the slice substitutes a must-match position of this (edited) guide: nothing to do here
+                const uint32_t top = (uint32_t)(q >> (2u * (L - sb))) & ((1u << (2u * sb)) - 1u);
+                if ((top ^ beta) & (__ldg(a.gtab + (size_t)g * GT_WORDS + GT_FMASK) >> (2u * (L - sb)))) B = -1;
+            }
+        }
+        // (1) guides whose only pattern in this slice is the unsubstituted one (budget 0), and the unsubstituted pattern of the guides
+        //     with budget 1: one pattern per lane, each lane with its own guide's masks (any plane layout); a node with more than 16
+        //     rows whose first 16 are dead reads its second sector right here
+        {
+            const bool mine = B == 0 || B == 1;
+            const uint32_t mmask = __ballot_sync(FULL, mine);
+            st.sectors += __popc(mmask); st.lines += __popc(mmask);                  // (the unsubstituted pattern opens its table line)
+            uint32_t idx = 0, alive = 0, w0 = 0;
+            bool more = false;
+            if (mine) {
+                idx = hi_bits | __ldg(a.gtab + (size_t)g * GT_WORDS + GT_QLOW);
+                alive = lean_unit_eval(a.gtab + (size_t)g * GT_WORDS, sum0, sum2, idx, (uint32_t)B, 0u, w0);
+                more = alive == 0u && !(w0 & SUM_WIDE32) && (w0 & SUM_WIDE16);
+            }
+            const uint32_t moremask = __ballot_sync(FULL, more);
+            if (moremask) {
+                st.sectors += __popc(moremask);
+                uint32_t w1;
+                if (more) alive = lean_unit_eval(a.gtab + (size_t)g * GT_WORDS, sum1, sum2, idx, (uint32_t)B, 1u, w1);
+            }
+            st.nodes += (w0 & 0xFFFFu) ? 1u : 0u;
+            st.two += (w0 & SUM_TWO_BLOCKS) ? 1u : 0u;
+            const uint32_t Bp = (uint32_t)(B > 0 ? B : 0);
+            lean_emit(a, lane, (alive | (w0 & SUM_WIDE32)) != 0u, idx, ((g << 1) | strand) | ((M - Bp) << 24) | (Bp << 27), tab);
+        }
+        // (2) guides with budget left after the slice characters, one at a time, all lanes on that guide's patterns
+        uint32_t todo = __ballot_sync(FULL, B >= 1);
+        while (todo) {
+            const uint32_t o = (uint32_t)__ffs(todo) - 1u; todo &= todo - 1u;
+            const uint32_t Bo = (uint32_t)__shfl_sync(FULL, B, o), go = gb * 32u + o;
+            const uint4* gp = reinterpret_cast<const uint4*>(a.gtab + (size_t)go * GT_WORDS);      // same address in every lane: one transaction
+            const uint4 g1 = __ldg(gp + 1), g2 = __ldg(gp + 2), g3 = __ldg(gp + 3), g4 = __ldg(gp + 4);
+            LeanRun r;
+            r.sum0 = sum0; r.sum1 = sum1; r.sum2 = sum2; r.tab = tab; r.qh = hi_bits | g3.w;
+            r.X[0] = g1.w; r.X[1] = g2.x; r.X[2] = g2.y; r.X[3] = g2.z; r.X[4] = g2.w; r.X[5] = g3.x; r.X[6] = g3.y;
+            r.codes2 = g4.y; r.fm = g4.z & 0x0FFFFFFFu; r.tl = (go << 1) | strand;
+            const uint32_t shape = g4.w;
+            if (shape == 0u) lean_run<0, NB, FORCED>(a, s_plan, pk, s_xtab, lane, r, Bo, st);
+            else if (shape == 1u) lean_run<1, NB, FORCED>(a, s_plan, pk, s_xtab, lane, r, Bo, st);
+            else lean_run<2, NB, FORCED>(a, s_plan, pk, s_xtab, lane, r, Bo, st);
+        }
+    }
+    unsigned long long n_nodes = st.nodes, n_two = st.two;
+    for (int o = 16; o; o >>= 1) { n_nodes += __shfl_xor_sync(FULL, n_nodes, o); n_two += __shfl_xor_sync(FULL, n_two, o); }
+    if (lane == 0) { atomicAdd(a.stats + 0, n_nodes); atomicAdd(a.stats + 1, n_nodes + n_two + st.lines); atomicAdd(a.stats + 5, (unsigned long long)st.sectors); }
+}
+
 cudaError_t launch_sweep_guides(const SweepArgs& a, cudaStream_t s) {
     sweep_guides_kernel<<<grid_for_n(a.n_guides, 256, 148 * 8), 256, 0, s>>>(a, a.gtab);
     return cudaGetLastError();
@@ -1103,8 +1392,22 @@ static cudaError_t launch_sweep_t(const SweepArgs& a, int sm_count, cudaStream_t
     else return cudaErrorInvalidValue;
     return cudaGetLastError();
 }
+template <int MINB>
+static cudaError_t launch_sweep_lean_t(const SweepArgs& a, int sm_count, cudaStream_t s) {
+    const bool shared_xt = a.n_xtab + 64u <= (uint32_t)XT_SMEM;                     // (else: a.xtab holds 64 readable words behind the table)
+    const dim3 grid(sm_count * MINB), block(8 * 32);
+    if (a.M <= 3 && shared_xt) {
+        if (a.fmask) sweep_lean_kernel<8, MINB, 4, true, false><<<grid, block, 0, s>>>(a); else sweep_lean_kernel<8, MINB, 4, false, false><<<grid, block, 0, s>>>(a);
+    } else if (a.M <= 4) {
+        if (a.fmask) sweep_lean_kernel<8, MINB, 5, true, true><<<grid, block, 0, s>>>(a); else sweep_lean_kernel<8, MINB, 5, false, true><<<grid, block, 0, s>>>(a);
+    } else return cudaErrorInvalidValue;
+    return cudaGetLastError();
+}
 cudaError_t launch_sweep(const SweepArgs& a, int variant, int sm_count, cudaStream_t s) {
     switch (variant) {
+    case 10: return launch_sweep_lean_t<4>(a, sm_count, s);   // lean loops, 1024 thr/SM
+    case 11: return launch_sweep_lean_t<5>(a, sm_count, s);   // 1280 thr/SM
+    case 12: return launch_sweep_lean_t<6>(a, sm_count, s);   // 1536 thr/SM
     case 0: return launch_sweep_t<8, 3>(a, sm_count, s);      // 768 thr/SM
     case 1: return launch_sweep_t<8, 2>(a, sm_count, s);      // 512 thr/SM
     case 2:                                                   // 1024 thr/SM
@@ -1409,6 +1712,34 @@ cudaError_t launch_specificity(const SpecArgs& a, cudaStream_t s) {
 }
 cudaError_t launch_threshold(const unsigned long long* gc, uint8_t* dropped, uint32_t n, cudaStream_t s) {
     threshold_kernel<<<grid_for(n, 256, 148 * 4), 256, 0, s>>>(gc, dropped, n); return cudaGetLastError();
+}
+// Small mid-pipeline read-backs (error flags and counts after a search launch, the hit total before the result arrays are
+// sized) go through a kernel that stores into pinned host memory instead of a cudaMemcpy: a copy would queue on the copy engine
+// behind the bulk result transfer of the PREVIOUS call when calls are pipelined (gsx_enumerate_start) -- measured: 12 ms of
+// waiting per 200 k-guide batch with two batches in flight.
+__global__ void publish_kernel(const uint32_t* __restrict__ src, uint32_t n, volatile uint32_t* dst) {
+    if (threadIdx.x < n) dst[threadIdx.x] = src[threadIdx.x];
+}
+cudaError_t launch_publish(const uint32_t* src, uint32_t n_words, uint32_t* host_dst, cudaStream_t s) {
+    publish_kernel<<<1, 32, 0, s>>>(src, n_words < 32u ? n_words : 32u, host_dst);
+    return cudaGetLastError();
+}
+// 64-bit total of n 32-bit counts, stored into pinned host memory (dst[0]); *scratch must be zero
+__global__ void total_u32_kernel(const uint32_t* __restrict__ in, uint32_t n, unsigned long long* scratch, unsigned int* done, volatile unsigned long long* dst) {
+    unsigned long long acc = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) acc += in[i];
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(scratch, acc);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(done, 1u) == gridDim.x - 1) { __threadfence(); dst[0] = atomicAdd(scratch, 0ull); }      // last block out publishes
+    }
+}
+cudaError_t launch_total_u32(const uint32_t* in, uint32_t n, unsigned long long* scratch, unsigned int* done, unsigned long long* host_dst, cudaStream_t s) {
+    const int blocks = (int)((n + 1023u) / 1024u < 1u ? 1u : ((n + 1023u) / 1024u > 296u ? 296u : (n + 1023u) / 1024u));
+    total_u32_kernel<<<blocks, 256, 0, s>>>(in, n, scratch, done, host_dst);
+    return cudaGetLastError();
 }
 // order-independent 64-bit digest of a device array (4-byte words, each mixed with its position): equal arrays <=> equal digests
 // for all practical purposes; used to check that the index replicas on several devices are byte-identical

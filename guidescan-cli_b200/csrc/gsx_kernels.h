@@ -56,6 +56,7 @@ struct SearchArgs {
     const uint32_t* fmask;
 };
 
+constexpr int kSweepXtabShared = 4352;          // words of shared memory the sweep kernels keep for the xor table (17 KB)
 struct SweepArgs {
     DevStrand st[2];
     const uint64_t* gq;                // as SearchArgs::gq
@@ -132,6 +133,9 @@ cudaError_t launch_expand(const MatchRec* m, const uint32_t* moff, const uint32_
 cudaError_t launch_locate_score(const LocateArgs& a, cudaStream_t s);
 cudaError_t launch_specificity(const SpecArgs& a, cudaStream_t s);
 cudaError_t launch_threshold(const unsigned long long* gc, uint8_t* dropped, uint32_t n, cudaStream_t s);
+// small read-backs that must not queue on the copy engine: stores into pinned host memory
+cudaError_t launch_publish(const uint32_t* src, uint32_t n_words, uint32_t* host_dst, cudaStream_t s);
+cudaError_t launch_total_u32(const uint32_t* in, uint32_t n, unsigned long long* scratch, unsigned int* done, unsigned long long* host_dst, cudaStream_t s);
 cudaError_t launch_checksum(const void* p, size_t bytes, unsigned long long seed, unsigned long long* out, cudaStream_t s);      // *out += digest
 cudaError_t launch_rank_query(const DevStrand& st, const uint32_t* rows, const uint8_t* syms, uint32_t n, uint32_t* out, cudaStream_t s);
 cudaError_t launch_locate_query(const DevStrand& st, const uint32_t* rows, uint32_t n, uint32_t* out, cudaStream_t s);

@@ -117,6 +117,7 @@ struct SweepPlan {
     // use the budget up) under budget B; xcnt[z][B] = their number
     uint32_t xoff[2][kMaxDist + 1];
     uint32_t xcnt[2][kMaxDist + 1];
+    uint32_t xlines[2][kMaxDist + 1];   // how many of those patterns leave the first two characters alone (each opens a jump-table line: work counter)
 };
 
 // node meta word

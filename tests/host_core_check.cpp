@@ -201,6 +201,7 @@ GSX_HD bool node_viable_exact(LoadSector ld, uint32_t sp, uint32_t ep, uint32_t 
 
 // slice-major front end (what sweep_kernel does): per task, the level-L nodes that pass node_viable
 static uint32_t g_sweep_sb = 0;
+static unsigned long long g_shape_checks[4] = {0, 0, 0, 0};      // patterns checked per plane layout of sweep_lean_kernel ([3]: other layouts)
 static std::map<uint32_t, std::vector<std::vector<Node>>> g_seeds_by_M;
 struct HostSectorLoader {            // whole 64-row lines (node_viable / node_viable_exact)
     const DevStrand* st; const std::vector<uint64_t>* look;
@@ -303,6 +304,18 @@ static void sweep_host(const DevStrand st[2], const Prepared& prep, uint32_t M) 
                                 summary_eval_masks<kMaxDist>(w, gm, M - mm, u2);
                                 for (int r = 0; r < kMaxDist; r++) if ((u1[r] & 0xFFFFu) != (u2[r] & 0xFFFFu)) { fprintf(stderr, "summary_eval_masks disagrees (idx %u stage %u r %d)\n", idx, stage, r); exit(3); }
                                 if (zero && summary_eval_exact(w, gm) != (u1[0] & 0xFFFFu)) { fprintf(stderr, "summary_eval_exact disagrees (idx %u stage %u)\n", idx, stage); exit(3); }
+                                // the per-layout forms of sweep_lean_kernel
+                                const int sh = sweep_shape_of(codes);
+                                if (sh >= 0) {
+                                    uint32_t u3[kMaxDist]; uint32_t ex;
+                                    if (sh == 0) { summary_masks_shape<0x3Fu, 0u, kMaxDist>(w, gm + 7, M - mm, u3); ex = summary_exact_shape<0x3Fu>(w, gm + 7); }
+                                    else if (sh == 1) { summary_masks_shape<0x7Fu, 0u, kMaxDist>(w, gm + 7, M - mm, u3); ex = summary_exact_shape<0x7Fu>(w, gm + 7); }
+                                    else { summary_masks_shape<0x1Fu, 0x40u, kMaxDist>(w, gm + 7, M - mm, u3); ex = summary_exact_shape<0x5Fu>(w, gm + 7); }
+                                    if (sweep_shape_proto(sh) != gm[14]) { fprintf(stderr, "sweep_shape_of disagrees with summary_masks (codes %x)\n", codes); exit(3); }
+                                    for (int r = 0; r < kMaxDist; r++) if ((u1[r] & 0xFFFFu) != (u3[r] & 0xFFFFu)) { fprintf(stderr, "summary_masks_shape disagrees (idx %u stage %u r %d shape %d)\n", idx, stage, r, sh); exit(3); }
+                                    if (zero && ex != (u1[0] & 0xFFFFu)) { fprintf(stderr, "summary_exact_shape disagrees (idx %u stage %u shape %d)\n", idx, stage, sh); exit(3); }
+                                    g_shape_checks[sh]++;
+                                } else g_shape_checks[3]++;
                             }
                         }
                         if (zero && summary_viable<1>(lds, idx, codes, codes2, 0) != ok2) { fprintf(stderr, "summary filter <1> disagrees (idx %u)\n", idx); exit(3); }
@@ -394,7 +407,51 @@ static void dfs(const DevStrand st[2], const Prepared& prep, uint32_t task, uint
     }
 }
 
+// the per-layout row filters of sweep_lean_kernel against the general forms, on random sectors and random guides of every layout the
+// kernel is compiled for (the golden genomes are too small for a jump table deep enough to produce layouts 0 and 2 naturally)
+static int shape_selftest() {
+    uint64_t rs = 0x243F6A8885A308D3ull;
+    auto rnd = [&]() { rs ^= rs << 13; rs ^= rs >> 7; rs ^= rs << 17; return (uint32_t)(rs >> 16); };
+    unsigned long long checked = 0;
+    for (int sh = 0; sh < kSweepShapes; sh++) {
+        const uint32_t proto = sweep_shape_proto(sh), pam = sweep_shape_pam(sh);
+        for (int it = 0; it < 200000; it++) {
+            uint32_t codes = 0;
+            for (uint32_t j = 0; j < 7; j++) {
+                uint32_t c;
+                if (proto & (1u << j)) c = rnd() & 3u; else if (pam & (1u << j)) c = 8u + (rnd() & 3u); else c = (rnd() & 1u) ? 12u : 7u;
+                codes |= c << (4u * j);
+            }
+            if (sweep_shape_of(codes) != sh) { fprintf(stderr, "sweep_shape_of(%x) != %d\n", codes, sh); return 3; }
+            uint32_t gm[15], w[8];
+            summary_masks(codes, gm);
+            // sectors as summary_build writes them: a row either follows the guide closely or is random
+            w[0] = (rnd() & 0xFFFFu) | ((rnd() & 7u) << 16);
+            for (int j = 1; j < 8; j++) {
+                const uint32_t noise = (it & 3) == 0 ? rnd() : (rnd() & rnd() & rnd());
+                w[j] = gm[7 + j - 1] ^ noise;
+            }
+            const uint32_t budget = rnd() % 5u;
+            uint32_t u1[kMaxDist], u3[kMaxDist], ex;
+            summary_eval_masks<kMaxDist>(w, gm, budget, u1);
+            if (sh == 0) { summary_masks_shape<0x3Fu, 0u, kMaxDist>(w, gm + 7, budget, u3); ex = summary_exact_shape<0x3Fu>(w, gm + 7); }
+            else if (sh == 1) { summary_masks_shape<0x7Fu, 0u, kMaxDist>(w, gm + 7, budget, u3); ex = summary_exact_shape<0x7Fu>(w, gm + 7); }
+            else { summary_masks_shape<0x1Fu, 0x40u, kMaxDist>(w, gm + 7, budget, u3); ex = summary_exact_shape<0x5Fu>(w, gm + 7); }
+            for (int r = 0; r < kMaxDist; r++) if ((u1[r] & 0xFFFFu) != (u3[r] & 0xFFFFu)) { fprintf(stderr, "summary_masks_shape disagrees (shape %d codes %x r %d)\n", sh, codes, r); return 3; }
+            if (ex != summary_eval_exact(w, gm)) { fprintf(stderr, "summary_exact_shape disagrees (shape %d codes %x)\n", sh, codes); return 3; }
+            // two-mask form of the unsubstituted-pattern step: budgets 0 and 1
+            if (budget <= 1u) { uint32_t u2[2]; summary_eval_masks<2>(w, gm, budget, u2); if ((u2[0] & 0xFFFFu) != (u1[0] & 0xFFFFu)) { fprintf(stderr, "summary_eval_masks<2> disagrees\n"); return 3; } }
+            checked++;
+        }
+    }
+    // layouts the lean loops are not compiled for are recognised as such
+    if (sweep_shape_of(0x7777777u) >= 0 || sweep_shape_of(0x0D00000u | 0x0012301u) >= 0 || sweep_shape_of(0xC333333u) != 0) { fprintf(stderr, "sweep_shape_of classifies wrongly\n"); return 3; }
+    printf("shape selftest ok: %llu sectors\n", checked);
+    return 0;
+}
+
 int main(int argc, char** argv) {
+    if (argc >= 2 && std::string(argv[1]) == "--shape-selftest") return shape_selftest();
     if (argc < 4) { fprintf(stderr, "usage: host_core_check <prefix> <guides.csv> <out> [options]\n"); return 2; }
     std::string prefix = argv[1], guides_csv = argv[2], out_path = argv[3];
     gsx_params p; gsx_params_default(&p);

@@ -155,3 +155,11 @@ def test_sweep_skips_patterns_that_substitute_an_inserted_position(harness, gold
         assert open(out).read() == slice_of(golden_output("g200k", variant).decode(), kw.get("fmt") == "sam")
         nodes[tag] = int(r.stderr.split(" guides, ")[1].split(" nodes")[0])
     assert nodes["forced"] <= nodes["all"] and (kw.get("mismatches", 3) == 0 or nodes["forced"] < nodes["all"]), nodes
+
+
+def test_per_layout_row_filters_equal_the_general_ones(harness):
+    """gsx_core.h summary_exact_shape / summary_masks_shape (the compiled-per-plane-layout filters of sweep_lean_kernel) against
+    summary_eval_exact / summary_eval_masks on 600 k random sectors and guides of every compiled layout; sweep_shape_of classification"""
+    r = subprocess.run([harness, "--shape-selftest"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "shape selftest ok" in r.stdout

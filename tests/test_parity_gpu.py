@@ -430,3 +430,65 @@ def test_every_sweep_kernel_variant_and_queue_overflow(gsx, seeded_case, monkeyp
     _, ctr = ix.enumerate_file(gcsv, out, gsx.make_params(mismatches=4))
     assert ctr["seeds"] > 0
     assert open(out, "rb").read() == open(want, "rb").read()
+
+
+def _mixed_length_guides(d, gcsv):
+    """the seeded guides cut to 14, 15 and 16 nt next to their PAM: at the jump-table depth of this genome (L = 9) those are the
+    three plane layouts sweep_lean_kernel is compiled for (five levels + wildcard + PAM character, six levels + wildcard, seven levels)"""
+    out = os.path.join(d, "mixed.guides.csv")
+    with open(gcsv) as f, open(out, "w") as o:
+        o.write(f.readline())
+        for i, line in enumerate(f):
+            fld = line.rstrip("\n").split(",")
+            fld[1] = fld[1][-(14 + i % 3):]
+            o.write(",".join(fld) + "\n")
+    return out
+
+
+@pytest.mark.parametrize("variant", [10, 11, 12])
+@pytest.mark.parametrize("kw", [dict(mismatches=3), dict(mismatches=2, threshold=1), dict(mismatches=0), dict(mismatches=1, fmt="sam"),
+                                dict(mismatches=3, alt_pams=("NAG",), fmt="sam"), dict(mismatches=2, alt_pams=("NGN", "NAG")),
+                                dict(mismatches=4, max_off_targets=3)])
+def test_lean_sweep_kernel_agrees_with_oracle_and_with_sweep_kernel(gsx, seeded_case, monkeypatch, variant, kw):
+    """sweep_lean_kernel (per-layout loops, two sectors in flight, one-word parking): same text as the oracle, same seeds and
+    work counters as sweep_kernel, for 20-nt guides and for a batch that mixes all compiled plane layouts"""
+    import oracle as O
+    d, gcsv, ix, oix, layout = seeded_case
+    if layout != "full":
+        pytest.skip("the front end needs the jump table and the look-ahead lines")
+    fmt = kw.get("fmt", "csv")
+    p = gsx.make_params(mismatches=kw["mismatches"], threshold=kw.get("threshold", -1), alt_pams=kw.get("alt_pams", ()),
+                        max_off_targets=kw.get("max_off_targets", -1))
+    monkeypatch.setenv("GSX_SWEEP", "1"); monkeypatch.setenv("GSX_SWEEP_MIN", "1")
+    for guides in (gcsv, _mixed_length_guides(d, gcsv)):
+        want = os.path.join(d, "o.out")
+        oix.enumerate_file(O.make_opts(**kw), guides, want, nthreads=8)
+        want = open(want, "rb").read()
+        for sb in (2, 5):
+            monkeypatch.setenv("GSX_SWEEP_SB", str(sb))
+            res = {}
+            for v in (2, variant):
+                monkeypatch.setenv("GSX_SWEEP_VARIANT", str(v))
+                monkeypatch.setenv("GSX_QUEUE_CAP", "64" if (v == 11 and sb == 5) else "0")       # 64: the grow-and-retry path
+                out = os.path.join(d, "l%d.out" % v)
+                _, ctr = ix.enumerate_file(guides, out, p, fmt=fmt)
+                assert open(out, "rb").read() == want, (guides, sb, v)
+                res[v] = ctr
+            if "threshold" not in kw:
+                assert res[variant]["seeds"] > 0
+            if not (variant == 11 and sb == 5):                                               # (a retried launch counts its work twice)
+                for k in ("seeds", "nodes", "lookups", "sectors", "matches", "hits"):
+                    assert res[variant][k] == res[2][k], (k, guides, sb)
+
+
+@pytest.mark.parametrize("variant", [v for v in BULGE_GOLDEN if "r2" not in v])
+@pytest.mark.parametrize("forced", ["0", "1"])
+def test_lean_sweep_kernel_on_edited_guides(gsx, gpu_index, tmp_path, monkeypatch, variant, forced):
+    """bulge batches through sweep_lean_kernel (edited guides of 19-21 nt in one launch, must-match positions on and off)"""
+    monkeypatch.setenv("GSX_SWEEP_VARIANT", "11"); monkeypatch.setenv("GSX_FORCED_SWEEP", forced); monkeypatch.setenv("GSX_SWEEP_MIN", "1")
+    kw = golden_manifest()["cases"]["g200k"]["variants"][variant]["opts"]
+    gcsv, slice_of = _ngg_subset(tmp_path)
+    out = os.path.join(tmp_path, "g.out")
+    _, ctr = gpu_index("g200k").enumerate_file(gcsv, out, _params(gsx, kw), fmt=kw.get("fmt", "csv"), mode=kw.get("mode", "complete"))
+    assert ctr["edited_guides"] > 0 and ctr["seeds"] > 0
+    assert open(out).read() == slice_of(golden_output("g200k", variant).decode(), kw.get("fmt") == "sam")

@@ -27,10 +27,21 @@ print(json.dumps(p))
 PY
       timeout 600 python tools/gpu_session.py --plan /tmp/smoke_plan.json --tag ${tag}_smoke --genome-mb 120 2> gpurun_out/${tag}_smoke.err || { tail -20 gpurun_out/${tag}_smoke.err; echo "SMOKE FAILED"; exit 1; }
       grep -c '"error"' gpurun_out/${tag}_smoke.jsonl; grep '"error"' gpurun_out/${tag}_smoke.jsonl | cut -c1-600
-      shift;;
+      shift 2;;
     plan)
       timeout 2400 python tools/gpu_session.py --plan $2 --tag ${tag} 2> gpurun_out/${tag}.err; tail -3 gpurun_out/${tag}.err
       cut -c1-420 gpurun_out/${tag}.jsonl; shift 2;;
+    pytestk)       # a subset of the gpu tests: pytestk "<-k expression>"
+      timeout 1500 python -m pytest tests -m gpu -q --maxfail 8 --timeout 900 -k "$2" > gpurun_out/${tag}_pytest_gpu_k.log 2>&1; echo "pytest rc=$?" >> gpurun_out/${tag}_pytest_gpu_k.log
+      tail -8 gpurun_out/${tag}_pytest_gpu_k.log; shift 2;;
+    ncu)           # ncu <kernel regex> <launch count> <plan>: one --set full capture of the matching launches of a session plan
+      timeout 1500 ncu --set full --clock-control none --import-source on -k "regex:$2" -c $3 -o gpurun_out/${tag}_ncu -f python tools/gpu_session.py --plan $4 --tag ${tag}_ncu_run > gpurun_out/${tag}_ncu.log 2>&1
+      tail -3 gpurun_out/${tag}_ncu.log
+      ncu -i gpurun_out/${tag}_ncu.ncu-rep --page raw --csv > gpurun_out/${tag}_ncu_raw.csv 2>/dev/null; wc -c gpurun_out/${tag}_ncu_raw.csv
+      shift 4;;
+    launches)      # launches <plan>: per-launch durations of a session plan (ncu launch list)
+      timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${tag}_launches.csv python tools/gpu_session.py --plan $2 --tag ${tag}_launches_run > gpurun_out/${tag}_launches.log 2>&1
+      tail -2 gpurun_out/${tag}_launches.log; shift 2;;
     bench)
       shift
       timeout 1200 python bench.py "$@" > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; tail -3 gpurun_out/${tag}_bench.err; cut -c1-1200 gpurun_out/${tag}_bench.json
