@@ -158,6 +158,9 @@ def make_workload(args, world):
     pos, kmers = synth.sample_guides(g, n_total, args.seed)
     n_plant = min(n_total, args.plant_guides)
     synth.plant(g, kmers[:n_plant], args.seed)
+    if args.skew:        # SURVEY 8(d) skew stressor: repeat families and low-complexity tracts, 1 % of the guides drawn from each
+        kmers, fam, low = synth.add_skew(g, kmers, args.seed, frac=args.skew_frac, lowc_mb=args.skew_lowc_mb)
+        log("skew: %d repeat-family guides, %d low-complexity guides, %.1f Mb of tracts" % (len(fam), len(low), args.skew_lowc_mb))
     if args.n_runs:      # runs of N (every real assembly has them): the index then holds exception rows beyond the sentinel
         rng = np.random.default_rng(args.seed + 3000003)
         for _ in range(args.n_runs):
@@ -356,7 +359,9 @@ def workload_config(args):
                         "%d NGG 20-mer guides per GPU per step, mismatches=%d, both strand indexes, locate + CFD + specificity"
                         % (args.genome_mb, args.seed, args.n_chr, args.plant_guides, args.guides_per_step, args.mismatches),
             "genome_mb": args.genome_mb, "guides_per_gpu_per_step": args.guides_per_step, "mismatches": args.mismatches,
-            "alt_pams": list(args.alt_pam), "rna_bulges": args.rna_bulges, "dna_bulges": args.dna_bulges}
+            "alt_pams": list(args.alt_pam), "rna_bulges": args.rna_bulges, "dna_bulges": args.dna_bulges,
+            "skew": ("repeat families (Zipf 10..10^4 near-copies) for %.1f %% of the guides + %.1f Mb of low-complexity tracts with %.1f %% of the guides drawn from them"
+                     % (100 * args.skew_frac, args.skew_lowc_mb, 100 * args.skew_frac)) if args.skew else None}
 
 
 def write_sample_csv(path, kmers, n):
@@ -481,6 +486,9 @@ def parse_args(argv=None):
     ap.add_argument("--no-file-e2e", action="store_true")
     ap.add_argument("--e2e-pipeline", type=int, default=2, help="batches in flight in the end-to-end loop (gsx_enumerate_start / _wait); 1 = one call after the other")
     ap.add_argument("--n-runs", type=int, default=0, help="insert this many runs of N (1..50000 bases) into the genome after the guides were sampled and planted")
+    ap.add_argument("--skew", action="store_true", help="SURVEY 8(d) skew stressor: Zipf repeat families for 1 %% of the guides, low-complexity tracts with another 1 %% of the guides drawn from them")
+    ap.add_argument("--skew-frac", type=float, default=0.01)
+    ap.add_argument("--skew-lowc-mb", type=float, default=2.0)
     ap.add_argument("--sweep-variants", default="")
     ap.add_argument("--variant", default=None, help="f<k> specialised kernel variant k, g<k> general kernel variant k")
     ap.add_argument("--workdir", default=os.environ.get("GSX_BENCH_DIR", "/tmp/gsx_bench"))

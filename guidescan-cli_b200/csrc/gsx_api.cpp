@@ -796,7 +796,10 @@ static void run_device_job(DeviceJob* job) {
                 CK(launch_sweep_guides(w, s)); n_launches++;
                 // sweep_lean_kernel (variants 10-12) where its compiled loops cover the batch: at most 4 mismatches, every guide length
                 // of the batch giving one of its plane layouts
-                int sv = env_int("GSX_SWEEP_VARIANT", 2);
+                // measured at 3.1 Gb (profiles/r02c_session_3100mb_sweep_lean3.jsonl): six CTAs per SM (variant 12) for plain batches of
+                // at most 3 mismatches -- 24.0 ms per 200 k guides against 36.6 for sweep_kernel --, five (variant 11) for 4 mismatches
+                // and for the edited guides of a bulge search
+                int sv = env_int("GSX_SWEEP_VARIANT", (m.p.M <= 3 && !m.fmask && !use_variants) ? 12 : 11);
                 if (sv >= 10) {
                     bool lean_ok = m.p.M <= 4;
                     for (uint32_t ql = lean_qmin; lean_ok && ql <= lean_qmax; ql++)
@@ -831,9 +834,9 @@ static void run_device_job(DeviceJob* job) {
         };
         auto grow_queue = [&]() { B.free_one(d_queue); d_queue = nullptr; queue_cap *= 4; if (queue_cap >= (1ull << 32)) throw std::runtime_error("seed queue keeps overflowing"); };
 
-        // Calls from several host threads (the reference's own worker threads, or gsx_enumerate_start) take turns on a device for the
-        // search .. specificity section: one call's guide packing, result copies and host-side assembly then run under the next
-        // call's kernels, instead of two sweeps sharing -- and thrashing -- the L2-resident slices.  GSX_DEVICE_LOCK=0 turns it off.
+        // Calls from several host threads (the reference's own worker threads, or gsx_enumerate_start) take turns on a device from the
+        // first search launch to the last result copy: one call's guide packing and host-side result assembly then run under the
+        // next call's kernels, and two sweeps never share -- and thrash -- the L2-resident slices.  GSX_DEVICE_LOCK=0 turns it off.
         static std::mutex device_mu[64];
         std::unique_lock<std::mutex> device_turn;
         if (env_int("GSX_DEVICE_LOCK", 1)) device_turn = std::unique_lock<std::mutex>(device_mu[di.device & 63]);
@@ -1088,7 +1091,6 @@ static void run_device_job(DeviceJob* job) {
         S.n_guides = n; S.n_dist = n_dist; S.sam_rule = p.sam_scoring ? 1 : 0; S.max_off_targets = p.max_off_targets;
         CK(launch_specificity(S, s));
         CK(cudaEventRecord(ev[4], s));
-        if (device_turn.owns_lock()) { CK(cudaStreamSynchronize(s)); device_turn.unlock(); }
         // ---- results to host ---------------------------------------------------------------------------------------------
         H.abs_pos = H.alloc<int64_t>(nh); H.sa_row = H.alloc<uint32_t>(nh); H.chr = H.alloc<int32_t>(nh); H.pos1 = H.alloc<uint32_t>(nh);
         H.strand = H.alloc<uint8_t>(nh); H.distance = H.alloc<uint8_t>(nh); H.rna = H.alloc<uint8_t>(nh); H.dna = H.alloc<uint8_t>(nh);
@@ -1103,6 +1105,10 @@ static void run_device_job(DeviceJob* job) {
         unsigned long long st[8]; d2h(st, d_stats, sizeof st);
         CK(cudaEventRecord(ev[5], s));
         CK(cudaStreamSynchronize(s)); CK(cudaStreamSynchronize(s2));
+        // the turn on the device ends with the copies: a result transfer running under the NEXT call's sweep slows both several
+        // times over (170 MB streaming through the L2 that holds the sweep's slices: profiles/r02b_session_3100mb_sweep_lean.jsonl,
+        // m3_lean_v11_pipe2); what overlaps between pipelined calls is the host work -- guide packing before, result assembly after
+        if (device_turn.owns_lock()) device_turn.unlock();
         float ms;
         CK(cudaEventElapsedTime(&ms, ev[0], ev[1])); job->ctr.ms_search = ms;
         CK(cudaEventElapsedTime(&ms, ev[1], ev[2])); job->ctr.ms_arrange = ms;

@@ -1109,7 +1109,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) sweep_kernel(SweepArgs a) {
 //   * 20 KB of shared memory per 256 threads instead of 47 and 38-55 registers: five or six CTAs per SM fit.
 // Same seeds, same counters as sweep_kernel (the tests run both).
 // ---------------------------------------------------------------------------------------------------------
-constexpr int PK_SLOTS = 96;           // parked table indices per warp: drained below 32 at the top of an iteration, which adds at most 64
+constexpr int PK_SLOTS = 96;           // parked nodes per warp: drained below 32 at the top of an iteration, which adds at most 64
 
 // predicated 32-byte summary load (L2 only): lanes without a pattern get w[0] = 0, i.e. an empty node (their other words are
 // whatever the registers held: every use is masked by w[0])
@@ -1130,7 +1130,10 @@ struct LeanRun {                       // warp-uniform: one guide in one slice o
     uint32_t codes2, tl, fm;
 };
 struct LeanStats { uint32_t nodes, two, lines, sectors; };      // nodes, two (nodes over two 64-row blocks): per lane; lines, sectors: warp-uniform
-struct ParkBuf { uint32_t* idx; uint32_t count; };               // count: warp-uniform
+// nodes with more than 16 rows whose first 16 are dead, waiting for a look at rows 16..31 (sum1): two words each -- table index |
+// remaining budget << 28, and the task (guide * 2 + strand; everything else is in the guide's row of the guide table).  The buffer
+// lives as long as the warp: it is drained 32 at a time, all lanes busy, whichever guides and slices the nodes came from.
+struct ParkBuf { uint32_t* idx; uint32_t* tl; uint32_t count; };      // count: warp-uniform
 
 // surviving level-L node -> seed queue (as sweep_emit)
 __device__ __forceinline__ void lean_emit(const SweepArgs& a, uint32_t lane, bool emit, uint32_t idx, uint32_t tlm, const FtabEntry* tab) {
@@ -1148,60 +1151,74 @@ __device__ __forceinline__ void lean_emit(const SweepArgs& a, uint32_t lane, boo
         } else atomicOr(a.error_flag, GSX_KERR_QUEUE_OVERFLOW);
     }
 }
-// word = table index | remaining budget << 28 of a node to look at again in sum1
-__device__ __forceinline__ void lean_park(ParkBuf& pk, uint32_t lane, bool park, uint32_t word) {
+__device__ __forceinline__ void lean_park(ParkBuf& pk, uint32_t lane, bool park, uint32_t word, uint32_t tl) {
     const uint32_t m = __ballot_sync(0xffffffffu, park);
     if (!m) return;
-    if (park) pk.idx[pk.count + __popc(m & ((1u << lane) - 1u))] = word;
+    if (park) { const uint32_t slot = pk.count + __popc(m & ((1u << lane) - 1u)); pk.idx[slot] = word; pk.tl[slot] = tl; }
     pk.count += __popc(m);
     __syncwarp();
 }
 // one judged first sector: counters, then nothing (empty node / no row left), the seed queue, or the parking buffer
 __device__ __forceinline__ void lean_settle(const SweepArgs& a, ParkBuf& pk, uint32_t lane, uint32_t w0, uint32_t alive, uint32_t idx, uint32_t budget,
-                                            uint32_t tlm, const FtabEntry* tab, LeanStats& st) {
+                                            uint32_t tl, const FtabEntry* tab, LeanStats& st) {
     // (w0 == 0 for lanes without a pattern and for empty table entries; the flags are only ever set on non-empty ones)
     const bool emit = (alive | (w0 & SUM_WIDE32)) != 0u;                             // (more than 32 rows: not summarised, the tree search takes it)
     const bool park = !emit && (w0 & SUM_WIDE16) != 0u;
     st.nodes += (w0 & 0xFFFFu) ? 1u : 0u;
     st.two += (w0 & SUM_TWO_BLOCKS) ? 1u : 0u;
-    lean_emit(a, lane, emit, idx, tlm, tab);
-    lean_park(pk, lane, park, idx | (budget << 28));
+    lean_emit(a, lane, emit, idx, tl | ((a.M - budget) << 24) | (budget << 27), tab);
+    lean_park(pk, lane, park, idx | (budget << 28), tl);
 }
-// up to 32 parked nodes of the current pass: rows 16..31 of their intervals
-template <uint32_t PROTO, uint32_t PAM, int NB, bool EXACT>
-__device__ __forceinline__ void lean_drain(const SweepArgs& a, ParkBuf& pk, uint32_t lane, const LeanRun& r, uint32_t tl_m, LeanStats& st) {
+// one pattern of one guide -- its row of the guide table, any plane layout -- against one summary sector: rows still alive after
+// the seven planes and, where the guide has them, the two levels behind (sum2).  EXACT: no budget left.
+template <int NBX, bool EXACT>
+__device__ __forceinline__ uint32_t lean_row_eval(const uint32_t* __restrict__ row, const unsigned char* sum, const unsigned char* sum2, uint32_t idx,
+                                                  uint32_t budget, uint32_t half, bool live, uint32_t& w0) {
+    const uint4* gp = reinterpret_cast<const uint4*>(row);
+    const uint4 g0 = __ldg(gp), g1 = __ldg(gp + 1), g2 = __ldg(gp + 2), g3 = __ldg(gp + 3);
+    const uint32_t gm[15] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w, g2.x, g2.y, g2.z, g2.w, g3.x, g3.y, g3.z};
+    const uint32_t codes2 = __ldg(row + GT_CODES2);
+    uint32_t w[8];
+    lean_load(sum, idx, live, w);
+    w0 = w[0];
+    const bool tail = sum2 && sweep_has_tail(codes2) && !(w0 & SUM_WIDE32);
+    if (EXACT) {
+        uint32_t v[1] = {summary_eval_exact(w, gm)};
+        if (v[0] && tail) { uint32_t t[4]; load_tail(sum2, idx, t); summary_tail<1>(t, half, codes2, v); }
+        return v[0];
+    }
+    uint32_t u[NBX];
+    summary_eval_masks<NBX>(w, gm, budget, u);
+    if (u[0] && tail) { uint32_t t[4]; load_tail(sum2, idx, t); summary_tail<NBX>(t, half, codes2, u); }
+    return u[0];
+}
+// up to 32 parked nodes: rows 16..31 of their intervals, each lane with its own node's guide
+template <int NB>
+__device__ __forceinline__ void lean_drain(const SweepArgs& a, ParkBuf& pk, uint32_t lane, LeanStats& st) {
     const uint32_t n = pk.count < 32u ? pk.count : 32u;
     const bool mine = lane < n;
-    const uint32_t word = mine ? pk.idx[pk.count - n + lane] : 0u;
+    uint32_t word = 0, tl = 0;
+    if (mine) { word = pk.idx[pk.count - n + lane]; tl = pk.tl[pk.count - n + lane]; }
     __syncwarp();
     pk.count -= n; st.sectors += n;
     const uint32_t idx = word & 0x0FFFFFFFu, budget = word >> 28;
-    uint32_t w[8];
-    lean_load(r.sum1, idx, mine, w);
-    const bool tail = r.sum2 != nullptr && sweep_has_tail(r.codes2);
-    uint32_t alive;
-    if (EXACT) {
-        alive = summary_exact_shape<PROTO | PAM>(w, r.X);
-        if (alive && tail) { uint32_t t[4], v[1] = {alive}; load_tail(r.sum2, idx, t); summary_tail<1>(t, 1u, r.codes2, v); alive = v[0]; }
-    } else {
-        uint32_t u[NB];
-        summary_masks_shape<PROTO, PAM, NB>(w, r.X, budget, u);
-        if (u[0] && tail) { uint32_t t[4]; load_tail(r.sum2, idx, t); summary_tail<NB>(t, 1u, r.codes2, u); }
-        alive = u[0];
-    }
-    // tl_m: task | M << 24; mismatches used so far = M - budget
-    lean_emit(a, lane, alive != 0u, idx, (tl_m - (budget << 24)) | (budget << 27), r.tab);
+    const bool s1 = (tl & 1u) != 0u;
+    uint32_t alive = 0, w0;
+    if (mine) alive = lean_row_eval<NB, false>(a.gtab + (size_t)(tl >> 1) * GT_WORDS, s1 ? a.st[1].sum1 : a.st[0].sum1, s1 ? a.st[1].sum2 : a.st[0].sum2,
+                                               idx, budget, 1u, true, w0);
+    lean_emit(a, lane, alive != 0u, idx, tl | ((a.M - budget) << 24) | (budget << 27), reinterpret_cast<const FtabEntry*>(s1 ? a.st[1].ftab : a.st[0].ftab));
 }
 
 // the patterns of pass 1 (exactly B substitutions outside the slice: no budget left), 64 per iteration
 template <uint32_t USED, int NB, bool FORCED>
 __device__ __forceinline__ void lean_exact_pass(const SweepArgs& a, ParkBuf& pk, const uint32_t* xt, uint32_t n, uint32_t n_lines, uint32_t lane,
-                                                const LeanRun& r, uint32_t tl_m, LeanStats& st) {
+                                                const LeanRun& r, LeanStats& st) {
+    const uint32_t tl_m = r.tl | (a.M << 24);
     if (n == 0u) return;
     const bool tail = r.sum2 != nullptr && sweep_has_tail(r.codes2);
     if constexpr (!FORCED) { st.sectors += n; st.lines += n_lines; }
     for (uint32_t base = 0; base < n; base += 64u) {
-        while (pk.count >= 32u) lean_drain<USED, 0u, NB, true>(a, pk, lane, r, tl_m, st);
+        while (pk.count >= 32u) lean_drain<NB>(a, pk, lane, st);
         const bool two = base + 32u < n;                                             // warp-uniform: a second 32 patterns in this iteration
         const uint32_t t0 = base + lane, t1 = t0 + 32u;
         bool live0 = t0 < n, live1 = t1 < n;
@@ -1229,23 +1246,22 @@ __device__ __forceinline__ void lean_exact_pass(const SweepArgs& a, ParkBuf& pk,
         const uint32_t m0 = __ballot_sync(0xffffffffu, park0), m1 = __ballot_sync(0xffffffffu, park1);
         if (m0 | m1) {
             const uint32_t lt = (1u << lane) - 1u;
-            if (park0) pk.idx[pk.count + __popc(m0 & lt)] = idx0;
-            if (park1) pk.idx[pk.count + __popc(m0) + __popc(m1 & lt)] = idx1;
+            if (park0) { const uint32_t slot = pk.count + __popc(m0 & lt); pk.idx[slot] = idx0; pk.tl[slot] = r.tl; }
+            if (park1) { const uint32_t slot = pk.count + __popc(m0) + __popc(m1 & lt); pk.idx[slot] = idx1; pk.tl[slot] = r.tl; }
             pk.count += __popc(m0) + __popc(m1);
             __syncwarp();
         }
     }
-    while (pk.count) lean_drain<USED, 0u, NB, true>(a, pk, lane, r, tl_m, st);
 }
 // the patterns of pass 0 (fewer than B substitutions outside the slice: budget left), 32 per iteration
 template <uint32_t PROTO, uint32_t PAM, int NB, bool FORCED>
 __device__ __forceinline__ void lean_budget_pass(const SweepArgs& a, ParkBuf& pk, const uint32_t* xt, uint32_t n, uint32_t n_lines, uint32_t lane,
-                                                 const LeanRun& r, uint32_t B, uint32_t tl_m, LeanStats& st) {
+                                                 const LeanRun& r, uint32_t B, LeanStats& st) {
     if (n == 0u) return;
     const bool tail = r.sum2 != nullptr && sweep_has_tail(r.codes2);
     if constexpr (!FORCED) { st.sectors += n; st.lines += n_lines; }
     for (uint32_t base = 0; base < n; base += 32u) {
-        while (pk.count >= 32u) lean_drain<PROTO, PAM, NB, false>(a, pk, lane, r, tl_m, st);
+        while (pk.count >= 32u) lean_drain<NB>(a, pk, lane, st);
         const uint32_t t = base + lane;
         bool live = t < n;
         const uint32_t xw = xt[t];
@@ -1259,34 +1275,15 @@ __device__ __forceinline__ void lean_budget_pass(const SweepArgs& a, ParkBuf& pk
         uint32_t u[NB];
         summary_masks_shape<PROTO, PAM, NB>(w, r.X, budget, u);
         if (u[0] && tail && !(w[0] & SUM_WIDE32)) { uint32_t tt[4]; load_tail(r.sum2, idx, tt); summary_tail<NB>(tt, 0u, r.codes2, u); }
-        lean_settle(a, pk, lane, w[0], u[0], idx, budget, (tl_m - (budget << 24)) | (budget << 27), r.tab, st);
+        lean_settle(a, pk, lane, w[0], u[0], idx, budget, r.tl, r.tab, st);
     }
-    while (pk.count) lean_drain<PROTO, PAM, NB, false>(a, pk, lane, r, tl_m, st);
 }
 template <int SHAPE, int NB, bool FORCED>
 __device__ __forceinline__ void lean_run(const SweepArgs& a, const SweepPlan& pl, ParkBuf& pk, const uint32_t* xtab, uint32_t lane, const LeanRun& r,
                                          uint32_t B, LeanStats& st) {
     constexpr uint32_t PROTO = SHAPE == 0 ? 0x3Fu : SHAPE == 1 ? 0x7Fu : 0x1Fu, PAM = SHAPE == 2 ? 0x40u : 0u;
-    const uint32_t tl_m = r.tl | (a.M << 24);
-    lean_exact_pass<PROTO | PAM, NB, FORCED>(a, pk, xtab + pl.xoff[1][B], pl.xcnt[1][B], pl.xlines[1][B], lane, r, tl_m, st);
-    if (B >= 2u) lean_budget_pass<PROTO, PAM, NB, FORCED>(a, pk, xtab + pl.xoff[0][B], pl.xcnt[0][B], pl.xlines[0][B], lane, r, B, tl_m, st);
-}
-
-// the unsubstituted pattern of one guide (its row of the guide table: any plane layout) against one summary sector, budget 0 or 1:
-// rows still alive after the seven planes and, where the guide has them, the two levels behind (sum2)
-__device__ __forceinline__ uint32_t lean_unit_eval(const uint32_t* __restrict__ row, const unsigned char* sum, const unsigned char* sum2, uint32_t idx,
-                                                   uint32_t B, uint32_t half, uint32_t& w0) {
-    const uint4* gp = reinterpret_cast<const uint4*>(row);
-    const uint4 g0 = __ldg(gp), g1 = __ldg(gp + 1), g2 = __ldg(gp + 2), g3 = __ldg(gp + 3);
-    const uint32_t gm[15] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w, g2.x, g2.y, g2.z, g2.w, g3.x, g3.y, g3.z};
-    const uint32_t codes2 = __ldg(row + GT_CODES2);
-    uint32_t w[8];
-    lean_load(sum, idx, true, w);
-    w0 = w[0];
-    uint32_t u[2];
-    summary_eval_masks<2>(w, gm, B, u);
-    if (u[0] && sum2 && sweep_has_tail(codes2) && !(w0 & SUM_WIDE32)) { uint32_t t[4]; load_tail(sum2, idx, t); summary_tail<2>(t, half, codes2, u); }
-    return u[0];
+    lean_exact_pass<PROTO | PAM, NB, FORCED>(a, pk, xtab + pl.xoff[1][B], pl.xcnt[1][B], pl.xlines[1][B], lane, r, st);
+    lean_budget_pass<PROTO, PAM, NB, FORCED>(a, pk, xtab + pl.xoff[0][B], pl.xcnt[0][B], pl.xlines[0][B], lane, r, B, st);
 }
 
 // XTG: the xor table is too long for shared memory (4 mismatches: 15.8 k words) and is read from global memory (unit stride,
@@ -1294,7 +1291,8 @@ __device__ __forceinline__ uint32_t lean_unit_eval(const uint32_t* __restrict__ 
 template <int WARPS, int MINB, int NB, bool FORCED = false, bool XTG = false>
 __global__ void __launch_bounds__(WARPS * 32, MINB) sweep_lean_kernel(SweepArgs a) {
     __shared__ SweepPlan s_plan;
-    __shared__ uint32_t s_park[WARPS][PK_SLOTS];
+    __shared__ uint32_t s_park[WARPS][2][PK_SLOTS];
+    __shared__ uint32_t s_rank[WARPS][32];
     __shared__ uint32_t s_xtab_[XTG ? 1 : XT_SMEM];
     for (int i = threadIdx.x; i < (int)(sizeof(SweepPlan) / 4); i += blockDim.x)
         reinterpret_cast<uint32_t*>(&s_plan)[i] = reinterpret_cast<const uint32_t*>(&a.plan)[i];
@@ -1302,8 +1300,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) sweep_lean_kernel(SweepArgs 
     const uint32_t* const s_xtab = XTG ? a.xtab : s_xtab_;
     __syncthreads();
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, FULL = 0xffffffffu;
-    ParkBuf pk; pk.idx = s_park[warp]; pk.count = 0;
+    ParkBuf pk; pk.idx = s_park[warp][0]; pk.tl = s_park[warp][1]; pk.count = 0;
     const uint32_t L = s_plan.L, sb = s_plan.sb, M = a.M;
+    const uint32_t np1 = s_plan.xcnt[1][1], np1_magic = np1 ? 0xFFFFFFFFu / np1 + 1u : 0u;      // f / np1 = umulhi(f, magic) for the small f used here
     const uint32_t n_slices = 1u << (2u * sb), n_gb = (a.n_guides + 31u) >> 5;
     const uint32_t items_per_strand = n_slices * n_gb, n_items = 2u * items_per_strand;      // (the host keeps this below 2^32)
     LeanStats st = {0, 0, 0, 0};
@@ -1343,22 +1342,50 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) sweep_lean_kernel(SweepArgs 
             bool more = false;
             if (mine) {
                 idx = hi_bits | __ldg(a.gtab + (size_t)g * GT_WORDS + GT_QLOW);
-                alive = lean_unit_eval(a.gtab + (size_t)g * GT_WORDS, sum0, sum2, idx, (uint32_t)B, 0u, w0);
+                alive = lean_row_eval<2, false>(a.gtab + (size_t)g * GT_WORDS, sum0, sum2, idx, (uint32_t)B, 0u, true, w0);
                 more = alive == 0u && !(w0 & SUM_WIDE32) && (w0 & SUM_WIDE16);
             }
             const uint32_t moremask = __ballot_sync(FULL, more);
             if (moremask) {
                 st.sectors += __popc(moremask);
                 uint32_t w1;
-                if (more) alive = lean_unit_eval(a.gtab + (size_t)g * GT_WORDS, sum1, sum2, idx, (uint32_t)B, 1u, w1);
+                if (more) alive = lean_row_eval<2, false>(a.gtab + (size_t)g * GT_WORDS, sum1, sum2, idx, (uint32_t)B, 1u, true, w1);
             }
             st.nodes += (w0 & 0xFFFFu) ? 1u : 0u;
             st.two += (w0 & SUM_TWO_BLOCKS) ? 1u : 0u;
             const uint32_t Bp = (uint32_t)(B > 0 ? B : 0);
             lean_emit(a, lane, (alive | (w0 & SUM_WIDE32)) != 0u, idx, ((g << 1) | strand) | ((M - Bp) << 24) | (Bp << 27), tab);
         }
-        // (2) guides with budget left after the slice characters, one at a time, all lanes on that guide's patterns
-        uint32_t todo = __ballot_sync(FULL, B >= 1);
+        // (2) guides with budget 1: their patterns with exactly one substitution outside the slice, all of them as ONE list, 32 per
+        //     step, each lane with its own guide's masks.  (There are about three such guides per unit with 27 patterns each: a run per
+        //     guide costs more in set-up than in patterns -- 90 % of the runs of the first version of this kernel were these.)
+        {
+            const uint32_t todo1 = __ballot_sync(FULL, B == 1);
+            if (todo1 && np1) {
+                if (B == 1) s_rank[warp][__popc(todo1 & ((1u << lane) - 1u))] = lane;
+                __syncwarp();
+                const uint32_t total = (uint32_t)__popc(todo1) * np1;
+                const uint32_t* xt1 = s_xtab + s_plan.xoff[1][1];
+                for (uint32_t f0 = 0; f0 < total; f0 += 32u) {
+                    while (pk.count >= 32u) lean_drain<NB>(a, pk, lane, st);
+                    const uint32_t f = f0 + lane;
+                    bool live = f < total;
+                    const uint32_t k = live ? __umulhi(f, np1_magic) : 0u, t = live ? f - k * np1 : 0u;
+                    const uint32_t go = gb * 32u + s_rank[warp][k];
+                    const uint32_t* row = a.gtab + (size_t)go * GT_WORDS;
+                    const uint32_t xw = xt1[t];
+                    if constexpr (FORCED) live = live && !(xw & (__ldg(row + GT_FMASK) & 0x0FFFFFFFu));
+                    st.sectors += __popc(__ballot_sync(FULL, live)); st.lines += __popc(__ballot_sync(FULL, live && (xw & 15u) == 0u));
+                    const uint32_t idx = hi_bits | (__ldg(row + GT_QLOW) ^ (xw & 0x0FFFFFFFu));
+                    uint32_t w0;
+                    const uint32_t alive = lean_row_eval<1, true>(row, sum0, sum2, idx, 0u, 0u, live, w0);
+                    lean_settle(a, pk, lane, w0, alive, idx, 0u, (go << 1) | strand, tab, st);
+                }
+                __syncwarp();
+            }
+        }
+        // (3) guides with more budget left after the slice characters, one at a time, all lanes on that guide's patterns
+        uint32_t todo = __ballot_sync(FULL, B >= 2);
         while (todo) {
             const uint32_t o = (uint32_t)__ffs(todo) - 1u; todo &= todo - 1u;
             const uint32_t Bo = (uint32_t)__shfl_sync(FULL, B, o), go = gb * 32u + o;
@@ -1374,6 +1401,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) sweep_lean_kernel(SweepArgs 
             else lean_run<2, NB, FORCED>(a, s_plan, pk, s_xtab, lane, r, Bo, st);
         }
     }
+    while (pk.count) lean_drain<NB>(a, pk, lane, st);
     unsigned long long n_nodes = st.nodes, n_two = st.two;
     for (int o = 16; o; o >>= 1) { n_nodes += __shfl_xor_sync(FULL, n_nodes, o); n_two += __shfl_xor_sync(FULL, n_two, o); }
     if (lane == 0) { atomicAdd(a.stats + 0, n_nodes); atomicAdd(a.stats + 1, n_nodes + n_two + st.lines); atomicAdd(a.stats + 5, (unsigned long long)st.sectors); }

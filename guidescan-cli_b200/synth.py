@@ -128,3 +128,59 @@ def make_dataset(outdir: str, G: int, n_chr: int, n_guides: int, seed: int, name
     write_fasta(os.path.join(outdir, name + ".fa"), g, chroms)
     write_guides_csv(os.path.join(outdir, name + ".guides.csv"), pos, kmers, chroms)
     return g, chroms, pos, kmers
+
+
+def add_skew(g: np.ndarray, kmers: np.ndarray, seed: int, frac: float = 0.01, lowc_mb: float = 2.0, max_copies: int = 10000,
+             margin: int = 1000):
+    """SURVEY.md 8(d) skew stressor, in place (the plain recipe has no inter-guide skew at all: CV 0.2 %).
+    (1) Repeat families: `frac` of the guides get a Zipf-distributed number (10 .. max_copies) of extra near-copies of their site --
+        0-3 substitutions in the protospacer, random PAM first base, half of them reverse-complemented -- at random positions.
+    (2) Low complexity: `lowc_mb` Mb of tracts (10 kb each: homopolymer, di- and trinucleotide repeats that contain GG, 1-5 % noise),
+        and another `frac` of the guides REPLACED by 23-mers drawn from NGG sites inside the tracts.
+    Returns (kmers with the replaced rows, indices of the family guides, indices of the low-complexity guides)."""
+    rng = np.random.default_rng(seed + 4000003)
+    G, n = len(g), len(kmers)
+    k = max(1, int(n * frac))
+    fam = rng.choice(n, k, replace=False)
+    # Zipf(1.3) scaled to 10 .. max_copies: a few families of thousands, most of tens
+    copies = np.minimum(max_copies, 10 * rng.zipf(1.3, k)).astype(np.int64)
+    code = np.zeros(256, dtype=np.uint8)
+    code[_ACGT] = np.arange(4, dtype=np.uint8)
+    cols = np.arange(23)[None, :]
+    for gi, nc in zip(fam, copies):
+        nc = int(nc)
+        c = np.tile(kmers[gi], (nc, 1))
+        nsub = rng.integers(0, 4, nc)
+        where = rng.integers(0, 20, (nc, 3))
+        shift = rng.integers(1, 4, (nc, 3))
+        rows = np.arange(nc)
+        for j in range(3):                                   # (positions may coincide: "up to" three substitutions)
+            sel = rows[nsub > j]
+            w = where[sel, j]
+            c[sel, w] = _ACGT[(code[c[sel, w]] + shift[sel, j]) % 4]
+        c[:, 20] = _ACGT[rng.integers(0, 4, nc)]
+        rc = rng.random(nc) < 0.5
+        c[rc] = _COMP[c[rc][:, ::-1]]
+        at = rng.integers(margin, G - margin - 23, nc)
+        g[at[:, None] + cols] = c
+    units = [b"G", b"AG", b"CGG", b"AGG", b"TGG", b"GGA", b"GGC", b"GGT", b"AGGG", b"GGAA", b"CCGG", b"GAGG", b"GGTA", b"TCGG", b"AAGG", b"GGCA"]
+    tract = 10000
+    n_tracts = max(1, int(lowc_mb * 1e6) // tract)
+    starts = np.sort(rng.choice((G - 2 * margin) // tract - 1, n_tracts, replace=False)) * tract + margin
+    sites = []
+    for ti, s in enumerate(starts):
+        u = np.frombuffer(units[ti % len(units)], dtype=np.uint8)
+        body = np.tile(u, tract // len(u) + 1)[:tract].copy()
+        noise = rng.random(tract) < rng.uniform(0.01, 0.05)
+        body[noise] = _ACGT[rng.integers(0, 4, int(noise.sum()))]
+        g[s:s + tract] = body
+        p = np.arange(s, s + tract - 23)
+        ok = (g[p + 21] == ord("G")) & (g[p + 22] == ord("G"))
+        sites.append(p[ok])
+    sites = np.concatenate(sites)
+    rest = np.setdiff1d(np.arange(n), fam)
+    low = rng.choice(rest, min(k, len(rest)), replace=False)
+    at = rng.choice(sites, len(low), replace=len(sites) < len(low))
+    kmers = kmers.copy()
+    kmers[low] = g[at[:, None] + np.arange(23)[None, :]]
+    return kmers, fam, low

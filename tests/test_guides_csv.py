@@ -85,3 +85,31 @@ def test_large_file_parsed_by_several_threads(gsx, tmp_path):
     with pytest.raises(gsx.GsxError) as e:
         gsx.read_guides_csv(p)
     assert "wrong number of columns in kmers file line: oops,ACGT" in str(e.value)
+
+
+def test_output_file_is_written_by_several_threads_in_order(tmp_path):
+    """the whole-file driver's writer (gsx_format.cpp OutFile): every batch extends the file and the formatting workers' slices are
+    copied into the mapped extent in parallel; same bytes as sequential writes, for extents that start and end anywhere in a page;
+    sequential fallback for outputs that cannot be mapped"""
+    import ctypes as C
+    import random
+    import gsx
+    lib = C.CDLL(gsx.LIB_PATH)
+    lib.gsx_internal_write_parts.argtypes = [C.c_char_p, C.POINTER(C.c_char_p), C.POINTER(C.c_size_t), C.c_size_t, C.c_size_t]
+    rnd = random.Random(5)
+    for sizes in ([1], [0, 5, 0], [4095, 1, 4096, 8193], [100000, 0, 3, 777777, 12], [rnd.randrange(0, 300000) for _ in range(16)]):
+        parts = [bytes(rnd.randrange(33, 127) for _ in range(min(n, 997))) * (n // 997 + 1) for n in sizes]
+        parts = [p[:n] for p, n in zip(parts, sizes)]
+        arr = (C.c_char_p * len(parts))(*parts)
+        lens = (C.c_size_t * len(parts))(*sizes)
+        for env in (None, "1"):
+            if env:
+                os.environ["GSX_NO_MMAP_OUTPUT"] = env
+            else:
+                os.environ.pop("GSX_NO_MMAP_OUTPUT", None)
+            out = os.path.join(tmp_path, "w.out")
+            assert lib.gsx_internal_write_parts(out.encode(), arr, lens, len(parts), 3) == 0
+            assert open(out, "rb").read() == b"".join(parts) * 3
+        os.environ.pop("GSX_NO_MMAP_OUTPUT", None)
+    assert lib.gsx_internal_write_parts(b"/dev/null", arr, lens, len(parts), 2) == 0
+    assert lib.gsx_internal_write_parts(os.path.join(tmp_path, "no", "such", "dir", "x").encode(), arr, lens, len(parts), 1) != 0

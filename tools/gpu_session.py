@@ -39,6 +39,7 @@ class Session:
         self.args = args
         b = bench.parse_args([])
         b.genome_mb = args.genome_mb; b.n_runs = genome_spec.get("n_runs", 0); b.seed = args.seed
+        b.skew = bool(genome_spec.get("skew", False)); b.skew_lowc_mb = genome_spec.get("skew_lowc_mb", b.skew_lowc_mb)
         b.n_chr = 24 if args.genome_mb >= 1000 else 8
         b.guides_per_step = 200000; b.steps = 5; b.warmup = 3
         self.bargs = b
@@ -105,7 +106,7 @@ class Session:
                                  dna_bulges=e.get("dna_bulges", 0))
         out = {"name": e["name"], "env": e.get("env", {}), "mismatches": m, "alt_pams": e.get("alt_pams", []),
                "rna_bulges": e.get("rna_bulges", 0), "dna_bulges": e.get("dna_bulges", 0), "devices": self.devices,
-               "n_runs": self.bargs.n_runs, "genome_mb": self.bargs.genome_mb}
+               "n_runs": self.bargs.n_runs, "skew": self.bargs.skew, "genome_mb": self.bargs.genome_mb}
         if e.get("open_again"):
             devs = e.get("devices", self.devices)
             t0 = time.time()
