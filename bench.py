@@ -118,6 +118,31 @@ def dist_setup(n_gpus):
     return rank, world, local, dist
 
 
+def bind_to_gpu_numa_node(local):
+    """One process per GPU: keep the process -- and with it the pinned host buffers the library allocates for results -- on the NUMA node
+    the GPU hangs off, so that result copies of 8 ranks do not cross the socket interconnect.  Best effort; returns what it did."""
+    try:
+        bus = subprocess.run(["nvidia-smi", "-i", str(local), "--query-gpu=pci.bus_id", "--format=csv,noheader"], capture_output=True, text=True,
+                             timeout=20).stdout.strip().lower()
+        if not bus:
+            return None
+        bus = bus[-12:] if len(bus) > 12 else bus                              # sysfs spells the domain with four digits
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
+        if node < 0:
+            return {"node": node, "bound": False}
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if len(cpus) < 2:
+            return {"node": node, "bound": False}
+        os.sched_setaffinity(0, cpus)
+        return {"node": node, "bound": True, "cpus": len(cpus)}
+    except Exception as e:
+        return {"error": repr(e)[:120]}
+
+
 def barrier_sync(dist, local):
     import torch
     if torch.cuda.is_available():
@@ -195,6 +220,7 @@ def build_index(gsx, g, chroms, local, args, workdir):
 def run_gsx(args):
     import gsx
     rank, world, local, dist = dist_setup(args.gpus)
+    numa = bind_to_gpu_numa_node(local) if (world > 1 and not args.no_numa_bind) else None
     workdir = args.workdir
     os.makedirs(workdir, exist_ok=True)
     g, chroms, pos, kmers = make_workload(args, world)
@@ -264,7 +290,9 @@ def run_gsx(args):
         dev_ms += c["ms_total_device"]; search_ms += c["ms_search"]
         for k, v in c.items():
             ctr_tot[k] = ctr_tot.get(k, 0) + v
-        d2h_bytes = r.n_guides * (1 + 4 + 4 + 4 + 1 + 4 * (args.mismatches + 1)) + r.n_hits * (8 + 4 + 4 + 4 + 6 + 4 + 4) + c["matches"] * 32
+        # per guide: dropped, hit offset, hit count, specificity, perfect-match flag, counts per distance; per hit: abs_pos, sa_row, chr, pos1,
+        # strand / distance / rna / dna / index_id / counted, cfd, match-string key (two words with bulges) and length
+        d2h_bytes = r.n_guides * (1 + 4 + 4 + 4 + 1 + 4 * (args.mismatches + 1)) + r.n_hits * (8 + 4 + 4 + 4 + 6 + 4 + 8 + 1 + (8 if (args.rna_bulges or args.dna_bulges) else 0))
         r.close()
 
     for s in timed:
@@ -298,7 +326,7 @@ def run_gsx(args):
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {**workload_config(args),
-                       "index": how, "sa_sample_rows": 1 << args.sa_shift, "parallelism": "guides sharded x%d, index replicated" % world, "e2e_batches_in_flight": max(1, args.e2e_pipeline),
+                       "index": how, "sa_sample_rows": 1 << args.sa_shift, "parallelism": "guides sharded x%d, index replicated" % world, "e2e_batches_in_flight": max(1, args.e2e_pipeline), "numa_binding_rank0": numa,
                        "plant_guides": min(per * world * (args.steps + args.warmup), args.plant_guides), "index_open_seconds": list(ix.open_seconds()),
                        "l2": "index (%.2f GB) is far larger than L2; every step uses new guides" % (ix.device_bytes / 1e9)},
             "e2e": {"value": total_guides / e2e_s, "unit": "guides/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": int(d2h_bytes),
@@ -484,8 +512,9 @@ def parse_args(argv=None):
     ap.add_argument("--cpu-sample", type=int, default=8000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-file-e2e", action="store_true")
-    ap.add_argument("--e2e-pipeline", type=int, default=2, help="batches in flight in the end-to-end loop (gsx_enumerate_start / _wait); 1 = one call after the other")
+    ap.add_argument("--e2e-pipeline", type=int, default=1, help="batches in flight in the end-to-end loop (gsx_enumerate_start / _wait); 1 = one call after the other")
     ap.add_argument("--n-runs", type=int, default=0, help="insert this many runs of N (1..50000 bases) into the genome after the guides were sampled and planted")
+    ap.add_argument("--no-numa-bind", action="store_true", help="multi-GPU runs: do not bind each rank to its GPU's NUMA node")
     ap.add_argument("--skew", action="store_true", help="SURVEY 8(d) skew stressor: Zipf repeat families for 1 %% of the guides, low-complexity tracts with another 1 %% of the guides drawn from them")
     ap.add_argument("--skew-frac", type=float, default=0.01)
     ap.add_argument("--skew-lowc-mb", type=float, default=2.0)

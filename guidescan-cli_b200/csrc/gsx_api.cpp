@@ -1032,7 +1032,6 @@ static void run_device_job(DeviceJob* job) {
         }
         }
         CK(cudaEventRecord(ev[1], s));
-        H.matches = H.alloc<MatchRec>(n_matches); H.n_matches = n_matches;
         // ---- arrange --------------------------------------------------------------------------------------------------
         uint32_t* d_moff = B.alloc<uint32_t>(n + 1);
         uint32_t* d_cursor = B.alloc<uint32_t>(n, true, s);
@@ -1045,7 +1044,16 @@ static void run_device_job(DeviceJob* job) {
         CK(launch_scan(d_nmatch, d_moff, n, s)); n_launches += 2 + (n_matches ? 1 : 0);
         // thousands of matches per guide (bulges): global radix sort (gsx_arrange.cu); otherwise the per-guide rank sort
         // (GSX_ORDER: 0 warp per guide, 1 CTA per guide, 2 radix sort)
-        const int order_mode = env_int("GSX_ORDER", env_int("GSX_ORDER_CTA", 0) ? 1 : ((uint64_t)n_matches > (uint64_t)n * 256 ? 2 : 0));
+        // ... and whenever SOME guide has thousands (repeat families, low-complexity guides: the rank sort is quadratic per guide -- 457 ms
+        // per 200 k guides on the skew stressor of SURVEY 8(d), profiles/r02d_session_3100mb_files_cfg4_skew.jsonl)
+        uint64_t max_per_guide = 0;
+        if (n_matches && (uint64_t)n_matches <= (uint64_t)n * 256 && !env_int("GSX_ORDER", 0) && !env_int("GSX_ORDER_CTA", 0)) {
+            unsigned long long* d_tm = B.alloc<unsigned long long>(3, true, s);
+            CK(launch_total_u32(d_nmatch, n, d_tm, reinterpret_cast<unsigned int*>(d_tm + 2), reinterpret_cast<unsigned long long*>(mbox.p + 32), s)); n_launches++;
+            CK(cudaStreamSynchronize(s));
+            max_per_guide = reinterpret_cast<volatile unsigned long long*>(mbox.p + 32)[1];
+        }
+        const int order_mode = env_int("GSX_ORDER", env_int("GSX_ORDER_CTA", 0) ? 1 : (((uint64_t)n_matches > (uint64_t)n * 256 || max_per_guide > 2048) ? 2 : 0));
         if (order_mode == 2) {
             const size_t sb_bytes = order_sorted_scratch_bytes(n_matches);
             void* scratch = B.alloc<unsigned char>(sb_bytes);
@@ -1057,16 +1065,13 @@ static void run_device_job(DeviceJob* job) {
         }
         {   // total hits can exceed 2^32 only for absurd inputs; the scan is 32-bit, so the total is a 64-bit sum (device-side, stored
             // into the mailbox: the per-guide counts themselves travel with the other result arrays at the end)
-            unsigned long long* d_tot = B.alloc<unsigned long long>(2, true, s);
-            CK(launch_total_u32(d_nhits, n, d_tot, reinterpret_cast<unsigned int*>(d_tot + 1), reinterpret_cast<unsigned long long*>(mbox.p + 32), s)); n_launches++;
+            unsigned long long* d_tot = B.alloc<unsigned long long>(3, true, s);
+            CK(launch_total_u32(d_nhits, n, d_tot, reinterpret_cast<unsigned int*>(d_tot + 2), reinterpret_cast<unsigned long long*>(mbox.p + 32), s)); n_launches++;
             CK(cudaStreamSynchronize(s));
             const uint64_t tot = *reinterpret_cast<volatile unsigned long long*>(mbox.p + 32);
             if (tot >= (1ull << 32)) throw std::runtime_error("more than 2^32 hits in one batch; lower the batch size");
             H.n_hits = (size_t)tot;
         }
-        // the match arena is final: its copy to the host runs on the second stream, under the expand / locate / score kernels
-        // (issued after the small hit-count read-back above, which would otherwise queue behind it on the copy engine)
-        if (n_matches) CK(cudaMemcpyAsync(H.matches, d_matches, (size_t)n_matches * sizeof(MatchRec), cudaMemcpyDeviceToHost, s2));
         CK(launch_scan(d_nhits, d_hoff, n, s));
         const uint32_t nh = (uint32_t)H.n_hits;
         uint32_t* d_hit_match = B.alloc<uint32_t>(nh); uint32_t* d_hit_row = B.alloc<uint32_t>(nh); uint32_t* d_hit_guide = B.alloc<uint32_t>(nh);
@@ -1082,6 +1087,7 @@ static void run_device_job(DeviceJob* job) {
         L.abs_pos = B.alloc<int64_t>(nh); L.chr = B.alloc<int32_t>(nh); L.pos1 = B.alloc<uint32_t>(nh); L.strand = B.alloc<uint8_t>(nh);
         L.distance = B.alloc<uint8_t>(nh); L.dna = B.alloc<uint8_t>(nh); L.rna = B.alloc<uint8_t>(nh); L.index_id = B.alloc<uint8_t>(nh);
         L.cfd = B.alloc<float>(nh); L.flags = B.alloc<uint8_t>(nh); L.stats = d_stats;
+        L.key_lo = B.alloc<uint64_t>(nh); L.key_hi = wide ? B.alloc<uint64_t>(nh) : nullptr; L.mlen = B.alloc<uint8_t>(nh);
         CK(launch_locate_score(L, s));
         CK(cudaEventRecord(ev[3], s));
         // ---- specificity ------------------------------------------------------------------------------------------------
@@ -1094,14 +1100,16 @@ static void run_device_job(DeviceJob* job) {
         // ---- results to host ---------------------------------------------------------------------------------------------
         H.abs_pos = H.alloc<int64_t>(nh); H.sa_row = H.alloc<uint32_t>(nh); H.chr = H.alloc<int32_t>(nh); H.pos1 = H.alloc<uint32_t>(nh);
         H.strand = H.alloc<uint8_t>(nh); H.distance = H.alloc<uint8_t>(nh); H.rna = H.alloc<uint8_t>(nh); H.dna = H.alloc<uint8_t>(nh);
-        H.index_id = H.alloc<uint8_t>(nh); H.cfd = H.alloc<float>(nh); H.counted = H.alloc<uint8_t>(nh); H.hit_match = H.alloc<uint32_t>(nh);
+        H.index_id = H.alloc<uint8_t>(nh); H.cfd = H.alloc<float>(nh); H.counted = H.alloc<uint8_t>(nh);
+        H.key_lo = H.alloc<uint64_t>(nh); H.key_hi = wide ? H.alloc<uint64_t>(nh) : nullptr; H.mlen = H.alloc<uint8_t>(nh);
         auto d2h = [&](void* dst, const void* src, size_t bytes) { if (bytes) CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s)); };
         d2h(H.dropped, d_dropped, n); d2h(H.hoff, d_hoff, (size_t)(n + 1) * 4); d2h(H.n_hits_of, d_nhits, (size_t)n * 4); d2h(H.specificity, S.specificity, (size_t)n * 4);
         d2h(H.perfect, S.perfect, n); d2h(H.cbd, d_cbd, (size_t)n * n_dist * 4);
         d2h(H.abs_pos, L.abs_pos, (size_t)nh * 8); d2h(H.sa_row, d_hit_row, (size_t)nh * 4); d2h(H.chr, L.chr, (size_t)nh * 4);
         d2h(H.pos1, L.pos1, (size_t)nh * 4); d2h(H.strand, L.strand, nh); d2h(H.distance, L.distance, nh); d2h(H.rna, L.rna, nh);
         d2h(H.dna, L.dna, nh); d2h(H.index_id, L.index_id, nh); d2h(H.cfd, L.cfd, (size_t)nh * 4); d2h(H.counted, S.counted, nh);
-        d2h(H.hit_match, d_hit_match, (size_t)nh * 4);
+        d2h(H.key_lo, L.key_lo, (size_t)nh * 8); d2h(H.mlen, L.mlen, nh);
+        if (wide) d2h(H.key_hi, L.key_hi, (size_t)nh * 8);
         unsigned long long st[8]; d2h(st, d_stats, sizeof st);
         CK(cudaEventRecord(ev[5], s));
         CK(cudaStreamSynchronize(s)); CK(cudaStreamSynchronize(s2));
@@ -1237,8 +1245,11 @@ extern "C" int gsx_result_match_sequence(const gsx_result* r, size_t hit, char* 
     if (hit >= r->view.n_hits) return fail(GSX_ERR_ARG, "hit index out of range");
     size_t pi = std::upper_bound(r->part_h0.begin(), r->part_h0.end(), hit) - r->part_h0.begin() - 1;
     const HostArrays& p = r->parts[pi];
-    const MatchRec& m = p.matches[p.hit_match[hit - r->part_h0[pi]]];
-    const GuideRec& g = r->guides[r->part_g0[pi] + (m.task >> 1)];
+    const size_t hl = hit - r->part_h0[pi];
+    MatchRec m{}; m.key_lo = p.key_lo[hl]; m.key_hi = p.key_hi ? p.key_hi[hl] : 0; m.info = (uint32_t)p.mlen[hl] << 24;
+    // the guide of the hit: the last one whose first hit is not behind it (guides without hits share their successor's offset)
+    const size_t gi = (size_t)(std::upper_bound(r->first_hit.begin(), r->first_hit.end(), (uint64_t)hit) - r->first_hit.begin()) - 1;
+    const GuideRec& g = r->guides[gi];
     uint32_t len = decode_match(m, g, r->wide, buf);
     for (uint32_t i = 0; i < len; i++) buf[i] = complement_char(buf[i]);
     buf[len] = 0;

@@ -408,6 +408,8 @@ GSX_HD void score_hit(const LocateArgs& a, uint32_t h, const MatchRec& m, uint32
     a.abs_pos[h] = abs; a.chr[h] = chr; a.pos1[h] = pos1; a.strand[h] = sc;
     a.distance[h] = (uint8_t)mm; a.dna[h] = (uint8_t)((m.info >> 8) & 0xffu); a.rna[h] = (uint8_t)((m.info >> 16) & 0xffu);
     a.index_id[h] = (uint8_t)strand; a.cfd[h] = cfd; a.flags[h] = perfect ? 1 : 0;
+    a.key_lo[h] = m.key_lo; a.mlen[h] = (uint8_t)len;
+    if (a.key_hi) a.key_hi[h] = m.key_hi;
 }
 
 // per-guide float32 reduction in the reference's output order (printer.hpp:244-300 CSV rule / 115-170 SAM rule)

@@ -36,7 +36,7 @@ std::string revcomp(const std::string& x) { std::string r(x.size(), 'N'); for (s
 
 // match.sequence of hit h complemented as printed (= gsx_result_match_sequence, printer.hpp:232,264), table-driven: the
 // character selects of gsx_core.h decode_match mispredict on every other character when run on a host core
-inline size_t match_sequence_at(const gsx_result* r, uint64_t h, char* out) {
+inline size_t match_sequence_at(const gsx_result* r, size_t g, uint64_t h, char* out) {
     static const char UPC[8] = {'T', 'G', 'C', 'A', 'N', '?', '?', '?'};                    // complement of the guide's own symbol
     static const char LOWC[8] = {0, 't', 'g', 'c', 'a', '?', '?', '?'};                      // digit 1..4 = a,c,g,t -> complement
     static const char PAMC[8] = {'T', 'G', 'C', 'N', 'A', '?', '?', '?'};                    // PAM digit A,C,G,N,T -> complement
@@ -44,19 +44,19 @@ inline size_t match_sequence_at(const gsx_result* r, uint64_t h, char* out) {
     size_t pi = 0;
     if (r->parts.size() > 1) pi = (size_t)(std::upper_bound(r->part_h0.begin(), r->part_h0.end(), h) - r->part_h0.begin()) - 1;
     const HostArrays& P = r->parts[pi];
-    const MatchRec& m = P.matches[P.hit_match[h - r->part_h0[pi]]];
-    const uint32_t len = m.info >> 24;
+    const size_t hl = (size_t)(h - r->part_h0[pi]);
+    const uint32_t len = P.mlen[hl];
     if (r->wide) {
-        uint64_t hi = m.key_hi, lo = m.key_lo;
+        uint64_t hi = P.key_hi[hl], lo = P.key_lo[hl];
         for (uint32_t i = 0; i < len; i++) { out[i] = WIDEC[hi >> 60]; hi = (hi << 4) | (lo >> 60); lo <<= 4; }
         return len;
     }
-    const GuideRec& g = r->guides[r->part_g0[pi] + (m.task >> 1)];
-    const uint32_t qlen = g.qlen;
-    uint64_t k = m.key_lo;
+    const GuideRec& gr = r->guides[g];
+    const uint32_t qlen = gr.qlen;
+    uint64_t k = P.key_lo[hl];
     for (uint32_t i = len; i-- > 0;) {
         const uint32_t d = (uint32_t)(k % 5ull); k /= 5ull;
-        const char proto = d ? LOWC[d] : UPC[g.q[i < kMaxQ ? i : 0] & 7u];
+        const char proto = d ? LOWC[d] : UPC[gr.q[i < kMaxQ ? i : 0] & 7u];
         out[i] = i < qlen ? proto : PAMC[d];
     }
     return len;
@@ -97,7 +97,7 @@ void format_csv_guide(const gsx_index* ix, const gsx_result* r, const gsx_guide_
             memcpy(w, chr.data(), chr.size()); w += chr.size(); *w++ = ',';
             w = put_u64_at(w, v.pos1[h]); *w++ = ','; *w++ = (char)v.strand[h]; *w++ = ','; w = put_u64_at(w, v.distance[h]);
             if (complete) {
-                *w++ = ','; w += match_sequence_at(r, h, w);
+                *w++ = ','; w += match_sequence_at(r, g, h, w);
                 *w++ = ','; w = put_u64_at(w, v.rna_bulges[h]); *w++ = ','; w = put_u64_at(w, v.dna_bulges[h]);
             }
             *w++ = ','; memcpy(w, sp, spn); w += spn; *w++ = '\n';
@@ -341,34 +341,52 @@ extern "C" int gsx_guides_csv_row(const gsx_guide_table* g, size_t i, gsx_guide_
 }
 extern "C" void gsx_guides_csv_close(gsx_guide_table* g) { delete g; }
 
-// ---- output file written by several threads ------------------------------------------------------------------------------
-// One write(2) stream into the page cache tops out near 1.3 GB/s (measured: the whole-file driver was write-bound at a quarter of
-// the array path's rate).  A regular file is therefore extended batch by batch (ftruncate) and the new extent mapped: the
-// formatting workers copy their slices into the mapping in parallel -- page faults of different threads are served in parallel,
-// write() calls on one inode are not.  Anything that cannot be extended and mapped (/dev/null, a pipe) gets plain sequential writes.
+// ---- output file ---------------------------------------------------------------------------------------------------------
+// The formatting workers leave one buffer per slice; how those reach the file is a property of the file system more than of this
+// code (measured on the GPU box's /tmp, 1.09 GB of CSV: one write(2) stream 1.49 GB/s; extending the file and copying the slices
+// into a shared mapping on 16 threads 1.12 GB/s -- page faults on that file system are slower than write; /dev/null 2.7 M guides/s,
+// i.e. the formatter itself keeps up with the GPU).  Modes (GSX_OUT_MODE): "pwrite" = every slice written at its own offset by its
+// own thread (default for regular files), "write" = one sequential stream (pipes, devices), "mmap" = the mapped-extent copy.
 #include <fcntl.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
 namespace {
 struct OutFile {
-    int fd = -1; uint64_t size = 0; bool mappable = false;
+    int fd = -1; uint64_t size = 0; int mode = 0;       // 0 write, 1 pwrite, 2 mmap
     bool open(const char* path) {
         fd = ::open(path, O_RDWR | O_CREAT | O_TRUNC, 0644);
         if (fd < 0) { fd = ::open(path, O_WRONLY | O_CREAT | O_TRUNC, 0644); if (fd < 0) return false; }
         struct stat st;
-        mappable = fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && !getenv("GSX_NO_MMAP_OUTPUT");
+        const bool regular = fstat(fd, &st) == 0 && S_ISREG(st.st_mode);
+        const char* e = getenv("GSX_OUT_MODE");
+        mode = !regular ? 0 : (e && !strcmp(e, "write")) ? 0 : (e && !strcmp(e, "mmap")) ? 2 : 1;
         return true;
     }
-    bool write_all(const char* p, size_t n) {
+    static bool write_all(int fd, const char* p, size_t n) {
         while (n) { ssize_t w = ::write(fd, p, n); if (w < 0) return false; p += w; n -= (size_t)w; }
         return true;
     }
-    // appends the parts in order; the copies run on up to parts.size() threads
+    static bool pwrite_all(int fd, const char* p, size_t n, uint64_t off) {
+        while (n) { ssize_t w = ::pwrite(fd, p, n, (off_t)off); if (w < 0) return false; p += w; n -= (size_t)w; off += (uint64_t)w; }
+        return true;
+    }
+    // appends the parts in order; in the threaded modes the copies run on up to parts.size() threads
     bool append(const std::vector<std::string>& parts) {
         uint64_t total = 0; for (const std::string& s : parts) total += s.size();
         if (!total) return true;
-        if (mappable) {
+        if (mode == 1) {
+            std::vector<std::thread> th; std::vector<char> ok(parts.size(), 1); uint64_t off = size; size_t k = 0;
+            for (const std::string& s : parts) {
+                if (!s.empty()) th.emplace_back([this, off, &s, &ok, k] { ok[k] = pwrite_all(fd, s.data(), s.size(), off) ? 1 : 0; });
+                off += s.size(); k++;
+            }
+            for (auto& t : th) t.join();
+            for (char c : ok) if (!c) return false;
+            size += total;
+            return true;
+        }
+        if (mode == 2) {
             const uint64_t page = (uint64_t)sysconf(_SC_PAGESIZE), map_off = size & ~(page - 1), len = size + total - map_off;
             if (ftruncate(fd, (off_t)(size + total)) == 0) {
                 void* m = mmap(nullptr, (size_t)len, PROT_READ | PROT_WRITE, MAP_SHARED, fd, (off_t)map_off);
@@ -383,10 +401,10 @@ struct OutFile {
                 }
                 if (ftruncate(fd, (off_t)size) != 0) return false;
             }
-            mappable = false;                                                 // (not extendable / not mappable after all: sequential writes from here)
+            mode = 0;                                                         // (not extendable / not mappable after all: sequential writes from here)
             if (lseek(fd, (off_t)size, SEEK_SET) < 0) return false;
         }
-        for (const std::string& s : parts) if (!s.empty() && !write_all(s.data(), s.size())) return false;
+        for (const std::string& s : parts) if (!s.empty() && !write_all(fd, s.data(), s.size())) return false;
         size += total;
         return true;
     }

@@ -91,8 +91,8 @@ struct HostArrays {             // one device batch worth of results (pinned hos
     uint32_t* cbd = nullptr;
     int64_t* abs_pos = nullptr; uint32_t* sa_row = nullptr; int32_t* chr = nullptr; uint32_t* pos1 = nullptr; uint8_t* strand = nullptr;
     uint8_t* distance = nullptr; uint8_t* rna = nullptr; uint8_t* dna = nullptr; uint8_t* index_id = nullptr; float* cfd = nullptr;
-    uint8_t* counted = nullptr; uint32_t* hit_match = nullptr;
-    MatchRec* matches = nullptr; size_t n_matches = 0;
+    uint8_t* counted = nullptr;
+    uint64_t* key_lo = nullptr; uint64_t* key_hi = nullptr; uint8_t* mlen = nullptr;      // match string of each hit: sort key (key_hi: wide keys only) and length
     std::vector<std::pair<void*, size_t>> owned;
     template <class T> T* alloc(size_t n) {
         size_t bytes = (n ? n : 1) * sizeof(T);

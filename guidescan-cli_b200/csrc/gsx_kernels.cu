@@ -1752,16 +1752,16 @@ cudaError_t launch_publish(const uint32_t* src, uint32_t n_words, uint32_t* host
     publish_kernel<<<1, 32, 0, s>>>(src, n_words < 32u ? n_words : 32u, host_dst);
     return cudaGetLastError();
 }
-// 64-bit total of n 32-bit counts, stored into pinned host memory (dst[0]); *scratch must be zero
+// 64-bit total and maximum of n 32-bit counts, stored into pinned host memory (dst[0], dst[1]); scratch[0..1] and *done must be zero
 __global__ void total_u32_kernel(const uint32_t* __restrict__ in, uint32_t n, unsigned long long* scratch, unsigned int* done, volatile unsigned long long* dst) {
-    unsigned long long acc = 0;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) acc += in[i];
-    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(scratch, acc);
+    unsigned long long acc = 0; uint32_t mx = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) { const uint32_t v = in[i]; acc += v; mx = v > mx ? v : mx; }
+    for (int o = 16; o; o >>= 1) { acc += __shfl_xor_sync(0xffffffffu, acc, o); const uint32_t t = __shfl_xor_sync(0xffffffffu, mx, o); mx = t > mx ? t : mx; }
+    if ((threadIdx.x & 31) == 0 && acc) { atomicAdd(scratch, acc); atomicMax(scratch + 1, (unsigned long long)mx); }
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
-        if (atomicAdd(done, 1u) == gridDim.x - 1) { __threadfence(); dst[0] = atomicAdd(scratch, 0ull); }      // last block out publishes
+        if (atomicAdd(done, 1u) == gridDim.x - 1) { __threadfence(); dst[0] = atomicAdd(scratch, 0ull); dst[1] = atomicAdd(scratch + 1, 0ull); }      // last block out publishes
     }
 }
 cudaError_t launch_total_u32(const uint32_t* in, uint32_t n, unsigned long long* scratch, unsigned int* done, unsigned long long* host_dst, cudaStream_t s) {

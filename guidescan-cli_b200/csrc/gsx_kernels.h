@@ -87,6 +87,9 @@ struct LocateArgs {
     uint64_t genome_length;
     int64_t* abs_pos; int32_t* chr; uint32_t* pos1; uint8_t* strand; uint8_t* distance; uint8_t* dna; uint8_t* rna;
     uint8_t* index_id; float* cfd; uint8_t* flags;
+    // the match string of the hit, as the host decodes it (gsx_core.h decode_match): its sort key and its length -- so that the result
+    // carries 9 (17 with bulges) bytes per hit instead of the 32-byte match record and an index into the arena
+    uint64_t* key_lo; uint64_t* key_hi; uint8_t* mlen;      // key_hi: wide keys only (else nullptr)
     unsigned long long* stats;
 };
 
@@ -135,6 +138,7 @@ cudaError_t launch_specificity(const SpecArgs& a, cudaStream_t s);
 cudaError_t launch_threshold(const unsigned long long* gc, uint8_t* dropped, uint32_t n, cudaStream_t s);
 // small read-backs that must not queue on the copy engine: stores into pinned host memory
 cudaError_t launch_publish(const uint32_t* src, uint32_t n_words, uint32_t* host_dst, cudaStream_t s);
+// host_dst[0] = 64-bit sum, host_dst[1] = maximum of the n counts; scratch: 2 zeroed words, done: 1 zeroed word
 cudaError_t launch_total_u32(const uint32_t* in, uint32_t n, unsigned long long* scratch, unsigned int* done, unsigned long long* host_dst, cudaStream_t s);
 cudaError_t launch_checksum(const void* p, size_t bytes, unsigned long long seed, unsigned long long* out, cudaStream_t s);      // *out += digest
 cudaError_t launch_rank_query(const DevStrand& st, const uint32_t* rows, const uint8_t* syms, uint32_t n, uint32_t* out, cudaStream_t s);

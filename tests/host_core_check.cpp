@@ -606,6 +606,8 @@ int main(int argc, char** argv) {
     L.wide = prep.wide; L.genome_length = ix.host.genome_length; L.abs_pos = abs_pos.data(); L.chr = chr.data(); L.pos1 = pos1.data();
     L.strand = strand.data(); L.distance = distance.data(); L.dna = dna.data(); L.rna = rna.data(); L.index_id = index_id.data();
     L.cfd = cfd.data(); L.flags = flags.data();
+    std::vector<uint64_t> key_lo(nh + 1), key_hi(nh + 1); std::vector<uint8_t> mlen(nh + 1);
+    L.key_lo = key_lo.data(); L.key_hi = prep.wide ? key_hi.data() : nullptr; L.mlen = mlen.data();
     uint32_t steps = 0;
     for (uint32_t h = 0; h < nh; h++) {
         const MatchRec& m = sorted[hit_match[h]];
@@ -619,8 +621,8 @@ int main(int argc, char** argv) {
 
     H.dropped = dropped.data(); H.n_hits_of = nhits.data(); H.hoff = hoff.data(); H.specificity = spec.data(); H.perfect = perfect.data(); H.cbd = cbd.data();
     H.abs_pos = abs_pos.data(); H.sa_row = hit_row.data(); H.chr = chr.data(); H.pos1 = pos1.data(); H.strand = strand.data(); H.distance = distance.data();
-    H.rna = rna.data(); H.dna = dna.data(); H.index_id = index_id.data(); H.cfd = cfd.data(); H.counted = counted.data(); H.hit_match = hit_match.data();
-    H.matches = sorted.data(); H.n_matches = sorted.size();
+    H.rna = rna.data(); H.dna = dna.data(); H.index_id = index_id.data(); H.cfd = cfd.data(); H.counted = counted.data();
+    H.key_lo = key_lo.data(); H.key_hi = prep.wide ? key_hi.data() : nullptr; H.mlen = mlen.data();
     res.parts.push_back(H); res.part_g0.push_back(0); res.part_h0.push_back(0); res.n_dist = n_dist; res.wide = prep.wide; res.guides = prep.recs;
     gsx_build_view(&res);
 

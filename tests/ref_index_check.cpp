@@ -12,7 +12,10 @@
 // genome N) and every SA sample.  Used on the golden genomes by tests/test_ref_index.py and on the 3.1 Gb reference index of
 // tools/ref_3100mb.py (about ten minutes per strand, one host thread each).
 //
-// usage: ref_index_check <index prefix> <genome text file: upper-case concatenated chromosomes, no separators>
+// usage: ref_index_check <index prefix> <genome text file: upper-case concatenated chromosomes, no separators> [--dump DIR]
+//   --dump DIR: also write what the parser extracted -- DIR/bwt.<strand> (one byte per row, 0 in the sentinel row) and
+//   DIR/sa64.<strand> (u32 SA samples every 64 rows) -- the form the CPU oracle imports (oracle.py Index.from_bwt), so that the
+//   port can be timed on the reference's own index
 #include "../guidescan-cli_b200/csrc/gsx_host.h"
 #include "../guidescan-cli_b200/csrc/gsx_core.h"
 #include <chrono>
@@ -37,8 +40,9 @@ static DevStrand view_of(const HostStrand& h) {
 struct Report { bool ok = false; std::string msg; uint64_t steps = 0, samples = 0, exc = 0; double load_s = 0, walk_s = 0; };
 
 // text_at(p): character p of the text this strand indexes
+static std::string g_dump_dir;
 template <class TextAt>
-static void check_strand(const std::string& path, uint64_t G, TextAt text_at, Report& rep) {
+static void check_strand(const std::string& path, uint64_t G, TextAt text_at, Report& rep, const char* strand_name) {
     HostStrand h; std::string err;
     auto t0 = std::chrono::steady_clock::now();
     if (!load_sdsl_strand(path, h, err)) { rep.msg = err; return; }
@@ -46,6 +50,17 @@ static void check_strand(const std::string& path, uint64_t G, TextAt text_at, Re
     if (h.n != G + 1) { rep.msg = "row count " + std::to_string(h.n) + " != genome length + 1"; return; }
     const DevStrand st = view_of(h);
     static const char SYM[4] = {'A', 'C', 'G', 'T'};
+    if (!g_dump_dir.empty()) {
+        std::vector<uint8_t> bwt(h.n);
+        for (uint64_t row = 0; row < h.n; row++) { const OccBlock& b = h.blocks[row >> 6]; bwt[row] = (uint8_t)SYM[block_sym(b.hi, b.lo, (uint32_t)row)]; }
+        for (size_t i = 0; i < h.exc_rows.size(); i++) bwt[h.exc_rows[i]] = h.exc_sym[i];
+        FILE* f = fopen((g_dump_dir + "/bwt." + strand_name).c_str(), "wb");
+        if (!f || fwrite(bwt.data(), 1, bwt.size(), f) != bwt.size()) { rep.msg = "cannot write the BWT dump"; if (f) fclose(f); return; }
+        fclose(f);
+        f = fopen((g_dump_dir + "/sa64." + strand_name).c_str(), "wb");
+        if (!f || fwrite(h.sa_samples.data(), 4, h.sa_samples.size(), f) != h.sa_samples.size()) { rep.msg = "cannot write the SA sample dump"; if (f) fclose(f); return; }
+        fclose(f);
+    }
     t0 = std::chrono::steady_clock::now();
     uint64_t p = G; uint32_t r = 0;                              // row 0 = the empty suffix, SA[0] = G
     for (;;) {
@@ -79,8 +94,9 @@ static void check_strand(const std::string& path, uint64_t G, TextAt text_at, Re
 }
 
 int main(int argc, char** argv) {
-    if (argc < 3) { fprintf(stderr, "usage: ref_index_check <index prefix> <genome text file>\n"); return 2; }
+    if (argc < 3) { fprintf(stderr, "usage: ref_index_check <index prefix> <genome text file> [--dump DIR]\n"); return 2; }
     const std::string prefix = argv[1];
+    if (argc >= 5 && std::string(argv[3]) == "--dump") g_dump_dir = argv[4];
     std::vector<uint8_t> text;
     {
         FILE* f = fopen(argv[2], "rb");
@@ -93,9 +109,9 @@ int main(int argc, char** argv) {
     }
     const uint64_t G = text.size();
     Report rep[2];
-    std::thread t0([&] { check_strand(prefix + ".forward", G, [&](uint64_t p) { return text[p]; }, rep[0]); });
+    std::thread t0([&] { check_strand(prefix + ".forward", G, [&](uint64_t p) { return text[p]; }, rep[0], "forward"); });
     // the reverse index is over the reverse complement of the whole concatenated genome (reference src/genomics/seq_io.cxx:65-72)
-    std::thread t1([&] { check_strand(prefix + ".reverse", G, [&](uint64_t p) { return (uint8_t)complement_char((char)text[G - 1 - p]); }, rep[1]); });
+    std::thread t1([&] { check_strand(prefix + ".reverse", G, [&](uint64_t p) { return (uint8_t)complement_char((char)text[G - 1 - p]); }, rep[1], "reverse"); });
     t0.join(); t1.join();
     int rc = 0;
     for (int s = 0; s < 2; s++) {

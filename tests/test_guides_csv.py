@@ -88,9 +88,9 @@ def test_large_file_parsed_by_several_threads(gsx, tmp_path):
 
 
 def test_output_file_is_written_by_several_threads_in_order(tmp_path):
-    """the whole-file driver's writer (gsx_format.cpp OutFile): every batch extends the file and the formatting workers' slices are
-    copied into the mapped extent in parallel; same bytes as sequential writes, for extents that start and end anywhere in a page;
-    sequential fallback for outputs that cannot be mapped"""
+    """the whole-file driver's writer (gsx_format.cpp OutFile): the formatting workers' slices reach the file at their own offsets on their
+    own threads (pwrite), through a mapped extent, or as one sequential stream: same bytes in every mode, for slices that start and end
+    anywhere in a page; sequential writes for outputs that are not regular files"""
     import ctypes as C
     import random
     import gsx
@@ -102,14 +102,14 @@ def test_output_file_is_written_by_several_threads_in_order(tmp_path):
         parts = [p[:n] for p, n in zip(parts, sizes)]
         arr = (C.c_char_p * len(parts))(*parts)
         lens = (C.c_size_t * len(parts))(*sizes)
-        for env in (None, "1"):
+        for env in (None, "write", "mmap", "pwrite"):
             if env:
-                os.environ["GSX_NO_MMAP_OUTPUT"] = env
+                os.environ["GSX_OUT_MODE"] = env
             else:
-                os.environ.pop("GSX_NO_MMAP_OUTPUT", None)
+                os.environ.pop("GSX_OUT_MODE", None)
             out = os.path.join(tmp_path, "w.out")
             assert lib.gsx_internal_write_parts(out.encode(), arr, lens, len(parts), 3) == 0
             assert open(out, "rb").read() == b"".join(parts) * 3
-        os.environ.pop("GSX_NO_MMAP_OUTPUT", None)
+        os.environ.pop("GSX_OUT_MODE", None)
     assert lib.gsx_internal_write_parts(b"/dev/null", arr, lens, len(parts), 2) == 0
     assert lib.gsx_internal_write_parts(os.path.join(tmp_path, "no", "such", "dir", "x").encode(), arr, lens, len(parts), 1) != 0

@@ -42,6 +42,12 @@ PY
     launches)      # launches <plan>: per-launch durations of a session plan (ncu launch list)
       timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${tag}_launches.csv python tools/gpu_session.py --plan $2 --tag ${tag}_launches_run > gpurun_out/${tag}_launches.log 2>&1
       tail -2 gpurun_out/${tag}_launches.log; shift 2;;
+    torchbench)    # torchbench <N> <steps> <warmup>: bench.py as the driver launches it on N GPUs
+      timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $2 --steps $3 --warmup $4 > gpurun_out/${tag}_bench_n$2.json 2> gpurun_out/${tag}_bench_n$2.err
+      tail -2 gpurun_out/${tag}_bench_n$2.err; cut -c1-900 gpurun_out/${tag}_bench_n$2.json; shift 4;;
+    cfg5)          # cfg5 <N gpus> <kmers Mb> <csv guides>: tools/config5_run.py
+      timeout 2400 python tools/config5_run.py --gpus $2 --kmers-mb $3 --csv-guides $4 --out gpurun_out/${tag}_config5_$2gpu.json > gpurun_out/${tag}_config5.log 2> gpurun_out/${tag}_config5.err
+      tail -4 gpurun_out/${tag}_config5.err | cut -c1-600; shift 4;;
     bench)
       shift
       timeout 1200 python bench.py "$@" > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; tail -3 gpurun_out/${tag}_bench.err; cut -c1-1200 gpurun_out/${tag}_bench.json
