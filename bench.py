@@ -102,11 +102,14 @@ def dist_setup(n_gpus):
     local = int(os.environ.get("LOCAL_RANK", 0))
     dist = None
     if world > 1:
-        # NCCL carries the barrier and the timing reductions only.  Its INFO lines (rank count, transports) go to a side file so that
-        # stdout holds the JSON line alone; a level set by the caller is respected
-        os.environ.setdefault("NCCL_DEBUG", os.environ.get("GSX_NCCL_DEBUG", "INFO"))
-        os.environ.setdefault("NCCL_DEBUG_FILE", os.path.join(os.environ.get("GSX_BENCH_DIR", "/tmp/gsx_bench"), "nccl_%h_%p.log"))
-        os.makedirs(os.environ.get("GSX_BENCH_DIR", "/tmp/gsx_bench"), exist_ok=True)
+        # NCCL carries the barrier and the timing reductions only.  Its INFO lines would land on stdout next to the JSON line (the
+        # version banner does even with NCCL_DEBUG_FILE set), so the default level is WARN; a level set by the caller is respected, and
+        # GSX_NCCL_DEBUG=INFO sends the INFO lines (rank count, transports) to a side file
+        if "NCCL_DEBUG" not in os.environ:
+            os.environ["NCCL_DEBUG"] = os.environ.get("GSX_NCCL_DEBUG", "WARN")
+            if os.environ["NCCL_DEBUG"] != "WARN":
+                os.makedirs(os.environ.get("GSX_BENCH_DIR", "/tmp/gsx_bench"), exist_ok=True)
+                os.environ.setdefault("NCCL_DEBUG_FILE", os.path.join(os.environ.get("GSX_BENCH_DIR", "/tmp/gsx_bench"), "nccl_%h_%p.log"))
         import torch
         import torch.distributed as dist_mod
         torch.cuda.set_device(local)

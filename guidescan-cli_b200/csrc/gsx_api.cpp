@@ -1133,25 +1133,13 @@ static void run_device_job(DeviceJob* job) {
     catch (const std::exception& e) { job->status = GSX_ERR_INTERNAL; job->err = e.what(); }
 }
 
-void gsx_build_view(gsx_result* r) {
+// The public view.  One part: its arrays as they are.  Several parts (one per device): the per-guide and per-hit arrays are
+// concatenated -- lazily, when gsx_result_view_get is first called; the library's own formatter reads the parts in place.
+static void merge_parts(gsx_result* r) {
     gsx_result_view& v = r->view;
-    size_t ng = 0, nh = 0;
-    for (auto& p : r->parts) { ng += p.n_guides; nh += p.n_hits; }
-    v.n_guides = ng; v.n_hits = nh; v.n_dist = r->n_dist;
-    r->first_hit.resize(ng);
-    size_t g = 0, h = 0;
-    for (auto& p : r->parts) { for (size_t i = 0; i < p.n_guides; i++) r->first_hit[g + i] = h + p.hoff[i]; g += p.n_guides; h += p.n_hits; }
-    v.first_hit = r->first_hit.data();
-    if (r->parts.size() == 1) {
-        HostArrays& p = r->parts[0];
-        v.dropped = p.dropped; v.n_hits_of = p.n_hits_of; v.specificity = p.specificity; v.perfect_match = p.perfect; v.count_by_distance = p.cbd;
-        v.abs_pos = p.abs_pos; v.sa_row = p.sa_row; v.chr = p.chr; v.pos1 = p.pos1; v.strand = p.strand; v.distance = p.distance;
-        v.rna_bulges = p.rna; v.dna_bulges = p.dna; v.index_id = p.index_id; v.cfd = p.cfd; v.counted = p.counted;
-        return;
-    }
     auto cat = [&](auto& dst, auto member, bool per_hit, size_t mult) {
         dst.clear();
-        for (auto& p : r->parts) { size_t n = (per_hit ? p.n_hits : p.n_guides) * mult; auto* src = p.*member; dst.insert(dst.end(), src, src + n); }
+        for (auto& p : r->parts) { size_t n = (per_hit ? p.n_hits : p.n_guides) * mult; auto* src = p.*member; if (n) dst.insert(dst.end(), src, src + n); }
     };
     cat(r->dropped, &HostArrays::dropped, false, 1); cat(r->n_hits_of, &HostArrays::n_hits_of, false, 1);
     cat(r->specificity, &HostArrays::specificity, false, 1); cat(r->perfect, &HostArrays::perfect, false, 1);
@@ -1164,6 +1152,25 @@ void gsx_build_view(gsx_result* r) {
     v.count_by_distance = r->cbd.data(); v.abs_pos = r->abs_pos.data(); v.sa_row = r->sa_row.data(); v.chr = r->chr.data(); v.pos1 = r->pos1.data();
     v.strand = r->strand.data(); v.distance = r->distance.data(); v.rna_bulges = r->rna.data(); v.dna_bulges = r->dna.data();
     v.index_id = r->index_id.data(); v.cfd = r->cfd.data(); v.counted = r->counted.data();
+}
+
+void gsx_build_view(gsx_result* r) {
+    gsx_result_view& v = r->view;
+    size_t ng = 0, nh = 0;
+    for (auto& p : r->parts) { ng += p.n_guides; nh += p.n_hits; }
+    v.n_guides = ng; v.n_hits = nh; v.n_dist = r->n_dist;
+    r->first_hit.resize(ng + 1);                                             // (one entry more than guides: the end of the last guide's hits)
+    size_t g = 0, h = 0;
+    for (auto& p : r->parts) { for (size_t i = 0; i < p.n_guides; i++) r->first_hit[g + i] = h + p.hoff[i]; g += p.n_guides; h += p.n_hits; }
+    r->first_hit[ng] = nh;
+    v.first_hit = r->first_hit.data();
+    r->merged = r->parts.size() == 1;
+    if (r->parts.size() == 1) {
+        HostArrays& p = r->parts[0];
+        v.dropped = p.dropped; v.n_hits_of = p.n_hits_of; v.specificity = p.specificity; v.perfect_match = p.perfect; v.count_by_distance = p.cbd;
+        v.abs_pos = p.abs_pos; v.sa_row = p.sa_row; v.chr = p.chr; v.pos1 = p.pos1; v.strand = p.strand; v.distance = p.distance;
+        v.rna_bulges = p.rna; v.dna_bulges = p.dna; v.index_id = p.index_id; v.cfd = p.cfd; v.counted = p.counted;
+    }
 }
 
 static int enumerate_impl(const gsx_index* ix, const gsx_guide* guides, size_t n_guides, const gsx_params* p, gsx_result** out);
@@ -1237,7 +1244,16 @@ extern "C" int gsx_enumerate_wait(gsx_pending* pd, gsx_result** out) {
     return rc ? fail(rc, msg) : (int)GSX_OK;
 }
 
-extern "C" int gsx_result_view_get(const gsx_result* r, gsx_result_view* view) { if (!r || !view) return fail(GSX_ERR_ARG, "null argument"); *view = r->view; return GSX_OK; }
+extern "C" int gsx_result_view_get(const gsx_result* r, gsx_result_view* view) {
+    if (!r || !view) return fail(GSX_ERR_ARG, "null argument");
+    return guarded([&] {
+        gsx_result* w = const_cast<gsx_result*>(r);                             // (the merged copy is a cache: built once, under the result's own lock)
+        std::lock_guard<std::mutex> lk(w->merge_mu);
+        if (!w->merged) { merge_parts(w); w->merged = true; }
+        *view = w->view;
+        return (int)GSX_OK;
+    });
+}
 extern "C" int gsx_result_counters(const gsx_result* r, gsx_counters* out) { if (!r || !out) return fail(GSX_ERR_ARG, "null argument"); *out = r->counters; return GSX_OK; }
 
 extern "C" int gsx_result_match_sequence(const gsx_result* r, size_t hit, char* buf, size_t buf_len) {
@@ -1248,7 +1264,7 @@ extern "C" int gsx_result_match_sequence(const gsx_result* r, size_t hit, char* 
     const size_t hl = hit - r->part_h0[pi];
     MatchRec m{}; m.key_lo = p.key_lo[hl]; m.key_hi = p.key_hi ? p.key_hi[hl] : 0; m.info = (uint32_t)p.mlen[hl] << 24;
     // the guide of the hit: the last one whose first hit is not behind it (guides without hits share their successor's offset)
-    const size_t gi = (size_t)(std::upper_bound(r->first_hit.begin(), r->first_hit.end(), (uint64_t)hit) - r->first_hit.begin()) - 1;
+    const size_t gi = (size_t)(std::upper_bound(r->first_hit.begin(), r->first_hit.end() - 1, (uint64_t)hit) - r->first_hit.begin()) - 1;
     const GuideRec& g = r->guides[gi];
     uint32_t len = decode_match(m, g, r->wide, buf);
     for (uint32_t i = 0; i < len; i++) buf[i] = complement_char(buf[i]);

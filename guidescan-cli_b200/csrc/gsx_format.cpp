@@ -28,23 +28,36 @@ inline void put_u64(std::string& s, uint64_t v) {
     s.append(t + n, 24 - n);
 }
 inline void put_float(std::string& s, float f) { char t[64]; int n = snprintf(t, sizeof t, "%f", (double)f); s.append(t, n); }   // std::to_string(float)
-inline void put_hex_le64(std::string& s, uint64_t v) {                                      // printer.hpp:18-88
-    static const char H[] = "0123456789abcdef";
-    for (int i = 0; i < 8; i++) { unsigned b = (unsigned)(v & 255); v >>= 8; s.push_back(H[b >> 4]); s.push_back(H[b & 15]); }
+// 16 hex digits of a little-endian int64 (printer.hpp:18-88), two at a time from a table, into a buffer the caller sized
+struct HexPairs { char t[256][2]; HexPairs() { static const char H[] = "0123456789abcdef"; for (int b = 0; b < 256; b++) { t[b][0] = H[b >> 4]; t[b][1] = H[b & 15]; } } };
+static const HexPairs kHex;
+inline char* put_hex_le64_at(char* w, uint64_t v) {
+    for (int i = 0; i < 8; i++) { const unsigned b = (unsigned)(v & 255); v >>= 8; w[0] = kHex.t[b][0]; w[1] = kHex.t[b][1]; w += 2; }
+    return w;
 }
 std::string revcomp(const std::string& x) { std::string r(x.size(), 'N'); for (size_t i = 0; i < x.size(); i++) r[i] = complement_char(x[x.size() - 1 - i]); return r; }
 
-// match.sequence of hit h complemented as printed (= gsx_result_match_sequence, printer.hpp:232,264), table-driven: the
-// character selects of gsx_core.h decode_match mispredict on every other character when run on a host core
-inline size_t match_sequence_at(const gsx_result* r, size_t g, uint64_t h, char* out) {
+// The results of a call lie in one part per device (gsx_host.h HostArrays), each with its own guide and hit numbering.  The
+// formatter reads the parts in place: the merged arrays of the public view are only built when a caller asks for them
+// (gsx_result_view_get) -- for a multi-GPU SAM job that concatenation was a second copy of gigabytes per batch.
+struct GuideAt {
+    const gsx::HostArrays* P; size_t gl; uint64_t b; uint32_t n;      // the part, the guide's number in it, its first hit there, its hit count
+};
+inline GuideAt guide_at(const gsx_result* r, size_t g) {
+    size_t pi = 0;
+    if (r->parts.size() > 1) pi = (size_t)(std::upper_bound(r->part_g0.begin(), r->part_g0.end(), g) - r->part_g0.begin()) - 1;
+    const HostArrays& P = r->parts[pi];
+    const size_t gl = g - r->part_g0[pi];
+    return {&P, gl, P.hoff[gl], P.n_hits_of[gl]};
+}
+
+// match.sequence of hit hl (numbered within the part) of guide g, complemented as printed (= gsx_result_match_sequence,
+// printer.hpp:232,264), table-driven: the character selects of gsx_core.h decode_match mispredict on every other character on a host core
+inline size_t match_sequence_at(const gsx_result* r, const HostArrays& P, size_t g, uint64_t hl, char* out) {
     static const char UPC[8] = {'T', 'G', 'C', 'A', 'N', '?', '?', '?'};                    // complement of the guide's own symbol
     static const char LOWC[8] = {0, 't', 'g', 'c', 'a', '?', '?', '?'};                      // digit 1..4 = a,c,g,t -> complement
     static const char PAMC[8] = {'T', 'G', 'C', 'N', 'A', '?', '?', '?'};                    // PAM digit A,C,G,N,T -> complement
     static const char WIDEC[16] = {'?', '.', 'T', 'G', 'C', 'N', 'A', 't', 'g', 'c', 'a', '?', '?', '?', '?', '?'};
-    size_t pi = 0;
-    if (r->parts.size() > 1) pi = (size_t)(std::upper_bound(r->part_h0.begin(), r->part_h0.end(), h) - r->part_h0.begin()) - 1;
-    const HostArrays& P = r->parts[pi];
-    const size_t hl = (size_t)(h - r->part_h0[pi]);
     const uint32_t len = P.mlen[hl];
     if (r->wide) {
         uint64_t hi = P.key_hi[hl], lo = P.key_lo[hl];
@@ -71,11 +84,12 @@ inline char* put_u64_at(char* w, uint64_t v) {
 // One CSV row per counted hit (printer.hpp:244-300).  Rows are assembled in a local buffer and appended once: at millions of
 // rows per second per thread the per-field std::string appends were the cost.
 void format_csv_guide(const gsx_index* ix, const gsx_result* r, const gsx_guide_row& row, size_t g, const gsx_params* p, bool complete, std::string& out) {
-    const gsx_result_view& v = r->view;
-    if (v.dropped[g]) return;                                                                // process.hpp:68-70: nothing is printed
+    const GuideAt at = guide_at(r, g);
+    const HostArrays& P = *at.P;
+    if (P.dropped[at.gl]) return;                                                            // process.hpp:68-70: nothing is printed
     std::string prefix(row.id); prefix += ",";
     if (p->start) { prefix += row.pam; prefix += row.seq; } else { prefix += row.seq; prefix += row.pam; }
-    const uint64_t b = v.first_hit[g]; const uint32_t n = v.n_hits_of[g];
+    const uint64_t b = at.b; const uint32_t n = at.n;
     if (n == 0) {                                                                            // printer.hpp:190-199
         out += prefix; out += ",NA,NA,NA,0";
         if (complete) out += ",NA,NA,NA";
@@ -83,67 +97,72 @@ void format_csv_guide(const gsx_index* ix, const gsx_result* r, const gsx_guide_
         return;
     }
     prefix += ",";
-    char sp[64]; int spn = snprintf(sp, sizeof sp, "%f", (double)v.specificity[g]);
-    char ms[64];
+    char sp[64]; int spn = snprintf(sp, sizeof sp, "%f", (double)P.specificity[at.gl]);
     constexpr size_t kLine = 1024;
     char line[kLine];
     const bool fits = prefix.size() + 400 < kLine;                                           // (chromosome names are checked per row)
     if (fits) memcpy(line, prefix.data(), prefix.size());
     for (uint64_t h = b; h < b + n; h++) {
-        if (!v.counted[h]) continue;
-        const std::string& chr = ix->host.chr_names[v.chr[h]];
+        if (!P.counted[h]) continue;
+        const std::string& chr = ix->host.chr_names[P.chr[h]];
         if (fits && chr.size() < 256) {
             char* w = line + prefix.size();
             memcpy(w, chr.data(), chr.size()); w += chr.size(); *w++ = ',';
-            w = put_u64_at(w, v.pos1[h]); *w++ = ','; *w++ = (char)v.strand[h]; *w++ = ','; w = put_u64_at(w, v.distance[h]);
+            w = put_u64_at(w, P.pos1[h]); *w++ = ','; *w++ = (char)P.strand[h]; *w++ = ','; w = put_u64_at(w, P.distance[h]);
             if (complete) {
-                *w++ = ','; w += match_sequence_at(r, g, h, w);
-                *w++ = ','; w = put_u64_at(w, v.rna_bulges[h]); *w++ = ','; w = put_u64_at(w, v.dna_bulges[h]);
+                *w++ = ','; w += match_sequence_at(r, P, g, h, w);
+                *w++ = ','; w = put_u64_at(w, P.rna[h]); *w++ = ','; w = put_u64_at(w, P.dna[h]);
             }
             *w++ = ','; memcpy(w, sp, spn); w += spn; *w++ = '\n';
             out.append(line, (size_t)(w - line));
             continue;
         }
         out += prefix;
-        out += chr; out += ","; put_u64(out, v.pos1[h]); out += ",";
-        out.push_back((char)v.strand[h]); out += ","; put_u64(out, v.distance[h]);
+        out += chr; out += ","; put_u64(out, P.pos1[h]); out += ",";
+        out.push_back((char)P.strand[h]); out += ","; put_u64(out, P.distance[h]);
         if (complete) {
-            gsx_result_match_sequence(r, h, ms, sizeof ms);
-            out += ","; out += ms; out += ","; put_u64(out, v.rna_bulges[h]); out += ","; put_u64(out, v.dna_bulges[h]);
+            char ms[64]; const size_t ml = match_sequence_at(r, P, g, h, ms);
+            out += ","; out.append(ms, ml); out += ","; put_u64(out, P.rna[h]); out += ","; put_u64(out, P.dna[h]);
         }
         out += ","; out.append(sp, spn); out += "\n";
     }
 }
 
 void format_sam_guide(const gsx_index* ix, const gsx_result* r, const gsx_guide_row& row, size_t g, const gsx_params* p, bool complete, std::string& out) {
-    const gsx_result_view& v = r->view;
-    if (v.dropped[g]) return;
-    const uint64_t b = v.first_hit[g]; const uint32_t n = v.n_hits_of[g];
+    const GuideAt at = guide_at(r, g);
+    const HostArrays& P = *at.P;
+    if (P.dropped[at.gl]) return;
+    const uint64_t b = at.b; const uint32_t n = at.n, n_dist = r->n_dist;
     if (n == 0) return;
-    bool any0 = false;
-    for (uint64_t h = b; h < b + n && v.distance[h] == 0; h++) any0 = true;
-    if (!any0) return;                                                                       // rows exist only for 0-mismatch alignments
+    uint32_t n0 = 0;
+    for (uint64_t h = b; h < b + n && P.distance[h] == 0; h++) n0++;
+    if (!n0) return;                                                                         // rows exist only for 0-mismatch alignments
     std::string sequence = p->start ? std::string(row.pam) + row.seq : std::string(row.seq) + row.pam;
     std::string seq_out = row.sense_positive ? sequence : revcomp(sequence);
-    std::string hex;
-    if (complete) {                                                                          // off_target_fields, printer.hpp:115-170
-        int64_t delim = -((int64_t)ix->host.genome_length + 1);
-        uint64_t h = b;
-        for (uint32_t d = 0; d < v.n_dist; d++) {
-            uint32_t cnt = v.count_by_distance[g * v.n_dist + d];
-            for (uint32_t j = 0; j < cnt; j++, h++) if (v.counted[h]) put_hex_le64(hex, (uint64_t)v.abs_pos[h]);
-            put_hex_le64(hex, d); put_hex_le64(hex, (uint64_t)delim);
-        }
-    }
-    char sp[64]; int spn = snprintf(sp, sizeof sp, "%f", (double)v.specificity[g]);
-    for (uint64_t h = b; h < b + n; h++) {
-        if (v.distance[h] != 0) continue;
+    const uint32_t* cbd = P.cbd + at.gl * n_dist;
+    // the row up to the of:H: list, and behind it; the list itself (off_target_fields, printer.hpp:115-170) is written straight into
+    // the output buffer: 16 hex digits per counted hit plus a (distance, delimiter) pair per distance -- kilobytes per guide at m = 4
+    size_t hex_len = 0;
+    if (complete) { size_t cnt = 0; for (uint64_t h = b; h < b + n; h++) cnt += P.counted[h] ? 1 : 0; hex_len = (cnt + 2 * (size_t)n_dist) * 16; }
+    char sp[64]; int spn = snprintf(sp, sizeof sp, "%f", (double)P.specificity[at.gl]);
+    const int64_t delim = -((int64_t)ix->host.genome_length + 1);
+    for (uint64_t h0 = b; h0 < b + n0; h0++) {
         out += row.id; out += "\t"; out += row.sense_positive ? "0" : "16"; out += "\t";
-        if (v.chr[h] >= 0) { out += ix->host.chr_names[v.chr[h]]; out += "\t"; put_u64(out, v.pos1[h]); }
+        if (P.chr[h0] >= 0) { out += ix->host.chr_names[P.chr[h0]]; out += "\t"; put_u64(out, P.pos1[h0]); }
         else out += "\t0";                                                                   // sentinel coordinates: chr "" offset 0
         out += "\t100\t"; put_u64(out, sequence.size()); out += "M\t*\t0\t0\t"; out += seq_out; out += "\t*";
-        for (uint32_t d = 0; d < v.n_dist; d++) { out += "\tk"; put_u64(out, d); out += ":i:"; put_u64(out, v.count_by_distance[g * v.n_dist + d]); }
-        if (complete) { out += "\tof:H:"; out += hex; }
+        for (uint32_t d = 0; d < n_dist; d++) { out += "\tk"; put_u64(out, d); out += ":i:"; put_u64(out, cbd[d]); }
+        if (complete) {
+            out += "\tof:H:";
+            const size_t at0 = out.size();
+            out.resize(at0 + hex_len);
+            char* w = &out[at0];
+            uint64_t h = b;
+            for (uint32_t d = 0; d < n_dist; d++) {
+                for (uint32_t j = 0; j < cbd[d]; j++, h++) if (P.counted[h]) w = put_hex_le64_at(w, (uint64_t)P.abs_pos[h]);
+                w = put_hex_le64_at(w, d); w = put_hex_le64_at(w, (uint64_t)delim);
+            }
+        }
         out += "\tsp:f:"; out.append(sp, spn); out += "\n";
     }
 }
@@ -281,8 +300,8 @@ static void format_rows_parts(const gsx_index* ix, const gsx_result* r, const gs
                               const gsx_params* p, int format_sam, int complete, std::vector<std::string>& parts) {
     size_t n = g1 - g0;
     // slices of about equal numbers of ROWS (a guide with bulges has thousands of hits, a plain one about ten), cut at guides
-    const gsx_result_view& v = r->view;
-    const uint64_t h0 = n ? v.first_hit[g0] : 0, h1 = n ? v.first_hit[g1 - 1] + v.n_hits_of[g1 - 1] : 0;
+    const std::vector<uint64_t>& first_hit = r->first_hit;                                   // (n_guides + 1 entries)
+    const uint64_t h0 = n ? first_hit[g0] : 0, h1 = n ? first_hit[g1] : 0;
     unsigned nt = (unsigned)std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), std::max<size_t>({(size_t)1, n / 2048, (size_t)((h1 - h0) / 32768)}));
     if (const char* e = getenv("GSX_FORMAT_THREADS")) if (*e) nt = (unsigned)std::max(1, atoi(e));      // tests
     if (nt > n) nt = (unsigned)std::max<size_t>(1, n);
@@ -291,14 +310,14 @@ static void format_rows_parts(const gsx_index* ix, const gsx_result* r, const gs
     for (unsigned t = 1; t < nt; t++) {
         const uint64_t target = h0 + (h1 - h0) * t / nt + (uint64_t)n * t / nt;               // rows + guides: guides without hits still cost a row
         size_t lo = cut[t - 1], hi = g1;                                                     // first guide whose (first_hit + index) reaches the target
-        while (lo < hi) { const size_t mid = lo + (hi - lo) / 2; if (v.first_hit[mid] + (mid - g0) < target) lo = mid + 1; else hi = mid; }
+        while (lo < hi) { const size_t mid = lo + (hi - lo) / 2; if (first_hit[mid] + (mid - g0) < target) lo = mid + 1; else hi = mid; }
         cut[t] = lo;
     }
     parts.assign(nt, std::string());
     auto work = [&](unsigned t) {
         size_t a = cut[t], b = cut[t + 1];
         std::string& o = parts[t];
-        size_t hits = (b > a) ? (size_t)(v.first_hit[b - 1] + v.n_hits_of[b - 1] - v.first_hit[a]) : 0;
+        size_t hits = (b > a) ? (size_t)(first_hit[b] - first_hit[a]) : 0;
         o.reserve(format_sam ? (b - a) * 256 : hits * 112 + (b - a) * 64);
         for (size_t g = a; g < b; g++) {
             if (format_sam) format_sam_guide(ix, r, rows[g - g0], g, p, complete != 0, o);
@@ -452,6 +471,10 @@ extern "C" int gsx_enumerate_file(const gsx_index* ix, const char* kmers_csv, co
             batch_guides = (size_t)std::min<uint64_t>(batch_guides, std::max<uint64_t>(64, (4u << 20) / forms));
         }
         batch_guides *= (size_t)std::max(1, gsx_index_n_devices(ix));                         // (guides are sharded over the index's devices)
+        // a file of only a few such batches: smaller ones, so that formatting and writing batch k still overlap the search of batch
+        // k+1 (not below 50 k guides per device: the slice-major kernels lose a fifth of their rate there)
+        if (!(e && *e) && !(p->rna_bulges || p->dna_bulges) && n < 4 * batch_guides)
+            batch_guides = std::max<size_t>((n + 3) / 4, (size_t)50000 * (size_t)std::max(1, gsx_index_n_devices(ix)));
         if (batch_guides == 0) batch_guides = 1;
     }
     struct Item { gsx_result* r; size_t b0, b1; };

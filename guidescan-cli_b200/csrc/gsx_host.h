@@ -3,6 +3,7 @@
 #define GSX_HOST_H
 #include "gsx_types.h"
 #include "gsx_kernels.h"
+#include <mutex>
 #include <string>
 #include <vector>
 #include <cstdint>
@@ -138,7 +139,8 @@ struct gsx_result {
     using HostArrays = gsx::HostArrays; using GuideRec = gsx::GuideRec;
     std::vector<HostArrays> parts;          // in guide order
     std::vector<size_t> part_g0, part_h0;
-    // merged view (only materialised when there is more than one part)
+    // merged view (only materialised when there is more than one part, and only when gsx_result_view_get asks for it)
+    bool merged = false; std::mutex merge_mu;
     std::vector<uint8_t> dropped, perfect, strand, distance, rna, dna, index_id, counted;
     std::vector<uint64_t> first_hit; std::vector<uint32_t> n_hits_of, cbd, sa_row, pos1; std::vector<float> specificity, cfd;
     std::vector<int64_t> abs_pos; std::vector<int32_t> chr;

@@ -70,6 +70,27 @@ def main():
         res["enumerate"] = {"guides": a.sample, "threads": cores, "mismatches": a.mismatches, "wall_seconds": t1 - t0,
                             "log": [l for l in lines if "Processed:" not in l][-12:], "rows": sum(1 for _ in open(out)) - 1}
         json.dump(res, open(res_path, "w"), indent=1)
+    if a.stage in ("all", "port"):
+        # the CPU port on the SAME index: BWT and SA samples as the product's parser extracted them from the reference's files
+        # (tests/_build/ref_index_check <prefix> <text> --dump <workdir>/dump), same guides, same thread count
+        import numpy as np
+        d = os.path.join(a.workdir, "dump")
+        if os.path.exists(os.path.join(d, "bwt.forward")):
+            chroms = synth.chromosome_table(int(args.genome_mb * 1e6), args.n_chr)
+            b0, b1 = np.fromfile(os.path.join(d, "bwt.forward"), dtype=np.uint8), np.fromfile(os.path.join(d, "bwt.reverse"), dtype=np.uint8)
+            s0, s1 = np.fromfile(os.path.join(d, "sa64.forward"), dtype=np.uint32), np.fromfile(os.path.join(d, "sa64.reverse"), dtype=np.uint32)
+            t0 = time.time()
+            oix = O.Index.from_bwt(b0, s0, b1, s1, chroms)
+            t1 = time.time()
+            out = os.path.join(a.workdir, "port.out")
+            oix.enumerate_file(O.make_opts(mismatches=a.mismatches), gcsv, out, nthreads=os.cpu_count())
+            t2 = time.time()
+            ref_lines = sorted(open(os.path.join(a.workdir, "ref.out"), "rb").read().split(b"\n"))
+            port_lines = sorted(open(out, "rb").read().split(b"\n"))
+            res["port"] = {"import_seconds": t1 - t0, "enumerate_seconds": t2 - t1, "guides_per_s": a.sample / (t2 - t1), "threads": os.cpu_count(),
+                           "output_equals_reference_sorted": ref_lines == port_lines,
+                           "port_over_reference_speed": (a.sample / (t2 - t1)) / (a.sample / 112.358) if "enumerate" in res else None}
+            json.dump(res, open(res_path, "w"), indent=1)
     print(json.dumps(res))
 
 
