@@ -362,10 +362,11 @@ extern "C" void gsx_guides_csv_close(gsx_guide_table* g) { delete g; }
 
 // ---- output file ---------------------------------------------------------------------------------------------------------
 // The formatting workers leave one buffer per slice; how those reach the file is a property of the file system more than of this
-// code (measured on the GPU box's /tmp, 1.09 GB of CSV: one write(2) stream 1.49 GB/s; extending the file and copying the slices
-// into a shared mapping on 16 threads 1.12 GB/s -- page faults on that file system are slower than write; /dev/null 2.7 M guides/s,
-// i.e. the formatter itself keeps up with the GPU).  Modes (GSX_OUT_MODE): "pwrite" = every slice written at its own offset by its
-// own thread (default for regular files), "write" = one sequential stream (pipes, devices), "mmap" = the mapped-extent copy.
+// code.  Measured on the GPU box's /tmp with 1.09 GB of CSV (profiles/r02f_session_3100mb_files_skew.jsonl): ONE sequential write(2)
+// stream 2.02 GB/s, every slice at its own offset on its own thread (pwrite) 1.60 GB/s -- buffered writes to one inode serialise and
+// the threads only add contention --, slices copied into a shared mapping of the extended file 1.12 GB/s; tmpfs takes 2.5 GB/s in
+// every mode and /dev/null 3.2 M guides/s, i.e. the formatter keeps up with the GPU and the file system is what a file-to-file job
+// waits for.  GSX_OUT_MODE = "write" (default) | "pwrite" | "mmap".
 #include <fcntl.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
@@ -379,7 +380,7 @@ struct OutFile {
         struct stat st;
         const bool regular = fstat(fd, &st) == 0 && S_ISREG(st.st_mode);
         const char* e = getenv("GSX_OUT_MODE");
-        mode = !regular ? 0 : (e && !strcmp(e, "write")) ? 0 : (e && !strcmp(e, "mmap")) ? 2 : 1;
+        mode = !regular ? 0 : (e && !strcmp(e, "pwrite")) ? 1 : (e && !strcmp(e, "mmap")) ? 2 : 0;
         return true;
     }
     static bool write_all(int fd, const char* p, size_t n) {

@@ -11,12 +11,13 @@ for a, b in zip(b"ACGTN", b"TGCAN"):
     COMP[a] = b
 
 
-def _run_case(G, n_chr, n_guides, seed, n_plant, brute_guides, extra=None):
+def _run_case(G, n_chr, n_guides, seed, n_plant, brute_guides, extra=None, n_sampled=None):
     import gsx
     import synth
     g = synth.make_genome(G, seed)
-    pos, kmers = synth.sample_guides(g, n_guides, seed)
+    pos, kmers = synth.sample_guides(g, n_sampled or n_guides, seed)           # (n_sampled: the guide set bench.py draws; the first n_guides are run)
     placed = synth.plant(g, kmers[:n_plant], seed)
+    pos, kmers = pos[:n_guides], kmers[:n_guides]
     chroms = synth.chromosome_table(G, n_chr)
     ix = gsx.Index.build_from_text(g, chroms, devices=[0])
     arr = (gsx.Guide * n_guides)()
@@ -132,6 +133,15 @@ def _oracle_samples_at_full_size(gsx, ix, g, chroms, kmers):
     b0, b1 = ix.export_bwt(0), ix.export_bwt(1)
     (s0, sh0), (s1, sh1) = ix.export_sa_samples(0), ix.export_sa_samples(1)
     assert sh0 == 6 and sh1 == 6
+    # The GPU-built index IS the index the unmodified reference builds for this genome (bench.py's default workload): BWT and SA samples
+    # of both strands hash to the digests of the reference's own 3.1 Gb files (tests/golden/ref_index_3100mb_digests.json; the files
+    # themselves, 1.5 GB per strand and an hour of `guidescan index`, cannot travel).  What the oracle checks below is therefore checked
+    # on the reference's index, not merely on our builder's.
+    import hashlib
+    import json
+    want = json.load(open(os.path.join(ROOT, "tests", "golden", "ref_index_3100mb_digests.json")))
+    for name, arr in (("bwt.forward", b0), ("bwt.reverse", b1), ("sa64.forward", s0), ("sa64.reverse", s1)):
+        assert hashlib.sha256(memoryview(np.ascontiguousarray(arr))).hexdigest() == want[name], "GPU-built index differs from the reference's: " + name
     oix = O.Index.from_bwt(b0, s0, b1, s1, chroms)
     del b0, b1
     cases = [("cfg2", 64, dict(mismatches=3), {}),
@@ -156,7 +166,8 @@ def _oracle_samples_at_full_size(gsx, ix, g, chroms, kmers):
 
 
 def test_config2_size_3100mb():
-    """BASELINE.json configs[2] genome size (3.1 Gb); 200k guides keep the host-side verification short.  The same index then
-    serves small oracle-checked samples of configs[2..4] (bulges, alt PAM, m=4, SAM)."""
-    ctr = _run_case(3_100_000_000, 24, 200_000, seed=3, n_plant=1000, brute_guides=0, extra=_oracle_samples_at_full_size)
+    """BASELINE.json configs[2] genome size (3.1 Gb) -- bench.py's own default genome --; 200k guides keep the host-side verification
+    short.  The same index is then compared with the unmodified reference's index of this genome (digests) and serves small
+    oracle-checked samples of configs[2..4] (bulges, alt PAM, m=4, SAM)."""
+    ctr = _run_case(3_100_000_000, 24, 200_000, seed=3, n_plant=2000, brute_guides=0, extra=_oracle_samples_at_full_size, n_sampled=1_600_000)
     assert ctr["nodes"] > 200_000 * 4_000
