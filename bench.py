@@ -49,6 +49,21 @@ def measured_traffic(args):
     return None
 
 
+def slice_gather_ceiling():
+    """G sectors/s of dependent-free random 32-byte gathers inside 8 MB slices (tools/slice_gather.cu, profiles/r01j_slice_gather.jsonl)"""
+    p = os.path.join(ROOT, "profiles", "r01j_slice_gather.jsonl")
+    best = None
+    if os.path.exists(p):
+        for line in open(p):
+            try:
+                d = json.loads(line)
+            except ValueError:
+                continue
+            if d.get("slice_mb") == 8 and d.get("sectors_per_lookup") == 1:
+                best = max(best or 0.0, d["glookups_per_s"])
+    return best
+
+
 def random_gather_peak():
     p = os.path.join(ROOT, "profiles", "random_gather_peak.json")
     if os.path.exists(p):
@@ -324,6 +339,7 @@ def run_gsx(args):
         achieved = alg_bytes_per_launch / (launch_ms * 1e-3) / 1e9
         rg = random_gather_peak()
         tr = measured_traffic(args)
+        sg = slice_gather_ceiling()
         line = {
             "metric": METRIC, "value": total_guides / (dev_ms * 1e-3), "unit": "guides/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -337,12 +353,17 @@ def run_gsx(args):
             "gpu_launches": int(ctr_tot["launches"]),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": tr["dram_bytes_per_launch"] if tr else None,
                          "traffic_source": tr["source"] if tr else None,
-                         "kernel": ("sweep_kernel + search_fast_kernel" if ctr_tot["seeds"] else "search_fast_kernel") if not os.environ.get("GSX_FORCE_GENERAL", "0") == "1" else "search_kernel", "peak_source": peak_src,
+                         "traffic_capture_commit": tr.get("capture_commit") if tr else None,
+                         "kernel": (tr["kernel"] if tr and ctr_tot["seeds"] else ("sweep_lean_kernel + search_fast_kernel" if ctr_tot["seeds"] else "search_fast_kernel")) if not os.environ.get("GSX_FORCE_GENERAL", "0") == "1" else "search_kernel", "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes_per_launch, "sectors_per_guide": ctr_tot["sectors"] / (per * args.steps),
                          "reference_unit_lookups_per_guide": lookups / total_guides,
                          "nodes_per_guide": nodes / total_guides, "launch_ms": launch_ms,
                          "random_sector_peak_gbs": rg["gb_per_s"] if rg else None,
-                         "frac_of_random_sector_peak": (achieved / rg["gb_per_s"]) if rg else None},
+                         "frac_of_random_sector_peak": (achieved / rg["gb_per_s"]) if rg else None,
+                         # the ceiling that applies to a slice-major sweep: independent 32-byte gathers confined to an L2-sized slice
+                         "sweep_gsectors_per_s": ctr_tot["sectors"] / args.steps / (ctr_tot["ms_sweep"] / args.steps * 1e-3) / 1e9 if ctr_tot["ms_sweep"] else None,
+                         "slice_gather_ceiling_gsectors_per_s": sg,
+                         "frac_of_slice_gather_ceiling": (ctr_tot["sectors"] / args.steps / (ctr_tot["ms_sweep"] / args.steps * 1e-3) / 1e9 / sg) if (sg and ctr_tot["ms_sweep"]) else None},
             "counters": {"hits_per_guide": hits / total_guides, "spills": ctr_tot["spills"], "lf_steps": ctr_tot["lf_steps"],
                          "ms_search": ctr_tot["ms_search"] / args.steps, "ms_sweep": ctr_tot["ms_sweep"] / args.steps,
                          "seeds_per_guide": ctr_tot["seeds"] / (per * args.steps), "edited_guides_per_guide": ctr_tot.get("edited_guides", 0) / (per * args.steps), "ms_arrange": ctr_tot["ms_arrange"] / args.steps,

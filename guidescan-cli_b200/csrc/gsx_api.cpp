@@ -875,7 +875,33 @@ static void run_device_job(DeviceJob* job) {
         // ---- main search ---------------------------------------------------------------------------------------------
         const bool wide = prep.wide;
         const int variant = wide ? variant_w : variant_n;
-        uint64_t match_cap = std::max<uint64_t>((uint64_t)n * (wide ? 2048 : 48), 1u << 18);
+        // Match arena: an overflow costs a second run of the whole search, so the first size has to be right.  Expected matches per
+        // guide on a genome without structure = 2 strands x rows x (substitution patterns within the budget) / 4^length x the fraction
+        // of sites a PAM list accepts: 11 at 3 mismatches / NGG on 3.1 Gb, 300 at 4 mismatches with NGG + NAG (the size round 1 got
+        // wrong: n x 48 -- every such call searched twice).  What a call actually needed is remembered per index and option set and
+        // serves as the floor for the next call (real genomes have repeats that no formula knows).
+        const uint64_t learn_key = (uint64_t)p.mismatches | ((uint64_t)prep.n_fast_pams << 8) | ((uint64_t)p.rna_bulges << 16) | ((uint64_t)p.dna_bulges << 24) |
+                                   ((uint64_t)prep.min_qlen << 32) | ((uint64_t)(wide ? 1 : 0) << 40);
+        double per_guide = wide ? 2048.0 : 48.0;
+        if (!wide) {
+            const double ql = (double)std::max<uint32_t>(prep.min_qlen, 1);
+            double patterns = 0, c = 1;                                           // sum over j <= M of C(q, j) 3^j
+            for (uint32_t j = 0; j <= p.mismatches && j <= prep.min_qlen; j++) { patterns += c; c = c * 3.0 * (ql - j) / (j + 1.0); }
+            double pam_frac = 0;
+            for (int ps = 0; ps < kMaxPamSets; ps++) {
+                double f = 0;
+                for (int k = 0; k < prep.pamsets[ps].n_pams; k++) { double g1 = 1; for (int j = 0; j < prep.pamsets[ps].plen[k]; j++) if (prep.pamsets[ps].sym[k][j] != SYM_N) g1 *= 0.25; f += g1; }
+                pam_frac = std::max(pam_frac, std::min(1.0, f));
+            }
+            const double expect = 2.0 * (double)di.st[0].d.n * patterns / std::pow(4.0, ql) * pam_frac;
+            per_guide = std::max(per_guide, 1.5 * expect + 8.0);
+        }
+        {
+            std::lock_guard<std::mutex> lk(job->ix->learn_mu);
+            auto it = job->ix->learned_matches_per_guide.find(learn_key);
+            if (it != job->ix->learned_matches_per_guide.end()) per_guide = std::max(per_guide, 1.25 * it->second);
+        }
+        uint64_t match_cap = std::max<uint64_t>((uint64_t)((double)n * per_guide), 1u << 18);
         match_cap = std::min<uint64_t>(match_cap, 1u << 27);
         uint32_t spill_cap = wide ? 8192 : 2048;
         if (env_int("GSX_MATCH_CAP", 0) > 0) match_cap = (uint64_t)env_int("GSX_MATCH_CAP", 0);      // tests: force the retry path
@@ -1032,6 +1058,11 @@ static void run_device_job(DeviceJob* job) {
         }
         }
         CK(cudaEventRecord(ev[1], s));
+        if (n) {
+            std::lock_guard<std::mutex> lk(job->ix->learn_mu);
+            double& v = job->ix->learned_matches_per_guide[learn_key];
+            v = std::max(v * 0.9, (double)n_matches / (double)n);                  // (decays, so that one odd batch does not inflate the arenas for good)
+        }
         // ---- arrange --------------------------------------------------------------------------------------------------
         uint32_t* d_moff = B.alloc<uint32_t>(n + 1);
         uint32_t* d_cursor = B.alloc<uint32_t>(n, true, s);

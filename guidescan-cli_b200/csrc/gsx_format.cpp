@@ -295,6 +295,18 @@ extern "C" int gsx_format_header(const gsx_index* ix, int format_sam, int comple
     return ret_buf(s, buf, len);
 }
 
+// Output buffers of the formatter slices, recycled between batches: a multi-GPU SAM job formats gigabytes per batch, and fresh
+// allocations of that size are page faults on every 4 KB of them (32 formatter threads fighting over one address-space lock: the
+// 8-GPU run of configs[4] spent more time there than in the search).  A buffer handed back keeps its capacity.
+namespace {
+struct StringPool {
+    std::mutex mu; std::vector<std::string> free_;
+    std::string get() { std::lock_guard<std::mutex> g(mu); if (free_.empty()) return std::string(); std::string s = std::move(free_.back()); free_.pop_back(); return s; }
+    void put(std::string&& s) { s.clear(); std::lock_guard<std::mutex> g(mu); if (free_.size() < 128 && s.capacity() <= (512u << 20)) free_.push_back(std::move(s)); }
+};
+StringPool& string_pool() { static StringPool p; return p; }
+}  // namespace
+
 // guides are independent: slices are formatted on host threads into their own buffers, in guide order
 static void format_rows_parts(const gsx_index* ix, const gsx_result* r, const gsx_guide_row* rows, size_t g0, size_t g1,
                               const gsx_params* p, int format_sam, int complete, std::vector<std::string>& parts) {
@@ -313,12 +325,15 @@ static void format_rows_parts(const gsx_index* ix, const gsx_result* r, const gs
         while (lo < hi) { const size_t mid = lo + (hi - lo) / 2; if (first_hit[mid] + (mid - g0) < target) lo = mid + 1; else hi = mid; }
         cut[t] = lo;
     }
-    parts.assign(nt, std::string());
+    for (std::string& old : parts) string_pool().put(std::move(old));
+    parts.clear(); parts.resize(nt);
+    for (unsigned t = 0; t < nt; t++) parts[t] = string_pool().get();
     auto work = [&](unsigned t) {
         size_t a = cut[t], b = cut[t + 1];
         std::string& o = parts[t];
         size_t hits = (b > a) ? (size_t)(first_hit[b] - first_hit[a]) : 0;
-        o.reserve(format_sam ? (b - a) * 256 : hits * 112 + (b - a) * 64);
+        // (SAM complete: 16 hex digits per hit in the of:H: list, a few hundred bytes of row around it)
+        o.reserve(format_sam ? (b - a) * 320 + (complete ? hits * 17 : 0) : hits * 112 + (b - a) * 64);
         for (size_t g = a; g < b; g++) {
             if (format_sam) format_sam_guide(ix, r, rows[g - g0], g, p, complete != 0, o);
             else format_csv_guide(ix, r, rows[g - g0], g, p, complete != 0, o);
@@ -489,6 +504,7 @@ extern "C" int gsx_enumerate_file(const gsx_index* ix, const char* kmers_csv, co
             Text tx;
             { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return !wqueue.empty() || fdone; }); if (wqueue.empty()) return; tx = std::move(wqueue.front()); }
             if (wrc == GSX_OK && !out.append(tx.parts)) wrc = GSX_ERR_IO;
+            for (std::string& sp : tx.parts) string_pool().put(std::move(sp));
             { std::lock_guard<std::mutex> lk(mu); wqueue.pop_front(); }                // (popped after the work: the formatter stays at most two batches ahead)
             cv.notify_all();
         }

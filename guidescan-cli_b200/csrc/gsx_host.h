@@ -3,6 +3,7 @@
 #define GSX_HOST_H
 #include "gsx_types.h"
 #include "gsx_kernels.h"
+#include <map>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -75,6 +76,9 @@ struct gsx_index {
     // seconds spent by gsx_index_open / gsx_index_build: [0] reading + converting the files (or suffix sorting), [1] upload and
     // derived arrays (jump table, look-ahead lines, summaries) on the first device, [2] replication to the other devices
     double open_seconds[3] = {0, 0, 0};
+    // matches per guide that earlier calls needed, per option set (gsx_api.cpp: first size of the match arena); the one mutable
+    // part of an otherwise immutable handle
+    mutable std::mutex learn_mu; mutable std::map<uint64_t, double> learned_matches_per_guide;
 };
 
 #include "../../include/gsx.h"
