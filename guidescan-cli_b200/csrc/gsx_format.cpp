@@ -314,7 +314,11 @@ static void format_rows_parts(const gsx_index* ix, const gsx_result* r, const gs
     // slices of about equal numbers of ROWS (a guide with bulges has thousands of hits, a plain one about ten), cut at guides
     const std::vector<uint64_t>& first_hit = r->first_hit;                                   // (n_guides + 1 entries)
     const uint64_t h0 = n ? first_hit[g0] : 0, h1 = n ? first_hit[g1] : 0;
-    unsigned nt = (unsigned)std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), std::max<size_t>({(size_t)1, n / 2048, (size_t)((h1 - h0) / 32768)}));
+    // (with several devices every device job has a host thread that must stay responsive -- it launches that device's kernels between
+    // read-backs -- so those cores are left to them)
+    unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    if (ix->dev.size() > 1 && hw > 2 * ix->dev.size() + 2) hw -= (unsigned)ix->dev.size() + 1;
+    unsigned nt = (unsigned)std::min<size_t>(hw, std::max<size_t>({(size_t)1, n / 2048, (size_t)((h1 - h0) / 32768)}));
     if (const char* e = getenv("GSX_FORMAT_THREADS")) if (*e) nt = (unsigned)std::max(1, atoi(e));      // tests
     if (nt > n) nt = (unsigned)std::max<size_t>(1, n);
     std::vector<size_t> cut(nt + 1, g1);
