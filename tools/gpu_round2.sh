@@ -48,7 +48,7 @@ PY
     cfg5)          # cfg5 <N gpus> <kmers Mb> <csv guides>: tools/config5_run.py
       timeout 2400 python tools/config5_run.py --gpus $2 --kmers-mb $3 --csv-guides $4 --out gpurun_out/${tag}_config5_$2gpu.json > gpurun_out/${tag}_config5.log 2> gpurun_out/${tag}_config5.err
       tail -4 gpurun_out/${tag}_config5.err | cut -c1-600; shift 4;;
-    smoke)         # __graft_entry__.smoke() as the driver runs it
+    entrysmoke)    # __graft_entry__.smoke() as the driver runs it
       timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${tag}_smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/${tag}_smoke.log; tail -2 gpurun_out/${tag}_smoke.log; shift;;
     sanitize)      # sanitize <tool> "<-k expression>": a few small GPU tests under compute-sanitizer
       timeout 1500 compute-sanitizer --tool $2 --error-exitcode 99 --target-processes all python -m pytest tests -m gpu -q -x --timeout 1400 -k "$3" > gpurun_out/${tag}_sanitizer_$2.log 2>&1; echo "sanitizer rc=$?" >> gpurun_out/${tag}_sanitizer_$2.log
