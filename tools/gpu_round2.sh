@@ -54,7 +54,8 @@ PY
       timeout 1500 compute-sanitizer --tool $2 --error-exitcode 99 --target-processes all python -m pytest tests -m gpu -q -x --timeout 1400 -k "$3" > gpurun_out/${tag}_sanitizer_$2.log 2>&1; echo "sanitizer rc=$?" >> gpurun_out/${tag}_sanitizer_$2.log
       grep -c "ERROR SUMMARY\|=========" gpurun_out/${tag}_sanitizer_$2.log; tail -4 gpurun_out/${tag}_sanitizer_$2.log | cut -c1-300; shift 3;;
     benchlaunches) # the launch list of two bench steps (per-launch durations under ncu; the kernel SHARES are what counts)
-      timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_bench_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-file-e2e > gpurun_out/${tag}_bench_launches.log 2>&1
+      # (only the kernels of the enumerate path are profiled: the index build in front of them is a thousand radix-sort launches)
+      timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none -k "regex:sweep|search_|scan_u32|scatter_matches|order_matches|expand_hits|locate_score|specificity|publish|total_u32|variant_|threshold" -c 400 --csv --log-file gpurun_out/${tag}_bench_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-file-e2e > gpurun_out/${tag}_bench_launches.log 2>&1
       tail -2 gpurun_out/${tag}_bench_launches.log | cut -c1-300; shift;;
     bench)
       shift
