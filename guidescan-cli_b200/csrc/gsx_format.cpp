@@ -28,12 +28,21 @@ inline void put_u64(std::string& s, uint64_t v) {
     s.append(t + n, 24 - n);
 }
 inline void put_float(std::string& s, float f) { char t[64]; int n = snprintf(t, sizeof t, "%f", (double)f); s.append(t, n); }   // std::to_string(float)
-// 16 hex digits of a little-endian int64 (printer.hpp:18-88), two at a time from a table, into a buffer the caller sized
-struct HexPairs { char t[256][2]; HexPairs() { static const char H[] = "0123456789abcdef"; for (int b = 0; b < 256; b++) { t[b][0] = H[b >> 4]; t[b][1] = H[b & 15]; } } };
-static const HexPairs kHex;
+// 16 hex digits of a little-endian int64 (printer.hpp:18-88: byte by byte from the low one, high nibble first), four bytes at a time
+// in one 64-bit word: bytes spread to 16-bit lanes, nibbles split and swapped into output order, '0'..'9' / 'a'..'f' added without a
+// table or a branch.  (A guide at 4 mismatches has hundreds of these; this loop is what the host spends its time in on SAM output.)
+inline uint64_t hex8_of_u32(uint32_t x) {
+    uint64_t t = x;
+    t = (t | (t << 16)) & 0x0000FFFF0000FFFFull;
+    t = (t | (t << 8)) & 0x00FF00FF00FF00FFull;                                   // byte i in the low half of 16-bit lane i
+    const uint64_t n = ((t >> 4) & 0x000F000F000F000Full) | ((t & 0x000F000F000F000Full) << 8);      // lane: [high nibble][low nibble] in memory order
+    const uint64_t alpha = ((n + 0x0606060606060606ull) >> 4) & 0x0101010101010101ull;                 // 1 where the nibble is 10..15
+    return n + 0x3030303030303030ull + alpha * 39u;                                // '0' + n, + ('a' - '0' - 10) for letters
+}
 inline char* put_hex_le64_at(char* w, uint64_t v) {
-    for (int i = 0; i < 8; i++) { const unsigned b = (unsigned)(v & 255); v >>= 8; w[0] = kHex.t[b][0]; w[1] = kHex.t[b][1]; w += 2; }
-    return w;
+    const uint64_t lo = hex8_of_u32((uint32_t)v), hi = hex8_of_u32((uint32_t)(v >> 32));
+    memcpy(w, &lo, 8); memcpy(w + 8, &hi, 8);                                      // (little-endian host: lane 0 is the first character)
+    return w + 16;
 }
 std::string revcomp(const std::string& x) { std::string r(x.size(), 'N'); for (size_t i = 0; i < x.size(); i++) r[i] = complement_char(x[x.size() - 1 - i]); return r; }
 
@@ -357,6 +366,7 @@ extern "C" int gsx_format_rows(const gsx_index* ix, const gsx_result* r, const g
     if (!b) return GSX_ERR_NOMEM;
     size_t o = 0; for (auto& s : parts) { memcpy(b + o, s.data(), s.size()); o += s.size(); }
     b[tot] = 0; *buf = b; *len = tot;
+    for (std::string& s : parts) string_pool().put(std::move(s));
     return GSX_OK;
 }
 
