@@ -1111,24 +1111,16 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) sweep_kernel(SweepArgs a) {
 // ---------------------------------------------------------------------------------------------------------
 constexpr int PK_SLOTS = 96;           // parked nodes per warp: drained below 32 at the top of an iteration, which adds at most 64
 
-// 32-byte summary load (L2 only) for the lanes that have a pattern; the others see w[0] = 0, i.e. an empty node.
-// PRED: the load is predicated off for them (and the registers zeroed first); else they load table entry 0 -- one more sector per
-// warp instruction at most, all idle lanes on the same address -- and only w[0] is masked: nine instructions fewer per load.
-template <bool PRED = true>
+// predicated 32-byte summary load (L2 only): lanes without a pattern keep w = 0, i.e. an empty node.  (Letting those lanes load table
+// entry 0 instead -- no predicate, no zeroing, nine instructions fewer per load -- was measured and lost 1-2 %: the idle lanes' extra
+// sector costs more than the instructions, profiles/r02l_session_3100mb_variant13.jsonl.)
 __device__ __forceinline__ void lean_load(const unsigned char* sum, uint32_t idx, bool live, uint32_t w[8]) {
-    if (PRED) {
-        w[0] = 0u;
+    w[0] = 0u;
 #pragma unroll
-        for (int j = 1; j < 8; j++) w[j] = 0u;
-        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %9, 0;\n\t@p ld.global.cg.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n\t}"
-                     : "+r"(w[0]), "+r"(w[1]), "+r"(w[2]), "+r"(w[3]), "+r"(w[4]), "+r"(w[5]), "+r"(w[6]), "+r"(w[7])
-                     : "l"(sum + ((size_t)idx << 5)), "r"((uint32_t)live));
-    } else {
-        asm volatile("ld.global.cg.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                     : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
-                     : "l"(sum + ((size_t)(live ? idx : 0u) << 5)));
-        w[0] = live ? w[0] : 0u;
-    }
+    for (int j = 1; j < 8; j++) w[j] = 0u;
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %9, 0;\n\t@p ld.global.cg.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n\t}"
+                 : "+r"(w[0]), "+r"(w[1]), "+r"(w[2]), "+r"(w[3]), "+r"(w[4]), "+r"(w[5]), "+r"(w[6]), "+r"(w[7])
+                 : "l"(sum + ((size_t)idx << 5)), "r"((uint32_t)live));
 }
 
 struct LeanRun {                       // warp-uniform: one guide in one slice of one strand
@@ -1219,7 +1211,7 @@ __device__ __forceinline__ void lean_drain(const SweepArgs& a, ParkBuf& pk, uint
 }
 
 // the patterns of pass 1 (exactly B substitutions outside the slice: no budget left), 64 per iteration
-template <uint32_t USED, int NB, bool FORCED, bool PRED>
+template <uint32_t USED, int NB, bool FORCED>
 __device__ __forceinline__ void lean_exact_pass(const SweepArgs& a, ParkBuf& pk, const uint32_t* xt, uint32_t n, uint32_t n_lines, uint32_t lane,
                                                 const LeanRun& r, LeanStats& st) {
     const uint32_t tl_m = r.tl | (a.M << 24);
@@ -1240,8 +1232,8 @@ __device__ __forceinline__ void lean_exact_pass(const SweepArgs& a, ParkBuf& pk,
         }
         const uint32_t idx0 = r.qh ^ (x0 & 0x0FFFFFFFu), idx1 = r.qh ^ (x1 & 0x0FFFFFFFu);
         uint32_t w0[8], w1[8];
-        lean_load<PRED>(r.sum0, idx0, live0, w0);
-        lean_load<PRED>(r.sum0, idx1, live1, w1);                                    // (no lane has a pattern there when there is no second 32)
+        lean_load(r.sum0, idx0, live0, w0);
+        lean_load(r.sum0, idx1, live1, w1);                                    // (no lane has a pattern there when there is no second 32)
         uint32_t al0 = summary_exact_shape<USED>(w0, r.X), al1 = two ? summary_exact_shape<USED>(w1, r.X) : 0u;
         if (!two) w1[0] = 0u;
         if (al0 && tail && !(w0[0] & SUM_WIDE32)) { uint32_t t[4], v[1] = {al0}; load_tail(r.sum2, idx0, t); summary_tail<1>(t, 0u, r.codes2, v); al0 = v[0]; }
@@ -1287,17 +1279,17 @@ __device__ __forceinline__ void lean_budget_pass(const SweepArgs& a, ParkBuf& pk
         lean_settle(a, pk, lane, w[0], u[0], idx, budget, r.tl, r.tab, st);
     }
 }
-template <int SHAPE, int NB, bool FORCED, bool PRED>
+template <int SHAPE, int NB, bool FORCED>
 __device__ __forceinline__ void lean_run(const SweepArgs& a, const SweepPlan& pl, ParkBuf& pk, const uint32_t* xtab, uint32_t lane, const LeanRun& r,
                                          uint32_t B, LeanStats& st) {
     constexpr uint32_t PROTO = SHAPE == 0 ? 0x3Fu : SHAPE == 1 ? 0x7Fu : 0x1Fu, PAM = SHAPE == 2 ? 0x40u : 0u;
-    lean_exact_pass<PROTO | PAM, NB, FORCED, PRED>(a, pk, xtab + pl.xoff[1][B], pl.xcnt[1][B], pl.xlines[1][B], lane, r, st);
+    lean_exact_pass<PROTO | PAM, NB, FORCED>(a, pk, xtab + pl.xoff[1][B], pl.xcnt[1][B], pl.xlines[1][B], lane, r, st);
     lean_budget_pass<PROTO, PAM, NB, FORCED>(a, pk, xtab + pl.xoff[0][B], pl.xcnt[0][B], pl.xlines[0][B], lane, r, B, st);
 }
 
 // XTG: the xor table is too long for shared memory (4 mismatches: 15.8 k words) and is read from global memory (unit stride,
 // the same few KB by every warp: L1 hits); the host pads it with 64 readable words
-template <int WARPS, int MINB, int NB, bool FORCED = false, bool XTG = false, bool PRED = true>
+template <int WARPS, int MINB, int NB, bool FORCED = false, bool XTG = false>
 __global__ void __launch_bounds__(WARPS * 32, MINB) sweep_lean_kernel(SweepArgs a) {
     __shared__ SweepPlan s_plan;
     __shared__ uint32_t s_park[WARPS][2][PK_SLOTS];
@@ -1405,9 +1397,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) sweep_lean_kernel(SweepArgs 
             r.X[0] = g1.w; r.X[1] = g2.x; r.X[2] = g2.y; r.X[3] = g2.z; r.X[4] = g2.w; r.X[5] = g3.x; r.X[6] = g3.y;
             r.codes2 = g4.y; r.fm = g4.z & 0x0FFFFFFFu; r.tl = (go << 1) | strand;
             const uint32_t shape = g4.w;
-            if (shape == 0u) lean_run<0, NB, FORCED, PRED>(a, s_plan, pk, s_xtab, lane, r, Bo, st);
-            else if (shape == 1u) lean_run<1, NB, FORCED, PRED>(a, s_plan, pk, s_xtab, lane, r, Bo, st);
-            else lean_run<2, NB, FORCED, PRED>(a, s_plan, pk, s_xtab, lane, r, Bo, st);
+            if (shape == 0u) lean_run<0, NB, FORCED>(a, s_plan, pk, s_xtab, lane, r, Bo, st);
+            else if (shape == 1u) lean_run<1, NB, FORCED>(a, s_plan, pk, s_xtab, lane, r, Bo, st);
+            else lean_run<2, NB, FORCED>(a, s_plan, pk, s_xtab, lane, r, Bo, st);
         }
     }
     while (pk.count) lean_drain<NB>(a, pk, lane, st);
@@ -1445,9 +1437,6 @@ cudaError_t launch_sweep(const SweepArgs& a, int variant, int sm_count, cudaStre
     case 10: return launch_sweep_lean_t<4>(a, sm_count, s);   // lean loops, 1024 thr/SM
     case 11: return launch_sweep_lean_t<5>(a, sm_count, s);   // 1280 thr/SM
     case 12: return launch_sweep_lean_t<6>(a, sm_count, s);   // 1536 thr/SM
-    case 13:                                                  // 1536 thr/SM, unpredicated loads in the 64-wide pass (plain batches of at most 3 mismatches)
-        if (a.M <= 3 && !a.fmask && a.n_xtab + 64u <= (uint32_t)XT_SMEM) { sweep_lean_kernel<8, 6, 4, false, false, false><<<sm_count * 6, 8 * 32, 0, s>>>(a); return cudaGetLastError(); }
-        return launch_sweep_lean_t<6>(a, sm_count, s);
     case 0: return launch_sweep_t<8, 3>(a, sm_count, s);      // 768 thr/SM
     case 1: return launch_sweep_t<8, 2>(a, sm_count, s);      // 512 thr/SM
     case 2:                                                   // 1024 thr/SM

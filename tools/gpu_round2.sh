@@ -55,7 +55,7 @@ PY
       grep -c "ERROR SUMMARY\|=========" gpurun_out/${tag}_sanitizer_$2.log; tail -4 gpurun_out/${tag}_sanitizer_$2.log | cut -c1-300; shift 3;;
     benchlaunches) # the launch list of two bench steps (per-launch durations under ncu; the kernel SHARES are what counts)
       # (only the kernels of the enumerate path are profiled: the index build in front of them is a thousand radix-sort launches)
-      timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none -k "regex:sweep|search_|scan_u32|scatter_matches|order_matches|expand_hits|locate_score|specificity|publish|total_u32|variant_|threshold" -c 400 --csv --log-file gpurun_out/${tag}_bench_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-file-e2e > gpurun_out/${tag}_bench_launches.log 2>&1
+      timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none -k "regex:sweep_lean|sweep_kernel|sweep_guides|search_fast|search_kernel|scan_u32|scatter_matches|order_matches|expand_hits|locate_score|specificity|publish|total_u32|variant_|threshold" -c 400 --csv --log-file gpurun_out/${tag}_bench_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-file-e2e > gpurun_out/${tag}_bench_launches.log 2>&1
       tail -2 gpurun_out/${tag}_bench_launches.log | cut -c1-300; shift;;
     bench)
       shift
