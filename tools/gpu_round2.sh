@@ -39,9 +39,9 @@ PY
       tail -3 gpurun_out/${tag}_ncu.log
       ncu -i gpurun_out/${tag}_ncu.ncu-rep --page raw --csv > gpurun_out/${tag}_ncu_raw.csv 2>/dev/null; wc -c gpurun_out/${tag}_ncu_raw.csv
       shift 4;;
-    launches)      # launches <plan>: per-launch durations of a session plan (ncu launch list)
-      timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${tag}_launches.csv python tools/gpu_session.py --plan $2 --tag ${tag}_launches_run > gpurun_out/${tag}_launches.log 2>&1
-      tail -2 gpurun_out/${tag}_launches.log; shift 2;;
+    launches)      # launches <plan>: per-launch durations of the enumerate-path kernels of a session plan (ncu launch list)
+      timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none -k "regex:sweep_lean|sweep_kernel|sweep_guides|search_fast|search_kernel|scan_u32|scatter_matches|order_matches|expand_hits|locate_score|specificity|publish|total_u32|variant_|threshold|order_|DeviceRadixSort|DeviceScan" -c 3000 --csv --log-file gpurun_out/${tag}_launches.csv python tools/gpu_session.py --plan $2 --tag ${tag}_launches_run > gpurun_out/${tag}_launches.log 2>&1
+      tail -2 gpurun_out/${tag}_launches.log | cut -c1-300; shift 2;;
     torchbench)    # torchbench <N> <steps> <warmup>: bench.py as the driver launches it on N GPUs
       timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $2 --steps $3 --warmup $4 > gpurun_out/${tag}_bench_n$2.json 2> gpurun_out/${tag}_bench_n$2.err
       tail -2 gpurun_out/${tag}_bench_n$2.err; cut -c1-900 gpurun_out/${tag}_bench_n$2.json; shift 4;;

@@ -10,6 +10,7 @@ Experiment keys (all optional but name): name, env {VAR: value}, mismatches, alt
 (per step), steps, warmup, pipeline (batches in flight through gsx_enumerate_start / _wait; 0 = plain gsx_enumerate calls),
 parity_sample (guides diffed byte for byte against the CPU oracle over the exported FM-index), file_e2e {"guides": n, "fmt":
 "csv"|"sam"} (whole-file driver instead of the array path), open_again (re-open timing from a saved .gsx on "devices").
+Genome keys: n_runs, skew, devices, sa_shift, save_prefix (also write <workdir>/<prefix>.gsx), open_prefix (open that file instead of building).
 """
 import argparse
 import ctypes as C
@@ -49,8 +50,11 @@ class Session:
         log("genome: %.1f s" % (time.time() - t0))
         t0 = time.time()
         self.save_prefix = genome_spec.get("save_prefix")
-        self.ix = gsx.Index.build_from_text(self.g, self.chroms, sa_shift=genome_spec.get("sa_shift", 2), devices=self.devices,
-                                            save_prefix=self.save_prefix)
+        if genome_spec.get("open_prefix"):       # an index saved by an earlier process (no suffix sorting in this one: profiles stay clean)
+            self.ix = gsx.Index.open(genome_spec["open_prefix"], devices=self.devices)
+        else:
+            self.ix = gsx.Index.build_from_text(self.g, self.chroms, sa_shift=genome_spec.get("sa_shift", 2), devices=self.devices,
+                                                save_prefix=self.save_prefix)
         self.index_s = time.time() - t0
         self.open_s = self.ix.open_seconds()
         log("index: %.1f s %s, %.2f GB/device on %s" % (self.index_s, self.open_s, self.ix.device_bytes / 1e9, self.devices))
@@ -210,8 +214,9 @@ def main():
     path = os.path.join(ROOT, "gpurun_out", args.tag + ".jsonl")
     with open(path, "a") as f:
         for gspec in plan["genomes"]:
-            if gspec.get("save_prefix"):
-                gspec["save_prefix"] = os.path.join(args.workdir, gspec["save_prefix"])
+            for key in ("save_prefix", "open_prefix"):
+                if gspec.get(key):
+                    gspec[key] = os.path.join(args.workdir, gspec[key])
             s = Session(args, gspec)
             f.write(json.dumps({"name": "_index", "n_runs": gspec.get("n_runs", 0), "index_wall_s": s.index_s, "open_seconds": s.open_s,
                                 "device_gb": s.ix.device_bytes / 1e9, "devices": s.devices}) + "\n"); f.flush()
