@@ -1126,6 +1126,7 @@ static void run_device_job(DeviceJob* job) {
         S.guide_hoff = d_hoff; S.count_by_distance = d_cbd; S.chr = L.chr; S.cfd = L.cfd; S.flags = L.flags;
         S.counted = B.alloc<uint8_t>(nh, true, s); S.specificity = B.alloc<float>(n); S.perfect = B.alloc<uint8_t>(n);
         S.n_guides = n; S.n_dist = n_dist; S.sam_rule = p.sam_scoring ? 1 : 0; S.max_off_targets = p.max_off_targets;
+        S.warp_per_guide = (uint32_t)env_int("GSX_SPEC_WARP", (uint64_t)nh > (uint64_t)n * 64 ? 1 : 0);
         CK(launch_specificity(S, s));
         CK(cudaEventRecord(ev[4], s));
         // ---- results to host ---------------------------------------------------------------------------------------------

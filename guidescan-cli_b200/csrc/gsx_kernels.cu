@@ -1680,9 +1680,61 @@ __global__ void locate_score_kernel(LocateArgs a) {
     if ((threadIdx.x & 31) == 0 && steps) atomicAdd(a.stats + 3, (unsigned long long)steps);
 }
 
-// one thread per guide: float32 running sum in the reference's output order
+// one thread per guide: float32 running sum in the reference's output order (batches with a dozen hits per guide)
 __global__ void specificity_kernel(SpecArgs a) {
     for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < a.n_guides; g += gridDim.x * blockDim.x) guide_specificity(a, g);
+}
+// One WARP per guide, for batches with hundreds or thousands of hits per guide (bulges: 14 k; repeat-family and low-complexity
+// guides): the per-thread form walks its hits one dependent load at a time (8.7 ms for 512 bulge guides, a third of the device time on
+// the skew stressor).  Here the lanes fetch 32 consecutive hits at once; which of them the reference's loop visits before its
+// max_off_targets cut (printer.hpp:129 / :259) is a prefix count (ballot); the float32 additions then happen in hit order, one lane's
+// value after the other, so the sum has the reference's rounding (same statement as gsx_core.h guide_specificity, checked against it
+// by the golden tests in both forms).
+__global__ void specificity_warp_kernel(SpecArgs a) {
+    const uint32_t lane = threadIdx.x & 31u, FULL = 0xffffffffu;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t g = warp; g < a.n_guides; g += n_warps) {
+        const uint32_t b = a.guide_hoff[g], n = a.guide_hoff[g + 1] - b;
+        float cfd_sum = 0.0f; bool perfect = false;
+        uint32_t i = 0;
+        for (uint32_t d = 0; d < a.n_dist; d++) {
+            const uint32_t cnt = a.count_by_distance[(size_t)g * a.n_dist + d];
+            long long n_off = 0;                                                  // resolved hits of this distance so far (SAM rule)
+            bool cut = false;                                                     // the reference's loop has hit its `break`
+            for (uint32_t j0 = 0; j0 < cnt && !cut; j0 += 32u) {
+                const uint32_t j = j0 + lane;
+                const bool in = j < cnt;
+                const uint32_t h = b + i + j;
+                uint8_t fl = 0; int32_t chr = -1; float c = 0.0f;
+                if (in) { fl = a.flags[h]; chr = a.chr[h]; c = a.cfd[h]; }
+                const bool resolved = in && chr >= 0;
+                const uint32_t rmask = __ballot_sync(FULL, resolved);
+                // visited: the loop reaches hit j (every hit before the cut is looked at, resolved or not)
+                bool visited = in;
+                if (a.max_off_targets != -1) {
+                    if (a.sam_rule) visited = in && n_off + (long long)__popc(rmask & ((1u << lane) - 1u)) < (long long)a.max_off_targets;
+                    else visited = in && (long long)j < (long long)a.max_off_targets;
+                }
+                const uint32_t vmask = __ballot_sync(FULL, visited);
+                if (__ballot_sync(FULL, visited && (fl & 1))) perfect = true;
+                const bool add = visited && resolved;
+                uint32_t amask = __ballot_sync(FULL, add);
+                if (add) a.counted[h] = 1;
+                n_off += __popc(amask);
+                // the additions, in hit order (every lane keeps the same running sum)
+                while (amask) {
+                    const int src = __ffs(amask) - 1; amask &= amask - 1u;
+                    cfd_sum += __shfl_sync(FULL, c, src);
+                }
+                if (vmask != __ballot_sync(FULL, in)) cut = true;                 // some hit of this chunk was not visited: the loop has broken
+            }
+            i += cnt;
+        }
+        float spec = 0.0f;
+        if (n == 0 && !a.sam_rule) spec = 1.0f;                                   // NA row, printer.hpp:190-199
+        else { if (!perfect) cfd_sum += 1.0f; if (cfd_sum > 0.0f) spec = 1.0f / cfd_sum; }
+        if (lane == 0) { a.specificity[g] = spec; a.perfect[g] = perfect ? 1 : 0; }
+    }
 }
 
 __global__ void threshold_kernel(const unsigned long long* guide_count, uint8_t* dropped, uint32_t n_guides) {
@@ -1737,7 +1789,9 @@ cudaError_t launch_locate_score(const LocateArgs& a, cudaStream_t s) {
     locate_score_kernel<<<grid_for(a.n_hits, 128, 148 * 16), 128, 0, s>>>(a); return cudaGetLastError();
 }
 cudaError_t launch_specificity(const SpecArgs& a, cudaStream_t s) {
-    specificity_kernel<<<grid_for(a.n_guides, 128, 148 * 8), 128, 0, s>>>(a); return cudaGetLastError();
+    if (a.warp_per_guide) specificity_warp_kernel<<<grid_for(a.n_guides * 32u, 128, 148 * 16), 128, 0, s>>>(a);
+    else specificity_kernel<<<grid_for(a.n_guides, 128, 148 * 8), 128, 0, s>>>(a);
+    return cudaGetLastError();
 }
 cudaError_t launch_threshold(const unsigned long long* gc, uint8_t* dropped, uint32_t n, cudaStream_t s) {
     threshold_kernel<<<grid_for(n, 256, 148 * 4), 256, 0, s>>>(gc, dropped, n); return cudaGetLastError();

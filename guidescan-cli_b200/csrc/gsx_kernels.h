@@ -100,6 +100,7 @@ struct SpecArgs {
     uint8_t* counted; float* specificity; uint8_t* perfect;
     uint32_t n_guides, n_dist, sam_rule;
     int64_t max_off_targets;
+    uint32_t warp_per_guide;           // 1: one warp per guide (batches averaging more than 64 hits per guide), 0: one thread per guide
 };
 
 cudaError_t upload_cfd_tables();

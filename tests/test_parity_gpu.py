@@ -492,3 +492,15 @@ def test_lean_sweep_kernel_on_edited_guides(gsx, gpu_index, tmp_path, monkeypatc
     _, ctr = gpu_index("g200k").enumerate_file(gcsv, out, _params(gsx, kw), fmt=kw.get("fmt", "csv"), mode=kw.get("mode", "complete"))
     assert ctr["edited_guides"] > 0 and ctr["seeds"] > 0
     assert open(out).read() == slice_of(golden_output("g200k", variant).decode(), kw.get("fmt") == "sam")
+
+
+@pytest.mark.parametrize("case,variant", [(c, v) for c, v in golden_cases() if v in ("m4_max1_sam", "m4_max2_csv", "m3_csv", "m2_sam", "m1_r1_d1_altNAG_max3_csv",
+                                                                                      "m1_r1_d1_sam_succinct", "m3_thr1_csv", "m0_r1_d1_csv")])
+def test_warp_per_guide_specificity(gsx, gpu_index, golden_dir, tmp_path, monkeypatch, case, variant):
+    """specificity_warp_kernel (one warp per guide: chosen by itself above 64 hits per guide) forced on golden cases with few and with
+    many hits per guide, with the max_off_targets cut of the CSV rule (index-based) and of the SAM rule (count-based)"""
+    monkeypatch.setenv("GSX_SPEC_WARP", "1")
+    kw = golden_manifest()["cases"][case]["variants"][variant]["opts"]
+    out = os.path.join(tmp_path, "g.out")
+    gpu_index(case).enumerate_file(golden_dir[case][1], out, _params(gsx, kw), fmt=kw.get("fmt", "csv"), mode=kw.get("mode", "complete"))
+    assert open(out, "rb").read() == golden_output(case, variant)
