@@ -109,8 +109,10 @@ typedef struct {
 
 /* ---- index ------------------------------------------------------------------------------------------- */
 /* Opens <prefix>.forward / .reverse / .gs written by the reference's `guidescan index` (sdsl csa_wt<wt_huff<>,64,8192>;
- * layout: SURVEY.md App. B) or by gsx_index_build, converts to the GPU layout and replicates it on `devices`
- * (NULL / 0 => device 0).  Replaces sdsl::load_from_file + genome_index construction, src/guidescan.cxx:186-211. */
+ * layout: SURVEY.md App. B) or <prefix>.gsx / .gs written by gsx_index_build, lays the index out on the first of `devices`
+ * (NULL / 0 => device 0; the derived arrays -- jump table, look-ahead lines, pattern summaries -- are computed there) and copies the
+ * finished arrays to every further device, peer to peer.  A device named twice gives two job slots over one copy.
+ * Replaces sdsl::load_from_file + genome_index construction, src/guidescan.cxx:186-211. */
 int gsx_index_open(const char* prefix, const int* devices, int n_devices, gsx_index** out);
 /* Builds the GPU index directly from a FASTA file on the device (suffix sorting on the GPU); replaces
  * do_index_cmd, src/guidescan.cxx:109-179.  If save_prefix != NULL also writes <save_prefix>.gsx + .gs. */
@@ -151,13 +153,15 @@ int gsx_index_export_sa_samples(const gsx_index*, int strand, uint32_t* out, uin
 int gsx_enumerate(const gsx_index*, const gsx_guide* guides, size_t n_guides, const gsx_params*, gsx_result** out);
 /* The same call in two halves, for callers that pipeline batches: gsx_enumerate_start returns at once and the batch runs on a
  * library thread; gsx_enumerate_wait blocks until it is done, hands out the result (or the error) and releases the handle.
- * Calls in flight on the same device take turns for its kernels, so batch k's copies to the host and the caller's work on its
- * result overlap batch k+1's search -- what the reference gets from N worker threads behind one output mutex
- * (src/guidescan.cxx:241-251, process.hpp:119-126).  `guides`, the strings they point to and `params` stay borrowed until
+ * Calls in flight on the same device take turns from their first kernel to their last result copy, so what overlaps a running batch
+ * is host work: packing the guides of the next one, formatting the result of the last one -- what the reference gets from N worker
+ * threads behind one output mutex (src/guidescan.cxx:241-251, process.hpp:119-126).  `guides`, the strings they point to and `params` stay borrowed until
  * gsx_enumerate_wait returns. */
 typedef struct gsx_pending gsx_pending;
 int gsx_enumerate_start(const gsx_index*, const gsx_guide* guides, size_t n_guides, const gsx_params*, gsx_pending** out);
 int gsx_enumerate_wait(gsx_pending*, gsx_result** out);
+/* The arrays of the result.  With several devices every device returns its own part; the merged arrays of this view are built on the
+ * first call (the library's own formatter, gsx_format_rows / gsx_enumerate_file, reads the parts in place and never needs them). */
 int gsx_result_view_get(const gsx_result*, gsx_result_view* view);
 int gsx_result_counters(const gsx_result*, gsx_counters* out);
 /* The reference's match.sequence of hit `hit` complemented as it is printed (printer.hpp:232,264); buf >= 48 bytes. */
