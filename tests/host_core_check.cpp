@@ -45,6 +45,7 @@ static bool g_prune = false;
 static bool g_fused = false;     // alternative PAMs in one pass (gsx_core.h fused_pam_ok), as gsx_enumerate does under GSX_FUSED_PAMS=1
 static bool g_forced = false;    // the sweep skips patterns that substitute an inserted position of an edited guide (sweep_kernel<..., FORCED>)
 static std::vector<uint32_t> g_vfmask;
+static int g_parts = 1;          // split the result into this many parts, as gsx_enumerate does over several devices (formatter / merged view)
 static bool g_variants = false;  // bulges through edited guides (gsx_core.h variant_rewrite), as gsx_enumerate does when Prepared::variant_ok
 
 static std::vector<uint64_t> g_tail[2];     // 4 words per block: hi7, lo7, hi8, lo8 (the scratch planes the summaries' sum2 is built from)
@@ -465,6 +466,7 @@ int main(int argc, char** argv) {
         else if (a == "--ftab") g_ftab_L = atoi(argv[++i]);
         else if (a == "--sweep") g_sweep_sb = atoi(argv[++i]);
         else if (a == "--variants") g_variants = true;
+        else if (a == "--parts") g_parts = atoi(argv[++i]);
         else if (a == "--fused") g_fused = true;
         else if (a == "--forced") g_forced = true;
         else if (a == "--sam") sam = true; else if (a == "--succinct") complete = false; else if (a == "-a") alts.push_back(argv[++i]);
@@ -623,8 +625,46 @@ int main(int argc, char** argv) {
     H.abs_pos = abs_pos.data(); H.sa_row = hit_row.data(); H.chr = chr.data(); H.pos1 = pos1.data(); H.strand = strand.data(); H.distance = distance.data();
     H.rna = rna.data(); H.dna = dna.data(); H.index_id = index_id.data(); H.cfd = cfd.data(); H.counted = counted.data();
     H.key_lo = key_lo.data(); H.key_hi = prep.wide ? key_hi.data() : nullptr; H.mlen = mlen.data();
-    res.parts.push_back(H); res.part_g0.push_back(0); res.part_h0.push_back(0); res.n_dist = n_dist; res.wide = prep.wide; res.guides = prep.recs;
+    res.n_dist = n_dist; res.wide = prep.wide; res.guides = prep.recs;
+    std::vector<std::vector<uint32_t>> part_hoff;
+    if (g_parts <= 1) { res.parts.push_back(H); res.part_g0.push_back(0); res.part_h0.push_back(0); }
+    else {
+        // the same arrays cut into contiguous guide shards, one HostArrays each with its own guide and hit numbering: what
+        // gsx_enumerate assembles from several devices (some shards empty when there are fewer guides than parts)
+        part_hoff.resize(g_parts);
+        for (int k = 0; k < g_parts; k++) {
+            const size_t g0 = n * k / g_parts, g1 = n * (k + 1) / g_parts; const uint32_t h0 = hoff[g0], h1 = hoff[g1];
+            HostArrays P = H;
+            P.n_guides = g1 - g0; P.n_hits = h1 - h0;
+            part_hoff[k].resize(g1 - g0 + 1);
+            for (size_t i = 0; i <= g1 - g0; i++) part_hoff[k][i] = hoff[g0 + i] - h0;
+            P.hoff = part_hoff[k].data(); P.dropped += g0; P.n_hits_of += g0; P.specificity += g0; P.perfect += g0; P.cbd += g0 * n_dist;
+            P.abs_pos += h0; P.sa_row += h0; P.chr += h0; P.pos1 += h0; P.strand += h0; P.distance += h0; P.rna += h0; P.dna += h0; P.index_id += h0;
+            P.cfd += h0; P.counted += h0; P.key_lo += h0; if (P.key_hi) P.key_hi += h0; P.mlen += h0;
+            res.parts.push_back(P); res.part_g0.push_back(g0); res.part_h0.push_back(h0);
+        }
+    }
     gsx_build_view(&res);
+    if (g_parts > 1) {
+        // the merged view (built on request) must be the unsplit arrays again
+        gsx_result_view v;
+        if (gsx_result_view_get(&res, &v)) { fprintf(stderr, "view failed\n"); return 1; }
+        bool same = v.n_guides == n && v.n_hits == nh && !memcmp(v.specificity, spec.data(), n * 4) && !memcmp(v.n_hits_of, nhits.data(), n * 4) &&
+                    !memcmp(v.count_by_distance, cbd.data(), n * n_dist * 4) && !memcmp(v.dropped, dropped.data(), n);
+        same = same && (nh == 0 || (!memcmp(v.abs_pos, abs_pos.data(), nh * 8) && !memcmp(v.chr, chr.data(), nh * 4) && !memcmp(v.pos1, pos1.data(), nh * 4) &&
+                                    !memcmp(v.cfd, cfd.data(), nh * 4) && !memcmp(v.counted, counted.data(), nh) && !memcmp(v.distance, distance.data(), nh) &&
+                                    !memcmp(v.sa_row, hit_row.data(), nh * 4) && !memcmp(v.strand, strand.data(), nh)));
+        for (size_t g = 0; same && g < n; g++) same = v.first_hit[g] == hoff[g];
+        char a1[64], a2[64];
+        for (uint32_t h = 0; same && h < nh; h += 7) {                      // match strings through the part lookup of the ABI call
+            gsx_result_match_sequence(&res, h, a1, sizeof a1);
+            MatchRec m{}; m.key_lo = key_lo[h]; m.key_hi = prep.wide ? key_hi[h] : 0; m.info = (uint32_t)mlen[h] << 24;
+            size_t gi = (size_t)(std::upper_bound(hoff.begin(), hoff.end() - 1, h) - hoff.begin()) - 1;
+            uint32_t len = decode_match(m, prep.recs[gi], prep.wide, a2); for (uint32_t i = 0; i < len; i++) a2[i] = complement_char(a2[i]); a2[len] = 0;
+            same = !strcmp(a1, a2);
+        }
+        if (!same) { fprintf(stderr, "merged view of %d parts differs from the unsplit arrays\n", g_parts); return 3; }
+    }
 
     FILE* out = fopen(out_path.c_str(), "wb");
     char* buf; size_t len;

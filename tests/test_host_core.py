@@ -163,3 +163,17 @@ def test_per_layout_row_filters_equal_the_general_ones(harness):
     r = subprocess.run([harness, "--shape-selftest"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     assert "shape selftest ok" in r.stdout
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("case,variant", [("g200k", "m3_csv"), ("g200k", "m3_altNAG_sam"), ("g150kN", "m1_r1_d1_csv"), ("g200k", "m4_max1_sam"), ("g150kN", "m3_thr1_csv")])
+@pytest.mark.parametrize("parts", [2, 3, 64])
+def test_results_in_several_parts_format_and_merge_like_one(harness, golden_dir, golden_index, tmp_path, case, variant, parts):
+    """what gsx_enumerate assembles from several devices, without a GPU: the result cut into contiguous guide shards (64: more parts than
+    guides, so some are empty) formats to the golden text -- the formatter reads the parts in place -- and the merged view built by
+    gsx_result_view_get, first_hit and gsx_result_match_sequence equal the unsplit arrays"""
+    kw = golden_manifest()["cases"][case]["variants"][variant]["opts"]
+    out = os.path.join(tmp_path, "h.out")
+    r = subprocess.run([harness, golden_index[case], golden_dir[case][1], out] + variant_cli_args(kw) + ["--parts", str(parts)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert open(out, "rb").read() == golden_output(case, variant)
