@@ -8,6 +8,12 @@ device-resident number (`value`), wall clock bracketed by barrier + synchronize 
 C ABI with host buffers (`e2e`), max over ranks.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl gsx|reference] [--genome-mb MB] [--guides-per-step G]
+                  [--mismatches M] [--alt-pam NAG] [--rna-bulges R] [--dna-bulges D] [--n-runs K] [--skew] [--e2e-pipeline P]
+
+Side blocks of the line: `roofline` (algorithmic sector bytes over the search launches' time against the measured streaming peak, with the
+DRAM traffic of the committed ncu capture and the commit it was taken at, and the slice-gather ceiling that applies to a slice-major
+sweep), `cpu_baseline` + `parity_on_cpu_sample` (the CPU arm on the first guides of the workload, its text diffed against the GPU arm's),
+`file_e2e` (guides CSV in, CSV text out through gsx_enumerate_file; also to /dev/null), `clocks` (nvidia-smi during the timed region).
 """
 from __future__ import annotations
 
