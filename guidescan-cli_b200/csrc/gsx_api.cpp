@@ -309,6 +309,11 @@ extern "C" int gsx_index_build_text(const uint8_t* text, uint64_t length, const 
     });
 }
 
+extern "C" int gsx_index_save_reference_format(const gsx_index* ix, const char* prefix) {
+    if (!ix || !prefix) return fail(GSX_ERR_ARG, "null argument");
+    return guarded([&] { std::string err; return save_sdsl_index(prefix, ix->host, err) ? (int)GSX_OK : fail(GSX_ERR_IO, err); });
+}
+
 extern "C" int gsx_index_close(gsx_index* ix) {
     if (!ix) return GSX_OK;
     for (auto& d : ix->dev) { free_device_index(d); pool_trim(d.device); }
@@ -603,15 +608,6 @@ int gsx_prepare_guides(const gsx_guide* guides, size_t n, const gsx_params* p, g
 // of the grid idle while a bulge search runs for seconds.  The roots are therefore expanded on the host, breadth first and
 // through the kernels' own node arithmetic (gsx_core.h make_child over the host copy of the blocks), until there are enough
 // nodes for every warp; the kernel then takes those nodes as its tasks.  Same tree, same matches.
-static DevStrand host_view(const HostStrand& h) {
-    DevStrand d{};
-    d.blocks = h.blocks.data(); d.sa_samples = h.sa_samples.data(); d.exc_rows = h.exc_rows.data(); d.exc_lf = h.exc_lf.data();
-    d.n_rows = h.n_rows.data(); d.n = (uint32_t)h.n; d.n_exc = (uint32_t)h.exc_rows.size(); d.n_nrows = (uint32_t)h.n_rows.size();
-    d.sa_shift = h.sa_shift; for (int c = 0; c < 5; c++) d.C[c] = h.C[c];
-    d.exc_lo = h.exc_rows.empty() ? 0xFFFFFFFFu : h.exc_rows.front(); d.exc_hi = h.exc_rows.empty() ? 0u : h.exc_rows.back();
-    d.blk_shift = 5;
-    return d;
-}
 template <bool WIDE>
 static std::vector<Node> expand_roots(const gsx_index* ix, const Prepared& prep, size_t g0, uint32_t n, uint32_t M, uint32_t R, uint32_t D,
                                       size_t want, uint32_t max_depth) {

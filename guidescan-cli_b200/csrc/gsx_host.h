@@ -45,6 +45,13 @@ bool load_genome_structure(const std::string& path, HostIndex& ix, std::string& 
 bool read_fasta(const std::string& path, std::vector<uint8_t>& seq, HostIndex& ix, std::string& err);   // seq_io.cxx:57-63,74-110
 bool save_gsx(const std::string& prefix, const HostIndex& ix, std::string& err);
 bool load_gsx(const std::string& prefix, HostIndex& ix, std::string& err);
+DevStrand host_view(const HostStrand& h);                          // the host arrays behind the kernels' own index arithmetic (gsx_core.h)
+// the reference's own format back out (gsx_sdsl_write.cpp): <prefix>.forward / .reverse / .gs, byte for byte what `guidescan index` writes
+bool save_sdsl_index(const std::string& prefix, const HostIndex& ix, std::string& err);
+bool save_sdsl_strand(const std::string& path, const HostStrand& h, unsigned threads, std::string& err);
+// parts of it on their own, for tests/sdsl_write_check.cpp
+bool sdsl_write_wavelet_tree(const std::string& path, const HostStrand& h, unsigned threads, std::string& err);
+bool sdsl_write_bit_vector_supports(const std::string& path, const std::vector<uint64_t>& words, uint64_t n_bits, std::string& err);
 
 // the device arrays of one strand index, each with its size in bytes (the replicas on further devices are peer copies)
 //   exc_map: one bit per 64-row block holding an exception row (SearchArgs::exc_map)

@@ -12,6 +12,7 @@
 #include <cstring>
 #include <fstream>
 #include <sstream>
+#include <thread>
 
 namespace gsx {
 
@@ -99,7 +100,8 @@ bool load_sdsl_strand(const std::string& path, HostStrand& out, std::string& err
     if (size == 0 || size > 0xFFFFFFFFull) return fail("size out of range for 32-bit rows");
     std::vector<uint64_t> bv;
     if (!r.int_vector(1, bits, w, &bv)) return fail("wavelet tree bit vector");
-    if (!r.int_vector(64, bits, w, nullptr)) return fail("rank support");
+    uint64_t skipped;
+    if (!r.int_vector(64, skipped, w, nullptr)) return fail("rank support");
     if (!r.skip_select() || !r.skip_select()) return fail("select support");
     uint64_t n_nodes; if (!r.u64(n_nodes) || n_nodes == 0 || n_nodes > 1024) return fail("tree size");
     std::vector<WtNode> nodes(n_nodes);
@@ -113,22 +115,93 @@ bool load_sdsl_strand(const std::string& path, HostStrand& out, std::string& err
     fclose(r.f);
     if (sa_w == 0 || sa_w > 32) { err = "SA sample width unsupported in " + path; return false; }
 
-    // BWT recovery: walk the tree for every row with one read cursor per inner node (children receive their
-    // elements in order, so no rank is needed).
-    std::vector<uint64_t> cursor(n_nodes);
-    for (size_t v = 0; v < n_nodes; v++) cursor[v] = nodes[v].bv_pos;
-    StrandBuilder b(&out, size);
-    const uint64_t* bvp = bv.data();
-    for (uint64_t i = 0; i < size; i++) {
-        uint32_t v = 0;
-        while (nodes[v].child[0] != 0xFFFF) {
-            uint64_t p = cursor[v]++;
-            uint32_t bit = (uint32_t)((bvp[p >> 6] >> (p & 63)) & 1);
-            v = nodes[v].child[bit];
-        }
-        b.push((uint8_t)nodes[v].bv_pos_rank);
+    for (size_t v = 0; v < n_nodes; v++) {                       // breadth-first layout: children come after their parent
+        const WtNode& nd = nodes[v];
+        const bool leaf = nd.child[0] == 0xFFFF;
+        if (leaf ? nd.child[1] != 0xFFFF : (nd.child[0] <= v || nd.child[1] <= v || nd.child[0] >= n_nodes || nd.child[1] >= n_nodes || nd.bv_pos > bits))
+            { err = "malformed index file " + path + " (tree)"; return false; }
     }
-    b.finish();
+    // BWT recovery: walk the tree for every row with one read cursor per inner node (children receive their elements in order,
+    // so no rank is needed along the way).  Row ranges are independent once the cursors at a range start are known: the rows
+    // before r that pass a node are counted down from the root with ranks over the bit vector (ones before each 512-bit block
+    // are summed here; the file's own rank directory is not trusted with it).  One host thread per range.
+    const uint64_t* bvp = bv.data();
+    std::vector<uint64_t> ones512(bv.size() / 8 + 2, 0);
+    for (size_t w = 0; w < bv.size(); w++) { if ((w & 7) == 0) ones512[w / 8 + 1] = ones512[w / 8]; ones512[w / 8 + 1] += (uint64_t)__builtin_popcountll(bvp[w]); }
+    auto rank1 = [&](uint64_t pos) {                           // ones in bits [0, pos)
+        uint64_t r = ones512[pos >> 9];
+        for (uint64_t w = (pos >> 9) * 8; w < (pos >> 6); w++) r += (uint64_t)__builtin_popcountll(bvp[w]);
+        if (pos & 63) r += (uint64_t)__builtin_popcountll(bvp[pos >> 6] & (~0ull >> (64 - (pos & 63))));
+        return r;
+    };
+    const uint64_t n_blocks = size / 64 + 1;
+    out.n = size; out.blocks.assign(n_blocks, OccBlock{});
+    out.exc_rows.clear(); out.exc_lf.clear(); out.n_rows.clear(); out.exc_sym.clear();
+    const char* knob = getenv("GSX_LOAD_THREADS");               // tests: several ranges on a small index
+    const unsigned T = knob && atoi(knob) > 0 ? (unsigned)atoi(knob)
+                     : (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(std::max(1u, std::thread::hardware_concurrency()), size / (1u << 20) + 1));
+    struct Range { uint64_t run[256]; std::vector<uint32_t> exc_rows, n_rows; std::vector<uint8_t> exc_sym; std::vector<uint64_t> exc_rank; bool ok = true; };
+    std::vector<Range> ranges(T);
+    auto decode = [&](unsigned t) {
+        Range& R = ranges[t];
+        const uint64_t r0 = (size / 64) * t / T * 64, r1 = t + 1 == T ? size : (size / 64) * (t + 1) / T * 64;
+        std::vector<uint64_t> passing(n_nodes, 0), cursor(n_nodes, 0);
+        memset(R.run, 0, sizeof R.run);
+        passing[0] = r0;
+        for (size_t v = 0; v < n_nodes; v++) {
+            const WtNode& nd = nodes[v];
+            if (nd.child[0] == 0xFFFF) { R.run[(uint8_t)nd.bv_pos_rank] = passing[v]; continue; }
+            if (nd.bv_pos + passing[v] > bits) { R.ok = false; return; }
+            const uint64_t ones = rank1(nd.bv_pos + passing[v]) - rank1(nd.bv_pos);
+            passing[nd.child[1]] = ones; passing[nd.child[0]] = passing[v] - ones;
+            cursor[v] = nd.bv_pos + passing[v];
+        }
+        OccBlock cur{};
+        for (uint64_t row = r0; row < r1; row++) {
+            const uint32_t r = (uint32_t)(row & 63);
+            if (r == 0) {
+                cur = OccBlock{};
+                cur.cnt[0] = (uint32_t)R.run['A']; cur.cnt[1] = (uint32_t)R.run['C']; cur.cnt[2] = (uint32_t)R.run['G']; cur.cnt[3] = (uint32_t)R.run['T'];
+            }
+            uint32_t v = 0;
+            while (nodes[v].child[0] != 0xFFFF) {
+                const uint64_t p = cursor[v]++;
+                if (p >= bits) { R.ok = false; return; }
+                v = nodes[v].child[(bvp[p >> 6] >> (p & 63)) & 1];
+            }
+            const uint8_t sym = (uint8_t)nodes[v].bv_pos_rank;
+            int code = sym_code(sym);
+            if (code < 0) {
+                R.exc_rows.push_back((uint32_t)row); R.exc_sym.push_back(sym); R.exc_rank.push_back(R.run[sym]);
+                if (sym == 'N') R.n_rows.push_back((uint32_t)row);
+                code = 0;
+            }
+            cur.hi |= (uint64_t)(code >> 1) << r; cur.lo |= (uint64_t)(code & 1) << r;
+            R.run[sym]++;
+            if (r == 63 || row + 1 == size) out.blocks[row >> 6] = cur;
+        }
+    };
+    {
+        std::vector<std::thread> pool;
+        for (unsigned t = 1; t < T; t++) pool.emplace_back(decode, t);
+        decode(0);
+        for (auto& th : pool) th.join();
+    }
+    for (const Range& R : ranges) if (!R.ok) { err = "malformed index file " + path + " (wavelet tree bits)"; return false; }
+    const uint64_t* total = ranges[T - 1].run;                  // a range starts from the counts before it, so the last one ends on the totals
+    if (size % 64 == 0) {                                      // one more checkpoint-only block for lookups at i == n
+        OccBlock& last = out.blocks[n_blocks - 1];
+        last.cnt[0] = (uint32_t)total['A']; last.cnt[1] = (uint32_t)total['C']; last.cnt[2] = (uint32_t)total['G']; last.cnt[3] = (uint32_t)total['T'];
+    }
+    uint64_t Cb[257], acc = 0;
+    for (int c = 0; c < 256; c++) { Cb[c] = acc; acc += total[c]; }
+    out.C[0] = (uint32_t)Cb['A']; out.C[1] = (uint32_t)Cb['C']; out.C[2] = (uint32_t)Cb['G']; out.C[3] = (uint32_t)Cb['T']; out.C[4] = (uint32_t)Cb['N'];
+    for (const Range& R : ranges) {
+        out.exc_rows.insert(out.exc_rows.end(), R.exc_rows.begin(), R.exc_rows.end());
+        out.n_rows.insert(out.n_rows.end(), R.n_rows.begin(), R.n_rows.end());
+        out.exc_sym.insert(out.exc_sym.end(), R.exc_sym.begin(), R.exc_sym.end());
+        for (size_t i = 0; i < R.exc_rows.size(); i++) out.exc_lf.push_back((uint32_t)(Cb[R.exc_sym[i]] + R.exc_rank[i]));
+    }
     // SA samples: entry k = SA[64 k], bit-packed little-endian (csa_sampling_strategy.hpp:85-111)
     uint64_t n_samples = sa_bits / sa_w;
     if (n_samples < (size + 63) / 64) { err = "too few SA samples in " + path; return false; }
@@ -142,6 +215,16 @@ bool load_sdsl_strand(const std::string& path, HostStrand& out, std::string& err
         out.sa_samples[k] = (uint32_t)(v & mask);
     }
     return true;
+}
+
+DevStrand host_view(const HostStrand& h) {
+    DevStrand d{};
+    d.blocks = h.blocks.data(); d.sa_samples = h.sa_samples.data(); d.exc_rows = h.exc_rows.data(); d.exc_lf = h.exc_lf.data();
+    d.n_rows = h.n_rows.data(); d.n = (uint32_t)h.n; d.n_exc = (uint32_t)h.exc_rows.size(); d.n_nrows = (uint32_t)h.n_rows.size();
+    d.sa_shift = h.sa_shift; for (int c = 0; c < 5; c++) d.C[c] = h.C[c];
+    d.exc_lo = h.exc_rows.empty() ? 0xFFFFFFFFu : h.exc_rows.front(); d.exc_hi = h.exc_rows.empty() ? 0u : h.exc_rows.back();
+    d.blk_shift = 5;
+    return d;
 }
 
 bool load_genome_structure(const std::string& path, HostIndex& ix, std::string& err) {

@@ -60,13 +60,14 @@ class GuideRow(C.Structure):
 EXPORTS = ["gsx_params_default", "gsx_index_open", "gsx_index_build", "gsx_index_build_text", "gsx_index_close",
            "gsx_index_genome_length",
            "gsx_index_n_chromosomes", "gsx_index_chromosome_name", "gsx_index_chromosome_length", "gsx_index_device_bytes",
-           "gsx_index_n_devices", "gsx_index_open_seconds", "gsx_index_device_checksum", "gsx_enumerate_start", "gsx_enumerate_wait", "gsx_index_rank", "gsx_index_locate", "gsx_index_export_bwt", "gsx_index_export_sa_samples", "gsx_enumerate", "gsx_result_view_get",
+           "gsx_index_n_devices", "gsx_index_save_reference_format", "gsx_index_open_seconds", "gsx_index_device_checksum", "gsx_enumerate_start", "gsx_enumerate_wait", "gsx_index_rank", "gsx_index_locate", "gsx_index_export_bwt", "gsx_index_export_sa_samples", "gsx_enumerate", "gsx_result_view_get",
            "gsx_result_counters", "gsx_result_match_sequence", "gsx_result_free", "gsx_format_rows", "gsx_format_header",
            "gsx_enumerate_file", "gsx_guides_csv_open", "gsx_guides_csv_row", "gsx_guides_csv_close", "gsx_generate_kmers", "gsx_free", "gsx_last_error", "gsx_version", "gsx_device_count"]
 
 _L.gsx_last_error.restype = C.c_char_p
 _L.gsx_version.restype = C.c_char_p
 _L.gsx_index_open.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]
+_L.gsx_index_save_reference_format.argtypes = [C.c_void_p, C.c_char_p]
 _L.gsx_index_build.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]
 _L.gsx_index_build_text.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_char_p), C.POINTER(C.c_uint64), C.c_uint32,
                                     C.c_uint32, C.c_char_p, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]
@@ -273,6 +274,10 @@ class Index:
         out = C.c_uint64()
         _ck(_L.gsx_index_device_checksum(self.h, slot, C.byref(out)), "gsx_index_device_checksum")
         return out.value
+
+    def save_reference_format(self, prefix: str) -> None:
+        """<prefix>.forward / .reverse / .gs as the reference's `guidescan index` writes them (src/guidescan.cxx:167-175)"""
+        _ck(_L.gsx_index_save_reference_format(self.h, prefix.encode()), "gsx_index_save_reference_format")
 
     def open_seconds(self):
         """(files / suffix sorting, upload + derived arrays on the first device, replication to the other devices)"""

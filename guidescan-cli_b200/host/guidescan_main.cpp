@@ -15,8 +15,9 @@ static void usage() {
     fprintf(stderr,
             "Guidescan all-in-one interface (B200 build).\n"
             "Usage: guidescan [--version] SUBCOMMAND ...\n\n"
-            "  index [--index PREFIX] GENOME.fa\n"
+            "  index [--index PREFIX] [--reference-format] GENOME.fa\n"
             "      Builds a genomic index over a FASTA file (GPU suffix sorting; writes PREFIX.gsx + PREFIX.gs).\n"
+            "      --reference-format          Also write PREFIX.forward / PREFIX.reverse, the files of the original guidescan (extension).\n"
             "  enumerate [OPTIONS] INDEX_PREFIX\n"
             "      --start                     Match PAM at start of kmer instead at end (default).\n"
             "      --max-off-targets INT=-1    Maximum number of off-targets to store for each number of mismatches.\n"
@@ -37,10 +38,11 @@ static void usage() {
 static std::string lower(std::string s) { std::transform(s.begin(), s.end(), s.begin(), ::tolower); return s; }
 
 static int do_index(int argc, char** argv) {
-    std::string fasta, prefix;
+    std::string fasta, prefix; bool reference_format = false;
     for (int i = 0; i < argc; i++) {
         std::string a = argv[i];
         if (a == "--index" && i + 1 < argc) prefix = argv[++i];
+        else if (a == "--reference-format") reference_format = true;
         else if (a.rfind("--index=", 0) == 0) prefix = a.substr(8);
         else fasta = a;
     }
@@ -49,6 +51,11 @@ static int do_index(int argc, char** argv) {
     gsx_index* ix = nullptr;
     int rc = gsx_index_build(fasta.c_str(), prefix.c_str(), nullptr, 0, &ix);
     if (rc) { fprintf(stderr, "ERROR: %s\n", gsx_last_error()); return 1; }
+    if (reference_format) {
+        const auto t0 = std::chrono::steady_clock::now();
+        if (gsx_index_save_reference_format(ix, prefix.c_str())) { fprintf(stderr, "ERROR: %s\n", gsx_last_error()); gsx_index_close(ix); return 1; }
+        printf("Wrote %s.forward and %s.reverse in %.2f s.\n", prefix.c_str(), prefix.c_str(), std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+    }
     printf("Index construction complete.\n");
     gsx_index_close(ix);
     return 0;

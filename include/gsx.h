@@ -123,6 +123,11 @@ int gsx_index_build(const char* fasta_path, const char* save_prefix, const int* 
 int gsx_index_build_text(const uint8_t* text, uint64_t length, const char* const* chr_names, const uint64_t* chr_lengths,
                          uint32_t n_chr, uint32_t sa_shift, const char* save_prefix, const int* devices, int n_devices,
                          gsx_index** out);
+/* Writes the index in the reference's own format: <prefix>.forward / .reverse (sdsl csa_wt<wt_huff<>,64,8192>, byte for byte the
+ * files the reference's `guidescan index` stores, src/guidescan.cxx:167-175) and <prefix>.gs, so that an index
+ * built here in seconds can be opened by the unmodified reference and by anything else that reads GuideScan2 indices.  Host work
+ * only (all cores); needs SA samples at least every 64 rows (sa_shift <= 6). */
+int gsx_index_save_reference_format(const gsx_index*, const char* prefix);
 int gsx_index_close(gsx_index*);
 uint64_t    gsx_index_genome_length(const gsx_index*);
 uint32_t    gsx_index_n_chromosomes(const gsx_index*);

@@ -142,6 +142,19 @@ def _oracle_samples_at_full_size(gsx, ix, g, chroms, kmers):
     want = json.load(open(os.path.join(ROOT, "tests", "golden", "ref_index_3100mb_digests.json")))
     for name, arr in (("bwt.forward", b0), ("bwt.reverse", b1), ("sa64.forward", s0), ("sa64.reverse", s1)):
         assert hashlib.sha256(memoryview(np.ascontiguousarray(arr))).hexdigest() == want[name], "GPU-built index differs from the reference's: " + name
+    # ... and written in the reference's own format (gsx_index_save_reference_format) it is the reference's FILES, byte for byte: the hour of
+    # `guidescan index` replaced by the GPU build plus this export, for any tool that reads GuideScan2 indices
+    import time
+    with tempfile.TemporaryDirectory() as d:
+        t0 = time.time()
+        ix.save_reference_format(os.path.join(d, "ix"))
+        print("reference-format export of the 3.1 Gb index: %.1f s on %d cores" % (time.time() - t0, os.cpu_count()))
+        for ext in ("forward", "reverse", "gs"):
+            h = hashlib.sha256()
+            with open(os.path.join(d, "ix." + ext), "rb") as f:
+                for chunk in iter(lambda: f.read(1 << 24), b""):
+                    h.update(chunk)
+            assert h.hexdigest() == want["file." + ext], "exported index file differs from the reference's: " + ext
     oix = O.Index.from_bwt(b0, s0, b1, s1, chroms)
     del b0, b1
     cases = [("cfg2", 64, dict(mismatches=3), {}),

@@ -97,6 +97,30 @@ def main():
                            "output_equals_reference_sorted": ref_lines == port_lines,
                            "port_over_reference_speed": res["enumerate"]["search_seconds"] / (t2 - t1) if res.get("enumerate", {}).get("search_seconds") else None}
             json.dump(res, open(res_path, "w"), indent=1)
+    if a.stage in ("all", "rewrite"):
+        # the reference's own files through the product's parser (load_sdsl_strand) and back out through its writer of the reference
+        # format (gsx_sdsl_write.cpp): identical files; their sha256 go to tests/golden (the GPU-built index must hash the same)
+        import hashlib
+        tool = os.path.join(ROOT, "tests", "_build", "sdsl_write_check")
+        rw = {"cores": os.cpu_count()}
+        for strand in ("forward", "reverse"):
+            src, out = prefix + "." + strand, os.path.join(a.workdir, "rewritten." + strand)
+            p = subprocess.run([tool, "rewrite", src, out], capture_output=True, text=True)
+            if p.returncode:
+                sys.exit("rewrite failed: " + p.stderr[-400:])
+            h = [hashlib.sha256(), hashlib.sha256()]
+            for k, path in enumerate((src, out)):
+                with open(path, "rb") as f:
+                    for chunk in iter(lambda: f.read(1 << 24), b""):
+                        h[k].update(chunk)
+            rw[strand] = {**json.loads(p.stdout), "bytes": os.path.getsize(src), "sha256_reference_file": h[0].hexdigest(),
+                          "rewritten_file_identical": h[0].digest() == h[1].digest() and os.path.getsize(out) == os.path.getsize(src)}
+            os.remove(out)
+        rw["gs_sha256"] = hashlib.sha256(open(prefix + ".gs", "rb").read()).hexdigest()
+        out_path = os.path.join(ROOT, "profiles", "r02q_reference_format_3100mb.json")
+        json.dump({"what": "profiles/r02_reference_3100mb.json's index files (unmodified reference, 4 091 s) parsed by load_sdsl_strand and written back "
+                           "by save_sdsl_strand (tests/sdsl_write_check rewrite), one strand at a time, all cores", **rw}, open(out_path, "w"), indent=1)
+        res["rewrite"] = rw
     print(json.dumps(res))
 
 
