@@ -148,13 +148,17 @@ def _oracle_samples_at_full_size(gsx, ix, g, chroms, kmers):
     with tempfile.TemporaryDirectory() as d:
         t0 = time.time()
         ix.save_reference_format(os.path.join(d, "ix"))
-        print("reference-format export of the 3.1 Gb index: %.1f s on %d cores" % (time.time() - t0, os.cpu_count()))
+        took = time.time() - t0
         for ext in ("forward", "reverse", "gs"):
             h = hashlib.sha256()
             with open(os.path.join(d, "ix." + ext), "rb") as f:
                 for chunk in iter(lambda: f.read(1 << 24), b""):
                     h.update(chunk)
             assert h.hexdigest() == want["file." + ext], "exported index file differs from the reference's: " + ext
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)           # the measurement travels back with the session's other outputs
+        json.dump({"what": "gsx_index_save_reference_format of the GPU-built 3.1 Gb index (both strands + .gs), files hash to the reference's",
+                   "seconds": took, "host_cores": os.cpu_count(), "bytes": {e: os.path.getsize(os.path.join(d, "ix." + e)) for e in ("forward", "reverse", "gs")}},
+                  open(os.path.join(ROOT, "gpurun_out", "reference_format_export_3100mb.json"), "w"), indent=1)
     oix = O.Index.from_bwt(b0, s0, b1, s1, chroms)
     del b0, b1
     cases = [("cfg2", 64, dict(mismatches=3), {}),
