@@ -15,6 +15,7 @@
 #include <stdexcept>
 #include <string>
 #include <thread>
+#include <sys/stat.h>
 #include <vector>
 
 using namespace gsx;
@@ -203,6 +204,11 @@ static void free_device_index(DeviceIndex& di) {
 }
 
 static bool file_exists(const std::string& p) { FILE* f = fopen(p.c_str(), "rb"); if (!f) return false; fclose(f); return true; }
+static bool file_newer(const std::string& a, const std::string& b) {      // a modified strictly after b
+    struct stat sa, sb;
+    if (stat(a.c_str(), &sa) != 0 || stat(b.c_str(), &sb) != 0) return false;
+    return sa.st_mtim.tv_sec != sb.st_mtim.tv_sec ? sa.st_mtim.tv_sec > sb.st_mtim.tv_sec : sa.st_mtim.tv_nsec > sb.st_mtim.tv_nsec;
+}
 
 static int check_devices(const int* devices, int n_devices) {
     int have = gsx_device_count();
@@ -232,7 +238,8 @@ extern "C" int gsx_index_open(const char* prefix, const int* devices, int n_devi
     if (!prefix || !out) return fail(GSX_ERR_ARG, "null argument");
     *out = nullptr;
     std::string p(prefix);
-    const bool sdsl = file_exists(p + ".forward") || !file_exists(p + ".gsx");
+    // both formats at one prefix (`guidescan index --reference-format`): the newer one; <prefix>.gsx needs no conversion
+    const bool sdsl = !file_exists(p + ".gsx") || (file_exists(p + ".forward") && file_newer(p + ".forward", p + ".gsx"));
     if (!sdsl || (file_exists(p + ".gs") && file_exists(p + ".forward") && file_exists(p + ".reverse")))
         if (int rc = check_devices(devices, n_devices)) return rc;           // (before reading gigabytes; missing files are reported first, as the reference does)
     gsx_index* ix = new gsx_index();

@@ -64,7 +64,7 @@ void StrandBuilder::finish() {
 // ---- sdsl file reader ------------------------------------------------------------------------------------
 namespace {
 struct Reader {
-    FILE* f = nullptr; std::string err;
+    FILE* f = nullptr; std::string err; uint64_t file_bytes = 0;
     bool u64(uint64_t& v) { return fread(&v, 8, 1, f) == 1; }
     bool u8(uint8_t& v) { return fread(&v, 1, 1, f) == 1; }
     // int_vector<w>: u64 size in bits, [u8 width if w == 0], ceil(bits/64) words  (sdsl int_vector.hpp:593-609,1563-1595)
@@ -73,6 +73,9 @@ struct Reader {
         width = (uint8_t)w;
         if (w == 0 && !u8(width)) return false;
         uint64_t words = (bits + 63) / 64;
+        // (a vector longer than what is left of the file is a corrupt or truncated file, not an allocation request)
+        const off_t at = ftello(f);
+        if (at < 0 || (uint64_t)at > file_bytes || words > (file_bytes - (uint64_t)at) / 8) return false;
         if (data) { data->resize(words); return words == 0 || fread(data->data(), 8, words, f) == words; }
         return fseeko(f, (off_t)(words * 8), SEEK_CUR) == 0;
     }
@@ -94,6 +97,8 @@ struct WtNode { uint64_t bv_pos, bv_pos_rank; uint16_t parent, child[2]; };
 bool load_sdsl_strand(const std::string& path, HostStrand& out, std::string& err) {
     Reader r; r.f = fopen(path.c_str(), "rb");
     if (!r.f) { err = "cannot open " + path; return false; }
+    if (fseeko(r.f, 0, SEEK_END) == 0) { const off_t e = ftello(r.f); r.file_bytes = e > 0 ? (uint64_t)e : 0; }
+    fseeko(r.f, 0, SEEK_SET);
     auto fail = [&](const char* what) { err = std::string("malformed index file ") + path + " (" + what + ")"; fclose(r.f); return false; };
     uint64_t size, sigma, bits; uint8_t w;
     if (!r.u64(size) || !r.u64(sigma)) return fail("header");

@@ -4,6 +4,8 @@
 #include "../../include/gsx.h"
 #include <algorithm>
 #include <chrono>
+#include <fcntl.h>
+#include <sys/stat.h>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -54,6 +56,7 @@ static int do_index(int argc, char** argv) {
     if (reference_format) {
         const auto t0 = std::chrono::steady_clock::now();
         if (gsx_index_save_reference_format(ix, prefix.c_str())) { fprintf(stderr, "ERROR: %s\n", gsx_last_error()); gsx_index_close(ix); return 1; }
+        utimensat(AT_FDCWD, (prefix + ".gsx").c_str(), nullptr, 0);     // gsx_index_open takes the newer format: keep that the one without conversion
         printf("Wrote %s.forward and %s.reverse in %.2f s.\n", prefix.c_str(), prefix.c_str(), std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
     }
     printf("Index construction complete.\n");

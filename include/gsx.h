@@ -109,7 +109,8 @@ typedef struct {
 
 /* ---- index ------------------------------------------------------------------------------------------- */
 /* Opens <prefix>.forward / .reverse / .gs written by the reference's `guidescan index` (sdsl csa_wt<wt_huff<>,64,8192>;
- * layout: SURVEY.md App. B) or <prefix>.gsx / .gs written by gsx_index_build, lays the index out on the first of `devices`
+ * layout: SURVEY.md App. B) or <prefix>.gsx / .gs written by gsx_index_build (both present: the more recently written), lays the
+ * index out on the first of `devices`
  * (NULL / 0 => device 0; the derived arrays -- jump table, look-ahead lines, pattern summaries -- are computed there) and copies the
  * finished arrays to every further device, peer to peer.  A device named twice gives two job slots over one copy.
  * Replaces sdsl::load_from_file + genome_index construction, src/guidescan.cxx:186-211. */

@@ -58,6 +58,22 @@ def test_reference_index_files_survive_parse_and_rewrite_unchanged(tool, golden_
         assert _same(src, out), (case, strand)
 
 
+def test_truncated_or_scrambled_reference_files_are_refused(tool, golden_index, tmp_path):
+    src = golden_index["g200k"] + ".forward"
+    data = open(src, "rb").read()
+    bad = os.path.join(tmp_path, "bad")
+    for cut in (8, 100, 4096, int(len(data) * 0.3), int(len(data) * 0.6), int(len(data) * 0.8)):
+        open(bad, "wb").write(data[:cut])
+        r = subprocess.run([tool, "rewrite", bad, os.path.join(tmp_path, "out")], capture_output=True, text=True)
+        assert r.returncode == 1 and ("malformed index file" in r.stderr or "too few SA samples" in r.stderr), (cut, r.stderr)
+    # a size field that asks for more than the file holds
+    broken = bytearray(data)
+    broken[16:24] = (1 << 50).to_bytes(8, "little")
+    open(bad, "wb").write(bytes(broken))
+    r = subprocess.run([tool, "rewrite", bad, os.path.join(tmp_path, "out")], capture_output=True, text=True)
+    assert r.returncode == 1 and "malformed index file" in r.stderr
+
+
 def _bit_vector_cases():
     rng = np.random.default_rng(11)
     cases = []
@@ -171,8 +187,18 @@ def test_unmodified_reference_enumerates_over_an_index_written_by_the_cli(golden
     out = os.path.join(tmp_path, "ref.out")
     O.ref_enumerate(prefix, guides, out, mismatches=3)
     assert open(out, "rb").read() == golden_output("g150kN", "m3_csv")
-    # and the product opens its own reference-format files like the reference's
+    # both formats at the prefix: gsx_index_open takes the more recently written one (the CLI leaves that to be <prefix>.gsx)
     import gsx
+    import shutil
+    good = open(prefix + ".forward", "rb").read()
+    open(prefix + ".forward", "wb").write(good[:4096])                      # not an index any more ...
+    os.utime(prefix + ".forward", ns=(0, os.stat(prefix + ".gsx").st_mtime_ns - 10**9))   # ... but older than <prefix>.gsx: not looked at
+    gsx.Index.open(prefix).close()
+    os.utime(prefix + ".forward")                                          # newer: looked at, and refused
+    with pytest.raises(gsx.GsxError, match="malformed index file"):
+        gsx.Index.open(prefix)
+    open(prefix + ".forward", "wb").write(good)
+    # and the product opens its own reference-format files like the reference's
     os.remove(prefix + ".gsx")
     ix = gsx.Index.open(prefix)
     res = ix.enumerate_file(guides, os.path.join(tmp_path, "gpu.out"), gsx.make_params(mismatches=3))

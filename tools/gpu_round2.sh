@@ -57,6 +57,9 @@ PY
       # (only the kernels of the enumerate path are profiled: the index build in front of them is a thousand radix-sort launches)
       timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none -k "regex:sweep_lean|sweep_kernel|sweep_guides|search_fast|search_kernel|scan_u32|scatter_matches|order_matches|expand_hits|locate_score|specificity|publish|total_u32|variant_|threshold" -c 400 --csv --log-file gpurun_out/${tag}_bench_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-file-e2e > gpurun_out/${tag}_bench_launches.log 2>&1
       tail -2 gpurun_out/${tag}_bench_launches.log | cut -c1-300; shift;;
+    refformat)     # refformat <genome Mb>: tools/ref_format_roundtrip.py (GPU build -> reference-format files -> product and unmodified reference open them)
+      timeout 1200 python tools/ref_format_roundtrip.py --genome-mb $2 --out gpurun_out/${tag}_reference_format_roundtrip_$2mb.json > gpurun_out/${tag}_refformat_$2.log 2> gpurun_out/${tag}_refformat_$2.err || tail -5 gpurun_out/${tag}_refformat_$2.err
+      cut -c1-1500 gpurun_out/${tag}_refformat_$2.log; shift 2;;
     bench)
       shift
       timeout 1200 python bench.py "$@" > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; tail -3 gpurun_out/${tag}_bench.err; cut -c1-1200 gpurun_out/${tag}_bench.json
