@@ -224,53 +224,93 @@ struct SelectDir {
     Packed superblock; std::vector<uint8_t> is_mini; std::vector<uint8_t> blocks;      // serialized blocks, in order
 };
 
-SelectDir build_select(const std::vector<uint64_t>& bv, uint64_t n_bits, bool ones) {
+// The blocks are independent of each other but for one look at the first arg of the next block, so ranges of blocks are built by
+// one thread each: a range starts at the word that holds its first arg, found through the arg counts of the 512-bit chunks.
+SelectDir build_select(const std::vector<uint64_t>& bv, uint64_t n_bits, bool ones, unsigned threads) {
     SelectDir d;
     const uint64_t capacity = bv.size() * 64;
-    uint64_t n_ones = 0; for (uint64_t x : bv) n_ones += (uint64_t)__builtin_popcountll(x);
+    const bool fast = n_bits >= 100000;
+    const uint64_t view_bits = fast ? capacity : n_bits;            // where the args are looked for
+    auto args_of = [&](uint64_t w) {                                // the args of word w as set bits
+        uint64_t x = ones ? bv[w] : ~bv[w];
+        if ((w + 1) * 64 > view_bits) { const uint64_t keep = view_bits - w * 64; x &= keep ? (~0ull >> (64 - keep)) : 0ull; }
+        return x;
+    };
+    std::vector<uint64_t> before(bv.size() / 8 + 2, 0);             // args (word view) before each chunk of 8 words
+    uint64_t n_ones = 0;
+    for (uint64_t w = 0; w < bv.size(); w++) {
+        if ((w & 7) == 0) before[w / 8 + 1] = before[w / 8];
+        before[w / 8 + 1] += (uint64_t)__builtin_popcountll(args_of(w)); n_ones += (uint64_t)__builtin_popcountll(bv[w]);
+    }
+    const uint64_t n_view = before[(bv.size() + 7) / 8];            // args in the word view (phantoms included)
     d.n_args = ones ? n_ones : n_bits - n_ones;
     if (!d.n_args) return d;
     d.n_sb = (d.n_args + 4095) >> 12;
     const uint32_t logn = top_bit(capacity) + 1; const uint64_t logn4 = (uint64_t)logn * logn * logn * logn;
     d.superblock = Packed(d.n_sb, logn);
     d.is_mini.assign(d.n_sb, 0);
-    const bool fast = n_bits >= 100000;
-    std::vector<uint64_t> P(4097); uint64_t have = 0, k = 0;
-    auto store = [&](const Packed& v, bool mini) { if (mini) d.is_mini[k] = 1; else d.any_long = true; v.append_to(d.blocks); };
-    // `have` args buffered, at most 4096 of them belong to block k, P[4096] (if present) is the first of the next block
-    auto close_block = [&]() {
-        const uint64_t c = std::min<uint64_t>(have, 4096);
-        if (k >= d.n_sb) { d.any_long = true; return; }
-        if (!fast) {
-            const uint64_t first = P[0], last = P[c - 1], span = last - first;
-            d.superblock.set(k, first);
-            if (span > logn4) { Packed v(4096, top_bit(last) + 1); for (uint64_t j = 0; j < c; j++) v.set(j, P[j]); store(v, false); }
-            else { Packed v(64, top_bit(span) + 1); for (uint64_t j = 0; j < c; j += 64) v.set(j / 64, P[j] - first); store(v, true); }
-            return;
+    const uint64_t n_view_blocks = (n_view + 4095) >> 12;
+    const unsigned T = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(threads ? threads : 1, n_view_blocks / 4 + 1));
+    struct Part { std::vector<uint64_t> first; std::vector<uint8_t> is_mini, blocks; bool any_long = false; };
+    std::vector<Part> parts(T);
+    auto build = [&](unsigned t) {
+        Part& part = parts[t];
+        const uint64_t k0 = n_view_blocks * t / T, k1 = n_view_blocks * (t + 1) / T;
+        if (k0 == k1) return;
+        std::vector<uint64_t> P(4097); uint64_t have = 0, k = k0;
+        auto store = [&](const Packed& v, bool mini, uint64_t first) {
+            part.first.push_back(first); part.is_mini.push_back(mini ? 1 : 0); if (!mini) part.any_long = true; v.append_to(part.blocks);
+        };
+        // `have` args buffered, at most 4096 of them belong to block k, P[4096] (if present) is the first of the next block
+        auto close_block = [&]() {
+            const uint64_t c = std::min<uint64_t>(have, 4096);
+            if (k >= d.n_sb) { part.any_long = true; return; }
+            if (!fast) {
+                const uint64_t first = P[0], last = P[c - 1], span = last - first;
+                if (span > logn4) { Packed v(4096, top_bit(last) + 1); for (uint64_t j = 0; j < c; j++) v.set(j, P[j]); store(v, false, first); }
+                else { Packed v(64, top_bit(span) + 1); for (uint64_t j = 0; j < c; j += 64) v.set(j / 64, P[j] - first); store(v, true, first); }
+                return;
+            }
+            if (c >= 4033) {
+                const uint64_t first = P[0]; uint64_t last = P[4032];
+                for (uint64_t j = have - 1; j > 4032; j--) if (P[j] < n_bits) { last = P[j]; break; }
+                const uint64_t span = last - first;
+                if (span > logn4) { Packed v(4096, top_bit(last) + 1); for (uint64_t j = 0; j < c && P[j] <= last; j++) v.set(j, P[j]); store(v, false, first); }
+                else { Packed v(64, top_bit(span) + 1); for (uint64_t j = 0; j < 4096; j += 64) v.set(j / 64, P[j] - first); store(v, true, first); }
+            } else {
+                Packed v(4096, top_bit(n_bits - 1) + 1);
+                for (uint64_t j = 0; j < c && P[j] < n_bits; j++) v.set(j, P[j]);
+                store(v, false, 0);                                 // (superblock[k] stays 0)
+            }
+        };
+        // the word of arg number 4096 k0 (counted from 0), and how many args of that word belong to the block before
+        const uint64_t a0 = k0 << 12;
+        uint64_t chunk = (uint64_t)(std::upper_bound(before.begin(), before.begin() + (long)((bv.size() + 7) / 8 + 1), a0) - before.begin()) - 1;
+        uint64_t w = chunk * 8, seen = before[chunk];
+        for (;; w++) { const uint64_t c = (uint64_t)__builtin_popcountll(args_of(w)); if (seen + c > a0) break; seen += c; }
+        uint64_t skip = a0 - seen;
+        for (; w < bv.size() && k < k1; w++) {
+            uint64_t x = args_of(w);
+            for (; skip && x; skip--) x &= x - 1;
+            while (x && k < k1) {
+                P[have++] = w * 64 + (uint64_t)__builtin_ctzll(x); x &= x - 1;
+                if (have == 4097) { close_block(); k++; P[0] = P[4096]; have = 1; }
+            }
         }
-        if (c >= 4033) {
-            const uint64_t first = P[0]; uint64_t last = P[4032];
-            for (uint64_t j = have - 1; j > 4032; j--) if (P[j] < n_bits) { last = P[j]; break; }
-            const uint64_t span = last - first;
-            d.superblock.set(k, first);
-            if (span > logn4) { Packed v(4096, top_bit(last) + 1); for (uint64_t j = 0; j < c && P[j] <= last; j++) v.set(j, P[j]); store(v, false); }
-            else { Packed v(64, top_bit(span) + 1); for (uint64_t j = 0; j < 4096; j += 64) v.set(j / 64, P[j] - first); store(v, true); }
-        } else {
-            Packed v(4096, top_bit(n_bits - 1) + 1);
-            for (uint64_t j = 0; j < c && P[j] < n_bits; j++) v.set(j, P[j]);
-            store(v, false);
-        }
+        if (k < k1 && have) { close_block(); k++; }                  // the end of the vector (last range only)
     };
-    const uint64_t view_bits = fast ? capacity : n_bits;            // where the args are looked for
-    for (uint64_t w = 0; w < bv.size(); w++) {
-        uint64_t x = ones ? bv[w] : ~bv[w];
-        if ((w + 1) * 64 > view_bits) { const uint64_t keep = view_bits - w * 64; x &= keep ? (~0ull >> (64 - keep)) : 0ull; }
-        while (x) {
-            P[have++] = w * 64 + (uint64_t)__builtin_ctzll(x); x &= x - 1;
-            if (have == 4097) { close_block(); k++; P[0] = P[4096]; have = 1; }
-        }
+    {
+        std::vector<std::thread> pool;
+        for (unsigned t = 1; t < T; t++) pool.emplace_back(build, t);
+        build(0);
+        for (auto& th : pool) th.join();
     }
-    if (have) { close_block(); k++; }
+    uint64_t k = 0;
+    for (const Part& part : parts) {
+        d.any_long = d.any_long || part.any_long;
+        for (size_t i = 0; i < part.first.size(); i++, k++) { d.superblock.set(k, part.first[i]); d.is_mini[k] = part.is_mini[i]; }
+        d.blocks.insert(d.blocks.end(), part.blocks.begin(), part.blocks.end());
+    }
     return d;
 }
 
@@ -361,8 +401,8 @@ bool sdsl_write_bit_vector_supports(const std::string& path, const std::vector<u
     Sink s; s.f = fopen(path.c_str(), "wb");
     if (!s.f) { err = "cannot write " + path; return false; }
     put_rank_directory(s, words);
-    put_select(s, build_select(words, n_bits, true));
-    put_select(s, build_select(words, n_bits, false));
+    put_select(s, build_select(words, n_bits, true, 3));
+    put_select(s, build_select(words, n_bits, false, 3));
     const bool ok = s.ok; fclose(s.f);
     if (!ok) err = "short write to " + path;
     return ok;
@@ -382,8 +422,8 @@ static bool put_wavelet_tree(Sink& s, const HostStrand& h, const uint64_t count[
     lap("bits + rank directory out");
     SelectDir sel1, sel0;
     {
-        std::thread other([&] { sel0 = build_select(bv, t.bv_bits, false); });
-        sel1 = build_select(bv, t.bv_bits, true);
+        std::thread other([&] { sel0 = build_select(bv, t.bv_bits, false, (threads + 1) / 2); });
+        sel1 = build_select(bv, t.bv_bits, true, (threads + 1) / 2);
         other.join();
     }
     lap("select directories");
