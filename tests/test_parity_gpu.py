@@ -494,26 +494,6 @@ def test_lean_sweep_kernel_on_edited_guides(gsx, gpu_index, tmp_path, monkeypatc
     assert open(out).read() == slice_of(golden_output("g200k", variant).decode(), kw.get("fmt") == "sam")
 
 
-@pytest.mark.parametrize("variant", [v for v in BULGE_GOLDEN if "r2" not in v])
-@pytest.mark.parametrize("mates,sweep", [("1", "11"), ("2", "11"), ("3", "12"), ("4", "10"), ("4", "12")])
-def test_edited_guides_sharing_sector_loads(gsx, gpu_index, tmp_path, monkeypatch, variant, mates, sweep):
-    """sweep_lean_kernel<..., FORCED>: up to GSX_SWEEP_MATES edited forms of a guide with the same table index run together, one sector
-    load judged with every member's masks (lean_run_shared), and the flat list of the budget-1 guides runs pattern by pattern; same
-    text whatever the group size and the occupancy variant, and fewer sectors requested than without sharing"""
-    monkeypatch.setenv("GSX_SWEEP_MIN", "1")
-    kw = golden_manifest()["cases"]["g200k"]["variants"][variant]["opts"]
-    gcsv, slice_of = _ngg_subset(tmp_path)
-    ctrs = {}
-    for m, sv in ((mates, sweep), ("1", "11")):
-        monkeypatch.setenv("GSX_SWEEP_MATES", m); monkeypatch.setenv("GSX_SWEEP_VARIANT", sv)
-        out = os.path.join(tmp_path, "g%s.out" % m)
-        _, ctrs[m] = gpu_index("g200k").enumerate_file(gcsv, out, _params(gsx, kw), fmt=kw.get("fmt", "csv"), mode=kw.get("mode", "complete"))
-        assert open(out).read() == slice_of(golden_output("g200k", variant).decode(), kw.get("fmt") == "sam")
-    assert ctrs[mates]["edited_guides"] > 0 and ctrs[mates]["seeds"] == ctrs["1"]["seeds"]
-    if mates != "1":
-        assert ctrs[mates]["sectors"] < ctrs["1"]["sectors"]
-
-
 @pytest.mark.parametrize("case,variant", [(c, v) for c, v in golden_cases() if v in ("m4_max1_sam", "m4_max2_csv", "m3_csv", "m2_sam", "m1_r1_d1_altNAG_max3_csv",
                                                                                       "m1_r1_d1_sam_succinct", "m3_thr1_csv", "m0_r1_d1_csv")])
 def test_warp_per_guide_specificity(gsx, gpu_index, golden_dir, tmp_path, monkeypatch, case, variant):
