@@ -791,7 +791,7 @@ static void run_device_job(DeviceJob* job) {
                 if (!d_queue) d_queue = B.alloc<SeedNode>(queue_cap);
                 w.st[0] = m.st[0]; w.st[1] = m.st[1]; w.gq = m.gq; w.skip = m.skip; w.n_guides = ng; w.xtab = d_xtab; w.n_xtab = n_xtab;
                 w.M = m.p.M; w.plen = m.plen; w.pampack = m.pampack; w.load_mode = (uint32_t)env_int("GSX_SWEEP_LOAD", 2);
-                w.mates = (uint32_t)env_int("GSX_SWEEP_MATES", 4);                 // edited guides of one run that share its sectors (sweep_lean_kernel<..., FORCED>)
+                w.parts = 1;                                                       // measured: cutting the units does not pay (profiles/r01r_*)
                 w.queue = d_queue; w.queue_cap = (uint32_t)queue_cap; w.queue_count = d_ctrs + 3; w.item_counter = d_ctrs + 4;
                 w.error_flag = d_ctrs + 2; w.stats = d_stats; w.fmask = m.fmask;
                 if (gtab_cap < ng) { if (d_gtab) B.free_one(d_gtab); d_gtab = B.alloc<uint32_t>((size_t)ng * 20); gtab_cap = ng; }

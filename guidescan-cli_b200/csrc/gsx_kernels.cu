@@ -1110,8 +1110,6 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) sweep_kernel(SweepArgs a) {
 // Same seeds, same counters as sweep_kernel (the tests run both).
 // ---------------------------------------------------------------------------------------------------------
 constexpr int PK_SLOTS = 96;           // parked nodes per warp: drained below 32 at the top of an iteration, which adds at most 64
-constexpr int PK_SLOTS_SHARED = 160;   // ... and at most 4 x 32 where up to four edited guides share the sectors of a run (lean_run_shared)
-constexpr int LEAN_MATES = 4;          // edited guides per shared run
 
 // predicated 32-byte summary load (L2 only): lanes without a pattern keep w = 0, i.e. an empty node.  (Letting those lanes load table
 // entry 0 instead -- no predicate, no zeroing, nine instructions fewer per load -- was measured and lost 1-2 %: the idle lanes' extra
@@ -1289,58 +1287,13 @@ __device__ __forceinline__ void lean_run(const SweepArgs& a, const SweepPlan& pl
     lean_budget_pass<PROTO, PAM, NB, FORCED>(a, pk, xtab + pl.xoff[0][B], pl.xcnt[0][B], pl.xlines[0][B], lane, r, B, st);
 }
 
-// Edited guides (bulges): many of the forms of one guide differ only behind the characters of the table index -- same index
-// for every pattern, same must-match mask, same budget in this slice -- and sit next to each other in the batch.  Up to
-// LEAN_MATES of them run together: each sector is loaded once and judged with every member's masks (kept in shared memory,
-// read as broadcasts), each member emitting and parking under its own task.  r carries what the members share; 32 patterns
-// per iteration.  For the forms of a guide with one RNA and one DNA bulge this more than halves the sectors requested.
-template <int SHAPE, int NB>
-__device__ __forceinline__ void lean_run_shared(const SweepArgs& a, const SweepPlan& pl, ParkBuf& pk, const uint32_t* xtab, uint32_t lane, const LeanRun& r,
-                                                const uint32_t (*mates)[9], uint32_t n_mates, uint32_t B, LeanStats& st) {
-    constexpr uint32_t PROTO = SHAPE == 0 ? 0x3Fu : SHAPE == 1 ? 0x7Fu : 0x1Fu, PAM = SHAPE == 2 ? 0x40u : 0u;
-#pragma unroll 1
-    for (int pass = 1; pass >= 0; pass--) {                                  // 1: exactly B substitutions (no budget left), 0: fewer
-        const uint32_t* xt = xtab + pl.xoff[pass][B]; const uint32_t n = pl.xcnt[pass][B];
-        for (uint32_t base = 0; base < n; base += 32u) {
-            while (pk.count >= 32u) lean_drain<NB>(a, pk, lane, st);
-            const uint32_t t = base + lane;
-            const uint32_t xw = xt[t];
-            const bool live = t < n && !(xw & r.fm);
-            st.sectors += __popc(__ballot_sync(0xffffffffu, live)); st.lines += __popc(__ballot_sync(0xffffffffu, live && (xw & 15u) == 0u));
-            const uint32_t idx = r.qh ^ (xw & 0x0FFFFFFFu), budget = pass ? 0u : B - (xw >> 28);
-            uint32_t w[8];
-            lean_load(r.sum0, idx, live, w);
-#pragma unroll 1
-            for (uint32_t m = 0; m < n_mates; m++) {
-                uint32_t X[7];
-#pragma unroll
-                for (int k = 0; k < 7; k++) X[k] = mates[m][k];
-                const uint32_t codes2 = mates[m][7], tl = mates[m][8];
-                const bool tail = r.sum2 != nullptr && sweep_has_tail(codes2) && !(w[0] & SUM_WIDE32);
-                uint32_t alive;
-                if (pass) {
-                    alive = summary_exact_shape<PROTO | PAM>(w, X);
-                    if (alive && tail) { uint32_t tt[4], v[1] = {alive}; load_tail(r.sum2, idx, tt); summary_tail<1>(tt, 0u, codes2, v); alive = v[0]; }
-                } else {
-                    uint32_t u[NB];
-                    summary_masks_shape<PROTO, PAM, NB>(w, X, budget, u);
-                    if (u[0] && tail) { uint32_t tt[4]; load_tail(r.sum2, idx, tt); summary_tail<NB>(tt, 0u, codes2, u); }
-                    alive = u[0];
-                }
-                lean_settle(a, pk, lane, w[0], alive, idx, budget, tl, r.tab, st);
-            }
-        }
-    }
-}
-
 // XTG: the xor table is too long for shared memory (4 mismatches: 15.8 k words) and is read from global memory (unit stride,
 // the same few KB by every warp: L1 hits); the host pads it with 64 readable words
 template <int WARPS, int MINB, int NB, bool FORCED = false, bool XTG = false>
 __global__ void __launch_bounds__(WARPS * 32, MINB) sweep_lean_kernel(SweepArgs a) {
     __shared__ SweepPlan s_plan;
-    __shared__ uint32_t s_park[WARPS][2][FORCED ? PK_SLOTS_SHARED : PK_SLOTS];
+    __shared__ uint32_t s_park[WARPS][2][PK_SLOTS];
     __shared__ uint32_t s_rank[WARPS][32];
-    __shared__ uint32_t s_mates[FORCED ? WARPS : 1][LEAN_MATES][9];              // per member of a shared run: X[7], codes2, task
     __shared__ uint32_t s_xtab_[XTG ? 1 : XT_SMEM];
     for (int i = threadIdx.x; i < (int)(sizeof(SweepPlan) / 4); i += blockDim.x)
         reinterpret_cast<uint32_t*>(&s_plan)[i] = reinterpret_cast<const uint32_t*>(&a.plan)[i];
@@ -1350,7 +1303,6 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) sweep_lean_kernel(SweepArgs 
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, FULL = 0xffffffffu;
     ParkBuf pk; pk.idx = s_park[warp][0]; pk.tl = s_park[warp][1]; pk.count = 0;
     const uint32_t L = s_plan.L, sb = s_plan.sb, M = a.M;
-    const uint32_t max_mates = FORCED ? (a.mates < 1u ? 1u : a.mates > (uint32_t)LEAN_MATES ? (uint32_t)LEAN_MATES : a.mates) : 1u;
     const uint32_t np1 = s_plan.xcnt[1][1], np1_magic = np1 ? 0xFFFFFFFFu / np1 + 1u : 0u;      // f / np1 = umulhi(f, magic) for the small f used here
     const uint32_t n_slices = 1u << (2u * sb), n_gb = (a.n_guides + 31u) >> 5;
     const uint32_t items_per_strand = n_slices * n_gb, n_items = 2u * items_per_strand;      // (the host keeps this below 2^32)
@@ -1413,19 +1365,13 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) sweep_lean_kernel(SweepArgs 
             if (todo1 && np1) {
                 if (B == 1) s_rank[warp][__popc(todo1 & ((1u << lane) - 1u))] = lane;
                 __syncwarp();
-                const uint32_t n1 = (uint32_t)__popc(todo1), total = n1 * np1;
+                const uint32_t total = (uint32_t)__popc(todo1) * np1;
                 const uint32_t* xt1 = s_xtab + s_plan.xoff[1][1];
-                // FORCED (edited guides): the list runs pattern by pattern over the guides instead of guide by guide over the patterns,
-                // so that neighbouring forms of one guide -- same index for the same pattern -- ask for their sector in the same load
-                const bool by_pattern = FORCED && max_mates >= 2u && n1 >= 2u;     // (one guide: nothing to share, and the magic number needs a divisor above 1)
-                const uint32_t n1_magic = by_pattern ? 0xFFFFFFFFu / n1 + 1u : 0u;
                 for (uint32_t f0 = 0; f0 < total; f0 += 32u) {
                     while (pk.count >= 32u) lean_drain<NB>(a, pk, lane, st);
                     const uint32_t f = f0 + lane;
                     bool live = f < total;
-                    uint32_t k, t;
-                    if (by_pattern) { t = live ? __umulhi(f, n1_magic) : 0u; k = live ? f - t * n1 : 0u; }
-                    else { k = live ? __umulhi(f, np1_magic) : 0u; t = live ? f - k * np1 : 0u; }
+                    const uint32_t k = live ? __umulhi(f, np1_magic) : 0u, t = live ? f - k * np1 : 0u;
                     const uint32_t go = gb * 32u + s_rank[warp][k];
                     const uint32_t* row = a.gtab + (size_t)go * GT_WORDS;
                     const uint32_t xw = xt1[t];
@@ -1441,45 +1387,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) sweep_lean_kernel(SweepArgs 
         }
         // (3) guides with more budget left after the slice characters, one at a time, all lanes on that guide's patterns
         uint32_t todo = __ballot_sync(FULL, B >= 2);
-        uint32_t same = 1u << lane;                                          // FORCED: the lanes whose guide can share this lane's sectors
-        if constexpr (FORCED) {
-            if (B >= 2 && max_mates >= 2u) {
-                const uint32_t* row = a.gtab + (size_t)g * GT_WORDS;
-                const uint32_t low = (1u << (2u * (L - sb))) - 1u;              // (the patterns only touch these index bits)
-                const uint32_t k1 = __ldg(row + GT_QLOW), k2 = (__ldg(row + GT_FMASK) & low & 0x0FFFFFFFu) | (__ldg(row + GT_SHAPE) << 28) | ((uint32_t)(B - 2) << 30);
-                same = __match_any_sync(todo, k1) & __match_any_sync(todo, k2);
-            }
-        }
         while (todo) {
-            const uint32_t o = (uint32_t)__ffs(todo) - 1u;
-            if constexpr (FORCED) {
-                uint32_t grp = __shfl_sync(FULL, same, o) & todo, mem = 0, n_mates = 0;
-                while (grp && n_mates < max_mates) { mem |= grp & (0u - grp); grp &= grp - 1u; n_mates++; }
-                todo &= ~mem;
-                if (n_mates >= 2u) {
-                    const uint32_t Bo = (uint32_t)__shfl_sync(FULL, B, o), go = gb * 32u + o;
-                    __syncwarp();
-                    {   // lane 8 j + k fetches word k of member j: X[0..6] = words 7..13 of its row, then codes2; lane j writes the task
-                        const uint32_t j = lane >> 3, k = lane & 7u;
-                        uint32_t mj = mem; for (uint32_t i = 0; i < j && mj; i++) mj &= mj - 1u;
-                        if (j < n_mates) {
-                            const uint32_t gl = gb * 32u + ((uint32_t)__ffs(mj) - 1u);
-                            s_mates[warp][j][k] = __ldg(a.gtab + (size_t)gl * GT_WORDS + (k < 7u ? 7u + k : (uint32_t)GT_CODES2));
-                            if (k == 0u) s_mates[warp][j][8] = (gl << 1) | strand;
-                        }
-                    }
-                    __syncwarp();
-                    const uint32_t* lrow = a.gtab + (size_t)go * GT_WORDS;
-                    LeanRun r;
-                    r.sum0 = sum0; r.sum1 = sum1; r.sum2 = sum2; r.tab = tab; r.qh = hi_bits | __ldg(lrow + GT_QLOW);
-                    r.codes2 = 0; r.fm = __ldg(lrow + GT_FMASK) & 0x0FFFFFFFu; r.tl = 0;
-                    const uint32_t shape = __ldg(lrow + GT_SHAPE);
-                    if (shape == 0u) lean_run_shared<0, NB>(a, s_plan, pk, s_xtab, lane, r, s_mates[warp], n_mates, Bo, st);
-                    else if (shape == 1u) lean_run_shared<1, NB>(a, s_plan, pk, s_xtab, lane, r, s_mates[warp], n_mates, Bo, st);
-                    else lean_run_shared<2, NB>(a, s_plan, pk, s_xtab, lane, r, s_mates[warp], n_mates, Bo, st);
-                    continue;
-                }
-            } else todo &= todo - 1u;
+            const uint32_t o = (uint32_t)__ffs(todo) - 1u; todo &= todo - 1u;
             const uint32_t Bo = (uint32_t)__shfl_sync(FULL, B, o), go = gb * 32u + o;
             const uint4* gp = reinterpret_cast<const uint4*>(a.gtab + (size_t)go * GT_WORDS);      // same address in every lane: one transaction
             const uint4 g1 = __ldg(gp + 1), g2 = __ldg(gp + 2), g3 = __ldg(gp + 3), g4 = __ldg(gp + 4);

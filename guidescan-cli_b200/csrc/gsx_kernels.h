@@ -67,7 +67,7 @@ struct SweepArgs {
     uint32_t n_xtab;
     uint32_t* gtab;                    // n_guides * 20 words: per-guide constants, written by launch_sweep_guides
     uint32_t M, plen, pampack;
-    uint32_t mates;                    // sweep_lean_kernel on edited guides: how many of them may share the sectors of a run (<= 4; 0, 1 = none)
+    uint32_t parts;                    // (unused: cutting the work units was measured and did not pay)
     uint32_t load_mode;                // cache policy of the summary loads: 0 ld.global.nc, 1 + L1::no_allocate, 2 ld.global.cg
     SeedNode* queue; uint32_t queue_cap;
     uint32_t* queue_count; uint32_t* item_counter; uint32_t* error_flag;
