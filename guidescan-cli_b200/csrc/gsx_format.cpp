@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <condition_variable>
 #include <deque>
@@ -60,6 +61,9 @@ inline GuideAt guide_at(const gsx_result* r, size_t g) {
     return {&P, gl, P.hoff[gl], P.n_hits_of[gl]};
 }
 
+struct Base5x4 { uint8_t d[625][4]; constexpr Base5x4() : d() { for (int v = 0; v < 625; v++) { int x = v; for (int j = 0; j < 4; j++) { d[v][j] = (uint8_t)(x % 5); x /= 5; } } } };
+static constexpr Base5x4 kBase5{};                                                          // the four base-5 digits of 0 .. 624, lowest first
+
 // match.sequence of hit hl (numbered within the part) of guide g, complemented as printed (= gsx_result_match_sequence,
 // printer.hpp:232,264), table-driven: the character selects of gsx_core.h decode_match mispredict on every other character on a host core
 inline size_t match_sequence_at(const gsx_result* r, const HostArrays& P, size_t g, uint64_t hl, char* out) {
@@ -75,18 +79,34 @@ inline size_t match_sequence_at(const gsx_result* r, const HostArrays& P, size_t
     }
     const GuideRec& gr = r->guides[g];
     const uint32_t qlen = gr.qlen;
-    uint64_t k = P.key_lo[hl];
-    for (uint32_t i = len; i-- > 0;) {
-        const uint32_t d = (uint32_t)(k % 5ull); k /= 5ull;
+    // base-5 digits, last character in the lowest digit: a chain of 27 dependent divisions by 5 is the slowest thing in a CSV row, so
+    // the key is cut in two halves that divide independently, four digits (a division by 625 and a table of their digits) at a time
+    uint8_t dg[32];
+    {
+        const uint64_t k = P.key_lo[hl];
+        uint64_t lo = k % 244140625ull, hi = k / 244140625ull;                               // 5^12: digits len-12 .. len-1 | the rest
+        for (int c = 0; c < 3; c++) {
+            const uint32_t a = (uint32_t)(lo % 625u), b = (uint32_t)(hi % 625u); lo /= 625u; hi /= 625u;
+            memcpy(dg + 4 * c, kBase5.d[a], 4); memcpy(dg + 12 + 4 * c, kBase5.d[b], 4);
+        }
+        memcpy(dg + 24, kBase5.d[hi % 625u], 4); memcpy(dg + 28, kBase5.d[(hi / 625u) % 625u], 4);      // (a narrow key has at most 27 digits)
+    }
+    for (uint32_t i = 0; i < len; i++) {                                                     // dg[j] = digit of character len - 1 - j
+        const uint32_t d = dg[len - 1u - i];
         const char proto = d ? LOWC[d] : UPC[gr.q[i < kMaxQ ? i : 0] & 7u];
         out[i] = i < qlen ? proto : PAMC[d];
     }
     return len;
 }
 
+// decimal digits, two at a time from a 200-byte table (positions have up to ten digits; this and the match string are what a CSV row costs)
+struct Digits2 { char d[200]; constexpr Digits2() : d() { for (int i = 0; i < 100; i++) { d[2 * i] = (char)('0' + i / 10); d[2 * i + 1] = (char)('0' + i % 10); } } };
+static constexpr Digits2 kDigits2{};
 inline char* put_u64_at(char* w, uint64_t v) {
+    if (v < 10) { *w = (char)('0' + v); return w + 1; }
     char t[24]; int n = 24;
-    do { t[--n] = (char)('0' + v % 10); v /= 10; } while (v);
+    while (v >= 100) { const uint64_t q = v / 100; const uint32_t r = (uint32_t)(v - q * 100); v = q; n -= 2; memcpy(t + n, kDigits2.d + 2 * r, 2); }
+    if (v >= 10) { n -= 2; memcpy(t + n, kDigits2.d + 2 * v, 2); } else t[--n] = (char)('0' + v);
     memcpy(w, t + n, 24 - n); return w + (24 - n);
 }
 
@@ -470,6 +490,22 @@ extern "C" int gsx_internal_write_parts(const char* path, const char* const* par
     bool ok = true;
     for (size_t r = 0; r < rounds && ok; r++) ok = out.append(v);
     return out.close_file() && ok ? GSX_OK : GSX_ERR_IO;
+}
+
+// test hook (not part of the ABI): the formatter alone, as the whole-file driver runs it -- `rounds` passes over the rows of a result
+// into pooled buffers, nothing concatenated or written; seconds and bytes of the last pass
+extern "C" int gsx_internal_format_rate(const gsx_index* ix, const gsx_result* r, const gsx_guide_row* rows, size_t n, const gsx_params* p,
+                                        int format_sam, int complete, size_t rounds, double* seconds, size_t* bytes) {
+    if (!ix || !r || !rows || !p || !seconds || !bytes) return GSX_ERR_ARG;
+    for (size_t k = 0; k < rounds; k++) {
+        std::vector<std::string> parts;
+        const auto t0 = std::chrono::steady_clock::now();
+        format_rows_parts(ix, r, rows, 0, n, p, format_sam, complete, parts);
+        *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        *bytes = 0; for (auto& x : parts) *bytes += x.size();
+        for (std::string& x : parts) string_pool().put(std::move(x));
+    }
+    return GSX_OK;
 }
 
 // Whole-file driver.  Four things overlap: the GPU enumerates batch k+1 while the host packs the guides of batch k+2 (two-slot
