@@ -52,6 +52,7 @@ def main():
     ap.add_argument("--kmers-mb", type=float, default=32, help="guides are generated from the first this-many Mb of chromosome 1")
     ap.add_argument("--check-guides", type=int, default=200)
     ap.add_argument("--csv-guides", type=int, default=1000000, help="configs[2] leg: guides through the binary on 1 and on N GPUs (0 = skip)")
+    ap.add_argument("--file-batch", type=int, default=50000, help="guides per device and batch of the whole-file driver (0 = the library's default, 200 000)")
     ap.add_argument("--workdir", default="/tmp/gsx_cfg5")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "config5.json"))
     a = ap.parse_args()
@@ -110,7 +111,8 @@ def main():
                 break
             o.write(line)
     gpu_sam = os.path.join(a.workdir, "gpu.sam")
-    env5 = {"GSX_FILE_BATCH": "50000"}           # per device: ~300 hits per guide at m = 4 with two PAMs
+    env5 = {"GSX_FILE_BATCH": str(a.file_batch)} if a.file_batch else {}          # per device: ~300 hits per guide at m = 4 with two PAMs
+    res["file_batch_per_device"] = a.file_batch or 200000
     r_head = run_cli(common + ["-f", head_csv, "-o", gpu_sam, "-a", "NAG"], env=env5)
     want = open(cpu_sam, "rb").read()
     got = open(gpu_sam, "rb").read()

@@ -45,8 +45,8 @@ PY
     torchbench)    # torchbench <N> <steps> <warmup>: bench.py as the driver launches it on N GPUs
       timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $2 --steps $3 --warmup $4 > gpurun_out/${tag}_bench_n$2.json 2> gpurun_out/${tag}_bench_n$2.err
       tail -2 gpurun_out/${tag}_bench_n$2.err; cut -c1-900 gpurun_out/${tag}_bench_n$2.json; shift 4;;
-    cfg5)          # cfg5 <N gpus> <kmers Mb> <csv guides>: tools/config5_run.py
-      timeout 2400 python tools/config5_run.py --gpus $2 --kmers-mb $3 --csv-guides $4 --out gpurun_out/${tag}_config5_$2gpu.json > gpurun_out/${tag}_config5.log 2> gpurun_out/${tag}_config5.err
+    cfg5)          # cfg5 <N gpus> <kmers Mb> <csv guides>: tools/config5_run.py   (CFG5_FILE_BATCH: guides per device and batch, default 50000; 0 = library default)
+      timeout 2400 python tools/config5_run.py --gpus $2 --kmers-mb $3 --csv-guides $4 --file-batch ${CFG5_FILE_BATCH:-50000} --out gpurun_out/${tag}_config5_$2gpu_b${CFG5_FILE_BATCH:-50000}.json > gpurun_out/${tag}_config5.log 2> gpurun_out/${tag}_config5.err
       tail -4 gpurun_out/${tag}_config5.err | cut -c1-600; shift 4;;
     entrysmoke)    # __graft_entry__.smoke() as the driver runs it
       timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${tag}_smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/${tag}_smoke.log; tail -2 gpurun_out/${tag}_smoke.log; shift;;
