@@ -549,11 +549,20 @@ extern "C" int gsx_enumerate_file(const gsx_index* ix, const char* kmers_csv, co
     std::deque<Item> queue; bool done = false; int wrc = GSX_OK;
     std::deque<Text> wqueue; bool fdone = false;
     gsx_counters total{};
+    // GSX_FILE_TIMING=1: where the wall time of the job went (stderr): busy seconds of the formatter and the writer, and how long the
+    // submitting thread waited for a finished call and for room in the formatter's queue
+    const bool timing = getenv("GSX_FILE_TIMING") != nullptr;
+    double s_format = 0, s_free = 0, s_write = 0, s_wait_call = 0, s_wait_queue = 0, s_fwait_writer = 0;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto since = [](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t).count(); };
+    const auto t_job = now();
     std::thread writer([&] {
         for (;;) {
             Text tx;
             { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return !wqueue.empty() || fdone; }); if (wqueue.empty()) return; tx = std::move(wqueue.front()); }
+            const auto tw = now();
             if (wrc == GSX_OK && !out.append(tx.parts)) wrc = GSX_ERR_IO;
+            s_write += since(tw);
             for (std::string& sp : tx.parts) string_pool().put(std::move(sp));
             { std::lock_guard<std::mutex> lk(mu); wqueue.pop_front(); }                // (popped after the work: the formatter stays at most two batches ahead)
             cv.notify_all();
@@ -565,6 +574,7 @@ extern "C" int gsx_enumerate_file(const gsx_index* ix, const char* kmers_csv, co
             Item it;
             { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return !queue.empty() || done; }); if (queue.empty()) break; it = queue.front(); }
             Text tx;
+            const auto tf = now();
             if (wrc == GSX_OK) {
                 rows.resize(it.b1 - it.b0);
                 for (size_t i = it.b0; i < it.b1; i++) rows[i - it.b0] = {t.id[i], t.seq[i], t.pam[i], (int)t.positive[i]};
@@ -574,12 +584,17 @@ extern "C" int gsx_enumerate_file(const gsx_index* ix, const char* kmers_csv, co
                 total.ms_search += c.ms_search; total.ms_arrange += c.ms_arrange; total.ms_locate += c.ms_locate; total.ms_score += c.ms_score;
                 total.ms_total_device += c.ms_total_device; total.ms_h2d += c.ms_h2d; total.ms_d2h += c.ms_d2h; total.ms_sweep += c.ms_sweep; total.seeds += c.seeds; total.ms_prepare += c.ms_prepare; total.ms_wall += c.ms_wall; total.sectors += c.sectors; total.edited_guides += c.edited_guides;
             }
+            s_format += since(tf);
+            const auto tr = now();
             gsx_result_free(it.r);
+            s_free += since(tr);
             {
                 std::unique_lock<std::mutex> lk(mu);
                 queue.pop_front();                                                     // (popped after the work: the producer stays at most two batches ahead)
                 cv.notify_all();
+                const auto tq = now();
                 cv.wait(lk, [&] { return wqueue.size() < 2; });
+                s_fwait_writer += since(tq);
                 wqueue.push_back(std::move(tx));
             }
             cv.notify_all();
@@ -594,11 +609,15 @@ extern "C" int gsx_enumerate_file(const gsx_index* ix, const char* kmers_csv, co
     auto finish_one = [&]() {
         Slot& sl = slots[head]; head ^= 1; n_pending--;
         gsx_result* r = nullptr;
+        const auto tc = now();
         const int rc1 = gsx_enumerate_wait(sl.pd, &r); sl.pd = nullptr;
+        s_wait_call += since(tc);
         if (rc1) { if (rc == GSX_OK) { rc = rc1; rc_msg = gsx_last_error(); } return; }
         if (rc != GSX_OK) { gsx_result_free(r); return; }
         std::unique_lock<std::mutex> lk(mu);
+        const auto tq = now();
         cv.wait(lk, [&] { return queue.size() < 2; });
+        s_wait_queue += since(tq);
         queue.push_back({r, sl.b0, sl.b1});
         lk.unlock(); cv.notify_all();
     };
@@ -617,6 +636,11 @@ extern "C" int gsx_enumerate_file(const gsx_index* ix, const char* kmers_csv, co
     { std::lock_guard<std::mutex> lk(mu); done = true; }
     cv.notify_all();
     formatter.join(); writer.join();
+    if (timing)
+        fprintf(stderr, "gsx file job: %.3f s wall, %zu guides in batches of %zu; formatter busy %.3f s (+ %.3f s releasing results, %.3f s waiting for the writer), "
+                "writer busy %.3f s; submitter waited %.3f s for calls and %.3f s for the formatter; calls: device %.3f s, d2h %.3f s, h2d %.3f s, prepare %.3f s, call walls %.3f s\n",
+                since(t_job), n, batch_guides, s_format, s_free, s_fwait_writer, s_write, s_wait_call, s_wait_queue, total.ms_total_device / 1e3, total.ms_d2h / 1e3,
+                total.ms_h2d / 1e3, total.ms_prepare / 1e3, total.ms_wall / 1e3);
     if (!out.close_file() && wrc == GSX_OK) wrc = GSX_ERR_IO;
     if (rc) return gsx_set_error(rc, rc_msg);
     if (wrc) return gsx_set_error(wrc, std::string("cannot write ") + out_path);

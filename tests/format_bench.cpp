@@ -38,7 +38,7 @@ int main(int argc, char** argv) {
     gsx_params p; gsx_params_default(&p); p.mismatches = 4;
     {
         double sec; size_t len;
-        if (gsx_internal_format_rate(&ix, &res, rows.data(), G, &p, sam, getenv("SUCC") ? 0 : 1, 4, &sec, &len)) { fprintf(stderr, "format failed\n"); return 1; }
+        if (gsx_internal_format_rate(&ix, &res, rows.data(), G, &p, sam, getenv("SUCC") ? 0 : 1, getenv("ROUNDS") ? atoi(getenv("ROUNDS")) : 4, &sec, &len)) { fprintf(stderr, "format failed\n"); return 1; }
         printf("%s: %zu guides x %zu hits: %.3f s, %.1f MB, %.0f MB/s, %.2f M guides/s, %.1f ns/hit\n", sam ? "SAM" : "CSV", G, HPG, sec, len / 1e6, len / sec / 1e6, G / sec / 1e6, sec / nh * 1e9);
     }
     res.parts.clear();

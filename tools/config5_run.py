@@ -35,14 +35,16 @@ def log(*a):
 
 def run_cli(args, env=None):
     t0 = time.time()
-    r = subprocess.run([EXE] + args, capture_output=True, text=True, env={**os.environ, **(env or {})})
+    r = subprocess.run([EXE] + args, capture_output=True, text=True, env={**os.environ, "GSX_FILE_TIMING": "1", **(env or {})})
     dt = time.time() - t0
     if r.returncode:
         raise RuntimeError("guidescan %s failed: %s" % (" ".join(args), r.stderr[-800:]))
+    timing = [l for l in r.stderr.splitlines() if l.startswith("gsx file job:")]
     m = re.search(r"Processed (\d+) kmers in \d+ seconds. \(([\d.]+) s, ([\d.]+) kmers/s; device ([\d.]+) ms", r.stdout)
     o = re.search(r"files ([\d.]+) s, device layout ([\d.]+) s, replication ([\d.]+) s", r.stdout)
     return {"wall_s": dt, "guides": int(m.group(1)), "enumerate_s": float(m.group(2)), "guides_per_s": float(m.group(3)), "device_ms_sum": float(m.group(4)),
-            "index_open_s": {"files": float(o.group(1)), "device_layout": float(o.group(2)), "replication": float(o.group(3))} if o else None}
+            "index_open_s": {"files": float(o.group(1)), "device_layout": float(o.group(2)), "replication": float(o.group(3))} if o else None,
+            "file_job_timing": timing[-1] if timing else None}
 
 
 def main():
