@@ -15,6 +15,7 @@
 #include <stdexcept>
 #include <string>
 #include <thread>
+#include <type_traits>
 #include <sys/stat.h>
 #include <vector>
 
@@ -665,6 +666,7 @@ struct DeviceJob {
     size_t g0 = 0, g1 = 0;
     HostArrays out; gsx_counters ctr{};
     int status = GSX_OK; std::string err;
+    uint32_t want = kWantAll;            // per-hit arrays to bring to the host (gsx_host.h)
 };
 
 
@@ -1133,18 +1135,22 @@ static void run_device_job(DeviceJob* job) {
         CK(launch_specificity(S, s));
         CK(cudaEventRecord(ev[4], s));
         // ---- results to host ---------------------------------------------------------------------------------------------
-        H.abs_pos = H.alloc<int64_t>(nh); H.sa_row = H.alloc<uint32_t>(nh); H.chr = H.alloc<int32_t>(nh); H.pos1 = H.alloc<uint32_t>(nh);
-        H.strand = H.alloc<uint8_t>(nh); H.distance = H.alloc<uint8_t>(nh); H.rna = H.alloc<uint8_t>(nh); H.dna = H.alloc<uint8_t>(nh);
-        H.index_id = H.alloc<uint8_t>(nh); H.cfd = H.alloc<float>(nh); H.counted = H.alloc<uint8_t>(nh);
-        H.key_lo = H.alloc<uint64_t>(nh); H.key_hi = wide ? H.alloc<uint64_t>(nh) : nullptr; H.mlen = H.alloc<uint8_t>(nh);
         auto d2h = [&](void* dst, const void* src, size_t bytes) { if (bytes) CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s)); };
         d2h(H.dropped, d_dropped, n); d2h(H.hoff, d_hoff, (size_t)(n + 1) * 4); d2h(H.n_hits_of, d_nhits, (size_t)n * 4); d2h(H.specificity, S.specificity, (size_t)n * 4);
         d2h(H.perfect, S.perfect, n); d2h(H.cbd, d_cbd, (size_t)n * n_dist * 4);
-        d2h(H.abs_pos, L.abs_pos, (size_t)nh * 8); d2h(H.sa_row, d_hit_row, (size_t)nh * 4); d2h(H.chr, L.chr, (size_t)nh * 4);
-        d2h(H.pos1, L.pos1, (size_t)nh * 4); d2h(H.strand, L.strand, nh); d2h(H.distance, L.distance, nh); d2h(H.rna, L.rna, nh);
-        d2h(H.dna, L.dna, nh); d2h(H.index_id, L.index_id, nh); d2h(H.cfd, L.cfd, (size_t)nh * 4); d2h(H.counted, S.counted, nh);
-        d2h(H.key_lo, L.key_lo, (size_t)nh * 8); d2h(H.mlen, L.mlen, nh);
-        if (wide) d2h(H.key_hi, L.key_hi, (size_t)nh * 8);
+        // the per-hit arrays: those the caller reads (all of them for the public calls)
+        const uint32_t want = job->want;
+        auto hit_array = [&](uint32_t bit, auto*& dst, const auto* src) {
+            using T = std::remove_pointer_t<std::remove_reference_t<decltype(dst)>>;
+            if (!(want & bit)) { dst = nullptr; return; }
+            dst = H.alloc<T>(nh); d2h(dst, src, (size_t)nh * sizeof(T));
+        };
+        hit_array(kWantAbsPos, H.abs_pos, L.abs_pos); hit_array(kWantSaRow, H.sa_row, d_hit_row); hit_array(kWantChr, H.chr, L.chr);
+        hit_array(kWantPos1, H.pos1, L.pos1); hit_array(kWantStrand, H.strand, L.strand); hit_array(kWantDistance, H.distance, L.distance);
+        hit_array(kWantBulges, H.rna, L.rna); hit_array(kWantBulges, H.dna, L.dna); hit_array(kWantIndexId, H.index_id, L.index_id);
+        hit_array(kWantCfd, H.cfd, L.cfd); hit_array(kWantCounted, H.counted, S.counted);
+        hit_array(kWantMatchString, H.key_lo, L.key_lo); hit_array(kWantMatchString, H.mlen, L.mlen);
+        H.key_hi = nullptr; if (wide) hit_array(kWantMatchString, H.key_hi, L.key_hi);
         unsigned long long st[8]; d2h(st, d_stats, sizeof st);
         CK(cudaEventRecord(ev[5], s));
         CK(cudaStreamSynchronize(s)); CK(cudaStreamSynchronize(s2));
@@ -1174,7 +1180,7 @@ static void merge_parts(gsx_result* r) {
     gsx_result_view& v = r->view;
     auto cat = [&](auto& dst, auto member, bool per_hit, size_t mult) {
         dst.clear();
-        for (auto& p : r->parts) { size_t n = (per_hit ? p.n_hits : p.n_guides) * mult; auto* src = p.*member; if (n) dst.insert(dst.end(), src, src + n); }
+        for (auto& p : r->parts) { size_t n = (per_hit ? p.n_hits : p.n_guides) * mult; auto* src = p.*member; if (n && src) dst.insert(dst.end(), src, src + n); }
     };
     cat(r->dropped, &HostArrays::dropped, false, 1); cat(r->n_hits_of, &HostArrays::n_hits_of, false, 1);
     cat(r->specificity, &HostArrays::specificity, false, 1); cat(r->perfect, &HostArrays::perfect, false, 1);
@@ -1208,13 +1214,13 @@ void gsx_build_view(gsx_result* r) {
     }
 }
 
-static int enumerate_impl(const gsx_index* ix, const gsx_guide* guides, size_t n_guides, const gsx_params* p, gsx_result** out);
+static int enumerate_impl(const gsx_index* ix, const gsx_guide* guides, size_t n_guides, const gsx_params* p, gsx_result** out, uint32_t want);
 extern "C" int gsx_enumerate(const gsx_index* ix, const gsx_guide* guides, size_t n_guides, const gsx_params* p, gsx_result** out) {
     if (!ix || !p || !out || (!guides && n_guides)) return fail(GSX_ERR_ARG, "null argument");
     *out = nullptr;
-    return guarded([&] { return enumerate_impl(ix, guides, n_guides, p, out); });
+    return guarded([&] { return enumerate_impl(ix, guides, n_guides, p, out, kWantAll); });
 }
-static int enumerate_impl(const gsx_index* ix, const gsx_guide* guides, size_t n_guides, const gsx_params* p, gsx_result** out) {
+static int enumerate_impl(const gsx_index* ix, const gsx_guide* guides, size_t n_guides, const gsx_params* p, gsx_result** out, uint32_t want) {
     if (ix->dev.empty()) return fail(GSX_ERR_NO_DEVICE, "index is not resident on any device");
     if (n_guides >= (1ull << 30)) return fail(GSX_ERR_ARG, "too many guides in one call");
     const auto t_call = std::chrono::steady_clock::now();
@@ -1225,7 +1231,7 @@ static int enumerate_impl(const gsx_index* ix, const gsx_guide* guides, size_t n
     // guides are independent: contiguous shards per device, no data-path collective
     std::vector<DeviceJob> jobs(nd);
     for (size_t d = 0; d < nd; d++) {
-        jobs[d].ix = ix; jobs[d].slot = (int)d; jobs[d].prep = &prep; jobs[d].p = p;
+        jobs[d].ix = ix; jobs[d].slot = (int)d; jobs[d].prep = &prep; jobs[d].p = p; jobs[d].want = want;
         jobs[d].g0 = n_guides * d / nd; jobs[d].g1 = n_guides * (d + 1) / nd;
     }
     if (nd == 1) run_device_job(&jobs[0]);
@@ -1256,13 +1262,18 @@ struct gsx_pending {
     std::thread th; gsx_result* result = nullptr; int status = GSX_OK; std::string err;
 };
 extern "C" int gsx_enumerate_start(const gsx_index* ix, const gsx_guide* guides, size_t n_guides, const gsx_params* p, gsx_pending** out) {
+    return gsx_internal_enumerate_start_want(ix, guides, n_guides, p, kWantAll, out);
+}
+// (not in include/gsx.h: the whole-file driver's form of the call, bringing only the per-hit arrays it formats from -- gsx_host.h)
+extern "C" int gsx_internal_enumerate_start_want(const gsx_index* ix, const gsx_guide* guides, size_t n_guides, const gsx_params* p, uint32_t want, gsx_pending** out) {
     if (!ix || !p || !out || (!guides && n_guides)) return fail(GSX_ERR_ARG, "null argument");
     *out = nullptr;
     return guarded([&] {
         gsx_pending* pd = new gsx_pending();
         try {
             pd->th = std::thread([=] {
-                pd->status = gsx_enumerate(ix, guides, n_guides, p, &pd->result);
+                pd->result = nullptr;
+                pd->status = guarded([&] { return enumerate_impl(ix, guides, n_guides, p, &pd->result, want); });
                 if (pd->status) pd->err = g_err;                            // (the message lives in the worker thread's slot)
             });
         } catch (...) { delete pd; throw; }

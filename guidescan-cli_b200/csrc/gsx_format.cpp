@@ -603,6 +603,10 @@ extern "C" int gsx_enumerate_file(const gsx_index* ix, const char* kmers_csv, co
         cv.notify_all();
     });
     int rc = GSX_OK; std::string rc_msg;
+    // only the per-hit arrays the formatter reads come back from the devices (format_sam_guide: 18 of the 39 bytes per hit,
+    // format_csv_guide: 22, 12 in succinct mode)
+    const uint32_t want = format_sam ? (kWantDistance | kWantCounted | kWantAbsPos | kWantChr | kWantPos1)
+                                     : (kWantDistance | kWantCounted | kWantChr | kWantPos1 | kWantStrand | (complete ? kWantBulges | kWantMatchString : 0u));
     // two batches in flight: the guides of batch k+1 are packed (and its small uploads issued) while batch k runs on the device
     struct Slot { std::vector<gsx_guide> g; gsx_pending* pd = nullptr; size_t b0 = 0, b1 = 0; };
     Slot slots[2]; int n_pending = 0, head = 0;
@@ -628,7 +632,7 @@ extern "C" int gsx_enumerate_file(const gsx_index* ix, const char* kmers_csv, co
         sl.b0 = b0; sl.b1 = std::min(n, b0 + batch_guides);
         sl.g.resize(sl.b1 - sl.b0);
         for (size_t i = sl.b0; i < sl.b1; i++) sl.g[i - sl.b0] = {t.seq[i], t.pam[i]};
-        const int rc1 = gsx_enumerate_start(ix, sl.g.data(), sl.g.size(), &pp, &sl.pd);
+        const int rc1 = gsx_internal_enumerate_start_want(ix, sl.g.data(), sl.g.size(), &pp, want, &sl.pd);
         if (rc1) { rc = rc1; rc_msg = gsx_last_error(); break; }
         n_pending++;
     }

@@ -162,6 +162,13 @@ struct gsx_result {
 };
 
 
+// per-hit result arrays a caller inside the library wants on the host (gsx_internal_enumerate_start_want): the whole-file driver
+// formats SAM from 18 of the 39 bytes per hit and CSV from 22, and at hundreds of hits per guide the result copy is a third of a
+// call.  The public calls copy everything (kWantAll); an array that was not wanted is a null pointer in HostArrays.
+enum : uint32_t { kWantAbsPos = 1u, kWantSaRow = 2u, kWantChr = 4u, kWantPos1 = 8u, kWantStrand = 16u, kWantDistance = 32u, kWantBulges = 64u,
+                  kWantIndexId = 128u, kWantCfd = 256u, kWantCounted = 512u, kWantMatchString = 1024u, kWantAll = 0xFFFFFFFFu };
+extern "C" int gsx_internal_enumerate_start_want(const gsx_index* ix, const gsx_guide* guides, size_t n_guides, const gsx_params* p, uint32_t want, gsx_pending** out);
+
 // internal entry points shared with the host-side unit-test harness (tests/host_core_check.cpp)
 int gsx_prepare_guides(const gsx_guide* guides, size_t n, const gsx_params* p, gsx::Prepared& out);
 void gsx_build_view(gsx_result* r);
