@@ -429,6 +429,7 @@ namespace {
 struct Pool {
     std::mutex mu;
     std::multimap<size_t, void*> free_;
+    std::map<void*, size_t> capacity;        // pinned host blocks: what each was allocated with (a block may serve a smaller request)
 };
 Pool& pool_of(int device) { static Pool pools[65]; return pools[device + 1]; }
 size_t bucket(size_t bytes) { size_t b = 512; while (b < bytes) b <<= 1; return b; }
@@ -439,8 +440,10 @@ void* gsx::pool_get(int device, size_t bytes) {
     Pool& P = pool_of(device);
     {
         std::lock_guard<std::mutex> g(P.mu);
-        auto it = P.free_.find(b);
-        if (it != P.free_.end()) { void* p = it->second; P.free_.erase(it); return p; }
+        // pinned host memory costs half a second per GB to allocate (profiles/r02z_d2h_probe.json) and the result arrays of
+        // successive batches straddle bucket boundaries: a free block of up to four times the bucket serves the request
+        auto it = device < 0 ? P.free_.lower_bound(b) : P.free_.find(b);
+        if (it != P.free_.end() && (device >= 0 || it->first <= 4 * b)) { void* p = it->second; P.free_.erase(it); return p; }
     }
     void* p = nullptr;
     cudaError_t e = device < 0 ? cudaHostAlloc(&p, b, cudaHostAllocDefault) : cudaMalloc(&p, b);
@@ -449,18 +452,21 @@ void* gsx::pool_get(int device, size_t bytes) {
         e = device < 0 ? cudaHostAlloc(&p, b, cudaHostAllocDefault) : cudaMalloc(&p, b);
         if (e != cudaSuccess) { cudaGetLastError(); return nullptr; }
     }
+    if (device < 0) { std::lock_guard<std::mutex> g(P.mu); P.capacity[p] = b; }
     return p;
 }
 void gsx::pool_put(int device, void* p, size_t bytes) {
     if (!p) return;
     Pool& P = pool_of(device);
     std::lock_guard<std::mutex> g(P.mu);
-    P.free_.emplace(bucket(bytes), p);
+    size_t key = bucket(bytes);
+    if (device < 0) { auto c = P.capacity.find(p); if (c != P.capacity.end()) key = c->second; }      // (its real size, not the request's)
+    P.free_.emplace(key, p);
 }
 void gsx::pool_trim(int device) {
     Pool& P = pool_of(device);
     std::lock_guard<std::mutex> g(P.mu);
-    for (auto& kv : P.free_) { if (device < 0) cudaFreeHost(kv.second); else cudaFree(kv.second); }
+    for (auto& kv : P.free_) { if (device < 0) { cudaFreeHost(kv.second); P.capacity.erase(kv.second); } else cudaFree(kv.second); }
     P.free_.clear();
 }
 
